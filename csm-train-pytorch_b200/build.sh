@@ -1,0 +1,27 @@
+#!/usr/bin/env bash
+# Builds libcsm_b200.so in-tree for sm_100a (cross-compiles without a GPU).
+set -euo pipefail
+HERE="$(cd "$(dirname "${BASH_SOURCE[0]}")" && pwd)"
+NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
+OUT="$HERE/libcsm_b200.so"
+SRCS=("$HERE"/csrc/*.cu)
+mkdir -p "$HERE/build"
+OBJS=()
+pids=()
+for s in "${SRCS[@]}"; do
+  o="$HERE/build/$(basename "${s%.cu}").o"
+  OBJS+=("$o")
+  if [[ ! -f "$o" || "$s" -nt "$o" || "$HERE/csrc/common.cuh" -nt "$o" || "$HERE/csrc/tc_common.cuh" -nt "$o" || "$HERE/../include/csm_b200.h" -nt "$o" ]]; then
+    "$NVCC" -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 \
+      -Xcompiler -fPIC -Xptxas -v -c "$s" -o "$o" > "$HERE/build/$(basename "${s%.cu}").log" 2>&1 &
+    pids+=($!)
+  fi
+done
+fail=0
+for p in "${pids[@]:-}"; do [[ -z "$p" ]] || wait "$p" || fail=1; done
+if [[ $fail -ne 0 ]]; then
+  for l in "$HERE"/build/*.log; do grep -E "error|Error|fatal" "$l" >/dev/null && { echo "== $l"; grep -v "^ptxas info" "$l" | head -40; }; done
+  exit 1
+fi
+"$NVCC" -gencode arch=compute_100a,code=sm_100a -shared -o "$OUT" "${OBJS[@]}" -lcudart
+echo "built $OUT"

@@ -1,0 +1,266 @@
+"""Tensor-level wrappers over the C ABI (no autograd here; see csm/autograd.py).
+
+PyTorch is plumbing only: it owns device memory and the stream; every arithmetic op on the training
+path is a kernel in libcsm_b200.so.  All tensors must be CUDA, contiguous in the documented layout and
+bf16 unless stated otherwise.
+"""
+from __future__ import annotations
+
+import math
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+
+BF16 = torch.bfloat16
+GEMM_AUTO, GEMM_SIMT, GEMM_TC = 0, 1, 2
+_backend_override = GEMM_AUTO
+
+
+def set_gemm_backend(b: int) -> None:
+    """Test hook: force the scalar (1) or tcgen05 (2) GEMM back-end; 0 = automatic."""
+    global _backend_override
+    _backend_override = b
+
+
+def _p(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _st():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _chk_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("csm ops need CUDA tensors: libcsm_b200 has no CPU fallback")
+
+
+# ----------------------------------------------------------------------------- embeddings
+def embed_gather_sum(tokens, mask, audio_emb, text_emb, *, debug: bool = False):
+    """tokens int64 [B,S,C+1], mask bool [B,S,C+1] -> h bf16 [B,S,D] (+ (idx, eff_mask, status) when debug)."""
+    _chk_cuda(tokens, mask, audio_emb, text_emb)
+    B, S, W = tokens.shape
+    C = W - 1
+    D = audio_emb.shape[1]
+    V = audio_emb.shape[0] // C
+    tokens = tokens.contiguous()
+    mask_u8 = mask.contiguous().view(torch.uint8) if mask.dtype == torch.bool else mask.to(torch.uint8).contiguous()
+    h = torch.empty(B, S, D, dtype=BF16, device=tokens.device)
+    idx = msk = status = None
+    if debug:
+        idx = torch.empty_like(tokens)
+        msk = torch.empty(B, S, W, dtype=torch.uint8, device=tokens.device)
+        status = torch.zeros(1, dtype=torch.int32, device=tokens.device)
+    lib = _lib.load()
+    _lib.check(lib.csm_embed_gather_sum_fwd(_p(tokens), _p(mask_u8), _p(audio_emb), _p(text_emb), _p(h), _p(idx),
+                                            _p(msk), _p(status), B * S, C, V, text_emb.shape[0], D, _st()),
+               "embed_gather_sum_fwd")
+    return (h, idx, msk, status) if debug else h
+
+
+def embed_gather_sum_bwd(tokens, mask, dh, d_audio: Optional[torch.Tensor], d_text: Optional[torch.Tensor],
+                         audio_vocab: int, text_vocab: int) -> None:
+    B, S, W = tokens.shape
+    mask_u8 = mask.contiguous().view(torch.uint8) if mask.dtype == torch.bool else mask.to(torch.uint8).contiguous()
+    lib = _lib.load()
+    _lib.check(lib.csm_embed_gather_sum_bwd(_p(tokens.contiguous()), _p(mask_u8), _p(dh.contiguous()), _p(d_audio),
+                                            _p(d_text), B * S, W - 1, audio_vocab, text_vocab, dh.shape[-1], _st()),
+               "embed_gather_sum_bwd")
+
+
+def decoder_input(h, audio_emb, targets, frame_idx, codebooks: int, audio_vocab: int):
+    """h bf16 [B,S,D], targets int64 [B,T,C], frame_idx int64 [Ns,2] -> x bf16 [Ns, C, D]."""
+    B, S, D = h.shape
+    Ns = frame_idx.shape[0]
+    x = torch.empty(Ns, codebooks, D, dtype=BF16, device=h.device)
+    lib = _lib.load()
+    _lib.check(lib.csm_decoder_input_fwd(_p(h), _p(audio_emb), _p(targets.contiguous()), _p(frame_idx.contiguous()),
+                                         _p(x), Ns, S, targets.shape[1], codebooks, audio_vocab, D, _st()),
+               "decoder_input_fwd")
+    return x
+
+
+def decoder_input_bwd(dx, targets, frame_idx, dh, d_audio, codebooks: int, audio_vocab: int) -> None:
+    """dh bf16 [B,S,D] (accumulated in place), d_audio nullable (accumulated in place)."""
+    B, S, D = dh.shape
+    lib = _lib.load()
+    _lib.check(lib.csm_decoder_input_bwd(_p(dx.contiguous()), _p(targets.contiguous()), _p(frame_idx.contiguous()),
+                                         _p(dh), _p(d_audio), frame_idx.shape[0], S, targets.shape[1], codebooks,
+                                         audio_vocab, D, _st()), "decoder_input_bwd")
+
+
+# ----------------------------------------------------------------------------- norm / rope / swiglu
+def rmsnorm(x, scale, eps: float) -> Tuple[torch.Tensor, torch.Tensor]:
+    D = x.shape[-1]
+    rows = x.numel() // D
+    y = torch.empty_like(x)
+    rstd = torch.empty(rows, dtype=torch.float32, device=x.device)
+    lib = _lib.load()
+    _lib.check(lib.csm_rmsnorm_fwd(_p(x), _p(scale), _p(y), _p(rstd), rows, D, eps, _st()), "rmsnorm_fwd")
+    return y, rstd
+
+
+def rmsnorm_bwd(dy, x, scale, rstd, dres: Optional[torch.Tensor], dscale_f32: Optional[torch.Tensor]):
+    D = x.shape[-1]
+    rows = x.numel() // D
+    dx = torch.empty_like(x)
+    lib = _lib.load()
+    _lib.check(lib.csm_rmsnorm_bwd(_p(dy), _p(x), _p(scale), _p(rstd), _p(dres), _p(dx), _p(dscale_f32), rows, D,
+                                   _st()), "rmsnorm_bwd")
+    return dx
+
+
+def rope_(x2d, cache, seq_len: int, heads: int, head_dim: int, inverse: bool = False, ld: Optional[int] = None):
+    """In place on x2d [rows, >= heads*head_dim] (row stride ld)."""
+    rows = x2d.shape[0]
+    ld = x2d.stride(0) if ld is None else ld
+    lib = _lib.load()
+    _lib.check(lib.csm_rope(_p(x2d), _p(cache), rows, seq_len, heads, head_dim, ld, 1 if inverse else 0, _st()),
+               "rope")
+    return x2d
+
+
+def swiglu(gate, up):
+    rows, cols = gate.shape
+    out = torch.empty(rows, cols, dtype=BF16, device=gate.device)
+    lib = _lib.load()
+    _lib.check(lib.csm_swiglu_fwd(_p(gate), _p(up), _p(out), rows, cols, gate.stride(0), up.stride(0), cols, _st()),
+               "swiglu_fwd")
+    return out
+
+
+def swiglu_bwd(dout, gate, up, dgate=None, dup=None):
+    rows, cols = gate.shape
+    dgate = torch.empty(rows, cols, dtype=BF16, device=gate.device) if dgate is None else dgate
+    dup = torch.empty(rows, cols, dtype=BF16, device=gate.device) if dup is None else dup
+    lib = _lib.load()
+    _lib.check(lib.csm_swiglu_bwd(_p(dout), _p(gate), _p(up), _p(dgate), _p(dup), rows, cols, dout.stride(0),
+                                  gate.stride(0), up.stride(0), dgate.stride(0), dup.stride(0), _st()), "swiglu_bwd")
+    return dgate, dup
+
+
+# ----------------------------------------------------------------------------- GEMM
+def gemm(a, b, *, trans_a: bool = False, trans_b: bool = False, out: Optional[torch.Tensor] = None,
+         residual: Optional[torch.Tensor] = None, accumulate: bool = False, alpha: float = 1.0,
+         a2: Optional[torch.Tensor] = None, b2: Optional[torch.Tensor] = None, out_dtype=BF16,
+         backend: Optional[int] = None):
+    """out[M,N] (=|+=) alpha*(op(a) @ op(b)^T-style product [+ a2 @ b2]) [+ residual].
+
+    a: [M,K] (or [K,M] when trans_a); b: [N,K] (nn.Linear layout; or [K,N] when trans_b); 2-D, unit inner stride.
+    """
+    _chk_cuda(a, b)
+    assert a.dim() == 2 and b.dim() == 2 and a.stride(1) == 1 and b.stride(1) == 1
+    M, K = (a.shape[1], a.shape[0]) if trans_a else a.shape
+    N, Kb = (b.shape[1], b.shape[0]) if trans_b else b.shape
+    if K != Kb:
+        raise RuntimeError(f"gemm: inner dimensions differ ({K} vs {Kb})")
+    if out is None:
+        out = torch.empty(M, N, dtype=out_dtype, device=a.device)
+    assert out.shape == (M, N) and out.stride(1) == 1
+    K2 = 0
+    if a2 is not None:
+        K2 = a2.shape[0] if trans_a else a2.shape[1]
+        assert a2.stride(1) == 1 and b2.stride(1) == 1
+    lib = _lib.load()
+    be = _backend_override if backend is None else backend
+    _lib.check(lib.csm_gemm_bf16(_p(a), _p(b), _p(out), _p(residual), M, N, K, a.stride(0), b.stride(0),
+                                 out.stride(0), residual.stride(0) if residual is not None else 0,
+                                 1 if trans_a else 0, 1 if trans_b else 0, 1 if out.dtype == torch.float32 else 0,
+                                 1 if accumulate else 0, alpha, _p(a2), _p(b2), K2,
+                                 a2.stride(0) if a2 is not None else 0, b2.stride(0) if b2 is not None else 0,
+                                 be, _st()), "gemm_bf16")
+    return out
+
+
+# ----------------------------------------------------------------------------- attention
+def attention_fwd(q, k, v, batch: int, seq: int, heads: int, kv_heads: int, head_dim: int):
+    """q [B*S, H*hd], k/v [B*S, KV*hd] (row strides free) -> (o [B*S, H*hd], lse fp32 [B,H,S])."""
+    o = torch.empty(batch * seq, heads * head_dim, dtype=BF16, device=q.device)
+    lse = torch.empty(batch, heads, seq, dtype=torch.float32, device=q.device)
+    lib = _lib.load()
+    _lib.check(lib.csm_attn_causal_gqa_fwd(_p(q), _p(k), _p(v), _p(o), _p(lse), batch, seq, heads, kv_heads,
+                                           head_dim, q.stride(0), k.stride(0), v.stride(0), o.stride(0),
+                                           1.0 / math.sqrt(head_dim), _st()), "attn_fwd")
+    return o, lse
+
+
+def attention_bwd(q, k, v, o, lse, dout, batch, seq, heads, kv_heads, head_dim, dq=None, dk=None, dv=None):
+    dev = q.device
+    dq = torch.empty(batch * seq, heads * head_dim, dtype=BF16, device=dev) if dq is None else dq
+    dk = torch.empty(batch * seq, kv_heads * head_dim, dtype=BF16, device=dev) if dk is None else dk
+    dv = torch.empty(batch * seq, kv_heads * head_dim, dtype=BF16, device=dev) if dv is None else dv
+    lib = _lib.load()
+    nbytes = lib.csm_attn_bwd_workspace_bytes(batch, seq, heads, kv_heads, head_dim)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    _lib.check(lib.csm_attn_causal_gqa_bwd(_p(q), _p(k), _p(v), _p(o), _p(lse), _p(dout), _p(dq), _p(dk), _p(dv),
+                                           batch, seq, heads, kv_heads, head_dim, q.stride(0), k.stride(0),
+                                           v.stride(0), o.stride(0), dq.stride(0), dk.stride(0), dv.stride(0),
+                                           1.0 / math.sqrt(head_dim), _p(ws), nbytes, _st()), "attn_bwd")
+    return dq, dk, dv
+
+
+# ----------------------------------------------------------------------------- fused linear + cross-entropy
+def _ce_geometry(h, w, trans_w: bool, groups: int):
+    if groups == 1:
+        M, K = h.shape
+        V = w.shape[1] if trans_w else w.shape[0]
+        return M, V, K, h.stride(0), 0, w.stride(0), 0
+    # grouped: h [M, G(+off), K] view with strides, w [G, V, K] or [G, K, V]
+    M, G, K = h.shape
+    assert G == groups and h.stride(2) == 1
+    V = w.shape[2] if trans_w else w.shape[1]
+    return M, V, K, h.stride(0), h.stride(1), w.stride(1), w.stride(0)
+
+
+def linear_ce_fwd(h, w, targets, *, trans_w: bool = False, groups: int = 1, tgt_row_stride: int = 1,
+                  tgt_group_stride: int = 0, backend: Optional[int] = None):
+    """Returns (loss_rows fp32 [groups, M], lse fp32 [groups, M]).  `targets` is an int64 tensor whose element
+    for (group g, row m) sits at offset m*tgt_row_stride + g*tgt_group_stride from its data pointer."""
+    M, V, K, ldh, hgs, ldw, wgs = _ce_geometry(h, w, trans_w, groups)
+    lib = _lib.load()
+    nbytes = lib.csm_linear_ce_workspace_bytes(M, V, K, groups)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=h.device)
+    loss = torch.empty(groups, M, dtype=torch.float32, device=h.device)
+    lse = torch.empty(groups, M, dtype=torch.float32, device=h.device)
+    be = _backend_override if backend is None else backend
+    _lib.check(lib.csm_linear_ce_fwd(_p(h), _p(w), _p(targets), _p(loss), _p(lse), M, V, K, groups, ldh, hgs, ldw,
+                                     wgs, 1 if trans_w else 0, tgt_row_stride, tgt_group_stride, _p(ws), nbytes, be,
+                                     _st()), "linear_ce_fwd")
+    return loss, lse
+
+
+def linear_ce_bwd(h, w, targets, lse, grad_scale: float, *, dh: torch.Tensor, dw: Optional[torch.Tensor] = None,
+                  dw_accumulate: bool = False, trans_w: bool = False, groups: int = 1, tgt_row_stride: int = 1,
+                  tgt_group_stride: int = 0, backend: Optional[int] = None):
+    M, V, K, ldh, hgs, ldw, wgs = _ce_geometry(h, w, trans_w, groups)
+    lib = _lib.load()
+    nbytes = lib.csm_linear_ce_workspace_bytes(M, V, K, groups)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=h.device)
+    if groups == 1:
+        lddh, dhgs = dh.stride(0), 0
+    else:
+        lddh, dhgs = dh.stride(0), dh.stride(1)
+    be = _backend_override if backend is None else backend
+    _lib.check(lib.csm_linear_ce_bwd(_p(h), _p(w), _p(targets), _p(lse), grad_scale, _p(dh), _p(dw),
+                                     1 if dw_accumulate else 0, M, V, K, groups, ldh, hgs, ldw, wgs,
+                                     1 if trans_w else 0, tgt_row_stride, tgt_group_stride, lddh, dhgs, _p(ws),
+                                     nbytes, be, _st()), "linear_ce_bwd")
+    return dh, dw
+
+
+# ----------------------------------------------------------------------------- helpers
+def f32_to_bf16_(src_f32, dst_bf16, scale: float = 1.0, accumulate: bool = False):
+    lib = _lib.load()
+    _lib.check(lib.csm_f32_to_bf16(_p(src_f32), _p(dst_bf16), src_f32.numel(), scale, 1 if accumulate else 0, _st()),
+               "f32_to_bf16")
+    return dst_bf16
+
+
+def add_bf16(a, b, out=None):
+    out = torch.empty_like(a) if out is None else out
+    lib = _lib.load()
+    _lib.check(lib.csm_add_bf16(_p(a), _p(b), _p(out), a.numel(), _st()), "add_bf16")
+    return out

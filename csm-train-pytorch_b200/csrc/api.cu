@@ -1,0 +1,141 @@
+// extern "C" surface that is not tied to one kernel file: error state, device probe, GEMM/attention dispatch.
+#include <stdarg.h>
+#include <string.h>
+
+#include "common.cuh"
+
+namespace csm {
+
+static thread_local char g_err[512] = "";
+std::atomic<int64_t> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int num_sms() {
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0, v = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess &&
+        cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && v > 0)
+      sms = v;
+    else
+      sms = 148;
+  }
+  return sms;
+}
+
+int gemm_simt_launch(const void*, const void*, void*, const void*, int64_t, int64_t, int64_t, int64_t, int64_t,
+                     int64_t, int64_t, int, int, int, int, float, const void*, const void*, int64_t, int64_t,
+                     int64_t, cudaStream_t);
+bool gemm_tc_supported(const void* A, const void* B, const void* C, const void* R, int64_t M, int64_t N, int64_t K,
+                       int64_t lda, int64_t ldb, int64_t ldc, int64_t ldr, int transA, int transB, int c_dtype,
+                       const void* A2, const void* B2, int64_t K2, int64_t lda2, int64_t ldb2);
+int gemm_tc_launch(const void*, const void*, void*, const void*, int64_t, int64_t, int64_t, int64_t, int64_t,
+                   int64_t, int64_t, int, int, int, int, float, const void*, const void*, int64_t, int64_t, int64_t,
+                   cudaStream_t);
+int attn_fwd_simt_launch(const void*, const void*, const void*, void*, float*, int, int, int, int, int, int64_t,
+                         int64_t, int64_t, int64_t, float, cudaStream_t);
+int attn_bwd_simt_launch(const void*, const void*, const void*, const void*, const float*, const void*, void*,
+                         void*, void*, float*, int, int, int, int, int, int64_t, int64_t, int64_t, int64_t, int64_t,
+                         int64_t, int64_t, float, cudaStream_t);
+bool attn_mma_supported(int hd, int64_t ldq, int64_t ldk, int64_t ldv, int64_t ldo);
+int attn_fwd_mma_launch(const void*, const void*, const void*, void*, float*, int, int, int, int, int, int64_t,
+                        int64_t, int64_t, int64_t, float, cudaStream_t);
+int attn_bwd_mma_launch(const void*, const void*, const void*, const void*, const float*, const void*, void*,
+                        void*, void*, float*, int, int, int, int, int, int64_t, int64_t, int64_t, int64_t, int64_t,
+                        int64_t, int64_t, float, cudaStream_t);
+
+int gemm_dispatch(const void* A, const void* B, void* C, const void* R, int64_t M, int64_t N, int64_t K,
+                  int64_t lda, int64_t ldb, int64_t ldc, int64_t ldr, int transA, int transB, int c_dtype,
+                  int accumulate, float alpha, const void* A2, const void* B2, int64_t K2, int64_t lda2,
+                  int64_t ldb2, int backend, cudaStream_t stream) {
+  CSM_REQUIRE(M >= 0 && N >= 0 && K >= 0, CSM_ERR_SHAPE, "gemm: negative dimension");
+  CSM_REQUIRE(c_dtype == CSM_DT_BF16 || c_dtype == CSM_DT_F32, CSM_ERR_SHAPE, "gemm: bad c_dtype %d", c_dtype);
+  CSM_REQUIRE((A2 == nullptr) == (B2 == nullptr), CSM_ERR_SHAPE, "gemm: A2 and B2 must be given together");
+  if (M == 0 || N == 0) return CSM_OK;
+  const bool tc_ok = gemm_tc_supported(A, B, C, R, M, N, K, lda, ldb, ldc, ldr, transA, transB, c_dtype, A2, B2,
+                                       A2 ? K2 : 0, lda2, ldb2);
+  if (backend == CSM_GEMM_TCGEN05) {
+    CSM_REQUIRE(tc_ok, CSM_ERR_ALIGN,
+                "gemm: tcgen05 path needs 16-byte aligned pointers, leading dimensions that are multiples of 8 "
+                "and K >= 16 (got M=%lld N=%lld K=%lld lda=%lld ldb=%lld ldc=%lld)",
+                (long long)M, (long long)N, (long long)K, (long long)lda, (long long)ldb, (long long)ldc);
+  }
+  if (tc_ok && backend != CSM_GEMM_SIMT)
+    return gemm_tc_launch(A, B, C, R, M, N, K, lda, ldb, ldc, ldr, transA, transB, c_dtype, accumulate, alpha, A2,
+                          B2, A2 ? K2 : 0, lda2, ldb2, stream);
+  return gemm_simt_launch(A, B, C, R, M, N, K, lda, ldb, ldc, ldr, transA, transB, c_dtype, accumulate, alpha, A2,
+                          B2, K2, lda2, ldb2, stream);
+}
+
+}  // namespace csm
+
+using namespace csm;
+
+extern "C" int csm_abi_version(void) { return CSM_ABI_VERSION; }
+extern "C" const char* csm_last_error(void) { return g_err; }
+extern "C" int64_t csm_launch_count(void) { return g_launches.load(); }
+
+extern "C" int csm_device_supported(void) {
+  int dev = 0, major = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); return 0; }
+  if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return major == 10 ? 1 : 0;
+}
+
+extern "C" int csm_gemm_bf16(const void* A, const void* B, void* C, const void* R, int64_t M, int64_t N, int64_t K,
+                             int64_t lda, int64_t ldb, int64_t ldc, int64_t ldr, int32_t transA, int32_t transB,
+                             int32_t c_dtype, int32_t accumulate, float alpha, const void* A2, const void* B2,
+                             int64_t K2, int64_t lda2, int64_t ldb2, int32_t backend, csm_stream_t stream) {
+  return gemm_dispatch(A, B, C, R, M, N, K, lda, ldb, ldc, ldr, transA, transB, c_dtype, accumulate, alpha, A2, B2,
+                       K2, lda2, ldb2, backend, as_stream(stream));
+}
+
+extern "C" int csm_attn_causal_gqa_fwd(const void* q, const void* k, const void* v, void* o, float* lse,
+                                       int32_t batch, int32_t seq, int32_t heads, int32_t kv_heads,
+                                       int32_t head_dim, int64_t ldq, int64_t ldk, int64_t ldv, int64_t ldo,
+                                       float scale, csm_stream_t stream) {
+  CSM_REQUIRE(batch >= 0 && seq > 0 && heads > 0 && kv_heads > 0 && heads % kv_heads == 0 && head_dim > 0 &&
+                  head_dim <= 128,
+              CSM_ERR_SHAPE, "attn_fwd: bad shape B=%d S=%d H=%d KV=%d hd=%d", batch, seq, heads, kv_heads, head_dim);
+  if (batch == 0) return CSM_OK;
+  if (attn_mma_supported(head_dim, ldq, ldk, ldv, ldo))
+    return attn_fwd_mma_launch(q, k, v, o, lse, batch, seq, heads, kv_heads, head_dim, ldq, ldk, ldv, ldo, scale,
+                               as_stream(stream));
+  return attn_fwd_simt_launch(q, k, v, o, lse, batch, seq, heads, kv_heads, head_dim, ldq, ldk, ldv, ldo, scale,
+                              as_stream(stream));
+}
+
+extern "C" size_t csm_attn_bwd_workspace_bytes(int32_t batch, int32_t seq, int32_t heads, int32_t kv_heads,
+                                               int32_t head_dim) {
+  (void)kv_heads; (void)head_dim;
+  return (size_t)batch * heads * seq * sizeof(float) + 256;
+}
+
+extern "C" int csm_attn_causal_gqa_bwd(const void* q, const void* k, const void* v, const void* o,
+                                       const float* lse, const void* dout, void* dq, void* dk, void* dv,
+                                       int32_t batch, int32_t seq, int32_t heads, int32_t kv_heads,
+                                       int32_t head_dim, int64_t ldq, int64_t ldk, int64_t ldv, int64_t ldo,
+                                       int64_t lddq, int64_t lddk, int64_t lddv, float scale, void* workspace,
+                                       size_t workspace_bytes, csm_stream_t stream) {
+  CSM_REQUIRE(batch >= 0 && seq > 0 && heads > 0 && kv_heads > 0 && heads % kv_heads == 0 && head_dim > 0 &&
+                  head_dim <= 128,
+              CSM_ERR_SHAPE, "attn_bwd: bad shape");
+  if (batch == 0) return CSM_OK;
+  CSM_REQUIRE(workspace && workspace_bytes >= csm_attn_bwd_workspace_bytes(batch, seq, heads, kv_heads, head_dim),
+              CSM_ERR_SHAPE, "attn_bwd: workspace too small");
+  float* delta = reinterpret_cast<float*>(workspace);
+  if (attn_mma_supported(head_dim, ldq, ldk, ldv, ldo))
+    return attn_bwd_mma_launch(q, k, v, o, lse, dout, dq, dk, dv, delta, batch, seq, heads, kv_heads, head_dim, ldq,
+                               ldk, ldv, ldo, lddq, lddk, lddv, scale, as_stream(stream));
+  return attn_bwd_simt_launch(q, k, v, o, lse, dout, dq, dk, dv, delta, batch, seq, heads, kv_heads, head_dim, ldq,
+                              ldk, ldv, ldo, lddq, lddk, lddv, scale, as_stream(stream));
+}

@@ -1,0 +1,321 @@
+// RMSNorm fwd/bwd, interleaved-pair RoPE, SwiGLU fwd/bwd and small conversion helpers.
+// All HBM-bound: 16-byte vector accesses, fp32 math, one rounding per bf16 the reference rounds
+// (oracle/torchtune_shim.py restates torchtune 0.4.0's RMSNorm / Llama3ScaledRoPE / FeedForward).
+#include "common.cuh"
+
+namespace csm {
+
+constexpr int kNormThreads = 256;
+constexpr int kNormMaxChunks = 4;  // dim <= 256*8*4 = 8192
+
+__device__ __forceinline__ float block_sum(float v, float* smem) {
+  v = warp_sum(v);
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  __syncthreads();
+  if (lane == 0) smem[w] = v;
+  __syncthreads();
+  float t = (lane < nw) ? smem[lane] : 0.f;
+  return warp_sum(t);
+}
+
+__device__ __forceinline__ void unpack8(const uint4& v, float* f) {
+  f[0] = bf16_lo(v.x); f[1] = bf16_hi(v.x); f[2] = bf16_lo(v.y); f[3] = bf16_hi(v.y);
+  f[4] = bf16_lo(v.z); f[5] = bf16_hi(v.z); f[6] = bf16_lo(v.w); f[7] = bf16_hi(v.w);
+}
+__device__ __forceinline__ uint4 pack8(const float* f) {
+  uint4 o;
+  o.x = pack_bf16(f[0], f[1]); o.y = pack_bf16(f[2], f[3]);
+  o.z = pack_bf16(f[4], f[5]); o.w = pack_bf16(f[6], f[7]);
+  return o;
+}
+__device__ __forceinline__ float round_bf16(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
+
+__global__ void __launch_bounds__(kNormThreads)
+rmsnorm_fwd_kernel(const bf16* __restrict__ x, const bf16* __restrict__ scale, bf16* __restrict__ y,
+                   float* __restrict__ rstd, int64_t rows, int D, float eps) {
+  __shared__ float red[32];
+  for (int64_t r = blockIdx.x; r < rows; r += gridDim.x) {
+    const bf16* xr = x + r * D;
+    uint4 v[kNormMaxChunks];
+    float ss = 0.f;
+#pragma unroll
+    for (int c = 0; c < kNormMaxChunks; ++c) {
+      const int d0 = (c * kNormThreads + threadIdx.x) * 8;
+      if (d0 < D) {
+        v[c] = *reinterpret_cast<const uint4*>(xr + d0);
+        float f[8];
+        unpack8(v[c], f);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) ss += f[i] * f[i];
+      }
+    }
+    ss = block_sum(ss, red);
+    const float rs = rsqrtf(ss / (float)D + eps);
+    if (threadIdx.x == 0 && rstd) rstd[r] = rs;
+#pragma unroll
+    for (int c = 0; c < kNormMaxChunks; ++c) {
+      const int d0 = (c * kNormThreads + threadIdx.x) * 8;
+      if (d0 < D) {
+        float f[8], s[8];
+        unpack8(v[c], f);
+        unpack8(*reinterpret_cast<const uint4*>(scale + d0), s);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) f[i] = round_bf16(f[i] * rs) * s[i];
+        *reinterpret_cast<uint4*>(y + r * D + d0) = pack8(f);
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kNormThreads)
+rmsnorm_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, const bf16* __restrict__ scale,
+                   const float* __restrict__ rstd, const bf16* __restrict__ dres, bf16* __restrict__ dx,
+                   float* __restrict__ dscale, int64_t rows, int D) {
+  __shared__ float red[32];
+  float ds[kNormMaxChunks][8];
+#pragma unroll
+  for (int c = 0; c < kNormMaxChunks; ++c)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) ds[c][i] = 0.f;
+  for (int64_t r = blockIdx.x; r < rows; r += gridDim.x) {
+    const float rs = rstd[r];
+    float xh[kNormMaxChunks][8], gs[kNormMaxChunks][8];
+    float dot = 0.f;
+#pragma unroll
+    for (int c = 0; c < kNormMaxChunks; ++c) {
+      const int d0 = (c * kNormThreads + threadIdx.x) * 8;
+      if (d0 < D) {
+        float g[8], s[8];
+        unpack8(*reinterpret_cast<const uint4*>(x + r * D + d0), xh[c]);
+        unpack8(*reinterpret_cast<const uint4*>(dy + r * D + d0), g);
+        unpack8(*reinterpret_cast<const uint4*>(scale + d0), s);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          xh[c][i] *= rs;
+          ds[c][i] += g[i] * xh[c][i];
+          gs[c][i] = g[i] * s[i];
+          dot += gs[c][i] * xh[c][i];
+        }
+      }
+    }
+    dot = block_sum(dot, red) / (float)D;
+#pragma unroll
+    for (int c = 0; c < kNormMaxChunks; ++c) {
+      const int d0 = (c * kNormThreads + threadIdx.x) * 8;
+      if (d0 < D) {
+        float o[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] = rs * (gs[c][i] - xh[c][i] * dot);
+        if (dres) {
+          float e[8];
+          unpack8(*reinterpret_cast<const uint4*>(dres + r * D + d0), e);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) o[i] += e[i];
+        }
+        *reinterpret_cast<uint4*>(dx + r * D + d0) = pack8(o);
+      }
+    }
+  }
+  if (dscale) {
+#pragma unroll
+    for (int c = 0; c < kNormMaxChunks; ++c) {
+      const int d0 = (c * kNormThreads + threadIdx.x) * 8;
+      if (d0 < D) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) atomicAdd(dscale + d0 + i, ds[c][i]);
+      }
+    }
+  }
+}
+
+// one thread per 8 bf16 (= 4 rotation pairs)
+__global__ void __launch_bounds__(256)
+rope_kernel(bf16* __restrict__ x, const float* __restrict__ cache, int64_t rows, int seq_len, int heads,
+            int hd, int64_t ldx, float sgn) {
+  const int vec_per_head = hd / 8;
+  const int64_t total = rows * heads * vec_per_head;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int vv = (int)(i % vec_per_head);
+    const int64_t t = i / vec_per_head;
+    const int hh = (int)(t % heads);
+    const int64_t r = t / heads;
+    const int pos = (int)(r % seq_len);
+    bf16* p = x + r * ldx + (int64_t)hh * hd + vv * 8;
+    float f[8];
+    unpack8(*reinterpret_cast<const uint4*>(p), f);
+    const float4* cs = reinterpret_cast<const float4*>(cache + ((int64_t)pos * (hd / 2) + vv * 4) * 2);
+    const float4 c01 = cs[0], c23 = cs[1];
+    const float co[4] = {c01.x, c01.z, c23.x, c23.z};
+    const float si[4] = {c01.y * sgn, c01.w * sgn, c23.y * sgn, c23.w * sgn};
+    float o[8];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      o[2 * j] = f[2 * j] * co[j] - f[2 * j + 1] * si[j];
+      o[2 * j + 1] = f[2 * j + 1] * co[j] + f[2 * j] * si[j];
+    }
+    *reinterpret_cast<uint4*>(p) = pack8(o);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+swiglu_fwd_kernel(const bf16* __restrict__ gate, const bf16* __restrict__ up, bf16* __restrict__ out,
+                  int64_t rows, int64_t cols, int64_t ldg, int64_t ldu, int64_t ldo) {
+  const int64_t vc = cols / 8, total = rows * vc;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / vc, c = (i % vc) * 8;
+    float g[8], u[8];
+    unpack8(*reinterpret_cast<const uint4*>(gate + r * ldg + c), g);
+    unpack8(*reinterpret_cast<const uint4*>(up + r * ldu + c), u);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) g[j] = round_bf16(g[j] / (1.f + __expf(-g[j]))) * u[j];
+    *reinterpret_cast<uint4*>(out + r * ldo + c) = pack8(g);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+swiglu_bwd_kernel(const bf16* __restrict__ dout, const bf16* __restrict__ gate, const bf16* __restrict__ up,
+                  bf16* __restrict__ dgate, bf16* __restrict__ dup, int64_t rows, int64_t cols, int64_t ldo,
+                  int64_t ldg, int64_t ldu, int64_t lddg, int64_t lddu) {
+  const int64_t vc = cols / 8, total = rows * vc;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / vc, c = (i % vc) * 8;
+    float g[8], u[8], d[8], dg[8], du[8];
+    unpack8(*reinterpret_cast<const uint4*>(gate + r * ldg + c), g);
+    unpack8(*reinterpret_cast<const uint4*>(up + r * ldu + c), u);
+    unpack8(*reinterpret_cast<const uint4*>(dout + r * ldo + c), d);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float s = 1.f / (1.f + __expf(-g[j]));
+      du[j] = d[j] * g[j] * s;
+      dg[j] = d[j] * u[j] * s * (1.f + g[j] * (1.f - s));
+    }
+    *reinterpret_cast<uint4*>(dgate + r * lddg + c) = pack8(dg);
+    *reinterpret_cast<uint4*>(dup + r * lddu + c) = pack8(du);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+f32_to_bf16_kernel(const float* __restrict__ src, bf16* __restrict__ dst, int64_t n, float scale, int acc) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float v = src[i] * scale;
+    if (acc) v += __bfloat162float(dst[i]);
+    dst[i] = __float2bfloat16_rn(v);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+add_bf16_kernel(const bf16* __restrict__ a, const bf16* __restrict__ b, bf16* __restrict__ o, int64_t n) {
+  const int64_t nv = n / 8;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nv; i += (int64_t)gridDim.x * blockDim.x) {
+    float x[8], y[8];
+    unpack8(*reinterpret_cast<const uint4*>(a + i * 8), x);
+    unpack8(*reinterpret_cast<const uint4*>(b + i * 8), y);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) x[j] += y[j];
+    *reinterpret_cast<uint4*>(o + i * 8) = pack8(x);
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0)
+    for (int64_t i = nv * 8; i < n; ++i) o[i] = __float2bfloat16_rn(__bfloat162float(a[i]) + __bfloat162float(b[i]));
+}
+
+static inline unsigned grid_for(int64_t work_items, int threads, int max_waves = 8) {
+  int64_t g = (work_items + threads - 1) / threads;
+  int64_t cap = (int64_t)num_sms() * max_waves;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return (unsigned)g;
+}
+
+}  // namespace csm
+
+using namespace csm;
+
+extern "C" int csm_rmsnorm_fwd(const void* x, const void* scale, void* y, float* rstd, int64_t rows,
+                               int32_t dim, float eps, csm_stream_t stream) {
+  CSM_REQUIRE(rows >= 0 && dim > 0 && dim % 8 == 0 && dim <= kNormThreads * 8 * kNormMaxChunks, CSM_ERR_SHAPE,
+              "rmsnorm_fwd: dim=%d must be a multiple of 8 and <= %d", dim, kNormThreads * 8 * kNormMaxChunks);
+  CSM_REQUIRE(aligned16(x) && aligned16(y) && aligned16(scale), CSM_ERR_ALIGN, "rmsnorm_fwd: misaligned pointer");
+  if (rows == 0) return CSM_OK;
+  unsigned grid = (unsigned)(rows < (int64_t)num_sms() * 8 ? rows : (int64_t)num_sms() * 8);
+  rmsnorm_fwd_kernel<<<grid, kNormThreads, 0, as_stream(stream)>>>((const bf16*)x, (const bf16*)scale, (bf16*)y,
+                                                                   rstd, rows, dim, eps);
+  CSM_CHECK_LAUNCH("rmsnorm_fwd");
+  return CSM_OK;
+}
+
+extern "C" int csm_rmsnorm_bwd(const void* dy, const void* x, const void* scale, const float* rstd,
+                               const void* dres, void* dx, float* dscale_f32, int64_t rows, int32_t dim,
+                               csm_stream_t stream) {
+  CSM_REQUIRE(rows >= 0 && dim > 0 && dim % 8 == 0 && dim <= kNormThreads * 8 * kNormMaxChunks, CSM_ERR_SHAPE,
+              "rmsnorm_bwd: bad dim=%d", dim);
+  CSM_REQUIRE(aligned16(x) && aligned16(dy) && aligned16(dx) && aligned16(scale) && aligned16(dres),
+              CSM_ERR_ALIGN, "rmsnorm_bwd: misaligned pointer");
+  if (rows == 0) return CSM_OK;
+  unsigned grid = (unsigned)(rows < (int64_t)num_sms() * 2 ? rows : (int64_t)num_sms() * 2);
+  rmsnorm_bwd_kernel<<<grid, kNormThreads, 0, as_stream(stream)>>>((const bf16*)dy, (const bf16*)x,
+                                                                   (const bf16*)scale, rstd, (const bf16*)dres,
+                                                                   (bf16*)dx, dscale_f32, rows, dim);
+  CSM_CHECK_LAUNCH("rmsnorm_bwd");
+  return CSM_OK;
+}
+
+extern "C" int csm_rope(void* x, const float* cache, int64_t rows, int32_t seq_len, int32_t heads,
+                        int32_t head_dim, int64_t ldx, int32_t inverse, csm_stream_t stream) {
+  CSM_REQUIRE(rows >= 0 && seq_len > 0 && heads > 0 && head_dim > 0 && head_dim % 8 == 0 && ldx % 8 == 0,
+              CSM_ERR_SHAPE, "rope: head_dim=%d and ldx=%lld must be multiples of 8", head_dim, (long long)ldx);
+  CSM_REQUIRE(aligned16(x) && aligned16(cache), CSM_ERR_ALIGN, "rope: misaligned pointer");
+  if (rows == 0) return CSM_OK;
+  const int64_t total = rows * heads * (head_dim / 8);
+  rope_kernel<<<grid_for(total, 256), 256, 0, as_stream(stream)>>>((bf16*)x, cache, rows, seq_len, heads,
+                                                                   head_dim, ldx, inverse ? -1.f : 1.f);
+  CSM_CHECK_LAUNCH("rope");
+  return CSM_OK;
+}
+
+extern "C" int csm_swiglu_fwd(const void* gate, const void* up, void* out, int64_t rows, int64_t cols,
+                              int64_t ldg, int64_t ldu, int64_t ldo, csm_stream_t stream) {
+  CSM_REQUIRE(rows >= 0 && cols > 0 && cols % 8 == 0 && ldg % 8 == 0 && ldu % 8 == 0 && ldo % 8 == 0,
+              CSM_ERR_SHAPE, "swiglu_fwd: cols and strides must be multiples of 8");
+  CSM_REQUIRE(aligned16(gate) && aligned16(up) && aligned16(out), CSM_ERR_ALIGN, "swiglu_fwd: misaligned");
+  if (rows == 0) return CSM_OK;
+  swiglu_fwd_kernel<<<grid_for(rows * (cols / 8), 256), 256, 0, as_stream(stream)>>>(
+      (const bf16*)gate, (const bf16*)up, (bf16*)out, rows, cols, ldg, ldu, ldo);
+  CSM_CHECK_LAUNCH("swiglu_fwd");
+  return CSM_OK;
+}
+
+extern "C" int csm_swiglu_bwd(const void* dout, const void* gate, const void* up, void* dgate, void* dup,
+                              int64_t rows, int64_t cols, int64_t ldo, int64_t ldg, int64_t ldu, int64_t lddg,
+                              int64_t lddu, csm_stream_t stream) {
+  CSM_REQUIRE(rows >= 0 && cols > 0 && cols % 8 == 0 && ldg % 8 == 0 && ldu % 8 == 0 && ldo % 8 == 0 &&
+                  lddg % 8 == 0 && lddu % 8 == 0,
+              CSM_ERR_SHAPE, "swiglu_bwd: cols and strides must be multiples of 8");
+  CSM_REQUIRE(aligned16(gate) && aligned16(up) && aligned16(dout) && aligned16(dgate) && aligned16(dup),
+              CSM_ERR_ALIGN, "swiglu_bwd: misaligned");
+  if (rows == 0) return CSM_OK;
+  swiglu_bwd_kernel<<<grid_for(rows * (cols / 8), 256), 256, 0, as_stream(stream)>>>(
+      (const bf16*)dout, (const bf16*)gate, (const bf16*)up, (bf16*)dgate, (bf16*)dup, rows, cols, ldo, ldg,
+      ldu, lddg, lddu);
+  CSM_CHECK_LAUNCH("swiglu_bwd");
+  return CSM_OK;
+}
+
+extern "C" int csm_f32_to_bf16(const float* src, void* dst, int64_t n, float scale, int32_t accumulate,
+                               csm_stream_t stream) {
+  if (n <= 0) return CSM_OK;
+  f32_to_bf16_kernel<<<grid_for(n, 256), 256, 0, as_stream(stream)>>>(src, (bf16*)dst, n, scale, accumulate);
+  CSM_CHECK_LAUNCH("f32_to_bf16");
+  return CSM_OK;
+}
+
+extern "C" int csm_add_bf16(const void* a, const void* b, void* out, int64_t n, csm_stream_t stream) {
+  if (n <= 0) return CSM_OK;
+  CSM_REQUIRE(aligned16(a) && aligned16(b) && aligned16(out), CSM_ERR_ALIGN, "add_bf16: misaligned");
+  add_bf16_kernel<<<grid_for(n / 8 + 1, 256), 256, 0, as_stream(stream)>>>((const bf16*)a, (const bf16*)b,
+                                                                           (bf16*)out, n);
+  CSM_CHECK_LAUNCH("add_bf16");
+  return CSM_OK;
+}

@@ -1,0 +1,158 @@
+/* csm_b200.h — C ABI of libcsm_b200.so: the sm_100a kernels behind the CSM training step.
+ *
+ * Drop-in boundary.  The reference (imaginateit/csm-train-pytorch) is pure Python
+ * and reaches its arithmetic through torch / torchtune calls; each entry point below replaces one of
+ * those call sites (cited per function, paths relative to /root/reference).  A maintainer binds them
+ * with ctypes (INTEGRATION.md shows the stub); the product binding is csm-train-pytorch_b200/csm/_lib.py.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer on the current device unless marked host; the caller owns all
+ *     buffers (inputs, outputs, workspace); nothing here allocates, frees or retains device memory.
+ *   - bf16 storage, fp32 accumulation. "ld*" are row strides in ELEMENTS. Rows must be 16-byte aligned
+ *     for the tensor-core paths; other shapes run the scalar-FMA small-shape kernels (tiny test model).
+ *   - all calls are asynchronous on `stream` (a cudaStream_t) and never synchronise the host.
+ *   - return 0 on success; <0 on error: -1 bad shape/argument, -2 misaligned pointer or stride,
+ *     -3 unsupported device (needs sm_100), -4 CUDA launch/runtime error. csm_last_error() returns a
+ *     thread-local message.  There is NO CPU fallback.
+ */
+#ifndef CSM_B200_H
+#define CSM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* csm_stream_t; /* cudaStream_t */
+
+#define CSM_ABI_VERSION 1
+
+#define CSM_OK 0
+#define CSM_ERR_SHAPE (-1)
+#define CSM_ERR_ALIGN (-2)
+#define CSM_ERR_ARCH (-3)
+#define CSM_ERR_CUDA (-4)
+
+#define CSM_DT_BF16 0
+#define CSM_DT_F32 1
+
+/* GEMM back-end selector (csm_gemm_bf16 `backend`): AUTO picks tcgen05 when the shape is tileable. */
+#define CSM_GEMM_AUTO 0
+#define CSM_GEMM_SIMT 1
+#define CSM_GEMM_TCGEN05 2
+
+int csm_abi_version(void);
+const char* csm_last_error(void);
+/* 1 if the current device is compute capability 10.x, else 0 (no CUDA call fails on a CPU-only host: returns 0). */
+int csm_device_supported(void);
+/* number of kernel launches issued through this library by the calling process so far */
+int64_t csm_launch_count(void);
+
+/* ---- A2: Model._embed_tokens + mask-mul + sum (src/csm/models/model.py:206-217, src/csm/training/utils.py:85-87)
+ * h[n,:] = sum_{c<=C} mask[n,c] * table_c[idx[n,c],:], summed in fp32 in order c=0..C, rounded once to bf16.
+ * idx[n,c] = tokens[n,c] + c*audio_vocab (c<C, into audio_emb); idx[n,C] = tokens[n,C] (into text_emb).
+ * idx_out / mask_out (nullable) export the integer index and effective mask the kernel used (bit-exact parity hook).
+ * status (nullable int32[1]) is set to 1 if any index was out of range (the row is then treated as masked). */
+int csm_embed_gather_sum_fwd(const int64_t* tokens, const uint8_t* mask, const void* audio_emb,
+                             const void* text_emb, void* h, int64_t* idx_out, uint8_t* mask_out,
+                             int32_t* status, int64_t n_frames, int32_t codebooks, int64_t audio_vocab,
+                             int64_t text_vocab, int32_t dim, csm_stream_t stream);
+/* backward of the above: d_table_c[idx[n,c],:] += mask[n,c]*dh[n,:] (bf16 atomics; either table grad may be NULL). */
+int csm_embed_gather_sum_bwd(const int64_t* tokens, const uint8_t* mask, const void* dh, void* d_audio_emb,
+                             void* d_text_emb, int64_t n_frames, int32_t codebooks, int64_t audio_vocab,
+                             int64_t text_vocab, int32_t dim, csm_stream_t stream);
+
+/* ---- A7 decoder input assembly (model.py:176,189-191 teacher-forced; _embed_audio model.py:202-204)
+ * x[f,0,:] = h[b_f*seq + p_f,:]; x[f,1+i,:] = audio_emb[targets[b_f,p_f,i] + i*audio_vocab,:], i < C-1.
+ * frame_idx int64 [n_sel,2] = (b,p); targets int64 [batch, tgt_len, C]. */
+int csm_decoder_input_fwd(const void* h, const void* audio_emb, const int64_t* targets, const int64_t* frame_idx,
+                          void* x, int64_t n_sel, int64_t seq, int64_t tgt_len, int32_t codebooks,
+                          int64_t audio_vocab, int32_t dim, csm_stream_t stream);
+/* dh[b*seq+p,:] += dx[f,0,:]; d_audio_emb[row,:] += dx[f,1+i,:] (d_audio_emb nullable). */
+int csm_decoder_input_bwd(const void* dx, const int64_t* targets, const int64_t* frame_idx, void* dh,
+                          void* d_audio_emb, int64_t n_sel, int64_t seq, int64_t tgt_len, int32_t codebooks,
+                          int64_t audio_vocab, int32_t dim, csm_stream_t stream);
+
+/* ---- torchtune RMSNorm (call sites model.py:13-25 norm_eps; restated in oracle/torchtune_shim.py)
+ * y = bf16(x * rsqrt(mean(x^2)+eps)) * scale ; rstd[rows] fp32 is saved for backward. */
+int csm_rmsnorm_fwd(const void* x, const void* scale, void* y, float* rstd, int64_t rows, int32_t dim,
+                    float eps, csm_stream_t stream);
+/* dx = dres + d(rmsnorm)/dx (dres nullable); dscale_f32[dim] += sum_rows dy*xhat (nullable; fp32 atomics). */
+int csm_rmsnorm_bwd(const void* dy, const void* x, const void* scale, const float* rstd, const void* dres,
+                    void* dx, float* dscale_f32, int64_t rows, int32_t dim, csm_stream_t stream);
+
+/* ---- torchtune Llama3ScaledRoPE, interleaved pairs, fp32 math (restated in oracle/torchtune_shim.py)
+ * in place on x[rows, heads, head_dim] with row stride ldx; position = row % seq_len;
+ * cache fp32 [max_seq, head_dim/2, 2] = (cos, sin). inverse != 0 applies the transpose rotation (backward). */
+int csm_rope(void* x, const float* cache, int64_t rows, int32_t seq_len, int32_t heads, int32_t head_dim,
+             int64_t ldx, int32_t inverse, csm_stream_t stream);
+
+/* ---- F.linear / torch.mm / their autograd (model.py:124-126,187; every torchtune projection)
+ * C[M,N] (=|+=) alpha * op(A)[M,K] * op(B)[K,N] (+ A2[M,K2] * B2[N,K2]^T) (+ R[M,N])
+ *   transA == 0: A stored [M,K] row-major (lda);  transA != 0: stored [K,M] row-major.
+ *   transB == 0: B stored [N,K] row-major (nn.Linear weight layout); transB != 0: stored [K,N] row-major.
+ *   A2/B2 (nullable): LoRA low-rank tail (K2 <= 64), stored with the SAME orientation as A/B (A2 is [M,K2] or,
+ *   when transA, [K2,M]; B2 is [N,K2] or, when transB, [K2,N]); fused into the main loop as one more K block
+ *   (lora.py:82-105: y = x W0^T + (alpha/r)(x A^T) B^T).
+ *   R (nullable, bf16, ldr): residual added in the epilogue.  c_dtype: CSM_DT_BF16 | CSM_DT_F32.
+ *   accumulate != 0: C += result (read-modify-write in c_dtype). */
+int csm_gemm_bf16(const void* A, const void* B, void* C, const void* R, int64_t M, int64_t N, int64_t K,
+                  int64_t lda, int64_t ldb, int64_t ldc, int64_t ldr, int32_t transA, int32_t transB,
+                  int32_t c_dtype, int32_t accumulate, float alpha, const void* A2, const void* B2,
+                  int64_t K2, int64_t lda2, int64_t ldb2, int32_t backend, csm_stream_t stream);
+
+/* ---- torchtune FeedForward activation: out = silu(gate) * up (elementwise, fp32 math) */
+int csm_swiglu_fwd(const void* gate, const void* up, void* out, int64_t rows, int64_t cols, int64_t ldg,
+                   int64_t ldu, int64_t ldo, csm_stream_t stream);
+int csm_swiglu_bwd(const void* dout, const void* gate, const void* up, void* dgate, void* dup, int64_t rows,
+                   int64_t cols, int64_t ldo, int64_t ldg, int64_t ldu, int64_t lddg, int64_t lddu,
+                   csm_stream_t stream);
+
+/* ---- torchtune MultiHeadAttention core = F.scaled_dot_product_attention(is_causal=True) with GQA
+ * q [batch*seq, heads*hd] (ldq), k/v [batch*seq, kv_heads*hd], o like q; kv head j serves q heads
+ * j*(heads/kv_heads) .. (j+1)*(heads/kv_heads)-1.  lse fp32 [batch, heads, seq] saved for backward. */
+int csm_attn_causal_gqa_fwd(const void* q, const void* k, const void* v, void* o, float* lse, int32_t batch,
+                            int32_t seq, int32_t heads, int32_t kv_heads, int32_t head_dim, int64_t ldq,
+                            int64_t ldk, int64_t ldv, int64_t ldo, float scale, csm_stream_t stream);
+/* workspace: csm_attn_bwd_workspace_bytes() bytes (delta[batch,heads,seq] fp32 + fp32 dk/dv staging). */
+size_t csm_attn_bwd_workspace_bytes(int32_t batch, int32_t seq, int32_t heads, int32_t kv_heads,
+                                    int32_t head_dim);
+int csm_attn_causal_gqa_bwd(const void* q, const void* k, const void* v, const void* o, const float* lse,
+                            const void* dout, void* dq, void* dk, void* dv, int32_t batch, int32_t seq,
+                            int32_t heads, int32_t kv_heads, int32_t head_dim, int64_t ldq, int64_t ldk,
+                            int64_t ldv, int64_t ldo, int64_t lddq, int64_t lddk, int64_t lddv, float scale,
+                            void* workspace, size_t workspace_bytes, csm_stream_t stream);
+
+/* ---- codebook0_head + F.cross_entropy (utils.py:98-107) and audio_head[i-1] + CE (model.py:187, A7)
+ * `groups` independent heads g: logits_g = H_g[M,K] * W_g; loss_rows[g*M+m] = lse - logit[target];
+ * H_g = H + g*h_group_stride (row stride ldh), W_g = W + g*w_group_stride, stored [V,K] (transW==0,
+ * nn.Linear layout, ldw) or [K,V] (transW!=0, audio_head layout); targets[m*tgt_row_stride + g*tgt_group_stride].
+ * Full logits are never written on the tcgen05 path (per-tile online-softmax partials only).
+ * lse fp32 [groups*M] is saved for backward. */
+size_t csm_linear_ce_workspace_bytes(int64_t M, int64_t V, int64_t K, int32_t groups);
+int csm_linear_ce_fwd(const void* H, const void* W, const int64_t* targets, float* loss_rows, float* lse,
+                      int64_t M, int64_t V, int64_t K, int32_t groups, int64_t ldh, int64_t h_group_stride,
+                      int64_t ldw, int64_t w_group_stride, int32_t transW, int64_t tgt_row_stride,
+                      int64_t tgt_group_stride, void* workspace, size_t workspace_bytes, int32_t backend,
+                      csm_stream_t stream);
+/* dH_g (bf16, lddh / dh_group_stride) = grad_scale * (softmax - onehot) * W_g^T ; dW_g (nullable, bf16,
+ * same layout as W, accumulated when dw_accumulate) = grad_scale * H_g^T (softmax - onehot). */
+int csm_linear_ce_bwd(const void* H, const void* W, const int64_t* targets, const float* lse, float grad_scale,
+                      void* dH, void* dW, int32_t dw_accumulate, int64_t M, int64_t V, int64_t K,
+                      int32_t groups, int64_t ldh, int64_t h_group_stride, int64_t ldw, int64_t w_group_stride,
+                      int32_t transW, int64_t tgt_row_stride, int64_t tgt_group_stride, int64_t lddh,
+                      int64_t dh_group_stride, void* workspace, size_t workspace_bytes, int32_t backend,
+                      csm_stream_t stream);
+
+/* ---- small helpers used by the training step */
+/* dst_bf16[i] (=|+=) src_f32[i] * scale */
+int csm_f32_to_bf16(const float* src, void* dst, int64_t n, float scale, int32_t accumulate, csm_stream_t stream);
+/* out_bf16 = a_bf16 + b_bf16 (elementwise, fp32 add) */
+int csm_add_bf16(const void* a, const void* b, void* out, int64_t n, csm_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CSM_B200_H */

@@ -1,0 +1,269 @@
+"""GPU parity of every C-ABI op against a plain PyTorch fp32 restatement of the same op (bf16 inputs).
+These call through libcsm_b200.so (ctypes) — the product path; nothing here falls back to torch."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+BF = torch.bfloat16
+
+
+def rel_err(a, b):
+    a, b = a.float(), b.float()
+    return float((a - b).norm() / (b.norm() + 1e-12))
+
+
+def cos(a, b):
+    return float(F.cosine_similarity(a.float().flatten(), b.float().flatten(), dim=0))
+
+
+@pytest.fixture(scope="module")
+def ops(cuda):
+    from csm import ops as o
+    return o
+
+
+def test_library_loads_and_device_supported(cuda):
+    from csm import _lib
+    lib = _lib.load()
+    assert lib.csm_abi_version() == 1
+    assert lib.csm_device_supported() == 1
+
+
+@pytest.mark.parametrize("D,C,V,Vt,B,S", [(32, 32, 200, 1000, 2, 32), (2048, 32, 2051, 128256, 2, 256)])
+def test_embed_gather_sum_bit_exact(ops, cuda, D, C, V, Vt, B, S):
+    g = torch.Generator().manual_seed(0)
+    audio = (torch.randn(C * V, D, generator=g) * 0.02).to(BF).to(cuda)
+    text = (torch.randn(Vt, D, generator=g) * 0.02).to(BF).to(cuda)
+    tokens = torch.zeros(B, S, C + 1, dtype=torch.int64)
+    tokens[..., :C] = torch.randint(0, V, (B, S, C), generator=g)
+    tokens[..., C] = torch.randint(0, Vt, (B, S), generator=g)
+    mask = torch.rand(B, S, C + 1, generator=g) < 0.6
+    mask[:, -2:] = False                      # padding frames
+    mask[:, 0, :C] = False                    # a text-only frame
+    tokens, mask = tokens.to(cuda), mask.to(cuda)
+    h, idx, eff, status = ops.embed_gather_sum(tokens, mask, audio, text, debug=True)
+    # integer half: bit exact (model.py:210-212)
+    ref_idx = tokens.clone()
+    ref_idx[..., :C] += V * torch.arange(C, device=cuda)
+    assert torch.equal(idx, ref_idx)
+    assert torch.equal(eff.bool(), mask)
+    assert int(status.item()) == 0
+    # value half: reference formula in the model dtype (model.py:206-217 + utils.py:85-87)
+    emb = torch.cat([audio[ref_idx[..., :C]], text[tokens[..., C]].unsqueeze(-2)], dim=-2)
+    ref = (emb * mask.unsqueeze(-1)).sum(dim=2)
+    exact = (h == ref).float().mean().item()
+    assert exact > 0.999, exact
+    assert torch.allclose(h.float(), ref.float(), atol=1e-3, rtol=1e-2)
+    assert torch.equal(h[:, -2:], torch.zeros_like(h[:, -2:]))
+    # backward: scatter-add
+    dh = (torch.randn(B, S, D, generator=g) * 0.1).to(BF).to(cuda)
+    da = torch.zeros_like(audio)
+    dt = torch.zeros_like(text)
+    ops.embed_gather_sum_bwd(tokens, mask, dh, da, dt, V, Vt)
+    ra = torch.zeros(C * V, D, device=cuda)
+    rt = torch.zeros(Vt, D, device=cuda)
+    contrib = (dh.float().unsqueeze(2) * mask.unsqueeze(-1))
+    ra.index_add_(0, ref_idx[..., :C].reshape(-1), contrib[:, :, :C].reshape(-1, D))
+    rt.index_add_(0, tokens[..., C].reshape(-1), contrib[:, :, C].reshape(-1, D))
+    assert cos(da, ra) > 0.9999 and cos(dt, rt) > 0.9999
+
+
+def test_embed_out_of_range_sets_status(ops, cuda):
+    C, V, Vt, D = 4, 10, 20, 16
+    audio = torch.randn(C * V, D, device=cuda).to(BF)
+    text = torch.randn(Vt, D, device=cuda).to(BF)
+    tokens = torch.zeros(1, 2, C + 1, dtype=torch.int64, device=cuda)
+    tokens[0, 1, 2] = V            # out of range for its codebook
+    mask = torch.ones(1, 2, C + 1, dtype=torch.bool, device=cuda)
+    _, _, _, status = ops.embed_gather_sum(tokens, mask, audio, text, debug=True)
+    assert int(status.item()) == 1
+
+
+@pytest.mark.parametrize("rows,D", [(64, 32), (50, 16), (777, 2048), (300, 1024)])
+def test_rmsnorm(ops, cuda, rows, D):
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(rows, D, generator=g).to(BF).to(cuda)
+    scale = (1 + 0.1 * torch.randn(D, generator=g)).to(BF).to(cuda)
+    dy = torch.randn(rows, D, generator=g).to(BF).to(cuda)
+    dres = torch.randn(rows, D, generator=g).to(BF).to(cuda)
+    y, rstd = ops.rmsnorm(x, scale, 1e-5)
+    x32 = x.float().requires_grad_(True)
+    s32 = scale.float().requires_grad_(True)
+    ref = ((x32 * torch.rsqrt(x32.pow(2).mean(-1, keepdim=True) + 1e-5)).to(BF).float() * s32)
+    assert torch.allclose(y.float(), ref.to(BF).float(), atol=2e-2, rtol=2e-2)
+    assert rel_err(y, ref) < 4e-3
+    # backward vs autograd of the fp32 formula (without the intermediate rounding)
+    ref2 = (x32 * torch.rsqrt(x32.pow(2).mean(-1, keepdim=True) + 1e-5)) * s32
+    ref2.backward(dy.float())
+    ds = torch.zeros(D, dtype=torch.float32, device=cuda)
+    dx = ops.rmsnorm_bwd(dy, x, scale, rstd, dres, ds)
+    assert cos(dx, x32.grad + dres.float()) > 0.9999
+    assert cos(ds, s32.grad) > 0.9999
+
+
+def _rope_cache(hd, max_seq, base=500000.0, scale=32.0):
+    from csm.models.rope import build_rope_cache
+    return build_rope_cache(hd, max_seq, base, scale)
+
+
+@pytest.mark.parametrize("hd,heads,seq,batch", [(8, 4, 32, 2), (64, 8, 128, 2), (128, 2, 32, 5)])
+def test_rope_matches_interleaved_formula(ops, cuda, hd, heads, seq, batch):
+    g = torch.Generator().manual_seed(2)
+    cache = _rope_cache(hd, 256).to(cuda)
+    x = torch.randn(batch * seq, heads * hd, generator=g).to(BF).to(cuda)
+    y = x.clone()
+    ops.rope_(y, cache, seq, heads, hd)
+    xs = x.float().view(batch, seq, heads, hd // 2, 2)
+    rc = cache[:seq].view(1, seq, 1, hd // 2, 2)
+    ref = torch.stack([xs[..., 0] * rc[..., 0] - xs[..., 1] * rc[..., 1],
+                       xs[..., 1] * rc[..., 0] + xs[..., 0] * rc[..., 1]], -1).flatten(3).to(BF)
+    assert torch.equal(y.view(batch, seq, heads, hd), ref)
+    # inverse rotation is the transpose: rope^T(rope(x)) == x up to bf16 rounding
+    z = y.clone()
+    ops.rope_(z, cache, seq, heads, hd, inverse=True)
+    assert rel_err(z, x) < 6e-3
+
+
+def test_swiglu(ops, cuda):
+    g = torch.Generator().manual_seed(3)
+    gate = torch.randn(200, 512, generator=g).to(BF).to(cuda)
+    up = torch.randn(200, 512, generator=g).to(BF).to(cuda)
+    dout = torch.randn(200, 512, generator=g).to(BF).to(cuda)
+    out = ops.swiglu(gate, up)
+    ref = (F.silu(gate.float()).to(BF).float() * up.float()).to(BF)
+    assert rel_err(out, ref) < 2e-3
+    g32, u32 = gate.float().requires_grad_(True), up.float().requires_grad_(True)
+    (F.silu(g32) * u32).backward(dout.float())
+    dg, du = ops.swiglu_bwd(dout, gate, up)
+    assert cos(dg, g32.grad) > 0.9999 and cos(du, u32.grad) > 0.9999
+
+
+GEMM_SHAPES = [(128, 256, 64), (200, 136, 72), (4096, 2048, 2048), (1000, 512, 2048), (232, 2051, 1024),
+               (4096, 8192, 2048), (37, 24, 16)]
+
+
+@pytest.mark.parametrize("backend", [1, 2])
+@pytest.mark.parametrize("ta,tb", [(False, False), (False, True), (True, False), (True, True)])
+@pytest.mark.parametrize("M,N,K", GEMM_SHAPES)
+def test_gemm_all_majors(ops, cuda, backend, ta, tb, M, N, K):
+    if backend == 2 and (K < 64 or M * N < 4096):
+        pytest.skip("below tcgen05 tile minimum: scalar kernel only")
+    if backend == 1 and M * N * K > 2 ** 33:
+        pytest.skip("scalar kernel: keep test time bounded")
+    g = torch.Generator().manual_seed(M * 7 + N * 3 + K)
+    # leading dimensions padded to a multiple of 8 elements so the same tensors feed both back-ends
+    def mk(r, c):
+        ld = (c + 7) // 8 * 8
+        t = (torch.randn(r, ld, generator=g) * 0.5).to(BF).to(cuda)
+        return t[:, :c]
+    a = mk(K, M) if ta else mk(M, K)
+    b = mk(K, N) if tb else mk(N, K)
+    A = (a.float().t() if ta else a.float())
+    Bm = (b.float() if tb else b.float().t())
+    ref = A @ Bm
+    out = ops.gemm(a, b, trans_a=ta, trans_b=tb, backend=backend)
+    assert out.shape == (M, N)
+    assert rel_err(out, ref) < 5e-3, rel_err(out, ref)
+
+
+@pytest.mark.parametrize("backend", [1, 2])
+def test_gemm_epilogues_and_lora_tail(ops, cuda, backend):
+    g = torch.Generator().manual_seed(5)
+    M, N, K, r = 512, 384, 256, 8
+    x = (torch.randn(M, K, generator=g) * 0.5).to(BF).to(cuda)
+    w = (torch.randn(N, K, generator=g) * 0.1).to(BF).to(cuda)
+    res = torch.randn(M, N, generator=g).to(BF).to(cuda)
+    t = (torch.randn(M, r, generator=g) * 0.5).to(BF).to(cuda)
+    lb = (torch.randn(N, r, generator=g) * 0.1).to(BF).to(cuda)
+    ref = 0.5 * (x.float() @ w.float().t() + t.float() @ lb.float().t()) + res.float()
+    out = ops.gemm(x, w, residual=res, alpha=0.5, a2=t, b2=lb, backend=backend)
+    assert rel_err(out, ref) < 5e-3
+    # transposed B with a transposed tail (the dgrad form: dx = dy W + dt A)
+    wt = w.t().contiguous()            # [K, N]
+    lbt = lb.t().contiguous()          # [r, N]
+    out2 = ops.gemm(x, wt, trans_b=True, a2=t, b2=lbt, backend=backend)
+    ref2 = x.float() @ w.float().t() + t.float() @ lb.float().t()
+    assert rel_err(out2, ref2) < 5e-3
+    # accumulate into bf16 and fp32 outputs
+    acc = res.clone()
+    ops.gemm(x, w, out=acc, accumulate=True, backend=backend)
+    assert rel_err(acc, res.float() + x.float() @ w.float().t()) < 5e-3
+    acc32 = res.float().clone()
+    ops.gemm(x, w, out=acc32, accumulate=True, backend=backend)
+    assert rel_err(acc32, res.float() + x.float() @ w.float().t()) < 2e-3
+
+
+def _sdpa_ref(q, k, v, B, S, H, KV, hd):
+    q4 = q.float().view(B, S, H, hd).transpose(1, 2)
+    k4 = k.float().view(B, S, KV, hd).repeat_interleave(H // KV, dim=2).transpose(1, 2)
+    v4 = v.float().view(B, S, KV, hd).repeat_interleave(H // KV, dim=2).transpose(1, 2)
+    o = F.scaled_dot_product_attention(q4, k4, v4, is_causal=True)
+    return o.transpose(1, 2).reshape(B * S, H * hd)
+
+
+@pytest.mark.parametrize("B,S,H,KV,hd", [(2, 32, 4, 4, 8), (3, 32, 2, 2, 8), (2, 256, 8, 2, 64), (1, 300, 4, 1, 64),
+                                         (7, 32, 8, 2, 128), (1, 2048, 4, 1, 64)])
+def test_attention_fwd_bwd(ops, cuda, B, S, H, KV, hd):
+    g = torch.Generator().manual_seed(B * S + hd)
+    q = torch.randn(B * S, H * hd, generator=g).to(BF).to(cuda)
+    k = torch.randn(B * S, KV * hd, generator=g).to(BF).to(cuda)
+    v = torch.randn(B * S, KV * hd, generator=g).to(BF).to(cuda)
+    do = torch.randn(B * S, H * hd, generator=g).to(BF).to(cuda)
+    o, lse = ops.attention_fwd(q, k, v, B, S, H, KV, hd)
+    q32, k32, v32 = (t.float().requires_grad_(True) for t in (q, k, v))
+    ref = _sdpa_ref(q32, k32, v32, B, S, H, KV, hd)
+    assert rel_err(o, ref) < 1e-2, rel_err(o, ref)
+    ref.backward(do.float())
+    dq, dk, dv = ops.attention_bwd(q, k, v, o, lse, do, B, S, H, KV, hd)
+    assert cos(dq, q32.grad) > 0.999 and cos(dk, k32.grad) > 0.999 and cos(dv, v32.grad) > 0.999
+    assert rel_err(dq, q32.grad) < 2e-2 and rel_err(dk, k32.grad) < 2e-2 and rel_err(dv, v32.grad) < 2e-2
+
+
+@pytest.mark.parametrize("backend", [1, 2])
+@pytest.mark.parametrize("M,V,K", [(100, 200, 32), (300, 2051, 256), (1000, 2051, 2048)])
+def test_linear_ce_single_head(ops, cuda, backend, M, V, K):
+    if backend == 2 and K < 64:
+        pytest.skip("below tcgen05 tile minimum")
+    g = torch.Generator().manual_seed(M + V)
+    h = torch.randn(M, K, generator=g).to(BF).to(cuda)
+    w = (torch.randn(V, K, generator=g) * (2.0 / math.sqrt(K))).to(BF).to(cuda)
+    tgt = torch.randint(0, V, (M,), generator=g).to(cuda)
+    loss, lse = ops.linear_ce_fwd(h, w, tgt, backend=backend)
+    h32, w32 = h.float().requires_grad_(True), w.float().requires_grad_(True)
+    logits = h32 @ w32.t()
+    ref = F.cross_entropy(logits, tgt, reduction="none")
+    assert torch.allclose(loss[0], ref, atol=2e-3, rtol=2e-3), float((loss[0] - ref).abs().max())
+    ref.mean().backward()
+    dh = torch.empty_like(h)
+    dw = torch.zeros_like(w)
+    ops.linear_ce_bwd(h, w, tgt, lse, 1.0 / M, dh=dh, dw=dw, backend=backend)
+    assert cos(dh, h32.grad) > 0.999 and cos(dw, w32.grad) > 0.999
+
+
+@pytest.mark.parametrize("backend,trans_w", [(1, True), (1, False), (2, False)])
+def test_linear_ce_grouped_heads(ops, cuda, backend, trans_w):
+    g = torch.Generator().manual_seed(9)
+    Ns, C, Dd, V = 40, 32, 128, 2051
+    y = torch.randn(Ns, C, Dd, generator=g).to(BF).to(cuda)
+    head = (torch.randn(C - 1, Dd, V, generator=g) * 0.2).to(BF).to(cuda)       # audio_head layout [31, Dd, V]
+    codes = torch.randint(0, V, (Ns, C), generator=g).to(cuda)
+    w = head if trans_w else head.transpose(1, 2).contiguous()
+    hv = y[:, 1:]                                                                # position i -> head i-1
+    loss, lse = ops.linear_ce_fwd(hv, w, codes[:, 1:], trans_w=trans_w, groups=C - 1, tgt_row_stride=C,
+                                  tgt_group_stride=1, backend=backend)
+    y32, w32 = y.float().requires_grad_(True), head.float().requires_grad_(True)
+    logits = torch.einsum("ncd,cdv->ncv", y32[:, 1:], w32)
+    ref = F.cross_entropy(logits.reshape(-1, V), codes[:, 1:].reshape(-1), reduction="none").view(Ns, C - 1)
+    assert torch.allclose(loss.t(), ref, atol=3e-3, rtol=3e-3)
+    ref.mean().backward()
+    dy = torch.zeros_like(y)
+    dw = torch.zeros_like(w)
+    ops.linear_ce_bwd(hv, w, codes[:, 1:], lse, 1.0 / (Ns * (C - 1)), dh=dy[:, 1:], dw=dw, trans_w=trans_w,
+                      groups=C - 1, tgt_row_stride=C, tgt_group_stride=1, backend=backend)
+    assert cos(dy, y32.grad) > 0.999
+    dwr = w32.grad if trans_w else w32.grad.transpose(1, 2)
+    assert cos(dw, dwr) > 0.999
