@@ -1,0 +1,306 @@
+"""CSM ``Model`` on libcsm_b200 — drop-in for /root/reference/src/csm/models/model.py.
+
+Same constructor (``ModelArgs``), attributes and state-dict keys as the reference (model.py:99-126;
+backbone./decoder. keys follow torchtune 0.4.0: ``layers.{i}.attn.{q,k,v}_proj.weight``,
+``layers.{i}.attn.output_proj.weight``, ``layers.{i}.mlp.{w1,w2,w3}.weight``,
+``layers.{i}.{sa_norm,mlp_norm}.scale``, ``norm.scale``), same helpers (``_embed_tokens``, ``_embed_audio``,
+``_index_causal_mask``, ``_create_causal_mask``).  New: ``Model.forward`` — the training forward the reference only
+has as a free function (training/utils.py:56-119) plus the decoder term it leaves as a placeholder
+(utils.py:109-117; restated from generate_frame model.py:171-193).
+
+Every arithmetic op runs in a CUDA kernel of libcsm_b200.so (bf16 storage, fp32 accumulation).  There is no CPU
+path: calling forward on CPU tensors raises.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+from typing import Dict, Optional, Tuple
+
+import torch
+import torch.nn as nn
+
+from .. import ops
+from ..autograd import (DecoderInputFn, EmbedGatherSumFn, GroupedLinearCEFn, LinearCEFn, LinearFn, StackFn)
+from .rope import build_rope_cache
+
+BF16 = torch.bfloat16
+
+
+# ----------------------------------------------------------------------------- transformer modules (parameters only)
+class RMSNorm(nn.Module):
+    def __init__(self, dim: int, eps: float):
+        super().__init__()
+        self.eps = eps
+        self.scale = nn.Parameter(torch.ones(dim))
+
+
+class MultiHeadAttention(nn.Module):
+    def __init__(self, embed_dim, num_heads, num_kv_heads, head_dim):
+        super().__init__()
+        self.q_proj = nn.Linear(embed_dim, num_heads * head_dim, bias=False)
+        self.k_proj = nn.Linear(embed_dim, num_kv_heads * head_dim, bias=False)
+        self.v_proj = nn.Linear(embed_dim, num_kv_heads * head_dim, bias=False)
+        self.output_proj = nn.Linear(embed_dim, embed_dim, bias=False)
+
+
+class FeedForward(nn.Module):
+    def __init__(self, dim, hidden):
+        super().__init__()
+        self.w1 = nn.Linear(dim, hidden, bias=False)   # gate
+        self.w2 = nn.Linear(hidden, dim, bias=False)   # down
+        self.w3 = nn.Linear(dim, hidden, bias=False)   # up
+
+
+class TransformerLayer(nn.Module):
+    def __init__(self, embed_dim, num_heads, num_kv_heads, head_dim, intermediate_dim, eps):
+        super().__init__()
+        self.attn = MultiHeadAttention(embed_dim, num_heads, num_kv_heads, head_dim)
+        self.mlp = FeedForward(embed_dim, intermediate_dim)
+        self.sa_norm = RMSNorm(embed_dim, eps)
+        self.mlp_norm = RMSNorm(embed_dim, eps)
+
+
+class TransformerDecoder(nn.Module):
+    """Parameter container with torchtune's TransformerDecoder interface as the reference uses it
+    (model.py:53-55,137,169,184): ``tok_embeddings``/``output`` attributes, ``max_seq_len``,
+    ``forward(h, input_pos=, mask=) -> fp32``.  Causal attention only (training)."""
+
+    def __init__(self, num_layers, num_heads, num_kv_heads, embed_dim, max_seq_len, intermediate_dim,
+                 norm_eps=1e-5, rope_base=500_000.0, scale_factor=32.0):
+        super().__init__()
+        self.num_heads, self.num_kv_heads = num_heads, num_kv_heads
+        self.embed_dim, self.head_dim = embed_dim, embed_dim // num_heads
+        self.max_seq_len, self.norm_eps = max_seq_len, norm_eps
+        self.rope_base, self.scale_factor = rope_base, scale_factor
+        self.tok_embeddings = nn.Identity()
+        self.output = nn.Identity()
+        self.layers = nn.ModuleList([
+            TransformerLayer(embed_dim, num_heads, num_kv_heads, self.head_dim, intermediate_dim, norm_eps)
+            for _ in range(num_layers)])
+        self.norm = RMSNorm(embed_dim, norm_eps)
+        self._rope = {}
+
+    def rope_cache(self, device) -> torch.Tensor:
+        key = (str(device), self.max_seq_len)
+        if key not in self._rope:
+            self._rope[key] = build_rope_cache(self.head_dim, self.max_seq_len, self.rope_base,
+                                               self.scale_factor).to(device)
+        return self._rope[key]
+
+    def set_max_seq_len(self, n: int) -> None:
+        """Llama-3 scaling is position independent, so a longer context only extends the table."""
+        self.max_seq_len = n
+
+    def caches_are_enabled(self) -> bool:
+        return False
+
+    def setup_caches(self, *a, **k):
+        raise NotImplementedError("KV caches are an inference feature; the B200 path is the training step")
+
+    def reset_caches(self):
+        pass
+
+    def run(self, x: torch.Tensor) -> torch.Tensor:
+        """bf16 [B,S,D] -> bf16 [B,S,D] (layers + final norm) through the CUDA kernels."""
+        if not x.is_cuda:
+            raise RuntimeError("csm_b200: the transformer runs on CUDA only (no CPU fallback)")
+        if x.dtype != BF16:
+            raise RuntimeError(f"csm_b200: bf16 activations expected, got {x.dtype}; call model.to(torch.bfloat16)")
+        return StackFn.apply(x, self, *list(self.parameters()))
+
+    def forward(self, h: torch.Tensor, *, input_pos: Optional[torch.Tensor] = None,
+                mask: Optional[torch.Tensor] = None) -> torch.Tensor:
+        # input_pos must be arange(S) per row and mask the causal mask it indexes (utils.py:81-90): the kernels
+        # implement exactly that case (is_causal) and positions row % S.
+        return self.run(h).float()
+
+
+def _stack(**kw) -> TransformerDecoder:
+    return TransformerDecoder(**kw)
+
+
+def llama3_2_1B() -> TransformerDecoder:                     # model.py:11-25
+    return _stack(num_layers=16, num_heads=32, num_kv_heads=8, embed_dim=2048, max_seq_len=2048,
+                  intermediate_dim=8192, norm_eps=1e-5, rope_base=500_000, scale_factor=32)
+
+
+def llama3_2_100M() -> TransformerDecoder:                   # model.py:28-42
+    return _stack(num_layers=4, num_heads=8, num_kv_heads=2, embed_dim=1024, max_seq_len=2048,
+                  intermediate_dim=8192, norm_eps=1e-5, rope_base=500_000, scale_factor=32)
+
+
+def _tiny_backbone() -> TransformerDecoder:                  # tests/create_test_model.py:42-51,81,123-131
+    return _stack(num_layers=2, num_heads=4, num_kv_heads=4, embed_dim=32, max_seq_len=2048, intermediate_dim=128)
+
+
+def _tiny_decoder() -> TransformerDecoder:                   # tests/create_test_model.py:179-188
+    return _stack(num_layers=1, num_heads=2, num_kv_heads=2, embed_dim=16, max_seq_len=2048, intermediate_dim=64)
+
+
+def _small_backbone() -> TransformerDecoder:
+    return _stack(num_layers=2, num_heads=4, num_kv_heads=1, embed_dim=256, max_seq_len=2048, intermediate_dim=512)
+
+
+def _small_decoder() -> TransformerDecoder:
+    return _stack(num_layers=1, num_heads=2, num_kv_heads=1, embed_dim=256, max_seq_len=2048, intermediate_dim=512)
+
+
+FLAVORS = {
+    "llama-1B": llama3_2_1B,
+    "llama-100M": llama3_2_100M,
+    # test shapes (not in the reference's registry)
+    "tiny-backbone": _tiny_backbone,
+    "tiny-decoder": _tiny_decoder,
+    "small-backbone": _small_backbone,
+    "small-decoder": _small_decoder,
+}
+
+
+def _prepare_transformer(model):                             # model.py:51-56
+    return model, model.embed_dim
+
+
+def _create_causal_mask(seq_len: int, device: torch.device):  # model.py:59-61
+    return torch.tril(torch.ones(seq_len, seq_len, dtype=torch.bool, device=device))
+
+
+def _index_causal_mask(mask: torch.Tensor, input_pos: torch.Tensor):  # model.py:64-76
+    return mask[input_pos, :]
+
+
+@dataclass
+class ModelArgs:                                             # model.py:99-107
+    backbone_flavor: str
+    decoder_flavor: str
+    text_vocab_size: int
+    audio_vocab_size: int
+    audio_num_codebooks: int
+
+
+class Model(nn.Module):
+    def __init__(self, args: ModelArgs):
+        super().__init__()
+        self.args = args
+        self.backbone, backbone_dim = _prepare_transformer(FLAVORS[args.backbone_flavor]())
+        self.decoder, decoder_dim = _prepare_transformer(FLAVORS[args.decoder_flavor]())
+        self.text_embeddings = nn.Embedding(args.text_vocab_size, backbone_dim)
+        self.audio_embeddings = nn.Embedding(args.audio_vocab_size * args.audio_num_codebooks, backbone_dim)
+        self.projection = nn.Linear(backbone_dim, decoder_dim, bias=False)
+        self.codebook0_head = nn.Linear(backbone_dim, args.audio_vocab_size, bias=False)
+        self.audio_head = nn.Parameter(torch.empty(args.audio_num_codebooks - 1, decoder_dim, args.audio_vocab_size))
+        self._head_t = None
+        self._head_t_version = -1
+
+    # ---- reference helpers kept for API parity -------------------------------------------------
+    def setup_caches(self, max_batch_size: int) -> None:
+        """model.py:128-138: the reference uses this to obtain the causal-mask buffers; KV caches themselves are
+        not part of the training path and are not allocated."""
+        device = next(self.parameters()).device
+        self.register_buffer("backbone_causal_mask", _create_causal_mask(self.backbone.max_seq_len, device),
+                             persistent=False)
+        self.register_buffer("decoder_causal_mask", _create_causal_mask(self.args.audio_num_codebooks, device),
+                             persistent=False)
+
+    def reset_caches(self):
+        pass
+
+    def _index_causal_mask(self, mask: torch.Tensor, input_pos: torch.Tensor) -> torch.Tensor:
+        """Method form expected by compute_loss (utils.py:90) — a module-level function in the reference."""
+        return _index_causal_mask(mask, input_pos)
+
+    def _embed_audio(self, codebook: int, tokens: torch.Tensor) -> torch.Tensor:     # model.py:202-204
+        return self.audio_embeddings(tokens + codebook * self.args.audio_vocab_size)
+
+    def _embed_tokens(self, tokens: torch.Tensor) -> torch.Tensor:                   # model.py:206-217
+        """[B,S,33] -> [B,S,33,D], materialised.  API parity only (torch indexing = data movement); the training
+        forward never materialises this tensor: it uses the fused gather-sum kernel."""
+        C, V = self.args.audio_num_codebooks, self.args.audio_vocab_size
+        text = self.text_embeddings(tokens[:, :, -1]).unsqueeze(-2)
+        idx = tokens[:, :, :-1] + V * torch.arange(C, device=tokens.device)
+        audio = self.audio_embeddings(idx.view(-1)).reshape(tokens.size(0), tokens.size(1), C, -1)
+        return torch.cat([audio, text], dim=-2)
+
+    def generate_frame(self, *a, **k):
+        raise NotImplementedError("inference (generate_frame, model.py:140-195) is outside the B200 training path")
+
+    # ---- B200 training forward ---------------------------------------------------------------
+    def embed(self, tokens: torch.Tensor, tokens_mask: torch.Tensor) -> torch.Tensor:
+        """A2: fused gather + mask + 33-way sum -> bf16 [B,S,D]."""
+        return EmbedGatherSumFn.apply(tokens, tokens_mask, self.audio_embeddings.weight, self.text_embeddings.weight)
+
+    def _audio_head_t(self) -> torch.Tensor:
+        """[31, V, Dd] shadow of audio_head [31, Dd, V] (rows of V=2051 bf16 are not 16-byte aligned, so the native
+        layout cannot be a TMA operand); refreshed only when the parameter changed."""
+        ah = self.audio_head
+        if self._head_t is None or self._head_t_version != ah._version or self._head_t.device != ah.device:
+            self._head_t = ah.detach().transpose(1, 2).contiguous()
+            self._head_t_version = ah._version
+        return self._head_t
+
+    @staticmethod
+    def select_frames(tokens_mask: torch.Tensor, target_len: int, fraction: float = 1.0 / 16,
+                      generator: Optional[torch.Generator] = None) -> torch.Tensor:
+        """A8 (docs/reference/sesame_csm/training.md:58-62): per sample keep ceil(#audio/16) audio frames, uniformly
+        at random; returns int64 [N_sel, 2] of (b, p), p < min(S-1, T).  Runs on the host copy of the mask (the
+        data pipeline calls it before the H2D copy)."""
+        m = tokens_mask.detach().to("cpu")
+        B, S, W = m.shape
+        limit = min(S - 1, target_len)
+        out = []
+        for b in range(B):
+            cand = torch.nonzero(m[b, :limit, : W - 1].any(-1)).flatten()
+            if cand.numel() == 0:
+                continue
+            keep = max(1, math.ceil(cand.numel() * fraction))
+            sel = cand[torch.randperm(cand.numel(), generator=generator)[:keep]].sort().values
+            out.append(torch.stack([torch.full_like(sel, b), sel], dim=1))
+        return torch.cat(out, 0) if out else torch.zeros(0, 2, dtype=torch.int64)
+
+    def forward(self, tokens: torch.Tensor, tokens_mask: torch.Tensor,
+                target_audio_tokens: Optional[torch.Tensor] = None, *, frame_idx: Optional[torch.Tensor] = None,
+                decoder_frame_fraction: float = 1.0 / 16, semantic_weight: float = 100.0,
+                acoustic_weight: float = 1.0):
+        """tokens int64 [B,S,33], tokens_mask bool [B,S,33], target_audio_tokens int64 [B,T,32].
+
+        Returns (loss, {"semantic_loss", "acoustic_loss", "per_codebook_loss": fp32[32]}); with
+        target_audio_tokens=None returns the backbone hidden state bf16 [B,S,D].
+        """
+        if not tokens.is_cuda:
+            raise RuntimeError("csm_b200: Model.forward needs CUDA tensors (no CPU fallback)")
+        if self.codebook0_head.weight.dtype != BF16:
+            raise RuntimeError("csm_b200: the kernels compute in bf16; call model.to(torch.bfloat16) first")
+        B, S, W = tokens.shape
+        C, V = self.args.audio_num_codebooks, self.args.audio_vocab_size
+        h0 = self.embed(tokens, tokens_mask)
+        hb = self.backbone.run(h0)                               # [B,S,D] bf16 (final norm applied)
+        if target_audio_tokens is None:
+            return hb
+        T = target_audio_tokens.shape[1]
+        if T < S - 1:
+            raise RuntimeError(f"target_audio_tokens has {T} frames, need at least seq_len-1 = {S - 1}")
+        # ---- semantic term (utils.py:98-107): position p predicts targets[b,p,0], p < S-1, mean over B*(S-1)
+        tgt0 = torch.full((B, S), -1, dtype=torch.int64, device=tokens.device)
+        tgt0[:, : S - 1] = target_audio_tokens[:, : S - 1, 0]
+        sem, _ = LinearCEFn.apply(hb.view(B * S, -1), self.codebook0_head.weight, tgt0.view(-1), B * (S - 1))
+        per_cb = [sem.detach()]
+        # ---- acoustic term (A7/A8)
+        if frame_idx is None:
+            frame_idx = self.select_frames(tokens_mask, T, decoder_frame_fraction)
+        frame_idx = frame_idx.to(tokens.device)
+        if frame_idx.numel() > 0:
+            Ns = frame_idx.shape[0]
+            x = DecoderInputFn.apply(hb, self.audio_embeddings.weight, target_audio_tokens, frame_idx, C, V)
+            xp = LinearFn.apply(x.view(Ns * C, -1), self.projection.weight)
+            y = self.decoder.run(xp.view(Ns, C, -1))
+            codes = target_audio_tokens[frame_idx[:, 0], frame_idx[:, 1]].contiguous()      # [Ns, C] int64 gather
+            ac, rows = GroupedLinearCEFn.apply(y, self.audio_head, self._audio_head_t(), codes)
+            per_cb_ac = rows.mean(dim=1)
+        else:
+            ac = torch.zeros((), dtype=torch.float32, device=tokens.device)
+            per_cb_ac = torch.zeros(C - 1, dtype=torch.float32, device=tokens.device)
+        loss = semantic_weight * sem + acoustic_weight * ac
+        details: Dict[str, torch.Tensor] = {
+            "semantic_loss": sem, "acoustic_loss": ac,
+            "per_codebook_loss": torch.cat([per_cb[0].reshape(1), per_cb_ac.detach()])}
+        return loss, details

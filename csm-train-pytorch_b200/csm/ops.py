@@ -232,7 +232,7 @@ def linear_ce_fwd(h, w, targets, *, trans_w: bool = False, groups: int = 1, tgt_
     return loss, lse
 
 
-def linear_ce_bwd(h, w, targets, lse, grad_scale: float, *, dh: torch.Tensor, dw: Optional[torch.Tensor] = None,
+def linear_ce_bwd(h, w, targets, lse, grad_scale: float, *, dh: torch.Tensor, grad_scale_dev=None, dw: Optional[torch.Tensor] = None,
                   dw_accumulate: bool = False, trans_w: bool = False, groups: int = 1, tgt_row_stride: int = 1,
                   tgt_group_stride: int = 0, backend: Optional[int] = None):
     M, V, K, ldh, hgs, ldw, wgs = _ce_geometry(h, w, trans_w, groups)
@@ -244,7 +244,7 @@ def linear_ce_bwd(h, w, targets, lse, grad_scale: float, *, dh: torch.Tensor, dw
     else:
         lddh, dhgs = dh.stride(0), dh.stride(1)
     be = _backend_override if backend is None else backend
-    _lib.check(lib.csm_linear_ce_bwd(_p(h), _p(w), _p(targets), _p(lse), grad_scale, _p(dh), _p(dw),
+    _lib.check(lib.csm_linear_ce_bwd(_p(h), _p(w), _p(targets), _p(lse), grad_scale, _p(grad_scale_dev), _p(dh), _p(dw),
                                      1 if dw_accumulate else 0, M, V, K, groups, ldh, hgs, ldw, wgs,
                                      1 if trans_w else 0, tgt_row_stride, tgt_group_stride, lddh, dhgs, _p(ws),
                                      nbytes, be, _st()), "linear_ce_bwd")

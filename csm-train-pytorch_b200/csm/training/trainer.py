@@ -1,0 +1,195 @@
+"""``CSMTrainer`` — drop-in for /root/reference/src/csm/training/trainer.py:26-394 on the B200 kernels.
+
+Same constructor, ``prepare_optimizer`` (AdamW, lr x {backbone 0.1, decoder 1.0, embeddings 0.5, other 1.0} by name
+substring, trainer.py:123-173), ``train`` loop (grad accumulation, clip_grad_norm_, checkpoints, trainer.py:175-357)
+and ``_validate``.  Differences, all on purpose: no KV caches in training, the acoustic loss is real,
+``loss.item()`` is read once per optimiser step instead of every micro-batch (trainer.py:266 forces a sync), and the
+trainer is data-parallel when launched under torchrun (one process per GPU, NCCL all-reduce of gradients).
+"""
+from __future__ import annotations
+
+import time
+from pathlib import Path
+from typing import Dict, Optional
+
+import torch
+
+from ..models.model import Model, ModelArgs
+from . import dp
+from .utils import compute_loss, load_checkpoint, save_checkpoint, setup_logger
+
+
+def csm_1b_args() -> ModelArgs:                       # trainer.py:100-106
+    return ModelArgs(backbone_flavor="llama-1B", decoder_flavor="llama-100M", text_vocab_size=128256,
+                     audio_vocab_size=2051, audio_num_codebooks=32)
+
+
+def collate_variable_length(batch):
+    """Zero / False padding to the batch maximum — contract of data/training_data.py:379-408."""
+    S = max(b["input_tokens"].shape[0] for b in batch)
+    T = max(b["target_audio_tokens"].shape[0] for b in batch)
+    T = max(T, S)
+    W = batch[0]["input_tokens"].shape[1]
+    C = batch[0]["target_audio_tokens"].shape[1]
+    tok = torch.zeros(len(batch), S, W, dtype=torch.int64)
+    msk = torch.zeros(len(batch), S, W, dtype=torch.bool)
+    tgt = torch.zeros(len(batch), T, C, dtype=torch.int64)
+    for i, b in enumerate(batch):
+        s, t = b["input_tokens"].shape[0], b["target_audio_tokens"].shape[0]
+        tok[i, :s] = b["input_tokens"]
+        msk[i, :s] = b["input_masks"].bool()
+        tgt[i, :t] = b["target_audio_tokens"]
+    return {"input_tokens": tok, "input_masks": msk, "target_audio_tokens": tgt}
+
+
+def iterate_batches(dataset, batch_size: int, shuffle: bool, rank: int = 0, world: int = 1, seed: int = 0):
+    n = len(dataset)
+    order = torch.randperm(n, generator=torch.Generator().manual_seed(seed)).tolist() if shuffle else list(range(n))
+    order = order[rank::world]
+    for i in range(0, len(order), batch_size):
+        yield collate_variable_length([dataset[j] for j in order[i:i + batch_size]])
+
+
+class CSMTrainer:
+    def __init__(self, model_path: str, output_dir: str, device: str = "cuda", log_file: Optional[str] = None,
+                 learning_rate: float = 1e-5, backbone_lr_multiplier: float = 0.1,
+                 decoder_lr_multiplier: float = 1.0, embedding_lr_multiplier: float = 0.5,
+                 semantic_weight: float = 100.0, acoustic_weight: float = 1.0, weight_decay: float = 0.01):
+        self.model_path = model_path
+        self.output_dir = Path(output_dir)
+        self.output_dir.mkdir(parents=True, exist_ok=True)
+        self.rank, self.world, self.local_rank = dp.init_distributed()
+        self.device = f"cuda:{self.local_rank}" if (device == "cuda" and self.world > 1) else device
+        self.logger = setup_logger("csm_trainer", log_file or str(self.output_dir / "training.log"))
+        self.learning_rate = learning_rate
+        self.backbone_lr_multiplier = backbone_lr_multiplier
+        self.decoder_lr_multiplier = decoder_lr_multiplier
+        self.embedding_lr_multiplier = embedding_lr_multiplier
+        self.semantic_weight = semantic_weight
+        self.acoustic_weight = acoustic_weight
+        self.weight_decay = weight_decay
+        self.decoder_frame_fraction = 1.0 / 16
+        self.model = None
+        self.optimizer = None
+        self._sync = None
+        self._load_model()
+        self.epoch = 0
+        self.global_step = 0
+        self.best_loss = float("inf")
+
+    def _load_model(self):
+        if not self.model_path:                       # trainer.py:92-95: model injected later (tests)
+            self.logger.warning("Empty model path provided. Model will need to be set manually.")
+            return
+        if not self.model_path.endswith(".pt"):
+            raise ValueError("csm_b200 loads .pt state dicts (trainer.py:97-111); hub loading needs network access")
+        self.model = Model(csm_1b_args()).to(torch.bfloat16)
+        state = torch.load(self.model_path, map_location="cpu")
+        if "model" in state and "audio_head" not in state:
+            state = state["model"]
+        self.model.load_state_dict(state)
+        self.model = self.model.to(self.device)
+
+    def prepare_optimizer(self, freeze_backbone: bool = False, freeze_decoder: bool = False,
+                          freeze_embeddings: bool = False):
+        groups = {"backbone": [], "decoder": [], "embeddings": [], "other": []}
+        for name, p in self.model.named_parameters():
+            if freeze_backbone and "backbone" in name:
+                p.requires_grad = False
+            elif freeze_decoder and "decoder" in name:
+                p.requires_grad = False
+            elif freeze_embeddings and "embeddings" in name:
+                p.requires_grad = False
+            if p.requires_grad:
+                key = "backbone" if "backbone" in name else "decoder" if "decoder" in name else \
+                    "embeddings" if "embeddings" in name else "other"
+                groups[key].append(p)
+        total = sum(p.numel() for p in self.model.parameters() if p.requires_grad)
+        self.logger.info(f"Training with {total:,} trainable parameters")
+        lr = self.learning_rate
+        param_groups = [g for g in (
+            {"params": groups["backbone"], "lr": lr * self.backbone_lr_multiplier},
+            {"params": groups["decoder"], "lr": lr * self.decoder_lr_multiplier},
+            {"params": groups["embeddings"], "lr": lr * self.embedding_lr_multiplier},
+            {"params": groups["other"], "lr": lr}) if g["params"]]
+        on_cuda = next(self.model.parameters()).is_cuda
+        self.optimizer = torch.optim.AdamW(param_groups, weight_decay=self.weight_decay, fused=on_cuda)
+        trainable = [p for p in self.model.parameters() if p.requires_grad]
+        self._sync = dp.GradSynchronizer(trainable, bucket_bytes=64 << 20 if total > (32 << 20) else None)
+
+    def _to_device(self, batch) -> Dict[str, torch.Tensor]:
+        if "frame_idx" not in batch:                  # A8: chosen on the host copy, before the H2D copy
+            batch = dict(batch)
+            batch["frame_idx"] = Model.select_frames(batch["input_masks"], batch["target_audio_tokens"].shape[1],
+                                                     self.decoder_frame_fraction)
+        return {k: v.to(self.device, non_blocking=True) for k, v in batch.items()}
+
+    def train_micro_batch(self, batch, accumulation_steps: int = 1) -> torch.Tensor:
+        b = self._to_device(batch)
+        loss, _ = compute_loss(self.model, b["input_tokens"], b["input_masks"], b["target_audio_tokens"],
+                               self.semantic_weight, self.acoustic_weight, frame_idx=b["frame_idx"])
+        (loss / accumulation_steps).backward()
+        return loss.detach()
+
+    def optimizer_step(self, max_grad_norm: float = 1.0) -> None:
+        self._sync.finish()
+        if max_grad_norm and max_grad_norm > 0:
+            torch.nn.utils.clip_grad_norm_([p for p in self.model.parameters() if p.requires_grad], max_grad_norm)
+        self.optimizer.step()
+        self.optimizer.zero_grad(set_to_none=True)
+        self.global_step += 1
+
+    def train(self, train_dataset, val_dataset=None, batch_size: int = 2, accumulation_steps: int = 4,
+              epochs: int = 5, val_every: int = 100, save_every: int = 500, max_grad_norm: float = 1.0,
+              resume_from: Optional[str] = None):
+        if self.optimizer is None:
+            self.prepare_optimizer()
+        if resume_from:
+            meta = load_checkpoint(resume_from, self.model, self.optimizer, self.device)
+            self.epoch, self.global_step, self.best_loss = meta["epoch"], meta["global_step"], meta["loss"]
+        self.model.train()
+        avg_loss = float("nan")
+        for epoch in range(self.epoch, self.epoch + epochs):
+            t0 = time.time()
+            losses, window = [], []
+            for bi, batch in enumerate(iterate_batches(train_dataset, batch_size, True, self.rank, self.world,
+                                                       seed=epoch)):
+                window.append(self.train_micro_batch(batch, accumulation_steps))
+                if (bi + 1) % accumulation_steps == 0:
+                    self.optimizer_step(max_grad_norm)
+                    step_loss = float(torch.stack(window).mean())      # one D2H read per optimiser step
+                    losses.append(step_loss)
+                    window = []
+                    if val_dataset is not None and self.global_step % val_every == 0:
+                        val = self._validate(val_dataset, batch_size)
+                        self.logger.info(f"Epoch {epoch + 1}, Step {self.global_step}, Val Loss: {val:.6f}")
+                        if val < self.best_loss and self.rank == 0:
+                            self.best_loss = val
+                            save_checkpoint(self.model, self.optimizer, epoch + 1, self.global_step, val,
+                                            str(self.output_dir), "best")
+                    if self.global_step % save_every == 0 and self.rank == 0:
+                        save_checkpoint(self.model, self.optimizer, epoch + 1, self.global_step, step_loss,
+                                        str(self.output_dir))
+            avg_loss = sum(losses) / max(1, len(losses))
+            self.logger.info(f"Epoch {epoch + 1} completed in {time.time() - t0:.2f}s, Avg Loss: {avg_loss:.6f}")
+            if self.rank == 0:
+                save_checkpoint(self.model, self.optimizer, epoch + 1, self.global_step, avg_loss,
+                                str(self.output_dir), f"epoch_{epoch + 1}")
+            self.epoch = epoch + 1
+        if self.rank == 0:
+            save_checkpoint(self.model, self.optimizer, self.epoch, self.global_step, avg_loss,
+                            str(self.output_dir), "final")
+        return self.best_loss
+
+    def _validate(self, val_dataset, batch_size: int = 2) -> float:
+        self.model.eval()
+        total, n = 0.0, 0
+        with torch.no_grad():
+            for batch in iterate_batches(val_dataset, batch_size, False):
+                b = self._to_device(batch)
+                loss, _ = compute_loss(self.model, b["input_tokens"], b["input_masks"], b["target_audio_tokens"],
+                                       self.semantic_weight, self.acoustic_weight, frame_idx=b["frame_idx"])
+                total += float(loss)
+                n += 1
+        self.model.train()
+        return total / max(1, n)

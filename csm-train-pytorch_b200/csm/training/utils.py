@@ -1,0 +1,64 @@
+"""Training utilities — drop-in for /root/reference/src/csm/training/utils.py (PyTorch half).
+
+``compute_loss`` keeps the reference signature and return contract (utils.py:56-63,119) and delegates to
+``Model.forward`` (CUDA kernels).  Unlike the reference placeholder (utils.py:109-117) the acoustic term is real.
+Checkpoint helpers keep the reference's file format and naming (utils.py:526-574,864-895).
+"""
+from __future__ import annotations
+
+import logging
+import os
+from typing import Dict, Optional, Tuple
+
+import torch
+
+
+def setup_logger(name: str, log_file: Optional[str] = None, level: int = logging.INFO) -> logging.Logger:
+    logger = logging.getLogger(name)
+    logger.setLevel(level)
+    for h in logger.handlers[:]:
+        logger.removeHandler(h)
+    fmt = logging.Formatter("%(asctime)s - %(name)s - %(levelname)s - %(message)s")
+    ch = logging.StreamHandler()
+    ch.setLevel(level)
+    ch.setFormatter(fmt)
+    logger.addHandler(ch)
+    if log_file:
+        d = os.path.dirname(log_file)
+        if d:
+            os.makedirs(d, exist_ok=True)
+        fh = logging.FileHandler(log_file)
+        fh.setLevel(level)
+        fh.setFormatter(fmt)
+        logger.addHandler(fh)
+    return logger
+
+
+def compute_loss(model, input_tokens: torch.Tensor, input_masks: torch.Tensor, target_audio_tokens: torch.Tensor,
+                 semantic_weight: float = 100.0, acoustic_weight: float = 1.0, *,
+                 frame_idx: Optional[torch.Tensor] = None,
+                 decoder_frame_fraction: float = 1.0 / 16) -> Tuple[torch.Tensor, Dict[str, torch.Tensor]]:
+    """(total loss, {"semantic_loss", "acoustic_loss", "per_codebook_loss"}) — utils.py:56-119."""
+    return model(input_tokens, input_masks, target_audio_tokens, frame_idx=frame_idx,
+                 decoder_frame_fraction=decoder_frame_fraction, semantic_weight=semantic_weight,
+                 acoustic_weight=acoustic_weight)
+
+
+def save_checkpoint(model, optimizer, epoch: int, global_step: int, loss: float, save_dir: str,
+                    name: str = "checkpoint") -> str:
+    os.makedirs(save_dir, exist_ok=True)
+    payload = {"model": model.state_dict(), "optimizer": optimizer.state_dict() if optimizer is not None else None,
+               "epoch": epoch, "global_step": global_step, "loss": loss}
+    path = os.path.join(save_dir, f"{name}_epoch{epoch}_step{global_step}.pt")
+    torch.save(payload, path)
+    torch.save(payload, os.path.join(save_dir, f"{name}_latest.pt"))
+    return path
+
+
+def load_checkpoint(checkpoint_path: str, model, optimizer=None, device="cuda") -> Dict:
+    ckpt = torch.load(checkpoint_path, map_location=device)
+    model.load_state_dict(ckpt["model"])
+    if optimizer is not None and ckpt.get("optimizer") is not None:
+        optimizer.load_state_dict(ckpt["optimizer"])
+    return {"epoch": ckpt.get("epoch", 0), "global_step": ckpt.get("global_step", 0),
+            "loss": ckpt.get("loss", float("inf"))}

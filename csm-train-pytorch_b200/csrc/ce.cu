@@ -15,7 +15,7 @@ int linear_ce_tc_fwd(const void* H, const void* W, const int64_t* targets, float
                      int64_t V, int64_t K, int groups, int64_t ldh, int64_t hgs, int64_t ldw, int64_t wgs,
                      int transW, int64_t trs, int64_t tgs, void* ws, size_t ws_bytes, cudaStream_t st);
 int linear_ce_tc_bwd_dlogits(const void* H, const void* W, const int64_t* targets, const float* lse,
-                             float grad_scale, void* dlogits, int64_t ldd, int64_t M, int64_t V, int64_t K,
+                             float grad_scale, const float* grad_scale_dev, void* dlogits, int64_t ldd, int64_t M, int64_t V, int64_t K,
                              int64_t ldh, int64_t ldw, int transW, int64_t trs, cudaStream_t st);
 bool linear_ce_tc_supported(int64_t M, int64_t V, int64_t K, int64_t ldh, int64_t ldw, int transW,
                             const void* H, const void* W);
@@ -45,22 +45,22 @@ ce_rows_fwd_kernel(const float* __restrict__ logits, int64_t ldl, const int64_t*
   s = block_reduce(s, sm, false);
   if (threadIdx.x == 0) {
     const float L = mx + logf(s);
-    int64_t t = targets[r * tgt_stride];
-    t = t < 0 ? 0 : (t >= V ? V - 1 : t);
+    const int64_t t = targets[r * tgt_stride];
     lse[r] = L;
-    loss[r] = L - row[t];
+    loss[r] = (t < 0 || t >= V) ? 0.f : L - row[t];  // negative target == ignored row
   }
 }
 
 __global__ void __launch_bounds__(128)
 ce_rows_bwd_kernel(const float* __restrict__ logits, int64_t ldl, const int64_t* __restrict__ targets,
-                   int64_t tgt_stride, const float* __restrict__ lse, float gscale, bf16* __restrict__ dlogits,
-                   int64_t ldd, int64_t V) {
+                   int64_t tgt_stride, const float* __restrict__ lse, float gscale,
+                   const float* __restrict__ gscale_dev, bf16* __restrict__ dlogits, int64_t ldd, int64_t V) {
   const int64_t r = blockIdx.x;
   const float* row = logits + r * ldl;
   const float L = lse[r];
-  int64_t t = targets[r * tgt_stride];
-  t = t < 0 ? 0 : (t >= V ? V - 1 : t);
+  const int64_t t = targets[r * tgt_stride];
+  if (gscale_dev) gscale *= *gscale_dev;
+  if (t < 0 || t >= V) gscale = 0.f;
   for (int64_t c = threadIdx.x; c < ldd; c += blockDim.x) {
     float g = 0.f;
     if (c < V) g = gscale * (__expf(row[c] - L) - (c == t ? 1.f : 0.f));
@@ -84,7 +84,7 @@ ce_combine_kernel(const float4* __restrict__ part, int nt, float* __restrict__ l
   }
   const float L = mx + logf(s);
   lse[r] = L;
-  loss[r] = L - tl;
+  loss[r] = (tl == -INFINITY) ? 0.f : L - tl;  // no tile saw the target: ignored row (target < 0)
 }
 
 int ce_combine_launch(const void* part, int nt, float* loss, float* lse, int64_t rows, cudaStream_t st) {
@@ -139,7 +139,7 @@ extern "C" int csm_linear_ce_fwd(const void* H, const void* W, const int64_t* ta
 }
 
 extern "C" int csm_linear_ce_bwd(const void* H, const void* W, const int64_t* targets, const float* lse,
-                                 float grad_scale, void* dH, void* dW, int32_t dw_accumulate, int64_t M,
+                                 float grad_scale, const float* grad_scale_dev, void* dH, void* dW, int32_t dw_accumulate, int64_t M,
                                  int64_t V, int64_t K, int32_t groups, int64_t ldh, int64_t h_group_stride,
                                  int64_t ldw, int64_t w_group_stride, int32_t transW, int64_t tgt_row_stride,
                                  int64_t tgt_group_stride, int64_t lddh, int64_t dh_group_stride,
@@ -167,14 +167,14 @@ extern "C" int csm_linear_ce_bwd(const void* H, const void* W, const int64_t* ta
     const float* lg = lse + (int64_t)g * M;
     int rc;
     if (use_tc) {
-      rc = linear_ce_tc_bwd_dlogits(Hg, Wg, tg, lg, grad_scale, dlog, v8, M, V, K, ldh, ldw, transW,
+      rc = linear_ce_tc_bwd_dlogits(Hg, Wg, tg, lg, grad_scale, grad_scale_dev, dlog, v8, M, V, K, ldh, ldw, transW,
                                     tgt_row_stride, st);
       if (rc) return rc;
     } else {
       rc = gemm_dispatch(Hg, Wg, logits, nullptr, M, V, K, ldh, ldw, V, 0, 0, transW, CSM_DT_F32, 0, 1.f, nullptr,
                          nullptr, 0, 0, 0, CSM_GEMM_SIMT, st);
       if (rc) return rc;
-      ce_rows_bwd_kernel<<<(unsigned)M, 128, 0, st>>>(logits, V, tg, tgt_row_stride, lg, grad_scale, dlog, v8, V);
+      ce_rows_bwd_kernel<<<(unsigned)M, 128, 0, st>>>(logits, V, tg, tgt_row_stride, lg, grad_scale, grad_scale_dev, dlog, v8, V);
       CSM_CHECK_LAUNCH("ce_rows_bwd");
     }
     if (dH) {

@@ -31,7 +31,7 @@ struct GemmTcParams {
   // CE epilogues
   const int64_t* targets; int64_t tgt_row_stride, tgt_group_stride;
   float4* ce_part;          // [groups*M, num_n]
-  const float* lse; float gscale;
+  const float* lse; float gscale; const float* gscale_dev;
 };
 
 template <int BN> struct GemmCfg {
@@ -278,9 +278,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       } else {  // EPI_CE_DLOGITS: bf16 gscale * (softmax - onehot), zero beyond N up to ldc
         int64_t tgt = -1;
         float L = 0.f;
+        float gs = p.gscale;
+        if (p.gscale_dev) gs *= *p.gscale_dev;
         if (row_ok) {
           tgt = p.targets[(int64_t)g * p.tgt_group_stride + m * p.tgt_row_stride];
           L = p.lse[(int64_t)g * p.M + m];
+          if (tgt < 0 || tgt >= p.N) gs = 0.f;  // ignored row
         }
         bf16* crow = reinterpret_cast<bf16*>(p.C) + (int64_t)g * p.c_group_stride + m * p.ldc;
 #pragma unroll 1
@@ -295,7 +298,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
             const float pr = (n + i < p.N) ? __expf(__uint_as_float(v[i]) - L) : 0.f;
-            f[i] = p.gscale * (pr - ((n + i == tgt) ? 1.f : 0.f));
+            f[i] = gs * (pr - ((n + i == tgt) ? 1.f : 0.f));
           }
           if (n + 32 <= p.ldc) {
 #pragma unroll
@@ -501,7 +504,7 @@ int linear_ce_tc_fwd(const void* H, const void* W, const int64_t* targets, float
 }
 
 int linear_ce_tc_bwd_dlogits(const void* H, const void* W, const int64_t* targets, const float* lse,
-                             float grad_scale, void* dlogits, int64_t ldd, int64_t M, int64_t V, int64_t K,
+                             float grad_scale, const float* grad_scale_dev, void* dlogits, int64_t ldd, int64_t M, int64_t V, int64_t K,
                              int64_t ldh, int64_t ldw, int transW, int64_t trs, cudaStream_t st) {
   (void)transW;
   GemmTcOperands o{H, W, nullptr, nullptr, ldh, ldw, 0, 0, 0, 0, 0, 0, 0};
@@ -509,7 +512,7 @@ int linear_ce_tc_bwd_dlogits(const void* H, const void* W, const int64_t* target
   p.M = M; p.N = V; p.K = K; p.groups = 1;
   p.C = dlogits; p.ldc = ldd;
   p.targets = targets; p.tgt_row_stride = trs; p.tgt_group_stride = 0;
-  p.lse = lse; p.gscale = grad_scale;
+  p.lse = lse; p.gscale = grad_scale; p.gscale_dev = grad_scale_dev;
   return gemm_tc_run(o, p, EPI_CE_DLOGITS, st);
 }
 

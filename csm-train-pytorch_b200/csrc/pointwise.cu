@@ -151,8 +151,9 @@ rope_kernel(bf16* __restrict__ x, const float* __restrict__ cache, int64_t rows,
     float o[8];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      o[2 * j] = f[2 * j] * co[j] - f[2 * j + 1] * si[j];
-      o[2 * j + 1] = f[2 * j + 1] * co[j] + f[2 * j] * si[j];
+      // separate roundings (no FMA contraction): bit-identical to the fp32 torch formula of Llama3ScaledRoPE
+      o[2 * j] = __fsub_rn(__fmul_rn(f[2 * j], co[j]), __fmul_rn(f[2 * j + 1], si[j]));
+      o[2 * j + 1] = __fadd_rn(__fmul_rn(f[2 * j + 1], co[j]), __fmul_rn(f[2 * j], si[j]));
     }
     *reinterpret_cast<uint4*>(p) = pack8(o);
   }

@@ -137,10 +137,12 @@ int csm_linear_ce_fwd(const void* H, const void* W, const int64_t* targets, floa
                       int64_t ldw, int64_t w_group_stride, int32_t transW, int64_t tgt_row_stride,
                       int64_t tgt_group_stride, void* workspace, size_t workspace_bytes, int32_t backend,
                       csm_stream_t stream);
-/* dH_g (bf16, lddh / dh_group_stride) = grad_scale * (softmax - onehot) * W_g^T ; dW_g (nullable, bf16,
- * same layout as W, accumulated when dw_accumulate) = grad_scale * H_g^T (softmax - onehot). */
+/* dH_g (bf16, lddh / dh_group_stride) = s * (softmax - onehot) * W_g^T ; dW_g (nullable, bf16, same layout as W,
+ * accumulated when dw_accumulate) = s * H_g^T (softmax - onehot), with s = grad_scale * (grad_scale_dev ? *grad_scale_dev : 1)
+ * (the device scalar is the upstream autograd gradient, read on the device: no host sync).
+ * A negative target marks an ignored row (loss 0, zero gradient) like F.cross_entropy's ignore_index. */
 int csm_linear_ce_bwd(const void* H, const void* W, const int64_t* targets, const float* lse, float grad_scale,
-                      void* dH, void* dW, int32_t dw_accumulate, int64_t M, int64_t V, int64_t K,
+                      const float* grad_scale_dev, void* dH, void* dW, int32_t dw_accumulate, int64_t M, int64_t V, int64_t K,
                       int32_t groups, int64_t ldh, int64_t h_group_stride, int64_t ldw, int64_t w_group_stride,
                       int32_t transW, int64_t tgt_row_stride, int64_t tgt_group_stride, int64_t lddh,
                       int64_t dh_group_stride, void* workspace, size_t workspace_bytes, int32_t backend,

@@ -1,0 +1,158 @@
+"""Parity of the whole training step (Model.forward + backward through libcsm_b200) against the CPU oracle
+(oracle/csm_oracle.py, itself pinned bit-exactly to the reference's own code on the semantic path by
+tests/golden/make_golden.py).  Gates from BASELINE.json north_star: gather indices/masks bit-exact,
+per-codebook bf16 loss within 1e-2 relative, gradient cosine >= 0.999 per trainable tensor."""
+import os
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "c1_tiny.pt")
+LOSS_RTOL = 1e-2
+GRAD_COS = 0.999
+
+
+def _product_model(cfg_name):
+    from csm.models.model import Model, ModelArgs
+    from oracle import csm_oracle as O
+    cfg = O.CONFIGS[cfg_name]()
+    flav = {"tiny": ("tiny-backbone", "tiny-decoder"), "small": ("small-backbone", "small-decoder")}[cfg_name]
+    m = Model(ModelArgs(flav[0], flav[1], cfg.text_vocab_size, cfg.audio_vocab_size, cfg.audio_num_codebooks))
+    return m, cfg
+
+
+def _pair(cfg_name, device, lora, targets=None, r=8):
+    """(oracle bf16 on CPU, product bf16 on CUDA) with identical parameters."""
+    from csm.models import lora as plora
+    from oracle import csm_oracle as O
+    prod, cfg = _product_model(cfg_name)
+    orc = O.OracleModel(cfg)
+    O.init_weights(orc, 0)
+    orc = orc.to(torch.bfloat16)
+    prod = prod.to(torch.bfloat16)
+    if lora:
+        O.apply_lora(orc, r=r, alpha=16.0, target_modules=targets, seed=1)
+        plora.apply_lora(prod, r=r, alpha=16.0, target_modules=targets, seed=7)
+    prod.load_state_dict(orc.state_dict(), strict=True)
+    prod = prod.to(device)
+    return orc, prod, cfg
+
+
+def _run_both(orc, prod, cfg, B, S, device, seed=1234):
+    from oracle import csm_oracle as O
+    batch = O.synthetic_batch(cfg, B, S, seed=seed)
+    tok, msk, tgt, fidx = (batch[k] for k in ("input_tokens", "input_masks", "target_audio_tokens", "frame_idx"))
+    ol, od = O.oracle_forward(orc, tok, msk, tgt, fidx)
+    ol.backward()
+    pl, pd = prod(tok.to(device), msk.to(device), tgt.to(device), frame_idx=fidx.to(device))
+    pl.backward()
+    torch.cuda.synchronize()
+    return (ol.detach(), od), (pl.detach(), pd)
+
+
+def _check(orc, prod, o, p, min_cos=GRAD_COS):
+    (ol, od), (pl, pd) = o, p
+    assert abs(float(pl) - float(ol)) <= LOSS_RTOL * abs(float(ol)), (float(pl), float(ol))
+    ref = od["per_codebook_loss"].float()
+    got = pd["per_codebook_loss"].float().cpu()
+    rel = ((got - ref).abs() / ref.abs()).max().item()
+    assert rel <= LOSS_RTOL, f"per-codebook loss rel err {rel}"
+    og = {n: q.grad for n, q in orc.named_parameters() if q.grad is not None}
+    pg = {n: q.grad for n, q in prod.named_parameters() if q.grad is not None}
+    assert set(og) == set(pg), set(og) ^ set(pg)
+    worst = (1.0, None)
+    for n in og:
+        a, b = og[n].float().flatten(), pg[n].float().cpu().flatten()
+        if float(a.norm()) == 0.0 and float(b.norm()) == 0.0:
+            continue
+        c = float(F.cosine_similarity(a, b, dim=0))
+        if c < worst[0]:
+            worst = (c, n)
+    assert worst[0] >= min_cos, f"gradient cosine {worst[0]:.5f} for {worst[1]}"
+    return worst
+
+
+def test_c1_tiny_lora_matches_oracle_and_golden(cuda):
+    """BASELINE config 1: tiny model, LoRA r=8 q/v, batch 2."""
+    orc, prod, cfg = _pair("tiny", cuda, lora=True)
+    o, p = _run_both(orc, prod, cfg, 2, 32, cuda)
+    _check(orc, prod, o, p)
+    g = torch.load(GOLD)["lora_bf16"]
+    # the committed golden was produced by the same oracle code: it guards the oracle against drift ...
+    assert torch.allclose(o[1]["per_codebook_loss"], g["per_codebook_loss"], rtol=2e-3, atol=0)
+    # ... and pins the CUDA path directly to the committed numbers
+    got = p[1]["per_codebook_loss"].cpu()
+    assert ((got - g["per_codebook_loss"]).abs() / g["per_codebook_loss"]).max() <= LOSS_RTOL
+    named = dict(prod.named_parameters())
+    for n, gg in g["grads"].items():
+        mine = named[n].grad.float().cpu().flatten()
+        assert float(F.cosine_similarity(mine, gg.float().flatten(), dim=0)) >= GRAD_COS, n
+
+
+def test_c1_tiny_gather_indices_and_masks_bit_exact(cuda):
+    from csm import ops
+    gold = torch.load(GOLD)
+    orc, prod, cfg = _pair("tiny", cuda, lora=False)
+    tok, msk = gold["input_tokens"].to(cuda), gold["input_masks"].to(cuda)
+    h, idx, eff, status = ops.embed_gather_sum(tok, msk, prod.audio_embeddings.weight, prod.text_embeddings.weight,
+                                               debug=True)
+    assert torch.equal(idx.cpu(), gold["gather_idx"])                       # tokens + c*V, reference model.py:210-212
+    assert torch.equal(eff.bool().cpu(), gold["input_masks"])
+    assert int(status.item()) == 0
+    # causal mask helper == the reference's indexed tril mask (golden made by the reference's own function)
+    prod.backbone.max_seq_len = tok.shape[1]
+    prod.setup_caches(2)
+    S = tok.shape[1]
+    pos = torch.arange(S, device=cuda).unsqueeze(0).repeat(tok.shape[0], 1)
+    cm = prod._index_causal_mask(prod.backbone_causal_mask, pos)
+    assert torch.equal(cm.cpu(), gold["ref_causal_mask"])
+    # values: bit-exact against the oracle's (== reference's) formula evaluated on the same bf16 tables
+    oh = (orc._embed_tokens(gold["input_tokens"]) * gold["input_masks"].unsqueeze(-1)).sum(dim=2)
+    assert torch.equal(h.cpu(), oh)
+
+
+def test_tiny_full_finetune_grads(cuda):
+    orc, prod, cfg = _pair("tiny", cuda, lora=False)
+    o, p = _run_both(orc, prod, cfg, 2, 32, cuda)
+    _check(orc, prod, o, p, min_cos=0.99)      # bf16 oracle vs bf16 kernels on 32-wide layers: rounding-noise floor
+
+
+@pytest.mark.parametrize("targets,r", [(None, 8), (["q_proj", "k_proj", "v_proj", "o_proj", "gate_proj", "up_proj",
+                                                  "down_proj"], 16)])
+def test_small_lora_tensor_core_path(cuda, targets, r):
+    """head_dim 64/128, GQA 4:1, V=2051: runs the tcgen05 GEMM (+LoRA tail), fused CE and attention kernels.
+    (None, 8) is config 2's adapter set; the second case is config 4's (r=16 on all seven projections)."""
+    orc, prod, cfg = _pair("small", cuda, lora=True, targets=targets, r=r)
+    o, p = _run_both(orc, prod, cfg, 2, 128, cuda)
+    _check(orc, prod, o, p)
+
+
+def test_small_full_finetune_tensor_core_path(cuda):
+    orc, prod, cfg = _pair("small", cuda, lora=False)
+    o, p = _run_both(orc, prod, cfg, 2, 128, cuda)
+    _check(orc, prod, o, p, min_cos=0.99)
+
+
+def test_compute_loss_contract(cuda):
+    """The reference's own assertion on this path (test_training.py:209-236): scalar, positive, has semantic_loss."""
+    from csm.training.utils import compute_loss
+    orc, prod, cfg = _pair("tiny", cuda, lora=False)
+    B, S = 2, 5
+    tok = torch.randint(0, 100, (B, S, 33), device=cuda)
+    msk = torch.ones(B, S, 33, dtype=torch.bool, device=cuda)
+    tgt = torch.randint(0, 100, (B, S, 32), device=cuda)
+    loss, comp = compute_loss(prod, tok, msk, tgt)
+    assert isinstance(loss, torch.Tensor) and loss.dim() == 0 and loss.item() > 0
+    assert "semantic_loss" in comp and isinstance(comp["semantic_loss"], torch.Tensor)
+    assert "acoustic_loss" in comp
+
+
+def test_no_cpu_fallback():
+    from csm.models.model import Model, ModelArgs
+    m = Model(ModelArgs("tiny-backbone", "tiny-decoder", 1000, 200, 32)).to(torch.bfloat16)
+    tok = torch.zeros(1, 4, 33, dtype=torch.int64)
+    with pytest.raises(RuntimeError):
+        m(tok, torch.ones(1, 4, 33, dtype=torch.bool), torch.zeros(1, 4, 32, dtype=torch.int64))
