@@ -24,6 +24,21 @@ def set_gemm_backend(b: int) -> None:
     _backend_override = b
 
 
+_gemm_prof = None   # when a list: (flops, start_event, end_event) per GEMM launch (bench.py roofline leg)
+
+
+def gemm_profile_start() -> None:
+    global _gemm_prof
+    _gemm_prof = []
+
+
+def gemm_profile_stop():
+    """-> (total flops, total ms, launches) over the GEMM launches since gemm_profile_start(); caller synchronises."""
+    global _gemm_prof
+    rec, _gemm_prof = _gemm_prof or [], None
+    return (sum(f for f, _, _ in rec), sum(a.elapsed_time(b) for _, a, b in rec), len(rec))
+
+
 def _p(t: Optional[torch.Tensor]):
     return None if t is None else t.data_ptr()
 
@@ -166,12 +181,18 @@ def gemm(a, b, *, trans_a: bool = False, trans_b: bool = False, out: Optional[to
         assert a2.stride(1) == 1 and b2.stride(1) == 1
     lib = _lib.load()
     be = _backend_override if backend is None else backend
+    if _gemm_prof is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
     _lib.check(lib.csm_gemm_bf16(_p(a), _p(b), _p(out), _p(residual), M, N, K, a.stride(0), b.stride(0),
                                  out.stride(0), residual.stride(0) if residual is not None else 0,
                                  1 if trans_a else 0, 1 if trans_b else 0, 1 if out.dtype == torch.float32 else 0,
                                  1 if accumulate else 0, alpha, _p(a2), _p(b2), K2,
                                  a2.stride(0) if a2 is not None else 0, b2.stride(0) if b2 is not None else 0,
                                  be, _st()), "gemm_bf16")
+    if _gemm_prof is not None:
+        e1.record()
+        _gemm_prof.append((2.0 * M * N * (K + K2), e0, e1))
     return out
 
 
