@@ -5,6 +5,7 @@ HERE="$(cd "$(dirname "${BASH_SOURCE[0]}")" && pwd)"
 NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
 OUT="$HERE/libcsm_b200.so"
 SRCS=("$HERE"/csrc/*.cu)
+rm -f "$HERE"/build/stubs_v1.o
 mkdir -p "$HERE/build"
 OBJS=()
 pids=()

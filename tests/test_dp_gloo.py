@@ -1,0 +1,78 @@
+"""world_size-2 gloo tests (CPU) of the data-parallel gradient exchange (csm/training/dp.py)."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, bucket_bytes, q):
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, os.path.join(root, "csm-train-pytorch_b200"))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    from csm.training import dp
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        torch.manual_seed(0)
+        model = torch.nn.Sequential(torch.nn.Linear(8, 16), torch.nn.ReLU(), torch.nn.Linear(16, 4))
+        model[0].bias.requires_grad_(False)                   # a frozen parameter must be ignored
+        sync = dp.GradSynchronizer(model.parameters(), bucket_bytes=bucket_bytes)
+        for step in range(2):                                 # two steps: hooks/buckets must reset
+            x = torch.full((3, 8), float(rank + 1 + step))
+            model(x).sum().backward()
+            sync.finish()
+            local = [p.grad.clone() for p in model.parameters() if p.requires_grad]
+            # reference: average of both ranks' gradients computed locally
+            ref_model = torch.nn.Sequential(torch.nn.Linear(8, 16), torch.nn.ReLU(), torch.nn.Linear(16, 4))
+            ref_model.load_state_dict(model.state_dict())
+            acc = None
+            for r in range(world):
+                ref_model.zero_grad()
+                ref_model(torch.full((3, 8), float(r + 1 + step))).sum().backward()
+                gs = [p.grad.clone() for n, p in ref_model.named_parameters() if n != "0.bias"]
+                acc = gs if acc is None else [a + g for a, g in zip(acc, gs)]
+            for got, want in zip(local, acc):
+                assert torch.allclose(got, want / world, atol=1e-6)
+            model.zero_grad()
+        q.put((rank, "ok"))
+    except Exception as e:  # noqa: BLE001
+        q.put((rank, repr(e)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("bucket_bytes", [None, 256])
+def test_grad_synchronizer_world2(bucket_bytes):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, bucket_bytes, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(res) == [(0, "ok"), (1, "ok")], res
+
+
+def test_single_process_is_noop():
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, os.path.join(root, "csm-train-pytorch_b200"))
+    from csm.training import dp
+    lin = torch.nn.Linear(4, 4)
+    lin(torch.ones(2, 4)).sum().backward()
+    g = lin.weight.grad.clone()
+    dp.GradSynchronizer(lin.parameters()).finish()
+    assert torch.equal(lin.weight.grad, g)

@@ -1,0 +1,199 @@
+"""CPU tests of the host side: the C-ABI library loads and exports every declared symbol (no compute calls),
+the Python mirror keeps the reference's interface, data contract and persistence formats."""
+import inspect
+import os
+import re
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "csm_b200.h")
+
+
+def _declared_symbols():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(csm_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_header_symbol():
+    from csm import _lib
+    lib = _lib.load()
+    syms = _declared_symbols()
+    assert len(syms) >= 20
+    for s in syms:
+        assert hasattr(lib, s), f"{s} declared in include/csm_b200.h but not exported"
+    assert set(_lib.SIGNATURES) == set(syms), set(_lib.SIGNATURES) ^ set(syms)
+    assert lib.csm_abi_version() == 1
+    assert isinstance(lib.csm_last_error(), bytes)
+    # sizing helpers are pure host functions
+    assert lib.csm_attn_bwd_workspace_bytes(2, 64, 4, 1, 64) >= 2 * 4 * 64 * 4
+    assert lib.csm_linear_ce_workspace_bytes(128, 2051, 1024, 31) > 0
+
+
+def test_missing_library_fails_loudly(monkeypatch, tmp_path):
+    from csm import _lib
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "nope.so"))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        _lib.load()
+
+
+def test_model_state_dict_keys_match_reference_contract():
+    from csm.models.model import Model, ModelArgs
+    from oracle import csm_oracle as O
+    m = Model(ModelArgs("tiny-backbone", "tiny-decoder", 1000, 200, 32))
+    om = O.OracleModel(O.cfg_tiny())             # key set verified against the reference in test_oracle.py
+    assert set(m.state_dict()) == set(om.state_dict())
+    for k, v in om.state_dict().items():
+        assert m.state_dict()[k].shape == v.shape, k
+    assert m.audio_head.shape == (31, 16, 200)
+    # CSM-1B flavours: dims of model.py:11-42 without allocating them
+    from csm.models import model as mm
+    with torch.device("meta"):
+        bb, dec = mm.llama3_2_1B(), mm.llama3_2_100M()
+    assert (len(bb.layers), bb.num_heads, bb.num_kv_heads, bb.embed_dim, bb.head_dim) == (16, 32, 8, 2048, 64)
+    assert (len(dec.layers), dec.num_heads, dec.num_kv_heads, dec.embed_dim, dec.head_dim) == (4, 8, 2, 1024, 128)
+    assert bb.layers[0].mlp.w1.weight.shape == (8192, 2048)
+    n = sum(p.numel() for p in bb.parameters()) + sum(p.numel() for p in dec.parameters())
+    assert abs(n - 1.084e9) < 0.01e9
+
+
+def test_reference_helpers_present():
+    from csm.models import model as mm
+    m = mm.Model(mm.ModelArgs("tiny-backbone", "tiny-decoder", 1000, 200, 32))
+    tok = torch.randint(0, 100, (2, 5, 33))
+    e = m._embed_tokens(tok)
+    assert e.shape == (2, 5, 33, 32)
+    assert torch.equal(e[:, :, 3], m.audio_embeddings(tok[:, :, 3] + 3 * 200))
+    assert torch.equal(m._embed_audio(3, tok[:, :, 3]), e[:, :, 3])
+    mask = mm._create_causal_mask(6, torch.device("cpu"))
+    pos = torch.arange(5).unsqueeze(0).repeat(2, 1)
+    assert torch.equal(m._index_causal_mask(mask, pos), mask[pos])          # method form (fixes utils.py:90)
+    assert torch.equal(mm._index_causal_mask(mask, pos)[0, 2], torch.tensor([1, 1, 1, 0, 0, 0], dtype=torch.bool))
+
+
+def test_api_signatures_match_reference():
+    from csm.training.lora_trainer import CSMLoRATrainer
+    from csm.training.trainer import CSMTrainer
+    from csm.training.utils import compute_loss, load_checkpoint, save_checkpoint
+    p = list(inspect.signature(compute_loss).parameters)
+    assert p[:6] == ["model", "input_tokens", "input_masks", "target_audio_tokens", "semantic_weight",
+                     "acoustic_weight"]                                        # utils.py:56-63
+    sig = inspect.signature(compute_loss)
+    assert sig.parameters["semantic_weight"].default == 100.0 and sig.parameters["acoustic_weight"].default == 1.0
+    p = list(inspect.signature(CSMTrainer.__init__).parameters)[1:]
+    assert p == ["model_path", "output_dir", "device", "log_file", "learning_rate", "backbone_lr_multiplier",
+                 "decoder_lr_multiplier", "embedding_lr_multiplier", "semantic_weight", "acoustic_weight",
+                 "weight_decay"]                                               # trainer.py:29-42
+    p = list(inspect.signature(CSMTrainer.train).parameters)[1:]
+    assert p == ["train_dataset", "val_dataset", "batch_size", "accumulation_steps", "epochs", "val_every",
+                 "save_every", "max_grad_norm", "resume_from"]                 # trainer.py:175-186
+    p = list(inspect.signature(CSMLoRATrainer.__init__).parameters)[1:14]
+    assert p == ["model_path", "output_dir", "log_file", "learning_rate", "semantic_weight", "acoustic_weight",
+                 "weight_decay", "lora_r", "lora_alpha", "lora_dropout", "target_modules", "target_layers",
+                 "lora_use_bias"]                                              # lora_trainer.py:32-48
+    d = inspect.signature(CSMLoRATrainer.__init__).parameters
+    assert (d["learning_rate"].default, d["lora_r"].default, d["lora_alpha"].default) == (1e-4, 8, 16.0)
+    p = list(inspect.signature(CSMLoRATrainer.train).parameters)[1:]
+    assert p == ["train_dataset", "val_dataset", "batch_size", "epochs", "val_every", "save_every", "max_grad_norm",
+                 "resume_from"]                                                # mlx_trainer.py:733-743
+    for name in ("prepare_optimizer", "train_step", "save_model", "load_lora_weights"):
+        assert callable(getattr(CSMLoRATrainer, name))
+    assert list(inspect.signature(save_checkpoint).parameters) == ["model", "optimizer", "epoch", "global_step",
+                                                                   "loss", "save_dir", "name"]
+    assert list(inspect.signature(load_checkpoint).parameters)[:3] == ["checkpoint_path", "model", "optimizer"]
+
+
+def test_lora_names_counts_and_freezing():
+    from csm.models import lora
+    from csm.models.model import Model, ModelArgs
+    m = Model(ModelArgs("tiny-backbone", "tiny-decoder", 1000, 200, 32))
+    names = lora.apply_lora(m, r=8, alpha=16.0, seed=0)
+    assert len(names) == 2 * (2 + 1)                                          # q,v x (2 backbone + 1 decoder layers)
+    sd = lora.lora_state_dict(m)
+    assert "backbone.layers.0.attn.q_proj.lora_A" in sd and "decoder.layers.0.attn.v_proj.lora_B" in sd
+    assert sd["backbone.layers.0.attn.q_proj.lora_A"].shape == (8, 32)
+    assert sd["backbone.layers.0.attn.q_proj.lora_B"].shape == (32, 8)
+    assert float(sd["backbone.layers.0.attn.q_proj.lora_B"].abs().sum()) == 0.0   # B = 0 init (lora.py:66)
+    trainable = [n for n, p in m.named_parameters() if p.requires_grad]
+    assert sorted(trainable) == sorted(sd)
+    assert m.backbone.layers[0].attn.q_proj.lora_scaling == 2.0               # alpha / r
+    # CSM-1B r=8 q/v: 958 464 trainable parameters
+    n = 16 * (8 * 2048 + 2048 * 8 + 8 * 2048 + 512 * 8) + 4 * (8 * 1024 + 1024 * 8 + 8 * 1024 + 256 * 8)
+    assert n == 958_464
+    with pytest.raises(ValueError):
+        lora.apply_lora(m, target_modules=["nope"])
+    m2 = Model(ModelArgs("tiny-backbone", "tiny-decoder", 1000, 200, 32))
+    names = lora.apply_lora(m2, r=4, target_modules=["q_proj", "k_proj", "v_proj", "o_proj", "gate_proj", "up_proj",
+                                                     "down_proj"], target_layers=[0])
+    assert len(names) == 7 * 2
+
+
+def test_synthetic_batch_contract_and_frame_selection():
+    from csm.data.synthetic import synthetic_batch
+    from csm.models.model import Model
+    from oracle import csm_oracle as O
+    b = synthetic_batch(1000, 200, 32, 2, 64, seed=7)
+    ob = O.synthetic_batch(O.cfg_tiny(), 2, 64, seed=7)
+    for k in b:
+        assert torch.equal(b[k], ob[k]), k                                    # product generator == oracle generator
+    tok, msk, tgt, fi = b["input_tokens"], b["input_masks"], b["target_audio_tokens"], b["frame_idx"]
+    assert tok.shape == (2, 64, 33) and tok.dtype == torch.int64
+    assert msk.shape == (2, 64, 33) and msk.dtype == torch.bool
+    assert tgt.shape == (2, 64, 32)
+    assert not msk[:, -4:].any() and (tok[:, -4:] == 0).all()                 # padding frames: zeros / False
+    assert msk[:, :16, 32].all() and not msk[:, :16, :32].any()               # text frames
+    assert fi.shape[1] == 2 and int(fi[:, 1].max()) < 63
+    sel = Model.select_frames(msk, 64, 1 / 16, torch.Generator().manual_seed(0))
+    assert sel.shape == fi.shape
+    for bb, p in sel.tolist():
+        assert msk[bb, p, :32].any() and p < 63                               # only audio frames, p < S-1
+    assert Model.select_frames(torch.zeros(1, 8, 33, dtype=torch.bool), 8).shape == (0, 2)
+
+
+def test_collate_pads_like_reference():
+    from csm.training.trainer import collate_variable_length, iterate_batches
+    items = [{"input_tokens": torch.ones(s, 33, dtype=torch.int64), "input_masks": torch.ones(s, 33, dtype=torch.bool),
+              "target_audio_tokens": torch.ones(s, 32, dtype=torch.int64)} for s in (3, 5)]
+    out = collate_variable_length(items)
+    assert out["input_tokens"].shape == (2, 5, 33)
+    assert out["input_tokens"][0, 3:].sum() == 0 and not out["input_masks"][0, 3:].any()   # zero / False padding
+    assert out["target_audio_tokens"].shape == (2, 5, 32)
+    r0 = [b["input_tokens"].shape[0] for b in iterate_batches(items * 4, 2, True, rank=0, world=2, seed=1)]
+    r1 = [b["input_tokens"].shape[0] for b in iterate_batches(items * 4, 2, True, rank=1, world=2, seed=1)]
+    assert sum(r0) + sum(r1) == 8                                              # ranks partition the dataset
+
+
+def test_checkpoint_roundtrip_format(tmp_path):
+    from csm.models.model import Model, ModelArgs
+    from csm.training.utils import load_checkpoint, save_checkpoint
+    m = Model(ModelArgs("tiny-backbone", "tiny-decoder", 1000, 200, 32))
+    with torch.no_grad():
+        m.audio_head.normal_()
+    opt = torch.optim.AdamW(m.parameters(), lr=1e-3)
+    path = save_checkpoint(m, opt, 2, 17, 1.5, str(tmp_path))
+    assert os.path.basename(path) == "checkpoint_epoch2_step17.pt"             # utils.py:545
+    assert os.path.exists(tmp_path / "checkpoint_latest.pt")
+    ck = torch.load(path)
+    assert set(ck) == {"model", "optimizer", "epoch", "global_step", "loss"}
+    m2 = Model(ModelArgs("tiny-backbone", "tiny-decoder", 1000, 200, 32))
+    meta = load_checkpoint(path, m2, None, "cpu")
+    assert meta == {"epoch": 2, "global_step": 17, "loss": 1.5}
+    assert torch.equal(m2.audio_head, m.audio_head)
+
+
+def test_lora_trainer_rejects_unimplemented_options(tmp_path):
+    from csm.training.lora_trainer import CSMLoRATrainer
+    with pytest.raises(NotImplementedError):
+        CSMLoRATrainer("", str(tmp_path), lora_dropout=0.1)
+    with pytest.raises(NotImplementedError):
+        CSMLoRATrainer("", str(tmp_path), lora_use_bias=True)
+
+
+def test_rope_table_matches_oracle():
+    from csm.models.rope import build_rope_cache
+    from oracle.torchtune_shim import Llama3ScaledRoPE
+    for hd in (8, 64, 128):
+        assert torch.equal(build_rope_cache(hd, 4096, 500000.0, 32.0), Llama3ScaledRoPE(hd, 4096, 500000.0, 32.0).cache)
