@@ -112,8 +112,95 @@ def _acc(grads, i, g):
     grads[i] = g if grads[i] is None else ops.add_bf16(grads[i], g)
 
 
+def _packed_weight(mods, cache):
+    """One [sum(out_i), in] tensor holding the weights of several projections that share their input; the modules'
+    ``weight.data`` become row-slice views of it, so optimiser updates and ``load_state_dict`` write straight into the
+    fused operand.  Re-packed if the views were broken (e.g. by ``model.to(device)``)."""
+    key = tuple(id(m) for m in mods)
+    fused = cache.get(key)
+    ok = fused is not None and fused.device == mods[0].weight.device and fused.dtype == mods[0].weight.dtype
+    if ok:
+        off = 0
+        for m in mods:
+            w = m.weight
+            if w.data_ptr() != fused.data_ptr() + off * fused.stride(0) * fused.element_size() or \
+                    w.stride(0) != fused.stride(0):
+                ok = False
+                break
+            off += w.shape[0]
+    if not ok:
+        with torch.no_grad():
+            fused = torch.cat([m.weight.detach() for m in mods], dim=0).contiguous()
+            off = 0
+            for m in mods:
+                n = m.weight.shape[0]
+                m.weight.data = fused[off:off + n]
+                off += n
+        cache[key] = fused
+    return fused
+
+
+class _Group:
+    """Several bias-free projections of the SAME input as one GEMM: y = x [W_0; W_1; ..]^T  (q/k/v, gate/up).
+    LoRA adapters on any member ride in the same GEMM through the extra K block: t = x [A_0; A_1; ..]^T and a
+    block-diagonal [(s_0 B_0) 0; 0 (s_1 B_1)] tail operand."""
+
+    def __init__(self, mods, index_of, cache):
+        self.mods = mods
+        self.W = _packed_weight(mods, cache)
+        self.iw = [index_of[id(m.weight)] for m in mods]
+        self.offs, o = [], 0
+        for m in mods:
+            self.offs.append(o)
+            o += m.weight.shape[0]
+        self.n_out = o
+        self.lora = [(j, m) for j, m in enumerate(mods) if getattr(m, "lora_A", None) is not None]
+        self.A_cat = self.B_bd = None
+        if self.lora:
+            R = sum(m.lora_A.shape[0] for _, m in self.lora)
+            if R > 64:
+                raise RuntimeError("fused LoRA group: total rank must be <= 64")
+            self.A_cat = torch.cat([m.lora_A.detach() for _, m in self.lora], dim=0)            # [R, in]
+            self.B_bd = torch.zeros(self.n_out, R, dtype=self.W.dtype, device=self.W.device)      # [N, R]
+            self.slots, ro = [], 0
+            for j, m in self.lora:
+                r = m.lora_A.shape[0]
+                self.B_bd[self.offs[j]:self.offs[j] + m.weight.shape[0], ro:ro + r] = \
+                    m.lora_B.detach() * float(m.lora_scaling)
+                self.slots.append((j, m, ro, r, index_of[id(m.lora_A)], index_of[id(m.lora_B)]))
+                ro += r
+
+    def fwd(self, x):
+        if not self.lora:
+            return ops.gemm(x, self.W), None
+        t = ops.gemm(x, self.A_cat)                                    # [N, R]
+        return ops.gemm(x, self.W, a2=t, b2=self.B_bd), t
+
+    def bwd(self, dy, x, t, grads, need):
+        if any(need[i] for i in self.iw):
+            dW = ops.gemm(dy, x, trans_a=True, trans_b=True)          # [n_out, in] in one GEMM
+            for j, m in enumerate(self.mods):
+                if need[self.iw[j]]:
+                    _acc(grads, self.iw[j], dW[self.offs[j]:self.offs[j] + m.weight.shape[0]])
+        if not self.lora:
+            return ops.gemm(dy, self.W, trans_b=True)
+        dt = ops.gemm(dy, self.B_bd, trans_b=True)                     # dy (sB)_bd   [N, R]
+        if any(need[iB] for *_, iB in self.slots):
+            dB = ops.gemm(dy, t, trans_a=True, trans_b=True)          # dy^T t       [n_out, R]
+        if any(need[iA] for *_, iA, _ in self.slots):
+            dA = ops.gemm(dt, x, trans_a=True, trans_b=True)          # dt^T x       [R, in]
+        for j, m, ro, r, iA, iB in self.slots:
+            if need[iB]:
+                blk = dB[self.offs[j]:self.offs[j] + m.weight.shape[0], ro:ro + r]
+                _acc(grads, iB, (blk * float(m.lora_scaling)).contiguous())
+            if need[iA]:
+                _acc(grads, iA, dA[ro:ro + r])
+        return ops.gemm(dy, self.W, trans_b=True, a2=dt, b2=self.A_cat)
+
+
 class StackFn(Function):
-    """torchtune TransformerDecoder body (layers + final norm) — forward saves what backward needs, nothing more."""
+    """torchtune TransformerDecoder body (layers + final norm) — forward saves what backward needs, nothing more.
+    Per layer: 4 GEMMs forward (fused qkv, o, fused gate/up, down), residual adds in the GEMM epilogues."""
 
     @staticmethod
     def forward(ctx, x, stack, *params):
@@ -124,27 +211,28 @@ class StackFn(Function):
             raise ValueError(f"seq_len ({S}) of input tensor should be smaller than max_seq_len ({stack.max_seq_len})")
         cache = stack.rope_cache(x.device)
         index_of = {id(p): i for i, p in enumerate(params)}
+        nq, nkv = H * hd, KV * hd
         cur = x.reshape(N, D).contiguous()
         saved = []
         for layer in stack.layers:
             a = layer.attn
-            lq, lk, lv, lo = (_Lin(m, index_of) for m in (a.q_proj, a.k_proj, a.v_proj, a.output_proj))
-            l1, l3, l2 = (_Lin(m, index_of) for m in (layer.mlp.w1, layer.mlp.w3, layer.mlp.w2))
+            gqkv = _Group([a.q_proj, a.k_proj, a.v_proj], index_of, stack._packed)
+            g13 = _Group([layer.mlp.w1, layer.mlp.w3], index_of, stack._packed)
+            lo, l2 = _Lin(a.output_proj, index_of), _Lin(layer.mlp.w2, index_of)
+            I = layer.mlp.w1.weight.shape[0]
             xn, rstd1 = ops.rmsnorm(cur, layer.sa_norm.scale, eps)
-            q, tq = lq.fwd(xn)
-            k, tk = lk.fwd(xn)
-            v, tv = lv.fwd(xn)
+            qkv, tqkv = gqkv.fwd(xn)
+            q, k, v = qkv[:, :nq], qkv[:, nq:nq + nkv], qkv[:, nq + nkv:]
             ops.rope_(q, cache, S, H, hd)
             ops.rope_(k, cache, S, KV, hd)
             o, lse = ops.attention_fwd(q, k, v, B, S, H, KV, hd)
             h, to = lo.fwd(o, residual=cur)
             hn, rstd2 = ops.rmsnorm(h, layer.mlp_norm.scale, eps)
-            g, t1 = l1.fwd(hn)
-            u, t3 = l3.fwd(hn)
-            act = ops.swiglu(g, u)
+            gu, t13 = g13.fwd(hn)
+            act = ops.swiglu(gu[:, :I], gu[:, I:])
             out, t2 = l2.fwd(act, residual=h)
-            saved.append((cur, rstd1, xn, q, k, v, o, lse, h, rstd2, hn, g, u, act, (tq, tk, tv, to, t1, t3, t2),
-                          (lq, lk, lv, lo, l1, l3, l2), layer))
+            saved.append((cur, rstd1, xn, qkv, o, lse, h, rstd2, hn, gu, act, (tqkv, to, t13, t2),
+                          (gqkv, lo, g13, l2), layer))
             cur = out
         y, rstd_f = ops.rmsnorm(cur, stack.norm.scale, eps)
         ctx.saved = saved
@@ -161,6 +249,7 @@ class StackFn(Function):
         B, S, D = ctx.geom
         N = B * S
         H, KV, hd = stack.num_heads, stack.num_kv_heads, stack.head_dim
+        nq, nkv = H * hd, KV * hd
         cache = stack.rope_cache(dy.device)
         need = list(ctx.needs_input_grad[2:])
         grads: List[Optional[torch.Tensor]] = [None] * ctx.nparams
@@ -177,23 +266,25 @@ class StackFn(Function):
 
         xf, rstd_f = ctx.final
         dcur = norm_bwd(dy.reshape(N, D).contiguous(), xf, stack.norm, rstd_f, None)
-        for (x, rstd1, xn, q, k, v, o, lse, h, rstd2, hn, g, u, act, ts, lins, layer) in reversed(ctx.saved):
-            tq, tk, tv, to, t1, t3, t2 = ts
-            lq, lk, lv, lo, l1, l3, l2 = lins
+        for (x, rstd1, xn, qkv, o, lse, h, rstd2, hn, gu, act, ts, lins, layer) in reversed(ctx.saved):
+            tqkv, to, t13, t2 = ts
+            gqkv, lo, g13, l2 = lins
+            I = gu.shape[1] // 2
             # ---- MLP: out = h + w2(silu(w1 hn) * w3 hn)
             dact = l2.bwd(dcur, act, t2, grads, need)
-            dg, du = ops.swiglu_bwd(dact, g, u)
-            dhn = l1.bwd(dg, hn, t1, grads, need)
-            l3.bwd(du, hn, t3, grads, need, dx_out=dhn, accumulate=True)
+            dgu = torch.empty_like(gu)
+            ops.swiglu_bwd(dact, gu[:, :I], gu[:, I:], dgate=dgu[:, :I], dup=dgu[:, I:])
+            dhn = g13.bwd(dgu, hn, t13, grads, need)
             dh = norm_bwd(dhn, h, layer.mlp_norm, rstd2, dcur)
             # ---- attention: h = x + wo(attn(rope(wq xn), rope(wk xn), wv xn))
             do = lo.bwd(dh, o, to, grads, need)
-            dq, dk, dv = ops.attention_bwd(q, k, v, o, lse, do, B, S, H, KV, hd)
+            q, k, v = qkv[:, :nq], qkv[:, nq:nq + nkv], qkv[:, nq + nkv:]
+            dqkv = torch.empty_like(qkv)
+            dq, dk, dv = dqkv[:, :nq], dqkv[:, nq:nq + nkv], dqkv[:, nq + nkv:]
+            ops.attention_bwd(q, k, v, o, lse, do, B, S, H, KV, hd, dq=dq, dk=dk, dv=dv)
             ops.rope_(dq, cache, S, H, hd, inverse=True)
             ops.rope_(dk, cache, S, KV, hd, inverse=True)
-            dxn = lq.bwd(dq, xn, tq, grads, need)
-            lk.bwd(dk, xn, tk, grads, need, dx_out=dxn, accumulate=True)
-            lv.bwd(dv, xn, tv, grads, need, dx_out=dxn, accumulate=True)
+            dxn = gqkv.bwd(dqkv, xn, tqkv, grads, need)
             dcur = norm_bwd(dxn, x, layer.sa_norm, rstd1, dh)
         ctx.saved = None
         dx = dcur.view(B, S, D) if ctx.needs_input_grad[0] else None

@@ -80,6 +80,7 @@ class TransformerDecoder(nn.Module):
             for _ in range(num_layers)])
         self.norm = RMSNorm(embed_dim, norm_eps)
         self._rope = {}
+        self._packed = {}          # fused qkv / gate-up weight storage (csm/autograd.py::_packed_weight)
 
     def rope_cache(self, device) -> torch.Tensor:
         key = (str(device), self.max_seq_len)

@@ -69,6 +69,16 @@ int gemm_dispatch(const void* A, const void* B, void* C, const void* R, int64_t 
   if (tc_ok && backend != CSM_GEMM_SIMT)
     return gemm_tc_launch(A, B, C, R, M, N, K, lda, ldb, ldc, ldr, transA, transB, c_dtype, accumulate, alpha, A2,
                           B2, A2 ? K2 : 0, lda2, ldb2, stream);
+  if (backend != CSM_GEMM_SIMT && (double)M * (double)N * (double)K > 1e9) {
+    // a large GEMM on the scalar kernel is a performance bug, never silent: say why (first few times only)
+    static std::atomic<int> warned{0};
+    if (warned.fetch_add(1) < 8)
+      fprintf(stderr,
+              "[csm_b200] warning: GEMM M=%lld N=%lld K=%lld (transA=%d transB=%d) runs on the scalar kernel: "
+              "A=%p lda=%lld B=%p ldb=%lld A2=%p lda2=%lld B2=%p ldb2=%lld K2=%lld\n",
+              (long long)M, (long long)N, (long long)K, transA, transB, A, (long long)lda, B, (long long)ldb, A2,
+              (long long)lda2, B2, (long long)ldb2, (long long)K2);
+  }
   return gemm_simt_launch(A, B, C, R, M, N, K, lda, ldb, ldc, ldr, transA, transB, c_dtype, accumulate, alpha, A2,
                           B2, K2, lda2, ldb2, stream);
 }

@@ -451,8 +451,9 @@ bool gemm_tc_supported(const void* A, const void* B, const void* C, const void* 
                        const void* A2, const void* B2, int64_t K2, int64_t lda2, int64_t ldb2) {
   (void)C; (void)R; (void)ldc; (void)ldr; (void)c_dtype; (void)transA; (void)transB;
   if (M < 1 || N < 1 || K < 16) return false;
-  // below one tile in every dimension the scalar kernel is the right tool (tiny test model)
-  if (M * N < 64 * 64 || K < 64) return false;
+  // tiny problems (the tiny test model) are the scalar kernel's job; a small output with a long reduction
+  // (LoRA dA / dB: [r x in] = dt^T x over thousands of rows) still belongs on the tensor cores
+  if (K < 64 || (double)M * (double)N * (double)K < (double)(1 << 21)) return false;
   if (!tma_ok(A, lda) || !tma_ok(B, ldb)) return false;
   if (A2 && (!tma_ok(A2, lda2) || !tma_ok(B2, ldb2) || K2 < 1 || K2 > 64)) return false;
   if (M >= (1ll << 31) || N >= (1ll << 31) || K >= (1ll << 31)) return false;
