@@ -296,12 +296,14 @@ def main():
                "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e}
 
     # ---- roofline of the dominant kernel (tcgen05 GEMM): CUDA events around every GEMM launch of two more steps
+    # (every rank runs the two steps — they contain the gradient all-reduce — only rank 0 instruments them)
     roof = None
     if rank == 0:
         ops.gemm_profile_start()
-        for i in range(2):
-            step(resident[i % n_batches])
-        torch.cuda.synchronize()
+    for i in range(2):
+        step(resident[i % n_batches])
+    torch.cuda.synchronize()
+    if rank == 0:
         flops, gms, n_g = ops.gemm_profile_stop()
         peaks = {}
         try:

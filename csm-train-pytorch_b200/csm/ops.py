@@ -39,6 +39,11 @@ def gemm_profile_stop():
     return (sum(f for f, _, _ in rec), sum(a.elapsed_time(b) for _, a, b in rec), len(rec))
 
 
+def set_attn_backend(b: int) -> None:
+    """Test hook: 0 auto, 1 scalar, 2 mma.sync, 3 tcgen05 forward."""
+    _lib.load().csm_set_attn_backend(b)
+
+
 def _p(t: Optional[torch.Tensor]):
     return None if t is None else t.data_ptr()
 

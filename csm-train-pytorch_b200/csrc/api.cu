@@ -50,6 +50,15 @@ int attn_bwd_mma_launch(const void*, const void*, const void*, const void*, cons
                         void*, void*, float*, int, int, int, int, int, int64_t, int64_t, int64_t, int64_t, int64_t,
                         int64_t, int64_t, float, cudaStream_t);
 
+bool attn_tc_supported(int S, int hd, int64_t ldq, int64_t ldk, int64_t ldv, int64_t ldo, const void* q, const void* k,
+                       const void* v, const void* o);
+int attn_fwd_tc_launch(const void*, const void*, const void*, void*, float*, int, int, int, int, int64_t, int64_t,
+                       int64_t, int64_t, float, cudaStream_t);
+int attn_bwd_tc_launch(const void*, const void*, const void*, const void*, const float*, const void*, void*, void*,
+                       void*, float*, int, int, int, int, int64_t, int64_t, int64_t, int64_t, int64_t, int64_t, int64_t,
+                       float, cudaStream_t);
+static std::atomic<int> g_attn_backend{0};  // 0 auto, 1 scalar, 2 mma.sync, 3 tcgen05 (forward)
+
 int gemm_dispatch(const void* A, const void* B, void* C, const void* R, int64_t M, int64_t N, int64_t K,
                   int64_t lda, int64_t ldb, int64_t ldc, int64_t ldr, int transA, int transB, int c_dtype,
                   int accumulate, float alpha, const void* A2, const void* B2, int64_t K2, int64_t lda2,
@@ -88,6 +97,7 @@ int gemm_dispatch(const void* A, const void* B, void* C, const void* R, int64_t 
 using namespace csm;
 
 extern "C" int csm_abi_version(void) { return CSM_ABI_VERSION; }
+extern "C" void csm_set_attn_backend(int32_t backend) { g_attn_backend.store(backend); }
 extern "C" const char* csm_last_error(void) { return g_err; }
 extern "C" int64_t csm_launch_count(void) { return g_launches.load(); }
 
@@ -117,7 +127,12 @@ extern "C" int csm_attn_causal_gqa_fwd(const void* q, const void* k, const void*
                   head_dim <= 128,
               CSM_ERR_SHAPE, "attn_fwd: bad shape B=%d S=%d H=%d KV=%d hd=%d", batch, seq, heads, kv_heads, head_dim);
   if (batch == 0) return CSM_OK;
-  if (attn_mma_supported(head_dim, ldq, ldk, ldv, ldo))
+  const int be = g_attn_backend.load();
+  if ((be == 0 || be == 3) && attn_tc_supported(seq, head_dim, ldq, ldk, ldv, ldo, q, k, v, o))
+    return attn_fwd_tc_launch(q, k, v, o, lse, batch, seq, heads, kv_heads, ldq, ldk, ldv, ldo, scale,
+                              as_stream(stream));
+  CSM_REQUIRE(be != 3, CSM_ERR_SHAPE, "attn_fwd: shape not supported by the tcgen05 kernel (hd=64, seq>=128)");
+  if (be != 1 && attn_mma_supported(head_dim, ldq, ldk, ldv, ldo))
     return attn_fwd_mma_launch(q, k, v, o, lse, batch, seq, heads, kv_heads, head_dim, ldq, ldk, ldv, ldo, scale,
                                as_stream(stream));
   return attn_fwd_simt_launch(q, k, v, o, lse, batch, seq, heads, kv_heads, head_dim, ldq, ldk, ldv, ldo, scale,
@@ -143,7 +158,11 @@ extern "C" int csm_attn_causal_gqa_bwd(const void* q, const void* k, const void*
   CSM_REQUIRE(workspace && workspace_bytes >= csm_attn_bwd_workspace_bytes(batch, seq, heads, kv_heads, head_dim),
               CSM_ERR_SHAPE, "attn_bwd: workspace too small");
   float* delta = reinterpret_cast<float*>(workspace);
-  if (attn_mma_supported(head_dim, ldq, ldk, ldv, ldo))
+  const int be = g_attn_backend.load();
+  if ((be == 0 || be == 3) && attn_tc_supported(seq, head_dim, ldq, ldk, ldv, ldo, q, k, v, o))
+    return attn_bwd_tc_launch(q, k, v, o, lse, dout, dq, dk, dv, delta, batch, seq, heads, kv_heads, ldq, ldk, ldv, ldo,
+                              lddq, lddk, lddv, scale, as_stream(stream));
+  if (g_attn_backend.load() != 1 && attn_mma_supported(head_dim, ldq, ldk, ldv, ldo))
     return attn_bwd_mma_launch(q, k, v, o, lse, dout, dq, dk, dv, delta, batch, seq, heads, kv_heads, head_dim, ldq,
                                ldk, ldv, ldo, lddq, lddk, lddv, scale, as_stream(stream));
   return attn_bwd_simt_launch(q, k, v, o, lse, dout, dq, dk, dv, delta, batch, seq, heads, kv_heads, head_dim, ldq,

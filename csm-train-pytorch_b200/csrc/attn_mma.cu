@@ -440,6 +440,15 @@ attn_bwd_dkdv_mma_kernel(const bf16* __restrict__ q, const bf16* __restrict__ k,
 
 }  // namespace
 
+int attn_delta_launch(const void* o, const void* dout, float* delta, int B, int S, int H, int64_t ldo,
+                      cudaStream_t st) {
+  const int64_t rows = (int64_t)B * H * S;
+  attn_delta_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>((const bf16*)o, (const bf16*)dout, delta, B, S, H, ldo,
+                                                                ldo);
+  CSM_CHECK_LAUNCH("attn_delta");
+  return CSM_OK;
+}
+
 bool attn_mma_supported(int hd, int64_t ldq, int64_t ldk, int64_t ldv, int64_t ldo) {
   return hd == HD && ldq % 8 == 0 && ldk % 8 == 0 && ldv % 8 == 0 && ldo % 8 == 0;
 }

@@ -1,0 +1,637 @@
+// K5 on the 5th-gen tensor cores: causal GQA flash-attention FORWARD for head_dim 64 (CSM-1B backbone).
+//   warp 0     : TMA producer — Q tile once, then K_j / V_j tiles (128 keys x 64) into a 2-stage ring
+//   warp 1     : tcgen05.mma issuer — S_j = Q K_j^T (128x128, fp32 in TMEM, double buffered) and
+//                PV_j = P_j V_j (128x64, V consumed MN-major straight from its row-major tile)
+//   warps 2..5 : softmax — one query row per thread (row == TMEM lane, so no shuffles): two passes over the S row
+//                with tcgen05.ld (max, then exp2/sum), P_j written as bf16 into 128B-swizzled smem (the A operand
+//                of the PV MMA), running output kept in registers and updated from the PV_j tile one block later,
+//                so the tensor pipe computes S_{j+1} and PV_j while the softmax of the next block runs.
+#include "tc_common.cuh"
+
+namespace csm {
+
+using namespace tc;
+
+namespace {
+
+constexpr int TQ = 128, TK = 128, THD = 64;
+constexpr int kAttnThreads = 192;
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kLn2 = 0.6931471805599453f;
+
+constexpr int SM_Q = 0;
+constexpr int SM_K = SM_Q + TQ * THD * 2;                 // 16 KB
+constexpr int SM_V = SM_K + 2 * TK * THD * 2;             // + 32 KB
+constexpr int SM_P = SM_V + 2 * TK * THD * 2;             // + 32 KB
+constexpr int SM_BAR = SM_P + 2 * TQ * TK * 2;            // + 64 KB
+constexpr int kAttnSmem = SM_BAR + 256 + 1024;
+
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__global__ void __launch_bounds__(kAttnThreads, 1)
+attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                   const __grid_constant__ CUtensorMap tmV, bf16* __restrict__ o, float* __restrict__ lse, int S,
+                   int H, int KV, int64_t ldo, float scale_log2) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SM_BAR);
+  uint64_t* q_full = bars;            // 1
+  uint64_t* kv_full = bars + 1;       // 2
+  uint64_t* kv_empty = bars + 3;      // 2
+  uint64_t* s_full = bars + 5;        // 2
+  uint64_t* p_full = bars + 7;        // 2 (128 arrivals)
+  uint64_t* pv_full = bars + 9;       // 2
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 11);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int qb = gridDim.x - 1 - blockIdx.x;  // longest rows first
+  const int h = blockIdx.y, b = blockIdx.z;
+  const int kvh = h / (H / KV);
+  const int q0 = qb * TQ;
+  const int nblk = qb + 1;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+    mbar_init(q_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&kv_full[i], 1);
+      mbar_init(&kv_empty[i], 1);
+      mbar_init(&s_full[i], 1);
+      mbar_init(&p_full[i], 128);
+      mbar_init(&pv_full[i], 1);
+    }
+    mbar_fence_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  constexpr uint32_t COL_S = 0, COL_PV = 256;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(q_full, TQ * THD * 2);
+      tma_load_3d(smem + SM_Q, &tmQ, q_full, h * THD, q0, b);
+      for (int j = 0; j < nblk; ++j) {
+        const int st = j & 1;
+        mbar_wait(&kv_empty[st], ((j >> 1) & 1) ^ 1);
+        mbar_expect_tx(&kv_full[st], 2 * TK * THD * 2);
+        tma_load_3d(smem + SM_K + st * (TK * THD * 2), &tmK, &kv_full[st], kvh * THD, j * TK, b);
+        tma_load_3d(smem + SM_V + st * (TK * THD * 2), &tmV, &kv_full[st], kvh * THD, j * TK, b);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = make_idesc_bf16(TQ, TK, 0, 0);    // S = Q K^T : both K-major
+      constexpr uint32_t idesc_pv = make_idesc_bf16(TQ, THD, 0, 1);  // PV = P V  : V is MN-major ([key][hd] rows)
+      const uint32_t sq = smem_u32(smem + SM_Q);
+      auto issue_s = [&](int j) {
+        const int st = j & 1;
+        const uint32_t sk = smem_u32(smem + SM_K + st * (TK * THD * 2));
+        const uint64_t ad = make_smem_desc(sq, 16, 1024), bd = make_smem_desc(sk, 16, 1024);
+#pragma unroll
+        for (int kk = 0; kk < THD / 16; ++kk)
+          umma_bf16(tmem_base + COL_S + st * TK, ad + (uint64_t)((kk * 32) >> 4), bd + (uint64_t)((kk * 32) >> 4),
+                    idesc_s, kk ? 1u : 0u);
+        umma_commit(&s_full[st]);
+      };
+      mbar_wait(q_full, 0);
+      mbar_wait(&kv_full[0], 0);
+      tc_fence_after();
+      issue_s(0);
+      for (int j = 0; j < nblk; ++j) {
+        const int st = j & 1;
+        if (j + 1 < nblk) {
+          mbar_wait(&kv_full[st ^ 1], ((j + 1) >> 1) & 1);
+          tc_fence_after();
+          issue_s(j + 1);  // S buffer st^1 was drained before p_full(j-1) completed (waited last iteration)
+        }
+        mbar_wait(&p_full[st], (j >> 1) & 1);
+        tc_fence_after();
+        const uint32_t sp = smem_u32(smem + SM_P + st * (TQ * TK * 2));
+        const uint32_t sv = smem_u32(smem + SM_V + st * (TK * THD * 2));
+#pragma unroll
+        for (int kk = 0; kk < TK / 16; ++kk) {
+          // P: two 64-key swizzle atoms of 16 KB; inside an atom the K advance is 32 B.  V: 16 key-rows x 128 B.
+          const uint64_t ad = make_smem_desc(sp + (kk >> 2) * (TQ * 64 * 2) + (kk & 3) * 32, 16, 1024);
+          const uint64_t bd = make_smem_desc(sv + kk * 16 * 128, 64 * TK * 2, 1024);
+          umma_bf16(tmem_base + COL_PV + st * THD, ad, bd, idesc_pv, kk ? 1u : 0u);
+        }
+        umma_commit(&pv_full[st]);
+        umma_commit(&kv_empty[st]);
+      }
+    }
+  } else {
+    const int quad = warp & 3;
+    const int r = quad * 32 + lane;           // row inside the tile == TMEM lane
+    const int qi = q0 + r;                    // query index inside the sequence
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16);
+    float m = -INFINITY, l = 0.f, corr_prev = 1.f;
+    float oacc[THD];
+#pragma unroll
+    for (int i = 0; i < THD; ++i) oacc[i] = 0.f;
+
+    auto fold = [&](int j, float corr) {      // oacc = oacc * corr + PV_j
+      const int st = j & 1;
+      mbar_wait(&pv_full[st], (j >> 1) & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int c = 0; c < THD; c += 32) {
+        uint32_t v[32];
+        __syncwarp();
+        tmem_ld32(lane_addr + COL_PV + st * THD + c, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) oacc[c + i] = oacc[c + i] * corr + __uint_as_float(v[i]);
+      }
+    };
+
+    for (int j = 0; j < nblk; ++j) {
+      const int st = j & 1;
+      const bool diag = (j == nblk - 1);
+      const int kbase = j * TK;
+      mbar_wait(&s_full[st], (j >> 1) & 1);
+      tc_fence_after();
+      const uint32_t s_addr = lane_addr + COL_S + st * TK;
+      // pass 1: row max
+      float mx = m;
+#pragma unroll 1
+      for (int c = 0; c < TK; c += 32) {
+        uint32_t v[32];
+        __syncwarp();
+        tmem_ld32(s_addr + c, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          float x = __uint_as_float(v[i]) * scale_log2;
+          if (diag && (kbase + c + i > qi)) x = -INFINITY;
+          mx = fmaxf(mx, x);
+        }
+      }
+      const float corr = exp2f(m - mx);
+      m = mx;
+      // pass 2: p = exp2(s - m), row sum, bf16 P tile into swizzled smem
+      float rs = 0.f;
+      uint8_t* prow = smem + SM_P + st * (TQ * TK * 2) + r * 128;
+#pragma unroll 1
+      for (int c = 0; c < TK; c += 32) {
+        uint32_t v[32];
+        __syncwarp();
+        tmem_ld32(s_addr + c, v);
+        tmem_ld_wait();
+        float p[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          float x = __uint_as_float(v[i]) * scale_log2 - m;
+          if (diag && (kbase + c + i > qi)) x = -INFINITY;
+          p[i] = exp2f(x);
+          rs += p[i];
+        }
+        uint8_t* atom = prow + (c >> 6) * (TQ * 64 * 2);
+        const int c16 = (c & 63) >> 3;        // first 16-byte chunk of this 32-column group inside the atom
+#pragma unroll
+        for (int q4 = 0; q4 < 4; ++q4) {
+          uint4 w;
+          w.x = pack_bf16(p[q4 * 8 + 0], p[q4 * 8 + 1]); w.y = pack_bf16(p[q4 * 8 + 2], p[q4 * 8 + 3]);
+          w.z = pack_bf16(p[q4 * 8 + 4], p[q4 * 8 + 5]); w.w = pack_bf16(p[q4 * 8 + 6], p[q4 * 8 + 7]);
+          *reinterpret_cast<uint4*>(atom + (((c16 + q4) ^ (r & 7)) << 4)) = w;
+        }
+      }
+      l = l * corr + rs;
+      fence_async_smem();                     // generic-proxy smem writes -> visible to the tensor core (async proxy)
+      tc_fence_before();
+      mbar_arrive(&p_full[st]);
+      if (j > 0) fold(j - 1, corr_prev);
+      corr_prev = corr;
+    }
+    fold(nblk - 1, corr_prev);
+    if (qi < S) {
+      const float inv = 1.f / l;
+      bf16* op = o + ((int64_t)b * S + qi) * ldo + (int64_t)h * THD;
+#pragma unroll
+      for (int c = 0; c < THD; c += 8) {
+        uint4 w;
+        w.x = pack_bf16(oacc[c + 0] * inv, oacc[c + 1] * inv); w.y = pack_bf16(oacc[c + 2] * inv, oacc[c + 3] * inv);
+        w.z = pack_bf16(oacc[c + 4] * inv, oacc[c + 5] * inv); w.w = pack_bf16(oacc[c + 6] * inv, oacc[c + 7] * inv);
+        *reinterpret_cast<uint4*>(op + c) = w;
+      }
+      lse[((int64_t)b * H + h) * S + qi] = m * kLn2 + logf(l);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+
+// =====================================================================================================================
+// Backward on tcgen05.  Two kernels that each own their output rows (no atomics, deterministic):
+//   dQ kernel   : CTA = 128 queries of one head; per 128-key block  S = Q K^T, dP = dO V^T  (TMEM)  ->
+//                 dS = P o (dP - delta) * scale (bf16, swizzled smem)  ->  dQ += dS K  accumulated in TMEM.
+//   dKdV kernel : CTA = 128 keys of one kv head; per (q head of the group, 128-query block)  S^T = K Q^T,
+//                 dP^T = V dO^T  ->  P^T, dS^T (smem)  ->  dV += P^T dO,  dK += dS^T Q  accumulated in TMEM.
+// The Q / dO / K / V tiles are loaded once per use by TMA as [rows][64] 128B-swizzled tiles and serve BOTH as a
+// K-major operand (rows = M or N, hd = K) and as an MN-major B operand (hd = N, rows = K): same bytes, two descriptors.
+// 8 compute warps: warp w and w+4 share a TMEM lane quadrant and split the 128 columns, so no row reductions are
+// needed (lse and delta come from the forward / the delta pre-pass).
+constexpr int kBwdThreads = 320;  // warp0 TMA, warp1 MMA, warps 2..9 compute
+
+constexpr int DQ_Q = 0;                              // 16 KB  Q tile
+constexpr int DQ_DO = DQ_Q + TQ * THD * 2;           // 16 KB  dO tile
+constexpr int DQ_K = DQ_DO + TQ * THD * 2;           // 2 x 16 KB
+constexpr int DQ_V = DQ_K + 2 * TK * THD * 2;        // 2 x 16 KB
+constexpr int DQ_DS = DQ_V + 2 * TK * THD * 2;       // 32 KB  dS tile (A operand)
+constexpr int DQ_BAR = DQ_DS + TQ * TK * 2;
+constexpr int kDqSmem = DQ_BAR + 256 + 1024;
+
+__device__ __forceinline__ void store_row_chunk32(uint8_t* tile, int r, int col0, const float* f) {
+  // 32 consecutive columns [col0, col0+32) of row r into a [128 x 128] bf16 A-operand tile made of two
+  // 64-column 128B-swizzled atoms of 16 KB each
+  uint8_t* atom = tile + (col0 >> 6) * (128 * 64 * 2) + r * 128;
+  const int c16 = (col0 & 63) >> 3;
+#pragma unroll
+  for (int q4 = 0; q4 < 4; ++q4) {
+    uint4 w;
+    w.x = pack_bf16(f[q4 * 8 + 0], f[q4 * 8 + 1]); w.y = pack_bf16(f[q4 * 8 + 2], f[q4 * 8 + 3]);
+    w.z = pack_bf16(f[q4 * 8 + 4], f[q4 * 8 + 5]); w.w = pack_bf16(f[q4 * 8 + 6], f[q4 * 8 + 7]);
+    *reinterpret_cast<uint4*>(atom + (((c16 + q4) ^ (r & 7)) << 4)) = w;
+  }
+}
+
+// D[128 x 64] (+)= A[128 x 128 (two swizzle atoms)] * B where B is a [128 rows x 64] tile used MN-major
+__device__ __forceinline__ void issue_ak_bmn(uint32_t d_tmem, uint32_t a_smem, uint32_t b_smem, bool accumulate_first) {
+  constexpr uint32_t idesc = make_idesc_bf16(128, THD, 0, 1);
+#pragma unroll
+  for (int kk = 0; kk < 128 / 16; ++kk) {
+    const uint64_t ad = make_smem_desc(a_smem + (kk >> 2) * (128 * 64 * 2) + (kk & 3) * 32, 16, 1024);
+    const uint64_t bd = make_smem_desc(b_smem + kk * 16 * 128, 64 * 128 * 2, 1024);
+    umma_bf16(d_tmem, ad, bd, idesc, (accumulate_first || kk) ? 1u : 0u);
+  }
+}
+// D[128 x 128] = A[128 x 64] * B[128 x 64]^T, both K-major tiles
+__device__ __forceinline__ void issue_nt_128(uint32_t d_tmem, uint32_t a_smem, uint32_t b_smem) {
+  constexpr uint32_t idesc = make_idesc_bf16(128, 128, 0, 0);
+  const uint64_t ad = make_smem_desc(a_smem, 16, 1024), bd = make_smem_desc(b_smem, 16, 1024);
+#pragma unroll
+  for (int kk = 0; kk < THD / 16; ++kk)
+    umma_bf16(d_tmem, ad + (uint64_t)((kk * 32) >> 4), bd + (uint64_t)((kk * 32) >> 4), idesc, kk ? 1u : 0u);
+}
+
+__global__ void __launch_bounds__(kBwdThreads, 1)
+attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                      const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmDO,
+                      const float* __restrict__ lse, const float* __restrict__ delta, bf16* __restrict__ dq, int S,
+                      int H, int KV, int64_t lddq, float scale) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + DQ_BAR);
+  uint64_t* q_full = bars;          // Q + dO landed
+  uint64_t* kv_full = bars + 1;     // [2]
+  uint64_t* kv_empty = bars + 3;    // [2]
+  uint64_t* s_full = bars + 5;      // S and dP ready in TMEM
+  uint64_t* ds_full = bars + 6;     // dS tile written (256 arrivals)
+  uint64_t* acc_full = bars + 7;    // dQ accumulator final
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int qb = gridDim.x - 1 - blockIdx.x;
+  const int h = blockIdx.y, b = blockIdx.z;
+  const int kvh = h / (H / KV);
+  const int q0 = qb * TQ;
+  const int nblk = qb + 1;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV); tma_prefetch_desc(&tmDO);
+    mbar_init(q_full, 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
+    mbar_init(s_full, 1);
+    mbar_init(ds_full, 256);
+    mbar_init(acc_full, 1);
+    mbar_fence_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  constexpr uint32_t COL_S = 0, COL_DP = 128, COL_DQ = 256;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(q_full, 2 * TQ * THD * 2);
+      tma_load_3d(smem + DQ_Q, &tmQ, q_full, h * THD, q0, b);
+      tma_load_3d(smem + DQ_DO, &tmDO, q_full, h * THD, q0, b);
+      for (int j = 0; j < nblk; ++j) {
+        const int st = j & 1;
+        mbar_wait(&kv_empty[st], ((j >> 1) & 1) ^ 1);
+        mbar_expect_tx(&kv_full[st], 2 * TK * THD * 2);
+        tma_load_3d(smem + DQ_K + st * (TK * THD * 2), &tmK, &kv_full[st], kvh * THD, j * TK, b);
+        tma_load_3d(smem + DQ_V + st * (TK * THD * 2), &tmV, &kv_full[st], kvh * THD, j * TK, b);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t sq = smem_u32(smem + DQ_Q), sdo = smem_u32(smem + DQ_DO), sds = smem_u32(smem + DQ_DS);
+      mbar_wait(q_full, 0);
+      for (int j = 0; j < nblk; ++j) {
+        const int st = j & 1;
+        const uint32_t sk = smem_u32(smem + DQ_K + st * (TK * THD * 2));
+        const uint32_t sv = smem_u32(smem + DQ_V + st * (TK * THD * 2));
+        mbar_wait(&kv_full[st], (j >> 1) & 1);
+        tc_fence_after();
+        issue_nt_128(tmem_base + COL_S, sq, sk);      // S  = Q K^T   (the compute warps finished block j-1:
+        issue_nt_128(tmem_base + COL_DP, sdo, sv);    // dP = dO V^T   ds_full(j-1) was waited below)
+        umma_commit(s_full);
+        mbar_wait(ds_full, j & 1);
+        tc_fence_after();
+        issue_ak_bmn(tmem_base + COL_DQ, sds, sk, j > 0);   // dQ += dS K
+        umma_commit(&kv_empty[st]);
+      }
+      umma_commit(acc_full);
+    }
+  } else {
+    const int quad = warp & 3, half = (warp - 2) >> 2;
+    const int r = quad * 32 + lane, qi = q0 + r;
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16);
+    const float scale_log2 = scale * kLog2e;
+    const int64_t li = ((int64_t)b * H + h) * S + qi;
+    const float L2 = (qi < S) ? lse[li] * kLog2e : INFINITY;   // +inf => P = 0 for rows past the sequence end
+    const float Dl = (qi < S) ? delta[li] : 0.f;
+    for (int j = 0; j < nblk; ++j) {
+      const bool diag = (j == nblk - 1);
+      const int kbase = j * TK + half * 64;
+      mbar_wait(s_full, j & 1);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c = 0; c < 64; c += 32) {
+        uint32_t sv_[32], dv_[32];
+        __syncwarp();
+        tmem_ld32(lane_addr + COL_S + half * 64 + c, sv_);
+        tmem_ld32(lane_addr + COL_DP + half * 64 + c, dv_);
+        tmem_ld_wait();
+        float f[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          float p = exp2f(__uint_as_float(sv_[i]) * scale_log2 - L2);
+          if (diag && (kbase + c + i > qi)) p = 0.f;
+          f[i] = p * (__uint_as_float(dv_[i]) - Dl) * scale;
+        }
+        store_row_chunk32(smem + DQ_DS, r, half * 64 + c, f);
+      }
+      fence_async_smem();
+      tc_fence_before();
+      mbar_arrive(ds_full);
+    }
+    mbar_wait(acc_full, 0);
+    tc_fence_after();
+    {
+      uint32_t v[32];
+      __syncwarp();
+      tmem_ld32(lane_addr + COL_DQ + half * 32, v);
+      tmem_ld_wait();
+      if (qi < S) {
+        bf16* dp_ = dq + ((int64_t)b * S + qi) * lddq + (int64_t)h * THD + half * 32;
+#pragma unroll
+        for (int c = 0; c < 32; c += 8) {
+          uint4 w;
+          w.x = pack_bf16(__uint_as_float(v[c + 0]), __uint_as_float(v[c + 1]));
+          w.y = pack_bf16(__uint_as_float(v[c + 2]), __uint_as_float(v[c + 3]));
+          w.z = pack_bf16(__uint_as_float(v[c + 4]), __uint_as_float(v[c + 5]));
+          w.w = pack_bf16(__uint_as_float(v[c + 6]), __uint_as_float(v[c + 7]));
+          *reinterpret_cast<uint4*>(dp_ + c) = w;
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+constexpr int DK_K = 0;                              // 16 KB  K tile
+constexpr int DK_V = DK_K + TK * THD * 2;            // 16 KB  V tile
+constexpr int DK_Q = DK_V + TK * THD * 2;            // 2 x 16 KB Q tiles
+constexpr int DK_DO = DK_Q + 2 * TQ * THD * 2;       // 2 x 16 KB dO tiles
+constexpr int DK_PT = DK_DO + 2 * TQ * THD * 2;      // 32 KB P^T
+constexpr int DK_DST = DK_PT + TK * TQ * 2;          // 32 KB dS^T
+constexpr int DK_BAR = DK_DST + TK * TQ * 2;
+constexpr int kDkSmem = DK_BAR + 256 + 1024;
+
+__global__ void __launch_bounds__(kBwdThreads, 1)
+attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                        const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmDO,
+                        const float* __restrict__ lse, const float* __restrict__ delta, bf16* __restrict__ dk,
+                        bf16* __restrict__ dv, int S, int H, int KV, int64_t lddk, int64_t lddv, float scale) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + DK_BAR);
+  uint64_t* kv_full = bars;         // K + V landed
+  uint64_t* qd_full = bars + 1;     // [2] Q_i + dO_i landed
+  uint64_t* qd_empty = bars + 3;    // [2]
+  uint64_t* st_full = bars + 5;     // S^T and dP^T ready
+  uint64_t* pt_full = bars + 6;     // P^T and dS^T tiles written (256 arrivals)
+  uint64_t* acc_full = bars + 7;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int kvb = blockIdx.x, kvh = blockIdx.y, b = blockIdx.z;
+  const int rep = H / KV;
+  const int k0 = kvb * TK;
+  const int nqb = (S + TQ - 1) / TQ;
+  const int nq_iter = nqb - kvb;
+  const int total = rep * nq_iter;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV); tma_prefetch_desc(&tmDO);
+    mbar_init(kv_full, 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(&qd_full[i], 1); mbar_init(&qd_empty[i], 1); }
+    mbar_init(st_full, 1);
+    mbar_init(pt_full, 256);
+    mbar_init(acc_full, 1);
+    mbar_fence_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  constexpr uint32_t COL_ST = 0, COL_DPT = 128, COL_DK = 256, COL_DV = 320;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(kv_full, 2 * TK * THD * 2);
+      tma_load_3d(smem + DK_K, &tmK, kv_full, kvh * THD, k0, b);
+      tma_load_3d(smem + DK_V, &tmV, kv_full, kvh * THD, k0, b);
+      for (int it = 0; it < total; ++it) {
+        const int st = it & 1;
+        const int h = kvh * rep + it / nq_iter, qb = kvb + it % nq_iter;
+        mbar_wait(&qd_empty[st], ((it >> 1) & 1) ^ 1);
+        mbar_expect_tx(&qd_full[st], 2 * TQ * THD * 2);
+        tma_load_3d(smem + DK_Q + st * (TQ * THD * 2), &tmQ, &qd_full[st], h * THD, qb * TQ, b);
+        tma_load_3d(smem + DK_DO + st * (TQ * THD * 2), &tmDO, &qd_full[st], h * THD, qb * TQ, b);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t sk = smem_u32(smem + DK_K), sv = smem_u32(smem + DK_V);
+      const uint32_t spt = smem_u32(smem + DK_PT), sdst = smem_u32(smem + DK_DST);
+      mbar_wait(kv_full, 0);
+      for (int it = 0; it < total; ++it) {
+        const int st = it & 1;
+        const uint32_t sq = smem_u32(smem + DK_Q + st * (TQ * THD * 2));
+        const uint32_t sdo = smem_u32(smem + DK_DO + st * (TQ * THD * 2));
+        mbar_wait(&qd_full[st], (it >> 1) & 1);
+        tc_fence_after();
+        issue_nt_128(tmem_base + COL_ST, sk, sq);      // S^T  = K Q^T
+        issue_nt_128(tmem_base + COL_DPT, sv, sdo);    // dP^T = V dO^T
+        umma_commit(st_full);
+        mbar_wait(pt_full, it & 1);
+        tc_fence_after();
+        issue_ak_bmn(tmem_base + COL_DV, spt, sdo, it > 0);    // dV += P^T dO
+        issue_ak_bmn(tmem_base + COL_DK, sdst, sq, it > 0);    // dK += dS^T Q
+        umma_commit(&qd_empty[st]);
+      }
+      umma_commit(acc_full);
+    }
+  } else {
+    const int quad = warp & 3, half = (warp - 2) >> 2;
+    const int r = quad * 32 + lane, kj = k0 + r;               // this thread's key
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16);
+    const float scale_log2 = scale * kLog2e;
+    for (int it = 0; it < total; ++it) {
+      const int h = kvh * rep + it / nq_iter, qb = kvb + it % nq_iter;
+      const bool diag = (qb == kvb);
+      const int qbase = qb * TQ + half * 64;
+      const float* Lp = lse + ((int64_t)b * H + h) * S;
+      const float* Dp = delta + ((int64_t)b * H + h) * S;
+      mbar_wait(st_full, it & 1);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c = 0; c < 64; c += 32) {
+        uint32_t sv_[32], dv_[32];
+        __syncwarp();
+        tmem_ld32(lane_addr + COL_ST + half * 64 + c, sv_);
+        tmem_ld32(lane_addr + COL_DPT + half * 64 + c, dv_);
+        tmem_ld_wait();
+        float pf[32], df[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const int q = qbase + c + i;
+          const bool ok = (q < S) && !(diag && kj > q);
+          const float L2 = ok ? __ldg(Lp + q) * kLog2e : 0.f;
+          const float Dl = ok ? __ldg(Dp + q) : 0.f;
+          const float p = ok ? exp2f(__uint_as_float(sv_[i]) * scale_log2 - L2) : 0.f;
+          pf[i] = p;
+          df[i] = p * (__uint_as_float(dv_[i]) - Dl) * scale;
+        }
+        store_row_chunk32(smem + DK_PT, r, half * 64 + c, pf);
+        store_row_chunk32(smem + DK_DST, r, half * 64 + c, df);
+      }
+      fence_async_smem();
+      tc_fence_before();
+      mbar_arrive(pt_full);
+    }
+    mbar_wait(acc_full, 0);
+    tc_fence_after();
+    // warps 2..5 store dK rows, warps 6..9 store dV rows (64 columns each)
+    bf16* outp = half == 0 ? dk + ((int64_t)b * S + kj) * lddk + (int64_t)kvh * THD
+                           : dv + ((int64_t)b * S + kj) * lddv + (int64_t)kvh * THD;
+    const uint32_t col = half == 0 ? COL_DK : COL_DV;
+#pragma unroll
+    for (int c = 0; c < THD; c += 32) {
+      uint32_t v[32];
+      __syncwarp();
+      tmem_ld32(lane_addr + col + c, v);
+      tmem_ld_wait();
+      if (kj < S) {
+#pragma unroll
+        for (int c8 = 0; c8 < 32; c8 += 8) {
+          uint4 w;
+          w.x = pack_bf16(__uint_as_float(v[c8 + 0]), __uint_as_float(v[c8 + 1]));
+          w.y = pack_bf16(__uint_as_float(v[c8 + 2]), __uint_as_float(v[c8 + 3]));
+          w.z = pack_bf16(__uint_as_float(v[c8 + 4]), __uint_as_float(v[c8 + 5]));
+          w.w = pack_bf16(__uint_as_float(v[c8 + 6]), __uint_as_float(v[c8 + 7]));
+          *reinterpret_cast<uint4*>(outp + c + c8) = w;
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+}  // namespace
+
+bool attn_tc_supported(int S, int hd, int64_t ldq, int64_t ldk, int64_t ldv, int64_t ldo, const void* q, const void* k,
+                       const void* v, const void* o) {
+  return hd == THD && S >= 128 && ldq % 8 == 0 && ldk % 8 == 0 && ldv % 8 == 0 && ldo % 8 == 0 && aligned16(q) &&
+         aligned16(k) && aligned16(v) && aligned16(o);
+}
+
+int attn_fwd_tc_launch(const void* q, const void* k, const void* v, void* o, float* lse, int B, int S, int H, int KV,
+                       int64_t ldq, int64_t ldk, int64_t ldv, int64_t ldo, float scale, cudaStream_t st) {
+  CUtensorMap tq, tk, tv;
+  int rc;
+  if ((rc = encode_tmap_bf16(&tq, q, (uint64_t)H * THD, S, B, ldq, (uint64_t)S * ldq, TQ))) return rc;
+  if ((rc = encode_tmap_bf16(&tk, k, (uint64_t)KV * THD, S, B, ldk, (uint64_t)S * ldk, TK))) return rc;
+  if ((rc = encode_tmap_bf16(&tv, v, (uint64_t)KV * THD, S, B, ldv, (uint64_t)S * ldv, TK))) return rc;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(attn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem);
+    if (e != cudaSuccess) { set_error("attn_fwd_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return CSM_ERR_CUDA; }
+    configured = true;
+  }
+  dim3 grid((S + TQ - 1) / TQ, H, B);
+  attn_fwd_tc_kernel<<<grid, kAttnThreads, kAttnSmem, st>>>(tq, tk, tv, (bf16*)o, lse, S, H, KV, ldo, scale * kLog2e);
+  CSM_CHECK_LAUNCH("attn_fwd_tc");
+  return CSM_OK;
+}
+
+int attn_delta_launch(const void* o, const void* dout, float* delta, int B, int S, int H, int64_t ldo,
+                      cudaStream_t st);
+
+int attn_bwd_tc_launch(const void* q, const void* k, const void* v, const void* o, const float* lse, const void* dout,
+                       void* dq, void* dk, void* dv, float* delta, int B, int S, int H, int KV, int64_t ldq, int64_t ldk,
+                       int64_t ldv, int64_t ldo, int64_t lddq, int64_t lddk, int64_t lddv, float scale, cudaStream_t st) {
+  CSM_REQUIRE(aligned16(dout) && aligned16(dq) && aligned16(dk) && aligned16(dv) && lddq % 8 == 0 && lddk % 8 == 0 &&
+                  lddv % 8 == 0,
+              CSM_ERR_ALIGN, "attn_bwd_tc: misaligned gradient buffers");
+  int rc = attn_delta_launch(o, dout, delta, B, S, H, ldo, st);
+  if (rc) return rc;
+  CUtensorMap tq, tk, tv, tdo;
+  if ((rc = encode_tmap_bf16(&tq, q, (uint64_t)H * THD, S, B, ldq, (uint64_t)S * ldq, TQ))) return rc;
+  if ((rc = encode_tmap_bf16(&tk, k, (uint64_t)KV * THD, S, B, ldk, (uint64_t)S * ldk, TK))) return rc;
+  if ((rc = encode_tmap_bf16(&tv, v, (uint64_t)KV * THD, S, B, ldv, (uint64_t)S * ldv, TK))) return rc;
+  if ((rc = encode_tmap_bf16(&tdo, dout, (uint64_t)H * THD, S, B, ldo, (uint64_t)S * ldo, TQ))) return rc;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(attn_bwd_dq_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDqSmem);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(attn_bwd_dkdv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDkSmem);
+    if (e != cudaSuccess) { set_error("attn_bwd_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return CSM_ERR_CUDA; }
+    configured = true;
+  }
+  dim3 gq((S + TQ - 1) / TQ, H, B);
+  attn_bwd_dq_tc_kernel<<<gq, kBwdThreads, kDqSmem, st>>>(tq, tk, tv, tdo, lse, delta, (bf16*)dq, S, H, KV, lddq, scale);
+  CSM_CHECK_LAUNCH("attn_bwd_dq_tc");
+  dim3 gk((S + TK - 1) / TK, KV, B);
+  attn_bwd_dkdv_tc_kernel<<<gk, kBwdThreads, kDkSmem, st>>>(tq, tk, tv, tdo, lse, delta, (bf16*)dk, (bf16*)dv, S, H, KV,
+                                                            lddk, lddv, scale);
+  CSM_CHECK_LAUNCH("attn_bwd_dkdv_tc");
+  return CSM_OK;
+}
+
+}  // namespace csm

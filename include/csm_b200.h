@@ -116,6 +116,9 @@ int csm_swiglu_bwd(const void* dout, const void* gate, const void* up, void* dga
 int csm_attn_causal_gqa_fwd(const void* q, const void* k, const void* v, void* o, float* lse, int32_t batch,
                             int32_t seq, int32_t heads, int32_t kv_heads, int32_t head_dim, int64_t ldq,
                             int64_t ldk, int64_t ldv, int64_t ldo, float scale, csm_stream_t stream);
+/* test hook: force the attention back-end. 0 = automatic (tcgen05 forward for head_dim 64 and seq >= 128, mma.sync
+ * for head_dim 64, scalar otherwise), 1 = scalar, 2 = mma.sync, 3 = tcgen05 (forward; error if unsupported). */
+void csm_set_attn_backend(int32_t backend);
 /* workspace: csm_attn_bwd_workspace_bytes() bytes (delta[batch,heads,seq] fp32 + fp32 dk/dv staging). */
 size_t csm_attn_bwd_workspace_bytes(int32_t batch, int32_t seq, int32_t heads, int32_t kv_heads,
                                     int32_t head_dim);

@@ -205,9 +205,23 @@ def _sdpa_ref(q, k, v, B, S, H, KV, hd):
     return o.transpose(1, 2).reshape(B * S, H * hd)
 
 
+@pytest.mark.parametrize("backend", [0, 1, 2])
 @pytest.mark.parametrize("B,S,H,KV,hd", [(2, 32, 4, 4, 8), (3, 32, 2, 2, 8), (2, 256, 8, 2, 64), (1, 300, 4, 1, 64),
-                                         (7, 32, 8, 2, 128), (1, 2048, 4, 1, 64)])
-def test_attention_fwd_bwd(ops, cuda, B, S, H, KV, hd):
+                                         (7, 32, 8, 2, 128), (1, 2048, 4, 1, 64), (2, 128, 4, 4, 64), (1, 1000, 8, 2, 64)])
+def test_attention_fwd_bwd(ops, cuda, backend, B, S, H, KV, hd):
+    """backend 0 = automatic (tcgen05 forward when hd=64 and S>=128), 1 = scalar kernels, 2 = mma.sync kernels."""
+    if backend == 2 and hd != 64:
+        pytest.skip("mma.sync kernels are head_dim 64 only")
+    if backend == 1 and S > 512:
+        pytest.skip("scalar kernel: keep test time bounded")
+    ops.set_attn_backend(backend)
+    try:
+        _attention_case(ops, cuda, B, S, H, KV, hd)
+    finally:
+        ops.set_attn_backend(0)
+
+
+def _attention_case(ops, cuda, B, S, H, KV, hd):
     g = torch.Generator().manual_seed(B * S + hd)
     q = torch.randn(B * S, H * hd, generator=g).to(BF).to(cuda)
     k = torch.randn(B * S, KV * hd, generator=g).to(BF).to(cuda)

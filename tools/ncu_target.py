@@ -1,0 +1,50 @@
+#!/usr/bin/env python
+"""Tiny launch targets for `ncu --set full` (one kernel family per invocation, a handful of launches).
+   python tools/ncu_target.py gemm|ce|embed|attn"""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "csm-train-pytorch_b200"))
+import torch  # noqa: E402
+
+from csm import ops  # noqa: E402
+
+dev = torch.device("cuda:0")
+BF = torch.bfloat16
+what = sys.argv[1] if len(sys.argv) > 1 else "gemm"
+torch.manual_seed(0)
+if what == "gemm":          # the MLP gate/up forward GEMM of one backbone layer (fused w1|w3): 4096 x 16384 x 2048
+    x = torch.randn(4096, 2048, device=dev).to(BF)
+    w = torch.randn(16384, 2048, device=dev).to(BF)
+    out = torch.empty(4096, 16384, dtype=BF, device=dev)
+    for _ in range(4):
+        ops.gemm(x, w, out=out)
+elif what == "ce":          # grouped audio_head fused CE forward at the c2 decoder size (232 frames)
+    Dd, V, G, Ns = 1024, 2051, 31, 232
+    head_t = (torch.randn(G, V, Dd, device=dev) * 0.05).to(BF)
+    y = torch.randn(Ns, 32, Dd, device=dev).to(BF)
+    codes = torch.randint(0, V, (Ns, 32), device=dev)
+    for _ in range(4):
+        ops.linear_ce_fwd(y[:, 1:], head_t, codes[:, 1:], groups=G, tgt_row_stride=32, tgt_group_stride=1)
+elif what == "embed":       # K1 at the c2 size: 4096 audio frames
+    C, V, Vt, D, N = 32, 2051, 128256, 2048, 4096
+    audio = torch.randn(C * V, D, device=dev).to(BF)
+    text = torch.randn(Vt, D, device=dev).to(BF)
+    tok = torch.randint(0, V, (1, N, C + 1), device=dev)
+    msk = torch.ones(1, N, C + 1, dtype=torch.bool, device=dev)
+    msk[..., C] = False
+    for _ in range(4):
+        ops.embed_gather_sum(tok, msk, audio, text)
+elif what == "attn":
+    B, S, H, KV, hd = 2, 2048, 32, 8, 64
+    q = torch.randn(B * S, H * hd, device=dev).to(BF)
+    k = torch.randn(B * S, KV * hd, device=dev).to(BF)
+    v = torch.randn(B * S, KV * hd, device=dev).to(BF)
+    do = torch.randn(B * S, H * hd, device=dev).to(BF)
+    for _ in range(2):
+        o, lse = ops.attention_fwd(q, k, v, B, S, H, KV, hd)
+        ops.attention_bwd(q, k, v, o, lse, do, B, S, H, KV, hd)
+torch.cuda.synchronize()
+print("done", what)
