@@ -6,6 +6,8 @@
 //                with tcgen05.ld (max, then exp2/sum), P_j written as bf16 into 128B-swizzled smem (the A operand
 //                of the PV MMA), running output kept in registers and updated from the PV_j tile one block later,
 //                so the tensor pipe computes S_{j+1} and PV_j while the softmax of the next block runs.
+#include <type_traits>
+
 #include "tc_common.cuh"
 
 namespace csm {
@@ -27,6 +29,28 @@ constexpr int SM_BAR = SM_P + 2 * TQ * TK * 2;            // + 64 KB
 constexpr int kAttnSmem = SM_BAR + 256 + 1024;
 
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ float ex2(float x) {   // one MUFU; -inf -> 0
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+__device__ __forceinline__ void store_row_chunk32(uint8_t* tile, int r, int col0, const float* f) {
+  // 32 consecutive columns [col0, col0+32) of row r into a [128 x 128] bf16 A-operand tile made of two
+  // 64-column 128B-swizzled atoms of 16 KB each
+  uint8_t* atom = tile + (col0 >> 6) * (128 * 64 * 2) + r * 128;
+  const int c16 = (col0 & 63) >> 3;
+#pragma unroll
+  for (int q4 = 0; q4 < 4; ++q4) {
+    uint4 w;
+    w.x = pack_bf16(f[q4 * 8 + 0], f[q4 * 8 + 1]); w.y = pack_bf16(f[q4 * 8 + 2], f[q4 * 8 + 3]);
+    w.z = pack_bf16(f[q4 * 8 + 4], f[q4 * 8 + 5]); w.w = pack_bf16(f[q4 * 8 + 6], f[q4 * 8 + 7]);
+    *reinterpret_cast<uint4*>(atom + (((c16 + q4) ^ (r & 7)) << 4)) = w;
+  }
+}
 
 __global__ void __launch_bounds__(kAttnThreads, 1)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
@@ -59,7 +83,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       mbar_init(&kv_full[i], 1);
       mbar_init(&kv_empty[i], 1);
       mbar_init(&s_full[i], 1);
-      mbar_init(&p_full[i], 128);
+      mbar_init(&p_full[i], 4);
       mbar_init(&pv_full[i], 1);
     }
     mbar_fence_init();
@@ -138,75 +162,61 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       const int st = j & 1;
       mbar_wait(&pv_full[st], (j >> 1) & 1);
       tc_fence_after();
+      uint32_t v[THD];
+      __syncwarp();
 #pragma unroll
-      for (int c = 0; c < THD; c += 32) {
-        uint32_t v[32];
-        __syncwarp();
-        tmem_ld32(lane_addr + COL_PV + st * THD + c, v);
-        tmem_ld_wait();
+      for (int c = 0; c < THD; c += 32) tmem_ld32(lane_addr + COL_PV + st * THD + c, v + c);
+      tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 32; ++i) oacc[c + i] = oacc[c + i] * corr + __uint_as_float(v[i]);
-      }
+      for (int i = 0; i < THD; ++i) oacc[i] = fmaf(oacc[i], corr, __uint_as_float(v[i]));
     };
 
-    for (int j = 0; j < nblk; ++j) {
+    // one KV block of the online softmax; DIAG is the block on the causal diagonal (the only one that needs masks)
+    auto block = [&](int j, auto diag_tag) {
+      constexpr bool DIAG = decltype(diag_tag)::value;
       const int st = j & 1;
-      const bool diag = (j == nblk - 1);
       const int kbase = j * TK;
       mbar_wait(&s_full[st], (j >> 1) & 1);
       tc_fence_after();
       const uint32_t s_addr = lane_addr + COL_S + st * TK;
-      // pass 1: row max
-      float mx = m;
-#pragma unroll 1
-      for (int c = 0; c < TK; c += 32) {
-        uint32_t v[32];
-        __syncwarp();
-        tmem_ld32(s_addr + c, v);
-        tmem_ld_wait();
+      // the whole 128-column S row in registers: 4 tcgen05.ld in flight, ONE wait (a single TMEM round trip)
+      uint32_t v[TK];
+      __syncwarp();
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          float x = __uint_as_float(v[i]) * scale_log2;
-          if (diag && (kbase + c + i > qi)) x = -INFINITY;
-          mx = fmaxf(mx, x);
-        }
+      for (int c = 0; c < TK; c += 32) tmem_ld32(s_addr + c, v + c);
+      tmem_ld_wait();
+      float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+      for (int i = 0; i < TK; ++i) {
+        if (DIAG && (kbase + i > qi)) v[i] = 0xff800000u;   // -inf
+        m4[i & 3] = fmaxf(m4[i & 3], __uint_as_float(v[i]));
       }
-      const float corr = exp2f(m - mx);
+      const float mr = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));   // scale > 0: scaling commutes with max
+      const float mx = fmaxf(m, mr * scale_log2);
+      const float corr = ex2(m - mx);
       m = mx;
-      // pass 2: p = exp2(s - m), row sum, bf16 P tile into swizzled smem
-      float rs = 0.f;
-      uint8_t* prow = smem + SM_P + st * (TQ * TK * 2) + r * 128;
-#pragma unroll 1
+      float rs4[4] = {0.f, 0.f, 0.f, 0.f};
+      uint8_t* ptile = smem + SM_P + st * (TQ * TK * 2);
+#pragma unroll
       for (int c = 0; c < TK; c += 32) {
-        uint32_t v[32];
-        __syncwarp();
-        tmem_ld32(s_addr + c, v);
-        tmem_ld_wait();
         float p[32];
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
-          float x = __uint_as_float(v[i]) * scale_log2 - m;
-          if (diag && (kbase + c + i > qi)) x = -INFINITY;
-          p[i] = exp2f(x);
-          rs += p[i];
+          p[i] = ex2(fmaf(__uint_as_float(v[c + i]), scale_log2, -m));   // exp2(-inf) = 0 for masked keys
+          rs4[i & 3] += p[i];
         }
-        uint8_t* atom = prow + (c >> 6) * (TQ * 64 * 2);
-        const int c16 = (c & 63) >> 3;        // first 16-byte chunk of this 32-column group inside the atom
-#pragma unroll
-        for (int q4 = 0; q4 < 4; ++q4) {
-          uint4 w;
-          w.x = pack_bf16(p[q4 * 8 + 0], p[q4 * 8 + 1]); w.y = pack_bf16(p[q4 * 8 + 2], p[q4 * 8 + 3]);
-          w.z = pack_bf16(p[q4 * 8 + 4], p[q4 * 8 + 5]); w.w = pack_bf16(p[q4 * 8 + 6], p[q4 * 8 + 7]);
-          *reinterpret_cast<uint4*>(atom + (((c16 + q4) ^ (r & 7)) << 4)) = w;
-        }
+        store_row_chunk32(ptile, r, c, p);
       }
-      l = l * corr + rs;
+      l = l * corr + ((rs4[0] + rs4[1]) + (rs4[2] + rs4[3]));
       fence_async_smem();                     // generic-proxy smem writes -> visible to the tensor core (async proxy)
       tc_fence_before();
-      mbar_arrive(&p_full[st]);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_full[st]);
       if (j > 0) fold(j - 1, corr_prev);
       corr_prev = corr;
-    }
+    };
+    for (int j = 0; j < nblk - 1; ++j) block(j, std::false_type{});
+    block(nblk - 1, std::true_type{});
     fold(nblk - 1, corr_prev);
     if (qi < S) {
       const float inv = 1.f / l;
@@ -249,20 +259,6 @@ constexpr int DQ_V = DQ_K + 2 * TK * THD * 2;        // 2 x 16 KB
 constexpr int DQ_DS = DQ_V + 2 * TK * THD * 2;       // 32 KB  dS tile (A operand)
 constexpr int DQ_BAR = DQ_DS + TQ * TK * 2;
 constexpr int kDqSmem = DQ_BAR + 256 + 1024;
-
-__device__ __forceinline__ void store_row_chunk32(uint8_t* tile, int r, int col0, const float* f) {
-  // 32 consecutive columns [col0, col0+32) of row r into a [128 x 128] bf16 A-operand tile made of two
-  // 64-column 128B-swizzled atoms of 16 KB each
-  uint8_t* atom = tile + (col0 >> 6) * (128 * 64 * 2) + r * 128;
-  const int c16 = (col0 & 63) >> 3;
-#pragma unroll
-  for (int q4 = 0; q4 < 4; ++q4) {
-    uint4 w;
-    w.x = pack_bf16(f[q4 * 8 + 0], f[q4 * 8 + 1]); w.y = pack_bf16(f[q4 * 8 + 2], f[q4 * 8 + 3]);
-    w.z = pack_bf16(f[q4 * 8 + 4], f[q4 * 8 + 5]); w.w = pack_bf16(f[q4 * 8 + 6], f[q4 * 8 + 7]);
-    *reinterpret_cast<uint4*>(atom + (((c16 + q4) ^ (r & 7)) << 4)) = w;
-  }
-}
 
 // D[128 x 64] (+)= A[128 x 128 (two swizzle atoms)] * B where B is a [128 rows x 64] tile used MN-major
 __device__ __forceinline__ void issue_ak_bmn(uint32_t d_tmem, uint32_t a_smem, uint32_t b_smem, bool accumulate_first) {
@@ -311,7 +307,7 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     mbar_init(q_full, 1);
     for (int i = 0; i < 2; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
     mbar_init(s_full, 1);
-    mbar_init(ds_full, 256);
+    mbar_init(ds_full, 8);
     mbar_init(acc_full, 1);
     mbar_fence_init();
   }
@@ -362,32 +358,37 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     const float scale_log2 = scale * kLog2e;
     const int64_t li = ((int64_t)b * H + h) * S + qi;
     const float L2 = (qi < S) ? lse[li] * kLog2e : INFINITY;   // +inf => P = 0 for rows past the sequence end
-    const float Dl = (qi < S) ? delta[li] : 0.f;
-    for (int j = 0; j < nblk; ++j) {
-      const bool diag = (j == nblk - 1);
+    const float Dls = (qi < S) ? delta[li] * scale : 0.f;
+    auto block = [&](int j, auto diag_tag) {
+      constexpr bool DIAG = decltype(diag_tag)::value;
       const int kbase = j * TK + half * 64;
       mbar_wait(s_full, j & 1);
       tc_fence_after();
-#pragma unroll 1
+      uint32_t sv_[64], dv_[64];
+      __syncwarp();
+      tmem_ld32(lane_addr + COL_S + half * 64, sv_);
+      tmem_ld32(lane_addr + COL_S + half * 64 + 32, sv_ + 32);
+      tmem_ld32(lane_addr + COL_DP + half * 64, dv_);
+      tmem_ld32(lane_addr + COL_DP + half * 64 + 32, dv_ + 32);
+      tmem_ld_wait();
+#pragma unroll
       for (int c = 0; c < 64; c += 32) {
-        uint32_t sv_[32], dv_[32];
-        __syncwarp();
-        tmem_ld32(lane_addr + COL_S + half * 64 + c, sv_);
-        tmem_ld32(lane_addr + COL_DP + half * 64 + c, dv_);
-        tmem_ld_wait();
         float f[32];
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
-          float p = exp2f(__uint_as_float(sv_[i]) * scale_log2 - L2);
-          if (diag && (kbase + c + i > qi)) p = 0.f;
-          f[i] = p * (__uint_as_float(dv_[i]) - Dl) * scale;
+          float x = fmaf(__uint_as_float(sv_[c + i]), scale_log2, -L2);
+          if (DIAG && (kbase + c + i > qi)) x = -INFINITY;
+          f[i] = ex2(x) * fmaf(__uint_as_float(dv_[c + i]), scale, -Dls);     // P * (dP - delta) * scale
         }
         store_row_chunk32(smem + DQ_DS, r, half * 64 + c, f);
       }
       fence_async_smem();
       tc_fence_before();
-      mbar_arrive(ds_full);
-    }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(ds_full);
+    };
+    for (int j = 0; j < nblk - 1; ++j) block(j, std::false_type{});
+    block(nblk - 1, std::true_type{});
     mbar_wait(acc_full, 0);
     tc_fence_after();
     {
@@ -423,7 +424,8 @@ constexpr int DK_Q = DK_V + TK * THD * 2;            // 2 x 16 KB Q tiles
 constexpr int DK_DO = DK_Q + 2 * TQ * THD * 2;       // 2 x 16 KB dO tiles
 constexpr int DK_PT = DK_DO + 2 * TQ * THD * 2;      // 32 KB P^T
 constexpr int DK_DST = DK_PT + TK * TQ * 2;          // 32 KB dS^T
-constexpr int DK_BAR = DK_DST + TK * TQ * 2;
+constexpr int DK_LD = DK_DST + TK * TQ * 2;          // 2 x (128 lse*log2e + 128 delta*scale) floats
+constexpr int DK_BAR = DK_LD + 2 * 256 * 4;
 constexpr int kDkSmem = DK_BAR + 256 + 1024;
 
 __global__ void __launch_bounds__(kBwdThreads, 1)
@@ -455,7 +457,7 @@ attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
     mbar_init(kv_full, 1);
     for (int i = 0; i < 2; ++i) { mbar_init(&qd_full[i], 1); mbar_init(&qd_empty[i], 1); }
     mbar_init(st_full, 1);
-    mbar_init(pt_full, 256);
+    mbar_init(pt_full, 8);
     mbar_init(acc_full, 1);
     mbar_fence_init();
   }
@@ -507,38 +509,62 @@ attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
     const int r = quad * 32 + lane, kj = k0 + r;               // this thread's key
     const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16);
     const float scale_log2 = scale * kLog2e;
-    for (int it = 0; it < total; ++it) {
+    const int ctid = threadIdx.x - 64;                         // 0..255 among the compute warps
+    auto iter = [&](int it, auto diag_tag) {
+      constexpr bool DIAG = decltype(diag_tag)::value;
       const int h = kvh * rep + it / nq_iter, qb = kvb + it % nq_iter;
-      const bool diag = (qb == kvb);
       const int qbase = qb * TQ + half * 64;
-      const float* Lp = lse + ((int64_t)b * H + h) * S;
-      const float* Dp = delta + ((int64_t)b * H + h) * S;
+      // stage this query block's lse*log2e (+inf past the sequence end => P = 0) and delta*scale once per CTA
+      float* sLD = reinterpret_cast<float*>(smem + DK_LD) + (it & 1) * 256;
+      {
+        const int q = qb * TQ + (ctid & 127);
+        const int64_t li = ((int64_t)b * H + h) * S + q;
+        float val;
+        if (ctid < 128) val = (q < S) ? __ldg(lse + li) * kLog2e : INFINITY;
+        else val = (q < S) ? __ldg(delta + li) * scale : 0.f;
+        sLD[ctid] = val;
+      }
+      named_bar_sync(1, 256);
       mbar_wait(st_full, it & 1);
       tc_fence_after();
-#pragma unroll 1
-      for (int c = 0; c < 64; c += 32) {
-        uint32_t sv_[32], dv_[32];
-        __syncwarp();
-        tmem_ld32(lane_addr + COL_ST + half * 64 + c, sv_);
-        tmem_ld32(lane_addr + COL_DPT + half * 64 + c, dv_);
-        tmem_ld_wait();
-        float pf[32], df[32];
+      uint32_t sv_all[64], dv_all[64];
+      __syncwarp();
+      tmem_ld32(lane_addr + COL_ST + half * 64, sv_all);
+      tmem_ld32(lane_addr + COL_ST + half * 64 + 32, sv_all + 32);
+      tmem_ld32(lane_addr + COL_DPT + half * 64, dv_all);
+      tmem_ld32(lane_addr + COL_DPT + half * 64 + 32, dv_all + 32);
+      tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const int q = qbase + c + i;
-          const bool ok = (q < S) && !(diag && kj > q);
-          const float L2 = ok ? __ldg(Lp + q) * kLog2e : 0.f;
-          const float Dl = ok ? __ldg(Dp + q) : 0.f;
-          const float p = ok ? exp2f(__uint_as_float(sv_[i]) * scale_log2 - L2) : 0.f;
-          pf[i] = p;
-          df[i] = p * (__uint_as_float(dv_[i]) - Dl) * scale;
+      for (int c = 0; c < 64; c += 32) {
+        const uint32_t* sv_ = sv_all + c;
+        const uint32_t* dv_ = dv_all + c;
+        float pf[32], df[32];
+        const float4* L4 = reinterpret_cast<const float4*>(sLD + half * 64 + c);
+        const float4* D4 = reinterpret_cast<const float4*>(sLD + 128 + half * 64 + c);
+#pragma unroll
+        for (int i4 = 0; i4 < 8; ++i4) {
+          const float4 Lq = L4[i4], Dq = D4[i4];
+          const float Ls[4] = {Lq.x, Lq.y, Lq.z, Lq.w}, Ds[4] = {Dq.x, Dq.y, Dq.z, Dq.w};
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int i = i4 * 4 + u;
+            float x = fmaf(__uint_as_float(sv_[i]), scale_log2, -Ls[u]);
+            if (DIAG && (kj > qbase + c + i)) x = -INFINITY;
+            const float pv = ex2(x);
+            pf[i] = pv;
+            df[i] = pv * fmaf(__uint_as_float(dv_[i]), scale, -Ds[u]);
+          }
         }
         store_row_chunk32(smem + DK_PT, r, half * 64 + c, pf);
         store_row_chunk32(smem + DK_DST, r, half * 64 + c, df);
       }
       fence_async_smem();
       tc_fence_before();
-      mbar_arrive(pt_full);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(pt_full);
+    };
+    for (int it = 0; it < total; ++it) {
+      if (it % nq_iter == 0) iter(it, std::true_type{}); else iter(it, std::false_type{});
     }
     mbar_wait(acc_full, 0);
     tc_fence_after();
