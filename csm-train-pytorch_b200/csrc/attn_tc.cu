@@ -242,42 +242,46 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 
 // =====================================================================================================================
 // Backward on tcgen05.  Two kernels that each own their output rows (no atomics, deterministic):
-//   dQ kernel   : CTA = 128 queries of one head; per 128-key block  S = Q K^T, dP = dO V^T  (TMEM)  ->
-//                 dS = P o (dP - delta) * scale (bf16, swizzled smem)  ->  dQ += dS K  accumulated in TMEM.
-//   dKdV kernel : CTA = 128 keys of one kv head; per (q head of the group, 128-query block)  S^T = K Q^T,
+//   dQ kernel   : CTA = 128 queries of one head; per 64-key sub-block  S = Q K^T, dP = dO V^T  (TMEM, double
+//                 buffered)  ->  dS = P o (dP - delta) * scale (bf16, swizzled smem, double buffered)  ->
+//                 dQ += dS K  accumulated in TMEM over the whole key range.
+//   dKdV kernel : CTA = 128 keys of one kv head; per (q head of the group, 64-query sub-block)  S^T = K Q^T,
 //                 dP^T = V dO^T  ->  P^T, dS^T (smem)  ->  dV += P^T dO,  dK += dS^T Q  accumulated in TMEM.
+// The MMA warp runs one sub-block ahead of the 8 compute warps (TMEM and smem tiles are double buffered and
+// handed back through mbarriers as soon as they have been read), so tensor-core time and exp/FMA time overlap.
 // The Q / dO / K / V tiles are loaded once per use by TMA as [rows][64] 128B-swizzled tiles and serve BOTH as a
 // K-major operand (rows = M or N, hd = K) and as an MN-major B operand (hd = N, rows = K): same bytes, two descriptors.
-// 8 compute warps: warp w and w+4 share a TMEM lane quadrant and split the 128 columns, so no row reductions are
+// Compute warps w and w+4 share a TMEM lane quadrant and split the 64 columns of a sub-block; no row reductions are
 // needed (lse and delta come from the forward / the delta pre-pass).
 constexpr int kBwdThreads = 320;  // warp0 TMA, warp1 MMA, warps 2..9 compute
+constexpr int SUB = 64;           // columns (keys resp. queries) per pipelined sub-block
 
-constexpr int DQ_Q = 0;                              // 16 KB  Q tile
-constexpr int DQ_DO = DQ_Q + TQ * THD * 2;           // 16 KB  dO tile
-constexpr int DQ_K = DQ_DO + TQ * THD * 2;           // 2 x 16 KB
-constexpr int DQ_V = DQ_K + 2 * TK * THD * 2;        // 2 x 16 KB
-constexpr int DQ_DS = DQ_V + 2 * TK * THD * 2;       // 32 KB  dS tile (A operand)
-constexpr int DQ_BAR = DQ_DS + TQ * TK * 2;
-constexpr int kDqSmem = DQ_BAR + 256 + 1024;
-
-// D[128 x 64] (+)= A[128 x 128 (two swizzle atoms)] * B where B is a [128 rows x 64] tile used MN-major
-__device__ __forceinline__ void issue_ak_bmn(uint32_t d_tmem, uint32_t a_smem, uint32_t b_smem, bool accumulate_first) {
+// D[128 x 64] (+)= A[128 x 64 (one swizzle atom, K-major)] * B, B = [64 rows x 64] tile used MN-major
+__device__ __forceinline__ void issue_a64_bmn(uint32_t d_tmem, uint32_t a_smem, uint32_t b_smem, bool accumulate_first) {
   constexpr uint32_t idesc = make_idesc_bf16(128, THD, 0, 1);
 #pragma unroll
-  for (int kk = 0; kk < 128 / 16; ++kk) {
-    const uint64_t ad = make_smem_desc(a_smem + (kk >> 2) * (128 * 64 * 2) + (kk & 3) * 32, 16, 1024);
+  for (int kk = 0; kk < SUB / 16; ++kk) {
+    const uint64_t ad = make_smem_desc(a_smem + kk * 32, 16, 1024);
     const uint64_t bd = make_smem_desc(b_smem + kk * 16 * 128, 64 * 128 * 2, 1024);
     umma_bf16(d_tmem, ad, bd, idesc, (accumulate_first || kk) ? 1u : 0u);
   }
 }
-// D[128 x 128] = A[128 x 64] * B[128 x 64]^T, both K-major tiles
-__device__ __forceinline__ void issue_nt_128(uint32_t d_tmem, uint32_t a_smem, uint32_t b_smem) {
-  constexpr uint32_t idesc = make_idesc_bf16(128, 128, 0, 0);
+// D[128 x 64] = A[128 x 64] * B[64 x 64]^T, both K-major tiles (reduction over head_dim)
+__device__ __forceinline__ void issue_nt_64(uint32_t d_tmem, uint32_t a_smem, uint32_t b_smem) {
+  constexpr uint32_t idesc = make_idesc_bf16(128, SUB, 0, 0);
   const uint64_t ad = make_smem_desc(a_smem, 16, 1024), bd = make_smem_desc(b_smem, 16, 1024);
 #pragma unroll
   for (int kk = 0; kk < THD / 16; ++kk)
     umma_bf16(d_tmem, ad + (uint64_t)((kk * 32) >> 4), bd + (uint64_t)((kk * 32) >> 4), idesc, kk ? 1u : 0u);
 }
+
+constexpr int DQ_Q = 0;                              // 16 KB  Q tile
+constexpr int DQ_DO = DQ_Q + TQ * THD * 2;           // 16 KB  dO tile
+constexpr int DQ_K = DQ_DO + TQ * THD * 2;           // 2 x 16 KB (128-key tiles = two sub-blocks each)
+constexpr int DQ_V = DQ_K + 2 * TK * THD * 2;        // 2 x 16 KB
+constexpr int DQ_DS = DQ_V + 2 * TK * THD * 2;       // 2 x 16 KB  dS sub-tiles [128 q x 64 keys]
+constexpr int DQ_BAR = DQ_DS + 2 * TQ * SUB * 2;
+constexpr int kDqSmem = DQ_BAR + 256 + 1024;
 
 __global__ void __launch_bounds__(kBwdThreads, 1)
 attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
@@ -287,13 +291,15 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + DQ_BAR);
-  uint64_t* q_full = bars;          // Q + dO landed
-  uint64_t* kv_full = bars + 1;     // [2]
-  uint64_t* kv_empty = bars + 3;    // [2]
-  uint64_t* s_full = bars + 5;      // S and dP ready in TMEM
-  uint64_t* ds_full = bars + 6;     // dS tile written (256 arrivals)
-  uint64_t* acc_full = bars + 7;    // dQ accumulator final
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+  uint64_t* q_full = bars;            // Q + dO landed
+  uint64_t* kv_full = bars + 1;       // [2]
+  uint64_t* kv_empty = bars + 3;      // [2]
+  uint64_t* sdp_full = bars + 5;      // [2] S and dP sub-block ready in TMEM
+  uint64_t* sdp_empty = bars + 7;     // [2] ... and read back by the 8 compute warps
+  uint64_t* ds_full = bars + 9;       // [2] dS sub-tile written (8 warp arrivals)
+  uint64_t* ds_empty = bars + 11;     // [2] ... and consumed by the dQ MMA
+  uint64_t* acc_full = bars + 13;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int qb = gridDim.x - 1 - blockIdx.x;
@@ -301,13 +307,16 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
   const int kvh = h / (H / KV);
   const int q0 = qb * TQ;
   const int nblk = qb + 1;
+  const int nsub = 2 * nblk;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV); tma_prefetch_desc(&tmDO);
     mbar_init(q_full, 1);
-    for (int i = 0; i < 2; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
-    mbar_init(s_full, 1);
-    mbar_init(ds_full, 8);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1);
+      mbar_init(&sdp_full[i], 1); mbar_init(&sdp_empty[i], 8);
+      mbar_init(&ds_full[i], 8); mbar_init(&ds_empty[i], 1);
+    }
     mbar_init(acc_full, 1);
     mbar_fence_init();
   }
@@ -333,21 +342,29 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      const uint32_t sq = smem_u32(smem + DQ_Q), sdo = smem_u32(smem + DQ_DO), sds = smem_u32(smem + DQ_DS);
+      const uint32_t sq = smem_u32(smem + DQ_Q), sdo = smem_u32(smem + DQ_DO);
+      auto issue_sdp = [&](int u) {
+        const int jt = u >> 1, hk = u & 1, st = jt & 1, bb = u & 1;
+        if (hk == 0) mbar_wait(&kv_full[st], (jt >> 1) & 1);
+        mbar_wait(&sdp_empty[bb], ((u >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t sk = smem_u32(smem + DQ_K + st * (TK * THD * 2)) + hk * (SUB * 128);
+        const uint32_t sv = smem_u32(smem + DQ_V + st * (TK * THD * 2)) + hk * (SUB * 128);
+        issue_nt_64(tmem_base + COL_S + bb * SUB, sq, sk);     // S  = Q K_sub^T
+        issue_nt_64(tmem_base + COL_DP + bb * SUB, sdo, sv);   // dP = dO V_sub^T
+        umma_commit(&sdp_full[bb]);
+      };
       mbar_wait(q_full, 0);
-      for (int j = 0; j < nblk; ++j) {
-        const int st = j & 1;
-        const uint32_t sk = smem_u32(smem + DQ_K + st * (TK * THD * 2));
-        const uint32_t sv = smem_u32(smem + DQ_V + st * (TK * THD * 2));
-        mbar_wait(&kv_full[st], (j >> 1) & 1);
+      issue_sdp(0);
+      for (int u = 0; u < nsub; ++u) {
+        if (u + 1 < nsub) issue_sdp(u + 1);
+        const int jt = u >> 1, hk = u & 1, st = jt & 1, bb = u & 1;
+        mbar_wait(&ds_full[bb], (u >> 1) & 1);
         tc_fence_after();
-        issue_nt_128(tmem_base + COL_S, sq, sk);      // S  = Q K^T   (the compute warps finished block j-1:
-        issue_nt_128(tmem_base + COL_DP, sdo, sv);    // dP = dO V^T   ds_full(j-1) was waited below)
-        umma_commit(s_full);
-        mbar_wait(ds_full, j & 1);
-        tc_fence_after();
-        issue_ak_bmn(tmem_base + COL_DQ, sds, sk, j > 0);   // dQ += dS K
-        umma_commit(&kv_empty[st]);
+        const uint32_t sk = smem_u32(smem + DQ_K + st * (TK * THD * 2)) + hk * (SUB * 128);
+        issue_a64_bmn(tmem_base + COL_DQ, smem_u32(smem + DQ_DS + bb * (TQ * SUB * 2)), sk, u > 0);   // dQ += dS K_sub
+        umma_commit(&ds_empty[bb]);
+        if (hk == 1) umma_commit(&kv_empty[st]);
       }
       umma_commit(acc_full);
     }
@@ -359,36 +376,36 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     const int64_t li = ((int64_t)b * H + h) * S + qi;
     const float L2 = (qi < S) ? lse[li] * kLog2e : INFINITY;   // +inf => P = 0 for rows past the sequence end
     const float Dls = (qi < S) ? delta[li] * scale : 0.f;
-    auto block = [&](int j, auto diag_tag) {
+    auto sub = [&](int u, auto diag_tag) {
       constexpr bool DIAG = decltype(diag_tag)::value;
-      const int kbase = j * TK + half * 64;
-      mbar_wait(s_full, j & 1);
+      const int bb = u & 1;
+      const int kbase = (u >> 1) * TK + (u & 1) * SUB + half * 32;
+      mbar_wait(&sdp_full[bb], (u >> 1) & 1);
       tc_fence_after();
-      uint32_t sv_[64], dv_[64];
+      uint32_t sv_[32], dv_[32];
       __syncwarp();
-      tmem_ld32(lane_addr + COL_S + half * 64, sv_);
-      tmem_ld32(lane_addr + COL_S + half * 64 + 32, sv_ + 32);
-      tmem_ld32(lane_addr + COL_DP + half * 64, dv_);
-      tmem_ld32(lane_addr + COL_DP + half * 64 + 32, dv_ + 32);
+      tmem_ld32(lane_addr + COL_S + bb * SUB + half * 32, sv_);
+      tmem_ld32(lane_addr + COL_DP + bb * SUB + half * 32, dv_);
       tmem_ld_wait();
-#pragma unroll
-      for (int c = 0; c < 64; c += 32) {
-        float f[32];
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          float x = fmaf(__uint_as_float(sv_[c + i]), scale_log2, -L2);
-          if (DIAG && (kbase + c + i > qi)) x = -INFINITY;
-          f[i] = ex2(x) * fmaf(__uint_as_float(dv_[c + i]), scale, -Dls);     // P * (dP - delta) * scale
-        }
-        store_row_chunk32(smem + DQ_DS, r, half * 64 + c, f);
-      }
-      fence_async_smem();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(ds_full);
+      if (lane == 0) mbar_arrive(&sdp_empty[bb]);              // TMEM sub-block handed back to the MMA warp
+      float f[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        float x = fmaf(__uint_as_float(sv_[i]), scale_log2, -L2);
+        if (DIAG && (kbase + i > qi)) x = -INFINITY;
+        f[i] = ex2(x) * fmaf(__uint_as_float(dv_[i]), scale, -Dls);     // P * (dP - delta) * scale
+      }
+      mbar_wait(&ds_empty[bb], ((u >> 1) & 1) ^ 1);
+      store_row_chunk32(smem + DQ_DS + bb * (TQ * SUB * 2), r, half * 32, f);
+      fence_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&ds_full[bb]);
     };
-    for (int j = 0; j < nblk - 1; ++j) block(j, std::false_type{});
-    block(nblk - 1, std::true_type{});
+    for (int u = 0; u < nsub - 2; ++u) sub(u, std::false_type{});
+    sub(nsub - 2, std::true_type{});
+    sub(nsub - 1, std::true_type{});
     mbar_wait(acc_full, 0);
     tc_fence_after();
     {
@@ -420,11 +437,11 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
 
 constexpr int DK_K = 0;                              // 16 KB  K tile
 constexpr int DK_V = DK_K + TK * THD * 2;            // 16 KB  V tile
-constexpr int DK_Q = DK_V + TK * THD * 2;            // 2 x 16 KB Q tiles
+constexpr int DK_Q = DK_V + TK * THD * 2;            // 2 x 16 KB Q tiles (128 queries = two sub-blocks each)
 constexpr int DK_DO = DK_Q + 2 * TQ * THD * 2;       // 2 x 16 KB dO tiles
-constexpr int DK_PT = DK_DO + 2 * TQ * THD * 2;      // 32 KB P^T
-constexpr int DK_DST = DK_PT + TK * TQ * 2;          // 32 KB dS^T
-constexpr int DK_LD = DK_DST + TK * TQ * 2;          // 2 x (128 lse*log2e + 128 delta*scale) floats
+constexpr int DK_PT = DK_DO + 2 * TQ * THD * 2;      // 2 x 16 KB P^T sub-tiles [128 keys x 64 q]
+constexpr int DK_DST = DK_PT + 2 * TK * SUB * 2;     // 2 x 16 KB dS^T sub-tiles
+constexpr int DK_LD = DK_DST + 2 * TK * SUB * 2;     // 2 x (128 lse*log2e + 128 delta*scale) floats
 constexpr int DK_BAR = DK_LD + 2 * 256 * 4;
 constexpr int kDkSmem = DK_BAR + 256 + 1024;
 
@@ -436,13 +453,15 @@ attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + DK_BAR);
-  uint64_t* kv_full = bars;         // K + V landed
-  uint64_t* qd_full = bars + 1;     // [2] Q_i + dO_i landed
-  uint64_t* qd_empty = bars + 3;    // [2]
-  uint64_t* st_full = bars + 5;     // S^T and dP^T ready
-  uint64_t* pt_full = bars + 6;     // P^T and dS^T tiles written (256 arrivals)
-  uint64_t* acc_full = bars + 7;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+  uint64_t* kv_full = bars;           // K + V landed
+  uint64_t* qd_full = bars + 1;       // [2] Q_i + dO_i tiles landed
+  uint64_t* qd_empty = bars + 3;      // [2]
+  uint64_t* sdp_full = bars + 5;      // [2] S^T and dP^T sub-block ready
+  uint64_t* sdp_empty = bars + 7;     // [2] ... read back (8 warp arrivals)
+  uint64_t* pt_full = bars + 9;       // [2] P^T and dS^T sub-tiles written (8 warp arrivals)
+  uint64_t* pt_empty = bars + 11;     // [2] ... consumed by the dV / dK MMAs
+  uint64_t* acc_full = bars + 13;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int kvb = blockIdx.x, kvh = blockIdx.y, b = blockIdx.z;
@@ -450,14 +469,17 @@ attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
   const int k0 = kvb * TK;
   const int nqb = (S + TQ - 1) / TQ;
   const int nq_iter = nqb - kvb;
-  const int total = rep * nq_iter;
+  const int total = rep * nq_iter;      // 128-query tiles
+  const int nsub = 2 * total;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV); tma_prefetch_desc(&tmDO);
     mbar_init(kv_full, 1);
-    for (int i = 0; i < 2; ++i) { mbar_init(&qd_full[i], 1); mbar_init(&qd_empty[i], 1); }
-    mbar_init(st_full, 1);
-    mbar_init(pt_full, 8);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&qd_full[i], 1); mbar_init(&qd_empty[i], 1);
+      mbar_init(&sdp_full[i], 1); mbar_init(&sdp_empty[i], 8);
+      mbar_init(&pt_full[i], 8); mbar_init(&pt_empty[i], 1);
+    }
     mbar_init(acc_full, 1);
     mbar_fence_init();
   }
@@ -485,22 +507,30 @@ attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
   } else if (warp == 1) {
     if (lane == 0) {
       const uint32_t sk = smem_u32(smem + DK_K), sv = smem_u32(smem + DK_V);
-      const uint32_t spt = smem_u32(smem + DK_PT), sdst = smem_u32(smem + DK_DST);
+      auto issue_sdp = [&](int u) {
+        const int it = u >> 1, hq = u & 1, st = it & 1, bb = u & 1;
+        if (hq == 0) mbar_wait(&qd_full[st], (it >> 1) & 1);
+        mbar_wait(&sdp_empty[bb], ((u >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t sq = smem_u32(smem + DK_Q + st * (TQ * THD * 2)) + hq * (SUB * 128);
+        const uint32_t sdo = smem_u32(smem + DK_DO + st * (TQ * THD * 2)) + hq * (SUB * 128);
+        issue_nt_64(tmem_base + COL_ST + bb * SUB, sk, sq);      // S^T  = K Q_sub^T
+        issue_nt_64(tmem_base + COL_DPT + bb * SUB, sv, sdo);    // dP^T = V dO_sub^T
+        umma_commit(&sdp_full[bb]);
+      };
       mbar_wait(kv_full, 0);
-      for (int it = 0; it < total; ++it) {
-        const int st = it & 1;
-        const uint32_t sq = smem_u32(smem + DK_Q + st * (TQ * THD * 2));
-        const uint32_t sdo = smem_u32(smem + DK_DO + st * (TQ * THD * 2));
-        mbar_wait(&qd_full[st], (it >> 1) & 1);
+      issue_sdp(0);
+      for (int u = 0; u < nsub; ++u) {
+        if (u + 1 < nsub) issue_sdp(u + 1);
+        const int it = u >> 1, hq = u & 1, st = it & 1, bb = u & 1;
+        mbar_wait(&pt_full[bb], (u >> 1) & 1);
         tc_fence_after();
-        issue_nt_128(tmem_base + COL_ST, sk, sq);      // S^T  = K Q^T
-        issue_nt_128(tmem_base + COL_DPT, sv, sdo);    // dP^T = V dO^T
-        umma_commit(st_full);
-        mbar_wait(pt_full, it & 1);
-        tc_fence_after();
-        issue_ak_bmn(tmem_base + COL_DV, spt, sdo, it > 0);    // dV += P^T dO
-        issue_ak_bmn(tmem_base + COL_DK, sdst, sq, it > 0);    // dK += dS^T Q
-        umma_commit(&qd_empty[st]);
+        const uint32_t sq = smem_u32(smem + DK_Q + st * (TQ * THD * 2)) + hq * (SUB * 128);
+        const uint32_t sdo = smem_u32(smem + DK_DO + st * (TQ * THD * 2)) + hq * (SUB * 128);
+        issue_a64_bmn(tmem_base + COL_DV, smem_u32(smem + DK_PT + bb * (TK * SUB * 2)), sdo, u > 0);   // dV += P^T dO
+        issue_a64_bmn(tmem_base + COL_DK, smem_u32(smem + DK_DST + bb * (TK * SUB * 2)), sq, u > 0);   // dK += dS^T Q
+        umma_commit(&pt_empty[bb]);
+        if (hq == 1) umma_commit(&qd_empty[st]);
       }
       umma_commit(acc_full);
     }
@@ -510,61 +540,59 @@ attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
     const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16);
     const float scale_log2 = scale * kLog2e;
     const int ctid = threadIdx.x - 64;                         // 0..255 among the compute warps
-    auto iter = [&](int it, auto diag_tag) {
+    auto sub = [&](int u, auto diag_tag) {
       constexpr bool DIAG = decltype(diag_tag)::value;
+      const int it = u >> 1, hq = u & 1, bb = u & 1;
       const int h = kvh * rep + it / nq_iter, qb = kvb + it % nq_iter;
-      const int qbase = qb * TQ + half * 64;
-      // stage this query block's lse*log2e (+inf past the sequence end => P = 0) and delta*scale once per CTA
       float* sLD = reinterpret_cast<float*>(smem + DK_LD) + (it & 1) * 256;
-      {
+      if (hq == 0) {
+        // stage this 128-query tile's lse*log2e (+inf past the sequence end => P = 0) and delta*scale once per CTA
         const int q = qb * TQ + (ctid & 127);
         const int64_t li = ((int64_t)b * H + h) * S + q;
         float val;
         if (ctid < 128) val = (q < S) ? __ldg(lse + li) * kLog2e : INFINITY;
         else val = (q < S) ? __ldg(delta + li) * scale : 0.f;
         sLD[ctid] = val;
+        named_bar_sync(1, 256);
       }
-      named_bar_sync(1, 256);
-      mbar_wait(st_full, it & 1);
+      const int col0 = hq * SUB + half * 32;                   // first query column (inside the 128-query tile)
+      const int qbase = qb * TQ + col0;
+      mbar_wait(&sdp_full[bb], (u >> 1) & 1);
       tc_fence_after();
-      uint32_t sv_all[64], dv_all[64];
+      uint32_t sv_[32], dv_[32];
       __syncwarp();
-      tmem_ld32(lane_addr + COL_ST + half * 64, sv_all);
-      tmem_ld32(lane_addr + COL_ST + half * 64 + 32, sv_all + 32);
-      tmem_ld32(lane_addr + COL_DPT + half * 64, dv_all);
-      tmem_ld32(lane_addr + COL_DPT + half * 64 + 32, dv_all + 32);
+      tmem_ld32(lane_addr + COL_ST + bb * SUB + half * 32, sv_);
+      tmem_ld32(lane_addr + COL_DPT + bb * SUB + half * 32, dv_);
       tmem_ld_wait();
-#pragma unroll
-      for (int c = 0; c < 64; c += 32) {
-        const uint32_t* sv_ = sv_all + c;
-        const uint32_t* dv_ = dv_all + c;
-        float pf[32], df[32];
-        const float4* L4 = reinterpret_cast<const float4*>(sLD + half * 64 + c);
-        const float4* D4 = reinterpret_cast<const float4*>(sLD + 128 + half * 64 + c);
-#pragma unroll
-        for (int i4 = 0; i4 < 8; ++i4) {
-          const float4 Lq = L4[i4], Dq = D4[i4];
-          const float Ls[4] = {Lq.x, Lq.y, Lq.z, Lq.w}, Ds[4] = {Dq.x, Dq.y, Dq.z, Dq.w};
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const int i = i4 * 4 + u;
-            float x = fmaf(__uint_as_float(sv_[i]), scale_log2, -Ls[u]);
-            if (DIAG && (kj > qbase + c + i)) x = -INFINITY;
-            const float pv = ex2(x);
-            pf[i] = pv;
-            df[i] = pv * fmaf(__uint_as_float(dv_[i]), scale, -Ds[u]);
-          }
-        }
-        store_row_chunk32(smem + DK_PT, r, half * 64 + c, pf);
-        store_row_chunk32(smem + DK_DST, r, half * 64 + c, df);
-      }
-      fence_async_smem();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(pt_full);
+      if (lane == 0) mbar_arrive(&sdp_empty[bb]);
+      float pf[32], df[32];
+      const float4* L4 = reinterpret_cast<const float4*>(sLD + col0);
+      const float4* D4 = reinterpret_cast<const float4*>(sLD + 128 + col0);
+#pragma unroll
+      for (int i4 = 0; i4 < 8; ++i4) {
+        const float4 Lq = L4[i4], Dq = D4[i4];
+        const float Ls[4] = {Lq.x, Lq.y, Lq.z, Lq.w}, Ds[4] = {Dq.x, Dq.y, Dq.z, Dq.w};
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const int i = i4 * 4 + t;
+          float x = fmaf(__uint_as_float(sv_[i]), scale_log2, -Ls[t]);
+          if (DIAG && (kj > qbase + i)) x = -INFINITY;
+          const float pv = ex2(x);
+          pf[i] = pv;
+          df[i] = pv * fmaf(__uint_as_float(dv_[i]), scale, -Ds[t]);
+        }
+      }
+      mbar_wait(&pt_empty[bb], ((u >> 1) & 1) ^ 1);
+      store_row_chunk32(smem + DK_PT + bb * (TK * SUB * 2), r, half * 32, pf);
+      store_row_chunk32(smem + DK_DST + bb * (TK * SUB * 2), r, half * 32, df);
+      fence_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&pt_full[bb]);
     };
-    for (int it = 0; it < total; ++it) {
-      if (it % nq_iter == 0) iter(it, std::true_type{}); else iter(it, std::false_type{});
+    for (int u = 0; u < nsub; ++u) {
+      if ((u >> 1) % nq_iter == 0) sub(u, std::true_type{}); else sub(u, std::false_type{});
     }
     mbar_wait(acc_full, 0);
     tc_fence_after();
