@@ -195,6 +195,7 @@ def main():
     ap.add_argument("--cpu-seq", type=int, default=256, help="sequence length of the bounded CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="issue every kernel launch from Python (no CUDA graph)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -229,16 +230,21 @@ def main():
         trainer.model = model                      # adapters were applied by build_model (seeded)
         trainer.prepare_optimizer()
         step = lambda batch: trainer.train_step(batch)                      # noqa: E731
+        eager_step = lambda batch: trainer._step_impl(batch, 1.0)           # noqa: E731
     else:
         trainer = CSMTrainer("", outdir, device=str(device))
         trainer.logger.setLevel(logging.ERROR)
         trainer.model = model
         trainer.prepare_optimizer()
 
-        def step(batch):
+        step = lambda batch: trainer.train_step(batch)                      # noqa: E731
+
+        def eager_step(batch):
             loss = trainer.train_micro_batch(batch, 1)
             trainer.optimizer_step(1.0)
             return loss
+    if not args.no_graph:
+        trainer.enable_cuda_graph(warmup=args.warmup)
 
     n_batches = 4
     host = [synthetic_batch(128256, 2051, 32, B, S, seed=1234 + rank + 97 * i) for i in range(n_batches)]
@@ -266,7 +272,8 @@ def main():
         return float(ms.item())
 
     # ---- warm-up (also instantiates optimizer state, cuda modules)
-    for i in range(args.warmup):
+    n_warm = args.warmup + (2 if not args.no_graph else 0)       # graph mode: W eager steps, then capture + 1 replay
+    for i in range(n_warm):
         step(resident[i % n_batches])
     torch.cuda.synchronize()
 
@@ -277,6 +284,8 @@ def main():
     l0 = _lib.launch_count()
     ms_total = timed(lambda i: step(resident[i % n_batches]), args.steps)
     launches = _lib.launch_count() - l0
+    if not args.no_graph and getattr(trainer, "_graphed", None) is not None and trainer._graphed.graph is not None:
+        launches = trainer._graphed.kernels_per_replay * args.steps   # replayed graph nodes (counted at capture)
     clk = clocks.stop() if rank == 0 else None
     ms_step = ms_total / args.steps
     frames_per_step = world * B * S
@@ -301,7 +310,7 @@ def main():
     if rank == 0:
         ops.gemm_profile_start()
     for i in range(2):
-        step(resident[i % n_batches])
+        eager_step(resident[i % n_batches])
     torch.cuda.synchronize()
     if rank == 0:
         flops, gms, n_g = ops.gemm_profile_stop()
@@ -338,6 +347,7 @@ def main():
                 "config": {"workload": desc, "name": args.config, "batch_per_gpu": B, "global_batch": B * world,
                            "seq_len": S, "decoder_frames_per_gpu": n_sel,
                            "parallelism": f"dp{world}" if world > 1 else "single",
+                           "cuda_graph": not args.no_graph,
                            "l2": "per-step working set (3.1 GB weights + >4 GB activations) exceeds the 126 MB L2; "
                                  "4 distinct input batches cycled"},
                 "clocks": clk, "e2e": e2e, "gpu_launches": launches, "gpu_launches_per_step": launches / args.steps,

@@ -17,6 +17,7 @@ import torch
 from ..models import lora as lora_mod
 from ..models.model import Model
 from . import dp
+from .graph import GraphedStep
 from .trainer import csm_1b_args, iterate_batches
 from .utils import compute_loss, setup_logger
 
@@ -46,6 +47,7 @@ class CSMLoRATrainer:
         self.model = model
         self.optimizer = None
         self._sync = None
+        self._graphed = None
         self._load_model_with_lora()
         self.epoch, self.global_step, self.best_loss = 0, 0, float("inf")
 
@@ -78,9 +80,17 @@ class CSMLoRATrainer:
         params = list(self.get_lora_params().values())
         n = sum(p.numel() for p in params)
         self.logger.info(f"LoRA: {len(params)} tensors, {n:,} trainable parameters")
+        on_cuda = params[0].is_cuda
         self.optimizer = torch.optim.AdamW(params, lr=self.learning_rate, weight_decay=self.weight_decay,
-                                           fused=params[0].is_cuda)
+                                           fused=on_cuda, capturable=on_cuda)
         self._sync = dp.GradSynchronizer(params)
+
+    def enable_cuda_graph(self, warmup: int = 3, max_grad_norm: float = 1.0) -> None:
+        """Replay the whole optimiser step as one CUDA graph once shapes are static (see training/graph.py)."""
+        if self.optimizer is None:
+            self.prepare_optimizer()
+        self._graph_max_norm = max_grad_norm
+        self._graphed = GraphedStep(lambda b: self._step_impl(b, max_grad_norm), self.device, warmup)
 
     def _to_device(self, batch):
         if "frame_idx" not in batch:
@@ -94,7 +104,16 @@ class CSMLoRATrainer:
         device tensors).  Returns the detached loss tensor (on device; reading it is the caller's D2H)."""
         if self.optimizer is None:
             self.prepare_optimizer()
-        b = self._to_device(batch)
+        if "frame_idx" not in batch:
+            batch = dict(batch)
+            batch["frame_idx"] = Model.select_frames(batch["input_masks"], batch["target_audio_tokens"].shape[1],
+                                                     self.decoder_frame_fraction)
+        self.global_step += 1
+        if self._graphed is not None and max_grad_norm == self._graph_max_norm:
+            return self._graphed(batch)
+        return self._step_impl({k: v.to(self.device, non_blocking=True) for k, v in batch.items()}, max_grad_norm)
+
+    def _step_impl(self, b, max_grad_norm: float) -> torch.Tensor:
         loss, _ = compute_loss(self.model, b["input_tokens"], b["input_masks"], b["target_audio_tokens"],
                                self.semantic_weight, self.acoustic_weight, frame_idx=b["frame_idx"])
         loss.backward()
@@ -103,7 +122,6 @@ class CSMLoRATrainer:
             torch.nn.utils.clip_grad_norm_(list(self.get_lora_params().values()), max_grad_norm)
         self.optimizer.step()
         self.optimizer.zero_grad(set_to_none=True)
-        self.global_step += 1
         return loss.detach()
 
     def train(self, train_dataset, val_dataset=None, batch_size: int = 2, epochs: int = 5, val_every: int = 100,

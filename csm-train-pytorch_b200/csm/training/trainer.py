@@ -16,6 +16,7 @@ import torch
 
 from ..models.model import Model, ModelArgs
 from . import dp
+from .graph import GraphedStep
 from .utils import compute_loss, load_checkpoint, save_checkpoint, setup_logger
 
 
@@ -72,6 +73,7 @@ class CSMTrainer:
         self.model = None
         self.optimizer = None
         self._sync = None
+        self._graphed = None
         self._load_model()
         self.epoch = 0
         self.global_step = 0
@@ -113,9 +115,40 @@ class CSMTrainer:
             {"params": groups["embeddings"], "lr": lr * self.embedding_lr_multiplier},
             {"params": groups["other"], "lr": lr}) if g["params"]]
         on_cuda = next(self.model.parameters()).is_cuda
-        self.optimizer = torch.optim.AdamW(param_groups, weight_decay=self.weight_decay, fused=on_cuda)
+        self.optimizer = torch.optim.AdamW(param_groups, weight_decay=self.weight_decay, fused=on_cuda,
+                                           capturable=on_cuda)
         trainable = [p for p in self.model.parameters() if p.requires_grad]
         self._sync = dp.GradSynchronizer(trainable, bucket_bytes=64 << 20 if total > (32 << 20) else None)
+
+    def enable_cuda_graph(self, warmup: int = 3, max_grad_norm: float = 1.0) -> None:
+        """``train_step`` (one micro-batch + optimiser step) replayed as one CUDA graph (training/graph.py)."""
+        if self.optimizer is None:
+            self.prepare_optimizer()
+
+        def impl(b):
+            loss, _ = compute_loss(self.model, b["input_tokens"], b["input_masks"], b["target_audio_tokens"],
+                                   self.semantic_weight, self.acoustic_weight, frame_idx=b["frame_idx"])
+            loss.backward()
+            self._sync.finish()
+            if max_grad_norm and max_grad_norm > 0:
+                torch.nn.utils.clip_grad_norm_([p for p in self.model.parameters() if p.requires_grad], max_grad_norm)
+            self.optimizer.step()
+            self.optimizer.zero_grad(set_to_none=True)
+            return loss.detach()
+        self._graphed = GraphedStep(impl, self.device, warmup)
+
+    def train_step(self, batch) -> torch.Tensor:
+        """One micro-batch followed by one optimiser step (accumulation 1); graph-replayed when enabled."""
+        if "frame_idx" not in batch:
+            batch = dict(batch)
+            batch["frame_idx"] = Model.select_frames(batch["input_masks"], batch["target_audio_tokens"].shape[1],
+                                                     self.decoder_frame_fraction)
+        if getattr(self, "_graphed", None) is not None:
+            self.global_step += 1
+            return self._graphed(batch)
+        loss = self.train_micro_batch(batch, 1)
+        self.optimizer_step(1.0)
+        return loss
 
     def _to_device(self, batch) -> Dict[str, torch.Tensor]:
         if "frame_idx" not in batch:                  # A8: chosen on the host copy, before the H2D copy

@@ -1,0 +1,138 @@
+"""GPU tests of the trainer layer: CSMLoRATrainer / CSMTrainer steps through the kernels, CUDA-graph replay equals
+eager execution, adapter save / load / merge round trips."""
+import copy
+import json
+import os
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _small_model(device, seed=0):
+    from csm.models.model import Model, ModelArgs
+    from oracle import csm_oracle as O
+    cfg = O.cfg_small()
+    orc = O.OracleModel(cfg)
+    O.init_weights(orc, seed)
+    m = Model(ModelArgs("small-backbone", "small-decoder", cfg.text_vocab_size, cfg.audio_vocab_size,
+                        cfg.audio_num_codebooks)).to(torch.bfloat16)
+    m.load_state_dict(orc.to(torch.bfloat16).state_dict())
+    return m.to(device), cfg
+
+
+def _batches(cfg, n, B=2, S=128):
+    from csm.data.synthetic import synthetic_batch
+    return [synthetic_batch(cfg.text_vocab_size, cfg.audio_vocab_size, cfg.audio_num_codebooks, B, S, seed=100 + i)
+            for i in range(n)]
+
+
+def _lora_trainer(tmp_path, device, graph):
+    from csm.models import lora
+    from csm.training.lora_trainer import CSMLoRATrainer
+    model, cfg = _small_model(device)
+    t = CSMLoRATrainer("", str(tmp_path), learning_rate=1e-3, lora_r=8, model=None, device=str(device))
+    lora.apply_lora(model, r=8, alpha=16.0, seed=3, b_std=0.02)
+    t.model = model
+    t.prepare_optimizer()
+    if graph:
+        t.enable_cuda_graph(warmup=2)
+    return t, cfg
+
+
+def test_lora_train_step_graph_equals_eager(cuda, tmp_path):
+    te, cfg = _lora_trainer(tmp_path / "e", cuda, graph=False)
+    tg, _ = _lora_trainer(tmp_path / "g", cuda, graph=True)
+    batches = _batches(cfg, 6)
+    le = [float(te.train_step(b)) for b in batches]
+    lg = [float(tg.train_step(b)) for b in batches]        # steps 1-2 eager, step 3 captures, 4-6 replay
+    assert tg._graphed.graph is not None and tg._graphed.kernels_per_replay > 100
+    for a, b in zip(le, lg):
+        assert abs(a - b) <= 2e-3 * abs(a), (le, lg)
+    assert le[-1] < le[0]                                   # it trains
+    pe, pg = te.get_lora_params(), tg.get_lora_params()
+    for n in pe:
+        assert torch.allclose(pe[n].float(), pg[n].float(), atol=2e-3, rtol=2e-2), n
+
+
+def test_full_finetune_trainer_steps_and_graph(cuda, tmp_path):
+    from csm.training.trainer import CSMTrainer
+    losses = {}
+    for graph in (False, True):
+        model, cfg = _small_model(cuda)
+        t = CSMTrainer("", str(tmp_path / f"ft{int(graph)}"), device=str(cuda), learning_rate=2e-4)
+        t.model = model
+        t.prepare_optimizer()
+        if graph:
+            t.enable_cuda_graph(warmup=2)
+        losses[graph] = [float(t.train_step(b)) for b in _batches(cfg, 5)]
+        assert len(t.optimizer.param_groups) == 4          # backbone / decoder / embeddings / other (trainer.py:166-173)
+        lrs = sorted(g["lr"] for g in t.optimizer.param_groups)
+        assert lrs == sorted([2e-4 * 0.1, 2e-4 * 1.0, 2e-4 * 0.5, 2e-4])
+    for a, b in zip(losses[False], losses[True]):
+        assert abs(a - b) <= 5e-3 * abs(a), losses
+    assert losses[False][-1] < losses[False][0]
+
+
+def test_freeze_flags_and_grad_accumulation(cuda, tmp_path):
+    from csm.training.trainer import CSMTrainer
+    model, cfg = _small_model(cuda)
+    t = CSMTrainer("", str(tmp_path), device=str(cuda))
+    t.model = model
+    t.prepare_optimizer(freeze_backbone=True, freeze_embeddings=True)
+    assert not any(p.requires_grad for n, p in model.named_parameters() if "backbone" in n or "embeddings" in n)
+    b = _batches(cfg, 2)
+    t.train_micro_batch(b[0], accumulation_steps=2)
+    g1 = model.audio_head.grad.clone()
+    t.train_micro_batch(b[1], accumulation_steps=2)         # accumulates into .grad
+    assert not torch.equal(model.audio_head.grad, g1)
+    assert model.backbone.layers[0].attn.q_proj.weight.grad is None
+    t.optimizer_step(1.0)
+    assert model.audio_head.grad is None and t.global_step == 1
+
+
+def test_lora_save_load_merge_roundtrip(cuda, tmp_path):
+    from safetensors.torch import load_file
+    t, cfg = _lora_trainer(tmp_path, cuda, graph=False)
+    b = _batches(cfg, 1)[0]
+    t.train_step(b)
+    path = str(tmp_path / "adapter.safetensors")
+    t.save_model(path, "both")
+    lora_file = path.replace(".safetensors", "_lora.safetensors")
+    meta = json.load(open(lora_file.replace(".safetensors", "_metadata.json")))
+    assert meta["lora_r"] == 8 and meta["target_modules"] == ["q_proj", "v_proj"]
+    tensors = load_file(lora_file)
+    assert set(tensors) == set(t.get_lora_params())
+    assert "backbone.layers.0.attn.q_proj.lora_A" in tensors
+    # merged weights: W0 + (alpha/r) B A (lora.py:140-153), computed by the GEMM kernel
+    full = load_file(path.replace(".safetensors", "_full.safetensors"))
+    mod = t.model.backbone.layers[0].attn.q_proj
+    ref = mod.weight.float() + mod.lora_scaling * (mod.lora_B.float() @ mod.lora_A.float())
+    assert torch.allclose(full["backbone.layers.0.attn.q_proj.weight"].float().to(cuda), ref, atol=2e-2, rtol=2e-2)
+    assert not any(k.endswith(("lora_A", "lora_B")) for k in full)
+    # load back into a fresh trainer: identical loss on the same batch
+    t2, _ = _lora_trainer(tmp_path / "b", cuda, graph=False)
+    t2.load_lora_weights(lora_file)
+    from csm.training.utils import compute_loss
+    dev_b = {k: v.to(cuda) for k, v in b.items()}
+    with torch.no_grad():
+        l1, _ = compute_loss(t.model, dev_b["input_tokens"], dev_b["input_masks"], dev_b["target_audio_tokens"],
+                             frame_idx=dev_b["frame_idx"])
+        l2, _ = compute_loss(t2.model, dev_b["input_tokens"], dev_b["input_masks"], dev_b["target_audio_tokens"],
+                             frame_idx=dev_b["frame_idx"])
+    assert abs(float(l1) - float(l2)) < 1e-3 * abs(float(l1))
+
+
+def test_merge_lora_in_place_matches_adapter_forward(cuda, tmp_path):
+    from csm.models import lora
+    from csm.training.utils import compute_loss
+    t, cfg = _lora_trainer(tmp_path, cuda, graph=False)
+    b = {k: v.to(cuda) for k, v in _batches(cfg, 1)[0].items()}
+    with torch.no_grad():
+        l_adapter, _ = compute_loss(t.model, b["input_tokens"], b["input_masks"], b["target_audio_tokens"],
+                                    frame_idx=b["frame_idx"])
+        lora.merge_lora(t.model)                            # W += s B A ; B = 0
+        l_merged, _ = compute_loss(t.model, b["input_tokens"], b["input_masks"], b["target_audio_tokens"],
+                                   frame_idx=b["frame_idx"])
+    assert abs(float(l_adapter) - float(l_merged)) < 5e-3 * abs(float(l_adapter))
