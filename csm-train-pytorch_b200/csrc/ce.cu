@@ -15,8 +15,12 @@ int linear_ce_tc_fwd(const void* H, const void* W, const int64_t* targets, float
                      int64_t V, int64_t K, int groups, int64_t ldh, int64_t hgs, int64_t ldw, int64_t wgs,
                      int transW, int64_t trs, int64_t tgs, void* ws, size_t ws_bytes, cudaStream_t st);
 int linear_ce_tc_bwd_dlogits(const void* H, const void* W, const int64_t* targets, const float* lse,
-                             float grad_scale, const float* grad_scale_dev, void* dlogits, int64_t ldd, int64_t M, int64_t V, int64_t K,
-                             int64_t ldh, int64_t ldw, int transW, int64_t trs, cudaStream_t st);
+                             float grad_scale, const float* grad_scale_dev, void* dlogits, int64_t ldd, int64_t M,
+                             int64_t V, int64_t K, int groups, int64_t ldh, int64_t hgs, int64_t ldw, int64_t wgs,
+                             int64_t trs, int64_t tgs, cudaStream_t st);
+int gemm_tc_grouped(const void* A, const void* B, void* C, int64_t M, int64_t N, int64_t K, int groups, int64_t lda,
+                    int64_t ags, int64_t ldb, int64_t bgs, int64_t ldc, int64_t cgs, int transA, int transB,
+                    int accumulate, cudaStream_t st);
 bool linear_ce_tc_supported(int64_t M, int64_t V, int64_t K, int64_t ldh, int64_t ldw, int transW,
                             const void* H, const void* W);
 size_t linear_ce_tc_workspace(int64_t M, int64_t V, int groups);
@@ -103,7 +107,7 @@ extern "C" size_t csm_linear_ce_workspace_bytes(int64_t M, int64_t V, int64_t K,
   (void)K;
   const int64_t v8 = round_up(V, 8);
   size_t generic = (size_t)M * V * sizeof(float) + (size_t)M * v8 * sizeof(bf16) + 256;
-  size_t tc = linear_ce_tc_workspace(M, V, groups) + (size_t)M * v8 * sizeof(bf16) + 256;
+  size_t tc = linear_ce_tc_workspace(M, V, groups) + (size_t)groups * M * v8 * sizeof(bf16) + 256;
   return generic > tc ? generic : tc;
 }
 
@@ -160,23 +164,34 @@ extern "C" int csm_linear_ce_bwd(const void* H, const void* W, const int64_t* ta
   size_t off = use_tc ? 0 : ((size_t)M * V * sizeof(float) + 255) / 256 * 256;
   bf16* dlog = reinterpret_cast<bf16*>(wsp + off);
   const int gb = use_tc ? CSM_GEMM_AUTO : CSM_GEMM_SIMT;
+  if (use_tc) {
+    // tcgen05 path: every head in one launch per stage — dlogits [groups, M, v8], then grouped dH / dW GEMMs
+    int rc = linear_ce_tc_bwd_dlogits(H, W, targets, lse, grad_scale, grad_scale_dev, dlog, v8, M, V, K, groups, ldh,
+                                      h_group_stride, ldw, w_group_stride, tgt_row_stride, tgt_group_stride, st);
+    if (rc) return rc;
+    if (dH) {  // dH_g[M,K] = dlogits_g[M,V] * W_g   (W_g stored [V,K]: the [K_red, N_out] layout => transB)
+      rc = gemm_tc_grouped(dlog, W, dH, M, K, V, groups, v8, M * v8, ldw, w_group_stride, lddh, dh_group_stride, 0, 1,
+                           0, st);
+      if (rc) return rc;
+    }
+    if (dW) {  // dW_g[V,K] = dlogits_g^T[V,M] * H_g[M,K]
+      rc = gemm_tc_grouped(dlog, H, dW, V, K, M, groups, v8, M * v8, ldh, h_group_stride, ldw, w_group_stride, 1, 1,
+                           dw_accumulate, st);
+      if (rc) return rc;
+    }
+    return CSM_OK;
+  }
   for (int g = 0; g < groups; ++g) {
     const bf16* Hg = (const bf16*)H + g * h_group_stride;
     const bf16* Wg = (const bf16*)W + g * w_group_stride;
     const int64_t* tg = targets + g * tgt_group_stride;
     const float* lg = lse + (int64_t)g * M;
-    int rc;
-    if (use_tc) {
-      rc = linear_ce_tc_bwd_dlogits(Hg, Wg, tg, lg, grad_scale, grad_scale_dev, dlog, v8, M, V, K, ldh, ldw, transW,
-                                    tgt_row_stride, st);
-      if (rc) return rc;
-    } else {
-      rc = gemm_dispatch(Hg, Wg, logits, nullptr, M, V, K, ldh, ldw, V, 0, 0, transW, CSM_DT_F32, 0, 1.f, nullptr,
-                         nullptr, 0, 0, 0, CSM_GEMM_SIMT, st);
-      if (rc) return rc;
-      ce_rows_bwd_kernel<<<(unsigned)M, 128, 0, st>>>(logits, V, tg, tgt_row_stride, lg, grad_scale, grad_scale_dev, dlog, v8, V);
-      CSM_CHECK_LAUNCH("ce_rows_bwd");
-    }
+    int rc = gemm_dispatch(Hg, Wg, logits, nullptr, M, V, K, ldh, ldw, V, 0, 0, transW, CSM_DT_F32, 0, 1.f, nullptr,
+                           nullptr, 0, 0, 0, CSM_GEMM_SIMT, st);
+    if (rc) return rc;
+    ce_rows_bwd_kernel<<<(unsigned)M, 128, 0, st>>>(logits, V, tg, tgt_row_stride, lg, grad_scale, grad_scale_dev,
+                                                    dlog, v8, V);
+    CSM_CHECK_LAUNCH("ce_rows_bwd");
     if (dH) {
       // dH[M,K] = dlogits[M,V] * W ; W stored [V,K] (transW==0) is the [K_red=V, N_out=K] row-major layout
       rc = gemm_dispatch(dlog, Wg, (bf16*)dH + g * dh_group_stride, nullptr, M, K, V, v8, ldw, lddh, 0, 0,

@@ -505,16 +505,29 @@ int linear_ce_tc_fwd(const void* H, const void* W, const int64_t* targets, float
 }
 
 int linear_ce_tc_bwd_dlogits(const void* H, const void* W, const int64_t* targets, const float* lse,
-                             float grad_scale, const float* grad_scale_dev, void* dlogits, int64_t ldd, int64_t M, int64_t V, int64_t K,
-                             int64_t ldh, int64_t ldw, int transW, int64_t trs, cudaStream_t st) {
-  (void)transW;
-  GemmTcOperands o{H, W, nullptr, nullptr, ldh, ldw, 0, 0, 0, 0, 0, 0, 0};
+                             float grad_scale, const float* grad_scale_dev, void* dlogits, int64_t ldd, int64_t M,
+                             int64_t V, int64_t K, int groups, int64_t ldh, int64_t hgs, int64_t ldw, int64_t wgs,
+                             int64_t trs, int64_t tgs, cudaStream_t st) {
+  // all heads in ONE launch: dlogits [groups, M, ldd]
+  GemmTcOperands o{H, W, nullptr, nullptr, ldh, ldw, 0, 0, 0, hgs, wgs, 0, 0};
   GemmTcParams p{};
-  p.M = M; p.N = V; p.K = K; p.groups = 1;
-  p.C = dlogits; p.ldc = ldd;
-  p.targets = targets; p.tgt_row_stride = trs; p.tgt_group_stride = 0;
+  p.M = M; p.N = V; p.K = K; p.groups = groups;
+  p.C = dlogits; p.ldc = ldd; p.c_group_stride = M * ldd;
+  p.targets = targets; p.tgt_row_stride = trs; p.tgt_group_stride = tgs;
   p.lse = lse; p.gscale = grad_scale; p.gscale_dev = grad_scale_dev;
   return gemm_tc_run(o, p, EPI_CE_DLOGITS, st);
+}
+
+// groups independent GEMMs in one launch (3-D tensor maps): C_g = op(A_g) op(B_g)
+int gemm_tc_grouped(const void* A, const void* B, void* C, int64_t M, int64_t N, int64_t K, int groups, int64_t lda,
+                    int64_t ags, int64_t ldb, int64_t bgs, int64_t ldc, int64_t cgs, int transA, int transB,
+                    int accumulate, cudaStream_t st) {
+  GemmTcOperands o{A, B, nullptr, nullptr, lda, ldb, 0, 0, 0, ags, bgs, transA, transB};
+  GemmTcParams p{};
+  p.M = M; p.N = N; p.K = K; p.groups = groups;
+  p.C = C; p.ldc = ldc; p.c_group_stride = cgs;
+  p.c_f32 = 0; p.accumulate = accumulate; p.alpha = 1.f;
+  return gemm_tc_run(o, p, EPI_STORE, st);
 }
 
 }  // namespace csm
