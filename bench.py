@@ -257,6 +257,10 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    def phase(name):
+        if os.environ.get("CSM_BENCH_TRACE"):
+            print(f"[bench rank {rank}] {name}", file=sys.stderr, flush=True)
+
     def timed(fn, K):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -274,8 +278,12 @@ def main():
     # ---- warm-up (also instantiates optimizer state, cuda modules)
     n_warm = args.warmup + (2 if not args.no_graph else 0)       # graph mode: W eager steps, then capture + 1 replay
     for i in range(n_warm):
+        phase(f"warm-up step {i}")
         step(resident[i % n_batches])
+        if os.environ.get("CSM_BENCH_TRACE"):
+            torch.cuda.synchronize()
     torch.cuda.synchronize()
+    phase("timed region")
 
     # ---- device-resident throughput (value)
     clocks = ClockSampler(local)
@@ -355,7 +363,10 @@ def main():
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
-        dist.destroy_process_group()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)       # skip NCCL/graph teardown (destroy_process_group can hang while captured graphs hold NCCL work)
 
 
 if __name__ == "__main__":

@@ -264,8 +264,21 @@ class StackFn(Function):
                 _acc(grads, i, ds.to(BF16))
             return dx
 
+        sink = getattr(stack, "_grad_sink", None)   # data-parallel bucket owner (csm/training/dp.py), optional
+
+        def hand_over(module):
+            # gradients of `module` are final: give them to the DP synchroniser now so their all-reduce overlaps the
+            # rest of this backward; autograd then receives None for them
+            if sink is None:
+                return
+            for prm in module.parameters():
+                i = index_of[id(prm)]
+                if grads[i] is not None and sink.deliver(prm, grads[i]):
+                    grads[i] = None
+
         xf, rstd_f = ctx.final
         dcur = norm_bwd(dy.reshape(N, D).contiguous(), xf, stack.norm, rstd_f, None)
+        hand_over(stack.norm)
         for (x, rstd1, xn, qkv, o, lse, h, rstd2, hn, gu, act, ts, lins, layer) in reversed(ctx.saved):
             tqkv, to, t13, t2 = ts
             gqkv, lo, g13, l2 = lins
@@ -286,6 +299,7 @@ class StackFn(Function):
             ops.rope_(dk, cache, S, KV, hd, inverse=True)
             dxn = gqkv.bwd(dqkv, xn, tqkv, grads, need)
             dcur = norm_bwd(dxn, x, layer.sa_norm, rstd1, dh)
+            hand_over(layer)
         ctx.saved = None
         dx = dcur.view(B, S, D) if ctx.needs_input_grad[0] else None
         return (dx, None) + tuple(grads)

@@ -1,14 +1,17 @@
-"""Data-parallel gradient exchange: one process per GPU, full replica each, one all-reduce(sum) of the
-trainable gradients per optimiser step over NCCL/NVLink, then x 1/world.  The reference has no multi-GPU code.
+"""Data-parallel gradient exchange: one process per GPU, full replica each, one all-reduce(mean) of the
+trainable gradients per optimiser step over NCCL/NVLink.  The reference has no multi-GPU code.
 
-  * LoRA (<= ~20 M trainable params): one flat buffer, one latency-bound all-reduce after backward.
-  * full fine-tune: reverse-order buckets launched from post-accumulate-grad hooks on a side stream so the exchange
-    overlaps the remaining backward; the local sum of squares for global-norm clipping rides in the same pass.
+  * LoRA (<= ~20 M trainable params): one flat fp32 buffer, one latency-bound all-reduce after backward.
+  * full fine-tune: gradients live in flat bf16 **bucket buffers** laid out in backward order; ``param.grad`` is a view
+    into its bucket.  The transformer stack's hand-written backward delivers each layer's gradients as soon as the
+    layer is done (``deliver``), every other parameter arrives through a post-accumulate-grad hook; a bucket is
+    all-reduced in place on a high-priority side stream the moment its last gradient lands, so the exchange overlaps
+    the remaining backward (and is captured in the step's CUDA graph as a fork/join).
 """
 from __future__ import annotations
 
 import os
-from typing import Iterable, List, Optional
+from typing import Dict, Iterable, List, Optional
 
 import torch
 import torch.distributed as dist
@@ -36,88 +39,135 @@ class GradSynchronizer:
     """Averages gradients of `params` across ranks.
 
     bucket_bytes=None -> a single flat bucket reduced in ``finish()`` (LoRA);
-    otherwise reverse-order buckets reduced asynchronously as soon as all their gradients exist (full FT).
+    otherwise flat bucket buffers (``param.grad`` = view) reduced asynchronously as they fill (full fine-tune).
     """
 
-    def __init__(self, params: Iterable[torch.nn.Parameter], bucket_bytes: Optional[int] = None,
-                 group=None):
+    def __init__(self, params: Iterable[torch.nn.Parameter], bucket_bytes: Optional[int] = None, group=None,
+                 force_buckets: bool = False):
         self.params: List[torch.nn.Parameter] = [p for p in params if p.requires_grad]
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.group = group
-        self.bucket_bytes = bucket_bytes
-        self._buckets: List[List[torch.nn.Parameter]] = []
-        self._pending = {}
-        self._works = []
+        self.bucketed = bool(bucket_bytes) and (self.world > 1 or force_buckets)
+        self.accumulating = False            # True on all but the last micro-batch of an accumulation window
         self._hooks = []
-        self._stream = None
-        if self.world > 1 and bucket_bytes:
-            cur, size = [], 0
-            for p in reversed(self.params):                 # backward produces gradients roughly in reverse order
-                cur.append(p)
-                size += p.numel() * p.element_size()
-                if size >= bucket_bytes:
-                    self._buckets.append(cur)
-                    cur, size = [], 0
-            if cur:
-                self._buckets.append(cur)
-            self._bucket_of = {id(p): bi for bi, b in enumerate(self._buckets) for p in b}
-            if self.params and self.params[0].is_cuda:
-                self._stream = torch.cuda.Stream(priority=-1)
-            for p in self.params:
-                self._hooks.append(p.register_post_accumulate_grad_hook(self._on_grad))
-            self._reset()
+        if not self.bucketed:
+            return
+        backend = dist.get_backend(group) if dist.is_initialized() else "none"
+        self._avg = backend == "nccl"        # NCCL reduces with AVG in one pass; gloo needs SUM + scale
+        self._buckets: List[Dict] = []
+        self._slot: Dict[int, tuple] = {}    # id(param) -> (bucket index, grad view)
+        cur, size = [], 0
+        order = list(reversed(self.params))  # backward produces gradients roughly in reverse parameter order
 
+        def close(ps):
+            n = sum(p.numel() for p in ps)
+            buf = torch.zeros(n, dtype=ps[0].dtype, device=ps[0].device)
+            bi, off = len(self._buckets), 0
+            for p in ps:
+                self._slot[id(p)] = (bi, buf[off:off + p.numel()].view(p.shape))
+                off += p.numel()
+            self._buckets.append({"buf": buf, "n": len(ps), "params": ps})
+        for p in order:
+            if cur and (cur[0].dtype != p.dtype or cur[0].device != p.device):
+                close(cur)
+                cur, size = [], 0
+            cur.append(p)
+            size += p.numel() * p.element_size()
+            if size >= bucket_bytes:
+                close(cur)
+                cur, size = [], 0
+        if cur:
+            close(cur)
+        self._stream = torch.cuda.Stream(priority=-1) if self.params[0].is_cuda else None
+        for p in self.params:
+            self._hooks.append(p.register_post_accumulate_grad_hook(self._on_autograd_grad))
+        self._reset()
+
+    # ------------------------------------------------------------------ bucketed mode
     def _reset(self):
-        self._pending = {bi: len(b) for bi, b in enumerate(self._buckets)}
+        self._pending = [b["n"] for b in self._buckets]
+        self._arrived = set()
         self._works = []
 
-    def _reduce_bucket(self, bucket):
-        grads = [p.grad for p in bucket if p.grad is not None]
-        if not grads:
-            return
-        flat = torch.cat([g.reshape(-1) for g in grads])
-        work = dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
-        self._works.append((work, flat, grads))
-
-    def _on_grad(self, p):
-        bi = self._bucket_of[id(p)]
-        self._pending[bi] -= 1
-        if self._pending[bi] == 0:
-            if self._stream is not None:
-                self._stream.wait_stream(torch.cuda.current_stream())
-                with torch.cuda.stream(self._stream):
-                    self._reduce_bucket(self._buckets[bi])
-            else:
-                self._reduce_bucket(self._buckets[bi])
-
-    def finish(self) -> None:
-        """Call after backward, before clipping / optimizer.step()."""
+    def _launch(self, bi):
         if self.world == 1:
             return
-        inv = 1.0 / self.world
-        if not self.bucket_bytes:
+        buf = self._buckets[bi]["buf"]
+        op = dist.ReduceOp.AVG if self._avg else dist.ReduceOp.SUM
+        if self._stream is not None:
+            self._stream.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(self._stream):
+                self._works.append(dist.all_reduce(buf, op=op, group=self.group, async_op=True))
+        else:
+            self._works.append(dist.all_reduce(buf, op=op, group=self.group, async_op=True))
+
+    def _store(self, p, g) -> None:
+        bi, view = self._slot[id(p)]
+        if p.grad is view:                   # accumulation window: gradient of an earlier micro-batch is in the view
+            view.add_(g)
+        else:
+            view.copy_(g)
+            p.grad = view
+        self._mark(p, bi)
+
+    def _mark(self, p, bi) -> None:
+        if self.accumulating or id(p) in self._arrived:
+            return
+        self._arrived.add(id(p))
+        self._pending[bi] -= 1
+        if self._pending[bi] == 0:
+            self._launch(bi)
+
+    def deliver(self, p: torch.nn.Parameter, g: torch.Tensor) -> bool:
+        """Called by a hand-written backward with a FINAL gradient for `p`.  Returns True if the synchroniser took
+        ownership (the caller must then return None for `p` to autograd)."""
+        if not self.bucketed or id(p) not in self._slot:
+            return False
+        self._store(p, g)
+        return True
+
+    def _on_autograd_grad(self, p):
+        bi, view = self._slot[id(p)]
+        if p.grad is view:                   # autograd accumulated in place into the bucket view
+            self._mark(p, bi)
+            return
+        g = p.grad
+        p.grad = None
+        self._store(p, g)
+
+    # ------------------------------------------------------------------ both modes
+    def finish(self) -> None:
+        """Call after backward, before clipping / optimizer.step()."""
+        if self.world == 1 and not self.bucketed:
+            return
+        if not self.bucketed:
             grads = [p.grad for p in self.params if p.grad is not None]
             if not grads:
                 return
             flat = torch.cat([g.reshape(-1).float() for g in grads])
             dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group)
-            flat.mul_(inv)
+            flat.mul_(1.0 / self.world)
             off = 0
             for g in grads:
                 n = g.numel()
                 g.copy_(flat[off:off + n].view_as(g))
                 off += n
             return
-        for bi, left in self._pending.items():              # parameters that received no gradient this step
+        if self.accumulating:
+            return
+        for bi, left in enumerate(self._pending):      # parameters that received no gradient this step count as zero
             if left > 0:
-                self._reduce_bucket(self._buckets[bi])
-        for work, flat, grads in self._works:
-            work.wait()
-            off = 0
-            for g in grads:
-                n = g.numel()
-                g.copy_(flat[off:off + n].view_as(g)).mul_(inv)
-                off += n
+                for p in self._buckets[bi]["params"]:
+                    if id(p) not in self._arrived:
+                        _, view = self._slot[id(p)]
+                        view.zero_()
+                        p.grad = view
+                self._launch(bi)
+        for w in self._works:
+            w.wait()
         if self._stream is not None:
             torch.cuda.current_stream().wait_stream(self._stream)
+        if self.world > 1 and not self._avg:
+            for b in self._buckets:
+                b["buf"].mul_(1.0 / self.world)
         self._reset()

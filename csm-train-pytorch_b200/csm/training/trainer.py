@@ -119,6 +119,9 @@ class CSMTrainer:
                                            capturable=on_cuda)
         trainable = [p for p in self.model.parameters() if p.requires_grad]
         self._sync = dp.GradSynchronizer(trainable, bucket_bytes=64 << 20 if total > (32 << 20) else None)
+        sink = self._sync if self._sync.bucketed else None
+        self.model.backbone._grad_sink = sink        # the stacks hand their layers' gradients over as they finish
+        self.model.decoder._grad_sink = sink
 
     def enable_cuda_graph(self, warmup: int = 3, max_grad_norm: float = 1.0) -> None:
         """``train_step`` (one micro-batch + optimiser step) replayed as one CUDA graph (training/graph.py)."""
@@ -157,7 +160,9 @@ class CSMTrainer:
                                                      self.decoder_frame_fraction)
         return {k: v.to(self.device, non_blocking=True) for k, v in batch.items()}
 
-    def train_micro_batch(self, batch, accumulation_steps: int = 1) -> torch.Tensor:
+    def train_micro_batch(self, batch, accumulation_steps: int = 1, last: bool = True) -> torch.Tensor:
+        """`last` = this micro-batch closes the accumulation window (gradients are exchanged during its backward)."""
+        self._sync.accumulating = not last
         b = self._to_device(batch)
         loss, _ = compute_loss(self.model, b["input_tokens"], b["input_masks"], b["target_audio_tokens"],
                                self.semantic_weight, self.acoustic_weight, frame_idx=b["frame_idx"])
@@ -187,8 +192,9 @@ class CSMTrainer:
             losses, window = [], []
             for bi, batch in enumerate(iterate_batches(train_dataset, batch_size, True, self.rank, self.world,
                                                        seed=epoch)):
-                window.append(self.train_micro_batch(batch, accumulation_steps))
-                if (bi + 1) % accumulation_steps == 0:
+                closes = (bi + 1) % accumulation_steps == 0
+                window.append(self.train_micro_batch(batch, accumulation_steps, last=closes))
+                if closes:
                     self.optimizer_step(max_grad_norm)
                     step_loss = float(torch.stack(window).mean())      # one D2H read per optimiser step
                     losses.append(step_loss)

@@ -66,6 +66,57 @@ def test_grad_synchronizer_world2(bucket_bytes):
     assert sorted(res) == [(0, "ok"), (1, "ok")], res
 
 
+def _worker_deliver(rank, world, port, q):
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, os.path.join(root, "csm-train-pytorch_b200"))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    from csm.training import dp
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        a = torch.nn.Parameter(torch.zeros(4, 3))
+        b = torch.nn.Parameter(torch.zeros(5))
+        c = torch.nn.Parameter(torch.zeros(2, 2))
+        sync = dp.GradSynchronizer([a, b, c], bucket_bytes=32)
+        assert sync.bucketed and len(sync._buckets) >= 2
+        for step in range(2):
+            # accumulation window of two micro-batches: first accumulates locally, second exchanges
+            sync.accumulating = True
+            assert sync.deliver(a, torch.full((4, 3), 1.0 + rank))          # hand-written backward path
+            (b * (2.0 + rank)).sum().backward()                              # autograd path (hook)
+            sync.finish()                                                    # no-op while accumulating
+            sync.accumulating = False
+            assert sync.deliver(a, torch.full((4, 3), 10.0 * (rank + 1)))
+            (b * (3.0 + rank)).sum().backward()
+            sync.finish()                                                    # c never got a gradient: counts as zero
+            mean_a = sum((1.0 + r) + 10.0 * (r + 1) for r in range(world)) / world
+            mean_b = sum((2.0 + r) + (3.0 + r) for r in range(world)) / world
+            assert torch.allclose(a.grad, torch.full((4, 3), mean_a)), a.grad
+            assert torch.allclose(b.grad, torch.full((5,), mean_b)), b.grad
+            assert torch.equal(c.grad, torch.zeros(2, 2))
+            for p in (a, b, c):
+                p.grad = None
+        q.put((rank, "ok"))
+    except Exception as e:  # noqa: BLE001
+        import traceback
+        q.put((rank, traceback.format_exc()))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_bucket_views_deliver_and_accumulation_world2():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_deliver, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(res) == [(0, "ok"), (1, "ok")], res
+
+
 def test_single_process_is_noop():
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
