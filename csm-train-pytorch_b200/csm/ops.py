@@ -40,7 +40,7 @@ def gemm_profile_stop():
 
 
 def set_attn_backend(b: int) -> None:
-    """Test hook: 0 auto, 1 scalar, 2 mma.sync, 3 tcgen05 forward."""
+    """Test hook: 0 auto, 1 scalar, 2 mma.sync, 3 tcgen05, 4 short-sequence (seq <= 32)."""
     _lib.load().csm_set_attn_backend(b)
 
 

@@ -50,6 +50,13 @@ int attn_bwd_mma_launch(const void*, const void*, const void*, const void*, cons
                         void*, void*, float*, int, int, int, int, int, int64_t, int64_t, int64_t, int64_t, int64_t,
                         int64_t, int64_t, float, cudaStream_t);
 
+bool attn_small_supported(int S, int H, int KV, int hd, int64_t ldq, int64_t ldk, int64_t ldv, int64_t ldo,
+                          const void* q, const void* k, const void* v, const void* o);
+int attn_fwd_small_launch(const void*, const void*, const void*, void*, float*, int, int, int, int, int, int64_t,
+                          int64_t, int64_t, int64_t, float, cudaStream_t);
+int attn_bwd_small_launch(const void*, const void*, const void*, const void*, const float*, const void*, void*,
+                          void*, void*, int, int, int, int, int, int64_t, int64_t, int64_t, int64_t, int64_t, int64_t,
+                          int64_t, float, cudaStream_t);
 bool attn_tc_supported(int S, int hd, int64_t ldq, int64_t ldk, int64_t ldv, int64_t ldo, const void* q, const void* k,
                        const void* v, const void* o);
 int attn_fwd_tc_launch(const void*, const void*, const void*, void*, float*, int, int, int, int, int64_t, int64_t,
@@ -57,7 +64,7 @@ int attn_fwd_tc_launch(const void*, const void*, const void*, void*, float*, int
 int attn_bwd_tc_launch(const void*, const void*, const void*, const void*, const float*, const void*, void*, void*,
                        void*, float*, int, int, int, int, int64_t, int64_t, int64_t, int64_t, int64_t, int64_t, int64_t,
                        float, cudaStream_t);
-static std::atomic<int> g_attn_backend{0};  // 0 auto, 1 scalar, 2 mma.sync, 3 tcgen05 (forward)
+static std::atomic<int> g_attn_backend{0};  // 0 auto, 1 scalar, 2 mma.sync, 3 tcgen05, 4 short-sequence
 
 int gemm_dispatch(const void* A, const void* B, void* C, const void* R, int64_t M, int64_t N, int64_t K,
                   int64_t lda, int64_t ldb, int64_t ldc, int64_t ldr, int transA, int transB, int c_dtype,
@@ -132,6 +139,10 @@ extern "C" int csm_attn_causal_gqa_fwd(const void* q, const void* k, const void*
     return attn_fwd_tc_launch(q, k, v, o, lse, batch, seq, heads, kv_heads, ldq, ldk, ldv, ldo, scale,
                               as_stream(stream));
   CSM_REQUIRE(be != 3, CSM_ERR_SHAPE, "attn_fwd: shape not supported by the tcgen05 kernel (hd=64, seq>=128)");
+  if ((be == 0 || be == 4) && attn_small_supported(seq, heads, kv_heads, head_dim, ldq, ldk, ldv, ldo, q, k, v, o))
+    return attn_fwd_small_launch(q, k, v, o, lse, batch, seq, heads, kv_heads, head_dim, ldq, ldk, ldv, ldo, scale,
+                                 as_stream(stream));
+  CSM_REQUIRE(be != 4, CSM_ERR_SHAPE, "attn_fwd: shape not supported by the short-sequence kernel (seq<=32, hd 64/128)");
   if (be != 1 && attn_mma_supported(head_dim, ldq, ldk, ldv, ldo))
     return attn_fwd_mma_launch(q, k, v, o, lse, batch, seq, heads, kv_heads, head_dim, ldq, ldk, ldv, ldo, scale,
                                as_stream(stream));
@@ -162,7 +173,11 @@ extern "C" int csm_attn_causal_gqa_bwd(const void* q, const void* k, const void*
   if ((be == 0 || be == 3) && attn_tc_supported(seq, head_dim, ldq, ldk, ldv, ldo, q, k, v, o))
     return attn_bwd_tc_launch(q, k, v, o, lse, dout, dq, dk, dv, delta, batch, seq, heads, kv_heads, ldq, ldk, ldv, ldo,
                               lddq, lddk, lddv, scale, as_stream(stream));
-  if (g_attn_backend.load() != 1 && attn_mma_supported(head_dim, ldq, ldk, ldv, ldo))
+  if ((be == 0 || be == 4) && attn_small_supported(seq, heads, kv_heads, head_dim, ldq, ldk, ldv, ldo, q, k, v, o))
+    return attn_bwd_small_launch(q, k, v, o, lse, dout, dq, dk, dv, batch, seq, heads, kv_heads, head_dim, ldq, ldk,
+                                 ldv, ldo, lddq, lddk, lddv, scale, as_stream(stream));
+  CSM_REQUIRE(be != 4, CSM_ERR_SHAPE, "attn_bwd: shape not supported by the short-sequence kernel");
+  if (be != 1 && attn_mma_supported(head_dim, ldq, ldk, ldv, ldo))
     return attn_bwd_mma_launch(q, k, v, o, lse, dout, dq, dk, dv, delta, batch, seq, heads, kv_heads, head_dim, ldq,
                                ldk, ldv, ldo, lddq, lddk, lddv, scale, as_stream(stream));
   return attn_bwd_simt_launch(q, k, v, o, lse, dout, dq, dk, dv, delta, batch, seq, heads, kv_heads, head_dim, ldq,

@@ -1,11 +1,14 @@
 // K5 on the 5th-gen tensor cores: causal GQA flash-attention FORWARD for head_dim 64 (CSM-1B backbone).
-//   warp 0     : TMA producer — Q tile once, then K_j / V_j tiles (128 keys x 64) into a 2-stage ring
-//   warp 1     : tcgen05.mma issuer — S_j = Q K_j^T (128x128, fp32 in TMEM, double buffered) and
+//   warp 0     : TMA producer — Q tile once, then K_j / V_j tiles (64 keys x 64) into a 2-stage ring
+//   warp 1     : tcgen05.mma issuer — S_j = Q K_j^T (128x64, fp32 in TMEM, double buffered) and
 //                PV_j = P_j V_j (128x64, V consumed MN-major straight from its row-major tile)
-//   warps 2..5 : softmax — one query row per thread (row == TMEM lane, so no shuffles): two passes over the S row
-//                with tcgen05.ld (max, then exp2/sum), P_j written as bf16 into 128B-swizzled smem (the A operand
+//   warps 2..5 : softmax — one query row per thread (row == TMEM lane, so no shuffles): the S row is read with
+//                tcgen05.ld (max, then exp2/sum), P_j written as bf16 into 128B-swizzled smem (the A operand
 //                of the PV MMA), running output kept in registers and updated from the PV_j tile one block later,
 //                so the tensor pipe computes S_{j+1} and PV_j while the softmax of the next block runs.
+// The kernel is MUFU-bound (one ex2 per score, 16 per clock per SM), so what matters is keeping all four XU pipes
+// fed: 64-key blocks keep a CTA at 81 KB of shared memory and 256 TMEM columns, so TWO CTAs are resident per SM and
+// one CTA's softmax overlaps the other's TMEM round trips and mbarrier hand-offs.
 #include <type_traits>
 
 #include "tc_common.cuh"
@@ -17,16 +20,19 @@ using namespace tc;
 namespace {
 
 constexpr int TQ = 128, TK = 128, THD = 64;
+constexpr int FK = 64;   // keys per block of the FORWARD kernel
+constexpr int FST = 3;   // K/V ring depth of the forward kernel (a stage is held until its PV MMA has completed, so
+                         // two stages would put the ~1 us TMA latency of block j+1 on the softmax's critical path)
 constexpr int kAttnThreads = 192;
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kLn2 = 0.6931471805599453f;
 
 constexpr int SM_Q = 0;
 constexpr int SM_K = SM_Q + TQ * THD * 2;                 // 16 KB
-constexpr int SM_V = SM_K + 2 * TK * THD * 2;             // + 32 KB
-constexpr int SM_P = SM_V + 2 * TK * THD * 2;             // + 32 KB
-constexpr int SM_BAR = SM_P + 2 * TQ * TK * 2;            // + 64 KB
-constexpr int kAttnSmem = SM_BAR + 256 + 1024;
+constexpr int SM_V = SM_K + FST * FK * THD * 2;           // + 24 KB
+constexpr int SM_P = SM_V + FST * FK * THD * 2;           // + 24 KB
+constexpr int SM_BAR = SM_P + 2 * TQ * FK * 2;            // + 32 KB
+constexpr int kAttnSmem = SM_BAR + 256 + 1024;            // 97 KB: two CTAs per SM
 
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ float ex2(float x) {   // one MUFU; -inf -> 0
@@ -52,7 +58,7 @@ __device__ __forceinline__ void store_row_chunk32(uint8_t* tile, int r, int col0
   }
 }
 
-__global__ void __launch_bounds__(kAttnThreads, 1)
+__global__ void __launch_bounds__(kAttnThreads, 2)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                    const __grid_constant__ CUtensorMap tmV, bf16* __restrict__ o, float* __restrict__ lse, int S,
                    int H, int KV, int64_t ldo, float scale_log2) {
@@ -60,65 +66,68 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SM_BAR);
   uint64_t* q_full = bars;            // 1
-  uint64_t* kv_full = bars + 1;       // 2
-  uint64_t* kv_empty = bars + 3;      // 2
-  uint64_t* s_full = bars + 5;        // 2
-  uint64_t* p_full = bars + 7;        // 2 (128 arrivals)
-  uint64_t* pv_full = bars + 9;       // 2
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 11);
+  uint64_t* kv_full = bars + 1;       // FST
+  uint64_t* kv_empty = bars + 5;      // FST
+  uint64_t* s_full = bars + 9;        // 2
+  uint64_t* p_full = bars + 11;       // 2 (one arrival per softmax warp)
+  uint64_t* pv_full = bars + 13;      // 2
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
+  static_assert(FST <= 4, "barrier slots");
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int qb = gridDim.x - 1 - blockIdx.x;  // longest rows first
   const int h = blockIdx.y, b = blockIdx.z;
   const int kvh = h / (H / KV);
   const int q0 = qb * TQ;
-  const int nblk = qb + 1;
+  const int nblk = min(2 * (qb + 1), (S + FK - 1) / FK);   // 64-key blocks up to the diagonal
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmQ);
     tma_prefetch_desc(&tmK);
     tma_prefetch_desc(&tmV);
     mbar_init(q_full, 1);
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < FST; ++i) {
       mbar_init(&kv_full[i], 1);
       mbar_init(&kv_empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
       mbar_init(&s_full[i], 1);
       mbar_init(&p_full[i], 4);
       mbar_init(&pv_full[i], 1);
     }
     mbar_fence_init();
   }
-  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  if (warp == 1) tmem_alloc(tmem_slot, 256);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  constexpr uint32_t COL_S = 0, COL_PV = 256;
+  constexpr uint32_t COL_S = 0, COL_PV = 128;
 
   if (warp == 0) {
     if (lane == 0) {
       mbar_expect_tx(q_full, TQ * THD * 2);
       tma_load_3d(smem + SM_Q, &tmQ, q_full, h * THD, q0, b);
       for (int j = 0; j < nblk; ++j) {
-        const int st = j & 1;
-        mbar_wait(&kv_empty[st], ((j >> 1) & 1) ^ 1);
-        mbar_expect_tx(&kv_full[st], 2 * TK * THD * 2);
-        tma_load_3d(smem + SM_K + st * (TK * THD * 2), &tmK, &kv_full[st], kvh * THD, j * TK, b);
-        tma_load_3d(smem + SM_V + st * (TK * THD * 2), &tmV, &kv_full[st], kvh * THD, j * TK, b);
+        const int ks = j % FST;
+        mbar_wait(&kv_empty[ks], ((j / FST) & 1) ^ 1);
+        mbar_expect_tx(&kv_full[ks], 2 * FK * THD * 2);
+        tma_load_3d(smem + SM_K + ks * (FK * THD * 2), &tmK, &kv_full[ks], kvh * THD, j * FK, b);
+        tma_load_3d(smem + SM_V + ks * (FK * THD * 2), &tmV, &kv_full[ks], kvh * THD, j * FK, b);
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      constexpr uint32_t idesc_s = make_idesc_bf16(TQ, TK, 0, 0);    // S = Q K^T : both K-major
+      constexpr uint32_t idesc_s = make_idesc_bf16(TQ, FK, 0, 0);    // S = Q K^T : both K-major
       constexpr uint32_t idesc_pv = make_idesc_bf16(TQ, THD, 0, 1);  // PV = P V  : V is MN-major ([key][hd] rows)
       const uint32_t sq = smem_u32(smem + SM_Q);
       auto issue_s = [&](int j) {
         const int st = j & 1;
-        const uint32_t sk = smem_u32(smem + SM_K + st * (TK * THD * 2));
+        const uint32_t sk = smem_u32(smem + SM_K + (j % FST) * (FK * THD * 2));
         const uint64_t ad = make_smem_desc(sq, 16, 1024), bd = make_smem_desc(sk, 16, 1024);
 #pragma unroll
         for (int kk = 0; kk < THD / 16; ++kk)
-          umma_bf16(tmem_base + COL_S + st * TK, ad + (uint64_t)((kk * 32) >> 4), bd + (uint64_t)((kk * 32) >> 4),
+          umma_bf16(tmem_base + COL_S + st * FK, ad + (uint64_t)((kk * 32) >> 4), bd + (uint64_t)((kk * 32) >> 4),
                     idesc_s, kk ? 1u : 0u);
         umma_commit(&s_full[st]);
       };
@@ -129,23 +138,23 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       for (int j = 0; j < nblk; ++j) {
         const int st = j & 1;
         if (j + 1 < nblk) {
-          mbar_wait(&kv_full[st ^ 1], ((j + 1) >> 1) & 1);
+          mbar_wait(&kv_full[(j + 1) % FST], ((j + 1) / FST) & 1);
           tc_fence_after();
           issue_s(j + 1);  // S buffer st^1 was drained before p_full(j-1) completed (waited last iteration)
         }
         mbar_wait(&p_full[st], (j >> 1) & 1);
         tc_fence_after();
-        const uint32_t sp = smem_u32(smem + SM_P + st * (TQ * TK * 2));
-        const uint32_t sv = smem_u32(smem + SM_V + st * (TK * THD * 2));
+        const uint32_t sp = smem_u32(smem + SM_P + st * (TQ * FK * 2));
+        const uint32_t sv = smem_u32(smem + SM_V + (j % FST) * (FK * THD * 2));
 #pragma unroll
-        for (int kk = 0; kk < TK / 16; ++kk) {
+        for (int kk = 0; kk < FK / 16; ++kk) {
           // P: two 64-key swizzle atoms of 16 KB; inside an atom the K advance is 32 B.  V: 16 key-rows x 128 B.
           const uint64_t ad = make_smem_desc(sp + (kk >> 2) * (TQ * 64 * 2) + (kk & 3) * 32, 16, 1024);
-          const uint64_t bd = make_smem_desc(sv + kk * 16 * 128, 64 * TK * 2, 1024);
+          const uint64_t bd = make_smem_desc(sv + kk * 16 * 128, 64 * FK * 2, 1024);
           umma_bf16(tmem_base + COL_PV + st * THD, ad, bd, idesc_pv, kk ? 1u : 0u);
         }
         umma_commit(&pv_full[st]);
-        umma_commit(&kv_empty[st]);
+        umma_commit(&kv_empty[j % FST]);
       }
     }
   } else {
@@ -175,19 +184,19 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     auto block = [&](int j, auto diag_tag) {
       constexpr bool DIAG = decltype(diag_tag)::value;
       const int st = j & 1;
-      const int kbase = j * TK;
+      const int kbase = j * FK;
       mbar_wait(&s_full[st], (j >> 1) & 1);
       tc_fence_after();
-      const uint32_t s_addr = lane_addr + COL_S + st * TK;
+      const uint32_t s_addr = lane_addr + COL_S + st * FK;
       // the whole 128-column S row in registers: 4 tcgen05.ld in flight, ONE wait (a single TMEM round trip)
-      uint32_t v[TK];
+      uint32_t v[FK];
       __syncwarp();
 #pragma unroll
-      for (int c = 0; c < TK; c += 32) tmem_ld32(s_addr + c, v + c);
+      for (int c = 0; c < FK; c += 32) tmem_ld32(s_addr + c, v + c);
       tmem_ld_wait();
       float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
-      for (int i = 0; i < TK; ++i) {
+      for (int i = 0; i < FK; ++i) {
         if (DIAG && (kbase + i > qi)) v[i] = 0xff800000u;   // -inf
         m4[i & 3] = fmaxf(m4[i & 3], __uint_as_float(v[i]));
       }
@@ -196,9 +205,9 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       const float corr = ex2(m - mx);
       m = mx;
       float rs4[4] = {0.f, 0.f, 0.f, 0.f};
-      uint8_t* ptile = smem + SM_P + st * (TQ * TK * 2);
+      uint8_t* ptile = smem + SM_P + st * (TQ * FK * 2);
 #pragma unroll
-      for (int c = 0; c < TK; c += 32) {
+      for (int c = 0; c < FK; c += 32) {
         float p[32];
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
@@ -215,8 +224,10 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       if (j > 0) fold(j - 1, corr_prev);
       corr_prev = corr;
     };
-    for (int j = 0; j < nblk - 1; ++j) block(j, std::false_type{});
-    block(nblk - 1, std::true_type{});
+    // blocks that reach past the first query row of the tile (kbase + 63 > q0) need the causal mask: the last two
+    const int nfull = min(nblk, q0 / FK);
+    for (int j = 0; j < nfull; ++j) block(j, std::false_type{});
+    for (int j = nfull; j < nblk; ++j) block(j, std::true_type{});
     fold(nblk - 1, corr_prev);
     if (qi < S) {
       const float inv = 1.f / l;
@@ -235,7 +246,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
+    tmem_dealloc(tmem_base, 256);
   }
 }
 
@@ -640,8 +651,8 @@ int attn_fwd_tc_launch(const void* q, const void* k, const void* v, void* o, flo
   CUtensorMap tq, tk, tv;
   int rc;
   if ((rc = encode_tmap_bf16(&tq, q, (uint64_t)H * THD, S, B, ldq, (uint64_t)S * ldq, TQ))) return rc;
-  if ((rc = encode_tmap_bf16(&tk, k, (uint64_t)KV * THD, S, B, ldk, (uint64_t)S * ldk, TK))) return rc;
-  if ((rc = encode_tmap_bf16(&tv, v, (uint64_t)KV * THD, S, B, ldv, (uint64_t)S * ldv, TK))) return rc;
+  if ((rc = encode_tmap_bf16(&tk, k, (uint64_t)KV * THD, S, B, ldk, (uint64_t)S * ldk, FK))) return rc;
+  if ((rc = encode_tmap_bf16(&tv, v, (uint64_t)KV * THD, S, B, ldv, (uint64_t)S * ldv, FK))) return rc;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(attn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem);

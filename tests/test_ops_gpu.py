@@ -221,6 +221,17 @@ def test_attention_fwd_bwd(ops, cuda, backend, B, S, H, KV, hd):
         ops.set_attn_backend(0)
 
 
+@pytest.mark.parametrize("B,S,H,KV,hd", [(7, 32, 8, 2, 128), (5, 17, 8, 2, 128), (3, 32, 4, 4, 64), (4, 2, 2, 1, 128),
+                                         (232, 32, 8, 2, 128), (2, 9, 6, 2, 64)])
+def test_attention_short_sequence_kernel(ops, cuda, B, S, H, KV, hd):
+    """backend 4 = the depth decoder's kernel (seq <= 32, one CTA per (frame, kv head)); ragged S and GQA 1/3/4."""
+    ops.set_attn_backend(4)
+    try:
+        _attention_case(ops, cuda, B, S, H, KV, hd)
+    finally:
+        ops.set_attn_backend(0)
+
+
 def _attention_case(ops, cuda, B, S, H, KV, hd):
     g = torch.Generator().manual_seed(B * S + hd)
     q = torch.randn(B * S, H * hd, generator=g).to(BF).to(cuda)

@@ -47,7 +47,7 @@ def test_lora_train_step_graph_equals_eager(cuda, tmp_path):
     batches = _batches(cfg, 6)
     le = [float(te.train_step(b)) for b in batches]
     lg = [float(tg.train_step(b)) for b in batches]        # steps 1-2 eager, step 3 captures, 4-6 replay
-    assert tg._graphed.graph is not None and tg._graphed.kernels_per_replay > 100
+    assert tg._graphed.graph is not None and tg._graphed.kernels_per_replay > 50
     for a, b in zip(le, lg):
         assert abs(a - b) <= 2e-3 * abs(a), (le, lg)
     assert le[-1] < le[0]                                   # it trains
