@@ -44,18 +44,20 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
+__device__ __forceinline__ void sts128(uint32_t saddr, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
+}
+
 __device__ __forceinline__ void store_row_chunk32(uint8_t* tile, int r, int col0, const float* f) {
-  // 32 consecutive columns [col0, col0+32) of row r into a [128 x 128] bf16 A-operand tile made of two
-  // 64-column 128B-swizzled atoms of 16 KB each
-  uint8_t* atom = tile + (col0 >> 6) * (128 * 64 * 2) + r * 128;
+  // 32 consecutive columns [col0, col0+32) of row r into a [128 x 64k] bf16 A-operand tile made of
+  // 64-column 128B-swizzled atoms of 16 KB each (explicit st.shared: a generic store would cost a MEMBAR.ALL)
+  const uint32_t atom = smem_u32(tile) + (col0 >> 6) * (128 * 64 * 2) + r * 128;
   const int c16 = (col0 & 63) >> 3;
 #pragma unroll
-  for (int q4 = 0; q4 < 4; ++q4) {
-    uint4 w;
-    w.x = pack_bf16(f[q4 * 8 + 0], f[q4 * 8 + 1]); w.y = pack_bf16(f[q4 * 8 + 2], f[q4 * 8 + 3]);
-    w.z = pack_bf16(f[q4 * 8 + 4], f[q4 * 8 + 5]); w.w = pack_bf16(f[q4 * 8 + 6], f[q4 * 8 + 7]);
-    *reinterpret_cast<uint4*>(atom + (((c16 + q4) ^ (r & 7)) << 4)) = w;
-  }
+  for (int q4 = 0; q4 < 4; ++q4)
+    sts128(atom + (((c16 + q4) ^ (r & 7)) << 4), pack_bf16(f[q4 * 8 + 0], f[q4 * 8 + 1]),
+           pack_bf16(f[q4 * 8 + 2], f[q4 * 8 + 3]), pack_bf16(f[q4 * 8 + 4], f[q4 * 8 + 5]),
+           pack_bf16(f[q4 * 8 + 6], f[q4 * 8 + 7]));
 }
 
 __global__ void __launch_bounds__(kAttnThreads, 2)
@@ -104,32 +106,40 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   const uint32_t tmem_base = *tmem_slot;
   constexpr uint32_t COL_S = 0, COL_PV = 128;
 
+  // warps 0 and 1 keep warp-uniform control flow and elect one lane per TMA / tcgen05 issue (see tc::elect_one)
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {
       mbar_expect_tx(q_full, TQ * THD * 2);
       tma_load_3d(smem + SM_Q, &tmQ, q_full, h * THD, q0, b);
-      for (int j = 0; j < nblk; ++j) {
-        const int ks = j % FST;
-        mbar_wait(&kv_empty[ks], ((j / FST) & 1) ^ 1);
+    }
+    __syncwarp();
+    for (int j = 0; j < nblk; ++j) {
+      const int ks = j % FST;
+      mbar_wait(&kv_empty[ks], ((j / FST) & 1) ^ 1);
+      if (elect_one()) {
         mbar_expect_tx(&kv_full[ks], 2 * FK * THD * 2);
         tma_load_3d(smem + SM_K + ks * (FK * THD * 2), &tmK, &kv_full[ks], kvh * THD, j * FK, b);
         tma_load_3d(smem + SM_V + ks * (FK * THD * 2), &tmV, &kv_full[ks], kvh * THD, j * FK, b);
       }
+      __syncwarp();
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {
       constexpr uint32_t idesc_s = make_idesc_bf16(TQ, FK, 0, 0);    // S = Q K^T : both K-major
       constexpr uint32_t idesc_pv = make_idesc_bf16(TQ, THD, 0, 1);  // PV = P V  : V is MN-major ([key][hd] rows)
       const uint32_t sq = smem_u32(smem + SM_Q);
       auto issue_s = [&](int j) {
         const int st = j & 1;
-        const uint32_t sk = smem_u32(smem + SM_K + (j % FST) * (FK * THD * 2));
-        const uint64_t ad = make_smem_desc(sq, 16, 1024), bd = make_smem_desc(sk, 16, 1024);
+        if (elect_one()) {
+          const uint32_t sk = smem_u32(smem + SM_K + (j % FST) * (FK * THD * 2));
+          const uint64_t ad = make_smem_desc(sq, 16, 1024), bd = make_smem_desc(sk, 16, 1024);
 #pragma unroll
-        for (int kk = 0; kk < THD / 16; ++kk)
-          umma_bf16(tmem_base + COL_S + st * FK, ad + (uint64_t)((kk * 32) >> 4), bd + (uint64_t)((kk * 32) >> 4),
-                    idesc_s, kk ? 1u : 0u);
-        umma_commit(&s_full[st]);
+          for (int kk = 0; kk < THD / 16; ++kk)
+            umma_bf16(tmem_base + COL_S + st * FK, ad + (uint64_t)((kk * 32) >> 4), bd + (uint64_t)((kk * 32) >> 4),
+                      idesc_s, kk ? 1u : 0u);
+          umma_commit(&s_full[st]);
+        }
+        __syncwarp();
       };
       mbar_wait(q_full, 0);
       mbar_wait(&kv_full[0], 0);
@@ -144,17 +154,19 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         }
         mbar_wait(&p_full[st], (j >> 1) & 1);
         tc_fence_after();
-        const uint32_t sp = smem_u32(smem + SM_P + st * (TQ * FK * 2));
-        const uint32_t sv = smem_u32(smem + SM_V + (j % FST) * (FK * THD * 2));
+        if (elect_one()) {
+          const uint32_t sp = smem_u32(smem + SM_P + st * (TQ * FK * 2));
+          const uint32_t sv = smem_u32(smem + SM_V + (j % FST) * (FK * THD * 2));
+          // P: one 64-key swizzle atom, the K advance inside it is 32 B.  V: 16 key-rows x 128 B per K step.
+          const uint64_t ad = make_smem_desc(sp, 16, 1024), bd = make_smem_desc(sv, 64 * FK * 2, 1024);
 #pragma unroll
-        for (int kk = 0; kk < FK / 16; ++kk) {
-          // P: two 64-key swizzle atoms of 16 KB; inside an atom the K advance is 32 B.  V: 16 key-rows x 128 B.
-          const uint64_t ad = make_smem_desc(sp + (kk >> 2) * (TQ * 64 * 2) + (kk & 3) * 32, 16, 1024);
-          const uint64_t bd = make_smem_desc(sv + kk * 16 * 128, 64 * FK * 2, 1024);
-          umma_bf16(tmem_base + COL_PV + st * THD, ad, bd, idesc_pv, kk ? 1u : 0u);
+          for (int kk = 0; kk < FK / 16; ++kk)
+            umma_bf16(tmem_base + COL_PV + st * THD, ad + (uint64_t)((kk * 32) >> 4),
+                      bd + (uint64_t)((kk * 16 * 128) >> 4), idesc_pv, kk ? 1u : 0u);
+          umma_commit(&pv_full[st]);
+          umma_commit(&kv_empty[j % FST]);
         }
-        umma_commit(&pv_full[st]);
-        umma_commit(&kv_empty[j % FST]);
+        __syncwarp();
       }
     }
   } else {
@@ -270,12 +282,11 @@ constexpr int SUB = 64;           // columns (keys resp. queries) per pipelined 
 // D[128 x 64] (+)= A[128 x 64 (one swizzle atom, K-major)] * B, B = [64 rows x 64] tile used MN-major
 __device__ __forceinline__ void issue_a64_bmn(uint32_t d_tmem, uint32_t a_smem, uint32_t b_smem, bool accumulate_first) {
   constexpr uint32_t idesc = make_idesc_bf16(128, THD, 0, 1);
+  const uint64_t ad = make_smem_desc(a_smem, 16, 1024), bd = make_smem_desc(b_smem, 64 * 128 * 2, 1024);
 #pragma unroll
-  for (int kk = 0; kk < SUB / 16; ++kk) {
-    const uint64_t ad = make_smem_desc(a_smem + kk * 32, 16, 1024);
-    const uint64_t bd = make_smem_desc(b_smem + kk * 16 * 128, 64 * 128 * 2, 1024);
-    umma_bf16(d_tmem, ad, bd, idesc, (accumulate_first || kk) ? 1u : 0u);
-  }
+  for (int kk = 0; kk < SUB / 16; ++kk)
+    umma_bf16(d_tmem, ad + (uint64_t)((kk * 32) >> 4), bd + (uint64_t)((kk * 16 * 128) >> 4), idesc,
+              (accumulate_first || kk) ? 1u : 0u);
 }
 // D[128 x 64] = A[128 x 64] * B[64 x 64]^T, both K-major tiles (reduction over head_dim)
 __device__ __forceinline__ void issue_nt_64(uint32_t d_tmem, uint32_t a_smem, uint32_t b_smem) {
@@ -288,9 +299,11 @@ __device__ __forceinline__ void issue_nt_64(uint32_t d_tmem, uint32_t a_smem, ui
 
 constexpr int DQ_Q = 0;                              // 16 KB  Q tile
 constexpr int DQ_DO = DQ_Q + TQ * THD * 2;           // 16 KB  dO tile
-constexpr int DQ_K = DQ_DO + TQ * THD * 2;           // 2 x 16 KB (128-key tiles = two sub-blocks each)
-constexpr int DQ_V = DQ_K + 2 * TK * THD * 2;        // 2 x 16 KB
-constexpr int DQ_DS = DQ_V + 2 * TK * THD * 2;       // 2 x 16 KB  dS sub-tiles [128 q x 64 keys]
+constexpr int KST = 3;                               // K/V (resp. Q/dO) TMA ring depth of the backward kernels
+constexpr int NB = 3;                                // TMEM S/dP sub-block buffers: the MMA warp runs two ahead
+constexpr int DQ_K = DQ_DO + TQ * THD * 2;           // KST x 16 KB (128-key tiles = two sub-blocks each)
+constexpr int DQ_V = DQ_K + KST * TK * THD * 2;      // KST x 16 KB
+constexpr int DQ_DS = DQ_V + KST * TK * THD * 2;     // 2 x 16 KB  dS sub-tiles [128 q x 64 keys]
 constexpr int DQ_BAR = DQ_DS + 2 * TQ * SUB * 2;
 constexpr int kDqSmem = DQ_BAR + 256 + 1024;
 
@@ -303,14 +316,15 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + DQ_BAR);
   uint64_t* q_full = bars;            // Q + dO landed
-  uint64_t* kv_full = bars + 1;       // [2]
-  uint64_t* kv_empty = bars + 3;      // [2]
-  uint64_t* sdp_full = bars + 5;      // [2] S and dP sub-block ready in TMEM
-  uint64_t* sdp_empty = bars + 7;     // [2] ... and read back by the 8 compute warps
-  uint64_t* ds_full = bars + 9;       // [2] dS sub-tile written (8 warp arrivals)
-  uint64_t* ds_empty = bars + 11;     // [2] ... and consumed by the dQ MMA
-  uint64_t* acc_full = bars + 13;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
+  uint64_t* kv_full = bars + 1;       // [KST]
+  uint64_t* kv_empty = bars + 4;      // [KST]
+  uint64_t* sdp_full = bars + 7;      // [NB] S and dP sub-block ready in TMEM
+  uint64_t* sdp_empty = bars + 10;    // [NB] ... and read back by the 8 compute warps
+  uint64_t* ds_full = bars + 13;      // [2] dS sub-tile written (8 warp arrivals)
+  uint64_t* ds_empty = bars + 15;     // [2] ... and consumed by the dQ MMA
+  uint64_t* acc_full = bars + 17;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
+  static_assert(KST == 3 && NB == 3, "barrier slots");
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int qb = gridDim.x - 1 - blockIdx.x;
@@ -323,11 +337,11 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV); tma_prefetch_desc(&tmDO);
     mbar_init(q_full, 1);
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < 3; ++i) {
       mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1);
       mbar_init(&sdp_full[i], 1); mbar_init(&sdp_empty[i], 8);
-      mbar_init(&ds_full[i], 8); mbar_init(&ds_empty[i], 1);
     }
+    for (int i = 0; i < 2; ++i) { mbar_init(&ds_full[i], 8); mbar_init(&ds_empty[i], 1); }
     mbar_init(acc_full, 1);
     mbar_fence_init();
   }
@@ -336,48 +350,59 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  constexpr uint32_t COL_S = 0, COL_DP = 128, COL_DQ = 256;
+  constexpr uint32_t COL_S = 0, COL_DP = NB * SUB, COL_DQ = 2 * NB * SUB;   // 192 + 192 + 64 columns
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {
       mbar_expect_tx(q_full, 2 * TQ * THD * 2);
       tma_load_3d(smem + DQ_Q, &tmQ, q_full, h * THD, q0, b);
       tma_load_3d(smem + DQ_DO, &tmDO, q_full, h * THD, q0, b);
-      for (int j = 0; j < nblk; ++j) {
-        const int st = j & 1;
-        mbar_wait(&kv_empty[st], ((j >> 1) & 1) ^ 1);
+    }
+    __syncwarp();
+    for (int j = 0; j < nblk; ++j) {
+      const int st = j % KST;
+      mbar_wait(&kv_empty[st], ((j / KST) & 1) ^ 1);
+      if (elect_one()) {
         mbar_expect_tx(&kv_full[st], 2 * TK * THD * 2);
         tma_load_3d(smem + DQ_K + st * (TK * THD * 2), &tmK, &kv_full[st], kvh * THD, j * TK, b);
         tma_load_3d(smem + DQ_V + st * (TK * THD * 2), &tmV, &kv_full[st], kvh * THD, j * TK, b);
       }
+      __syncwarp();
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {
       const uint32_t sq = smem_u32(smem + DQ_Q), sdo = smem_u32(smem + DQ_DO);
       auto issue_sdp = [&](int u) {
-        const int jt = u >> 1, hk = u & 1, st = jt & 1, bb = u & 1;
-        if (hk == 0) mbar_wait(&kv_full[st], (jt >> 1) & 1);
-        mbar_wait(&sdp_empty[bb], ((u >> 1) & 1) ^ 1);
+        const int jt = u >> 1, hk = u & 1, st = jt % KST, bb = u % NB;
+        if (hk == 0) mbar_wait(&kv_full[st], (jt / KST) & 1);
+        mbar_wait(&sdp_empty[bb], ((u / NB) & 1) ^ 1);
         tc_fence_after();
-        const uint32_t sk = smem_u32(smem + DQ_K + st * (TK * THD * 2)) + hk * (SUB * 128);
-        const uint32_t sv = smem_u32(smem + DQ_V + st * (TK * THD * 2)) + hk * (SUB * 128);
-        issue_nt_64(tmem_base + COL_S + bb * SUB, sq, sk);     // S  = Q K_sub^T
-        issue_nt_64(tmem_base + COL_DP + bb * SUB, sdo, sv);   // dP = dO V_sub^T
-        umma_commit(&sdp_full[bb]);
+        if (elect_one()) {
+          const uint32_t sk = smem_u32(smem + DQ_K + st * (TK * THD * 2)) + hk * (SUB * 128);
+          const uint32_t sv = smem_u32(smem + DQ_V + st * (TK * THD * 2)) + hk * (SUB * 128);
+          issue_nt_64(tmem_base + COL_S + bb * SUB, sq, sk);     // S  = Q K_sub^T
+          issue_nt_64(tmem_base + COL_DP + bb * SUB, sdo, sv);   // dP = dO V_sub^T
+          umma_commit(&sdp_full[bb]);
+        }
+        __syncwarp();
       };
       mbar_wait(q_full, 0);
       issue_sdp(0);
+      issue_sdp(1);                    // nsub >= 2 always
       for (int u = 0; u < nsub; ++u) {
-        if (u + 1 < nsub) issue_sdp(u + 1);
-        const int jt = u >> 1, hk = u & 1, st = jt & 1, bb = u & 1;
-        mbar_wait(&ds_full[bb], (u >> 1) & 1);
+        if (u + 2 < nsub) issue_sdp(u + 2);
+        const int jt = u >> 1, hk = u & 1, st = jt % KST, db = u & 1;
+        mbar_wait(&ds_full[db], (u >> 1) & 1);
         tc_fence_after();
-        const uint32_t sk = smem_u32(smem + DQ_K + st * (TK * THD * 2)) + hk * (SUB * 128);
-        issue_a64_bmn(tmem_base + COL_DQ, smem_u32(smem + DQ_DS + bb * (TQ * SUB * 2)), sk, u > 0);   // dQ += dS K_sub
-        umma_commit(&ds_empty[bb]);
-        if (hk == 1) umma_commit(&kv_empty[st]);
+        if (elect_one()) {
+          const uint32_t sk = smem_u32(smem + DQ_K + st * (TK * THD * 2)) + hk * (SUB * 128);
+          issue_a64_bmn(tmem_base + COL_DQ, smem_u32(smem + DQ_DS + db * (TQ * SUB * 2)), sk, u > 0);   // dQ += dS K_sub
+          umma_commit(&ds_empty[db]);
+          if (hk == 1) umma_commit(&kv_empty[st]);
+          if (u == nsub - 1) umma_commit(acc_full);
+        }
+        __syncwarp();
       }
-      umma_commit(acc_full);
     }
   } else {
     const int quad = warp & 3, half = (warp - 2) >> 2;
@@ -389,9 +414,9 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     const float Dls = (qi < S) ? delta[li] * scale : 0.f;
     auto sub = [&](int u, auto diag_tag) {
       constexpr bool DIAG = decltype(diag_tag)::value;
-      const int bb = u & 1;
+      const int bb = u % NB, db = u & 1;
       const int kbase = (u >> 1) * TK + (u & 1) * SUB + half * 32;
-      mbar_wait(&sdp_full[bb], (u >> 1) & 1);
+      mbar_wait(&sdp_full[bb], (u / NB) & 1);
       tc_fence_after();
       uint32_t sv_[32], dv_[32];
       __syncwarp();
@@ -408,11 +433,11 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
         if (DIAG && (kbase + i > qi)) x = -INFINITY;
         f[i] = ex2(x) * fmaf(__uint_as_float(dv_[i]), scale, -Dls);     // P * (dP - delta) * scale
       }
-      mbar_wait(&ds_empty[bb], ((u >> 1) & 1) ^ 1);
-      store_row_chunk32(smem + DQ_DS + bb * (TQ * SUB * 2), r, half * 32, f);
+      mbar_wait(&ds_empty[db], ((u >> 1) & 1) ^ 1);
+      store_row_chunk32(smem + DQ_DS + db * (TQ * SUB * 2), r, half * 32, f);
       fence_async_smem();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&ds_full[bb]);
+      if (lane == 0) mbar_arrive(&ds_full[db]);
     };
     for (int u = 0; u < nsub - 2; ++u) sub(u, std::false_type{});
     sub(nsub - 2, std::true_type{});
@@ -448,9 +473,9 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
 
 constexpr int DK_K = 0;                              // 16 KB  K tile
 constexpr int DK_V = DK_K + TK * THD * 2;            // 16 KB  V tile
-constexpr int DK_Q = DK_V + TK * THD * 2;            // 2 x 16 KB Q tiles (128 queries = two sub-blocks each)
-constexpr int DK_DO = DK_Q + 2 * TQ * THD * 2;       // 2 x 16 KB dO tiles
-constexpr int DK_PT = DK_DO + 2 * TQ * THD * 2;      // 2 x 16 KB P^T sub-tiles [128 keys x 64 q]
+constexpr int DK_Q = DK_V + TK * THD * 2;            // KST x 16 KB Q tiles (128 queries = two sub-blocks each)
+constexpr int DK_DO = DK_Q + KST * TQ * THD * 2;     // KST x 16 KB dO tiles
+constexpr int DK_PT = DK_DO + KST * TQ * THD * 2;    // 2 x 16 KB P^T sub-tiles [128 keys x 64 q]
 constexpr int DK_DST = DK_PT + 2 * TK * SUB * 2;     // 2 x 16 KB dS^T sub-tiles
 constexpr int DK_LD = DK_DST + 2 * TK * SUB * 2;     // 2 x (128 lse*log2e + 128 delta*scale) floats
 constexpr int DK_BAR = DK_LD + 2 * 256 * 4;
@@ -465,14 +490,14 @@ attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + DK_BAR);
   uint64_t* kv_full = bars;           // K + V landed
-  uint64_t* qd_full = bars + 1;       // [2] Q_i + dO_i tiles landed
-  uint64_t* qd_empty = bars + 3;      // [2]
-  uint64_t* sdp_full = bars + 5;      // [2] S^T and dP^T sub-block ready
-  uint64_t* sdp_empty = bars + 7;     // [2] ... read back (8 warp arrivals)
-  uint64_t* pt_full = bars + 9;       // [2] P^T and dS^T sub-tiles written (8 warp arrivals)
-  uint64_t* pt_empty = bars + 11;     // [2] ... consumed by the dV / dK MMAs
-  uint64_t* acc_full = bars + 13;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
+  uint64_t* qd_full = bars + 1;       // [KST] Q_i + dO_i tiles landed
+  uint64_t* qd_empty = bars + 4;      // [KST]
+  uint64_t* sdp_full = bars + 7;      // [NB] S^T and dP^T sub-block ready
+  uint64_t* sdp_empty = bars + 10;    // [NB] ... read back (8 warp arrivals)
+  uint64_t* pt_full = bars + 13;      // [2] P^T and dS^T sub-tiles written (8 warp arrivals)
+  uint64_t* pt_empty = bars + 15;     // [2] ... consumed by the dV / dK MMAs
+  uint64_t* acc_full = bars + 17;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int kvb = blockIdx.x, kvh = blockIdx.y, b = blockIdx.z;
@@ -486,11 +511,11 @@ attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV); tma_prefetch_desc(&tmDO);
     mbar_init(kv_full, 1);
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < 3; ++i) {
       mbar_init(&qd_full[i], 1); mbar_init(&qd_empty[i], 1);
       mbar_init(&sdp_full[i], 1); mbar_init(&sdp_empty[i], 8);
-      mbar_init(&pt_full[i], 8); mbar_init(&pt_empty[i], 1);
     }
+    for (int i = 0; i < 2; ++i) { mbar_init(&pt_full[i], 8); mbar_init(&pt_empty[i], 1); }
     mbar_init(acc_full, 1);
     mbar_fence_init();
   }
@@ -499,51 +524,64 @@ attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  constexpr uint32_t COL_ST = 0, COL_DPT = 128, COL_DK = 256, COL_DV = 320;
+  constexpr uint32_t COL_ST = 0, COL_DPT = NB * SUB, COL_DK = 2 * NB * SUB, COL_DV = 2 * NB * SUB + THD;   // 512 columns
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {
       mbar_expect_tx(kv_full, 2 * TK * THD * 2);
       tma_load_3d(smem + DK_K, &tmK, kv_full, kvh * THD, k0, b);
       tma_load_3d(smem + DK_V, &tmV, kv_full, kvh * THD, k0, b);
-      for (int it = 0; it < total; ++it) {
-        const int st = it & 1;
-        const int h = kvh * rep + it / nq_iter, qb = kvb + it % nq_iter;
-        mbar_wait(&qd_empty[st], ((it >> 1) & 1) ^ 1);
+    }
+    __syncwarp();
+    int hh = 0, qi_ = 0;                          // it = hh * nq_iter + qi_ without divisions
+    for (int it = 0; it < total; ++it) {
+      const int st = it % KST;
+      const int h = kvh * rep + hh, qb = kvb + qi_;
+      mbar_wait(&qd_empty[st], ((it / KST) & 1) ^ 1);
+      if (elect_one()) {
         mbar_expect_tx(&qd_full[st], 2 * TQ * THD * 2);
         tma_load_3d(smem + DK_Q + st * (TQ * THD * 2), &tmQ, &qd_full[st], h * THD, qb * TQ, b);
         tma_load_3d(smem + DK_DO + st * (TQ * THD * 2), &tmDO, &qd_full[st], h * THD, qb * TQ, b);
       }
+      __syncwarp();
+      if (++qi_ == nq_iter) { qi_ = 0; ++hh; }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {
       const uint32_t sk = smem_u32(smem + DK_K), sv = smem_u32(smem + DK_V);
       auto issue_sdp = [&](int u) {
-        const int it = u >> 1, hq = u & 1, st = it & 1, bb = u & 1;
-        if (hq == 0) mbar_wait(&qd_full[st], (it >> 1) & 1);
-        mbar_wait(&sdp_empty[bb], ((u >> 1) & 1) ^ 1);
+        const int it = u >> 1, hq = u & 1, st = it % KST, bb = u % NB;
+        if (hq == 0) mbar_wait(&qd_full[st], (it / KST) & 1);
+        mbar_wait(&sdp_empty[bb], ((u / NB) & 1) ^ 1);
         tc_fence_after();
-        const uint32_t sq = smem_u32(smem + DK_Q + st * (TQ * THD * 2)) + hq * (SUB * 128);
-        const uint32_t sdo = smem_u32(smem + DK_DO + st * (TQ * THD * 2)) + hq * (SUB * 128);
-        issue_nt_64(tmem_base + COL_ST + bb * SUB, sk, sq);      // S^T  = K Q_sub^T
-        issue_nt_64(tmem_base + COL_DPT + bb * SUB, sv, sdo);    // dP^T = V dO_sub^T
-        umma_commit(&sdp_full[bb]);
+        if (elect_one()) {
+          const uint32_t sq = smem_u32(smem + DK_Q + st * (TQ * THD * 2)) + hq * (SUB * 128);
+          const uint32_t sdo = smem_u32(smem + DK_DO + st * (TQ * THD * 2)) + hq * (SUB * 128);
+          issue_nt_64(tmem_base + COL_ST + bb * SUB, sk, sq);      // S^T  = K Q_sub^T
+          issue_nt_64(tmem_base + COL_DPT + bb * SUB, sv, sdo);    // dP^T = V dO_sub^T
+          umma_commit(&sdp_full[bb]);
+        }
+        __syncwarp();
       };
       mbar_wait(kv_full, 0);
       issue_sdp(0);
+      issue_sdp(1);                    // nsub >= 2 always
       for (int u = 0; u < nsub; ++u) {
-        if (u + 1 < nsub) issue_sdp(u + 1);
-        const int it = u >> 1, hq = u & 1, st = it & 1, bb = u & 1;
-        mbar_wait(&pt_full[bb], (u >> 1) & 1);
+        if (u + 2 < nsub) issue_sdp(u + 2);
+        const int it = u >> 1, hq = u & 1, st = it % KST, db = u & 1;
+        mbar_wait(&pt_full[db], (u >> 1) & 1);
         tc_fence_after();
-        const uint32_t sq = smem_u32(smem + DK_Q + st * (TQ * THD * 2)) + hq * (SUB * 128);
-        const uint32_t sdo = smem_u32(smem + DK_DO + st * (TQ * THD * 2)) + hq * (SUB * 128);
-        issue_a64_bmn(tmem_base + COL_DV, smem_u32(smem + DK_PT + bb * (TK * SUB * 2)), sdo, u > 0);   // dV += P^T dO
-        issue_a64_bmn(tmem_base + COL_DK, smem_u32(smem + DK_DST + bb * (TK * SUB * 2)), sq, u > 0);   // dK += dS^T Q
-        umma_commit(&pt_empty[bb]);
-        if (hq == 1) umma_commit(&qd_empty[st]);
+        if (elect_one()) {
+          const uint32_t sq = smem_u32(smem + DK_Q + st * (TQ * THD * 2)) + hq * (SUB * 128);
+          const uint32_t sdo = smem_u32(smem + DK_DO + st * (TQ * THD * 2)) + hq * (SUB * 128);
+          issue_a64_bmn(tmem_base + COL_DV, smem_u32(smem + DK_PT + db * (TK * SUB * 2)), sdo, u > 0);   // dV += P^T dO
+          issue_a64_bmn(tmem_base + COL_DK, smem_u32(smem + DK_DST + db * (TK * SUB * 2)), sq, u > 0);   // dK += dS^T Q
+          umma_commit(&pt_empty[db]);
+          if (hq == 1) umma_commit(&qd_empty[st]);
+          if (u == nsub - 1) umma_commit(acc_full);
+        }
+        __syncwarp();
       }
-      umma_commit(acc_full);
     }
   } else {
     const int quad = warp & 3, half = (warp - 2) >> 2;
@@ -551,24 +589,29 @@ attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
     const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16);
     const float scale_log2 = scale * kLog2e;
     const int ctid = threadIdx.x - 64;                         // 0..255 among the compute warps
+    // per 128-query tile: lse*log2e (+inf past the sequence end => P = 0) and delta*scale, staged through smem once
+    // per CTA; the global load for tile it+1 is issued one tile early so its latency hides behind tile it's math
+    auto load_ld = [&](int it) -> float {
+      const int h = kvh * rep + it / nq_iter, qb = kvb + it % nq_iter;
+      const int q = qb * TQ + (ctid & 127);
+      const int64_t li = ((int64_t)b * H + h) * S + q;
+      if (ctid < 128) return (q < S) ? __ldg(lse + li) * kLog2e : INFINITY;
+      return (q < S) ? __ldg(delta + li) * scale : 0.f;
+    };
+    float ld_next = load_ld(0);
     auto sub = [&](int u, auto diag_tag) {
       constexpr bool DIAG = decltype(diag_tag)::value;
-      const int it = u >> 1, hq = u & 1, bb = u & 1;
-      const int h = kvh * rep + it / nq_iter, qb = kvb + it % nq_iter;
+      const int it = u >> 1, hq = u & 1, bb = u % NB, db = u & 1;
+      const int qb = kvb + it % nq_iter;
       float* sLD = reinterpret_cast<float*>(smem + DK_LD) + (it & 1) * 256;
       if (hq == 0) {
-        // stage this 128-query tile's lse*log2e (+inf past the sequence end => P = 0) and delta*scale once per CTA
-        const int q = qb * TQ + (ctid & 127);
-        const int64_t li = ((int64_t)b * H + h) * S + q;
-        float val;
-        if (ctid < 128) val = (q < S) ? __ldg(lse + li) * kLog2e : INFINITY;
-        else val = (q < S) ? __ldg(delta + li) * scale : 0.f;
-        sLD[ctid] = val;
+        sLD[ctid] = ld_next;
         named_bar_sync(1, 256);
+        if (it + 1 < total) ld_next = load_ld(it + 1);
       }
       const int col0 = hq * SUB + half * 32;                   // first query column (inside the 128-query tile)
       const int qbase = qb * TQ + col0;
-      mbar_wait(&sdp_full[bb], (u >> 1) & 1);
+      mbar_wait(&sdp_full[bb], (u / NB) & 1);
       tc_fence_after();
       uint32_t sv_[32], dv_[32];
       __syncwarp();
@@ -595,12 +638,12 @@ attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
           df[i] = pv * fmaf(__uint_as_float(dv_[i]), scale, -Ds[t]);
         }
       }
-      mbar_wait(&pt_empty[bb], ((u >> 1) & 1) ^ 1);
-      store_row_chunk32(smem + DK_PT + bb * (TK * SUB * 2), r, half * 32, pf);
-      store_row_chunk32(smem + DK_DST + bb * (TK * SUB * 2), r, half * 32, df);
+      mbar_wait(&pt_empty[db], ((u >> 1) & 1) ^ 1);
+      store_row_chunk32(smem + DK_PT + db * (TK * SUB * 2), r, half * 32, pf);
+      store_row_chunk32(smem + DK_DST + db * (TK * SUB * 2), r, half * 32, df);
       fence_async_smem();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&pt_full[bb]);
+      if (lane == 0) mbar_arrive(&pt_full[db]);
     };
     for (int u = 0; u < nsub; ++u) {
       if ((u >> 1) % nq_iter == 0) sub(u, std::true_type{}); else sub(u, std::false_type{});

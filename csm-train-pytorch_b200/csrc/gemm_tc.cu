@@ -90,15 +90,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
-      int stage = 0; uint32_t phase = 0;
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-        int g, mb, nb;
-        tile_coords(t, p.num_m, p.num_n, g, mb, nb);
-        const int m0 = mb * BM, n0 = nb * BN;
-        for (int kb = 0; kb < kb_total; ++kb) {
-          mbar_wait(&empty[stage], phase ^ 1);
+    // ===================== TMA producer (warp-uniform control flow, one elected lane issues) =====================
+    int stage = 0; uint32_t phase = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      int g, mb, nb;
+      tile_coords(t, p.num_m, p.num_n, g, mb, nb);
+      const int m0 = mb * BM, n0 = nb * BN;
+      for (int kb = 0; kb < kb_total; ++kb) {
+        mbar_wait(&empty[stage], phase ^ 1);
+        if (elect_one()) {
           uint8_t* sa = smem + stage * Cfg::kStageBytes;
           uint8_t* sb = sa + BM * BK * 2;
           mbar_expect_tx(&full[stage], Cfg::kStageBytes);
@@ -120,23 +120,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             for (int c = 0; c < BN / 64; ++c)                                   // box {64 n, 64 k} x BN/64
               tma_load_3d(sb + c * (64 * BK * 2), mbp, &full[stage], n0 + c * 64, k0, g);
           }
-          if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
+        __syncwarp();
+        if (++stage == kStages) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(BM, BN, kTransA ? 1 : 0, kTransB ? 1 : 0);
-      int stage = 0; uint32_t phase = 0;
-      int acc = 0; uint32_t acc_phase = 0;
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-        mbar_wait(&tempty[acc], acc_phase ^ 1);
+    // ===================== MMA issuer (warp-uniform control flow, one elected lane issues) =====================
+    constexpr uint32_t idesc = make_idesc_bf16(BM, BN, kTransA ? 1 : 0, kTransB ? 1 : 0);
+    int stage = 0; uint32_t phase = 0;
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      mbar_wait(&tempty[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+      for (int kb = 0; kb < kb_total; ++kb) {
+        mbar_wait(&full[stage], phase);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
-        for (int kb = 0; kb < kb_total; ++kb) {
-          mbar_wait(&full[stage], phase);
-          tc_fence_after();
+        if (elect_one()) {
           const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
           const uint32_t sb = sa + BM * BK * 2;
           // K-major: 8-row groups 1024 B apart, K advance = 32 B inside the swizzle atom.
@@ -150,11 +151,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             umma_bf16(d_tmem, ad, bd, idesc, (kb | kk) ? 1u : 0u);
           }
           umma_commit(&empty[stage]);  // frees the smem slot once these MMAs have read it
-          if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&tfull[acc]);      // accumulator complete -> epilogue
-        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        __syncwarp();
+        if (++stage == kStages) { stage = 0; phase ^= 1; }
       }
+      if (elect_one()) umma_commit(&tfull[acc]);      // accumulator complete -> epilogue
+      __syncwarp();
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   } else {
     // ===================== epilogue (4 warps, TMEM lane quadrant = warp % 4) =====================

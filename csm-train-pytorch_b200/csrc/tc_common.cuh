@@ -35,6 +35,23 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
 }
 
+// One lane of a converged warp.  The producer / MMA warps keep their control flow warp-uniform and guard only the
+// TMA / tcgen05 instructions with this: operands computed under `if (lane == 0)` live in vector registers and ptxas
+// wraps every UTCHMMA / UTCBAR / UTMALDG in an R2UR + ELECT + BRA.U.ANY "waterfall" loop (~45 issue cycles per MMA,
+// 180 cycles per MMA at 4 MMAs per commit — measured, tools/ubench/mma_rate.cu); with uniform control flow the
+// descriptors stay in uniform registers and the MMAs issue back to back (129.6 cycles per 128x256x16 MMA = pipe-bound).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "elect.sync _|p, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // ------------------------------------------------------------------ TMA
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(m) : "memory");
