@@ -39,6 +39,11 @@ def gemm_profile_stop():
     return (sum(f for f, _, _ in rec), sum(a.elapsed_time(b) for _, a, b in rec), len(rec))
 
 
+def set_gemm_cta_pair_mode(m: int) -> None:
+    """Test hook: CTA-pair (cta_group::2) GEMM mode: -1 automatic, 0 never, 1 whenever the shape allows."""
+    _lib.load().csm_set_gemm_cta_pair_mode(m)
+
+
 def set_attn_backend(b: int) -> None:
     """Test hook: 0 auto, 1 scalar, 2 mma.sync, 3 tcgen05, 4 short-sequence (seq <= 32)."""
     _lib.load().csm_set_attn_backend(b)

@@ -105,6 +105,8 @@ using namespace csm;
 
 extern "C" int csm_abi_version(void) { return CSM_ABI_VERSION; }
 extern "C" void csm_set_attn_backend(int32_t backend) { g_attn_backend.store(backend); }
+namespace csm { void gemm_tc_set_cta_pair_mode(int m); }
+extern "C" void csm_set_gemm_cta_pair_mode(int32_t mode) { csm::gemm_tc_set_cta_pair_mode(mode); }
 extern "C" const char* csm_last_error(void) { return g_err; }
 extern "C" int64_t csm_launch_count(void) { return g_launches.load(); }
 

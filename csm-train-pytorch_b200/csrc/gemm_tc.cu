@@ -34,9 +34,13 @@ struct GemmTcParams {
   const float* lse; float gscale; const float* gscale_dev;
 };
 
-template <int BN> struct GemmCfg {
-  static constexpr int kStages = (BN == 256) ? 4 : 6;
-  static constexpr int kStageBytes = BM * BK * 2 + BN * BK * 2;
+// kCta2: CTA-pair mode (cluster of 2, tcgen05 cta_group::2).  The pair computes a 256 x BN tile: each CTA keeps its
+// own 128 rows of A and HALF of the B tile in smem (32 KB per stage instead of 48 KB -> 6 stages, a third less
+// L2->SM traffic per flop), the leader CTA issues M=256 MMAs, each CTA's 128 x BN accumulator lives in its own TMEM.
+template <int BN, bool kCta2> struct GemmCfg {
+  static constexpr int kBRows = kCta2 ? BN / 2 : BN;            // B-tile rows held by this CTA
+  static constexpr int kStages = (BN == 256 && !kCta2) ? 4 : 6;
+  static constexpr int kStageBytes = BM * BK * 2 + kBRows * BK * 2;
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
   static constexpr int kTmemCols = 2 * BN;
 };
@@ -55,12 +59,12 @@ __device__ __forceinline__ void tile_coords(int t, int num_m, int num_n, int& g,
   nb = in_band / band_m;
 }
 
-template <bool kTransA, bool kTransB, int BN, int kEpi>
+template <bool kTransA, bool kTransB, int BN, int kEpi, bool kCta2>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2,
                const GemmTcParams p) {
-  using Cfg = GemmCfg<BN>;
+  using Cfg = GemmCfg<BN, kCta2>;
   constexpr int kStages = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -72,7 +76,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int num_tiles = p.groups * p.num_m * p.num_n;
+  // CTA-pair mode: the scheduling unit is the pair; it walks (m-block pair, n-block) super-tiles in lockstep
+  const uint32_t rank = kCta2 ? cluster_ctarank() : 0u;
+  const int tile_m = kCta2 ? (p.num_m + 1) / 2 : p.num_m;
+  const int num_tiles = p.groups * tile_m * p.num_n;
+  const int first_tile = kCta2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int tile_step = kCta2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   const int kb_total = p.k_blocks + p.has_tail;
 
   if (warp == 0 && lane == 0) {
@@ -80,45 +89,70 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     tma_prefetch_desc(&tmB);
     if (p.has_tail) { tma_prefetch_desc(&tmA2); tma_prefetch_desc(&tmB2); }
     for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 4); }
+    // pair mode: the leader's MMA warp waits for the epilogue warps of BOTH CTAs
+    for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], kCta2 ? 8 : 4); }
     mbar_fence_init();
   }
-  if (warp == 1) tmem_alloc(tmem_slot, Cfg::kTmemCols);
+  if (warp == 1) {
+    if (kCta2) tmem_alloc_2sm(tmem_slot, Cfg::kTmemCols); else tmem_alloc(tmem_slot, Cfg::kTmemCols);
+  }
   tc_fence_before();
   __syncthreads();
+  if (kCta2) cluster_sync();      // the peer's barriers are initialised before any remote arrive / complete_tx
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
     // ===================== TMA producer (warp-uniform control flow, one elected lane issues) =====================
     int stage = 0; uint32_t phase = 0;
-    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+    for (int t = first_tile; t < num_tiles; t += tile_step) {
       int g, mb, nb;
-      tile_coords(t, p.num_m, p.num_n, g, mb, nb);
-      const int m0 = mb * BM, n0 = nb * BN;
+      tile_coords(t, tile_m, p.num_n, g, mb, nb);
+      if (kCta2) mb = 2 * mb + (int)rank;
+      const int m0 = mb * BM;
+      const int n0 = nb * BN + (kCta2 ? (int)rank * Cfg::kBRows : 0);          // pair mode: this CTA's half of B
       for (int kb = 0; kb < kb_total; ++kb) {
         mbar_wait(&empty[stage], phase ^ 1);
         if (elect_one()) {
           uint8_t* sa = smem + stage * Cfg::kStageBytes;
           uint8_t* sb = sa + BM * BK * 2;
-          mbar_expect_tx(&full[stage], Cfg::kStageBytes);
           const bool tail = kb >= p.k_blocks;
           const CUtensorMap* ma = tail ? &tmA2 : &tmA;
           const CUtensorMap* mbp = tail ? &tmB2 : &tmB;
           const int k0 = tail ? 0 : kb * BK;
-          if (!kTransA) {
-            tma_load_3d(sa, ma, &full[stage], k0, m0, g);                       // box {64 k, 128 m}
-          } else {
+          if (!kCta2) {
+            mbar_expect_tx(&full[stage], Cfg::kStageBytes);
+            if (!kTransA) {
+              tma_load_3d(sa, ma, &full[stage], k0, m0, g);                     // box {64 k, 128 m}
+            } else {
 #pragma unroll
-            for (int c = 0; c < BM / 64; ++c)                                   // box {64 m, 64 k} x2
-              tma_load_3d(sa + c * (64 * BK * 2), ma, &full[stage], m0 + c * 64, k0, g);
-          }
-          if (!kTransB) {
-            tma_load_3d(sb, mbp, &full[stage], k0, n0, g);                      // box {64 k, BN n}
-          } else {
+              for (int c = 0; c < BM / 64; ++c)                                 // box {64 m, 64 k} x2
+                tma_load_3d(sa + c * (64 * BK * 2), ma, &full[stage], m0 + c * 64, k0, g);
+            }
+            if (!kTransB) {
+              tma_load_3d(sb, mbp, &full[stage], k0, n0, g);                    // box {64 k, BN n}
+            } else {
 #pragma unroll
-            for (int c = 0; c < BN / 64; ++c)                                   // box {64 n, 64 k} x BN/64
-              tma_load_3d(sb + c * (64 * BK * 2), mbp, &full[stage], n0 + c * 64, k0, g);
+              for (int c = 0; c < BN / 64; ++c)                                 // box {64 n, 64 k} x BN/64
+                tma_load_3d(sb + c * (64 * BK * 2), mbp, &full[stage], n0 + c * 64, k0, g);
+            }
+          } else {
+            // both CTAs' bytes are counted by the LEADER's full barrier (its MMA warp is the only consumer)
+            const uint32_t fbar = mapa(smem_u32(&full[stage]), 0);
+            if (rank == 0) mbar_expect_tx(&full[stage], 2 * Cfg::kStageBytes);
+            if (!kTransA) {
+              tma_load_3d_2sm(sa, ma, fbar, k0, m0, g);
+            } else {
+#pragma unroll
+              for (int c = 0; c < BM / 64; ++c) tma_load_3d_2sm(sa + c * (64 * BK * 2), ma, fbar, m0 + c * 64, k0, g);
+            }
+            if (!kTransB) {
+              tma_load_3d_2sm(sb, mbp, fbar, k0, n0, g);                        // box {64 k, BN/2 n}
+            } else {
+#pragma unroll
+              for (int c = 0; c < Cfg::kBRows / 64; ++c)
+                tma_load_3d_2sm(sb + c * (64 * BK * 2), mbp, fbar, n0 + c * 64, k0, g);
+            }
           }
         }
         __syncwarp();
@@ -127,10 +161,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (warp-uniform control flow, one elected lane issues) =====================
-    constexpr uint32_t idesc = make_idesc_bf16(BM, BN, kTransA ? 1 : 0, kTransB ? 1 : 0);
+    constexpr uint32_t idesc = make_idesc_bf16(kCta2 ? 2 * BM : BM, BN, kTransA ? 1 : 0, kTransB ? 1 : 0);
     int stage = 0; uint32_t phase = 0;
     int acc = 0; uint32_t acc_phase = 0;
-    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+    for (int t = first_tile; t < num_tiles && rank == 0; t += tile_step) {   // pair mode: the leader issues for both
       mbar_wait(&tempty[acc], acc_phase ^ 1);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
@@ -148,14 +182,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           for (int kk = 0; kk < BK / 16; ++kk) {
             const uint64_t ad = adesc + (uint64_t)((kTransA ? kk * 16 * 128 : kk * 32) >> 4);
             const uint64_t bd = bdesc + (uint64_t)((kTransB ? kk * 16 * 128 : kk * 32) >> 4);
-            umma_bf16(d_tmem, ad, bd, idesc, (kb | kk) ? 1u : 0u);
+            if (kCta2) umma_bf16_2sm(d_tmem, ad, bd, idesc, (kb | kk) ? 1u : 0u);
+            else umma_bf16(d_tmem, ad, bd, idesc, (kb | kk) ? 1u : 0u);
           }
-          umma_commit(&empty[stage]);  // frees the smem slot once these MMAs have read it
+          // frees the smem slot (in both CTAs of a pair) once these MMAs have read it
+          if (kCta2) umma_commit_2sm(&empty[stage], 3); else umma_commit(&empty[stage]);
         }
         __syncwarp();
         if (++stage == kStages) { stage = 0; phase ^= 1; }
       }
-      if (elect_one()) umma_commit(&tfull[acc]);      // accumulator complete -> epilogue
+      if (elect_one()) {                               // accumulator complete -> epilogue (of both CTAs)
+        if (kCta2) umma_commit_2sm(&tfull[acc], 3); else umma_commit(&tfull[acc]);
+      }
       __syncwarp();
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
@@ -163,9 +201,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // ===================== epilogue (4 warps, TMEM lane quadrant = warp % 4) =====================
     const int quad = warp & 3;
     int acc = 0; uint32_t acc_phase = 0;
-    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+    for (int t = first_tile; t < num_tiles; t += tile_step) {
       int g, mb, nb;
-      tile_coords(t, p.num_m, p.num_n, g, mb, nb);
+      tile_coords(t, tile_m, p.num_n, g, mb, nb);
+      if (kCta2) mb = 2 * mb + (int)rank;
       const int64_t m = (int64_t)mb * BM + quad * 32 + lane;
       const int64_t n0 = (int64_t)nb * BN;
       mbar_wait(&tfull[acc], acc_phase);
@@ -321,16 +360,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       // this warp has drained its quadrant of the accumulator
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty[acc]);
+      if (lane == 0) {
+        if (kCta2 && rank != 0) mbar_arrive_cluster(mapa(smem_u32(&tempty[acc]), 0));
+        else mbar_arrive(&tempty[acc]);
+      }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   }
 
   tc_fence_before();
   __syncthreads();
+  if (kCta2) cluster_sync();      // no CTA of the pair exits (or frees TMEM) while the other may still touch it
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+    if (kCta2) tmem_dealloc_2sm(tmem_base, Cfg::kTmemCols); else tmem_dealloc(tmem_base, Cfg::kTmemCols);
   }
 }
 
@@ -378,32 +421,64 @@ struct GemmTcOperands {
   int transA, transB;
 };
 
-template <bool TA, bool TB, int BN, int EPI>
+template <bool TA, bool TB, int BN, int EPI, bool CTA2>
 static int launch_inst(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& a2, const CUtensorMap& b2,
                        const GemmTcParams& p, cudaStream_t st) {
-  using Cfg = GemmCfg<BN>;
-  auto kern = gemm_tc_kernel<TA, TB, BN, EPI>;
+  using Cfg = GemmCfg<BN, CTA2>;
+  auto kern = gemm_tc_kernel<TA, TB, BN, EPI, CTA2>;
   static bool configured = false;
+  static int max_pairs = 0;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
     if (e != cudaSuccess) { set_error("gemm_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return CSM_ERR_CUDA; }
+    if (CTA2) {
+      // how many CTA pairs can be co-resident (a pair needs two SMs of one TPC): the persistent grid must not
+      // exceed it, or a late pair would start only after an early one has finished its whole share
+      cudaLaunchConfig_t q = {};
+      q.gridDim = dim3(num_sms() & ~1); q.blockDim = dim3(kGemmThreads); q.dynamicSmemBytes = Cfg::kSmemBytes;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeClusterDimension;
+      at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+      q.attrs = at; q.numAttrs = 1;
+      int n = 0;
+      e = cudaOccupancyMaxActiveClusters(&n, kern, &q);
+      if (e != cudaSuccess || n < 1) { cudaGetLastError(); n = num_sms() / 2 - 2; }
+      max_pairs = n < num_sms() / 2 ? n : num_sms() / 2;
+    }
     configured = true;
   }
-  const int tiles = p.groups * p.num_m * p.num_n;
-  const int grid = tiles < num_sms() ? tiles : num_sms();
-  kern<<<grid, kGemmThreads, Cfg::kSmemBytes, st>>>(a, b, a2, b2, p);
+  if (!CTA2) {
+    const int tiles = p.groups * p.num_m * p.num_n;
+    const int grid = tiles < num_sms() ? tiles : num_sms();
+    kern<<<grid, kGemmThreads, Cfg::kSmemBytes, st>>>(a, b, a2, b2, p);
+  } else {
+    const int tiles = p.groups * ((p.num_m + 1) / 2) * p.num_n;
+    const int pairs = tiles < max_pairs ? tiles : max_pairs;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * pairs); cfg.blockDim = dim3(kGemmThreads); cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, a, b, a2, b2, p);
+    if (e != cudaSuccess) { set_error("gemm_tc (CTA pair): launch failed: %s", cudaGetErrorString(e)); return CSM_ERR_CUDA; }
+  }
   CSM_CHECK_LAUNCH("gemm_tc");
   return CSM_OK;
 }
 
-template <int BN, int EPI>
+template <int BN, int EPI, bool CTA2>
 static int launch_major(const GemmTcOperands& o, const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& a2,
                         const CUtensorMap& b2, const GemmTcParams& p, cudaStream_t st) {
-  if (!o.transA && !o.transB) return launch_inst<false, false, BN, EPI>(a, b, a2, b2, p, st);
-  if (!o.transA && o.transB) return launch_inst<false, true, BN, EPI>(a, b, a2, b2, p, st);
-  if (o.transA && !o.transB) return launch_inst<true, false, BN, EPI>(a, b, a2, b2, p, st);
-  return launch_inst<true, true, BN, EPI>(a, b, a2, b2, p, st);
+  if (!o.transA && !o.transB) return launch_inst<false, false, BN, EPI, CTA2>(a, b, a2, b2, p, st);
+  if (!o.transA && o.transB) return launch_inst<false, true, BN, EPI, CTA2>(a, b, a2, b2, p, st);
+  if (o.transA && !o.transB) return launch_inst<true, false, BN, EPI, CTA2>(a, b, a2, b2, p, st);
+  return launch_inst<true, true, BN, EPI, CTA2>(a, b, a2, b2, p, st);
 }
+
+static std::atomic<int> g_cta2_mode{-1};   // -1 auto, 0 never, 1 whenever legal (test hook)
+void gemm_tc_set_cta_pair_mode(int m) { g_cta2_mode.store(m); }
 
 // BN = 256 unless that leaves SMs idle (or N is narrow) and 128 would fill them better
 static int choose_bn(int groups, int64_t M, int64_t N) {
@@ -413,8 +488,14 @@ static int choose_bn(int groups, int64_t M, int64_t N) {
 
 // Shared driver for the plain GEMM and the CE epilogues.
 int gemm_tc_run(const GemmTcOperands& o, GemmTcParams p, int epi, cudaStream_t st) {
-  const int bn = choose_bn(p.groups, p.M, p.N);
+  const int mode = g_cta2_mode.load();
   p.num_m = (int)((p.M + BM - 1) / BM);
+  // CTA-pair mode (256 x 256 super-tiles) for the plain GEMMs that can keep at least ~2/3 of the 74 pairs busy;
+  // the test hook (mode 1) turns it on for every shape with two m-blocks and more than one 128-column tile
+  const int64_t super256 = (int64_t)p.groups * ((p.num_m + 1) / 2) * ((p.N + 255) / 256);
+  const bool cta2 = epi == EPI_STORE && p.num_m >= 2 && p.N > 128 && mode != 0 && (mode == 1 || super256 >= 48);
+  const int bn = cta2 ? 256 : choose_bn(p.groups, p.M, p.N);
+  const uint32_t b_box = cta2 ? (uint32_t)bn / 2 : (uint32_t)bn;
   p.num_n = (int)((p.N + bn - 1) / bn);
   p.k_blocks = (int)((p.K + BK - 1) / BK);
   p.has_tail = (o.A2 && o.K2 > 0) ? 1 : 0;
@@ -428,19 +509,20 @@ int gemm_tc_run(const GemmTcOperands& o, GemmTcParams p, int epi, cudaStream_t s
                 : encode_tmap_bf16(&ta, o.A, p.K, p.M, G, o.lda, ags, BM);
   if (rc) return rc;
   rc = o.transB ? encode_tmap_bf16(&tb, o.B, p.N, p.K, G, o.ldb, bgs, 64)
-                : encode_tmap_bf16(&tb, o.B, p.K, p.N, G, o.ldb, bgs, bn);
+                : encode_tmap_bf16(&tb, o.B, p.K, p.N, G, o.ldb, bgs, b_box);
   if (rc) return rc;
   if (p.has_tail) {
     rc = o.transA ? encode_tmap_bf16(&ta2, o.A2, p.M, o.K2, 1, o.lda2, 8, 64)
                   : encode_tmap_bf16(&ta2, o.A2, o.K2, p.M, 1, o.lda2, 8, BM);
     if (rc) return rc;
     rc = o.transB ? encode_tmap_bf16(&tb2, o.B2, p.N, o.K2, 1, o.ldb2, 8, 64)
-                  : encode_tmap_bf16(&tb2, o.B2, o.K2, p.N, 1, o.ldb2, 8, bn);
+                  : encode_tmap_bf16(&tb2, o.B2, o.K2, p.N, 1, o.ldb2, 8, b_box);
     if (rc) return rc;
   } else {
     ta2 = ta; tb2 = tb;
   }
-#define DISPATCH(BN_, EPI_) return launch_major<BN_, EPI_>(o, ta, tb, ta2, tb2, p, st)
+#define DISPATCH(BN_, EPI_) return launch_major<BN_, EPI_, false>(o, ta, tb, ta2, tb2, p, st)
+  if (cta2) return launch_major<256, EPI_STORE, true>(o, ta, tb, ta2, tb2, p, st);
   if (epi == EPI_STORE) { if (bn == 256) DISPATCH(256, EPI_STORE); else DISPATCH(128, EPI_STORE); }
   if (epi == EPI_CE_PARTIAL) { if (bn == 256) DISPATCH(256, EPI_CE_PARTIAL); else DISPATCH(128, EPI_CE_PARTIAL); }
   if (bn == 256) DISPATCH(256, EPI_CE_DLOGITS); else DISPATCH(128, EPI_CE_DLOGITS);

@@ -116,9 +116,13 @@ int csm_swiglu_bwd(const void* dout, const void* gate, const void* up, void* dga
 int csm_attn_causal_gqa_fwd(const void* q, const void* k, const void* v, void* o, float* lse, int32_t batch,
                             int32_t seq, int32_t heads, int32_t kv_heads, int32_t head_dim, int64_t ldq,
                             int64_t ldk, int64_t ldv, int64_t ldo, float scale, csm_stream_t stream);
-/* test hook: force the attention back-end. 0 = automatic (tcgen05 forward for head_dim 64 and seq >= 128, mma.sync
- * for head_dim 64, scalar otherwise), 1 = scalar, 2 = mma.sync, 3 = tcgen05 (forward; error if unsupported). */
+/* test hook: force the attention back-end. 0 = automatic (tcgen05 for head_dim 64 and seq >= 128, the
+ * short-sequence kernel for seq <= 32 and head_dim 64/128 (depth decoder), mma.sync for other head_dim 64 shapes,
+ * scalar otherwise), 1 = scalar, 2 = mma.sync, 3 = tcgen05, 4 = short-sequence (3/4: error if unsupported). */
 void csm_set_attn_backend(int32_t backend);
+/* test hook: CTA-pair (tcgen05 cta_group::2, 256-row tiles) mode of the tensor-core GEMM. -1 = automatic (large
+ * plain GEMMs only), 0 = never, 1 = whenever the shape allows it. */
+void csm_set_gemm_cta_pair_mode(int32_t mode);
 /* workspace: csm_attn_bwd_workspace_bytes() bytes (delta[batch,heads,seq] fp32 + fp32 dk/dv staging). */
 size_t csm_attn_bwd_workspace_bytes(int32_t batch, int32_t seq, int32_t heads, int32_t kv_heads,
                                     int32_t head_dim);

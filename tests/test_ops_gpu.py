@@ -170,6 +170,38 @@ def test_gemm_all_majors(ops, cuda, backend, ta, tb, M, N, K):
     assert rel_err(out, ref) < 5e-3, rel_err(out, ref)
 
 
+@pytest.mark.parametrize("ta,tb", [(False, False), (False, True), (True, False), (True, True)])
+@pytest.mark.parametrize("M,N,K", [(256, 256, 64), (4096, 2048, 2048), (384, 520, 200), (1000, 2051, 1024),
+                                   (4096, 16384, 2048)])
+def test_gemm_cta_pair_mode(ops, cuda, ta, tb, M, N, K):
+    """tcgen05 cta_group::2 path (256-row tiles over a 2-CTA cluster) forced on: odd m-block counts, ragged N and K,
+    residual + alpha + accumulate epilogues and the LoRA extra K block."""
+    g = torch.Generator().manual_seed(M + N + K)
+    def mk(r, c):
+        ld = (c + 7) // 8 * 8
+        return (torch.randn(r, ld, generator=g) * 0.5).to(BF).to(cuda)[:, :c]
+    a = mk(K, M) if ta else mk(M, K)
+    b = mk(K, N) if tb else mk(N, K)
+    ref = (a.float().t() if ta else a.float()) @ (b.float() if tb else b.float().t())
+    ops.set_gemm_cta_pair_mode(1)
+    try:
+        out = ops.gemm(a, b, trans_a=ta, trans_b=tb, backend=2)
+        assert rel_err(out, ref) < 5e-3, rel_err(out, ref)
+        res = mk(M, N)
+        out2 = ops.gemm(a, b, trans_a=ta, trans_b=tb, residual=res, alpha=0.5, backend=2)
+        assert rel_err(out2, 0.5 * ref + res.float()) < 5e-3
+        acc = res.float().clone()
+        ops.gemm(a, b, trans_a=ta, trans_b=tb, out=acc, accumulate=True, backend=2)
+        assert rel_err(acc, res.float() + ref) < 2e-3
+        if not ta and not tb:
+            r = 16
+            t, lb = mk(M, r), mk(N, r)
+            out3 = ops.gemm(a, b, a2=t, b2=lb, backend=2)
+            assert rel_err(out3, ref + t.float() @ lb.float().t()) < 5e-3
+    finally:
+        ops.set_gemm_cta_pair_mode(-1)
+
+
 @pytest.mark.parametrize("backend", [1, 2])
 def test_gemm_epilogues_and_lora_tail(ops, cuda, backend):
     g = torch.Generator().manual_seed(5)
