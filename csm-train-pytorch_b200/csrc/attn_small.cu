@@ -245,40 +245,39 @@ attn_small_bwd_kernel(const bf16* __restrict__ q, const bf16* __restrict__ k, co
   __syncthreads();
 
   // ---- phase 2: column-parallel — dK[j] = sum_h sum_{i>=j} dS[i][j] Q[i], dV[j] = sum_h sum_{i>=j} P[i][j] dO[i]
-  constexpr int CW = 16;                 // head-dim elements per work item
+  // a work item is a pair of keys (j, 31 - j) x 8 head-dim elements: every item walks the same 33 query rows per
+  // head, so the causal triangle is balanced across the threads
+  constexpr int CW = 8;
   constexpr int NC = HD / CW;
-  for (int item = tid; item < kMaxS * NC; item += nthr) {
-    const int j = item / NC, c = item % NC;
-    if (j >= S) continue;
-    float ak[CW], av[CW];
+  for (int item = tid; item < (kMaxS / 2) * NC; item += nthr) {
+    const int jlo = item / NC, c = item % NC;
+#pragma unroll 1
+    for (int side = 0; side < 2; ++side) {
+      const int j = side ? kMaxS - 1 - jlo : jlo;
+      if (j >= S) continue;
+      float ak[CW], av[CW];
 #pragma unroll
-    for (int t = 0; t < CW; ++t) { ak[t] = 0.f; av[t] = 0.f; }
-    for (int r = 0; r < rep; ++r) {
-      const float* Pr = Ps + r * kMaxS * PS;
-      const float* Gr = Gs + r * kMaxS * PS;
-      const bf16* Qr = Qs + r * kMaxS * HD + c * CW;
-      const bf16* Dr = Ds + r * kMaxS * HD + c * CW;
-      for (int i = j; i < S; ++i) {
-        const float ds = Gr[i * PS + j], pp = Pr[i * PS + j];
-        float f[8];
-        unpack8(*reinterpret_cast<const uint4*>(Qr + i * HD), f);
+      for (int t = 0; t < CW; ++t) { ak[t] = 0.f; av[t] = 0.f; }
+      for (int r = 0; r < rep; ++r) {
+        const float* Pr = Ps + r * kMaxS * PS + j;
+        const float* Gr = Gs + r * kMaxS * PS + j;
+        const bf16* Qr = Qs + r * kMaxS * HD + c * CW;
+        const bf16* Dr = Ds + r * kMaxS * HD + c * CW;
+#pragma unroll 4
+        for (int i = j; i < S; ++i) {
+          const float ds = Gr[i * PS], pp = Pr[i * PS];
+          float f[8];
+          unpack8(*reinterpret_cast<const uint4*>(Qr + i * HD), f);
 #pragma unroll
-        for (int t = 0; t < 8; ++t) ak[t] += ds * f[t];
-        unpack8(*reinterpret_cast<const uint4*>(Qr + i * HD + 8), f);
+          for (int t = 0; t < 8; ++t) ak[t] += ds * f[t];
+          unpack8(*reinterpret_cast<const uint4*>(Dr + i * HD), f);
 #pragma unroll
-        for (int t = 0; t < 8; ++t) ak[8 + t] += ds * f[t];
-        unpack8(*reinterpret_cast<const uint4*>(Dr + i * HD), f);
-#pragma unroll
-        for (int t = 0; t < 8; ++t) av[t] += pp * f[t];
-        unpack8(*reinterpret_cast<const uint4*>(Dr + i * HD + 8), f);
-#pragma unroll
-        for (int t = 0; t < 8; ++t) av[8 + t] += pp * f[t];
+          for (int t = 0; t < 8; ++t) av[t] += pp * f[t];
+        }
       }
+      store_half_global<CW>(dk + ((int64_t)b * S + j) * lddk + (int64_t)kvh * HD + c * CW, ak, 1.f);
+      store_half_global<CW>(dv + ((int64_t)b * S + j) * lddv + (int64_t)kvh * HD + c * CW, av, 1.f);
     }
-    bf16* dkp = dk + ((int64_t)b * S + j) * lddk + (int64_t)kvh * HD + c * CW;
-    bf16* dvp = dv + ((int64_t)b * S + j) * lddv + (int64_t)kvh * HD + c * CW;
-    store_half_global<CW>(dkp, ak, 1.f);
-    store_half_global<CW>(dvp, av, 1.f);
   }
 }
 

@@ -77,8 +77,13 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   static_assert(FST <= 4, "barrier slots");
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int qb = gridDim.x - 1 - blockIdx.x;  // longest rows first
-  const int h = blockIdx.y, b = blockIdx.z;
+  // 1-D grid in longest-processing-time-first order: all (head, batch) CTAs of the last query tile (most key blocks)
+  // are dispatched before any of the next-to-last one, ... — the causal triangle then packs to ~95 % of the SM-time
+  const int nq = (S + TQ - 1) / TQ;
+  const int per_q = (int)gridDim.x / nq;       // H * B
+  const int qb = nq - 1 - (int)blockIdx.x / per_q;
+  const int hb = (int)blockIdx.x % per_q;
+  const int h = hb % H, b = hb / H;
   const int kvh = h / (H / KV);
   const int q0 = qb * TQ;
   const int nblk = min(2 * (qb + 1), (S + FK - 1) / FK);   // 64-key blocks up to the diagonal
@@ -327,8 +332,11 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
   static_assert(KST == 3 && NB == 3, "barrier slots");
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int qb = gridDim.x - 1 - blockIdx.x;
-  const int h = blockIdx.y, b = blockIdx.z;
+  const int nq = (S + TQ - 1) / TQ;            // 1-D grid, longest query tiles first (see the forward kernel)
+  const int per_q = (int)gridDim.x / nq;
+  const int qb = nq - 1 - (int)blockIdx.x / per_q;
+  const int hb = (int)blockIdx.x % per_q;
+  const int h = hb % H, b = hb / H;
   const int kvh = h / (H / KV);
   const int q0 = qb * TQ;
   const int nblk = qb + 1;
@@ -500,7 +508,10 @@ attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int kvb = blockIdx.x, kvh = blockIdx.y, b = blockIdx.z;
+  const int nkb = (S + TK - 1) / TK;           // 1-D grid, longest first: key tile 0 meets every query tile
+  const int per_k = (int)gridDim.x / nkb;      // KV * B
+  const int kvb = (int)blockIdx.x / per_k;
+  const int kvh = ((int)blockIdx.x % per_k) % KV, b = ((int)blockIdx.x % per_k) / KV;
   const int rep = H / KV;
   const int k0 = kvb * TK;
   const int nqb = (S + TQ - 1) / TQ;
@@ -702,7 +713,7 @@ int attn_fwd_tc_launch(const void* q, const void* k, const void* v, void* o, flo
     if (e != cudaSuccess) { set_error("attn_fwd_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return CSM_ERR_CUDA; }
     configured = true;
   }
-  dim3 grid((S + TQ - 1) / TQ, H, B);
+  dim3 grid(((S + TQ - 1) / TQ) * H * B);
   attn_fwd_tc_kernel<<<grid, kAttnThreads, kAttnSmem, st>>>(tq, tk, tv, (bf16*)o, lse, S, H, KV, ldo, scale * kLog2e);
   CSM_CHECK_LAUNCH("attn_fwd_tc");
   return CSM_OK;
@@ -732,10 +743,10 @@ int attn_bwd_tc_launch(const void* q, const void* k, const void* v, const void* 
     if (e != cudaSuccess) { set_error("attn_bwd_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return CSM_ERR_CUDA; }
     configured = true;
   }
-  dim3 gq((S + TQ - 1) / TQ, H, B);
+  dim3 gq(((S + TQ - 1) / TQ) * H * B);
   attn_bwd_dq_tc_kernel<<<gq, kBwdThreads, kDqSmem, st>>>(tq, tk, tv, tdo, lse, delta, (bf16*)dq, S, H, KV, lddq, scale);
   CSM_CHECK_LAUNCH("attn_bwd_dq_tc");
-  dim3 gk((S + TK - 1) / TK, KV, B);
+  dim3 gk(((S + TK - 1) / TK) * KV * B);
   attn_bwd_dkdv_tc_kernel<<<gk, kBwdThreads, kDkSmem, st>>>(tq, tk, tv, tdo, lse, delta, (bf16*)dk, (bf16*)dv, S, H, KV,
                                                             lddk, lddv, scale);
   CSM_CHECK_LAUNCH("attn_bwd_dkdv_tc");
