@@ -14,6 +14,10 @@ from torch.autograd import Function
 from . import ops
 
 BF16 = torch.bfloat16
+# The w2-dgrad GEMM with the SwiGLU backward in its epilogue is correct (tests/test_ops_gpu.py) but its epilogue reads
+# gate/up one row per lane and is latency-bound: 226 us against 87 + 68 us for GEMM + swiglu_bwd at 4096 x 8192 x 2048
+# (profiles/r1_summary.md), so the backward stays unfused; the forward fusion saves 43 us per layer and is on.
+FUSE_SWIGLU_BWD = False
 
 
 # ----------------------------------------------------------------------------- A2: embedding gather-sum
@@ -94,17 +98,23 @@ class _Lin:
         t = ops.gemm(x, self.A, alpha=self.s)                      # [N, r]
         return ops.gemm(x, self.w, residual=residual, a2=t, b2=self.B), t
 
-    def bwd(self, dy, x, t, grads, need, dx_out=None, accumulate=False):
-        """Accumulates parameter grads into `grads` and returns dx (optionally accumulated into dx_out)."""
+    def bwd(self, dy, x, t, grads, need, dx_out=None, accumulate=False, swiglu_gu=None):
+        """Accumulates parameter grads into `grads` and returns dx (optionally accumulated into dx_out).
+        With `swiglu_gu` (the saved gate|up buffer of a fused MLP) the dgrad GEMM's epilogue applies the SwiGLU
+        backward and the return value is dgate|dup instead of dx."""
         if need[self.iw]:
             _acc(grads, self.iw, ops.gemm(dy, x, trans_a=True, trans_b=True))
         if self.A is None:
+            if swiglu_gu is not None:
+                return ops.gemm_swiglu_bwd(dy, self.w, swiglu_gu)
             return ops.gemm(dy, self.w, trans_b=True, out=dx_out, accumulate=accumulate)
         dts = ops.gemm(dy, self.B, trans_b=True, alpha=self.s)     # s * dy B  [N, r]
         if need[self.iB]:
             _acc(grads, self.iB, ops.gemm(dy, t, trans_a=True, trans_b=True))      # dy^T t   [out, r]
         if need[self.iA]:
             _acc(grads, self.iA, ops.gemm(dts, x, trans_a=True, trans_b=True))     # dts^T x  [r, in]
+        if swiglu_gu is not None:
+            return ops.gemm_swiglu_bwd(dy, self.w, swiglu_gu, a2=dts, b2=self.A)
         return ops.gemm(dy, self.w, trans_b=True, a2=dts, b2=self.A, out=dx_out, accumulate=accumulate)
 
 
@@ -176,6 +186,15 @@ class _Group:
         t = ops.gemm(x, self.A_cat)                                    # [N, R]
         return ops.gemm(x, self.W, a2=t, b2=self.B_bd), t
 
+    def fwd_swiglu(self, x):
+        """gate/up group only: (gate|up, act = silu(gate) * up, t) with the SwiGLU in the GEMM epilogue."""
+        if not self.lora:
+            gu, act = ops.gemm_swiglu_fwd(x, self.W)
+            return gu, act, None
+        t = ops.gemm(x, self.A_cat)
+        gu, act = ops.gemm_swiglu_fwd(x, self.W, a2=t, b2=self.B_bd)
+        return gu, act, t
+
     def bwd(self, dy, x, t, grads, need):
         if any(need[i] for i in self.iw):
             dW = ops.gemm(dy, x, trans_a=True, trans_b=True)          # [n_out, in] in one GEMM
@@ -228,8 +247,11 @@ class StackFn(Function):
             o, lse = ops.attention_fwd(q, k, v, B, S, H, KV, hd)
             h, to = lo.fwd(o, residual=cur)
             hn, rstd2 = ops.rmsnorm(h, layer.mlp_norm.scale, eps)
-            gu, t13 = g13.fwd(hn)
-            act = ops.swiglu(gu[:, :I], gu[:, I:])
+            if ops.swiglu_fusable(N, I, D):
+                gu, act, t13 = g13.fwd_swiglu(hn)
+            else:
+                gu, t13 = g13.fwd(hn)
+                act = ops.swiglu(gu[:, :I], gu[:, I:])
             out, t2 = l2.fwd(act, residual=h)
             saved.append((cur, rstd1, xn, qkv, o, lse, h, rstd2, hn, gu, act, (tqkv, to, t13, t2),
                           (gqkv, lo, g13, l2), layer))
@@ -284,9 +306,12 @@ class StackFn(Function):
             gqkv, lo, g13, l2 = lins
             I = gu.shape[1] // 2
             # ---- MLP: out = h + w2(silu(w1 hn) * w3 hn)
-            dact = l2.bwd(dcur, act, t2, grads, need)
-            dgu = torch.empty_like(gu)
-            ops.swiglu_bwd(dact, gu[:, :I], gu[:, I:], dgate=dgu[:, :I], dup=dgu[:, I:])
+            if FUSE_SWIGLU_BWD and ops.swiglu_fusable(N, I, D):
+                dgu = l2.bwd(dcur, act, t2, grads, need, swiglu_gu=gu)
+            else:
+                dact = l2.bwd(dcur, act, t2, grads, need)
+                dgu = torch.empty_like(gu)
+                ops.swiglu_bwd(dact, gu[:, :I], gu[:, I:], dgate=dgu[:, :I], dup=dgu[:, I:])
             dhn = g13.bwd(dgu, hn, t13, grads, need)
             dh = norm_bwd(dhn, h, layer.mlp_norm, rstd2, dcur)
             # ---- attention: h = x + wo(attn(rope(wq xn), rope(wk xn), wv xn))

@@ -206,6 +206,53 @@ def gemm(a, b, *, trans_a: bool = False, trans_b: bool = False, out: Optional[to
     return out
 
 
+# ----------------------------------------------------------------------------- fused SwiGLU MLP GEMMs
+def swiglu_fusable(M: int, inter: int, K: int) -> bool:
+    """True when the w1|w3 GEMM + SwiGLU (and the w2 dgrad + SwiGLU backward) run as one tcgen05 launch each."""
+    return _backend_override != GEMM_SIMT and bool(_lib.load().csm_gemm_swiglu_supported(M, inter, K))
+
+
+def gemm_swiglu_fwd(x, w13, *, a2=None, b2=None):
+    """x [M,K], w13 = [w1; w3] [2I,K] -> (gate_up bf16 [M,2I], act bf16 [M,I]) ; optional LoRA tail a2 [M,r], b2 [2I,r]."""
+    M, K = x.shape
+    inter = w13.shape[0] // 2
+    gu = torch.empty(M, 2 * inter, dtype=BF16, device=x.device)
+    act = torch.empty(M, inter, dtype=BF16, device=x.device)
+    K2 = a2.shape[1] if a2 is not None else 0
+    lib = _lib.load()
+    if _gemm_prof is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+    _lib.check(lib.csm_gemm_swiglu_fwd(_p(x), _p(w13), _p(gu), _p(act), M, inter, K, x.stride(0), w13.stride(0),
+                                       gu.stride(0), act.stride(0), _p(a2), _p(b2), K2,
+                                       a2.stride(0) if a2 is not None else 0, b2.stride(0) if b2 is not None else 0,
+                                       _st()), "gemm_swiglu_fwd")
+    if _gemm_prof is not None:
+        e1.record()
+        _gemm_prof.append((2.0 * M * 2 * inter * (K + K2), e0, e1))
+    return gu, act
+
+
+def gemm_swiglu_bwd(dy, w2, gu, *, a2=None, b2=None):
+    """dy [M,K], w2 [K,I] (nn.Linear weight of the down projection), gu [M,2I] -> dgate_up bf16 [M,2I]."""
+    M, K = dy.shape
+    inter = w2.shape[1]
+    dgu = torch.empty(M, 2 * inter, dtype=BF16, device=dy.device)
+    K2 = a2.shape[1] if a2 is not None else 0
+    lib = _lib.load()
+    if _gemm_prof is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+    _lib.check(lib.csm_gemm_swiglu_bwd(_p(dy), _p(w2), _p(gu), _p(dgu), M, inter, K, dy.stride(0), w2.stride(0),
+                                       gu.stride(0), dgu.stride(0), _p(a2), _p(b2), K2,
+                                       a2.stride(0) if a2 is not None else 0, b2.stride(0) if b2 is not None else 0,
+                                       _st()), "gemm_swiglu_bwd")
+    if _gemm_prof is not None:
+        e1.record()
+        _gemm_prof.append((2.0 * M * inter * (K + K2), e0, e1))
+    return dgu
+
+
 # ----------------------------------------------------------------------------- attention
 def attention_fwd(q, k, v, batch: int, seq: int, heads: int, kv_heads: int, head_dim: int):
     """q [B*S, H*hd], k/v [B*S, KV*hd] (row strides free) -> (o [B*S, H*hd], lse fp32 [B,H,S])."""

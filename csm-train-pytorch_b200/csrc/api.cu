@@ -128,6 +128,52 @@ extern "C" int csm_gemm_bf16(const void* A, const void* B, void* C, const void* 
                        K2, lda2, ldb2, backend, as_stream(stream));
 }
 
+namespace csm {
+bool gemm_tc_swiglu_supported(int64_t M, int64_t inter, int64_t K);
+int gemm_tc_swiglu_fwd(const void*, const void*, void*, void*, int64_t, int64_t, int64_t, int64_t, int64_t, int64_t,
+                       int64_t, const void*, const void*, int64_t, int64_t, int64_t, cudaStream_t);
+int gemm_tc_swiglu_bwd(const void*, const void*, const void*, void*, int64_t, int64_t, int64_t, int64_t, int64_t,
+                       int64_t, int64_t, const void*, const void*, int64_t, int64_t, int64_t, cudaStream_t);
+}  // namespace csm
+
+static bool swiglu_args_ok(const void* a, const void* b, const void* c, const void* d, int64_t l0, int64_t l1,
+                           int64_t l2, int64_t l3, const void* a2, const void* b2, int64_t K2, int64_t lda2,
+                           int64_t ldb2) {
+  if (!aligned16(a) || !aligned16(b) || !aligned16(c) || !aligned16(d)) return false;
+  if ((l0 | l1 | l2 | l3) & 7) return false;
+  if (a2 && (!b2 || !aligned16(a2) || !aligned16(b2) || K2 < 1 || K2 > 64 || (lda2 & 7) || (ldb2 & 7))) return false;
+  return true;
+}
+
+extern "C" int csm_gemm_swiglu_supported(int64_t M, int64_t inter, int64_t K) {
+  return (csm_device_supported() == 1 && gemm_tc_swiglu_supported(M, inter, K)) ? 1 : 0;
+}
+
+extern "C" int csm_gemm_swiglu_fwd(const void* x, const void* w13, void* gate_up, void* act, int64_t M, int64_t inter,
+                                   int64_t K, int64_t ldx, int64_t ldw, int64_t ldgu, int64_t ldact, const void* A2,
+                                   const void* B2, int64_t K2, int64_t lda2, int64_t ldb2, csm_stream_t stream) {
+  CSM_REQUIRE(gemm_tc_swiglu_supported(M, inter, K), CSM_ERR_SHAPE,
+              "gemm_swiglu_fwd: shape M=%lld I=%lld K=%lld is below the CTA-pair tile grid; use gemm + swiglu",
+              (long long)M, (long long)inter, (long long)K);
+  CSM_REQUIRE(swiglu_args_ok(x, w13, gate_up, act, ldx, ldw, ldgu, ldact, A2, B2, K2, lda2, ldb2), CSM_ERR_ALIGN,
+              "gemm_swiglu_fwd: operands must be 16-byte aligned with strides that are multiples of 8");
+  return gemm_tc_swiglu_fwd(x, w13, gate_up, act, M, inter, K, ldx, ldw, ldgu, ldact, A2, A2 ? B2 : nullptr, A2 ? K2 : 0,
+                            lda2, ldb2, as_stream(stream));
+}
+
+extern "C" int csm_gemm_swiglu_bwd(const void* dy, const void* w2, const void* gate_up, void* dgate_up, int64_t M,
+                                   int64_t inter, int64_t K, int64_t lddy, int64_t ldw, int64_t ldgu, int64_t lddgu,
+                                   const void* A2, const void* B2, int64_t K2, int64_t lda2, int64_t ldb2,
+                                   csm_stream_t stream) {
+  CSM_REQUIRE(gemm_tc_swiglu_supported(M, inter, K), CSM_ERR_SHAPE,
+              "gemm_swiglu_bwd: shape M=%lld I=%lld K=%lld is below the CTA-pair tile grid; use gemm + swiglu_bwd",
+              (long long)M, (long long)inter, (long long)K);
+  CSM_REQUIRE(swiglu_args_ok(dy, w2, gate_up, dgate_up, lddy, ldw, ldgu, lddgu, A2, B2, K2, lda2, ldb2), CSM_ERR_ALIGN,
+              "gemm_swiglu_bwd: operands must be 16-byte aligned with strides that are multiples of 8");
+  return gemm_tc_swiglu_bwd(dy, w2, gate_up, dgate_up, M, inter, K, lddy, ldw, ldgu, lddgu, A2, A2 ? B2 : nullptr,
+                            A2 ? K2 : 0, lda2, ldb2, as_stream(stream));
+}
+
 extern "C" int csm_attn_causal_gqa_fwd(const void* q, const void* k, const void* v, void* o, float* lse,
                                        int32_t batch, int32_t seq, int32_t heads, int32_t kv_heads,
                                        int32_t head_dim, int64_t ldq, int64_t ldk, int64_t ldv, int64_t ldo,

@@ -13,9 +13,17 @@ namespace csm {
 using namespace tc;
 
 constexpr int BM = 128, BK = 64;
-constexpr int kGemmThreads = 192;
+constexpr int kGemmThreads = 320;   // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
+// Two epilogue warps per TMEM lane quadrant split the tile's columns (the fused SwiGLU epilogues must finish inside
+// one main loop, ~9 us at K = 2048); the CE epilogues keep whole rows thread-local, so only warps 2..5 work there.
+__host__ __device__ constexpr int epi_warps(int epi) { return (epi == 1 || epi == 2) ? 4 : 8; }
 
-enum { EPI_STORE = 0, EPI_CE_PARTIAL = 1, EPI_CE_DLOGITS = 2 };
+// EPI_SWIGLU_FWD (CTA-pair mode only): the B tile of a pair is [128 gate rows | 128 up rows] of the packed w1|w3
+//   weight (CTA 0 loads the gate rows, CTA 1 the up rows), so one accumulator row holds gate and up of the same 128
+//   columns: the epilogue writes gate, up (saved for backward) and act = silu(gate) * up — the swiglu kernel and its
+//   re-read of the [M, 2I] buffer disappear.
+// EPI_SWIGLU_BWD: the w2 dgrad GEMM's epilogue reads gate/up and writes dgate/dup directly (dact never exists).
+enum { EPI_STORE = 0, EPI_CE_PARTIAL = 1, EPI_CE_DLOGITS = 2, EPI_SWIGLU_FWD = 3, EPI_SWIGLU_BWD = 4 };
 
 struct GemmTcParams {
   int64_t M, N, K;          // per-group problem
@@ -28,6 +36,9 @@ struct GemmTcParams {
   int64_t ldc, ldr, c_group_stride, r_group_stride;
   int c_f32, accumulate;
   float alpha;
+  // SwiGLU epilogues: C = gate|up buffer [M, 2*inter] (fwd: written, bwd: R = gate|up read, C = dgate|dup written),
+  // C2 = act [M, inter] (fwd)
+  void* C2; int64_t ldc2; int64_t inter;
   // CE epilogues
   const int64_t* targets; int64_t tgt_row_stride, tgt_group_stride;
   float4* ce_part;          // [groups*M, num_n]
@@ -41,9 +52,44 @@ template <int BN, bool kCta2> struct GemmCfg {
   static constexpr int kBRows = kCta2 ? BN / 2 : BN;            // B-tile rows held by this CTA
   static constexpr int kStages = (BN == 256 && !kCta2) ? 4 : 6;
   static constexpr int kStageBytes = BM * BK * 2 + kBRows * BK * 2;
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int kStoreStageBytes = 8 * 2048;           // one 32 x 64 B staging tile per epilogue warp
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/ + kStoreStageBytes;
   static constexpr int kTmemCols = 2 * BN;
 };
+
+// sigmoid(x) = 0.5 * tanh(0.5 x) + 0.5: one MUFU instead of exp + full-precision divide (abs error ~1e-6 x 2^-11,
+// far below the bf16 rounding applied to every value it feeds)
+__device__ __forceinline__ float fast_sigmoid(float x) {
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * x));
+  return fmaf(t, 0.5f, 0.5f);
+}
+
+// Writes a 32-row x 32-column bf16 tile that the warp holds one ROW PER LANE (the TMEM layout) to global memory.
+// Stored straight from registers every lane would write 16 B into a different row: 32 half-filled 32-byte sectors per
+// instruction (ncu: l1tex->xbar write bytes = 2x the tile).  Staged through a 2 KB per-warp smem tile (XOR-swizzled
+// 16-byte chunks, conflict-free both ways) each instruction writes eight complete 64-byte row segments instead.
+__device__ __forceinline__ void store_tile_32x32(uint32_t stage_saddr, bf16* tile_origin, int64_t ld, int lane,
+                                                 const uint32_t* packed /*16 words = this lane's row*/, int rows_valid) {
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const uint32_t a = stage_saddr + lane * 64 + ((q ^ ((lane >> 1) & 3)) << 4);
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(packed[q * 4 + 0]), "r"(packed[q * 4 + 1]),
+                 "r"(packed[q * 4 + 2]), "r"(packed[q * 4 + 3])
+                 : "memory");
+  }
+  __syncwarp();
+  const int chunk = lane & 3;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int row = i * 8 + (lane >> 2);
+    const uint32_t a = stage_saddr + row * 64 + ((chunk ^ ((row >> 1) & 3)) << 4);
+    uint4 v;
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a) : "memory");
+    if (row < rows_valid) *reinterpret_cast<uint4*>(tile_origin + (int64_t)row * ld + chunk * 8) = v;
+  }
+  __syncwarp();
+}
 
 __device__ __forceinline__ void tile_coords(int t, int num_m, int num_n, int& g, int& mb, int& nb) {
   const int per_group = num_m * num_n;
@@ -90,7 +136,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (p.has_tail) { tma_prefetch_desc(&tmA2); tma_prefetch_desc(&tmB2); }
     for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
     // pair mode: the leader's MMA warp waits for the epilogue warps of BOTH CTAs
-    for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], kCta2 ? 8 : 4); }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tfull[a], 1);
+      mbar_init(&tempty[a], epi_warps(kEpi) * (kCta2 ? 2 : 1));
+    }
     mbar_fence_init();
   }
   if (warp == 1) {
@@ -110,7 +159,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       tile_coords(t, tile_m, p.num_n, g, mb, nb);
       if (kCta2) mb = 2 * mb + (int)rank;
       const int m0 = mb * BM;
-      const int n0 = nb * BN + (kCta2 ? (int)rank * Cfg::kBRows : 0);          // pair mode: this CTA's half of B
+      // pair mode: this CTA's half of the B tile (SwiGLU forward: rank 0 = gate rows, rank 1 = up rows)
+      const int n0 = kEpi == EPI_SWIGLU_FWD ? (int)rank * (int)p.inter + nb * Cfg::kBRows
+                                            : nb * BN + (kCta2 ? (int)rank * Cfg::kBRows : 0);
       for (int kb = 0; kb < kb_total; ++kb) {
         mbar_wait(&empty[stage], phase ^ 1);
         if (elect_one()) {
@@ -200,8 +251,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   } else {
     // ===================== epilogue (4 warps, TMEM lane quadrant = warp % 4) =====================
     const int quad = warp & 3;
+    const int ehalf = (warp - 2) >> 2;                        // which half of the tile's columns this warp drains
+    constexpr int kColsPerWarp = BN / (epi_warps(kEpi) / 4);
+    const int c_lo = ehalf * kColsPerWarp, c_hi = c_lo + kColsPerWarp;
     int acc = 0; uint32_t acc_phase = 0;
-    for (int t = first_tile; t < num_tiles; t += tile_step) {
+    for (int t = first_tile; t < num_tiles && ehalf < epi_warps(kEpi) / 4; t += tile_step) {
       int g, mb, nb;
       tile_coords(t, tile_m, p.num_n, g, mb, nb);
       if (kCta2) mb = 2 * mb + (int)rank;
@@ -211,18 +265,49 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       tc_fence_after();
       const uint32_t t_addr = tmem_base + (uint32_t)(acc * BN) + ((uint32_t)(quad * 32) << 16);
       const bool row_ok = m < p.M;
+      // coalesced tile stores (store_tile_32x32): the warp's first row and how many of its 32 rows exist
+      const int64_t wm0 = (int64_t)mb * BM + quad * 32;
+      const int wrows = (int)max((int64_t)0, min((int64_t)32, p.M - wm0));
+      const uint32_t stage_s = smem_u32(smem + kStages * Cfg::kStageBytes + 256) + (uint32_t)(warp - 2) * 2048u;
 
       if (kEpi == EPI_STORE) {
         const int64_t crow = (int64_t)g * p.c_group_stride + m * p.ldc;
         const bf16* rrow = p.R ? p.R + (int64_t)g * p.r_group_stride + m * p.ldr : nullptr;
 #pragma unroll 1
-        for (int c = 0; c < BN; c += 32) {
+        for (int c = c_lo; c < c_hi; c += 32) {
           uint32_t v[32];
           __syncwarp();
           tmem_ld32(t_addr + c, v);
           tmem_ld_wait();
           const int64_t n = n0 + c;
-          if (!row_ok || n >= p.N) continue;
+          if (n >= p.N) continue;
+          if (!p.c_f32 && n + 32 <= p.N && (p.ldc & 7) == 0 && (!rrow || (p.ldr & 7) == 0)) {
+            // warp-uniform fast path: full 32-column bf16 chunk, written as whole 64-byte row segments
+            uint32_t w[16];
+            bf16* cp = reinterpret_cast<bf16*>(p.C) + crow + n;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              float f8[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) f8[i] = __uint_as_float(v[q * 8 + i]) * p.alpha;
+              if (rrow && row_ok) {
+                const uint4 r4 = *reinterpret_cast<const uint4*>(rrow + n + q * 8);
+                f8[0] += bf16_lo(r4.x); f8[1] += bf16_hi(r4.x); f8[2] += bf16_lo(r4.y); f8[3] += bf16_hi(r4.y);
+                f8[4] += bf16_lo(r4.z); f8[5] += bf16_hi(r4.z); f8[6] += bf16_lo(r4.w); f8[7] += bf16_hi(r4.w);
+              }
+              if (p.accumulate && row_ok) {
+                const uint4 old = *reinterpret_cast<const uint4*>(cp + q * 8);
+                f8[0] += bf16_lo(old.x); f8[1] += bf16_hi(old.x); f8[2] += bf16_lo(old.y); f8[3] += bf16_hi(old.y);
+                f8[4] += bf16_lo(old.z); f8[5] += bf16_hi(old.z); f8[6] += bf16_lo(old.w); f8[7] += bf16_hi(old.w);
+              }
+              w[q * 4 + 0] = pack_bf16(f8[0], f8[1]); w[q * 4 + 1] = pack_bf16(f8[2], f8[3]);
+              w[q * 4 + 2] = pack_bf16(f8[4], f8[5]); w[q * 4 + 3] = pack_bf16(f8[6], f8[7]);
+            }
+            store_tile_32x32(stage_s, reinterpret_cast<bf16*>(p.C) + (int64_t)g * p.c_group_stride + wm0 * p.ldc + n,
+                             p.ldc, lane, w, wrows);
+            continue;
+          }
+          if (!row_ok) continue;
           float f[32];
 #pragma unroll
           for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]) * p.alpha;
@@ -287,6 +372,83 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 }
             }
           }
+        }
+      } else if (kEpi == EPI_SWIGLU_FWD) {
+        bf16* gu0 = reinterpret_cast<bf16*>(p.C) + wm0 * p.ldc;      // the warp's first row
+        bf16* act0 = reinterpret_cast<bf16*>(p.C2) + wm0 * p.ldc2;
+        const int64_t c0 = (int64_t)nb * (BN / 2);
+#pragma unroll 1
+        for (int c = c_lo / 2; c < c_hi / 2; c += 32) {
+          uint32_t vg[32], vu[32];
+          __syncwarp();
+          tmem_ld32(t_addr + c, vg);
+          tmem_ld32(t_addr + BN / 2 + c, vu);
+          tmem_ld_wait();
+          const int64_t n = c0 + c;
+          if (n >= p.inter) continue;                  // inter is a multiple of 128: chunks are all-or-nothing
+          uint32_t pg[16], pu[16], pa[16];
+#pragma unroll
+          for (int e = 0; e < 16; ++e) {
+            // the linear outputs are rounded to bf16 first (what the unfused path stores and re-reads)
+            pg[e] = pack_bf16(__uint_as_float(vg[2 * e]), __uint_as_float(vg[2 * e + 1]));
+            pu[e] = pack_bf16(__uint_as_float(vu[2 * e]), __uint_as_float(vu[2 * e + 1]));
+            const float g0 = bf16_lo(pg[e]), g1 = bf16_hi(pg[e]);
+            const uint32_t ps = pack_bf16(g0 * fast_sigmoid(g0), g1 * fast_sigmoid(g1));   // bf16(silu(gate))
+            pa[e] = pack_bf16(bf16_lo(ps) * bf16_lo(pu[e]), bf16_hi(ps) * bf16_hi(pu[e]));
+          }
+          store_tile_32x32(stage_s, gu0 + n, p.ldc, lane, pg, wrows);
+          store_tile_32x32(stage_s, gu0 + p.inter + n, p.ldc, lane, pu, wrows);
+          store_tile_32x32(stage_s, act0 + n, p.ldc2, lane, pa, wrows);
+        }
+      } else if (kEpi == EPI_SWIGLU_BWD) {
+        const bf16* gurow = p.R + m * p.ldr;
+        bf16* d0 = reinterpret_cast<bf16*>(p.C) + wm0 * p.ldc;        // the warp's first row
+        // gate/up of the NEXT 32-column chunk are fetched while this one is computed (the loads would otherwise sit
+        // exposed between a TMEM read and the stores, eight times per tile)
+        uint4 g4[4], u4[4];
+        auto fetch = [&](int c) {
+          const int64_t n = n0 + c;
+          const bool ok = row_ok && n < p.N && c < c_hi;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            g4[q] = ok ? ld_nc16(gurow + n + q * 8) : make_uint4(0, 0, 0, 0);
+            u4[q] = ok ? ld_nc16(gurow + p.inter + n + q * 8) : make_uint4(0, 0, 0, 0);
+          }
+        };
+        fetch(c_lo);
+#pragma unroll 1
+        for (int c = c_lo; c < c_hi; c += 32) {
+          uint32_t v[32];
+          __syncwarp();
+          tmem_ld32(t_addr + c, v);
+          tmem_ld_wait();
+          const int64_t n = n0 + c;
+          uint4 gq[4], uq[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) { gq[q] = g4[q]; uq[q] = u4[q]; }
+          fetch(c + 32);
+          if (n >= p.N) continue;                      // inter is a multiple of 128: chunks are all-or-nothing
+          uint32_t wdg[16], wdu[16];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const uint32_t gp[4] = {gq[q].x, gq[q].y, gq[q].z, gq[q].w}, up_[4] = {uq[q].x, uq[q].y, uq[q].z, uq[q].w};
+            uint32_t* dg = wdg + q * 4;
+            uint32_t* du = wdu + q * 4;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              // dact rounded to bf16 first (what the unfused path stores and re-reads)
+              const uint32_t dp = pack_bf16(__uint_as_float(v[q * 8 + 2 * e]) * p.alpha,
+                                            __uint_as_float(v[q * 8 + 2 * e + 1]) * p.alpha);
+              const float d0 = bf16_lo(dp), d1 = bf16_hi(dp);
+              const float g0 = bf16_lo(gp[e]), g1 = bf16_hi(gp[e]);
+              const float s0 = fast_sigmoid(g0), s1 = fast_sigmoid(g1);
+              du[e] = pack_bf16(d0 * g0 * s0, d1 * g1 * s1);
+              dg[e] = pack_bf16(d0 * bf16_lo(up_[e]) * s0 * fmaf(g0, 1.f - s0, 1.f),
+                                d1 * bf16_hi(up_[e]) * s1 * fmaf(g1, 1.f - s1, 1.f));
+            }
+          }
+          store_tile_32x32(stage_s, d0 + n, p.ldc, lane, wdg, wrows);
+          store_tile_32x32(stage_s, d0 + p.inter + n, p.ldc, lane, wdu, wrows);
         }
       } else if (kEpi == EPI_CE_PARTIAL) {
         // online softmax over this tile's columns; the row is thread-local (lane == TMEM lane == row)
@@ -493,10 +655,13 @@ int gemm_tc_run(const GemmTcOperands& o, GemmTcParams p, int epi, cudaStream_t s
   // CTA-pair mode (256 x 256 super-tiles) for the plain GEMMs that can keep at least ~2/3 of the 74 pairs busy;
   // the test hook (mode 1) turns it on for every shape with two m-blocks and more than one 128-column tile
   const int64_t super256 = (int64_t)p.groups * ((p.num_m + 1) / 2) * ((p.N + 255) / 256);
-  const bool cta2 = epi == EPI_STORE && p.num_m >= 2 && p.N > 128 && mode != 0 && (mode == 1 || super256 >= 48);
-  const int bn = cta2 ? 256 : choose_bn(p.groups, p.M, p.N);
+  bool cta2 = (epi == EPI_STORE || epi == EPI_SWIGLU_BWD) && p.num_m >= 2 && p.N > 128 && mode != 0 &&
+              (mode == 1 || super256 >= 48);
+  if (epi == EPI_SWIGLU_FWD) cta2 = true;                 // callers check gemm_tc_swiglu_supported()
+  const int bn = (cta2 || epi == EPI_SWIGLU_BWD) ? 256 : choose_bn(p.groups, p.M, p.N);
   const uint32_t b_box = cta2 ? (uint32_t)bn / 2 : (uint32_t)bn;
-  p.num_n = (int)((p.N + bn - 1) / bn);
+  p.num_n = epi == EPI_SWIGLU_FWD ? (int)((p.N + 127) / 128) : (int)((p.N + bn - 1) / bn);
+  const uint64_t b_rows = epi == EPI_SWIGLU_FWD ? 2 * (uint64_t)p.N : (uint64_t)p.N;   // packed gate|up weight
   p.k_blocks = (int)((p.K + BK - 1) / BK);
   p.has_tail = (o.A2 && o.K2 > 0) ? 1 : 0;
   CUtensorMap ta, tb, ta2, tb2;
@@ -509,19 +674,24 @@ int gemm_tc_run(const GemmTcOperands& o, GemmTcParams p, int epi, cudaStream_t s
                 : encode_tmap_bf16(&ta, o.A, p.K, p.M, G, o.lda, ags, BM);
   if (rc) return rc;
   rc = o.transB ? encode_tmap_bf16(&tb, o.B, p.N, p.K, G, o.ldb, bgs, 64)
-                : encode_tmap_bf16(&tb, o.B, p.K, p.N, G, o.ldb, bgs, b_box);
+                : encode_tmap_bf16(&tb, o.B, p.K, b_rows, G, o.ldb, bgs, b_box);
   if (rc) return rc;
   if (p.has_tail) {
     rc = o.transA ? encode_tmap_bf16(&ta2, o.A2, p.M, o.K2, 1, o.lda2, 8, 64)
                   : encode_tmap_bf16(&ta2, o.A2, o.K2, p.M, 1, o.lda2, 8, BM);
     if (rc) return rc;
     rc = o.transB ? encode_tmap_bf16(&tb2, o.B2, p.N, o.K2, 1, o.ldb2, 8, 64)
-                  : encode_tmap_bf16(&tb2, o.B2, o.K2, p.N, 1, o.ldb2, 8, b_box);
+                  : encode_tmap_bf16(&tb2, o.B2, o.K2, b_rows, 1, o.ldb2, 8, b_box);
     if (rc) return rc;
   } else {
     ta2 = ta; tb2 = tb;
   }
 #define DISPATCH(BN_, EPI_) return launch_major<BN_, EPI_, false>(o, ta, tb, ta2, tb2, p, st)
+  if (epi == EPI_SWIGLU_FWD) return launch_inst<false, false, 256, EPI_SWIGLU_FWD, true>(ta, tb, ta2, tb2, p, st);
+  if (epi == EPI_SWIGLU_BWD) {
+    if (cta2) return launch_inst<false, true, 256, EPI_SWIGLU_BWD, true>(ta, tb, ta2, tb2, p, st);
+    return launch_inst<false, true, 256, EPI_SWIGLU_BWD, false>(ta, tb, ta2, tb2, p, st);
+  }
   if (cta2) return launch_major<256, EPI_STORE, true>(o, ta, tb, ta2, tb2, p, st);
   if (epi == EPI_STORE) { if (bn == 256) DISPATCH(256, EPI_STORE); else DISPATCH(128, EPI_STORE); }
   if (epi == EPI_CE_PARTIAL) { if (bn == 256) DISPATCH(256, EPI_CE_PARTIAL); else DISPATCH(128, EPI_CE_PARTIAL); }
@@ -555,6 +725,36 @@ int gemm_tc_launch(const void* A, const void* B, void* C, const void* R, int64_t
   p.C = C; p.R = (const bf16*)R; p.ldc = ldc; p.ldr = ldr;
   p.c_f32 = (c_dtype == CSM_DT_F32); p.accumulate = accumulate; p.alpha = alpha;
   return gemm_tc_run(o, p, EPI_STORE, stream);
+}
+
+// ------------------------------------------------------------------------------------------- fused SwiGLU MLP
+// forward : gate|up = x W13^T (+ LoRA tail) and act = silu(gate) * up in one launch (CTA-pair tiles of 128 act columns)
+// backward: dgate|dup from dact = dy W2 (+ LoRA tail) in the dgrad GEMM's epilogue
+bool gemm_tc_swiglu_supported(int64_t M, int64_t inter, int64_t K) {
+  if (g_cta2_mode.load() == 0) return false;
+  if (M < 2 * BM || inter < 256 || inter % 128 != 0 || K < 64 || K % 8 != 0) return false;
+  return ((M + 2 * BM - 1) / (2 * BM)) * (inter / 128) >= 48;       // enough super-tiles for the 74 CTA pairs
+}
+
+int gemm_tc_swiglu_fwd(const void* X, const void* W13, void* GU, void* ACT, int64_t M, int64_t inter, int64_t K,
+                       int64_t ldx, int64_t ldw, int64_t ldgu, int64_t ldact, const void* A2, const void* B2, int64_t K2,
+                       int64_t lda2, int64_t ldb2, cudaStream_t st) {
+  GemmTcOperands o{X, W13, A2, B2, ldx, ldw, lda2, ldb2, K2, 0, 0, 0, 0};
+  GemmTcParams p{};
+  p.M = M; p.N = inter; p.K = K; p.groups = 1;
+  p.C = GU; p.ldc = ldgu; p.C2 = ACT; p.ldc2 = ldact; p.inter = inter; p.alpha = 1.f;
+  return gemm_tc_run(o, p, EPI_SWIGLU_FWD, st);
+}
+
+int gemm_tc_swiglu_bwd(const void* DY, const void* W2, const void* GU, void* DGU, int64_t M, int64_t inter, int64_t K,
+                       int64_t lddy, int64_t ldw, int64_t ldgu, int64_t lddgu, const void* A2, const void* B2,
+                       int64_t K2, int64_t lda2, int64_t ldb2, cudaStream_t st) {
+  // dact[M, inter] = dy[M, K] @ W2[K, inter]  (W2 is nn.Linear [out=K, in=inter]: the MN-major B operand)
+  GemmTcOperands o{DY, W2, A2, B2, lddy, ldw, lda2, ldb2, K2, 0, 0, 0, 1};
+  GemmTcParams p{};
+  p.M = M; p.N = inter; p.K = K; p.groups = 1;
+  p.C = DGU; p.ldc = lddgu; p.R = (const bf16*)GU; p.ldr = ldgu; p.inter = inter; p.alpha = 1.f;
+  return gemm_tc_run(o, p, EPI_SWIGLU_BWD, st);
 }
 
 // ------------------------------------------------------------------------------------------- fused CE

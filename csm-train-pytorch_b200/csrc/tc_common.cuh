@@ -128,8 +128,12 @@ __device__ __forceinline__ uint32_t mapa(uint32_t local_smem_addr, uint32_t rank
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_smem_addr), "r"(rank));
   return r;
 }
+// Relaxed on purpose: a .release.cluster arrive compiles to MEMBAR.ALL.GPU + ERRBAR, i.e. the epilogue warp would
+// wait for every global store of its tile to be acknowledged before handing the TMEM buffer back (measured: the
+// fused SwiGLU GEMMs dropped to 43-65 % tensor-pipe activity).  The hand-off only has to order the warp's TMEM reads,
+// which have completed (tcgen05.wait::ld) and are fenced by tcgen05.fence::before_thread_sync before this arrive.
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 // TMA load whose complete_tx lands on an mbarrier that may live in the peer CTA (shared::cluster address)
 __device__ __forceinline__ void tma_load_3d_2sm(void* smem_dst, const CUtensorMap* map, uint32_t bar_cluster_addr, int c0,

@@ -110,6 +110,19 @@ int csm_swiglu_bwd(const void* dout, const void* gate, const void* up, void* dga
                    int64_t cols, int64_t ldo, int64_t ldg, int64_t ldu, int64_t lddg, int64_t lddu,
                    csm_stream_t stream);
 
+/* ---- torchtune FeedForward w2(silu(w1 x) * w3 x) (llama3_2 builder, reference model.py:11-42) with the SwiGLU
+ * fused into the GEMM epilogues.  w13 = [w1; w3] packed [2*inter, K] row-major (gate rows first).
+ *   fwd: gate_up[M, 2*inter] = x w13^T (+ A2 B2^T LoRA tail), act[M, inter] = bf16(silu(gate)) * up — one launch.
+ *   bwd: dgate_up[M, 2*inter] from dact = dy w2 (+ A2 B2 tail; w2 is [K, inter] row-major), dact never materialised.
+ * csm_gemm_swiglu_supported() == 0 (small shapes): call csm_gemm_bf16 + csm_swiglu_{fwd,bwd} instead. */
+int csm_gemm_swiglu_supported(int64_t M, int64_t inter, int64_t K);
+int csm_gemm_swiglu_fwd(const void* x, const void* w13, void* gate_up, void* act, int64_t M, int64_t inter, int64_t K,
+                        int64_t ldx, int64_t ldw, int64_t ldgu, int64_t ldact, const void* A2, const void* B2,
+                        int64_t K2, int64_t lda2, int64_t ldb2, csm_stream_t stream);
+int csm_gemm_swiglu_bwd(const void* dy, const void* w2, const void* gate_up, void* dgate_up, int64_t M, int64_t inter,
+                        int64_t K, int64_t lddy, int64_t ldw, int64_t ldgu, int64_t lddgu, const void* A2,
+                        const void* B2, int64_t K2, int64_t lda2, int64_t ldb2, csm_stream_t stream);
+
 /* ---- torchtune MultiHeadAttention core = F.scaled_dot_product_attention(is_causal=True) with GQA
  * q [batch*seq, heads*hd] (ldq), k/v [batch*seq, kv_heads*hd], o like q; kv head j serves q heads
  * j*(heads/kv_heads) .. (j+1)*(heads/kv_heads)-1.  lse fp32 [batch, heads, seq] saved for backward. */

@@ -202,6 +202,29 @@ def test_gemm_cta_pair_mode(ops, cuda, ta, tb, M, N, K):
         ops.set_gemm_cta_pair_mode(-1)
 
 
+@pytest.mark.parametrize("M,I,K,r", [(4096, 1024, 512, 0), (2048, 2048, 256, 16), (1000, 8192, 1024, 8)])
+def test_gemm_swiglu_fused_matches_unfused(ops, cuda, M, I, K, r):
+    """w1|w3 GEMM + SwiGLU in one launch (and w2 dgrad + SwiGLU backward in one) equal the unfused kernel pairs."""
+    assert ops.swiglu_fusable(M, I, K)
+    g = torch.Generator().manual_seed(M + I)
+    mk = lambda a, b, sc=1.0: (torch.randn(a, b, generator=g) * sc).to(BF).to(cuda)
+    x, w13, w2, dy = mk(M, K), mk(2 * I, K, K ** -0.5), mk(K, I, I ** -0.5), mk(M, K)
+    t = bb = dts = A = None
+    if r:
+        t, bb, dts, A = mk(M, r, 0.1), mk(2 * I, r, 0.1), mk(M, r, 0.1), mk(r, I, 0.1)
+    gu, act = ops.gemm_swiglu_fwd(x, w13, a2=t, b2=bb)
+    gu_ref = ops.gemm(x, w13, a2=t, b2=bb)
+    act_ref = ops.swiglu(gu_ref[:, :I], gu_ref[:, I:])
+    assert rel_err(gu, gu_ref) < 1e-3 and rel_err(act, act_ref) < 2e-3
+    dgu = ops.gemm_swiglu_bwd(dy, w2, gu_ref, a2=dts, b2=A)
+    dact = ops.gemm(dy, w2, trans_b=True, a2=dts, b2=A)
+    dg, du = ops.swiglu_bwd(dact, gu_ref[:, :I], gu_ref[:, I:])
+    assert rel_err(dgu[:, :I], dg) < 2e-3 and rel_err(dgu[:, I:], du) < 2e-3
+    # against fp32 torch
+    g32, u32 = gu_ref[:, :I].float(), gu_ref[:, I:].float()
+    assert rel_err(act, F.silu(g32) * u32) < 1e-2
+
+
 @pytest.mark.parametrize("backend", [1, 2])
 def test_gemm_epilogues_and_lora_tail(ops, cuda, backend):
     g = torch.Generator().manual_seed(5)

@@ -65,6 +65,28 @@ def bench_gemm():
     return rows
 
 
+def bench_swiglu():
+    rows = []
+    M, I, K = 4096, 8192, 2048
+    x = torch.randn(M, K, device=dev).to(BF)
+    w13 = (torch.randn(2 * I, K, device=dev) * K ** -0.5).to(BF)
+    w2 = (torch.randn(K, I, device=dev) * I ** -0.5).to(BF)
+    dy = torch.randn(M, K, device=dev).to(BF)
+    gu = ops.gemm(x, w13)
+    f_fused = timeit(lambda: ops.gemm_swiglu_fwd(x, w13))
+    f_gemm = timeit(lambda: ops.gemm(x, w13))
+    f_sw = timeit(lambda: ops.swiglu(gu[:, :I], gu[:, I:]))
+    b_fused = timeit(lambda: ops.gemm_swiglu_bwd(dy, w2, gu))
+    b_gemm = timeit(lambda: ops.gemm(dy, w2, trans_b=True))
+    dact = ops.gemm(dy, w2, trans_b=True)
+    b_sw = timeit(lambda: ops.swiglu_bwd(dact, gu[:, :I], gu[:, I:]))
+    print(f"swiglu fwd: fused {f_fused*1e3:.1f} us vs gemm {f_gemm*1e3:.1f} + swiglu {f_sw*1e3:.1f} us", flush=True)
+    print(f"swiglu bwd: fused {b_fused*1e3:.1f} us vs gemm {b_gemm*1e3:.1f} + swiglu_bwd {b_sw*1e3:.1f} us", flush=True)
+    rows.append({"fwd_fused_ms": f_fused, "fwd_gemm_ms": f_gemm, "fwd_swiglu_ms": f_sw, "bwd_fused_ms": b_fused,
+                 "bwd_gemm_ms": b_gemm, "bwd_swiglu_ms": b_sw})
+    return rows
+
+
 def bench_attn():
     import torch.nn.functional as F
     rows = []
@@ -133,6 +155,8 @@ if __name__ == "__main__":
     out = {}
     if what in ("gemm", "all"):
         out["gemm"] = bench_gemm()
+    if what in ("swiglu", "all"):
+        out["swiglu"] = bench_swiglu()
     if what in ("attn", "all"):
         out["attn"] = bench_attn()
     if what in ("embed", "all"):

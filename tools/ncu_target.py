@@ -37,6 +37,16 @@ elif what == "embed":       # K1 at the c2 size: 4096 audio frames
     msk[..., C] = False
     for _ in range(4):
         ops.embed_gather_sum(tok, msk, audio, text)
+elif what == "swiglu":      # fused w1|w3 GEMM + SwiGLU forward and w2 dgrad + SwiGLU backward of one backbone layer
+    M, I, K = 4096, 8192, 2048
+    x = torch.randn(M, K, device=dev).to(BF)
+    w13 = (torch.randn(2 * I, K, device=dev) * K ** -0.5).to(BF)
+    w2 = (torch.randn(K, I, device=dev) * I ** -0.5).to(BF)
+    dy = torch.randn(M, K, device=dev).to(BF)
+    for _ in range(2):
+        gu, act = ops.gemm_swiglu_fwd(x, w13)
+        ops.gemm_swiglu_bwd(dy, w2, gu)
+        ops.gemm(x, w13)
 elif what == "attn":
     B, S, H, KV, hd = 2, 2048, 32, 8, 64
     q = torch.randn(B * S, H * hd, device=dev).to(BF)
