@@ -242,8 +242,7 @@ class StackFn(Function):
             xn, rstd1 = ops.rmsnorm(cur, layer.sa_norm.scale, eps)
             qkv, tqkv = gqkv.fwd(xn)
             q, k, v = qkv[:, :nq], qkv[:, nq:nq + nkv], qkv[:, nq + nkv:]
-            ops.rope_(q, cache, S, H, hd)
-            ops.rope_(k, cache, S, KV, hd)
+            ops.rope_(qkv[:, :nq + nkv], cache, S, H + KV, hd)     # q and k heads are adjacent columns: one launch
             o, lse = ops.attention_fwd(q, k, v, B, S, H, KV, hd)
             h, to = lo.fwd(o, residual=cur)
             hn, rstd2 = ops.rmsnorm(h, layer.mlp_norm.scale, eps)
@@ -320,8 +319,7 @@ class StackFn(Function):
             dqkv = torch.empty_like(qkv)
             dq, dk, dv = dqkv[:, :nq], dqkv[:, nq:nq + nkv], dqkv[:, nq + nkv:]
             ops.attention_bwd(q, k, v, o, lse, do, B, S, H, KV, hd, dq=dq, dk=dk, dv=dv)
-            ops.rope_(dq, cache, S, H, hd, inverse=True)
-            ops.rope_(dk, cache, S, KV, hd, inverse=True)
+            ops.rope_(dqkv[:, :nq + nkv], cache, S, H + KV, hd, inverse=True)
             dxn = gqkv.bwd(dqkv, xn, tqkv, grads, need)
             dcur = norm_bwd(dxn, x, layer.sa_norm, rstd1, dh)
             hand_over(layer)

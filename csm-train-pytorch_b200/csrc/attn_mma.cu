@@ -237,21 +237,48 @@ attn_fwd_mma_kernel(const bf16* __restrict__ q, const bf16* __restrict__ k, cons
 }
 
 // ------------------------------------------------------------------------------------------- delta = rowsum(dO * O)
+// 8 lanes per (row, head): one 16-byte load of O and dO each per lane, 3 shuffles, consecutive lanes walk consecutive
+// heads of a row so a warp reads 512 contiguous bytes per tensor; 4 independent pairs of loads in flight per lane.
 __global__ void __launch_bounds__(256)
 attn_delta_kernel(const bf16* __restrict__ o, const bf16* __restrict__ dout, float* __restrict__ delta, int B, int S,
                   int H, int64_t ldo, int64_t lddo) {
-  const int lane = threadIdx.x & 31;
-  const int64_t w = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (w >= (int64_t)B * H * S) return;
-  const int i = (int)(w % S);
-  const int h = (int)((w / S) % H);
-  const int b = (int)(w / ((int64_t)S * H));
-  const int64_t row = (int64_t)b * S + i;
-  const uint32_t a = *reinterpret_cast<const uint32_t*>(o + row * ldo + h * HD + lane * 2);
-  const uint32_t d = *reinterpret_cast<const uint32_t*>(dout + row * lddo + h * HD + lane * 2);
-  float s = bf16_lo(a) * bf16_lo(d) + bf16_hi(a) * bf16_hi(d);
-  s = warp_sum(s);
-  if (lane == 0) delta[((int64_t)b * H + h) * S + i] = s;
+  static_assert(HD == 64, "8 lanes x 8 elements per head");
+  const int sub = threadIdx.x & 7;
+  const int64_t total = (int64_t)B * S * H;                       // (row, head) pairs, head fastest
+  const int64_t stride = (int64_t)gridDim.x * (blockDim.x >> 3);
+  int64_t w = (int64_t)blockIdx.x * (blockDim.x >> 3) + (threadIdx.x >> 3);
+  constexpr int U = 4;
+  for (; w < total; w += U * stride) {
+    uint4 a[U], d[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t wu = w + u * stride;
+      a[u] = d[u] = make_uint4(0, 0, 0, 0);
+      if (wu < total) {
+        const int64_t row = wu / H;
+        const int h = (int)(wu % H);
+        a[u] = ld_nc16(o + row * ldo + h * HD + sub * 8);
+        d[u] = ld_nc16(dout + row * lddo + h * HD + sub * 8);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      float s = bf16_lo(a[u].x) * bf16_lo(d[u].x) + bf16_hi(a[u].x) * bf16_hi(d[u].x) +
+                bf16_lo(a[u].y) * bf16_lo(d[u].y) + bf16_hi(a[u].y) * bf16_hi(d[u].y) +
+                bf16_lo(a[u].z) * bf16_lo(d[u].z) + bf16_hi(a[u].z) * bf16_hi(d[u].z) +
+                bf16_lo(a[u].w) * bf16_lo(d[u].w) + bf16_hi(a[u].w) * bf16_hi(d[u].w);
+      s += __shfl_xor_sync(0xffffffffu, s, 1);
+      s += __shfl_xor_sync(0xffffffffu, s, 2);
+      s += __shfl_xor_sync(0xffffffffu, s, 4);
+      const int64_t wu = w + u * stride;
+      if (sub == 0 && wu < total) {
+        const int64_t row = wu / H;
+        const int h = (int)(wu % H);
+        const int64_t b = row / S, i = row % S;
+        delta[(b * H + h) * S + i] = s;
+      }
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------- backward: dQ
@@ -440,11 +467,16 @@ attn_bwd_dkdv_mma_kernel(const bf16* __restrict__ q, const bf16* __restrict__ k,
 
 }  // namespace
 
+static unsigned delta_grid(int64_t pairs) {
+  const int64_t want = (pairs + 32 * 4 - 1) / (32 * 4);           // 32 pairs per CTA pass, 4 passes per thread
+  const int64_t cap = (int64_t)num_sms() * 8;
+  return (unsigned)(want < 1 ? 1 : (want < cap ? want : cap));
+}
+
 int attn_delta_launch(const void* o, const void* dout, float* delta, int B, int S, int H, int64_t ldo,
                       cudaStream_t st) {
   const int64_t rows = (int64_t)B * H * S;
-  attn_delta_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>((const bf16*)o, (const bf16*)dout, delta, B, S, H, ldo,
-                                                                ldo);
+  attn_delta_kernel<<<delta_grid(rows), 256, 0, st>>>((const bf16*)o, (const bf16*)dout, delta, B, S, H, ldo, ldo);
   CSM_CHECK_LAUNCH("attn_delta");
   return CSM_OK;
 }
@@ -473,8 +505,7 @@ int attn_bwd_mma_launch(const void* q, const void* k, const void* v, const void*
                   aligned16(dk) && aligned16(dv) && lddq % 8 == 0 && lddk % 8 == 0 && lddv % 8 == 0,
               CSM_ERR_ALIGN, "attn_bwd: misaligned");
   const int64_t rows = (int64_t)B * H * S;
-  attn_delta_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>((const bf16*)o, (const bf16*)dout, delta, B, S, H, ldo,
-                                                                ldo);
+  attn_delta_kernel<<<delta_grid(rows), 256, 0, st>>>((const bf16*)o, (const bf16*)dout, delta, B, S, H, ldo, ldo);
   CSM_CHECK_LAUNCH("attn_delta");
   dim3 gq((S + BR - 1) / BR, H, B);
   attn_bwd_dq_mma_kernel<<<gq, NTHR, 0, st>>>((const bf16*)q, (const bf16*)k, (const bf16*)v, (const bf16*)dout, lse,

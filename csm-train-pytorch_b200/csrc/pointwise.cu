@@ -128,6 +128,112 @@ rmsnorm_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, cons
   }
 }
 
+// ---- warp-per-row RMSNorm for D = 256 * VPL (CSM-1B: 2048 and 1024).  No block barriers, VPL independent 16-byte
+// loads per tensor in flight per lane (the CTA-per-row kernels above keep one and are latency-bound at ~2.5 TB/s).
+template <int VPL>
+__global__ void __launch_bounds__(256)
+rmsnorm_fwd_warp_kernel(const bf16* __restrict__ x, const bf16* __restrict__ scale, bf16* __restrict__ y,
+                        float* __restrict__ rstd, int64_t rows, float eps) {
+  constexpr int D = 256 * VPL;
+  const int lane = threadIdx.x & 31;
+  const int64_t nw = (int64_t)gridDim.x * (blockDim.x >> 5);
+  for (int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); r < rows; r += nw) {
+    const bf16* xr = x + r * D;
+    uint4 v[VPL];
+#pragma unroll
+    for (int c = 0; c < VPL; ++c) v[c] = ld_nc16(xr + (c * 32 + lane) * 8);
+    float ss = 0.f;
+#pragma unroll
+    for (int c = 0; c < VPL; ++c) {
+      float f[8];
+      unpack8(v[c], f);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) ss += f[i] * f[i];
+    }
+    ss = warp_sum(ss);
+    const float rs = rsqrtf(ss / (float)D + eps);
+    if (lane == 0 && rstd) rstd[r] = rs;
+#pragma unroll
+    for (int c = 0; c < VPL; ++c) {
+      float f[8], s[8];
+      unpack8(v[c], f);
+      unpack8(*reinterpret_cast<const uint4*>(scale + (c * 32 + lane) * 8), s);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) f[i] = round_bf16(f[i] * rs) * s[i];
+      *reinterpret_cast<uint4*>(y + r * D + (c * 32 + lane) * 8) = pack8(f);
+    }
+  }
+}
+
+template <int VPL>
+__global__ void __launch_bounds__(256)
+rmsnorm_bwd_warp_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, const bf16* __restrict__ scale,
+                        const float* __restrict__ rstd, const bf16* __restrict__ dres, bf16* __restrict__ dx,
+                        float* __restrict__ dscale, int64_t rows) {
+  constexpr int D = 256 * VPL;
+  __shared__ float sds[256 * VPL];          // dscale partials of the CTA's 8 warps (only touched when dscale != null)
+  const int lane = threadIdx.x & 31;
+  const int64_t nw = (int64_t)gridDim.x * (blockDim.x >> 5);
+  float ds[VPL][8];
+  if (dscale) {
+#pragma unroll
+    for (int c = 0; c < VPL; ++c)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) ds[c][i] = 0.f;
+    for (int i = threadIdx.x; i < D; i += blockDim.x) sds[i] = 0.f;
+    __syncthreads();
+  }
+  for (int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); r < rows; r += nw) {
+    uint4 vx[VPL], vg[VPL], ve[VPL];
+#pragma unroll
+    for (int c = 0; c < VPL; ++c) {
+      vx[c] = ld_nc16(x + r * D + (c * 32 + lane) * 8);
+      vg[c] = ld_nc16(dy + r * D + (c * 32 + lane) * 8);
+      if (dres) ve[c] = ld_nc16(dres + r * D + (c * 32 + lane) * 8);
+    }
+    const float rs = rstd[r];
+    float dot = 0.f;
+#pragma unroll
+    for (int c = 0; c < VPL; ++c) {
+      float xh[8], g[8], s[8];
+      unpack8(vx[c], xh);
+      unpack8(vg[c], g);
+      unpack8(*reinterpret_cast<const uint4*>(scale + (c * 32 + lane) * 8), s);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        xh[i] *= rs;
+        if (dscale) ds[c][i] += g[i] * xh[i];
+        dot += g[i] * s[i] * xh[i];
+      }
+    }
+    dot = warp_sum(dot) / (float)D;
+#pragma unroll
+    for (int c = 0; c < VPL; ++c) {
+      float xh[8], g[8], s[8], o[8];
+      unpack8(vx[c], xh);
+      unpack8(vg[c], g);
+      unpack8(*reinterpret_cast<const uint4*>(scale + (c * 32 + lane) * 8), s);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o[i] = rs * (g[i] * s[i] - xh[i] * rs * dot);
+      if (dres) {
+        float e[8];
+        unpack8(ve[c], e);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] += e[i];
+      }
+      *reinterpret_cast<uint4*>(dx + r * D + (c * 32 + lane) * 8) = pack8(o);
+    }
+  }
+  if (dscale) {
+#pragma unroll
+    for (int c = 0; c < VPL; ++c)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) atomicAdd(&sds[(c * 32 + lane) * 8 + i], ds[c][i]);
+    __syncthreads();
+    for (int i = threadIdx.x; i < D; i += blockDim.x) atomicAdd(dscale + i, sds[i]);
+  }
+}
+
 // one thread per 8 bf16 (= 4 rotation pairs)
 __global__ void __launch_bounds__(256)
 rope_kernel(bf16* __restrict__ x, const float* __restrict__ cache, int64_t rows, int seq_len, int heads,
@@ -240,6 +346,18 @@ extern "C" int csm_rmsnorm_fwd(const void* x, const void* scale, void* y, float*
               "rmsnorm_fwd: dim=%d must be a multiple of 8 and <= %d", dim, kNormThreads * 8 * kNormMaxChunks);
   CSM_REQUIRE(aligned16(x) && aligned16(y) && aligned16(scale), CSM_ERR_ALIGN, "rmsnorm_fwd: misaligned pointer");
   if (rows == 0) return CSM_OK;
+  if ((dim == 2048 || dim == 1024) && rows >= 64) {
+    const int64_t ctas = (rows + 7) / 8, cap = (int64_t)num_sms() * 8;
+    const unsigned g = (unsigned)(ctas < cap ? ctas : cap);
+    if (dim == 2048)
+      rmsnorm_fwd_warp_kernel<8><<<g, 256, 0, as_stream(stream)>>>((const bf16*)x, (const bf16*)scale, (bf16*)y, rstd,
+                                                                   rows, eps);
+    else
+      rmsnorm_fwd_warp_kernel<4><<<g, 256, 0, as_stream(stream)>>>((const bf16*)x, (const bf16*)scale, (bf16*)y, rstd,
+                                                                   rows, eps);
+    CSM_CHECK_LAUNCH("rmsnorm_fwd");
+    return CSM_OK;
+  }
   unsigned grid = (unsigned)(rows < (int64_t)num_sms() * 8 ? rows : (int64_t)num_sms() * 8);
   rmsnorm_fwd_kernel<<<grid, kNormThreads, 0, as_stream(stream)>>>((const bf16*)x, (const bf16*)scale, (bf16*)y,
                                                                    rstd, rows, dim, eps);
@@ -255,6 +373,19 @@ extern "C" int csm_rmsnorm_bwd(const void* dy, const void* x, const void* scale,
   CSM_REQUIRE(aligned16(x) && aligned16(dy) && aligned16(dx) && aligned16(scale) && aligned16(dres),
               CSM_ERR_ALIGN, "rmsnorm_bwd: misaligned pointer");
   if (rows == 0) return CSM_OK;
+  if ((dim == 2048 || dim == 1024) && rows >= 64) {
+    // with dscale the grid stays small (one smem reduction + D global atomics per CTA), without it rows spread wide
+    const int64_t ctas = (rows + 7) / 8, cap = (int64_t)num_sms() * (dscale_f32 ? 2 : 6);
+    const unsigned g = (unsigned)(ctas < cap ? ctas : cap);
+    if (dim == 2048)
+      rmsnorm_bwd_warp_kernel<8><<<g, 256, 0, as_stream(stream)>>>((const bf16*)dy, (const bf16*)x, (const bf16*)scale,
+                                                                   rstd, (const bf16*)dres, (bf16*)dx, dscale_f32, rows);
+    else
+      rmsnorm_bwd_warp_kernel<4><<<g, 256, 0, as_stream(stream)>>>((const bf16*)dy, (const bf16*)x, (const bf16*)scale,
+                                                                   rstd, (const bf16*)dres, (bf16*)dx, dscale_f32, rows);
+    CSM_CHECK_LAUNCH("rmsnorm_bwd");
+    return CSM_OK;
+  }
   unsigned grid = (unsigned)(rows < (int64_t)num_sms() * 2 ? rows : (int64_t)num_sms() * 2);
   rmsnorm_bwd_kernel<<<grid, kNormThreads, 0, as_stream(stream)>>>((const bf16*)dy, (const bf16*)x,
                                                                    (const bf16*)scale, rstd, (const bf16*)dres,
