@@ -334,8 +334,14 @@ def main():
             peak, src = 1400.0, "fallback (B200_PROFILING.md sustained)"
         achieved = flops / (gms * 1e-3) / 1e12 if gms > 0 else 0.0
         step_flops = fwd_flops_per_frame(S) * (2 if mode == "lora" else 3) * B * S
-        roof = {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05/TMEM/TMA bf16 GEMM)", "achieved": achieved,
-                "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None, "peak_source": src,
+        # DRAM bytes of ONE launch of the dominant instantiation (CTA-pair kernel on the fused gate/up forward GEMM,
+        # 4096 x 16384 x 2048) from the committed `ncu --set full` capture: dram__bytes_read.sum + dram__bytes_write.sum
+        # = 84.3 MB + 90.8 MB (profiles/r1_ncu_gemm_cta_pair.txt); algorithmic operand bytes of that launch: 218.1 MB
+        roof = {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05 cta_group::2 / TMEM / TMA bf16 GEMM)",
+                "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                "traffic": 175.2e6 if (S == 2048 and B == 2) else None,
+                "traffic_note": "per launch of the 4096x16384x2048 gate/up GEMM (ncu, profiles/r1_ncu_gemm_cta_pair.txt)",
+                "peak_source": src,
                 "gemm_launches_per_step": n_g // 2, "gemm_ms_per_step": gms / 2, "gemm_share_of_step": (gms / 2) / ms_step,
                 "step_model_tflops": step_flops / (ms_step * 1e-3) / 1e12,
                 "step_frac_of_peak": step_flops / (ms_step * 1e-3) / 1e12 / peak}

@@ -144,14 +144,23 @@ class GradSynchronizer:
             grads = [p.grad for p in self.params if p.grad is not None]
             if not grads:
                 return
-            flat = torch.cat([g.reshape(-1).float() for g in grads])
-            dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group)
-            flat.mul_(1.0 / self.world)
-            off = 0
+            # one flat fp32 buffer (kept across steps), filled and drained by multi-tensor copies: a handful of
+            # launches instead of two per adapter tensor (~240 for r=8 q/v LoRA on CSM-1B)
+            n = sum(g.numel() for g in grads)
+            flat = getattr(self, "_flat", None)
+            if flat is None or flat.numel() != n or flat.device != grads[0].device:
+                flat = self._flat = torch.empty(n, dtype=torch.float32, device=grads[0].device)
+            views, off = [], 0
             for g in grads:
-                n = g.numel()
-                g.copy_(flat[off:off + n].view_as(g))
-                off += n
+                views.append(flat[off:off + g.numel()].view_as(g))
+                off += g.numel()
+            torch._foreach_copy_(views, grads)
+            if dist.get_backend(self.group) == "nccl":
+                dist.all_reduce(flat, op=dist.ReduceOp.AVG, group=self.group)
+            else:
+                dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group)
+                flat.mul_(1.0 / self.world)
+            torch._foreach_copy_(grads, views)
             return
         if self.accumulating:
             return

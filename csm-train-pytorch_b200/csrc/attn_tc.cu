@@ -602,12 +602,14 @@ attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
     const int ctid = threadIdx.x - 64;                         // 0..255 among the compute warps
     // per 128-query tile: lse*log2e (+inf past the sequence end => P = 0) and delta*scale, staged through smem once
     // per CTA; the global load for tile it+1 is issued one tile early so its latency hides behind tile it's math
+    // (raw value only: scaling it here would make the thread wait for the load right away)
+    const float ld_mul = ctid < 128 ? kLog2e : scale;
     auto load_ld = [&](int it) -> float {
       const int h = kvh * rep + it / nq_iter, qb = kvb + it % nq_iter;
       const int q = qb * TQ + (ctid & 127);
       const int64_t li = ((int64_t)b * H + h) * S + q;
-      if (ctid < 128) return (q < S) ? __ldg(lse + li) * kLog2e : INFINITY;
-      return (q < S) ? __ldg(delta + li) * scale : 0.f;
+      if (q >= S) return ctid < 128 ? INFINITY : 0.f;
+      return __ldg((ctid < 128 ? lse : delta) + li);
     };
     float ld_next = load_ld(0);
     auto sub = [&](int u, auto diag_tag) {
@@ -616,7 +618,7 @@ attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
       const int qb = kvb + it % nq_iter;
       float* sLD = reinterpret_cast<float*>(smem + DK_LD) + (it & 1) * 256;
       if (hq == 0) {
-        sLD[ctid] = ld_next;
+        sLD[ctid] = ld_next * ld_mul;
         named_bar_sync(1, 256);
         if (it + 1 < total) ld_next = load_ld(it + 1);
       }
