@@ -130,6 +130,28 @@ def test_small_lora_tensor_core_path(cuda, targets, r):
     _check(orc, prod, o, p)
 
 
+@pytest.mark.parametrize("lora", [True, False])
+def test_small_model_on_cta_pair_and_fused_swiglu_kernels(cuda, lora):
+    """The kernels CSM-1B shapes select automatically — tcgen05 cta_group::2 GEMMs (256-row tiles over a 2-CTA cluster)
+    and the w1|w3 GEMM with the SwiGLU epilogue — forced on for the small model so the whole training step is checked
+    against the oracle on them (LoRA on all seven projections: extra-K-block tail through both; and full fine-tune)."""
+    from csm import autograd, ops
+    targets = ["q_proj", "k_proj", "v_proj", "o_proj", "gate_proj", "up_proj", "down_proj"] if lora else None
+    orc, prod, cfg = _pair("small", cuda, lora=lora, targets=targets, r=16)
+    ops.set_gemm_cta_pair_mode(1)
+    try:
+        assert ops.swiglu_fusable(2 * 128, 512, 256)
+        for fuse_bwd in (False, True):
+            autograd.FUSE_SWIGLU_BWD = fuse_bwd
+            o, p = _run_both(orc, prod, cfg, 2, 128, cuda)
+            _check(orc, prod, o, p, min_cos=0.999 if lora else 0.99)
+            for q in list(orc.parameters()) + list(prod.parameters()):
+                q.grad = None
+    finally:
+        autograd.FUSE_SWIGLU_BWD = False
+        ops.set_gemm_cta_pair_mode(-1)
+
+
 def test_small_full_finetune_tensor_core_path(cuda):
     orc, prod, cfg = _pair("small", cuda, lora=False)
     o, p = _run_both(orc, prod, cfg, 2, 128, cuda)
