@@ -14,9 +14,10 @@ from torch.autograd import Function
 from . import ops
 
 BF16 = torch.bfloat16
-# The w2-dgrad GEMM with the SwiGLU backward in its epilogue is correct (tests/test_ops_gpu.py) but its epilogue reads
-# gate/up one row per lane and is latency-bound: 226 us against 87 + 68 us for GEMM + swiglu_bwd at 4096 x 8192 x 2048
-# (profiles/r1_summary.md), so the backward stays unfused; the forward fusion saves 43 us per layer and is on.
+# The w2-dgrad GEMM can apply the SwiGLU backward in its epilogue (gate/up fetched one chunk ahead as whole 64-byte row
+# segments and transposed to the row-per-lane TMEM layout through smem).  Cold-cache microbenchmark: 120 us against
+# 85 + 69 us for GEMM + swiglu_bwd at 4096 x 8192 x 2048; inside the step the unfused swiglu_bwd reads dact out of L2
+# and the whole step is 0.6 ms FASTER unfused (26.5 vs 27.1 ms), so the fused backward stays off (A/B switch, tested).
 FUSE_SWIGLU_BWD = False
 
 

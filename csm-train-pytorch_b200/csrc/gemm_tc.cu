@@ -91,6 +91,29 @@ __device__ __forceinline__ void store_tile_32x32(uint32_t stage_saddr, bf16* til
   __syncwarp();
 }
 
+// The mirror image for loads: `co[i]` holds the 16-byte piece (row i*8 + lane/4, chunk lane%4) of a 32 x 32 bf16 tile
+// (fetched with whole-64-byte-row-segment loads); returns this lane's own row (16 words) through the staging tile.
+__device__ __forceinline__ void rows_from_coalesced(uint32_t stage_saddr, int lane, const uint4* co, uint32_t* row_words) {
+  const int chunk = lane & 3;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int row = i * 8 + (lane >> 2);
+    const uint32_t a = stage_saddr + row * 64 + ((chunk ^ ((row >> 1) & 3)) << 4);
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(co[i].x), "r"(co[i].y), "r"(co[i].z), "r"(co[i].w)
+                 : "memory");
+  }
+  __syncwarp();
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const uint32_t a = stage_saddr + lane * 64 + ((q ^ ((lane >> 1) & 3)) << 4);
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(row_words[q * 4 + 0]), "=r"(row_words[q * 4 + 1]), "=r"(row_words[q * 4 + 2]), "=r"(row_words[q * 4 + 3])
+                 : "r"(a)
+                 : "memory");
+  }
+  __syncwarp();
+}
+
 __device__ __forceinline__ void tile_coords(int t, int num_m, int num_n, int& g, int& mb, int& nb) {
   const int per_group = num_m * num_n;
   g = t / per_group;
@@ -401,18 +424,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           store_tile_32x32(stage_s, act0 + n, p.ldc2, lane, pa, wrows);
         }
       } else if (kEpi == EPI_SWIGLU_BWD) {
-        const bf16* gurow = p.R + m * p.ldr;
-        bf16* d0 = reinterpret_cast<bf16*>(p.C) + wm0 * p.ldc;        // the warp's first row
-        // gate/up of the NEXT 32-column chunk are fetched while this one is computed (the loads would otherwise sit
-        // exposed between a TMEM read and the stores, eight times per tile)
-        uint4 g4[4], u4[4];
+        const bf16* g0p = p.R + wm0 * p.ldr;                          // gate|up, the warp's first row
+        bf16* d0 = reinterpret_cast<bf16*>(p.C) + wm0 * p.ldc;        // dgate|dup, the warp's first row
+        // gate/up of the NEXT 32-column chunk are fetched (whole 64-byte row segments, four rows x two tensors in flight
+        // per lane) while this one is computed; they reach the row-per-lane layout through the staging tile
+        uint4 gn[4], un[4];
         auto fetch = [&](int c) {
           const int64_t n = n0 + c;
-          const bool ok = row_ok && n < p.N && c < c_hi;
+          const bool chunk_ok = n < p.N && c < c_hi;
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            g4[q] = ok ? ld_nc16(gurow + n + q * 8) : make_uint4(0, 0, 0, 0);
-            u4[q] = ok ? ld_nc16(gurow + p.inter + n + q * 8) : make_uint4(0, 0, 0, 0);
+          for (int i = 0; i < 4; ++i) {
+            const int row = i * 8 + (lane >> 2);
+            const bf16* src = g0p + (int64_t)row * p.ldr + n + (lane & 3) * 8;
+            const bool ok = chunk_ok && row < wrows;
+            gn[i] = ok ? ld_nc16(src) : make_uint4(0, 0, 0, 0);
+            un[i] = ok ? ld_nc16(src + p.inter) : make_uint4(0, 0, 0, 0);
           }
         };
         fetch(c_lo);
@@ -423,29 +449,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           tmem_ld32(t_addr + c, v);
           tmem_ld_wait();
           const int64_t n = n0 + c;
-          uint4 gq[4], uq[4];
-#pragma unroll
-          for (int q = 0; q < 4; ++q) { gq[q] = g4[q]; uq[q] = u4[q]; }
+          uint32_t gw[16], uw[16];
+          rows_from_coalesced(stage_s, lane, gn, gw);
+          rows_from_coalesced(stage_s, lane, un, uw);
           fetch(c + 32);
           if (n >= p.N) continue;                      // inter is a multiple of 128: chunks are all-or-nothing
           uint32_t wdg[16], wdu[16];
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const uint32_t gp[4] = {gq[q].x, gq[q].y, gq[q].z, gq[q].w}, up_[4] = {uq[q].x, uq[q].y, uq[q].z, uq[q].w};
-            uint32_t* dg = wdg + q * 4;
-            uint32_t* du = wdu + q * 4;
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              // dact rounded to bf16 first (what the unfused path stores and re-reads)
-              const uint32_t dp = pack_bf16(__uint_as_float(v[q * 8 + 2 * e]) * p.alpha,
-                                            __uint_as_float(v[q * 8 + 2 * e + 1]) * p.alpha);
-              const float d0 = bf16_lo(dp), d1 = bf16_hi(dp);
-              const float g0 = bf16_lo(gp[e]), g1 = bf16_hi(gp[e]);
-              const float s0 = fast_sigmoid(g0), s1 = fast_sigmoid(g1);
-              du[e] = pack_bf16(d0 * g0 * s0, d1 * g1 * s1);
-              dg[e] = pack_bf16(d0 * bf16_lo(up_[e]) * s0 * fmaf(g0, 1.f - s0, 1.f),
-                                d1 * bf16_hi(up_[e]) * s1 * fmaf(g1, 1.f - s1, 1.f));
-            }
+          for (int e = 0; e < 16; ++e) {
+            // dact rounded to bf16 first (what the unfused path stores and re-reads)
+            const uint32_t dp = pack_bf16(__uint_as_float(v[2 * e]) * p.alpha, __uint_as_float(v[2 * e + 1]) * p.alpha);
+            const float d0f = bf16_lo(dp), d1f = bf16_hi(dp);
+            const float g0 = bf16_lo(gw[e]), g1 = bf16_hi(gw[e]);
+            const float s0 = fast_sigmoid(g0), s1 = fast_sigmoid(g1);
+            wdu[e] = pack_bf16(d0f * g0 * s0, d1f * g1 * s1);
+            wdg[e] = pack_bf16(d0f * bf16_lo(uw[e]) * s0 * fmaf(g0, 1.f - s0, 1.f),
+                               d1f * bf16_hi(uw[e]) * s1 * fmaf(g1, 1.f - s1, 1.f));
           }
           store_tile_32x32(stage_s, d0 + n, p.ldc, lane, wdg, wrows);
           store_tile_32x32(stage_s, d0 + p.inter + n, p.ldc, lane, wdu, wrows);
