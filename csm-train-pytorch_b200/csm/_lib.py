@@ -37,6 +37,7 @@ SIGNATURES = {
     "csm_attn_causal_gqa_fwd": (_i32, [_ptr] * 5 + [_i32] * 5 + [_i64] * 4 + [_f32, _ptr]),
     "csm_set_attn_backend": (None, [_i32]),
     "csm_set_gemm_cta_pair_mode": (None, [_i32]),
+    "csm_set_reserved_sms": (None, [_i32]),
     "csm_attn_bwd_workspace_bytes": (_sz, [_i32] * 5),
     "csm_attn_causal_gqa_bwd": (_i32, [_ptr] * 9 + [_i32] * 5 + [_i64] * 7 + [_f32, _ptr, _sz, _ptr]),
     "csm_linear_ce_workspace_bytes": (_sz, [_i64, _i64, _i64, _i32]),

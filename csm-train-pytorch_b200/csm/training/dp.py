@@ -79,6 +79,13 @@ class GradSynchronizer:
         if cur:
             close(cur)
         self._stream = torch.cuda.Stream(priority=-1) if self.params[0].is_cuda else None
+        if self.world > 1 and self.params[0].is_cuda:
+            # the all-reduce CTAs run beside the backward: keep SMs free for them so the persistent GEMM grids never
+            # wait for an SM that NCCL holds (CSM_DP_RESERVED_SMS, default 0 = off; pair with NCCL_MAX_CTAS)
+            n = int(os.environ.get("CSM_DP_RESERVED_SMS", "0"))
+            if n > 0:
+                from .. import _lib
+                _lib.load().csm_set_reserved_sms(n)
         for p in self.params:
             self._hooks.append(p.register_post_accumulate_grad_hook(self._on_autograd_grad))
         self._reset()

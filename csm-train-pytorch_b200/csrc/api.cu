@@ -16,6 +16,10 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+// SMs the persistent kernels size their grids for.  csm_set_reserved_sms(n) keeps n SMs free for a concurrently running
+// collective (data-parallel full fine-tune: NCCL's all-reduce CTAs overlap the backward; a persistent 148-CTA GEMM whose
+// last CTAs must wait for an SM held by NCCL would take twice as long).
+static std::atomic<int> g_reserved_sms{0};
 int num_sms() {
   static int sms = 0;
   if (sms == 0) {
@@ -26,7 +30,8 @@ int num_sms() {
     else
       sms = 148;
   }
-  return sms;
+  const int r = g_reserved_sms.load(std::memory_order_relaxed);
+  return sms - r > 8 ? sms - r : 8;
 }
 
 int gemm_simt_launch(const void*, const void*, void*, const void*, int64_t, int64_t, int64_t, int64_t, int64_t,
@@ -105,6 +110,7 @@ using namespace csm;
 
 extern "C" int csm_abi_version(void) { return CSM_ABI_VERSION; }
 extern "C" void csm_set_attn_backend(int32_t backend) { g_attn_backend.store(backend); }
+extern "C" void csm_set_reserved_sms(int32_t n) { csm::g_reserved_sms.store(n < 0 ? 0 : n); }
 namespace csm { void gemm_tc_set_cta_pair_mode(int m); }
 extern "C" void csm_set_gemm_cta_pair_mode(int32_t mode) { csm::gemm_tc_set_cta_pair_mode(mode); }
 extern "C" const char* csm_last_error(void) { return g_err; }

@@ -616,7 +616,7 @@ static int launch_inst(const CUtensorMap& a, const CUtensorMap& b, const CUtenso
       // how many CTA pairs can be co-resident (a pair needs two SMs of one TPC): the persistent grid must not
       // exceed it, or a late pair would start only after an early one has finished its whole share
       cudaLaunchConfig_t q = {};
-      q.gridDim = dim3(num_sms() & ~1); q.blockDim = dim3(kGemmThreads); q.dynamicSmemBytes = Cfg::kSmemBytes;
+      q.gridDim = dim3(148); q.blockDim = dim3(kGemmThreads); q.dynamicSmemBytes = Cfg::kSmemBytes;
       cudaLaunchAttribute at[1];
       at[0].id = cudaLaunchAttributeClusterDimension;
       at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
@@ -624,7 +624,7 @@ static int launch_inst(const CUtensorMap& a, const CUtensorMap& b, const CUtenso
       int n = 0;
       e = cudaOccupancyMaxActiveClusters(&n, kern, &q);
       if (e != cudaSuccess || n < 1) { cudaGetLastError(); n = num_sms() / 2 - 2; }
-      max_pairs = n < num_sms() / 2 ? n : num_sms() / 2;
+      max_pairs = n;
     }
     configured = true;
   }
@@ -634,7 +634,8 @@ static int launch_inst(const CUtensorMap& a, const CUtensorMap& b, const CUtenso
     kern<<<grid, kGemmThreads, Cfg::kSmemBytes, st>>>(a, b, a2, b2, p);
   } else {
     const int tiles = p.groups * ((p.num_m + 1) / 2) * p.num_n;
-    const int pairs = tiles < max_pairs ? tiles : max_pairs;
+    const int avail = max_pairs < num_sms() / 2 ? max_pairs : num_sms() / 2;   // num_sms() honours reserved SMs
+    const int pairs = tiles < avail ? tiles : avail;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(2 * pairs); cfg.blockDim = dim3(kGemmThreads); cfg.dynamicSmemBytes = Cfg::kSmemBytes;
     cfg.stream = st;

@@ -136,6 +136,9 @@ void csm_set_attn_backend(int32_t backend);
 /* test hook: CTA-pair (tcgen05 cta_group::2, 256-row tiles) mode of the tensor-core GEMM. -1 = automatic (large
  * plain GEMMs only), 0 = never, 1 = whenever the shape allows it. */
 void csm_set_gemm_cta_pair_mode(int32_t mode);
+/* Persistent kernels (GEMM, fused CE) size their grids for (SM count - n): leaves n SMs to a collective that runs
+ * concurrently on another stream (data-parallel gradient all-reduce overlapped with backward).  Default 0. */
+void csm_set_reserved_sms(int32_t n);
 /* workspace: csm_attn_bwd_workspace_bytes() bytes (delta[batch,heads,seq] fp32 + fp32 dk/dv staging). */
 size_t csm_attn_bwd_workspace_bytes(int32_t batch, int32_t seq, int32_t heads, int32_t kv_heads,
                                     int32_t head_dim);
