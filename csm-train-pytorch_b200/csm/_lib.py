@@ -29,6 +29,8 @@ SIGNATURES = {
     "csm_rmsnorm_bwd": (_i32, [_ptr] * 7 + [_i64, _i32, _ptr]),
     "csm_rope": (_i32, [_ptr, _ptr, _i64, _i32, _i32, _i32, _i64, _i32, _ptr]),
     "csm_gemm_bf16": (_i32, [_ptr] * 4 + [_i64] * 7 + [_i32] * 4 + [_f32, _ptr, _ptr, _i64, _i64, _i64, _i32, _ptr]),
+    "csm_gemm_splitk_workspace_bytes": (_sz, [_i64, _i64, _i32]),
+    "csm_gemm_bf16_splitk": (_i32, [_ptr] * 3 + [_i64] * 6 + [_i32, _i32, _f32, _i32, _ptr, _sz, _ptr]),
     "csm_gemm_swiglu_supported": (_i32, [_i64, _i64, _i64]),
     "csm_gemm_swiglu_fwd": (_i32, [_ptr] * 4 + [_i64] * 7 + [_ptr, _ptr, _i64, _i64, _i64, _ptr]),
     "csm_gemm_swiglu_bwd": (_i32, [_ptr] * 4 + [_i64] * 7 + [_ptr, _ptr, _i64, _i64, _i64, _ptr]),

@@ -171,20 +171,33 @@ class _Group:
             R = sum(m.lora_A.shape[0] for _, m in self.lora)
             if R > 64:
                 raise RuntimeError("fused LoRA group: total rank must be <= 64")
+            # the common scaling alpha/r rides on the skinny GEMMs' alpha (t = s x A^T, dts = s dy B): the block-diagonal
+            # tail operand then holds the raw B factors and no per-step scaling kernels are needed
+            scal = {float(m.lora_scaling) for _, m in self.lora}
+            self.s = scal.pop() if len(scal) == 1 else None
             self.A_cat = torch.cat([m.lora_A.detach() for _, m in self.lora], dim=0)            # [R, in]
-            self.B_bd = torch.zeros(self.n_out, R, dtype=self.W.dtype, device=self.W.device)      # [N, R]
+            key = ("B_bd",) + tuple(id(m) for m in mods)
+            self.B_bd = cache.get(key)
+            if self.B_bd is None or self.B_bd.shape != (self.n_out, R) or self.B_bd.device != self.W.device:
+                self.B_bd = cache[key] = torch.zeros(self.n_out, R, dtype=self.W.dtype, device=self.W.device)
             self.slots, ro = [], 0
             for j, m in self.lora:
                 r = m.lora_A.shape[0]
-                self.B_bd[self.offs[j]:self.offs[j] + m.weight.shape[0], ro:ro + r] = \
-                    m.lora_B.detach() * float(m.lora_scaling)
+                blk = self.B_bd[self.offs[j]:self.offs[j] + m.weight.shape[0], ro:ro + r]
+                if self.s is None:
+                    torch.mul(m.lora_B.detach(), float(m.lora_scaling), out=blk)
+                else:
+                    blk.copy_(m.lora_B.detach())
                 self.slots.append((j, m, ro, r, index_of[id(m.lora_A)], index_of[id(m.lora_B)]))
                 ro += r
+
+    def _t(self, x):
+        return ops.gemm(x, self.A_cat, alpha=self.s if self.s is not None else 1.0)             # [N, R]
 
     def fwd(self, x):
         if not self.lora:
             return ops.gemm(x, self.W), None
-        t = ops.gemm(x, self.A_cat)                                    # [N, R]
+        t = self._t(x)
         return ops.gemm(x, self.W, a2=t, b2=self.B_bd), t
 
     def fwd_swiglu(self, x):
@@ -192,7 +205,7 @@ class _Group:
         if not self.lora:
             gu, act = ops.gemm_swiglu_fwd(x, self.W)
             return gu, act, None
-        t = ops.gemm(x, self.A_cat)
+        t = self._t(x)
         gu, act = ops.gemm_swiglu_fwd(x, self.W, a2=t, b2=self.B_bd)
         return gu, act, t
 
@@ -204,18 +217,21 @@ class _Group:
                     _acc(grads, self.iw[j], dW[self.offs[j]:self.offs[j] + m.weight.shape[0]])
         if not self.lora:
             return ops.gemm(dy, self.W, trans_b=True)
-        dt = ops.gemm(dy, self.B_bd, trans_b=True)                     # dy (sB)_bd   [N, R]
+        # with the common scaling s folded into t and dts:  y = x W^T + t B^T,  t = s x A^T
+        #   dB = dy^T t,   dts = s dy B,   dA = dts^T x,   dx = dy W + dts A
+        s = self.s if self.s is not None else 1.0
+        dts = ops.gemm(dy, self.B_bd, trans_b=True, alpha=s)           # [N, R]
         if any(need[iB] for *_, iB in self.slots):
             dB = ops.gemm(dy, t, trans_a=True, trans_b=True)          # dy^T t       [n_out, R]
         if any(need[iA] for *_, iA, _ in self.slots):
-            dA = ops.gemm(dt, x, trans_a=True, trans_b=True)          # dt^T x       [R, in]
+            dA = ops.gemm(dts, x, trans_a=True, trans_b=True)         # dts^T x      [R, in]
         for j, m, ro, r, iA, iB in self.slots:
             if need[iB]:
                 blk = dB[self.offs[j]:self.offs[j] + m.weight.shape[0], ro:ro + r]
-                _acc(grads, iB, (blk * float(m.lora_scaling)).contiguous())
+                _acc(grads, iB, blk.contiguous() if self.s is not None else (blk * float(m.lora_scaling)).contiguous())
             if need[iA]:
                 _acc(grads, iA, dA[ro:ro + r])
-        return ops.gemm(dy, self.W, trans_b=True, a2=dt, b2=self.A_cat)
+        return ops.gemm(dy, self.W, trans_b=True, a2=dts, b2=self.A_cat)
 
 
 class StackFn(Function):

@@ -168,6 +168,24 @@ def swiglu_bwd(dout, gate, up, dgate=None, dup=None):
 
 
 # ----------------------------------------------------------------------------- GEMM
+SPLITK_ENABLED = True
+
+
+def _splitk_choice(M: int, N: int, K: int) -> int:
+    """Number of reduction groups for a skinny GEMM (0 = run it as one GEMM).  Skinny = one output dimension <= 64 and
+    at most 48 output tiles of 128 x 128; the split fills ~100-160 CTAs and keeps >= 256 reduction elements per group."""
+    if not SPLITK_ENABLED or min(M, N) > 64 or K < 1024:
+        return 0
+    tiles = ((M + 127) // 128) * ((N + 127) // 128)
+    if tiles > 48 or M * N * 4 * 16 > (64 << 20):
+        return 0
+    for s in (16, 8, 4, 2):
+        if K % (s * 64) == 0 and K // s >= 256 and tiles * s <= 160:
+            return s
+    return 0
+
+
+
 def gemm(a, b, *, trans_a: bool = False, trans_b: bool = False, out: Optional[torch.Tensor] = None,
          residual: Optional[torch.Tensor] = None, accumulate: bool = False, alpha: float = 1.0,
          a2: Optional[torch.Tensor] = None, b2: Optional[torch.Tensor] = None, out_dtype=BF16,
@@ -185,12 +203,28 @@ def gemm(a, b, *, trans_a: bool = False, trans_b: bool = False, out: Optional[to
     if out is None:
         out = torch.empty(M, N, dtype=out_dtype, device=a.device)
     assert out.shape == (M, N) and out.stride(1) == 1
+    be = _backend_override if backend is None else backend
+    splits = _splitk_choice(M, N, K) if (be != GEMM_SIMT and a2 is None and residual is None and not accumulate
+                                         and out.dtype == BF16) else 0
+    if splits:
+        lib = _lib.load()
+        nbytes = lib.csm_gemm_splitk_workspace_bytes(M, N, splits)
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=a.device)
+        if _gemm_prof is not None:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+        _lib.check(lib.csm_gemm_bf16_splitk(_p(a), _p(b), _p(out), M, N, K, a.stride(0), b.stride(0), out.stride(0),
+                                            1 if trans_a else 0, 1 if trans_b else 0, alpha, splits, _p(ws), nbytes,
+                                            _st()), "gemm_bf16_splitk")
+        if _gemm_prof is not None:
+            e1.record()
+            _gemm_prof.append((2.0 * M * N * K, e0, e1))
+        return out
     K2 = 0
     if a2 is not None:
         K2 = a2.shape[0] if trans_a else a2.shape[1]
         assert a2.stride(1) == 1 and b2.stride(1) == 1
     lib = _lib.load()
-    be = _backend_override if backend is None else backend
     if _gemm_prof is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()

@@ -142,6 +142,32 @@ int gemm_tc_swiglu_bwd(const void*, const void*, const void*, void*, int64_t, in
                        int64_t, int64_t, const void*, const void*, int64_t, int64_t, int64_t, cudaStream_t);
 }  // namespace csm
 
+namespace csm {
+bool gemm_tc_splitk_supported(int64_t M, int64_t N, int64_t K, int splits);
+int gemm_tc_splitk(const void*, const void*, void*, int64_t, int64_t, int64_t, int64_t, int64_t, int64_t, int, int, float,
+                   int, float*, cudaStream_t);
+}  // namespace csm
+
+extern "C" size_t csm_gemm_splitk_workspace_bytes(int64_t M, int64_t N, int32_t splits) {
+  return (size_t)splits * (size_t)M * (size_t)N * sizeof(float) + 256;
+}
+
+extern "C" int csm_gemm_bf16_splitk(const void* A, const void* B, void* C, int64_t M, int64_t N, int64_t K, int64_t lda,
+                                    int64_t ldb, int64_t ldc, int32_t transA, int32_t transB, float alpha,
+                                    int32_t splits, void* workspace, size_t workspace_bytes, csm_stream_t stream) {
+  CSM_REQUIRE(csm_device_supported() == 1, CSM_ERR_ARCH, "gemm_splitk: needs an sm_100 device");
+  CSM_REQUIRE(gemm_tc_splitk_supported(M, N, K, splits), CSM_ERR_SHAPE,
+              "gemm_splitk: K=%lld must split into %d groups of a multiple of 64", (long long)K, splits);
+  CSM_REQUIRE(gemm_tc_supported(A, B, C, nullptr, M, N, K / splits, lda, ldb, ldc, 0, transA, transB, CSM_DT_BF16,
+                                nullptr, nullptr, 0, 0, 0) ||
+                  (aligned16(A) && aligned16(B) && lda % 8 == 0 && ldb % 8 == 0),
+              CSM_ERR_ALIGN, "gemm_splitk: operands must be 16-byte aligned with strides that are multiples of 8");
+  CSM_REQUIRE(workspace && aligned16(workspace) && workspace_bytes >= csm_gemm_splitk_workspace_bytes(M, N, splits),
+              CSM_ERR_SHAPE, "gemm_splitk: workspace too small");
+  return gemm_tc_splitk(A, B, C, M, N, K, lda, ldb, ldc, transA, transB, alpha, splits,
+                        reinterpret_cast<float*>(workspace), as_stream(stream));
+}
+
 static bool swiglu_args_ok(const void* a, const void* b, const void* c, const void* d, int64_t l0, int64_t l1,
                            int64_t l2, int64_t l3, const void* a2, const void* b2, int64_t K2, int64_t lda2,
                            int64_t ldb2) {

@@ -824,6 +824,45 @@ int linear_ce_tc_bwd_dlogits(const void* H, const void* W, const int64_t* target
   return gemm_tc_run(o, p, EPI_CE_DLOGITS, st);
 }
 
+// ------------------------------------------------------------------------------------------- split-reduction GEMM
+// Skinny products (LoRA: t = x A^T [M x 16], dA = dt^T x [16 x in], ...) have a handful of output tiles and a long
+// reduction: 16-32 CTAs each streaming its operand at one SM's share of HBM (~1.3 TB/s in total).  Splitting the
+// reduction into `splits` groups (the kernel's `groups` dimension: group g covers K range [g*K/splits, (g+1)*K/splits))
+// puts 96-128 CTAs on the machine; the fp32 partials [splits, M, N] are summed by a small kernel.
+__global__ void __launch_bounds__(256)
+splitk_reduce_kernel(const float* __restrict__ part, bf16* __restrict__ out, int64_t M, int64_t N, int64_t ldc,
+                     int splits, float alpha) {
+  const int64_t total = M * N;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    float acc = 0.f;
+    for (int g = 0; g < splits; ++g) acc += part[(int64_t)g * total + i];
+    out[(i / N) * ldc + (i % N)] = __float2bfloat16_rn(acc * alpha);
+  }
+}
+
+bool gemm_tc_splitk_supported(int64_t M, int64_t N, int64_t K, int splits) {
+  return splits >= 2 && splits <= 16 && K % splits == 0 && (K / splits) % 64 == 0 && M >= 1 && N >= 1;
+}
+
+int gemm_tc_splitk(const void* A, const void* B, void* C, int64_t M, int64_t N, int64_t K, int64_t lda, int64_t ldb,
+                   int64_t ldc, int transA, int transB, float alpha, int splits, float* ws, cudaStream_t st) {
+  const int64_t Kg = K / splits;
+  // K-major operand: the group advances along the inner (K) dimension; MN-major: along the rows (K) dimension
+  GemmTcOperands o{A, B, nullptr, nullptr, lda, ldb, 0, 0, 0, transA ? Kg * lda : Kg, transB ? Kg * ldb : Kg, transA,
+                   transB};
+  GemmTcParams p{};
+  p.M = M; p.N = N; p.K = Kg; p.groups = splits;
+  p.C = ws; p.ldc = N; p.c_group_stride = M * N;
+  p.c_f32 = 1; p.accumulate = 0; p.alpha = 1.f;
+  int rc = gemm_tc_run(o, p, EPI_STORE, st);
+  if (rc) return rc;
+  const int64_t total = M * N;
+  const unsigned grid = (unsigned)((total + 255) / 256 < 1184 ? (total + 255) / 256 : 1184);
+  splitk_reduce_kernel<<<grid, 256, 0, st>>>(ws, (bf16*)C, M, N, ldc, splits, alpha);
+  CSM_CHECK_LAUNCH("splitk_reduce");
+  return CSM_OK;
+}
+
 // groups independent GEMMs in one launch (3-D tensor maps): C_g = op(A_g) op(B_g)
 int gemm_tc_grouped(const void* A, const void* B, void* C, int64_t M, int64_t N, int64_t K, int groups, int64_t lda,
                     int64_t ags, int64_t ldb, int64_t bgs, int64_t ldc, int64_t cgs, int transA, int transB,

@@ -103,6 +103,15 @@ int csm_gemm_bf16(const void* A, const void* B, void* C, const void* R, int64_t 
                   int32_t c_dtype, int32_t accumulate, float alpha, const void* A2, const void* B2,
                   int64_t K2, int64_t lda2, int64_t ldb2, int32_t backend, csm_stream_t stream);
 
+/* ---- skinny GEMM with a long reduction (LoRA t = x A^T, dA = dt^T x, dB = dy^T t): same operand conventions as
+ * csm_gemm_bf16 (no residual / tail / accumulate), C bf16 = alpha * op(A) op(B).  The reduction is split into `splits`
+ * groups computed by separate CTAs (fp32 partials in `workspace`, csm_gemm_splitk_workspace_bytes()) and summed by a
+ * second kernel.  K must be a multiple of splits * 64. */
+size_t csm_gemm_splitk_workspace_bytes(int64_t M, int64_t N, int32_t splits);
+int csm_gemm_bf16_splitk(const void* A, const void* B, void* C, int64_t M, int64_t N, int64_t K, int64_t lda, int64_t ldb,
+                         int64_t ldc, int32_t transA, int32_t transB, float alpha, int32_t splits, void* workspace,
+                         size_t workspace_bytes, csm_stream_t stream);
+
 /* ---- torchtune FeedForward activation: out = silu(gate) * up (elementwise, fp32 math) */
 int csm_swiglu_fwd(const void* gate, const void* up, void* out, int64_t rows, int64_t cols, int64_t ldg,
                    int64_t ldu, int64_t ldo, csm_stream_t stream);

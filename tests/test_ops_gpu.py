@@ -225,6 +225,30 @@ def test_gemm_swiglu_fused_matches_unfused(ops, cuda, M, I, K, r):
     assert rel_err(act, F.silu(g32) * u32) < 1e-2
 
 
+@pytest.mark.parametrize("M,N,K,ta,tb", [(4096, 16, 2048, False, False), (4096, 16, 3072, False, True),
+                                         (3072, 16, 4096, True, True), (16, 2048, 4096, True, True),
+                                         (2048, 8, 1024, False, False), (24, 1000, 7424, True, True)])
+def test_gemm_split_reduction_skinny(ops, cuda, M, N, K, ta, tb):
+    """LoRA-shaped skinny GEMMs take the split-reduction path (grouped partial GEMMs + fp32 reduce kernel)."""
+    from csm import ops as O
+    assert O._splitk_choice(M, N, K) >= 2
+    g = torch.Generator().manual_seed(M + N + K)
+    def mk(r, c):
+        ld = (c + 7) // 8 * 8
+        return (torch.randn(r, ld, generator=g) * 0.5).to(BF).to(cuda)[:, :c]
+    a = mk(K, M) if ta else mk(M, K)
+    b = mk(K, N) if tb else mk(N, K)
+    ref = (a.float().t() if ta else a.float()) @ (b.float() if tb else b.float().t())
+    out = ops.gemm(a, b, trans_a=ta, trans_b=tb, alpha=0.25)
+    assert rel_err(out, 0.25 * ref) < 5e-3, rel_err(out, 0.25 * ref)
+    O.SPLITK_ENABLED = False
+    try:
+        one = ops.gemm(a, b, trans_a=ta, trans_b=tb, alpha=0.25)
+    finally:
+        O.SPLITK_ENABLED = True
+    assert rel_err(out, one.float()) < 5e-3
+
+
 @pytest.mark.parametrize("backend", [1, 2])
 def test_gemm_epilogues_and_lora_tail(ops, cuda, backend):
     g = torch.Generator().manual_seed(5)
