@@ -18,7 +18,7 @@ from ..models import lora as lora_mod
 from ..models.model import Model
 from . import dp
 from .graph import GraphedStep
-from .trainer import csm_1b_args, iterate_batches
+from .trainer import clip_and_step, csm_1b_args, iterate_batches, make_optimizer
 from .utils import compute_loss, setup_logger
 
 
@@ -80,9 +80,7 @@ class CSMLoRATrainer:
         params = list(self.get_lora_params().values())
         n = sum(p.numel() for p in params)
         self.logger.info(f"LoRA: {len(params)} tensors, {n:,} trainable parameters")
-        on_cuda = params[0].is_cuda
-        self.optimizer = torch.optim.AdamW(params, lr=self.learning_rate, weight_decay=self.weight_decay,
-                                           fused=on_cuda, capturable=on_cuda)
+        self.optimizer = make_optimizer(params, self.learning_rate, self.weight_decay)
         self._sync = dp.GradSynchronizer(params)
 
     def enable_cuda_graph(self, warmup: int = 3, max_grad_norm: float = 1.0) -> None:
@@ -118,9 +116,7 @@ class CSMLoRATrainer:
                                self.semantic_weight, self.acoustic_weight, frame_idx=b["frame_idx"])
         loss.backward()
         self._sync.finish()
-        if max_grad_norm and max_grad_norm > 0:
-            torch.nn.utils.clip_grad_norm_(list(self.get_lora_params().values()), max_grad_norm)
-        self.optimizer.step()
+        clip_and_step(self.optimizer, list(self.get_lora_params().values()), max_grad_norm)
         self.optimizer.zero_grad(set_to_none=True)
         return loss.detach()
 

@@ -51,6 +51,27 @@ def iterate_batches(dataset, batch_size: int, shuffle: bool, rank: int = 0, worl
         yield collate_variable_length([dataset[j] for j in order[i:i + batch_size]])
 
 
+def make_optimizer(param_groups, lr: float, weight_decay: float):
+    """AdamW of the reference trainers (trainer.py:166-173).  CUDA bf16 parameters get the two-pass multi-tensor
+    clip + AdamW kernels (csm/training/optim.py); anything else (CPU unit tests of the host logic) stock torch AdamW."""
+    params = [p for g in param_groups for p in g["params"]] if isinstance(param_groups[0], dict) else list(param_groups)
+    if params and all(p.is_cuda and p.dtype == torch.bfloat16 for p in params):
+        from .optim import FusedClipAdamW
+        return FusedClipAdamW(param_groups, lr=lr, weight_decay=weight_decay)
+    return torch.optim.AdamW(param_groups, lr=lr, weight_decay=weight_decay)
+
+
+def clip_and_step(optimizer, params, max_grad_norm) -> None:
+    """clip_grad_norm_(params, max_grad_norm) + optimizer.step() (trainer.py:271-276)."""
+    from .optim import FusedClipAdamW
+    if isinstance(optimizer, FusedClipAdamW):
+        optimizer.step(max_grad_norm=max_grad_norm if max_grad_norm and max_grad_norm > 0 else 0.0)
+        return
+    if max_grad_norm and max_grad_norm > 0:
+        torch.nn.utils.clip_grad_norm_(params, max_grad_norm)
+    optimizer.step()
+
+
 class CSMTrainer:
     def __init__(self, model_path: str, output_dir: str, device: str = "cuda", log_file: Optional[str] = None,
                  learning_rate: float = 1e-5, backbone_lr_multiplier: float = 0.1,
@@ -114,9 +135,7 @@ class CSMTrainer:
             {"params": groups["decoder"], "lr": lr * self.decoder_lr_multiplier},
             {"params": groups["embeddings"], "lr": lr * self.embedding_lr_multiplier},
             {"params": groups["other"], "lr": lr}) if g["params"]]
-        on_cuda = next(self.model.parameters()).is_cuda
-        self.optimizer = torch.optim.AdamW(param_groups, weight_decay=self.weight_decay, fused=on_cuda,
-                                           capturable=on_cuda)
+        self.optimizer = make_optimizer(param_groups, lr, self.weight_decay)
         trainable = [p for p in self.model.parameters() if p.requires_grad]
         self._sync = dp.GradSynchronizer(trainable, bucket_bytes=64 << 20 if total > (32 << 20) else None)
         sink = self._sync if self._sync.bucketed else None
@@ -133,9 +152,7 @@ class CSMTrainer:
                                    self.semantic_weight, self.acoustic_weight, frame_idx=b["frame_idx"])
             loss.backward()
             self._sync.finish()
-            if max_grad_norm and max_grad_norm > 0:
-                torch.nn.utils.clip_grad_norm_([p for p in self.model.parameters() if p.requires_grad], max_grad_norm)
-            self.optimizer.step()
+            clip_and_step(self.optimizer, [p for p in self.model.parameters() if p.requires_grad], max_grad_norm)
             self.optimizer.zero_grad(set_to_none=True)
             return loss.detach()
         self._graphed = GraphedStep(impl, self.device, warmup)
@@ -171,9 +188,7 @@ class CSMTrainer:
 
     def optimizer_step(self, max_grad_norm: float = 1.0) -> None:
         self._sync.finish()
-        if max_grad_norm and max_grad_norm > 0:
-            torch.nn.utils.clip_grad_norm_([p for p in self.model.parameters() if p.requires_grad], max_grad_norm)
-        self.optimizer.step()
+        clip_and_step(self.optimizer, [p for p in self.model.parameters() if p.requires_grad], max_grad_norm)
         self.optimizer.zero_grad(set_to_none=True)
         self.global_step += 1
 

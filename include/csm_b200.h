@@ -103,6 +103,15 @@ int csm_gemm_bf16(const void* A, const void* B, void* C, const void* R, int64_t 
                   int32_t c_dtype, int32_t accumulate, float alpha, const void* A2, const void* B2,
                   int64_t K2, int64_t lda2, int64_t ldb2, int32_t backend, csm_stream_t stream);
 
+/* ---- optimiser step of the reference trainers (trainer.py:269-278): torch.nn.utils.clip_grad_norm_(max_norm) followed
+ * by torch.optim.AdamW.step (decoupled weight decay, bias correction), as one squared-norm pass and one update pass over
+ * n_tensors bf16 tensors.  All seven tables are HOST arrays of n_tensors entries (device pointers / sizes / per-tensor
+ * learning rate and weight decay).  step_dev: device float, incremented by this call; sq_norm_dev: device float, holds
+ * the squared global gradient norm afterwards.  max_norm <= 0 disables clipping. */
+int csm_adamw_clip_step(void* const* params, const void* const* grads, void* const* exp_avg, void* const* exp_avg_sq,
+                        const int64_t* numel, const float* lr, const float* weight_decay, int32_t n_tensors, float beta1,
+                        float beta2, float eps, float max_norm, float* step_dev, float* sq_norm_dev, csm_stream_t stream);
+
 /* ---- skinny GEMM with a long reduction (LoRA t = x A^T, dA = dt^T x, dB = dy^T t): same operand conventions as
  * csm_gemm_bf16 (no residual / tail / accumulate), C bf16 = alpha * op(A) op(B).  The reduction is split into `splits`
  * groups computed by separate CTAs (fp32 partials in `workspace`, csm_gemm_splitk_workspace_bytes()) and summed by a

@@ -136,3 +136,45 @@ def test_merge_lora_in_place_matches_adapter_forward(cuda, tmp_path):
         l_merged, _ = compute_loss(t.model, b["input_tokens"], b["input_masks"], b["target_audio_tokens"],
                                    frame_idx=b["frame_idx"])
     assert abs(float(l_adapter) - float(l_merged)) < 5e-3 * abs(float(l_adapter))
+
+
+@pytest.mark.parametrize("max_norm", [1.0, 0.0])
+def test_fused_clip_adamw_matches_torch(cuda, max_norm):
+    """csrc/optim.cu (squared-norm pass + AdamW pass with the clip coefficient derived on the device) against
+    torch.nn.utils.clip_grad_norm_ + torch.optim.AdamW on the same bf16 tensors: odd sizes, unaligned views,
+    two parameter groups with different learning rates / weight decay, three steps."""
+    from csm.training.optim import FusedClipAdamW
+    g = torch.Generator().manual_seed(0)
+    flat = torch.randn(3 + 50000, generator=g).to(torch.bfloat16).to(cuda)
+    shapes = [(257, 33), (4096,), (1000, 77), (5,), (300001,)]
+    def make():
+        ps = [torch.nn.Parameter((torch.randn(*s, generator=torch.Generator().manual_seed(i)) * 0.1).to(torch.bfloat16)
+                                 .to(cuda)) for i, s in enumerate(shapes)]
+        ps.append(torch.nn.Parameter(flat.clone()[3:]))          # 6-byte offset: the scalar (unaligned) path
+        return ps
+    pa, pb = make(), make()
+    groups = lambda ps: [{"params": ps[:3], "lr": 1e-2, "weight_decay": 0.1}, {"params": ps[3:], "lr": 3e-3}]
+    ref = torch.optim.AdamW(groups(pa), lr=1e-3, weight_decay=0.01, fused=True)
+    opt = FusedClipAdamW(groups(pb), lr=1e-3, weight_decay=0.01)
+    for step in range(3):
+        for i, (a, b) in enumerate(zip(pa, pb)):
+            gr = (torch.randn(a.shape, generator=torch.Generator().manual_seed(100 * step + i)) * 2.0)
+            a.grad = gr.to(torch.bfloat16).to(cuda)
+            b.grad = a.grad.clone()
+        exact = float(torch.sqrt(sum((b.grad.float() ** 2).sum() for b in pb)))
+        total = torch.nn.utils.clip_grad_norm_(pa, max_norm) if max_norm > 0 else None     # (a bf16 tensor)
+        ref.step()
+        opt.step(max_grad_norm=max_norm)
+        if total is not None:
+            assert abs(float(opt.grad_norm) - exact) <= 1e-4 * exact
+            assert abs(float(opt.grad_norm) - float(total)) <= 1e-2 * float(total)
+    for a, b in zip(pa, pb):
+        err = (a.float() - b.float()).abs().max().item()
+        assert err <= 2e-2 * a.float().abs().max().item() + 1e-3, err
+        sa, sb = ref.state[a], opt.state[b]
+        assert torch.allclose(sa["exp_avg"].float(), sb["exp_avg"].float(), atol=2e-2, rtol=2e-2)
+    sd = opt.state_dict()
+    assert sd["fused_step"] == 3.0 and all(float(s["step"]) == 3.0 for s in sd["state"].values())
+    opt2 = FusedClipAdamW(groups(make()), lr=1e-3, weight_decay=0.01)
+    opt2.load_state_dict(sd)
+    assert float(opt2._dev_scalars[0]) == 3.0
