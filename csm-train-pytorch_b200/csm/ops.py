@@ -169,6 +169,25 @@ def swiglu_bwd(dout, gate, up, dgate=None, dup=None):
 
 # ----------------------------------------------------------------------------- GEMM
 SPLITK_ENABLED = True
+_streamk_ws = {}       # device index -> zeroed scratch registered with the library (kept alive here)
+
+
+def _ensure_streamk_workspace(device) -> None:
+    """Registers the stream-K scratch of the CTA-pair GEMM once per process (first GEMM call, i.e. before any CUDA-graph
+    capture).  The library keeps one pointer, so a process drives one device — the one-process-per-GPU model of §8(e)."""
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    if idx in _streamk_ws:
+        return
+    lib = _lib.load()
+    nbytes = lib.csm_gemm_streamk_workspace_bytes()
+    buf = torch.zeros(nbytes, dtype=torch.uint8, device=device)
+    lib.csm_gemm_set_streamk_workspace(buf.data_ptr(), nbytes)
+    _streamk_ws[idx] = buf
+
+
+def set_gemm_streamk_mode(m: int) -> None:
+    """0 (default) whole tiles only; 1 stream-K schedule when the last wave of tiles would be badly filled."""
+    _lib.load().csm_set_gemm_streamk_mode(m)
 
 
 def _splitk_choice(M: int, N: int, K: int) -> int:
@@ -195,6 +214,7 @@ def gemm(a, b, *, trans_a: bool = False, trans_b: bool = False, out: Optional[to
     a: [M,K] (or [K,M] when trans_a); b: [N,K] (nn.Linear layout; or [K,N] when trans_b); 2-D, unit inner stride.
     """
     _chk_cuda(a, b)
+    _ensure_streamk_workspace(a.device)
     assert a.dim() == 2 and b.dim() == 2 and a.stride(1) == 1 and b.stride(1) == 1
     M, K = (a.shape[1], a.shape[0]) if trans_a else a.shape
     N, Kb = (b.shape[1], b.shape[0]) if trans_b else b.shape

@@ -39,6 +39,11 @@ struct GemmTcParams {
   // SwiGLU epilogues: C = gate|up buffer [M, 2*inter] (fwd: written, bwd: R = gate|up read, C = dgate|dup written),
   // C2 = act [M, inter] (fwd)
   void* C2; int64_t ldc2; int64_t inter;
+  // stream-K (CTA-pair EPI_STORE only): the tiles' k-blocks are dealt out evenly to the pairs; a tile cut between two
+  // pairs is finished by the pair that owns its last k-block, which adds the other pair's fp32 partial (sk_ws) first
+  int streamk;
+  float* sk_ws;             // [pairs][2 CTAs][BN cols][128 rows] fp32
+  int* sk_flags;            // [pairs][2 CTAs][2]: partial-ready count, readers-done count (self-resetting)
   // CE epilogues
   const int64_t* targets; int64_t tgt_row_stride, tgt_group_stride;
   float4* ce_part;          // [groups*M, num_n]
@@ -128,6 +133,36 @@ __device__ __forceinline__ void tile_coords(int t, int num_m, int num_n, int& g,
   nb = in_band / band_m;
 }
 
+// One unit of a CTA's (pair's) persistent loop: the k-blocks [kb0, kb1) of output tile `tile`.
+//   kind 0: the whole tile.   kind 1 (stream-K): the HEAD part of a tile that the next pair finishes — its fp32
+//   accumulator goes to the workspace.   kind 2 (stream-K): the TAIL part — adds the previous pair's partial, then the
+//   normal epilogue.  Every pair does its kind-1 item first and its kind-2 item second.
+struct WorkItem { int tile, kb0, kb1, kind; };
+
+__device__ __forceinline__ bool next_item(int streamk, int unit, int n_units, int num_tiles, int kb_total, int idx,
+                                          WorkItem& w) {
+  if (!streamk) {
+    w.tile = unit + idx * n_units; w.kb0 = 0; w.kb1 = kb_total; w.kind = 0;
+    return w.tile < num_tiles;
+  }
+  const long long U = (long long)num_tiles * kb_total;
+  const long long u0 = U * unit / n_units, u1 = U * (unit + 1) / n_units;
+  const int tA = (int)(u0 / kb_total), ka = (int)(u0 % kb_total);
+  const int tC = (int)(u1 / kb_total), kc = (int)(u1 % kb_total);
+  const int head = kc > 0 ? 1 : 0;                         // this pair starts a tile it does not finish
+  const int f0 = ka == 0 ? tA : tA + 1;                    // first whole tile
+  const int nfull = tC - f0;
+  // order: the head part first (its partial is what the NEXT pair waits for), then the tail part this pair finishes
+  // (the previous pair's partial is on its way; the fix-up epilogue then hides behind the whole tiles), then whole tiles
+  if (idx < head) { w.tile = tC; w.kb0 = 0; w.kb1 = kc; w.kind = 1; return true; }
+  idx -= head;
+  const int tail = ka > 0 ? 1 : 0;
+  if (idx < tail) { w.tile = tA; w.kb0 = ka; w.kb1 = kb_total; w.kind = 2; return true; }
+  idx -= tail;
+  if (idx < nfull) { w.tile = f0 + idx; w.kb0 = 0; w.kb1 = kb_total; w.kind = 0; return true; }
+  return false;
+}
+
 template <bool kTransA, bool kTransB, int BN, int kEpi, bool kCta2>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
@@ -152,6 +187,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int first_tile = kCta2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
   const int tile_step = kCta2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   const int kb_total = p.k_blocks + p.has_tail;
+  const int sk = (kCta2 && kEpi == EPI_STORE) ? p.streamk : 0;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -177,15 +213,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 0) {
     // ===================== TMA producer (warp-uniform control flow, one elected lane issues) =====================
     int stage = 0; uint32_t phase = 0;
-    for (int t = first_tile; t < num_tiles; t += tile_step) {
+    WorkItem w;
+    for (int it = 0; next_item(sk, first_tile, tile_step, num_tiles, kb_total, it, w); ++it) {
       int g, mb, nb;
-      tile_coords(t, tile_m, p.num_n, g, mb, nb);
+      tile_coords(w.tile, tile_m, p.num_n, g, mb, nb);
       if (kCta2) mb = 2 * mb + (int)rank;
       const int m0 = mb * BM;
       // pair mode: this CTA's half of the B tile (SwiGLU forward: rank 0 = gate rows, rank 1 = up rows)
       const int n0 = kEpi == EPI_SWIGLU_FWD ? (int)rank * (int)p.inter + nb * Cfg::kBRows
                                             : nb * BN + (kCta2 ? (int)rank * Cfg::kBRows : 0);
-      for (int kb = 0; kb < kb_total; ++kb) {
+      for (int kb = w.kb0; kb < w.kb1; ++kb) {
         mbar_wait(&empty[stage], phase ^ 1);
         if (elect_one()) {
           uint8_t* sa = smem + stage * Cfg::kStageBytes;
@@ -238,11 +275,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     constexpr uint32_t idesc = make_idesc_bf16(kCta2 ? 2 * BM : BM, BN, kTransA ? 1 : 0, kTransB ? 1 : 0);
     int stage = 0; uint32_t phase = 0;
     int acc = 0; uint32_t acc_phase = 0;
-    for (int t = first_tile; t < num_tiles && rank == 0; t += tile_step) {   // pair mode: the leader issues for both
+    WorkItem w;
+    for (int it = 0; rank == 0 && next_item(sk, first_tile, tile_step, num_tiles, kb_total, it, w); ++it) {
+      // (pair mode: the leader issues for both CTAs)
       mbar_wait(&tempty[acc], acc_phase ^ 1);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
-      for (int kb = 0; kb < kb_total; ++kb) {
+      for (int kb = w.kb0; kb < w.kb1; ++kb) {
         mbar_wait(&full[stage], phase);
         tc_fence_after();
         if (elect_one()) {
@@ -256,8 +295,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           for (int kk = 0; kk < BK / 16; ++kk) {
             const uint64_t ad = adesc + (uint64_t)((kTransA ? kk * 16 * 128 : kk * 32) >> 4);
             const uint64_t bd = bdesc + (uint64_t)((kTransB ? kk * 16 * 128 : kk * 32) >> 4);
-            if (kCta2) umma_bf16_2sm(d_tmem, ad, bd, idesc, (kb | kk) ? 1u : 0u);
-            else umma_bf16(d_tmem, ad, bd, idesc, (kb | kk) ? 1u : 0u);
+            const uint32_t accum = ((kb - w.kb0) | kk) ? 1u : 0u;      // the first MMA of a work item overwrites
+            if (kCta2) umma_bf16_2sm(d_tmem, ad, bd, idesc, accum);
+            else umma_bf16(d_tmem, ad, bd, idesc, accum);
           }
           // frees the smem slot (in both CTAs of a pair) once these MMAs have read it
           if (kCta2) umma_commit_2sm(&empty[stage], 3); else umma_commit(&empty[stage]);
@@ -278,9 +318,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     constexpr int kColsPerWarp = BN / (epi_warps(kEpi) / 4);
     const int c_lo = ehalf * kColsPerWarp, c_hi = c_lo + kColsPerWarp;
     int acc = 0; uint32_t acc_phase = 0;
-    for (int t = first_tile; t < num_tiles && ehalf < epi_warps(kEpi) / 4; t += tile_step) {
+    WorkItem w;
+    for (int it = 0; ehalf < epi_warps(kEpi) / 4 && next_item(sk, first_tile, tile_step, num_tiles, kb_total, it, w);
+         ++it) {
       int g, mb, nb;
-      tile_coords(t, tile_m, p.num_n, g, mb, nb);
+      tile_coords(w.tile, tile_m, p.num_n, g, mb, nb);
       if (kCta2) mb = 2 * mb + (int)rank;
       const int64_t m = (int64_t)mb * BM + quad * 32 + lane;
       const int64_t n0 = (int64_t)nb * BN;
@@ -296,12 +338,45 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (kEpi == EPI_STORE) {
         const int64_t crow = (int64_t)g * p.c_group_stride + m * p.ldc;
         const bf16* rrow = p.R ? p.R + (int64_t)g * p.r_group_stride + m * p.ldr : nullptr;
+        // stream-K partial tiles: column-major [BN][128] fp32 per (pair, CTA) so a warp's 32 rows are contiguous
+        const int my_pair = first_tile;
+        float* sk_out = nullptr;
+        const float* sk_in = nullptr;
+        // (layout [BN / 4][128 rows][4 cols]: one float4 per lane, 512 contiguous bytes per warp access)
+        if (kCta2 && w.kind == 1)
+          sk_out = p.sk_ws + ((size_t)(my_pair * 2 + (int)rank) * BN) * BM + (quad * 32 + lane) * 4;
+        if (kCta2 && w.kind == 2) {
+          sk_in = p.sk_ws + ((size_t)((my_pair - 1) * 2 + (int)rank) * BN) * BM + (quad * 32 + lane) * 4;
+          const int* ready = p.sk_flags + ((my_pair - 1) * 2 + (int)rank) * 2;
+          int seen;
+          do {
+            asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(seen) : "l"(ready) : "memory");
+          } while (seen < 8);
+        }
 #pragma unroll 1
         for (int c = c_lo; c < c_hi; c += 32) {
           uint32_t v[32];
           __syncwarp();
           tmem_ld32(t_addr + c, v);
           tmem_ld_wait();
+          if (sk_out) {                               // head part of a cut tile: park the raw accumulator, nothing else
+#pragma unroll
+            for (int i = 0; i < 32; i += 4)
+              *reinterpret_cast<uint4*>(sk_out + (size_t)(c + i) * BM) = make_uint4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+            continue;
+          }
+          if (sk_in) {
+            float4 part[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) part[i] = *reinterpret_cast<const float4*>(sk_in + (size_t)(c + 4 * i) * BM);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              v[4 * i + 0] = __float_as_uint(__uint_as_float(v[4 * i + 0]) + part[i].x);
+              v[4 * i + 1] = __float_as_uint(__uint_as_float(v[4 * i + 1]) + part[i].y);
+              v[4 * i + 2] = __float_as_uint(__uint_as_float(v[4 * i + 2]) + part[i].z);
+              v[4 * i + 3] = __float_as_uint(__uint_as_float(v[4 * i + 3]) + part[i].w);
+            }
+          }
           const int64_t n = n0 + c;
           if (n >= p.N) continue;
           if (!p.c_f32 && n + 32 <= p.N && (p.ldc & 7) == 0 && (!rrow || (p.ldr & 7) == 0)) {
@@ -393,6 +468,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                   if (p.accumulate) o += __bfloat162float(cp[i]);
                   cp[i] = __float2bfloat16_rn(o);
                 }
+            }
+          }
+        }
+        if (sk_out) {                                 // publish the partial: 8 warp arrivals per CTA
+          __threadfence();
+          __syncwarp();
+          if (lane == 0) atomicAdd(p.sk_flags + (my_pair * 2 + (int)rank) * 2, 1);
+        }
+        if (sk_in) {                                  // the last of the 8 reader warps re-arms the flags
+          __syncwarp();
+          if (lane == 0) {
+            int* fl = p.sk_flags + ((my_pair - 1) * 2 + (int)rank) * 2;
+            if (atomicAdd(fl + 1, 1) == 7) {
+              fl[1] = 0;
+              __threadfence();
+              asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(fl), "r"(0) : "memory");
             }
           }
         }
@@ -602,32 +693,44 @@ struct GemmTcOperands {
   int transA, transB;
 };
 
+// Stream-K scratch, registered once per process by the host side (csm_gemm_set_streamk_workspace): flags first, then
+// the fp32 partial tiles.  One buffer per device, so stream-K GEMMs must not run concurrently on two streams — on this
+// path every GEMM is issued on the step's main stream (only NCCL uses the side stream).
+static float* g_sk_ws = nullptr;
+static int* g_sk_flags = nullptr;
+// Measured (tools/bench_streamk.py): no gain on B200 — 4096x2048x8192: 94.2 us whole tiles vs 96.3 us stream-K;
+// x16384: 176.9 vs 174.8; x3072: 60.4 vs 66.5.  The GPU is power-capped, so the pairs that sit out the last partial
+// wave are not lost throughput (the busy ones clock higher).  Correct and tested, therefore kept, but OFF by default.
+static std::atomic<int> g_sk_mode{0};    // 0 off (default), 1 cut tiles when the last wave is badly filled
+constexpr size_t kSkFlagBytes = 4096;
+constexpr int kSkMaxPairs = 80;
+size_t gemm_tc_streamk_workspace_bytes() { return kSkFlagBytes + (size_t)kSkMaxPairs * 2 * 256 * BM * sizeof(float); }
+void gemm_tc_set_streamk_workspace(void* ptr, size_t bytes) {
+  if (ptr && bytes >= gemm_tc_streamk_workspace_bytes()) {
+    g_sk_flags = reinterpret_cast<int*>(ptr);
+    g_sk_ws = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(ptr) + kSkFlagBytes);
+  } else {
+    g_sk_flags = nullptr; g_sk_ws = nullptr;
+  }
+}
+void gemm_tc_set_streamk_mode(int m) { g_sk_mode.store(m); }
+
+// how many CTA pairs can be co-resident (a pair needs two SMs of one TPC); every pair instantiation has the same
+// block size and shared-memory footprint, so one query serves all
+static int pair_capacity();
+
 template <bool TA, bool TB, int BN, int EPI, bool CTA2>
 static int launch_inst(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& a2, const CUtensorMap& b2,
                        const GemmTcParams& p, cudaStream_t st) {
   using Cfg = GemmCfg<BN, CTA2>;
   auto kern = gemm_tc_kernel<TA, TB, BN, EPI, CTA2>;
   static bool configured = false;
-  static int max_pairs = 0;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
     if (e != cudaSuccess) { set_error("gemm_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return CSM_ERR_CUDA; }
-    if (CTA2) {
-      // how many CTA pairs can be co-resident (a pair needs two SMs of one TPC): the persistent grid must not
-      // exceed it, or a late pair would start only after an early one has finished its whole share
-      cudaLaunchConfig_t q = {};
-      q.gridDim = dim3(148); q.blockDim = dim3(kGemmThreads); q.dynamicSmemBytes = Cfg::kSmemBytes;
-      cudaLaunchAttribute at[1];
-      at[0].id = cudaLaunchAttributeClusterDimension;
-      at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-      q.attrs = at; q.numAttrs = 1;
-      int n = 0;
-      e = cudaOccupancyMaxActiveClusters(&n, kern, &q);
-      if (e != cudaSuccess || n < 1) { cudaGetLastError(); n = num_sms() / 2 - 2; }
-      max_pairs = n;
-    }
     configured = true;
   }
+  const int max_pairs = CTA2 ? pair_capacity() : 0;
   if (!CTA2) {
     const int tiles = p.groups * p.num_m * p.num_n;
     const int grid = tiles < num_sms() ? tiles : num_sms();
@@ -648,6 +751,28 @@ static int launch_inst(const CUtensorMap& a, const CUtensorMap& b, const CUtenso
   }
   CSM_CHECK_LAUNCH("gemm_tc");
   return CSM_OK;
+}
+
+static int pair_capacity() {
+  static int cap = 0;
+  if (cap == 0) {
+    // the persistent grid must not exceed the co-resident cluster count, or a late pair would start only after an
+    // early one has finished its whole share (and a stream-K finisher could wait for a pair that is not running)
+    using Cfg = GemmCfg<256, true>;
+    auto kern = gemm_tc_kernel<false, false, 256, EPI_STORE, true>;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+    cudaLaunchConfig_t q = {};
+    q.gridDim = dim3(148); q.blockDim = dim3(kGemmThreads); q.dynamicSmemBytes = Cfg::kSmemBytes;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    q.attrs = at; q.numAttrs = 1;
+    int n = 0;
+    cudaError_t e = cudaOccupancyMaxActiveClusters(&n, kern, &q);
+    if (e != cudaSuccess || n < 1) { cudaGetLastError(); n = 70; }
+    cap = n;
+  }
+  return cap;
 }
 
 template <int BN, int EPI, bool CTA2>
@@ -679,6 +804,17 @@ int gemm_tc_run(const GemmTcOperands& o, GemmTcParams p, int epi, cudaStream_t s
               (mode == 1 || super256 >= 48);
   if (epi == EPI_SWIGLU_FWD) cta2 = true;                 // callers check gemm_tc_swiglu_supported()
   const int bn = (cta2 || epi == EPI_SWIGLU_BWD) ? 256 : choose_bn(p.groups, p.M, p.N);
+  if (cta2 && epi == EPI_STORE && p.groups == 1 && g_sk_ws && g_sk_mode.load() == 1) {
+    // stream-K when the tile count leaves the last wave badly filled (e.g. 128 super-tiles on 74 pairs = 1.73 waves)
+    const int cap = pair_capacity();
+    const int P = cap < num_sms() / 2 ? cap : num_sms() / 2;
+    const int64_t T = (int64_t)((p.num_m + 1) / 2) * ((p.N + 255) / 256);
+    const int64_t kb = (p.K + BK - 1) / BK + ((o.A2 && o.K2 > 0) ? 1 : 0);
+    const int64_t waves = (T + P - 1) / P;
+    if (T > P && P <= kSkMaxPairs && kb >= 8 && (double)T / (double)(waves * P) < 0.93) {
+      p.streamk = 1; p.sk_ws = g_sk_ws; p.sk_flags = g_sk_flags;
+    }
+  }
   const uint32_t b_box = cta2 ? (uint32_t)bn / 2 : (uint32_t)bn;
   p.num_n = epi == EPI_SWIGLU_FWD ? (int)((p.N + 127) / 128) : (int)((p.N + bn - 1) / bn);
   const uint64_t b_rows = epi == EPI_SWIGLU_FWD ? 2 * (uint64_t)p.N : (uint64_t)p.N;   // packed gate|up weight

@@ -154,6 +154,14 @@ void csm_set_attn_backend(int32_t backend);
 /* test hook: CTA-pair (tcgen05 cta_group::2, 256-row tiles) mode of the tensor-core GEMM. -1 = automatic (large
  * plain GEMMs only), 0 = never, 1 = whenever the shape allows it. */
 void csm_set_gemm_cta_pair_mode(int32_t mode);
+/* Stream-K scratch of the CTA-pair GEMM (fp32 partial tiles + self-resetting flags).  The caller allocates
+ * csm_gemm_streamk_workspace_bytes() bytes of ZEROED device memory once per device and registers it; with no workspace
+ * registered the GEMM never cuts tiles.  One buffer per device: GEMMs that may use it must be issued on one stream.
+ * csm_set_gemm_streamk_mode: 0 never cut tiles (default: no gain measured on a power-capped B200), 1 cut tiles when
+ * the last wave of whole tiles would be badly filled. */
+size_t csm_gemm_streamk_workspace_bytes(void);
+void csm_gemm_set_streamk_workspace(void* workspace, size_t bytes);
+void csm_set_gemm_streamk_mode(int32_t mode);
 /* Persistent kernels (GEMM, fused CE) size their grids for (SM count - n): leaves n SMs to a collective that runs
  * concurrently on another stream (data-parallel gradient all-reduce overlapped with backward).  Default 0. */
 void csm_set_reserved_sms(int32_t n);

@@ -202,6 +202,39 @@ def test_gemm_cta_pair_mode(ops, cuda, ta, tb, M, N, K):
         ops.set_gemm_cta_pair_mode(-1)
 
 
+@pytest.mark.parametrize("ta,tb", [(False, False), (False, True), (True, True)])
+@pytest.mark.parametrize("M,N,K", [(4096, 2048, 2048), (4096, 2048, 8192), (7424, 1024, 1000), (5000, 2304, 520)])
+def test_gemm_stream_k_matches_whole_tiles(ops, cuda, ta, tb, M, N, K):
+    """Tile counts that fill the last wave badly are dealt out by k-blocks (stream-K): a tile cut between two CTA pairs
+    is finished by one of them from the other's fp32 partial.  Same result as the whole-tile schedule, with residual,
+    alpha, accumulate and the LoRA extra K block; repeated launches re-arm the flags."""
+    g = torch.Generator().manual_seed(M + N + K)
+    def mk(r, c):
+        ld = (c + 7) // 8 * 8
+        return (torch.randn(r, ld, generator=g) * 0.5).to(BF).to(cuda)[:, :c]
+    a = mk(K, M) if ta else mk(M, K)
+    b = mk(K, N) if tb else mk(N, K)
+    res = mk(M, N)
+    ref = (a.float().t() if ta else a.float()) @ (b.float() if tb else b.float().t())
+    outs = {}
+    for mode in (0, 1):
+        ops.set_gemm_streamk_mode(mode)
+        try:
+            o1 = ops.gemm(a, b, trans_a=ta, trans_b=tb, backend=2)
+            o2 = ops.gemm(a, b, trans_a=ta, trans_b=tb, residual=res, alpha=0.5, backend=2)
+            o3 = ops.gemm(a, b, trans_a=ta, trans_b=tb, backend=2)          # flags re-armed by the first launch
+            outs[mode] = (o1, o2, o3)
+            if not ta and not tb:
+                t, lb = mk(M, 16), mk(N, 16)
+                o4 = ops.gemm(a, b, a2=t, b2=lb, backend=2)
+                assert rel_err(o4, ref + t.float() @ lb.float().t()) < 5e-3
+        finally:
+            ops.set_gemm_streamk_mode(0)
+        assert rel_err(o1, ref) < 5e-3 and rel_err(o3, ref) < 5e-3
+        assert rel_err(o2, 0.5 * ref + res.float()) < 5e-3
+    assert rel_err(outs[1][0], outs[0][0].float()) < 2e-3
+
+
 @pytest.mark.parametrize("M,I,K,r", [(4096, 1024, 512, 0), (2048, 2048, 256, 16), (1000, 8192, 1024, 8)])
 def test_gemm_swiglu_fused_matches_unfused(ops, cuda, M, I, K, r):
     """w1|w3 GEMM + SwiGLU in one launch (and w2 dgrad + SwiGLU backward in one) equal the unfused kernel pairs."""
