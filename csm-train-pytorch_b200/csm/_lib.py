@@ -29,6 +29,7 @@ SIGNATURES = {
     "csm_rmsnorm_bwd": (_i32, [_ptr] * 7 + [_i64, _i32, _ptr]),
     "csm_rope": (_i32, [_ptr, _ptr, _i64, _i32, _i32, _i32, _i64, _i32, _ptr]),
     "csm_gemm_bf16": (_i32, [_ptr] * 4 + [_i64] * 7 + [_i32] * 4 + [_f32, _ptr, _ptr, _i64, _i64, _i64, _i32, _ptr]),
+    "csm_gemm_bf16_rope": (_i32, [_ptr] * 3 + [_i64] * 6 + [_ptr, _ptr, _i64, _i64, _i64, _ptr, _i32, _i32, _i32, _ptr]),
     "csm_gemm_splitk_workspace_bytes": (_sz, [_i64, _i64, _i32]),
     "csm_gemm_bf16_splitk": (_i32, [_ptr] * 3 + [_i64] * 6 + [_i32, _i32, _f32, _i32, _ptr, _sz, _ptr]),
     "csm_gemm_swiglu_supported": (_i32, [_i64, _i64, _i64]),
@@ -45,6 +46,7 @@ SIGNATURES = {
     "csm_set_gemm_streamk_mode": (None, [_i32]),
     "csm_attn_bwd_workspace_bytes": (_sz, [_i32] * 5),
     "csm_attn_causal_gqa_bwd": (_i32, [_ptr] * 9 + [_i32] * 5 + [_i64] * 7 + [_f32, _ptr, _sz, _ptr]),
+    "csm_attn_causal_gqa_bwd_rope": (_i32, [_ptr] * 9 + [_i32] * 5 + [_i64] * 7 + [_f32, _ptr, _ptr, _sz, _ptr]),
     "csm_linear_ce_workspace_bytes": (_sz, [_i64, _i64, _i64, _i32]),
     "csm_linear_ce_fwd": (_i32, [_ptr] * 5 + [_i64] * 3 + [_i32] + [_i64] * 4 + [_i32, _i64, _i64, _ptr, _sz, _i32, _ptr]),
     "csm_linear_ce_bwd": (_i32, [_ptr] * 4 + [_f32, _ptr, _ptr, _ptr, _i32] + [_i64] * 3 + [_i32] + [_i64] * 4 +

@@ -194,11 +194,13 @@ class _Group:
     def _t(self, x):
         return ops.gemm(x, self.A_cat, alpha=self.s if self.s is not None else 1.0)             # [N, R]
 
-    def fwd(self, x):
-        if not self.lora:
-            return ops.gemm(x, self.W), None
-        t = self._t(x)
-        return ops.gemm(x, self.W, a2=t, b2=self.B_bd), t
+    def fwd(self, x, rope=None):
+        """rope = (cache, seq_len, rope_cols, head_dim): rotate the leading columns in the GEMM's store epilogue."""
+        t = self._t(x) if self.lora else None
+        b2 = self.B_bd if self.lora else None
+        if rope is not None:
+            return ops.gemm_rope(x, self.W, *rope, a2=t, b2=b2), t
+        return ops.gemm(x, self.W, a2=t, b2=b2), t
 
     def fwd_swiglu(self, x):
         """gate/up group only: (gate|up, act = silu(gate) * up, t) with the SwiGLU in the GEMM epilogue."""
@@ -257,9 +259,8 @@ class StackFn(Function):
             lo, l2 = _Lin(a.output_proj, index_of), _Lin(layer.mlp.w2, index_of)
             I = layer.mlp.w1.weight.shape[0]
             xn, rstd1 = ops.rmsnorm(cur, layer.sa_norm.scale, eps)
-            qkv, tqkv = gqkv.fwd(xn)
+            qkv, tqkv = gqkv.fwd(xn, rope=(cache, S, nq + nkv, hd))   # q and k heads rotated in the store epilogue
             q, k, v = qkv[:, :nq], qkv[:, nq:nq + nkv], qkv[:, nq + nkv:]
-            ops.rope_(qkv[:, :nq + nkv], cache, S, H + KV, hd)     # q and k heads are adjacent columns: one launch
             o, lse = ops.attention_fwd(q, k, v, B, S, H, KV, hd)
             h, to = lo.fwd(o, residual=cur)
             hn, rstd2 = ops.rmsnorm(h, layer.mlp_norm.scale, eps)
@@ -335,8 +336,8 @@ class StackFn(Function):
             q, k, v = qkv[:, :nq], qkv[:, nq:nq + nkv], qkv[:, nq + nkv:]
             dqkv = torch.empty_like(qkv)
             dq, dk, dv = dqkv[:, :nq], dqkv[:, nq:nq + nkv], dqkv[:, nq + nkv:]
-            ops.attention_bwd(q, k, v, o, lse, do, B, S, H, KV, hd, dq=dq, dk=dk, dv=dv)
-            ops.rope_(dqkv[:, :nq + nkv], cache, S, H + KV, hd, inverse=True)
+            # (the inverse RoPE of dq / dk happens in the attention kernels' store epilogues when they can)
+            ops.attention_bwd(q, k, v, o, lse, do, B, S, H, KV, hd, dq=dq, dk=dk, dv=dv, rope_cache=cache)
             dxn = gqkv.bwd(dqkv, xn, tqkv, grads, need)
             dcur = norm_bwd(dxn, x, layer.sa_norm, rstd1, dh)
             hand_over(layer)

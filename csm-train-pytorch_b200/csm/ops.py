@@ -44,8 +44,13 @@ def set_gemm_cta_pair_mode(m: int) -> None:
     _lib.load().csm_set_gemm_cta_pair_mode(m)
 
 
+_attn_backend = 0
+
+
 def set_attn_backend(b: int) -> None:
     """Test hook: 0 auto, 1 scalar, 2 mma.sync, 3 tcgen05, 4 short-sequence (seq <= 32)."""
+    global _attn_backend
+    _attn_backend = b
     _lib.load().csm_set_attn_backend(b)
 
 
@@ -205,6 +210,35 @@ def _splitk_choice(M: int, N: int, K: int) -> int:
 
 
 
+def gemm_rope(a, b, cache, seq_len: int, rope_cols: int, head_dim: int, *, a2=None, b2=None):
+    """out = a @ b^T (+ a2 @ b2^T) with RoPE applied to columns [0, rope_cols) (heads of head_dim, position = row %
+    seq_len): the fused q|k|v projection.  One launch when the tcgen05 GEMM takes the shape, else gemm + rope."""
+    M, K = a.shape
+    N = b.shape[0]
+    be = _backend_override
+    fused = (be != GEMM_SIMT and N % 32 == 0 and K >= 64 and M * N * K >= (1 << 21) and a.stride(1) == 1
+             and b.stride(1) == 1 and a.stride(0) % 8 == 0 and b.stride(0) % 8 == 0)
+    if not fused:
+        out = gemm(a, b, a2=a2, b2=b2)
+        rope_(out[:, :rope_cols], cache, seq_len, rope_cols // head_dim, head_dim)
+        return out
+    _ensure_streamk_workspace(a.device)
+    out = torch.empty(M, N, dtype=BF16, device=a.device)
+    K2 = a2.shape[1] if a2 is not None else 0
+    lib = _lib.load()
+    if _gemm_prof is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+    _lib.check(lib.csm_gemm_bf16_rope(_p(a), _p(b), _p(out), M, N, K, a.stride(0), b.stride(0), out.stride(0), _p(a2),
+                                      _p(b2), K2, a2.stride(0) if a2 is not None else 0,
+                                      b2.stride(0) if b2 is not None else 0, _p(cache), seq_len, rope_cols, head_dim,
+                                      _st()), "gemm_bf16_rope")
+    if _gemm_prof is not None:
+        e1.record()
+        _gemm_prof.append((2.0 * M * N * (K + K2), e0, e1))
+    return out
+
+
 def gemm(a, b, *, trans_a: bool = False, trans_b: bool = False, out: Optional[torch.Tensor] = None,
          residual: Optional[torch.Tensor] = None, accumulate: bool = False, alpha: float = 1.0,
          a2: Optional[torch.Tensor] = None, b2: Optional[torch.Tensor] = None, out_dtype=BF16,
@@ -319,7 +353,10 @@ def attention_fwd(q, k, v, batch: int, seq: int, heads: int, kv_heads: int, head
     return o, lse
 
 
-def attention_bwd(q, k, v, o, lse, dout, batch, seq, heads, kv_heads, head_dim, dq=None, dk=None, dv=None):
+def attention_bwd(q, k, v, o, lse, dout, batch, seq, heads, kv_heads, head_dim, dq=None, dk=None, dv=None,
+                  rope_cache=None):
+    """With `rope_cache` the returned dq / dk are gradients w.r.t. the UN-rotated projections (inverse RoPE applied):
+    inside the tcgen05 kernels' store epilogues when they take the shape, else by the rope kernel afterwards."""
     dev = q.device
     dq = torch.empty(batch * seq, heads * head_dim, dtype=BF16, device=dev) if dq is None else dq
     dk = torch.empty(batch * seq, kv_heads * head_dim, dtype=BF16, device=dev) if dk is None else dk
@@ -327,10 +364,22 @@ def attention_bwd(q, k, v, o, lse, dout, batch, seq, heads, kv_heads, head_dim, 
     lib = _lib.load()
     nbytes = lib.csm_attn_bwd_workspace_bytes(batch, seq, heads, kv_heads, head_dim)
     ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    fuse = (rope_cache is not None and head_dim == 64 and seq >= 128 and _attn_backend in (0, 3)
+            and all(t.stride(0) % 8 == 0 and t.data_ptr() % 16 == 0 for t in (q, k, v, o, dq, dk, dv, dout)))
+    if fuse:
+        _lib.check(lib.csm_attn_causal_gqa_bwd_rope(_p(q), _p(k), _p(v), _p(o), _p(lse), _p(dout), _p(dq), _p(dk),
+                                                    _p(dv), batch, seq, heads, kv_heads, head_dim, q.stride(0),
+                                                    k.stride(0), v.stride(0), o.stride(0), dq.stride(0), dk.stride(0),
+                                                    dv.stride(0), 1.0 / math.sqrt(head_dim), _p(rope_cache), _p(ws),
+                                                    nbytes, _st()), "attn_bwd_rope")
+        return dq, dk, dv
     _lib.check(lib.csm_attn_causal_gqa_bwd(_p(q), _p(k), _p(v), _p(o), _p(lse), _p(dout), _p(dq), _p(dk), _p(dv),
                                            batch, seq, heads, kv_heads, head_dim, q.stride(0), k.stride(0),
                                            v.stride(0), o.stride(0), dq.stride(0), dk.stride(0), dv.stride(0),
                                            1.0 / math.sqrt(head_dim), _p(ws), nbytes, _st()), "attn_bwd")
+    if rope_cache is not None:
+        rope_(dq, rope_cache, seq, heads, head_dim, inverse=True)
+        rope_(dk, rope_cache, seq, kv_heads, head_dim, inverse=True)
     return dq, dk, dv
 
 

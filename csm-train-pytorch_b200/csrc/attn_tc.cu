@@ -316,7 +316,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1)
 attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                       const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmDO,
                       const float* __restrict__ lse, const float* __restrict__ delta, bf16* __restrict__ dq, int S,
-                      int H, int KV, int64_t lddq, float scale) {
+                      int H, int KV, int64_t lddq, float scale, const float* __restrict__ rope_cache) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + DQ_BAR);
@@ -461,12 +461,14 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
         bf16* dp_ = dq + ((int64_t)b * S + qi) * lddq + (int64_t)h * THD + half * 32;
 #pragma unroll
         for (int c = 0; c < 32; c += 8) {
-          uint4 w;
-          w.x = pack_bf16(__uint_as_float(v[c + 0]), __uint_as_float(v[c + 1]));
-          w.y = pack_bf16(__uint_as_float(v[c + 2]), __uint_as_float(v[c + 3]));
-          w.z = pack_bf16(__uint_as_float(v[c + 4]), __uint_as_float(v[c + 5]));
-          w.w = pack_bf16(__uint_as_float(v[c + 6]), __uint_as_float(v[c + 7]));
-          *reinterpret_cast<uint4*>(dp_ + c) = w;
+          uint32_t w[4];
+          w[0] = pack_bf16(__uint_as_float(v[c + 0]), __uint_as_float(v[c + 1]));
+          w[1] = pack_bf16(__uint_as_float(v[c + 2]), __uint_as_float(v[c + 3]));
+          w[2] = pack_bf16(__uint_as_float(v[c + 4]), __uint_as_float(v[c + 5]));
+          w[3] = pack_bf16(__uint_as_float(v[c + 6]), __uint_as_float(v[c + 7]));
+          // gradient w.r.t. the un-rotated q: the inverse rotation of the (bf16) gradient, as csm_rope(inverse) would do
+          if (rope_cache) rope_rotate8(w, rope_cache + (int64_t)qi * THD, (half * 32 + c) >> 1, -1.f);
+          *reinterpret_cast<uint4*>(dp_ + c) = make_uint4(w[0], w[1], w[2], w[3]);
         }
       }
     }
@@ -493,7 +495,8 @@ __global__ void __launch_bounds__(kBwdThreads, 1)
 attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                         const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmDO,
                         const float* __restrict__ lse, const float* __restrict__ delta, bf16* __restrict__ dk,
-                        bf16* __restrict__ dv, int S, int H, int KV, int64_t lddk, int64_t lddv, float scale) {
+                        bf16* __restrict__ dv, int S, int H, int KV, int64_t lddk, int64_t lddv, float scale,
+                        const float* __restrict__ rope_cache) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + DK_BAR);
@@ -676,12 +679,13 @@ attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
       if (kj < S) {
 #pragma unroll
         for (int c8 = 0; c8 < 32; c8 += 8) {
-          uint4 w;
-          w.x = pack_bf16(__uint_as_float(v[c8 + 0]), __uint_as_float(v[c8 + 1]));
-          w.y = pack_bf16(__uint_as_float(v[c8 + 2]), __uint_as_float(v[c8 + 3]));
-          w.z = pack_bf16(__uint_as_float(v[c8 + 4]), __uint_as_float(v[c8 + 5]));
-          w.w = pack_bf16(__uint_as_float(v[c8 + 6]), __uint_as_float(v[c8 + 7]));
-          *reinterpret_cast<uint4*>(outp + c + c8) = w;
+          uint32_t w[4];
+          w[0] = pack_bf16(__uint_as_float(v[c8 + 0]), __uint_as_float(v[c8 + 1]));
+          w[1] = pack_bf16(__uint_as_float(v[c8 + 2]), __uint_as_float(v[c8 + 3]));
+          w[2] = pack_bf16(__uint_as_float(v[c8 + 4]), __uint_as_float(v[c8 + 5]));
+          w[3] = pack_bf16(__uint_as_float(v[c8 + 6]), __uint_as_float(v[c8 + 7]));
+          if (rope_cache && half == 0) rope_rotate8(w, rope_cache + (int64_t)kj * THD, (c + c8) >> 1, -1.f);   // dK only
+          *reinterpret_cast<uint4*>(outp + c + c8) = make_uint4(w[0], w[1], w[2], w[3]);
         }
       }
     }
@@ -726,7 +730,8 @@ int attn_delta_launch(const void* o, const void* dout, float* delta, int B, int 
 
 int attn_bwd_tc_launch(const void* q, const void* k, const void* v, const void* o, const float* lse, const void* dout,
                        void* dq, void* dk, void* dv, float* delta, int B, int S, int H, int KV, int64_t ldq, int64_t ldk,
-                       int64_t ldv, int64_t ldo, int64_t lddq, int64_t lddk, int64_t lddv, float scale, cudaStream_t st) {
+                       int64_t ldv, int64_t ldo, int64_t lddq, int64_t lddk, int64_t lddv, float scale,
+                       const float* rope_cache, cudaStream_t st) {
   CSM_REQUIRE(aligned16(dout) && aligned16(dq) && aligned16(dk) && aligned16(dv) && lddq % 8 == 0 && lddk % 8 == 0 &&
                   lddv % 8 == 0,
               CSM_ERR_ALIGN, "attn_bwd_tc: misaligned gradient buffers");
@@ -746,11 +751,12 @@ int attn_bwd_tc_launch(const void* q, const void* k, const void* v, const void* 
     configured = true;
   }
   dim3 gq(((S + TQ - 1) / TQ) * H * B);
-  attn_bwd_dq_tc_kernel<<<gq, kBwdThreads, kDqSmem, st>>>(tq, tk, tv, tdo, lse, delta, (bf16*)dq, S, H, KV, lddq, scale);
+  attn_bwd_dq_tc_kernel<<<gq, kBwdThreads, kDqSmem, st>>>(tq, tk, tv, tdo, lse, delta, (bf16*)dq, S, H, KV, lddq, scale,
+                                                          rope_cache);
   CSM_CHECK_LAUNCH("attn_bwd_dq_tc");
   dim3 gk(((S + TK - 1) / TK) * KV * B);
   attn_bwd_dkdv_tc_kernel<<<gk, kBwdThreads, kDkSmem, st>>>(tq, tk, tv, tdo, lse, delta, (bf16*)dk, (bf16*)dv, S, H, KV,
-                                                            lddk, lddv, scale);
+                                                            lddk, lddv, scale, rope_cache);
   CSM_CHECK_LAUNCH("attn_bwd_dkdv_tc");
   return CSM_OK;
 }

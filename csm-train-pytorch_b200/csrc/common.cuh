@@ -59,6 +59,22 @@ __device__ __forceinline__ float warp_max(float v) {
   return v;
 }
 
+// Llama3ScaledRoPE on 8 consecutive bf16 of one head (4 interleaved pairs (x[2j], x[2j+1]), first pair index jg):
+// `cache_pos` points at the [head_dim/2][cos, sin] fp32 row of this position.  Separate roundings (no FMA
+// contraction): bit-identical to the fp32 torch formula and to rope_kernel; sgn = -1 gives the inverse rotation.
+__device__ __forceinline__ void rope_rotate8(uint32_t* w, const float* cache_pos, int jg, float sgn) {
+  const float4 c01 = *reinterpret_cast<const float4*>(cache_pos + jg * 2);
+  const float4 c23 = *reinterpret_cast<const float4*>(cache_pos + jg * 2 + 4);
+  const float co[4] = {c01.x, c01.z, c23.x, c23.z};
+  const float si[4] = {c01.y * sgn, c01.w * sgn, c23.y * sgn, c23.w * sgn};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float x0 = bf16_lo(w[j]), x1 = bf16_hi(w[j]);
+    w[j] = pack_bf16(__fsub_rn(__fmul_rn(x0, co[j]), __fmul_rn(x1, si[j])),
+                     __fadd_rn(__fmul_rn(x1, co[j]), __fmul_rn(x0, si[j])));
+  }
+}
+
 // 16-byte streaming load that does not pollute L1 (read-once data)
 __device__ __forceinline__ uint4 ld_nc16(const void* p) {
   uint4 r;

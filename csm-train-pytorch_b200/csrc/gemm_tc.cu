@@ -41,6 +41,9 @@ struct GemmTcParams {
   void* C2; int64_t ldc2; int64_t inter;
   // stream-K (CTA-pair EPI_STORE only): the tiles' k-blocks are dealt out evenly to the pairs; a tile cut between two
   // pairs is finished by the pair that owns its last k-block, which adds the other pair's fp32 partial (sk_ws) first
+  // RoPE in the store epilogue (fused q|k|v projection): columns [0, rope_cols) are heads of rope_hd that get rotated
+  // by the position row % rope_seq; the linear output is rounded to bf16 first, as the unfused rope kernel would read it
+  const float* rope_cache; int rope_seq, rope_cols, rope_hd;
   int streamk;
   float* sk_ws;             // [pairs][2 CTAs][BN cols][128 rows] fp32
   int* sk_flags;            // [pairs][2 CTAs][2]: partial-ready count, readers-done count (self-resetting)
@@ -400,6 +403,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               }
               w[q * 4 + 0] = pack_bf16(f8[0], f8[1]); w[q * 4 + 1] = pack_bf16(f8[2], f8[3]);
               w[q * 4 + 2] = pack_bf16(f8[4], f8[5]); w[q * 4 + 3] = pack_bf16(f8[6], f8[7]);
+              if (p.rope_cache && n + q * 8 < p.rope_cols && row_ok)
+                rope_rotate8(w + q * 4, p.rope_cache + (int64_t)(m % p.rope_seq) * p.rope_hd,
+                             (int)((n + q * 8) % p.rope_hd) >> 1, 1.f);
             }
             store_tile_32x32(stage_s, reinterpret_cast<bf16*>(p.C) + (int64_t)g * p.c_group_stride + wm0 * p.ldc + n,
                              p.ldc, lane, w, wrows);
@@ -871,16 +877,26 @@ bool gemm_tc_supported(const void* A, const void* B, const void* C, const void* 
   return true;
 }
 
-int gemm_tc_launch(const void* A, const void* B, void* C, const void* R, int64_t M, int64_t N, int64_t K,
-                   int64_t lda, int64_t ldb, int64_t ldc, int64_t ldr, int transA, int transB, int c_dtype,
-                   int accumulate, float alpha, const void* A2, const void* B2, int64_t K2, int64_t lda2,
-                   int64_t ldb2, cudaStream_t stream) {
+int gemm_tc_launch_rope(const void* A, const void* B, void* C, const void* R, int64_t M, int64_t N, int64_t K,
+                        int64_t lda, int64_t ldb, int64_t ldc, int64_t ldr, int transA, int transB, int c_dtype,
+                        int accumulate, float alpha, const void* A2, const void* B2, int64_t K2, int64_t lda2,
+                        int64_t ldb2, const float* rope_cache, int rope_seq, int rope_cols, int rope_hd,
+                        cudaStream_t stream) {
   GemmTcOperands o{A, B, A2, B2, lda, ldb, lda2, ldb2, K2, 0, 0, transA, transB};
   GemmTcParams p{};
   p.M = M; p.N = N; p.K = K; p.groups = 1;
   p.C = C; p.R = (const bf16*)R; p.ldc = ldc; p.ldr = ldr;
   p.c_f32 = (c_dtype == CSM_DT_F32); p.accumulate = accumulate; p.alpha = alpha;
+  p.rope_cache = rope_cache; p.rope_seq = rope_seq; p.rope_cols = rope_cols; p.rope_hd = rope_hd;
   return gemm_tc_run(o, p, EPI_STORE, stream);
+}
+
+int gemm_tc_launch(const void* A, const void* B, void* C, const void* R, int64_t M, int64_t N, int64_t K,
+                   int64_t lda, int64_t ldb, int64_t ldc, int64_t ldr, int transA, int transB, int c_dtype,
+                   int accumulate, float alpha, const void* A2, const void* B2, int64_t K2, int64_t lda2,
+                   int64_t ldb2, cudaStream_t stream) {
+  return gemm_tc_launch_rope(A, B, C, R, M, N, K, lda, ldb, ldc, ldr, transA, transB, c_dtype, accumulate, alpha, A2, B2,
+                             K2, lda2, ldb2, nullptr, 0, 0, 0, stream);
 }
 
 // ------------------------------------------------------------------------------------------- fused SwiGLU MLP

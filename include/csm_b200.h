@@ -112,6 +112,15 @@ int csm_adamw_clip_step(void* const* params, const void* const* grads, void* con
                         const int64_t* numel, const float* lr, const float* weight_decay, int32_t n_tensors, float beta1,
                         float beta2, float eps, float max_norm, float* step_dev, float* sq_norm_dev, csm_stream_t stream);
 
+/* ---- fused q|k|v projection + RoPE: C[M,N] = A[M,K] B[N,K]^T (+ A2 B2^T), then columns [0, rope_cols) — heads of
+ * head_dim — are rotated by position (row % seq_len) exactly as csm_rope would (bf16 rounding of the projection first).
+ * N must be a multiple of 32; returns CSM_ERR_SHAPE for shapes the tcgen05 GEMM does not take (then: csm_gemm_bf16 +
+ * csm_rope). */
+int csm_gemm_bf16_rope(const void* A, const void* B, void* C, int64_t M, int64_t N, int64_t K, int64_t lda, int64_t ldb,
+                       int64_t ldc, const void* A2, const void* B2, int64_t K2, int64_t lda2, int64_t ldb2,
+                       const float* rope_cache, int32_t seq_len, int32_t rope_cols, int32_t head_dim,
+                       csm_stream_t stream);
+
 /* ---- skinny GEMM with a long reduction (LoRA t = x A^T, dA = dt^T x, dB = dy^T t): same operand conventions as
  * csm_gemm_bf16 (no residual / tail / accumulate), C bf16 = alpha * op(A) op(B).  The reduction is split into `splits`
  * groups computed by separate CTAs (fp32 partials in `workspace`, csm_gemm_splitk_workspace_bytes()) and summed by a
@@ -173,6 +182,15 @@ int csm_attn_causal_gqa_bwd(const void* q, const void* k, const void* v, const v
                             int32_t heads, int32_t kv_heads, int32_t head_dim, int64_t ldq, int64_t ldk,
                             int64_t ldv, int64_t ldo, int64_t lddq, int64_t lddk, int64_t lddv, float scale,
                             void* workspace, size_t workspace_bytes, csm_stream_t stream);
+/* Same, returning the gradients w.r.t. the UN-rotated q and k: the inverse RoPE (rope_cache: fp32
+ * [seq][head_dim/2][cos, sin], position = row within the sequence) is applied to the bf16 dq / dk in the kernels'
+ * store epilogues, exactly as csm_rope(inverse=1) would afterwards.  tcgen05 kernels only (head_dim 64, seq >= 128);
+ * CSM_ERR_SHAPE otherwise (then: csm_attn_causal_gqa_bwd + csm_rope). */
+int csm_attn_causal_gqa_bwd_rope(const void* q, const void* k, const void* v, const void* o, const float* lse,
+                                 const void* dout, void* dq, void* dk, void* dv, int32_t batch, int32_t seq,
+                                 int32_t heads, int32_t kv_heads, int32_t head_dim, int64_t ldq, int64_t ldk, int64_t ldv,
+                                 int64_t ldo, int64_t lddq, int64_t lddk, int64_t lddv, float scale,
+                                 const float* rope_cache, void* workspace, size_t workspace_bytes, csm_stream_t stream);
 
 /* ---- codebook0_head + F.cross_entropy (utils.py:98-107) and audio_head[i-1] + CE (model.py:187, A7)
  * `groups` independent heads g: logits_g = H_g[M,K] * W_g; loss_rows[g*M+m] = lse - logit[target];

@@ -202,6 +202,24 @@ def test_gemm_cta_pair_mode(ops, cuda, ta, tb, M, N, K):
         ops.set_gemm_cta_pair_mode(-1)
 
 
+@pytest.mark.parametrize("M,N,K,S,hd,cols,r", [(4096, 3072, 2048, 2048, 64, 2560, 16), (928, 1536, 1024, 32, 128, 1280, 0),
+                                                 (256, 384, 256, 128, 64, 320, 8)])
+def test_gemm_rope_epilogue_bit_exact(ops, cuda, M, N, K, S, hd, cols, r):
+    """q|k|v projection with RoPE in the store epilogue == projection followed by the rope kernel, bit for bit
+    (CTA-pair and single-CTA tiles, with and without the LoRA extra K block)."""
+    from csm.models.rope import build_rope_cache
+    g = torch.Generator().manual_seed(M + N)
+    mk = lambda a, b, sc=1.0: (torch.randn(a, b, generator=g) * sc).to(BF).to(cuda)
+    x, w = mk(M, K), mk(N, K, K ** -0.5)
+    t, lb = (mk(M, r, 0.1), mk(N, r, 0.1)) if r else (None, None)
+    cache = build_rope_cache(hd, S, 500000.0, 32.0).to(cuda)
+    fused = ops.gemm_rope(x, w, cache, S, cols, hd, a2=t, b2=lb)
+    ref = ops.gemm(x, w, a2=t, b2=lb)
+    assert torch.equal(fused[:, cols:], ref[:, cols:])
+    ops.rope_(ref[:, :cols], cache, S, cols // hd, hd)
+    assert torch.equal(fused, ref)
+
+
 @pytest.mark.parametrize("ta,tb", [(False, False), (False, True), (True, True)])
 @pytest.mark.parametrize("M,N,K", [(4096, 2048, 2048), (4096, 2048, 8192), (7424, 1024, 1000), (5000, 2304, 520)])
 def test_gemm_stream_k_matches_whole_tiles(ops, cuda, ta, tb, M, N, K):
@@ -342,6 +360,23 @@ def test_attention_short_sequence_kernel(ops, cuda, B, S, H, KV, hd):
         _attention_case(ops, cuda, B, S, H, KV, hd)
     finally:
         ops.set_attn_backend(0)
+
+
+@pytest.mark.parametrize("B,S,H,KV", [(2, 256, 8, 2), (1, 300, 4, 1), (2, 2048, 32, 8)])
+def test_attention_bwd_fused_inverse_rope_bit_exact(ops, cuda, B, S, H, KV):
+    """tcgen05 backward with the inverse RoPE in the dq / dk store epilogues == backward followed by csm_rope(inverse)."""
+    from csm.models.rope import build_rope_cache
+    hd = 64
+    g = torch.Generator().manual_seed(S)
+    mk = lambda c: torch.randn(B * S, c, generator=g).to(BF).to(cuda)
+    q, k, v, do = mk(H * hd), mk(KV * hd), mk(KV * hd), mk(H * hd)
+    cache = build_rope_cache(hd, S, 500000.0, 32.0).to(cuda)
+    o, lse = ops.attention_fwd(q, k, v, B, S, H, KV, hd)
+    dq0, dk0, dv0 = ops.attention_bwd(q, k, v, o, lse, do, B, S, H, KV, hd)
+    ops.rope_(dq0, cache, S, H, hd, inverse=True)
+    ops.rope_(dk0, cache, S, KV, hd, inverse=True)
+    dq1, dk1, dv1 = ops.attention_bwd(q, k, v, o, lse, do, B, S, H, KV, hd, rope_cache=cache)
+    assert torch.equal(dq0, dq1) and torch.equal(dk0, dk1) and torch.equal(dv0, dv1)
 
 
 def _attention_case(ops, cuda, B, S, H, KV, hd):
