@@ -23,6 +23,10 @@ for _p in (ROOT, PKG):
     if _p not in sys.path:
         sys.path.insert(0, _p)
 
+# NCCL announces its version on STDOUT at NCCL_DEBUG=VERSION (what some launchers export): the driver reads one JSON line
+if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+    os.environ["NCCL_DEBUG"] = "WARN"
+
 import torch  # noqa: E402
 
 METRIC = "CSM-1B train-step audio frames/sec"
