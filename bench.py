@@ -23,9 +23,9 @@ for _p in (ROOT, PKG):
     if _p not in sys.path:
         sys.path.insert(0, _p)
 
-# NCCL announces its version on STDOUT at NCCL_DEBUG=VERSION (what some launchers export): the driver reads one JSON line
-if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-    os.environ["NCCL_DEBUG"] = "WARN"
+# NCCL writes its banner / debug lines to STDOUT when NCCL_DEBUG is VERSION or above (what some launchers export);
+# the driver reads one JSON line from stdout, so NCCL's output goes to stderr
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 
 import torch  # noqa: E402
 

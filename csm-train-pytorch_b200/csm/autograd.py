@@ -23,23 +23,36 @@ FUSE_SWIGLU_BWD = False
 
 # ----------------------------------------------------------------------------- A2: embedding gather-sum
 class EmbedGatherSumFn(Function):
-    """model.py:206-217 + utils.py:85-87 in one kernel."""
+    """model.py:206-217 + utils.py:85-87 in one kernel.
+
+    `text_exchange` (data-parallel full fine-tune, csm/training/dp.py): the text-embedding gradient touches at most one
+    row per frame, so instead of all-reducing the dense [128256, 2048] table the ranks all-gather (tokens, mask, dh) and
+    every rank scatters ALL ranks' rows into its own dense gradient — the same scatter kernel, ~17 MB per rank on the
+    wire instead of 525 MB."""
 
     @staticmethod
-    def forward(ctx, tokens, mask, audio_w, text_w):
+    def forward(ctx, tokens, mask, audio_w, text_w, text_exchange=None):
         ctx.save_for_backward(tokens, mask)
         ctx.shapes = (audio_w.shape, text_w.shape, tokens.shape[-1] - 1)
+        ctx.text_exchange = text_exchange
         return ops.embed_gather_sum(tokens, mask, audio_w, text_w)
 
     @staticmethod
     def backward(ctx, dh):
         tokens, mask = ctx.saved_tensors
         ashape, tshape, C = ctx.shapes
+        dh = dh.contiguous()
         da = torch.zeros(ashape, dtype=BF16, device=dh.device) if ctx.needs_input_grad[2] else None
-        dt = torch.zeros(tshape, dtype=BF16, device=dh.device) if ctx.needs_input_grad[3] else None
-        if da is not None or dt is not None:
-            ops.embed_gather_sum_bwd(tokens, mask, dh.contiguous(), da, dt, ashape[0] // C, tshape[0])
-        return None, None, da, dt
+        dt = None
+        if ctx.needs_input_grad[3]:
+            if ctx.text_exchange is not None:
+                dt = ctx.text_exchange(tokens, mask, dh, tshape)        # dense, already averaged over the ranks
+            else:
+                dt = torch.zeros(tshape, dtype=BF16, device=dh.device)
+        local_dt = dt if ctx.text_exchange is None else None
+        if da is not None or local_dt is not None:
+            ops.embed_gather_sum_bwd(tokens, mask, dh, da, local_dt, ashape[0] // C, tshape[0])
+        return None, None, da, dt, None
 
 
 # ----------------------------------------------------------------------------- A7: decoder input gather

@@ -228,7 +228,8 @@ class Model(nn.Module):
     # ---- B200 training forward ---------------------------------------------------------------
     def embed(self, tokens: torch.Tensor, tokens_mask: torch.Tensor) -> torch.Tensor:
         """A2: fused gather + mask + 33-way sum -> bf16 [B,S,D]."""
-        return EmbedGatherSumFn.apply(tokens, tokens_mask, self.audio_embeddings.weight, self.text_embeddings.weight)
+        return EmbedGatherSumFn.apply(tokens, tokens_mask, self.audio_embeddings.weight, self.text_embeddings.weight,
+                                      getattr(self, "_text_grad_exchange", None))
 
     def _audio_head_t(self) -> torch.Tensor:
         """[31, V, Dd] shadow of audio_head [31, Dd, V] (rows of V=2051 bf16 are not 16-byte aligned, so the native

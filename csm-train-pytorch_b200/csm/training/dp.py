@@ -43,11 +43,18 @@ class GradSynchronizer:
     """
 
     def __init__(self, params: Iterable[torch.nn.Parameter], bucket_bytes: Optional[int] = None, group=None,
-                 force_buckets: bool = False):
+                 force_buckets: bool = False, sparse_rows: Optional[torch.nn.Parameter] = None):
+        """`sparse_rows`: a parameter (the text-embedding table) whose gradient is exchanged as gathered rows by
+        ``exchange_text_rows`` from inside the embedding backward; it is kept out of the all-reduce buckets."""
         self.params: List[torch.nn.Parameter] = [p for p in params if p.requires_grad]
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.group = group
         self.bucketed = bool(bucket_bytes) and (self.world > 1 or force_buckets)
+        self.sparse_param = None
+        if self.bucketed and self.world > 1 and sparse_rows is not None and sparse_rows.requires_grad and \
+                sparse_rows.is_cuda and os.environ.get("CSM_DP_DENSE_TEXT_GRAD", "0") != "1":
+            self.sparse_param = sparse_rows
+            self.params = [p for p in self.params if p is not sparse_rows]
         self.accumulating = False            # True on all but the last micro-batch of an accumulation window
         self._hooks = []
         if not self.bucketed:
@@ -141,6 +148,27 @@ class GradSynchronizer:
         g = p.grad
         p.grad = None
         self._store(p, g)
+
+    # ------------------------------------------------------------------ row-sparse text-embedding gradient
+    def exchange_text_rows(self, tokens, mask, dh, table_shape) -> torch.Tensor:
+        """Called by EmbedGatherSumFn.backward: returns the dense, rank-averaged text-embedding gradient.
+        Every rank contributes (tokens [B,S,C+1], mask [B,S,C+1], dh [B,S,D]); after the all-gathers each rank runs
+        the embedding scatter kernel over all ranks' frames (text column only).  Fixed shapes: graph-capturable."""
+        from .. import ops
+        W = self.world
+        dt = torch.zeros(table_shape, dtype=dh.dtype, device=dh.device)   # fresh: autograd may adopt it as .grad
+        msk = mask.contiguous().view(torch.uint8) if mask.dtype == torch.bool else mask.to(torch.uint8).contiguous()
+        tok_all = torch.empty((W,) + tuple(tokens.shape), dtype=tokens.dtype, device=tokens.device)
+        msk_all = torch.empty((W,) + tuple(msk.shape), dtype=torch.uint8, device=tokens.device)
+        dh_all = torch.empty((W,) + tuple(dh.shape), dtype=dh.dtype, device=dh.device)
+        dist.all_gather_into_tensor(tok_all, tokens.contiguous(), group=self.group)
+        dist.all_gather_into_tensor(msk_all, msk, group=self.group)
+        dist.all_gather_into_tensor(dh_all, dh, group=self.group)
+        dh_all.mul_(1.0 / W)                                     # mean over the ranks, like the bucket all-reduce(AVG)
+        B, S, Wc = tokens.shape
+        ops.embed_gather_sum_bwd(tok_all.view(W * B, S, Wc), msk_all.view(W * B, S, Wc), dh_all.view(W * B, S, -1),
+                                 None, dt, 0, table_shape[0])
+        return dt
 
     # ------------------------------------------------------------------ both modes
     def finish(self) -> None:

@@ -137,7 +137,10 @@ class CSMTrainer:
             {"params": groups["other"], "lr": lr}) if g["params"]]
         self.optimizer = make_optimizer(param_groups, lr, self.weight_decay)
         trainable = [p for p in self.model.parameters() if p.requires_grad]
-        self._sync = dp.GradSynchronizer(trainable, bucket_bytes=64 << 20 if total > (32 << 20) else None)
+        self._sync = dp.GradSynchronizer(trainable, bucket_bytes=64 << 20 if total > (32 << 20) else None,
+                                         sparse_rows=self.model.text_embeddings.weight)
+        # text-embedding gradient: gathered rows instead of a dense 525 MB all-reduce (dp.exchange_text_rows)
+        self.model._text_grad_exchange = self._sync.exchange_text_rows if self._sync.sparse_param is not None else None
         sink = self._sync if self._sync.bucketed else None
         self.model.backbone._grad_sink = sink        # the stacks hand their layers' gradients over as they finish
         self.model.decoder._grad_sink = sink
