@@ -1,13 +1,15 @@
 // K5 on the 5th-gen tensor cores: causal GQA flash-attention FORWARD for head_dim 64 (CSM-1B backbone).
-//   warp 0     : TMA producer — Q tile once, then K_j / V_j tiles (64 keys x 64) into a 2-stage ring
+//   warp 0     : TMA producer — Q tile once, then K_j / V_j tiles (64 keys x 64) into a 3-stage ring
 //   warp 1     : tcgen05.mma issuer — S_j = Q K_j^T (128x64, fp32 in TMEM, double buffered) and
-//                PV_j = P_j V_j (128x64, V consumed MN-major straight from its row-major tile)
+//                PV_j = P_j V_j (128x64): P is read as the A operand straight out of TMEM, V is consumed MN-major from
+//                its row-major smem tile
 //   warps 2..5 : softmax — one query row per thread (row == TMEM lane, so no shuffles): the S row is read with
-//                tcgen05.ld (max, then exp2/sum), P_j written as bf16 into 128B-swizzled smem (the A operand
-//                of the PV MMA), running output kept in registers and updated from the PV_j tile one block later,
-//                so the tensor pipe computes S_{j+1} and PV_j while the softmax of the next block runs.
+//                tcgen05.ld (max, then exp2/sum), P_j goes back over the same TMEM columns as bf16 pairs
+//                (tcgen05.st) — it never touches shared memory; the running output is kept in registers and updated
+//                from the PV_j tile one block later, so the tensor pipe computes S_{j+1} and PV_j while the softmax of
+//                the next block runs.
 // The kernel is MUFU-bound (one ex2 per score, 16 per clock per SM), so what matters is keeping all four XU pipes
-// fed: 64-key blocks keep a CTA at 81 KB of shared memory and 256 TMEM columns, so TWO CTAs are resident per SM and
+// fed: 64-key blocks keep a CTA at 65 KB of shared memory and 256 TMEM columns, so TWO CTAs are resident per SM and
 // one CTA's softmax overlaps the other's TMEM round trips and mbarrier hand-offs.
 #include <type_traits>
 
@@ -30,11 +32,9 @@ constexpr float kLn2 = 0.6931471805599453f;
 constexpr int SM_Q = 0;
 constexpr int SM_K = SM_Q + TQ * THD * 2;                 // 16 KB
 constexpr int SM_V = SM_K + FST * FK * THD * 2;           // + 24 KB
-constexpr int SM_P = SM_V + FST * FK * THD * 2;           // + 24 KB
-constexpr int SM_BAR = SM_P + 2 * TQ * FK * 2;            // + 32 KB
-constexpr int kAttnSmem = SM_BAR + 256 + 1024;            // 97 KB: two CTAs per SM
+constexpr int SM_BAR = SM_V + FST * FK * THD * 2;         // + 24 KB (P never touches smem: it goes back into TMEM)
+constexpr int kAttnSmem = SM_BAR + 256 + 1024;            // 65 KB; two CTAs per SM (256 TMEM columns each)
 
-__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ float ex2(float x) {   // one MUFU; -inf -> 0
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -42,22 +42,6 @@ __device__ __forceinline__ float ex2(float x) {   // one MUFU; -inf -> 0
 }
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
-}
-
-__device__ __forceinline__ void sts128(uint32_t saddr, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
-  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
-}
-
-__device__ __forceinline__ void store_row_chunk32(uint8_t* tile, int r, int col0, const float* f) {
-  // 32 consecutive columns [col0, col0+32) of row r into a [128 x 64k] bf16 A-operand tile made of
-  // 64-column 128B-swizzled atoms of 16 KB each (explicit st.shared: a generic store would cost a MEMBAR.ALL)
-  const uint32_t atom = smem_u32(tile) + (col0 >> 6) * (128 * 64 * 2) + r * 128;
-  const int c16 = (col0 & 63) >> 3;
-#pragma unroll
-  for (int q4 = 0; q4 < 4; ++q4)
-    sts128(atom + (((c16 + q4) ^ (r & 7)) << 4), pack_bf16(f[q4 * 8 + 0], f[q4 * 8 + 1]),
-           pack_bf16(f[q4 * 8 + 2], f[q4 * 8 + 3]), pack_bf16(f[q4 * 8 + 4], f[q4 * 8 + 5]),
-           pack_bf16(f[q4 * 8 + 6], f[q4 * 8 + 7]));
 }
 
 __global__ void __launch_bounds__(kAttnThreads, 2)
@@ -160,14 +144,15 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         mbar_wait(&p_full[st], (j >> 1) & 1);
         tc_fence_after();
         if (elect_one()) {
-          const uint32_t sp = smem_u32(smem + SM_P + st * (TQ * FK * 2));
           const uint32_t sv = smem_u32(smem + SM_V + (j % FST) * (FK * THD * 2));
-          // P: one 64-key swizzle atom, the K advance inside it is 32 B.  V: 16 key-rows x 128 B per K step.
-          const uint64_t ad = make_smem_desc(sp, 16, 1024), bd = make_smem_desc(sv, 64 * FK * 2, 1024);
+          // P: read straight from TMEM (bf16 pairs written back over the S columns, 8 cells per 16 keys) — no smem
+          // round trip.  V: 16 key-rows x 128 B per K step.  The in-order tensor pipe runs PV(j) before S(j+2), which
+          // overwrites the same columns.
+          const uint64_t bd = make_smem_desc(sv, 64 * FK * 2, 1024);
 #pragma unroll
           for (int kk = 0; kk < FK / 16; ++kk)
-            umma_bf16(tmem_base + COL_PV + st * THD, ad + (uint64_t)((kk * 32) >> 4),
-                      bd + (uint64_t)((kk * 16 * 128) >> 4), idesc_pv, kk ? 1u : 0u);
+            umma_bf16_ts(tmem_base + COL_PV + st * THD, tmem_base + COL_S + st * FK + kk * 8,
+                         bd + (uint64_t)((kk * 16 * 128) >> 4), idesc_pv, kk ? 1u : 0u);
           umma_commit(&pv_full[st]);
           umma_commit(&kv_empty[j % FST]);
         }
@@ -222,7 +207,6 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       const float corr = ex2(m - mx);
       m = mx;
       float rs4[4] = {0.f, 0.f, 0.f, 0.f};
-      uint8_t* ptile = smem + SM_P + st * (TQ * FK * 2);
 #pragma unroll
       for (int c = 0; c < FK; c += 32) {
         float p[32];
@@ -231,10 +215,13 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           p[i] = ex2(fmaf(__uint_as_float(v[c + i]), scale_log2, -m));   // exp2(-inf) = 0 for masked keys
           rs4[i & 3] += p[i];
         }
-        store_row_chunk32(ptile, r, c, p);
+        uint32_t pw[16];                      // bf16 pairs (key, key+1): the A operand of the PV MMA, kept in TMEM
+#pragma unroll
+        for (int i = 0; i < 16; ++i) pw[i] = pack_bf16(p[2 * i], p[2 * i + 1]);
+        tmem_st16(s_addr + (c >> 1), pw);
       }
       l = l * corr + ((rs4[0] + rs4[1]) + (rs4[2] + rs4[3]));
-      fence_async_smem();                     // generic-proxy smem writes -> visible to the tensor core (async proxy)
+      tmem_st_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&p_full[st]);
@@ -270,13 +257,16 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 
 // =====================================================================================================================
 // Backward on tcgen05.  Two kernels that each own their output rows (no atomics, deterministic):
-//   dQ kernel   : CTA = 128 queries of one head; per 64-key sub-block  S = Q K^T, dP = dO V^T  (TMEM, double
-//                 buffered)  ->  dS = P o (dP - delta) * scale (bf16, swizzled smem, double buffered)  ->
-//                 dQ += dS K  accumulated in TMEM over the whole key range.
+//   dQ kernel   : CTA = 128 queries of one head; per 64-key sub-block  S = Q K^T, dP = dO V^T  (TMEM, triple
+//                 buffered)  ->  dS = P o (dP - delta) * scale, written back over the dP columns as bf16 pairs  ->
+//                 dQ += dS K with dS read as the A operand from TMEM, accumulated in TMEM over the whole key range.
 //   dKdV kernel : CTA = 128 keys of one kv head; per (q head of the group, 64-query sub-block)  S^T = K Q^T,
-//                 dP^T = V dO^T  ->  P^T, dS^T (smem)  ->  dV += P^T dO,  dK += dS^T Q  accumulated in TMEM.
-// The MMA warp runs one sub-block ahead of the 8 compute warps (TMEM and smem tiles are double buffered and
-// handed back through mbarriers as soon as they have been read), so tensor-core time and exp/FMA time overlap.
+//                 dP^T = V dO^T  ->  P^T, dS^T back into the same TMEM columns  ->  dV += P^T dO,  dK += dS^T Q.
+// P / dS never go through shared memory: the 128 x 64 MMAs with both operands in smem were operand-feed-bound
+// (6 KB of smem per 32 math cycles) and the compute warps' tile stores competed for the same 128 B/clk
+// (ncu: pipe_tc 56 % busy for 25 % of math) — with A in TMEM the backward went from 286 to 239 us at B=2, S=2048.
+// The MMA warp runs two sub-blocks ahead of the 8 compute warps; a TMEM buffer is handed back by the commit of the
+// MMAs that consumed P / dS from it.
 // The Q / dO / K / V tiles are loaded once per use by TMA as [rows][64] 128B-swizzled tiles and serve BOTH as a
 // K-major operand (rows = M or N, hd = K) and as an MN-major B operand (hd = N, rows = K): same bytes, two descriptors.
 // Compute warps w and w+4 share a TMEM lane quadrant and split the 64 columns of a sub-block; no row reductions are
@@ -284,15 +274,18 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 constexpr int kBwdThreads = 320;  // warp0 TMA, warp1 MMA, warps 2..9 compute
 constexpr int SUB = 64;           // columns (keys resp. queries) per pipelined sub-block
 
-// D[128 x 64] (+)= A[128 x 64 (one swizzle atom, K-major)] * B, B = [64 rows x 64] tile used MN-major
-__device__ __forceinline__ void issue_a64_bmn(uint32_t d_tmem, uint32_t a_smem, uint32_t b_smem, bool accumulate_first) {
+// D[128 x 64] (+)= A[TMEM, 128 lanes x 64 k as bf16 pairs] * B, B = [64 rows x 64] smem tile used MN-major.
+// The two compute warps of a lane quadrant each wrote 32 k (16 cells) at the start of their own 32-column half:
+// k-steps 0,1 live at columns 0 and 8, k-steps 2,3 at columns 32 and 40.
+__device__ __forceinline__ void issue_atmem_bmn(uint32_t d_tmem, uint32_t a_tmem, uint32_t b_smem, bool accumulate_first) {
   constexpr uint32_t idesc = make_idesc_bf16(128, THD, 0, 1);
-  const uint64_t ad = make_smem_desc(a_smem, 16, 1024), bd = make_smem_desc(b_smem, 64 * 128 * 2, 1024);
+  const uint64_t bd = make_smem_desc(b_smem, 64 * 128 * 2, 1024);
 #pragma unroll
   for (int kk = 0; kk < SUB / 16; ++kk)
-    umma_bf16(d_tmem, ad + (uint64_t)((kk * 32) >> 4), bd + (uint64_t)((kk * 16 * 128) >> 4), idesc,
-              (accumulate_first || kk) ? 1u : 0u);
+    umma_bf16_ts(d_tmem, a_tmem + (uint32_t)((kk >> 1) * 32 + (kk & 1) * 8), bd + (uint64_t)((kk * 16 * 128) >> 4), idesc,
+                 (accumulate_first || kk) ? 1u : 0u);
 }
+
 // D[128 x 64] = A[128 x 64] * B[64 x 64]^T, both K-major tiles (reduction over head_dim)
 __device__ __forceinline__ void issue_nt_64(uint32_t d_tmem, uint32_t a_smem, uint32_t b_smem) {
   constexpr uint32_t idesc = make_idesc_bf16(128, SUB, 0, 0);
@@ -308,8 +301,7 @@ constexpr int KST = 3;                               // K/V (resp. Q/dO) TMA rin
 constexpr int NB = 3;                                // TMEM S/dP sub-block buffers: the MMA warp runs two ahead
 constexpr int DQ_K = DQ_DO + TQ * THD * 2;           // KST x 16 KB (128-key tiles = two sub-blocks each)
 constexpr int DQ_V = DQ_K + KST * TK * THD * 2;      // KST x 16 KB
-constexpr int DQ_DS = DQ_V + KST * TK * THD * 2;     // 2 x 16 KB  dS sub-tiles [128 q x 64 keys]
-constexpr int DQ_BAR = DQ_DS + 2 * TQ * SUB * 2;
+constexpr int DQ_BAR = DQ_V + KST * TK * THD * 2;    // (dS goes back into TMEM, not through smem)
 constexpr int kDqSmem = DQ_BAR + 256 + 1024;
 
 __global__ void __launch_bounds__(kBwdThreads, 1)
@@ -324,9 +316,8 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
   uint64_t* kv_full = bars + 1;       // [KST]
   uint64_t* kv_empty = bars + 4;      // [KST]
   uint64_t* sdp_full = bars + 7;      // [NB] S and dP sub-block ready in TMEM
-  uint64_t* sdp_empty = bars + 10;    // [NB] ... and read back by the 8 compute warps
-  uint64_t* ds_full = bars + 13;      // [2] dS sub-tile written (8 warp arrivals)
-  uint64_t* ds_empty = bars + 15;     // [2] ... and consumed by the dQ MMA
+  uint64_t* sdp_empty = bars + 10;    // [NB] ... buffer free again (the dQ MMAs that read dS out of it have completed)
+  uint64_t* ds_full = bars + 13;      // [NB] dS written back over the dP columns as bf16 pairs (8 warp arrivals)
   uint64_t* acc_full = bars + 17;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
   static_assert(KST == 3 && NB == 3, "barrier slots");
@@ -347,9 +338,9 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     mbar_init(q_full, 1);
     for (int i = 0; i < 3; ++i) {
       mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1);
-      mbar_init(&sdp_full[i], 1); mbar_init(&sdp_empty[i], 8);
+      mbar_init(&sdp_full[i], 1); mbar_init(&sdp_empty[i], 1);
+      mbar_init(&ds_full[i], 8);
     }
-    for (int i = 0; i < 2; ++i) { mbar_init(&ds_full[i], 8); mbar_init(&ds_empty[i], 1); }
     mbar_init(acc_full, 1);
     mbar_fence_init();
   }
@@ -399,13 +390,13 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       issue_sdp(1);                    // nsub >= 2 always
       for (int u = 0; u < nsub; ++u) {
         if (u + 2 < nsub) issue_sdp(u + 2);
-        const int jt = u >> 1, hk = u & 1, st = jt % KST, db = u & 1;
-        mbar_wait(&ds_full[db], (u >> 1) & 1);
+        const int jt = u >> 1, hk = u & 1, st = jt % KST, bb = u % NB;
+        mbar_wait(&ds_full[bb], (u / NB) & 1);
         tc_fence_after();
         if (elect_one()) {
           const uint32_t sk = smem_u32(smem + DQ_K + st * (TK * THD * 2)) + hk * (SUB * 128);
-          issue_a64_bmn(tmem_base + COL_DQ, smem_u32(smem + DQ_DS + db * (TQ * SUB * 2)), sk, u > 0);   // dQ += dS K_sub
-          umma_commit(&ds_empty[db]);
+          issue_atmem_bmn(tmem_base + COL_DQ, tmem_base + COL_DP + bb * SUB, sk, u > 0);   // dQ += dS K_sub (dS in TMEM)
+          umma_commit(&sdp_empty[bb]);
           if (hk == 1) umma_commit(&kv_empty[st]);
           if (u == nsub - 1) umma_commit(acc_full);
         }
@@ -422,7 +413,7 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     const float Dls = (qi < S) ? delta[li] * scale : 0.f;
     auto sub = [&](int u, auto diag_tag) {
       constexpr bool DIAG = decltype(diag_tag)::value;
-      const int bb = u % NB, db = u & 1;
+      const int bb = u % NB;
       const int kbase = (u >> 1) * TK + (u & 1) * SUB + half * 32;
       mbar_wait(&sdp_full[bb], (u / NB) & 1);
       tc_fence_after();
@@ -431,9 +422,6 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       tmem_ld32(lane_addr + COL_S + bb * SUB + half * 32, sv_);
       tmem_ld32(lane_addr + COL_DP + bb * SUB + half * 32, dv_);
       tmem_ld_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&sdp_empty[bb]);              // TMEM sub-block handed back to the MMA warp
       float f[32];
 #pragma unroll
       for (int i = 0; i < 32; ++i) {
@@ -441,11 +429,15 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
         if (DIAG && (kbase + i > qi)) x = -INFINITY;
         f[i] = ex2(x) * fmaf(__uint_as_float(dv_[i]), scale, -Dls);     // P * (dP - delta) * scale
       }
-      mbar_wait(&ds_empty[db], ((u >> 1) & 1) ^ 1);
-      store_row_chunk32(smem + DQ_DS + db * (TQ * SUB * 2), r, half * 32, f);
-      fence_async_smem();
+      // dS as bf16 pairs (key, key+1) over the first 16 of this warp's own 32 dP columns: the A operand of dQ += dS K
+      uint32_t dw[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) dw[j] = pack_bf16(f[2 * j], f[2 * j + 1]);
+      tmem_st16(lane_addr + COL_DP + bb * SUB + half * 32, dw);
+      tmem_st_wait();
+      tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&ds_full[db]);
+      if (lane == 0) mbar_arrive(&ds_full[bb]);
     };
     for (int u = 0; u < nsub - 2; ++u) sub(u, std::false_type{});
     sub(nsub - 2, std::true_type{});
@@ -485,9 +477,8 @@ constexpr int DK_K = 0;                              // 16 KB  K tile
 constexpr int DK_V = DK_K + TK * THD * 2;            // 16 KB  V tile
 constexpr int DK_Q = DK_V + TK * THD * 2;            // KST x 16 KB Q tiles (128 queries = two sub-blocks each)
 constexpr int DK_DO = DK_Q + KST * TQ * THD * 2;     // KST x 16 KB dO tiles
-constexpr int DK_PT = DK_DO + KST * TQ * THD * 2;    // 2 x 16 KB P^T sub-tiles [128 keys x 64 q]
-constexpr int DK_DST = DK_PT + 2 * TK * SUB * 2;     // 2 x 16 KB dS^T sub-tiles
-constexpr int DK_LD = DK_DST + 2 * TK * SUB * 2;     // 2 x (128 lse*log2e + 128 delta*scale) floats
+constexpr int DK_LD = DK_DO + KST * TQ * THD * 2;    // 2 x (128 lse*log2e + 128 delta*scale) floats
+                                                     // (P^T / dS^T go back into TMEM, not through smem)
 constexpr int DK_BAR = DK_LD + 2 * 256 * 4;
 constexpr int kDkSmem = DK_BAR + 256 + 1024;
 
@@ -504,10 +495,10 @@ attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
   uint64_t* qd_full = bars + 1;       // [KST] Q_i + dO_i tiles landed
   uint64_t* qd_empty = bars + 4;      // [KST]
   uint64_t* sdp_full = bars + 7;      // [NB] S^T and dP^T sub-block ready
-  uint64_t* sdp_empty = bars + 10;    // [NB] ... read back (8 warp arrivals)
-  uint64_t* pt_full = bars + 13;      // [2] P^T and dS^T sub-tiles written (8 warp arrivals)
-  uint64_t* pt_empty = bars + 15;     // [2] ... consumed by the dV / dK MMAs
-  uint64_t* acc_full = bars + 17;
+  uint64_t* sdp_empty = bars + 10;    // [NB] ... its TMEM buffer is free again (the dV / dK MMAs that read P^T / dS^T
+                                      //      out of the same columns have completed)
+  uint64_t* pt_full = bars + 13;      // [NB] P^T and dS^T written back into the buffer as bf16 (8 warp arrivals)
+  uint64_t* acc_full = bars + 16;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -527,9 +518,9 @@ attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
     mbar_init(kv_full, 1);
     for (int i = 0; i < 3; ++i) {
       mbar_init(&qd_full[i], 1); mbar_init(&qd_empty[i], 1);
-      mbar_init(&sdp_full[i], 1); mbar_init(&sdp_empty[i], 8);
+      mbar_init(&sdp_full[i], 1); mbar_init(&sdp_empty[i], 1);
+      mbar_init(&pt_full[i], 8);
     }
-    for (int i = 0; i < 2; ++i) { mbar_init(&pt_full[i], 8); mbar_init(&pt_empty[i], 1); }
     mbar_init(acc_full, 1);
     mbar_fence_init();
   }
@@ -582,15 +573,17 @@ attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
       issue_sdp(1);                    // nsub >= 2 always
       for (int u = 0; u < nsub; ++u) {
         if (u + 2 < nsub) issue_sdp(u + 2);
-        const int it = u >> 1, hq = u & 1, st = it % KST, db = u & 1;
-        mbar_wait(&pt_full[db], (u >> 1) & 1);
+        const int it = u >> 1, hq = u & 1, st = it % KST, bb = u % NB;
+        mbar_wait(&pt_full[bb], (u / NB) & 1);
         tc_fence_after();
         if (elect_one()) {
           const uint32_t sq = smem_u32(smem + DK_Q + st * (TQ * THD * 2)) + hq * (SUB * 128);
           const uint32_t sdo = smem_u32(smem + DK_DO + st * (TQ * THD * 2)) + hq * (SUB * 128);
-          issue_a64_bmn(tmem_base + COL_DV, smem_u32(smem + DK_PT + db * (TK * SUB * 2)), sdo, u > 0);   // dV += P^T dO
-          issue_a64_bmn(tmem_base + COL_DK, smem_u32(smem + DK_DST + db * (TK * SUB * 2)), sq, u > 0);   // dK += dS^T Q
-          umma_commit(&pt_empty[db]);
+          // A operands straight from TMEM: P^T / dS^T were written back (bf16 pairs) over the S^T / dP^T columns they
+          // came from — no shared-memory round trip for the 128 x 64 tiles, and the MMAs read only B from smem
+          issue_atmem_bmn(tmem_base + COL_DV, tmem_base + COL_ST + bb * SUB, sdo, u > 0);    // dV += P^T dO
+          issue_atmem_bmn(tmem_base + COL_DK, tmem_base + COL_DPT + bb * SUB, sq, u > 0);    // dK += dS^T Q
+          umma_commit(&sdp_empty[bb]);
           if (hq == 1) umma_commit(&qd_empty[st]);
           if (u == nsub - 1) umma_commit(acc_full);
         }
@@ -617,7 +610,7 @@ attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
     float ld_next = load_ld(0);
     auto sub = [&](int u, auto diag_tag) {
       constexpr bool DIAG = decltype(diag_tag)::value;
-      const int it = u >> 1, hq = u & 1, bb = u % NB, db = u & 1;
+      const int it = u >> 1, hq = u & 1, bb = u % NB;
       const int qb = kvb + it % nq_iter;
       float* sLD = reinterpret_cast<float*>(smem + DK_LD) + (it & 1) * 256;
       if (hq == 0) {
@@ -634,9 +627,6 @@ attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
       tmem_ld32(lane_addr + COL_ST + bb * SUB + half * 32, sv_);
       tmem_ld32(lane_addr + COL_DPT + bb * SUB + half * 32, dv_);
       tmem_ld_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&sdp_empty[bb]);
       float pf[32], df[32];
       const float4* L4 = reinterpret_cast<const float4*>(sLD + col0);
       const float4* D4 = reinterpret_cast<const float4*>(sLD + 128 + col0);
@@ -654,12 +644,19 @@ attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
           df[i] = pv * fmaf(__uint_as_float(dv_[i]), scale, -Ds[t]);
         }
       }
-      mbar_wait(&pt_empty[db], ((u >> 1) & 1) ^ 1);
-      store_row_chunk32(smem + DK_PT + db * (TK * SUB * 2), r, half * 32, pf);
-      store_row_chunk32(smem + DK_DST + db * (TK * SUB * 2), r, half * 32, df);
-      fence_async_smem();
+      // bf16 pairs (q, q+1) back into the first 16 of this warp's own 32 columns of each buffer
+      uint32_t pw[16], dw[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        pw[j] = pack_bf16(pf[2 * j], pf[2 * j + 1]);
+        dw[j] = pack_bf16(df[2 * j], df[2 * j + 1]);
+      }
+      tmem_st16(lane_addr + COL_ST + bb * SUB + half * 32, pw);
+      tmem_st16(lane_addr + COL_DPT + bb * SUB + half * 32, dw);
+      tmem_st_wait();
+      tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&pt_full[db]);
+      if (lane == 0) mbar_arrive(&pt_full[bb]);
     };
     for (int u = 0; u < nsub; ++u) {
       if ((u >> 1) % nq_iter == 0) sub(u, std::true_type{}); else sub(u, std::false_type{});
