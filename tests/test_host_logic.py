@@ -197,3 +197,45 @@ def test_rope_table_matches_oracle():
     from oracle.torchtune_shim import Llama3ScaledRoPE
     for hd in (8, 64, 128):
         assert torch.equal(build_rope_cache(hd, 4096, 500000.0, 32.0), Llama3ScaledRoPE(hd, 4096, 500000.0, 32.0).cache)
+
+
+def test_skinny_gemm_split_choice():
+    """Which GEMMs take the split-reduction path (csm/ops.py::_splitk_choice): LoRA-shaped ones only."""
+    from csm import ops
+    # t = x A^T, dts = dy B, dB = dy^T t, dA = dts^T x  at CSM-1B c2 shapes
+    assert ops._splitk_choice(4096, 16, 2048) == 4
+    assert ops._splitk_choice(4096, 16, 3072) == 4
+    assert ops._splitk_choice(3072, 16, 4096) == 4
+    assert ops._splitk_choice(16, 2048, 4096) == 8
+    for M, N, K in [(4096, 2048, 2048), (4096, 16384, 2048), (232, 2051, 1024), (4096, 16, 512), (7424, 8, 1024)]:
+        assert ops._splitk_choice(M, N, K) == 0, (M, N, K)        # wide, short-K or many-tile problems: one GEMM
+    for M, N, K in [(4096, 16, 2048), (16, 2048, 4096), (24, 1000, 7424)]:
+        s = ops._splitk_choice(M, N, K)
+        assert K % (s * 64) == 0 and K // s >= 256                # every group is whole 64-wide k-blocks
+
+
+def test_optimizer_selection_and_loud_failure():
+    """CPU parameters get stock AdamW (host-logic tests); the kernel optimiser refuses anything but CUDA bf16."""
+    from csm.training.optim import FusedClipAdamW
+    from csm.training.trainer import clip_and_step, make_optimizer
+    p = torch.nn.Parameter(torch.ones(4, 4))
+    opt = make_optimizer([{"params": [p], "lr": 1e-2}], 1e-3, 0.01)
+    assert isinstance(opt, torch.optim.AdamW) and not isinstance(opt, FusedClipAdamW)
+    p.grad = torch.full_like(p, 10.0)
+    clip_and_step(opt, [p], 1.0)                                  # clip_grad_norm_ + step (trainer.py:271-276)
+    assert float(p.grad.norm()) <= 1.0 + 1e-4 and not torch.equal(p.data, torch.ones(4, 4))
+    q = torch.nn.Parameter(torch.ones(4, 4))
+    q.grad = torch.ones(4, 4)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        FusedClipAdamW([q], lr=1e-3).step()
+    with pytest.raises(ValueError):
+        FusedClipAdamW([{"params": [q], "betas": (0.9, 0.99)}, {"params": [p], "betas": (0.8, 0.99)}])
+
+
+def test_sparse_text_exchange_only_for_cuda_data_parallel():
+    """The row-sparse text-embedding exchange needs NCCL ranks and CUDA tensors; otherwise the table stays bucketed."""
+    from csm.training import dp
+    table = torch.nn.Parameter(torch.zeros(10, 4))
+    other = torch.nn.Parameter(torch.zeros(3, 3))
+    sync = dp.GradSynchronizer([table, other], bucket_bytes=1 << 20, sparse_rows=table)
+    assert sync.sparse_param is None and len(sync.params) == 2 and not sync.bucketed
