@@ -799,17 +799,28 @@ static int choose_bn(int groups, int64_t M, int64_t N) {
   return (t256 < num_sms() || N <= 128) ? 128 : 256;
 }
 
-// Shared driver for the plain GEMM and the CE epilogues.
-int gemm_tc_run(const GemmTcOperands& o, GemmTcParams p, int epi, cudaStream_t st) {
+// Tile width and CTA-pair decision for one launch (also used by the CE drivers, whose combine kernel must know how
+// many column tiles the partials have).
+static int gemm_tc_tiling(int epi, int groups, int64_t M, int64_t N, int transA, int transB, bool* pair) {
   const int mode = g_cta2_mode.load();
-  p.num_m = (int)((p.M + BM - 1) / BM);
-  // CTA-pair mode (256 x 256 super-tiles) for the plain GEMMs that can keep at least ~2/3 of the 74 pairs busy;
-  // the test hook (mode 1) turns it on for every shape with two m-blocks and more than one 128-column tile
-  const int64_t super256 = (int64_t)p.groups * ((p.num_m + 1) / 2) * ((p.N + 255) / 256);
-  bool cta2 = (epi == EPI_STORE || epi == EPI_SWIGLU_BWD) && p.num_m >= 2 && p.N > 128 && mode != 0 &&
+  const int num_m = (int)((M + BM - 1) / BM);
+  // CTA-pair mode (256 x 256 super-tiles) for the GEMMs that can keep at least ~2/3 of the 74 pairs busy; the test
+  // hook (mode 1) turns it on for every shape with two m-blocks and more than one 128-column tile
+  const int64_t super256 = (int64_t)groups * ((num_m + 1) / 2) * ((N + 255) / 256);
+  // (the fused-CE epilogues take K-major operands only: activations [M, K] and the [V, K] head)
+  const bool ce_pair_ok = (epi == EPI_CE_PARTIAL || epi == EPI_CE_DLOGITS) && !transA && !transB;
+  bool cta2 = (epi == EPI_STORE || epi == EPI_SWIGLU_BWD || ce_pair_ok) && num_m >= 2 && N > 128 && mode != 0 &&
               (mode == 1 || super256 >= 48);
   if (epi == EPI_SWIGLU_FWD) cta2 = true;                 // callers check gemm_tc_swiglu_supported()
-  const int bn = (cta2 || epi == EPI_SWIGLU_BWD) ? 256 : choose_bn(p.groups, p.M, p.N);
+  if (pair) *pair = cta2;
+  return (cta2 || epi == EPI_SWIGLU_BWD) ? 256 : choose_bn(groups, M, N);
+}
+
+// Shared driver for the plain GEMM and the CE epilogues.
+int gemm_tc_run(const GemmTcOperands& o, GemmTcParams p, int epi, cudaStream_t st) {
+  p.num_m = (int)((p.M + BM - 1) / BM);
+  bool cta2 = false;
+  const int bn = gemm_tc_tiling(epi, p.groups, p.M, p.N, o.transA, o.transB, &cta2);
   if (cta2 && epi == EPI_STORE && p.groups == 1 && g_sk_ws && g_sk_mode.load() == 1) {
     // stream-K when the tile count leaves the last wave badly filled (e.g. 128 super-tiles on 74 pairs = 1.73 waves)
     const int cap = pair_capacity();
@@ -854,6 +865,8 @@ int gemm_tc_run(const GemmTcOperands& o, GemmTcParams p, int epi, cudaStream_t s
     if (cta2) return launch_inst<false, true, 256, EPI_SWIGLU_BWD, true>(ta, tb, ta2, tb2, p, st);
     return launch_inst<false, true, 256, EPI_SWIGLU_BWD, false>(ta, tb, ta2, tb2, p, st);
   }
+  if (cta2 && epi == EPI_CE_PARTIAL) return launch_inst<false, false, 256, EPI_CE_PARTIAL, true>(ta, tb, ta2, tb2, p, st);
+  if (cta2 && epi == EPI_CE_DLOGITS) return launch_inst<false, false, 256, EPI_CE_DLOGITS, true>(ta, tb, ta2, tb2, p, st);
   if (cta2) return launch_major<256, EPI_STORE, true>(o, ta, tb, ta2, tb2, p, st);
   if (epi == EPI_STORE) { if (bn == 256) DISPATCH(256, EPI_STORE); else DISPATCH(128, EPI_STORE); }
   if (epi == EPI_CE_PARTIAL) { if (bn == 256) DISPATCH(256, EPI_CE_PARTIAL); else DISPATCH(128, EPI_CE_PARTIAL); }
@@ -957,7 +970,7 @@ int linear_ce_tc_fwd(const void* H, const void* W, const int64_t* targets, float
   p.ce_part = reinterpret_cast<float4*>(ws);
   int rc = gemm_tc_run(o, p, EPI_CE_PARTIAL, st);
   if (rc) return rc;
-  const int bn = choose_bn(groups, M, V);  // same choice gemm_tc_run made
+  const int bn = gemm_tc_tiling(EPI_CE_PARTIAL, groups, M, V, 0, 0, nullptr);  // the choice gemm_tc_run made
   const int nt = (int)((V + bn - 1) / bn);
   return ce_combine_launch(ws, nt, loss_rows, lse, (int64_t)groups * M, st);
 }
