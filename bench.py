@@ -298,7 +298,6 @@ def main():
     launches = _lib.launch_count() - l0
     if not args.no_graph and getattr(trainer, "_graphed", None) is not None and trainer._graphed.graph is not None:
         launches = trainer._graphed.kernels_per_replay * args.steps   # replayed graph nodes (counted at capture)
-    clk = clocks.stop() if rank == 0 else None
     ms_step = ms_total / args.steps
     frames_per_step = world * B * S
     value = frames_per_step / (ms_step * 1e-3)
@@ -315,6 +314,8 @@ def main():
         h2d = sum(v.numel() * v.element_size() for v in host[0].values())
         e2e = {"value": frames_per_step / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
                "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e}
+
+    clk = clocks.stop() if rank == 0 else None        # sampled across both timed regions (device-resident and e2e)
 
     # ---- roofline of the dominant kernel (tcgen05 GEMM): CUDA events around every GEMM launch of two more steps
     # (every rank runs the two steps — they contain the gradient all-reduce — only rank 0 instruments them)
