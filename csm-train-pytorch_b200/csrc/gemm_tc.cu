@@ -1,11 +1,19 @@
 // K4: persistent warp-specialised bf16 GEMM on the 5th-gen tensor cores.
-//   warp 0      : TMA producer (one elected lane) — 128B-swizzled A/B tiles into a kStages-deep smem ring
-//   warp 1      : TMEM allocator + tcgen05.mma issuer (one lane); accumulators live in TMEM, double-buffered
-//   warps 2..5  : epilogue — tcgen05.ld the 128 x BN fp32 tile, apply {alpha, residual, accumulate | CE partial |
-//                 CE dlogits}, store.  Overlaps the next tile's main loop through the second TMEM buffer.
+//   warp 0      : TMA producer — 128B-swizzled A/B tiles into a kStages-deep smem ring (mbarrier full/empty)
+//   warp 1      : TMEM allocator + tcgen05.mma issuer; accumulators live in TMEM, double-buffered
+//   warps 2..9  : epilogue — tcgen05.ld the 128 x BN fp32 tile, apply {alpha, residual, accumulate, RoPE | SwiGLU fwd /
+//                 bwd | CE partial | CE dlogits}, store through a swizzled smem tile (whole 64-byte row segments).
+//                 Overlaps the next tile's main loop through the second TMEM buffer.
+// Producer and MMA warps keep warp-uniform control flow and elect one lane per TMA / tcgen05 instruction
+// (tc::elect_one): issued under `if (lane == 0)` every UTCHMMA costs an R2UR/ELECT/BRA.U.ANY waterfall loop.
+// Two tilings: single CTA (128 x BN, BN 128/256) and CTA PAIR (cluster of 2, tcgen05.mma.cta_group::2, M = 256:
+// each CTA loads its own 128 rows of A and half of the B tile, the leader CTA issues the MMAs for both, loads of both
+// CTAs complete on the leader's barrier, commits are multicast to both).  The pair moves a third less operand data
+// per flop and is what the big shapes use (93.6 % tensor-pipe activity vs 71.6 % for the single-CTA tiling).
 // Operands may be K-major or MN-major (transposed storage) — the backward GEMMs (dgrad / wgrad) read the same
 // tensors the forward wrote, no transposes are materialised.  An optional extra K-block (A2/B2) carries the
-// LoRA low-rank term inside the main loop.  `groups` batches independent problems (31 audio heads) in one launch.
+// LoRA low-rank term inside the main loop.  `groups` batches independent problems (31 audio heads, or the K-slices of
+// a split reduction) in one launch.  A stream-K schedule exists for badly filled last waves (off: no gain measured).
 #include "tc_common.cuh"
 
 namespace csm {
