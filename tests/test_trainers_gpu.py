@@ -178,3 +178,31 @@ def test_fused_clip_adamw_matches_torch(cuda, max_norm):
     opt2 = FusedClipAdamW(groups(make()), lr=1e-3, weight_decay=0.01)
     opt2.load_state_dict(sd)
     assert float(opt2._dev_scalars[0]) == 3.0
+
+
+def test_full_finetune_checkpoint_resume(cuda, tmp_path):
+    """save_checkpoint / load_checkpoint (reference format, utils.py:526-574) carry the model and the kernel optimiser's
+    state (exp_avg, exp_avg_sq, step): a resumed trainer continues exactly like the uninterrupted one."""
+    from csm.training.optim import FusedClipAdamW
+    from csm.training.trainer import CSMTrainer
+    from csm.training.utils import load_checkpoint, save_checkpoint
+
+    def trainer(sub):
+        model, cfg = _small_model(cuda)
+        t = CSMTrainer("", str(tmp_path / sub), device=str(cuda), learning_rate=2e-4)
+        t.model = model
+        t.prepare_optimizer()
+        return t, cfg
+    ta, cfg = trainer("a")
+    assert isinstance(ta.optimizer, FusedClipAdamW)
+    batches = _batches(cfg, 4)
+    for b in batches[:2]:
+        ta.train_step(b)
+    path = save_checkpoint(ta.model, ta.optimizer, 1, ta.global_step, 0.0, str(tmp_path / "ckpt"))
+    la = [float(ta.train_step(b)) for b in batches[2:]]
+    tb, _ = trainer("b")
+    meta = load_checkpoint(path, tb.model, tb.optimizer, str(cuda))
+    assert meta["global_step"] == 2 and float(tb.optimizer._dev_scalars[0]) == 2.0
+    lb = [float(tb.train_step(b)) for b in batches[2:]]
+    for x, y in zip(la, lb):
+        assert abs(x - y) <= 2e-3 * abs(x), (la, lb)      # (embedding scatter uses atomics: not bit-reproducible)
