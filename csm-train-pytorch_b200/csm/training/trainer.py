@@ -26,21 +26,10 @@ def csm_1b_args() -> ModelArgs:                       # trainer.py:100-106
 
 
 def collate_variable_length(batch):
-    """Zero / False padding to the batch maximum — contract of data/training_data.py:379-408."""
-    S = max(b["input_tokens"].shape[0] for b in batch)
-    T = max(b["target_audio_tokens"].shape[0] for b in batch)
-    T = max(T, S)
-    W = batch[0]["input_tokens"].shape[1]
-    C = batch[0]["target_audio_tokens"].shape[1]
-    tok = torch.zeros(len(batch), S, W, dtype=torch.int64)
-    msk = torch.zeros(len(batch), S, W, dtype=torch.bool)
-    tgt = torch.zeros(len(batch), T, C, dtype=torch.int64)
-    for i, b in enumerate(batch):
-        s, t = b["input_tokens"].shape[0], b["target_audio_tokens"].shape[0]
-        tok[i, :s] = b["input_tokens"]
-        msk[i, :s] = b["input_masks"].bool()
-        tgt[i, :t] = b["target_audio_tokens"]
-    return {"input_tokens": tok, "input_masks": msk, "target_audio_tokens": tgt}
+    """Zero / False padding to the batch maximum — contract of data/training_data.py:379-408; the padded tensors are
+    pinned on a GPU host so the trainer's H2D copies are asynchronous (csm/data/frames.py)."""
+    from ..data.frames import collate_pinned
+    return collate_pinned(batch)
 
 
 def iterate_batches(dataset, batch_size: int, shuffle: bool, rank: int = 0, world: int = 1, seed: int = 0):

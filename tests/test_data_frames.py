@@ -1,0 +1,75 @@
+"""CPU tests of the data contract helpers (csm/data/frames.py) against the reference's layout rules."""
+import os
+
+import pytest
+import torch
+
+from csm.data import frames as F
+
+REF = "/root/reference/src/csm"
+
+
+def test_text_and_audio_frame_layout():
+    tok, msk = F.text_frames([5, 7, 9])
+    assert tok.shape == (3, 33) and tok[:, 32].tolist() == [5, 7, 9] and int(tok[:, :32].abs().sum()) == 0
+    assert msk[:, 32].all() and not msk[:, :32].any()                      # generator.py:91-95
+    codes = torch.arange(32 * 4).view(32, 4) % 2051
+    at, am = F.audio_frames(codes)
+    assert at.shape == (5, 33)                                              # + EOS frame (generator.py:117-119)
+    assert torch.equal(at[:4, :32], codes.t()) and int(at[4].sum()) == 0 and int(at[:, 32].sum()) == 0
+    assert am[:, :32].all() and not am[:, 32].any()
+    at2, _ = F.audio_frames(codes, add_eos=False)
+    assert at2.shape == (4, 33)
+    with pytest.raises(ValueError):
+        F.audio_frames(torch.zeros(3, dtype=torch.long))
+
+
+def test_build_sample_matches_reference_concatenation_and_truncation():
+    ctx_codes = torch.randint(0, 2051, (32, 6), generator=torch.Generator().manual_seed(0))
+    tgt_codes = torch.randint(0, 2051, (32, 9), generator=torch.Generator().manual_seed(1))
+    s = F.build_sample([([1, 2, 3], ctx_codes)], [4, 5], tgt_codes)
+    # context text (3) + context audio (6 + EOS) + target text (2)
+    assert s["input_tokens"].shape == (3 + 7 + 2, 33) and s["input_masks"].shape == (12, 33)
+    assert s["input_tokens"][-2:, 32].tolist() == [4, 5]
+    assert s["target_audio_tokens"].shape == (9, 32) and torch.equal(s["target_audio_tokens"], tgt_codes.t())
+    # truncation: cut from the beginning, keep min(max_seq_len, target text length) frames (training_data.py:289-294)
+    t = F.build_sample([([1, 2, 3], ctx_codes)], [4, 5], tgt_codes, max_seq_len=8)
+    assert t["input_tokens"].shape[0] == 2 and t["input_tokens"][:, 32].tolist() == [4, 5]
+
+
+@pytest.mark.skipif(not os.path.exists(REF), reason="reference tree not mounted")
+def test_collate_equals_reference_collate():
+    import importlib.util
+    import sys
+    import types
+    # the reference's collate lives in a module whose package imports need moshi etc.: load the function's source only
+    src = open(os.path.join(REF, "data", "training_data.py")).read()
+    start = src.index("def collate_variable_length(batch):")
+    ns = {"torch": torch}
+    exec(src[start:], ns)                                                   # noqa: S102 (reference code, test only)
+    ref_collate = ns["collate_variable_length"]
+    g = torch.Generator().manual_seed(3)
+    batch = []
+    for n, t in [(5, 7), (9, 4), (2, 9)]:
+        tok = torch.randint(0, 100, (n, 33), generator=g)
+        batch.append({"input_tokens": tok, "input_masks": torch.rand(n, 33, generator=g) > 0.5,
+                      "target_audio_tokens": torch.randint(0, 100, (t, 32), generator=g)})
+    ours, ref = F.collate_pinned(batch, pin=False), ref_collate(batch)
+    assert torch.equal(ours["input_tokens"], ref["input_tokens"])
+    assert torch.equal(ours["input_masks"], ref["input_masks"])
+    T = ref["target_audio_tokens"].shape[1]
+    assert torch.equal(ours["target_audio_tokens"][:, :T], ref["target_audio_tokens"])
+    assert int(ours["target_audio_tokens"][:, T:].abs().sum()) == 0          # only zero padding beyond the reference's
+    p = F.collate_pinned(batch, pin=False, pad_to_multiple=8)
+    assert p["input_tokens"].shape[1] == 16 and not p["input_masks"][:, 9:].any()
+
+
+def test_length_bucketing_cuts_padding_and_covers_every_sample():
+    g = torch.Generator().manual_seed(0)
+    lengths = (torch.rand(1000, generator=g) ** 3 * 2000 + 50).long().tolist()     # long-tailed
+    naive = [list(range(i, min(i + 8, 1000))) for i in range(0, 1000, 8)]
+    bucketed = F.length_bucketed_order(lengths, 8, seed=1)
+    assert sorted(j for b in bucketed for j in b) == list(range(1000))
+    assert all(1 <= len(b) <= 8 for b in bucketed)
+    assert F.padding_fraction(lengths, bucketed) < 0.5 * F.padding_fraction(lengths, naive)
+    assert bucketed != F.length_bucketed_order(lengths, 8, seed=2)                   # the epoch order stays random
