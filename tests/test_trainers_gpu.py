@@ -206,3 +206,35 @@ def test_full_finetune_checkpoint_resume(cuda, tmp_path):
     lb = [float(tb.train_step(b)) for b in batches[2:]]
     for x, y in zip(la, lb):
         assert abs(x - y) <= 2e-3 * abs(x), (la, lb)      # (embedding scatter uses atomics: not bit-reproducible)
+
+
+def _ragged_dataset(cfg, lengths):
+    """Variable-length samples in the reference's per-item format (training_data.py:296-300)."""
+    from csm.data.synthetic import synthetic_batch
+    items = []
+    for i, S in enumerate(lengths):
+        b = synthetic_batch(cfg.text_vocab_size, cfg.audio_vocab_size, cfg.audio_num_codebooks, 1, S, seed=50 + i)
+        items.append({"input_tokens": b["input_tokens"][0], "input_masks": b["input_masks"][0],
+                      "target_audio_tokens": b["target_audio_tokens"][0]})
+    return items
+
+
+def test_train_loops_on_ragged_dataset(cuda, tmp_path):
+    """CSMTrainer.train (accumulation, validation, checkpoints) and CSMLoRATrainer.train (adapter saves) end to end on
+    variable-length samples: pinned zero/False collate, host-side frame selection, kernel optimiser."""
+    from csm.training.trainer import CSMTrainer
+    model, cfg = _small_model(cuda)
+    data = _ragged_dataset(cfg, [128, 96, 160, 130, 144, 100, 128, 150])
+    t = CSMTrainer("", str(tmp_path / "ft"), device=str(cuda), learning_rate=2e-4)
+    t.model = model
+    t.prepare_optimizer(freeze_embeddings=True)
+    best = t.train(data[:6], data[6:], batch_size=2, accumulation_steps=2, epochs=2, val_every=1, save_every=1)
+    assert t.global_step == 2 and t.epoch == 2 and best < float("inf")
+    names = sorted(os.listdir(tmp_path / "ft"))
+    assert any(n.startswith("final_") for n in names) and any(n.startswith("best_") for n in names)
+    assert "checkpoint_latest.pt" in names
+    tl, _ = _lora_trainer(tmp_path / "lora", cuda, graph=False)
+    tl.train(data[:4], data[4:6], batch_size=2, epochs=1, val_every=1, save_every=1)
+    assert tl.global_step == 2
+    assert os.path.exists(tmp_path / "lora" / "final_lora.safetensors") or \
+        os.path.exists(tmp_path / "lora" / "final.safetensors")
