@@ -239,3 +239,47 @@ def test_sparse_text_exchange_only_for_cuda_data_parallel():
     other = torch.nn.Parameter(torch.zeros(3, 3))
     sync = dp.GradSynchronizer([table, other], bucket_bytes=1 << 20, sparse_rows=table)
     assert sync.sparse_param is None and len(sync.params) == 2 and not sync.bucketed
+
+
+def _streamk_items(unit, n_units, num_tiles, kb_total):
+    """Python mirror of csrc/gemm_tc.cu::next_item (stream-K branch) — keep in sync with the kernel."""
+    U = num_tiles * kb_total
+    u0, u1 = U * unit // n_units, U * (unit + 1) // n_units
+    tA, ka = divmod(u0, kb_total)
+    tC, kc = divmod(u1, kb_total)
+    items = []
+    if kc > 0:
+        items.append((tC, 0, kc, 1))                        # head part of a tile the next unit finishes
+    if ka > 0:
+        items.append((tA, ka, kb_total, 2))                 # tail part: this unit finishes the tile
+    f0 = tA if ka == 0 else tA + 1
+    items += [(t, 0, kb_total, 0) for t in range(f0, tC)]
+    return items
+
+
+@pytest.mark.parametrize("tiles,units,kb", [(128, 74, 128), (128, 74, 33), (116, 74, 16), (75, 74, 9), (300, 70, 48)])
+def test_stream_k_schedule_covers_every_k_block_once(tiles, units, kb):
+    """Every (tile, k-block) is computed exactly once; a cut tile has exactly one head owner (unit p) and one tail
+    owner (unit p + 1), the head is the first item of p and the tail comes before p + 1's whole tiles — the ordering the
+    fix-up protocol in the epilogue relies on (no finisher ever waits on work scheduled after its own)."""
+    seen = {}
+    for p in range(units):
+        items = _streamk_items(p, units, tiles, kb)
+        kinds = [k for *_, k in items]
+        assert kinds == sorted(kinds, key=lambda k: {1: 0, 2: 1, 0: 2}[k])          # head, tail, whole tiles
+        assert kinds.count(1) <= 1 and kinds.count(2) <= 1
+        for t, a, b, k in items:
+            assert 0 <= t < tiles and 0 <= a < b <= kb
+            for x in range(a, b):
+                assert (t, x) not in seen
+                seen[(t, x)] = (p, k)
+        load = sum(b - a for _, a, b, _ in items)
+        assert abs(load - tiles * kb / units) < 1.0 + 1e-9                           # balanced to one k-block
+    assert len(seen) == tiles * kb
+    for t in range(tiles):
+        owners = sorted({seen[(t, x)] for x in range(kb)})
+        if len(owners) == 2:
+            (p0, k0), (p1, k1) = owners
+            assert p1 == p0 + 1 and k0 == 1 and k1 == 2
+        else:
+            assert len(owners) == 1 and owners[0][1] == 0
