@@ -44,6 +44,7 @@ SIGNATURES = {
     "csm_gemm_streamk_workspace_bytes": (_sz, []),
     "csm_gemm_set_streamk_workspace": (None, [_ptr, _sz]),
     "csm_set_gemm_streamk_mode": (None, [_i32]),
+    "csm_set_gemm_narrow_tail_mode": (None, [_i32]),
     "csm_attn_bwd_workspace_bytes": (_sz, [_i32] * 5),
     "csm_attn_causal_gqa_bwd": (_i32, [_ptr] * 9 + [_i32] * 5 + [_i64] * 7 + [_f32, _ptr, _sz, _ptr]),
     "csm_attn_causal_gqa_bwd_rope": (_i32, [_ptr] * 9 + [_i32] * 5 + [_i64] * 7 + [_f32, _ptr, _ptr, _sz, _ptr]),

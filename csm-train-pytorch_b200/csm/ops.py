@@ -195,6 +195,11 @@ def set_gemm_streamk_mode(m: int) -> None:
     _lib.load().csm_set_gemm_streamk_mode(m)
 
 
+def set_gemm_narrow_tail_mode(m: int) -> None:
+    """Experimental (default 0): 1 narrows the MMAs of a ragged last column tile to the columns that exist."""
+    _lib.load().csm_set_gemm_narrow_tail_mode(m)
+
+
 def _splitk_choice(M: int, N: int, K: int) -> int:
     """Number of reduction groups for a skinny GEMM (0 = run it as one GEMM).  Skinny = one output dimension <= 64 and
     at most 48 output tiles of 128 x 128; the split fills ~100-160 CTAs and keeps >= 256 reduction elements per group."""

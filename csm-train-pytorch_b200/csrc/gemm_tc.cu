@@ -53,6 +53,8 @@ struct GemmTcParams {
   // by the position row % rope_seq; the linear output is rounded to bf16 first, as the unfused rope kernel would read it
   const float* rope_cache; int rope_seq, rope_cols, rope_hd;
   int streamk;
+  // experimental (off by default): issue the MMAs of a ragged last column tile with N rounded up to 16 instead of BN
+  int narrow_tail;
   float* sk_ws;             // [pairs][2 CTAs][BN cols][128 rows] fp32
   int* sk_flags;            // [pairs][2 CTAs][2]: partial-ready count, readers-done count (self-resetting)
   // CE epilogues
@@ -292,6 +294,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       mbar_wait(&tempty[acc], acc_phase ^ 1);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+      uint32_t tile_idesc = idesc;
+      if (!kTransB && (kEpi == EPI_STORE || kEpi == EPI_CE_PARTIAL || kEpi == EPI_CE_DLOGITS) && p.narrow_tail) {
+        // K-major B: smem rows are output columns, rows past N are TMA zero fill.  A pair takes N/2 rows from each
+        // CTA (columns [0, N/2) from the leader's half), so the narrow form needs every valid column in the leader.
+        int g, mb, nb;
+        tile_coords(w.tile, tile_m, p.num_n, g, mb, nb);
+        const int valid = (int)min((int64_t)BN, p.N - (int64_t)nb * BN);
+        const int n_eff = kCta2 ? (valid > BN / 2 ? BN : ((2 * valid + 15) & ~15)) : ((valid + 15) & ~15);
+        tile_idesc = make_idesc_bf16(kCta2 ? 2 * BM : BM, n_eff, kTransA ? 1 : 0, 0);
+      }
       for (int kb = w.kb0; kb < w.kb1; ++kb) {
         mbar_wait(&full[stage], phase);
         tc_fence_after();
@@ -307,8 +319,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const uint64_t ad = adesc + (uint64_t)((kTransA ? kk * 16 * 128 : kk * 32) >> 4);
             const uint64_t bd = bdesc + (uint64_t)((kTransB ? kk * 16 * 128 : kk * 32) >> 4);
             const uint32_t accum = ((kb - w.kb0) | kk) ? 1u : 0u;      // the first MMA of a work item overwrites
-            if (kCta2) umma_bf16_2sm(d_tmem, ad, bd, idesc, accum);
-            else umma_bf16(d_tmem, ad, bd, idesc, accum);
+            if (kCta2) umma_bf16_2sm(d_tmem, ad, bd, tile_idesc, accum);
+            else umma_bf16(d_tmem, ad, bd, tile_idesc, accum);
           }
           // frees the smem slot (in both CTAs of a pair) once these MMAs have read it
           if (kCta2) umma_commit_2sm(&empty[stage], 3); else umma_commit(&empty[stage]);
@@ -728,6 +740,8 @@ void gemm_tc_set_streamk_workspace(void* ptr, size_t bytes) {
   }
 }
 void gemm_tc_set_streamk_mode(int m) { g_sk_mode.store(m); }
+static std::atomic<int> g_tail_mode{0};  // 0 off (default), 1 narrow MMAs on ragged last column tiles (unmeasured)
+void gemm_tc_set_narrow_tail_mode(int m) { g_tail_mode.store(m); }
 
 // how many CTA pairs can be co-resident (a pair needs two SMs of one TPC); every pair instantiation has the same
 // block size and shared-memory footprint, so one query serves all
@@ -840,6 +854,7 @@ int gemm_tc_run(const GemmTcOperands& o, GemmTcParams p, int epi, cudaStream_t s
       p.streamk = 1; p.sk_ws = g_sk_ws; p.sk_flags = g_sk_flags;
     }
   }
+  p.narrow_tail = (g_tail_mode.load() == 1 && !p.streamk) ? 1 : 0;
   const uint32_t b_box = cta2 ? (uint32_t)bn / 2 : (uint32_t)bn;
   p.num_n = epi == EPI_SWIGLU_FWD ? (int)((p.N + 127) / 128) : (int)((p.N + bn - 1) / bn);
   const uint64_t b_rows = epi == EPI_SWIGLU_FWD ? 2 * (uint64_t)p.N : (uint64_t)p.N;   // packed gate|up weight

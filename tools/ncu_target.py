@@ -16,6 +16,8 @@ BF = torch.bfloat16
 what = sys.argv[1] if len(sys.argv) > 1 else "gemm"
 if os.environ.get("CSM_PAIR_MODE"):            # A/B: 0 = never use the CTA-pair GEMM, 1 = whenever legal
     ops.set_gemm_cta_pair_mode(int(os.environ["CSM_PAIR_MODE"]))
+if os.environ.get("CSM_NARROW_TAIL"):         # A/B: 1 = narrow MMAs on ragged last column tiles (experimental)
+    ops.set_gemm_narrow_tail_mode(int(os.environ["CSM_NARROW_TAIL"]))
 torch.manual_seed(0)
 if what == "gemm":          # the MLP gate/up forward GEMM of one backbone layer (fused w1|w3): 4096 x 16384 x 2048
     x = torch.randn(4096, 2048, device=dev).to(BF)
