@@ -131,6 +131,64 @@ def test_rope_scaling_matches_transformers_llama3():
     assert torch.allclose(ours, inv.float(), rtol=1e-6)
 
 
+def test_llama_stack_restatement_matches_transformers_llama():
+    """The whole restated torchtune stack (RMSNorm, scaled RoPE, GQA attention, SwiGLU, residual wiring, final norm)
+    against transformers' independent Llama implementation on the same weights, forward and input gradient.  HF
+    rotates (i, i + hd/2) pairs where torchtune rotates (2i, 2i + 1): the q/k projection rows are permuted per head,
+    which leaves q.k unchanged."""
+    pytest.importorskip("transformers")
+    from transformers import LlamaConfig, LlamaModel
+    torch.manual_seed(0)
+    D, H, KV, L, I, S = 128, 4, 2, 3, 256, 40
+    hd = D // H
+    dec = tt.llama3_2(vocab_size=32, num_layers=L, num_heads=H, num_kv_heads=KV, embed_dim=D, max_seq_len=2048,
+                      intermediate_dim=I, norm_eps=1e-5, scale_factor=32)
+    dec.tok_embeddings = torch.nn.Identity()                 # as the reference does (model.py:51-56)
+    for p_ in dec.parameters():
+        torch.nn.init.normal_(p_, std=0.08)
+    for m in dec.modules():
+        if isinstance(m, tt.RMSNorm):
+            torch.nn.init.normal_(m.scale, mean=1.0, std=0.1)
+    try:
+        cfg = LlamaConfig(vocab_size=32, hidden_size=D, intermediate_size=I, num_hidden_layers=L,
+                          num_attention_heads=H, num_key_value_heads=KV, head_dim=hd, max_position_embeddings=131072,
+                          rms_norm_eps=1e-5, rope_theta=500000.0, attention_bias=False, mlp_bias=False,
+                          rope_scaling={"rope_type": "llama3", "factor": 32.0, "low_freq_factor": 1.0,
+                                        "high_freq_factor": 4.0, "original_max_position_embeddings": 8192},
+                          attn_implementation="eager")
+        hf = LlamaModel(cfg).eval()
+    except Exception as e:                                   # config schema differs across transformers versions
+        pytest.skip(f"transformers Llama config API changed: {e}")
+
+    def halves(w, nh):                                       # interleaved pair layout -> HF's two-halves layout
+        w = w.view(nh, hd // 2, 2, -1)
+        return torch.cat([w[:, :, 0], w[:, :, 1]], 1).reshape(nh * hd, -1)
+
+    with torch.no_grad():
+        for a, b in zip(dec.layers, hf.layers):
+            b.self_attn.q_proj.weight.copy_(halves(a.attn.q_proj.weight, H))
+            b.self_attn.k_proj.weight.copy_(halves(a.attn.k_proj.weight, KV))
+            b.self_attn.v_proj.weight.copy_(a.attn.v_proj.weight)
+            b.self_attn.o_proj.weight.copy_(a.attn.output_proj.weight)
+            b.mlp.gate_proj.weight.copy_(a.mlp.w1.weight)
+            b.mlp.down_proj.weight.copy_(a.mlp.w2.weight)
+            b.mlp.up_proj.weight.copy_(a.mlp.w3.weight)
+            b.input_layernorm.weight.copy_(a.sa_norm.scale)
+            b.post_attention_layernorm.weight.copy_(a.mlp_norm.scale)
+        hf.norm.weight.copy_(dec.norm.scale)
+    x1 = torch.randn(2, S, D, requires_grad=True)
+    x2 = x1.detach().clone().requires_grad_(True)
+    pos = torch.arange(S)[None].expand(2, -1)
+    mask = torch.tril(torch.ones(S, S, dtype=torch.bool))[None].expand(2, -1, -1)
+    o1 = dec(x1, mask=mask, input_pos=pos)
+    o2 = hf(inputs_embeds=x2, position_ids=pos).last_hidden_state
+    assert torch.allclose(o1, o2, atol=2e-5, rtol=1e-5), float((o1 - o2).abs().max())
+    probe = torch.randn_like(o1)
+    (o1 * probe).sum().backward()
+    (o2 * probe).sum().backward()
+    assert torch.allclose(x1.grad, x2.grad, atol=2e-5, rtol=1e-4), float((x1.grad - x2.grad).abs().max())
+
+
 def test_attention_restatement_matches_dense_formula():
     torch.manual_seed(0)
     b, s, H, KV, hd = 2, 9, 4, 2, 8
