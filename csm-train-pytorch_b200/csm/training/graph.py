@@ -43,10 +43,10 @@ class GraphedStep:
                 self.loss = self.step_fn(self.static)
             self.kernels_per_replay = _lib.launch_count() - n0     # libcsm_b200 kernels recorded in the graph
             self.graph.replay()
-            return self.loss
+            return self.loss.clone()
         if self._signature(batch) != self.sig:
             return self.step_fn({k: v.to(self.device, non_blocking=True) for k, v in batch.items()})
         for k, v in batch.items():
             self.static[k].copy_(v, non_blocking=True)      # H2D (pinned host batch) or D2D into the captured buffers
         self.graph.replay()
-        return self.loss
+        return self.loss.clone()       # the captured loss buffer is overwritten by the next replay

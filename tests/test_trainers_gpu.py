@@ -46,7 +46,8 @@ def test_lora_train_step_graph_equals_eager(cuda, tmp_path):
     tg, _ = _lora_trainer(tmp_path / "g", cuda, graph=True)
     batches = _batches(cfg, 6)
     le = [float(te.train_step(b)) for b in batches]
-    lg = [float(tg.train_step(b)) for b in batches]        # steps 1-2 eager, step 3 captures, 4-6 replay
+    held = [tg.train_step(b) for b in batches]              # steps 1-2 eager, step 3 captures, 4-6 replay
+    lg = [float(x) for x in held]                           # read late: a replay must not overwrite earlier results
     assert tg._graphed.graph is not None and tg._graphed.kernels_per_replay > 50
     for a, b in zip(le, lg):
         assert abs(a - b) <= 2e-3 * abs(a), (le, lg)
