@@ -158,6 +158,7 @@ class GradSynchronizer:
         W = self.world
         dt = torch.zeros(table_shape, dtype=dh.dtype, device=dh.device)   # fresh: autograd may adopt it as .grad
         msk = mask.contiguous().view(torch.uint8) if mask.dtype == torch.bool else mask.to(torch.uint8).contiguous()
+        tokens, msk, dh = self.pad_to_common_frames(tokens, msk, dh)
         tok_all = torch.empty((W,) + tuple(tokens.shape), dtype=tokens.dtype, device=tokens.device)
         msk_all = torch.empty((W,) + tuple(msk.shape), dtype=torch.uint8, device=tokens.device)
         dh_all = torch.empty((W,) + tuple(dh.shape), dtype=dh.dtype, device=dh.device)
@@ -169,6 +170,26 @@ class GradSynchronizer:
         ops.embed_gather_sum_bwd(tok_all.view(W * B, S, Wc), msk_all.view(W * B, S, Wc), dh_all.view(W * B, S, -1),
                                  None, dt, 0, table_shape[0])
         return dt
+
+    def pad_to_common_frames(self, tokens, msk, dh):
+        """Ragged data: each rank pads its batch to its own longest sample, so [B, S] can differ between ranks while
+        the all-gathers need one shape.  Pads with masked-out frames (mask 0, dh 0: they scatter nothing) up to the
+        maximum over the ranks.  One tiny MAX all-reduce + host read per step; skipped while a CUDA graph is being
+        captured, where the shapes are static and equal by construction."""
+        if self.world == 1 or (tokens.is_cuda and torch.cuda.is_current_stream_capturing()):
+            return tokens, msk, dh
+        shape = torch.tensor([tokens.shape[0], tokens.shape[1]], dtype=torch.int64, device=tokens.device)
+        dist.all_reduce(shape, op=dist.ReduceOp.MAX, group=self.group)
+        Bm, Sm = (int(x) for x in shape.tolist())
+        B, S = tokens.shape[0], tokens.shape[1]
+        if (Bm, Sm) == (B, S):
+            return tokens, msk, dh
+
+        def grow(t):
+            out = t.new_zeros((Bm, Sm) + tuple(t.shape[2:]))
+            out[:B, :S] = t
+            return out
+        return grow(tokens), grow(msk), grow(dh)
 
     # ------------------------------------------------------------------ both modes
     def finish(self) -> None:

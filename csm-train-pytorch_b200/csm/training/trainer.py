@@ -35,6 +35,9 @@ def collate_variable_length(batch):
 def iterate_batches(dataset, batch_size: int, shuffle: bool, rank: int = 0, world: int = 1, seed: int = 0):
     n = len(dataset)
     order = torch.randperm(n, generator=torch.Generator().manual_seed(seed)).tolist() if shuffle else list(range(n))
+    if world > 1:
+        # every rank must run the same number of steps (each one ends in a collective): drop the ragged tail
+        order = order[:(n // world) * world]
     order = order[rank::world]
     for i in range(0, len(order), batch_size):
         yield collate_variable_length([dataset[j] for j in order[i:i + batch_size]])

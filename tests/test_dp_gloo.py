@@ -127,3 +127,57 @@ def test_single_process_is_noop():
     g = lin.weight.grad.clone()
     dp.GradSynchronizer(lin.parameters()).finish()
     assert torch.equal(lin.weight.grad, g)
+
+
+def _worker_ragged(rank, world, port, q):
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, os.path.join(root, "csm-train-pytorch_b200"))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    from csm.training import dp
+    from csm.training.trainer import iterate_batches
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        # (1) ragged shapes: rank 0 holds [2, 5] frames, rank 1 [1, 7]; after padding both hold [2, 7] and the padding
+        #     is masked out with a zero upstream gradient, so the scatter kernel ignores it
+        sync = dp.GradSynchronizer([torch.nn.Parameter(torch.zeros(3))], bucket_bytes=64)
+        B, S = (2, 5) if rank == 0 else (1, 7)
+        tok = torch.arange(B * S * 3).view(B, S, 3) + 1
+        msk = torch.ones(B, S, 3, dtype=torch.uint8)
+        dh = torch.ones(B, S, 4)
+        t2, m2, d2 = sync.pad_to_common_frames(tok, msk, dh)
+        assert t2.shape == (2, 7, 3) and m2.shape == (2, 7, 3) and d2.shape == (2, 7, 4)
+        assert torch.equal(t2[:B, :S], tok) and torch.equal(m2[:B, :S], msk) and torch.equal(d2[:B, :S], dh)
+        assert int(m2.sum()) == B * S * 3 and float(d2.sum()) == B * S * 4      # everything added is zero / masked
+        gathered = torch.empty((world * t2.shape[0],) + tuple(t2.shape[1:]), dtype=t2.dtype)
+        dist.all_gather_into_tensor(gathered, t2)                                 # one shape on every rank now
+        # equal shapes: returned untouched
+        same = torch.zeros(2, 4, 3, dtype=torch.int64)
+        assert sync.pad_to_common_frames(same, same.to(torch.uint8), torch.zeros(2, 4, 4))[0] is same
+        # (2) every rank sees the same number of batches even when the dataset does not divide evenly
+        data = [{"input_tokens": torch.ones(3 + i, 33, dtype=torch.long),
+                 "input_masks": torch.ones(3 + i, 33, dtype=torch.bool),
+                 "target_audio_tokens": torch.ones(3 + i, 32, dtype=torch.long)} for i in range(7)]
+        mine = sum(1 for _ in iterate_batches(data, 2, True, rank, world, seed=1))
+        counts = [None] * world
+        dist.all_gather_object(counts, mine)
+        assert counts == [2, 2], counts                                           # 7 samples -> 3 per rank -> 2 batches
+        q.put((rank, "ok"))
+    except Exception:  # noqa: BLE001
+        import traceback
+        q.put((rank, traceback.format_exc()))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_ragged_batches_share_shapes_and_step_counts_world2():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_ragged, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(res) == [(0, "ok"), (1, "ok")], res
