@@ -233,10 +233,16 @@ class Model(nn.Module):
 
     def _audio_head_t(self) -> torch.Tensor:
         """[31, V, Dd] shadow of audio_head [31, Dd, V] (rows of V=2051 bf16 are not 16-byte aligned, so the native
-        layout cannot be a TMA operand); refreshed only when the parameter changed."""
+        layout cannot be a TMA operand); a frozen head (LoRA) is transposed once, a trainable one every forward."""
         ah = self.audio_head
-        if self._head_t is None or self._head_t_version != ah._version or self._head_t.device != ah.device:
+        if self._head_t is None or self._head_t.device != ah.device or self._head_t.dtype != ah.dtype:
             self._head_t = ah.detach().transpose(1, 2).contiguous()
+            self._head_t_version = ah._version
+        elif ah.requires_grad or self._head_t_version != ah._version:
+            # a trainable head is re-read on every forward: a replayed CUDA graph (and any kernel that updates the
+            # parameter through its raw pointer) does not move the version counter.  Same buffer, so the copy is
+            # captured with the step.
+            self._head_t.copy_(ah.detach().transpose(1, 2))
             self._head_t_version = ah._version
         return self._head_t
 

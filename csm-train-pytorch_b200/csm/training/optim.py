@@ -75,7 +75,7 @@ class FusedClipAdamW(torch.optim.Optimizer):
         if closure is not None:
             raise NotImplementedError("FusedClipAdamW does not take a closure")
         max_norm = self.max_grad_norm if max_grad_norm is None else max_grad_norm
-        ps, gs, ms, vs, ns, lrs, wds = [], [], [], [], [], [], []
+        ps, gs, ms, vs, ns, lrs, wds, updated = [], [], [], [], [], [], [], []
         device = None
         for group in self.param_groups:
             for p in group["params"]:
@@ -88,6 +88,7 @@ class FusedClipAdamW(torch.optim.Optimizer):
                 g = p.grad if p.grad.is_contiguous() else p.grad.contiguous()
                 st = self._init_state(p)
                 device = p.device
+                updated.append(p)
                 ps.append(p.data_ptr()); gs.append(g.data_ptr()); ms.append(st["exp_avg"].data_ptr())
                 vs.append(st["exp_avg_sq"].data_ptr()); ns.append(p.numel())
                 lrs.append(float(group["lr"])); wds.append(float(group["weight_decay"]))
@@ -112,4 +113,6 @@ class FusedClipAdamW(torch.optim.Optimizer):
                                            sc.data_ptr(), sc.data_ptr() + 4,
                                            torch.cuda.current_stream().cuda_stream), "adamw_clip_step")
         self._keepalive = []
+        # the kernels wrote through raw pointers: tell autograd / version-keyed caches the parameters changed
+        torch.autograd.graph.increment_version(updated)
         return None

@@ -67,7 +67,12 @@ def test_full_finetune_trainer_steps_and_graph(cuda, tmp_path):
         t.prepare_optimizer()
         if graph:
             t.enable_cuda_graph(warmup=2)
+        head0_t = model.audio_head.detach().transpose(1, 2).clone()
         losses[graph] = [float(t.train_step(b)) for b in _batches(cfg, 5)]
+        # the [31, V, Dd] shadow the fused-CE kernels read follows the trainable head (the optimiser kernels and the
+        # replayed graph write through raw pointers): it moved with the updates, and a forward refreshes it
+        assert not torch.equal(model._head_t, head0_t)
+        assert torch.equal(model._audio_head_t(), model.audio_head.detach().transpose(1, 2))
         assert len(t.optimizer.param_groups) == 4          # backbone / decoder / embeddings / other (trainer.py:166-173)
         lrs = sorted(g["lr"] for g in t.optimizer.param_groups)
         assert lrs == sorted([2e-4 * 0.1, 2e-4 * 1.0, 2e-4 * 0.5, 2e-4])
