@@ -151,7 +151,9 @@ def run_reference(args):
         return
     desc, mode, r, targets, _, S = WORKLOADS[args.config]
     S_cpu = args.cpu_seq
-    steps, warmup = max(1, min(args.steps, 3)), max(0, min(args.warmup, 1))
+    # K and W as asked (each step is the bounded B=1, S=cpu_seq sample: ~0.7 s on the GPU box's host cores, ~2 s on 8
+    # cores); capped so that a very long request still ends within a few minutes
+    steps, warmup = max(1, min(args.steps, 30)), max(0, min(args.warmup, 5))
     res = cpu_reference_step_rate(S_cpu, steps, warmup, r, targets, mode)
     line = {"impl": "reference", "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": args.gpus,
             "steps": steps, "warmup": warmup, "ms_per_step": res["ms_per_step"], "higher_is_better": True,
