@@ -93,6 +93,7 @@ def embed_gather_sum(tokens, mask, audio_emb, text_emb, *, debug: bool = False):
 
 def embed_gather_sum_bwd(tokens, mask, dh, d_audio: Optional[torch.Tensor], d_text: Optional[torch.Tensor],
                          audio_vocab: int, text_vocab: int) -> None:
+    _chk_cuda(tokens, mask, dh, d_audio, d_text)
     B, S, W = tokens.shape
     mask_u8 = mask.contiguous().view(torch.uint8) if mask.dtype == torch.bool else mask.to(torch.uint8).contiguous()
     lib = _lib.load()
@@ -103,6 +104,7 @@ def embed_gather_sum_bwd(tokens, mask, dh, d_audio: Optional[torch.Tensor], d_te
 
 def decoder_input(h, audio_emb, targets, frame_idx, codebooks: int, audio_vocab: int):
     """h bf16 [B,S,D], targets int64 [B,T,C], frame_idx int64 [Ns,2] -> x bf16 [Ns, C, D]."""
+    _chk_cuda(h, audio_emb, targets, frame_idx)
     B, S, D = h.shape
     Ns = frame_idx.shape[0]
     x = torch.empty(Ns, codebooks, D, dtype=BF16, device=h.device)
@@ -115,6 +117,7 @@ def decoder_input(h, audio_emb, targets, frame_idx, codebooks: int, audio_vocab:
 
 def decoder_input_bwd(dx, targets, frame_idx, dh, d_audio, codebooks: int, audio_vocab: int) -> None:
     """dh bf16 [B,S,D] (accumulated in place), d_audio nullable (accumulated in place)."""
+    _chk_cuda(dx, targets, frame_idx, dh, d_audio)
     B, S, D = dh.shape
     lib = _lib.load()
     _lib.check(lib.csm_decoder_input_bwd(_p(dx.contiguous()), _p(targets.contiguous()), _p(frame_idx.contiguous()),
@@ -124,6 +127,7 @@ def decoder_input_bwd(dx, targets, frame_idx, dh, d_audio, codebooks: int, audio
 
 # ----------------------------------------------------------------------------- norm / rope / swiglu
 def rmsnorm(x, scale, eps: float) -> Tuple[torch.Tensor, torch.Tensor]:
+    _chk_cuda(x, scale)
     D = x.shape[-1]
     rows = x.numel() // D
     y = torch.empty_like(x)
@@ -134,6 +138,7 @@ def rmsnorm(x, scale, eps: float) -> Tuple[torch.Tensor, torch.Tensor]:
 
 
 def rmsnorm_bwd(dy, x, scale, rstd, dres: Optional[torch.Tensor], dscale_f32: Optional[torch.Tensor]):
+    _chk_cuda(dy, x, scale, rstd, dres, dscale_f32)
     D = x.shape[-1]
     rows = x.numel() // D
     dx = torch.empty_like(x)
@@ -145,6 +150,7 @@ def rmsnorm_bwd(dy, x, scale, rstd, dres: Optional[torch.Tensor], dscale_f32: Op
 
 def rope_(x2d, cache, seq_len: int, heads: int, head_dim: int, inverse: bool = False, ld: Optional[int] = None):
     """In place on x2d [rows, >= heads*head_dim] (row stride ld)."""
+    _chk_cuda(x2d, cache)
     rows = x2d.shape[0]
     ld = x2d.stride(0) if ld is None else ld
     lib = _lib.load()
@@ -154,6 +160,7 @@ def rope_(x2d, cache, seq_len: int, heads: int, head_dim: int, inverse: bool = F
 
 
 def swiglu(gate, up):
+    _chk_cuda(gate, up)
     rows, cols = gate.shape
     out = torch.empty(rows, cols, dtype=BF16, device=gate.device)
     lib = _lib.load()
@@ -163,6 +170,7 @@ def swiglu(gate, up):
 
 
 def swiglu_bwd(dout, gate, up, dgate=None, dup=None):
+    _chk_cuda(dout, gate, up, dgate, dup)
     rows, cols = gate.shape
     dgate = torch.empty(rows, cols, dtype=BF16, device=gate.device) if dgate is None else dgate
     dup = torch.empty(rows, cols, dtype=BF16, device=gate.device) if dup is None else dup
@@ -218,6 +226,7 @@ def _splitk_choice(M: int, N: int, K: int) -> int:
 def gemm_rope(a, b, cache, seq_len: int, rope_cols: int, head_dim: int, *, a2=None, b2=None):
     """out = a @ b^T (+ a2 @ b2^T) with RoPE applied to columns [0, rope_cols) (heads of head_dim, position = row %
     seq_len): the fused q|k|v projection.  One launch when the tcgen05 GEMM takes the shape, else gemm + rope."""
+    _chk_cuda(a, b, cache, a2, b2)
     M, K = a.shape
     N = b.shape[0]
     be = _backend_override
@@ -252,7 +261,7 @@ def gemm(a, b, *, trans_a: bool = False, trans_b: bool = False, out: Optional[to
 
     a: [M,K] (or [K,M] when trans_a); b: [N,K] (nn.Linear layout; or [K,N] when trans_b); 2-D, unit inner stride.
     """
-    _chk_cuda(a, b)
+    _chk_cuda(a, b, out, residual, a2, b2)
     _ensure_streamk_workspace(a.device)
     assert a.dim() == 2 and b.dim() == 2 and a.stride(1) == 1 and b.stride(1) == 1
     M, K = (a.shape[1], a.shape[0]) if trans_a else a.shape
@@ -307,6 +316,7 @@ def swiglu_fusable(M: int, inter: int, K: int) -> bool:
 
 def gemm_swiglu_fwd(x, w13, *, a2=None, b2=None):
     """x [M,K], w13 = [w1; w3] [2I,K] -> (gate_up bf16 [M,2I], act bf16 [M,I]) ; optional LoRA tail a2 [M,r], b2 [2I,r]."""
+    _chk_cuda(x, w13, a2, b2)
     M, K = x.shape
     inter = w13.shape[0] // 2
     gu = torch.empty(M, 2 * inter, dtype=BF16, device=x.device)
@@ -328,6 +338,7 @@ def gemm_swiglu_fwd(x, w13, *, a2=None, b2=None):
 
 def gemm_swiglu_bwd(dy, w2, gu, *, a2=None, b2=None):
     """dy [M,K], w2 [K,I] (nn.Linear weight of the down projection), gu [M,2I] -> dgate_up bf16 [M,2I]."""
+    _chk_cuda(dy, w2, gu, a2, b2)
     M, K = dy.shape
     inter = w2.shape[1]
     dgu = torch.empty(M, 2 * inter, dtype=BF16, device=dy.device)
@@ -349,6 +360,7 @@ def gemm_swiglu_bwd(dy, w2, gu, *, a2=None, b2=None):
 # ----------------------------------------------------------------------------- attention
 def attention_fwd(q, k, v, batch: int, seq: int, heads: int, kv_heads: int, head_dim: int):
     """q [B*S, H*hd], k/v [B*S, KV*hd] (row strides free) -> (o [B*S, H*hd], lse fp32 [B,H,S])."""
+    _chk_cuda(q, k, v)
     o = torch.empty(batch * seq, heads * head_dim, dtype=BF16, device=q.device)
     lse = torch.empty(batch, heads, seq, dtype=torch.float32, device=q.device)
     lib = _lib.load()
@@ -362,6 +374,7 @@ def attention_bwd(q, k, v, o, lse, dout, batch, seq, heads, kv_heads, head_dim, 
                   rope_cache=None):
     """With `rope_cache` the returned dq / dk are gradients w.r.t. the UN-rotated projections (inverse RoPE applied):
     inside the tcgen05 kernels' store epilogues when they take the shape, else by the rope kernel afterwards."""
+    _chk_cuda(q, k, v, o, lse, dout, dq, dk, dv)
     dev = q.device
     dq = torch.empty(batch * seq, heads * head_dim, dtype=BF16, device=dev) if dq is None else dq
     dk = torch.empty(batch * seq, kv_heads * head_dim, dtype=BF16, device=dev) if dk is None else dk
@@ -405,6 +418,7 @@ def linear_ce_fwd(h, w, targets, *, trans_w: bool = False, groups: int = 1, tgt_
                   tgt_group_stride: int = 0, backend: Optional[int] = None):
     """Returns (loss_rows fp32 [groups, M], lse fp32 [groups, M]).  `targets` is an int64 tensor whose element
     for (group g, row m) sits at offset m*tgt_row_stride + g*tgt_group_stride from its data pointer."""
+    _chk_cuda(h, w, targets)
     M, V, K, ldh, hgs, ldw, wgs = _ce_geometry(h, w, trans_w, groups)
     lib = _lib.load()
     nbytes = lib.csm_linear_ce_workspace_bytes(M, V, K, groups)
@@ -421,6 +435,7 @@ def linear_ce_fwd(h, w, targets, *, trans_w: bool = False, groups: int = 1, tgt_
 def linear_ce_bwd(h, w, targets, lse, grad_scale: float, *, dh: torch.Tensor, grad_scale_dev=None, dw: Optional[torch.Tensor] = None,
                   dw_accumulate: bool = False, trans_w: bool = False, groups: int = 1, tgt_row_stride: int = 1,
                   tgt_group_stride: int = 0, backend: Optional[int] = None):
+    _chk_cuda(h, w, targets, lse, dh, dw, grad_scale_dev)
     M, V, K, ldh, hgs, ldw, wgs = _ce_geometry(h, w, trans_w, groups)
     lib = _lib.load()
     nbytes = lib.csm_linear_ce_workspace_bytes(M, V, K, groups)
@@ -439,6 +454,7 @@ def linear_ce_bwd(h, w, targets, lse, grad_scale: float, *, dh: torch.Tensor, gr
 
 # ----------------------------------------------------------------------------- helpers
 def f32_to_bf16_(src_f32, dst_bf16, scale: float = 1.0, accumulate: bool = False):
+    _chk_cuda(src_f32, dst_bf16)
     lib = _lib.load()
     _lib.check(lib.csm_f32_to_bf16(_p(src_f32), _p(dst_bf16), src_f32.numel(), scale, 1 if accumulate else 0, _st()),
                "f32_to_bf16")
@@ -446,6 +462,7 @@ def f32_to_bf16_(src_f32, dst_bf16, scale: float = 1.0, accumulate: bool = False
 
 
 def add_bf16(a, b, out=None):
+    _chk_cuda(a, b, out)
     out = torch.empty_like(a) if out is None else out
     lib = _lib.load()
     _lib.check(lib.csm_add_bf16(_p(a), _p(b), _p(out), a.numel(), _st()), "add_bf16")

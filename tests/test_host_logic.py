@@ -283,3 +283,36 @@ def test_stream_k_schedule_covers_every_k_block_once(tiles, units, kb):
             assert p1 == p0 + 1 and k0 == 1 and k1 == 2
         else:
             assert len(owners) == 1 and owners[0][1] == 0
+
+
+def test_every_op_rejects_cpu_tensors_before_touching_the_library():
+    """No CPU fallback and no host pointers handed to a kernel: each compute wrapper raises on CPU tensors."""
+    from csm import ops
+    bf = torch.bfloat16
+    x, w = torch.zeros(4, 8, dtype=bf), torch.zeros(8, 8, dtype=bf)
+    tok, msk = torch.zeros(1, 2, 3, dtype=torch.long), torch.ones(1, 2, 3, dtype=torch.bool)
+    f32 = torch.zeros(4)
+    calls = [
+        lambda: ops.embed_gather_sum(tok, msk, w, w),
+        lambda: ops.embed_gather_sum_bwd(tok, msk, x, w, w, 4, 8),
+        lambda: ops.decoder_input(x.view(1, 4, 8), w, tok, tok[0, :, :2], 3, 2),
+        lambda: ops.decoder_input_bwd(x, tok, tok[0, :, :2], x.view(1, 4, 8), None, 3, 2),
+        lambda: ops.rmsnorm(x, w[0], 1e-5),
+        lambda: ops.rmsnorm_bwd(x, x, w[0], f32, None, None),
+        lambda: ops.rope_(x, f32, 4, 1, 8),
+        lambda: ops.swiglu(x, x),
+        lambda: ops.swiglu_bwd(x, x, x),
+        lambda: ops.gemm(x, w),
+        lambda: ops.gemm_rope(x, w, f32, 4, 8, 8),
+        lambda: ops.gemm_swiglu_fwd(x, w),
+        lambda: ops.gemm_swiglu_bwd(x, w, x),
+        lambda: ops.attention_fwd(x, x, x, 1, 4, 1, 1, 8),
+        lambda: ops.attention_bwd(x, x, x, x, f32, x, 1, 4, 1, 1, 8),
+        lambda: ops.linear_ce_fwd(x, w, tok.view(-1)[:4]),
+        lambda: ops.linear_ce_bwd(x, w, tok.view(-1)[:4], f32, 1.0, dh=x),
+        lambda: ops.f32_to_bf16_(f32, x),
+        lambda: ops.add_bf16(x, x),
+    ]
+    for i, c in enumerate(calls):
+        with pytest.raises(RuntimeError, match="no CPU fallback"):
+            c()
