@@ -53,7 +53,7 @@ struct GemmTcParams {
   // by the position row % rope_seq; the linear output is rounded to bf16 first, as the unfused rope kernel would read it
   const float* rope_cache; int rope_seq, rope_cols, rope_hd;
   int streamk;
-  // experimental (off by default): issue the MMAs of a ragged last column tile with N rounded up to 16 instead of BN
+  // off by default (no gain measured): issue the MMAs of a ragged last column tile with N rounded up to 16 instead of BN
   int narrow_tail;
   float* sk_ws;             // [pairs][2 CTAs][BN cols][128 rows] fp32
   int* sk_flags;            // [pairs][2 CTAs][2]: partial-ready count, readers-done count (self-resetting)
@@ -740,7 +740,7 @@ void gemm_tc_set_streamk_workspace(void* ptr, size_t bytes) {
   }
 }
 void gemm_tc_set_streamk_mode(int m) { g_sk_mode.store(m); }
-static std::atomic<int> g_tail_mode{0};  // 0 off (default), 1 narrow MMAs on ragged last column tiles (unmeasured)
+static std::atomic<int> g_tail_mode{0};  // 0 off (default), 1 narrow MMAs on ragged last column tiles (bit-identical, no gain measured)
 void gemm_tc_set_narrow_tail_mode(int m) { g_tail_mode.store(m); }
 
 // how many CTA pairs can be co-resident (a pair needs two SMs of one TPC); every pair instantiation has the same

@@ -171,7 +171,7 @@ void csm_set_gemm_cta_pair_mode(int32_t mode);
 size_t csm_gemm_streamk_workspace_bytes(void);
 void csm_gemm_set_streamk_workspace(void* workspace, size_t bytes);
 void csm_set_gemm_streamk_mode(int32_t mode);
-/* Experimental, default 0 (not yet measured on the GPU): 1 issues the MMAs of a ragged last column tile (K-major B
+/* Experimental, default 0 (measured: bit-identical, no gain — profiles/r1_ctest_narrow_tail.txt): 1 issues the MMAs of a ragged last column tile (K-major B
  * operand; e.g. the 3 leftover columns of the 2051-wide audio heads) with N rounded up to 16 instead of the full tile
  * width.  Results are identical; only tensor-pipe time changes. */
 void csm_set_gemm_narrow_tail_mode(int32_t mode);

@@ -418,7 +418,8 @@ def test_linear_ce_single_head(ops, cuda, backend, M, V, K):
 
 
 @pytest.mark.skipif(os.environ.get("CSM_TEST_EXPERIMENTAL") != "1",
-                    reason="narrow-tail MMA mode is off by default and not yet measured (CSM_TEST_EXPERIMENTAL=1 runs it)")
+                    reason="narrow-tail MMA mode stays off (bit-identical, no gain: profiles/r1_ctest_narrow_tail.txt); "
+                           "CSM_TEST_EXPERIMENTAL=1 runs this test")
 @pytest.mark.parametrize("pair", [0, 1])
 @pytest.mark.parametrize("M,V,K", [(232, 2051, 1024), (300, 2051, 256), (256, 2200, 512), (200, 330, 256)])
 def test_narrow_tail_mode_is_bit_identical(ops, cuda, pair, M, V, K):
