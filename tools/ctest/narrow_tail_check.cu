@@ -49,25 +49,25 @@ static float bf(const __nv_bfloat16& x) { return __bfloat162float(x); }
 
 int main() {
   if (csm_device_supported() != 1) { printf("no sm_100 device\n"); return 1; }
-  const int G = 31, M = 232, V = 2051, K = 1024, LDC = 2056;
+  const int G = 31, M = 232, MAXM = 512, V = 2051, K = 1024, LDC = 2056;
   __nv_bfloat16 *H, *W, *dH[2], *C[2];
   int64_t* T;
   float *loss[2], *lse[2];
   void* ws;
   uint8_t* flush;
-  const size_t nH = (size_t)G * M * K, nW = (size_t)G * V * K;
-  CK(cudaMalloc(&H, nH * 2)); CK(cudaMalloc(&W, nW * 2)); CK(cudaMalloc(&T, (size_t)G * M * 8));
+  const size_t nH = (size_t)G * MAXM * K, nW = (size_t)G * V * K;
+  CK(cudaMalloc(&H, nH * 2)); CK(cudaMalloc(&W, nW * 2)); CK(cudaMalloc(&T, (size_t)G * MAXM * 8));
   for (int i = 0; i < 2; ++i) {
     CK(cudaMalloc(&dH[i], nH * 2)); CK(cudaMalloc(&C[i], (size_t)M * LDC * 2));
-    CK(cudaMalloc(&loss[i], (size_t)G * M * 4)); CK(cudaMalloc(&lse[i], (size_t)G * M * 4));
+    CK(cudaMalloc(&loss[i], (size_t)G * MAXM * 4)); CK(cudaMalloc(&lse[i], (size_t)G * MAXM * 4));
   }
-  const size_t wsb = csm_linear_ce_workspace_bytes(M, V, K, G);
+  const size_t wsb = csm_linear_ce_workspace_bytes(MAXM, V, K, G);
   CK(cudaMalloc(&ws, wsb));
   const size_t fl = 256u << 20;
   CK(cudaMalloc(&flush, fl));
   fill_bf16<<<1024, 256>>>(H, nH, 17u, 1.0f);
   fill_bf16<<<4096, 256>>>(W, nW, 99u, 0.0625f);
-  fill_targets<<<64, 256>>>(T, (size_t)G * M, V);
+  fill_targets<<<64, 256>>>(T, (size_t)G * MAXM, V);
   CK(cudaDeviceSynchronize());
 
   auto ce_fwd = [&](int i) {
@@ -165,6 +165,29 @@ int main() {
     }
   }
   csm_set_gemm_narrow_tail_mode(0);
+  // ---- 4. where the ridge is: CE forward time against the number of rows per head (weights streamed: 130.2 MB)
+  for (int pair : {-1, 0}) {
+    csm_set_gemm_cta_pair_mode(pair);
+    for (int rows : {32, 64, 128, 192, 232, 256, 384, 512}) {
+      std::vector<float> ts;
+      for (int it = 0; it < 13; ++it) {
+        CK(cudaMemsetAsync(flush, it, fl));
+        CK(cudaEventRecord(e0));
+        CSM(csm_linear_ce_fwd(H, W, T, loss[1], lse[1], rows, V, K, G, K, (int64_t)rows * K, K, (int64_t)V * K, 0, 1, rows,
+                              ws, wsb, 2, nullptr));
+        CK(cudaEventRecord(e1));
+        CK(cudaEventSynchronize(e1));
+        float ms;
+        CK(cudaEventElapsedTime(&ms, e0, e1));
+        if (it >= 3) ts.push_back(ms);
+      }
+      std::sort(ts.begin(), ts.end());
+      const double us = ts[ts.size() / 2] * 1e3;
+      printf("ce_fwd rows/head %3d pair mode %2d: %.1f us  (%.0f GB/s of weights, %.0f TFLOP/s useful)\n", rows, pair, us,
+             130.2e6 / (us * 1e-6) / 1e9, 2.0 * G * rows * (double)V * K / (us * 1e-6) / 1e12);
+    }
+  }
+  csm_set_gemm_cta_pair_mode(-1);
   printf(bad ? "RESULT: FAIL (%d)\n" : "RESULT: PASS\n", bad);
   return bad ? 4 : 0;
 }
