@@ -234,6 +234,21 @@ def oracle_backbone(model, tokens, tokens_mask) -> torch.Tensor:
     return model.backbone(h)          # mask=None => is_causal (same values as the indexed tril mask)
 
 
+def oracle_decoder_ce(model, hf: torch.Tensor, codes: torch.Tensor) -> torch.Tensor:
+    """A7 for Ns frames: hf [Ns, D] backbone states (model dtype), codes int64 [Ns, C] -> fp32 CE [Ns, C-1], column
+    i-1 = loss of code i.  X = projection([hf, emb(0,c_0) .. emb(C-2,c_{C-2})]), Y = decoder(X) causal over the C
+    positions, logits_i = Y[i] @ audio_head[i-1] (model.py:176-191)."""
+    dtype = next(model.parameters()).dtype
+    C = codes.shape[1]
+    V = model.audio_head.shape[2]
+    embs = [model._embed_audio(i, codes[:, i]) for i in range(C - 1)]
+    x = torch.stack([hf] + embs, dim=1)                        # [Ns, C, D]
+    y = model.decoder(model.projection(x)).to(dtype)           # [Ns, C, Dd]
+    logits = torch.einsum("ncd,cdv->ncv", y[:, 1:], model.audio_head)   # [Ns, C-1, V]
+    ce = F.cross_entropy(logits.float().reshape(-1, V), codes[:, 1:].reshape(-1), reduction="none")
+    return ce.view(-1, C - 1)
+
+
 def oracle_forward(model, tokens, tokens_mask, targets, frame_idx=None,
                    semantic_weight: float = 100.0, acoustic_weight: float = 1.0):
     """Returns (loss, {"semantic_loss","acoustic_loss","per_codebook_loss"[C]}).
@@ -255,14 +270,7 @@ def oracle_forward(model, tokens, tokens_mask, targets, frame_idx=None,
     if frame_idx is not None and frame_idx.numel() > 0:
         b_i, p_i = frame_idx[:, 0], frame_idx[:, 1]
         assert int(p_i.max()) < min(S - 1, targets.size(1))
-        hf = h[b_i, p_i]                                       # [Ns, D]
-        codes = targets[b_i, p_i]                              # [Ns, C]
-        embs = [model._embed_audio(i, codes[:, i]) for i in range(C - 1)]
-        x = torch.stack([hf] + embs, dim=1)                    # [Ns, C, D]
-        y = model.decoder(model.projection(x)).to(dtype)       # [Ns, C, Dd]
-        logits = torch.einsum("ncd,cdv->ncv", y[:, 1:], model.audio_head)   # [Ns, C-1, V]
-        ce = F.cross_entropy(logits.float().reshape(-1, V), codes[:, 1:].reshape(-1), reduction="none")
-        ce = ce.view(-1, C - 1)
+        ce = oracle_decoder_ce(model, h[b_i, p_i], targets[b_i, p_i])
         per_cb += list(ce.mean(0))
         ac = ce.mean()
     else:

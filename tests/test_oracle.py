@@ -189,6 +189,73 @@ def test_llama_stack_restatement_matches_transformers_llama():
     assert torch.allclose(x1.grad, x2.grad, atol=2e-5, rtol=1e-4), float((x1.grad - x2.grad).abs().max())
 
 
+def test_decoder_term_matches_transformers_csm_depth_decoder():
+    """The acoustic term the reference leaves as a placeholder (utils.py:109-117), restated in the oracle from
+    generate_frame (model.py:171-193), against the training loss of transformers' CSM port on the same weights:
+    ``CsmDepthDecoderForCausalLM`` takes [placeholder, c_0 .. c_{C-2}] with the backbone state written over position 0,
+    embeds position i with codebook i-1's table, projects, runs the depth decoder and scores position i with head i-1
+    against c_i (modeling_csm.py:441-488, 522-539, 565-623).  Same alignment, same mean over frames x (C-1) codes."""
+    pytest.importorskip("transformers")
+    try:
+        from transformers.models.csm.configuration_csm import CsmDepthDecoderConfig
+        from transformers.models.csm.modeling_csm import CsmDepthDecoderForCausalLM
+    except Exception as e:
+        pytest.skip(f"transformers has no CSM port: {e}")
+    torch.manual_seed(0)
+    C, V, D, Dd, H, KV, L, I = 8, 50, 96, 64, 4, 2, 2, 128
+    hd = Dd // H
+    cfg = O.OracleCfg(backbone=O.StackCfg(1, 2, 2, D, 64, 2048), decoder=O.StackCfg(L, H, KV, Dd, I, 2048),
+                      text_vocab_size=30, audio_vocab_size=V, audio_num_codebooks=C)
+    om = O.OracleModel(cfg)
+    O.init_weights(om, 3, std=0.08)
+    for m in om.decoder.modules():
+        if isinstance(m, tt.RMSNorm):
+            torch.nn.init.normal_(m.scale, mean=1.0, std=0.1)
+    try:
+        hc = CsmDepthDecoderConfig(
+            num_codebooks=C, backbone_hidden_size=D, vocab_size=V, hidden_size=Dd, intermediate_size=I,
+            num_hidden_layers=L, num_attention_heads=H, num_key_value_heads=KV, max_position_embeddings=33,
+            rms_norm_eps=1e-5,
+            rope_parameters={"rope_type": "llama3", "rope_theta": 500000.0, "factor": 32.0, "low_freq_factor": 1.0,
+                             "high_freq_factor": 4.0, "original_max_position_embeddings": 8192})
+        hc._attn_implementation = "eager"
+        hf = CsmDepthDecoderForCausalLM(hc).eval()
+    except Exception as e:                                   # config schema differs across transformers versions
+        pytest.skip(f"transformers CSM config API changed: {e}")
+
+    def halves(w, nh):                                       # interleaved pair layout -> HF's two-halves layout
+        w = w.view(nh, hd // 2, 2, -1)
+        return torch.cat([w[:, :, 0], w[:, :, 1]], 1).reshape(nh * hd, -1)
+
+    with torch.no_grad():
+        hf.model.embed_tokens.weight.copy_(om.audio_embeddings.weight)
+        hf.model.inputs_embeds_projector.weight.copy_(om.projection.weight)
+        hf.codebooks_head.weight.copy_(om.audio_head)
+        for a, b in zip(om.decoder.layers, hf.model.layers):
+            b.self_attn.q_proj.weight.copy_(halves(a.attn.q_proj.weight, H))
+            b.self_attn.k_proj.weight.copy_(halves(a.attn.k_proj.weight, KV))
+            b.self_attn.v_proj.weight.copy_(a.attn.v_proj.weight)
+            b.self_attn.o_proj.weight.copy_(a.attn.output_proj.weight)
+            b.mlp.gate_proj.weight.copy_(a.mlp.w1.weight)
+            b.mlp.down_proj.weight.copy_(a.mlp.w2.weight)
+            b.mlp.up_proj.weight.copy_(a.mlp.w3.weight)
+            b.input_layernorm.weight.copy_(a.sa_norm.scale)
+            b.post_attention_layernorm.weight.copy_(a.mlp_norm.scale)
+        hf.model.norm.weight.copy_(om.decoder.norm.scale)
+    Ns = 5
+    hrows = torch.randn(Ns, D)
+    codes = torch.randint(0, V, (Ns, C))
+    with torch.no_grad():
+        ce = O.oracle_decoder_ce(om, hrows, codes)                                   # [Ns, C-1]
+        ids = torch.nn.functional.pad(codes[:, : C - 1], (1, 0), value=0)
+        out = hf(input_ids=ids, backbone_last_hidden_state=hrows.clone(), labels=codes, use_cache=False)
+    assert out.logits.shape == (Ns, C - 1, V)
+    assert abs(float(ce.mean()) - float(out.loss)) < 1e-5 * float(out.loss)
+    per_code = torch.nn.functional.cross_entropy(out.logits.reshape(-1, V), codes[:, 1:].reshape(-1),
+                                                 reduction="none").view(Ns, C - 1)
+    assert torch.allclose(ce, per_code, atol=1e-4, rtol=1e-4)
+
+
 def test_attention_restatement_matches_dense_formula():
     torch.manual_seed(0)
     b, s, H, KV, hd = 2, 9, 4, 2, 8
