@@ -365,7 +365,8 @@ class LinearCEFn(Function):
     Returns (mean loss fp32 0-dim, per-row losses [M] fp32 (non-differentiable))."""
 
     @staticmethod
-    def forward(ctx, h2d, w, targets, count: int):
+    def forward(ctx, h2d, w, targets, count):
+        """`count`: rows the mean runs over — a Python int, or a 0-dim device tensor when it depends on the batch."""
         loss_rows, lse = ops.linear_ce_fwd(h2d, w, targets)
         ctx.save_for_backward(h2d, w, targets, lse)
         ctx.count = count
@@ -379,7 +380,12 @@ class LinearCEFn(Function):
         h, w, targets, lse = ctx.saved_tensors
         dh = torch.empty_like(h)
         dw = torch.empty_like(w) if ctx.needs_input_grad[1] else None
-        ops.linear_ce_bwd(h, w, targets, lse, 1.0 / ctx.count, grad_scale_dev=g.contiguous().float(), dh=dh, dw=dw)
+        g = g.contiguous().float()
+        if torch.is_tensor(ctx.count):
+            scale, g = 1.0, g / ctx.count
+        else:
+            scale = 1.0 / ctx.count
+        ops.linear_ce_bwd(h, w, targets, lse, scale, grad_scale_dev=g, dh=dh, dw=dw)
         return dh, dw, None, None
 
 

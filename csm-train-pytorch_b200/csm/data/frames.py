@@ -73,7 +73,9 @@ def collate_pinned(batch: List[Dict[str, torch.Tensor]], pin: bool = True,
                    pad_to_multiple: int = 1) -> Dict[str, torch.Tensor]:
     """Zero / False padding to the batch maximum (training_data.py:379-408) straight into pinned host tensors, so the
     trainer's H2D copies are asynchronous.  The target length is raised to the input length (the semantic term reads
-    targets[:, :S-1]); ``pad_to_multiple`` rounds the frame count up (e.g. 128: whole attention tiles)."""
+    targets[:, :S-1]); ``pad_to_multiple`` rounds the frame count up (e.g. 128: whole attention tiles).  One key more
+    than the reference's collate: ``target_lengths`` int64 [B], each sample's target frames before padding, so that the
+    decoder is never trained on padded all-zero code frames (Model.select_frames)."""
     S = max(b["input_tokens"].shape[0] for b in batch)
     S = (S + pad_to_multiple - 1) // pad_to_multiple * pad_to_multiple
     T = max(max(b["target_audio_tokens"].shape[0] for b in batch), S)
@@ -83,12 +85,14 @@ def collate_pinned(batch: List[Dict[str, torch.Tensor]], pin: bool = True,
     tok = torch.zeros(len(batch), S, W, dtype=torch.int64, pin_memory=pin)
     msk = torch.zeros(len(batch), S, W, dtype=torch.bool, pin_memory=pin)
     tgt = torch.zeros(len(batch), T, C, dtype=torch.int64, pin_memory=pin)
+    lens = torch.zeros(len(batch), dtype=torch.int64, pin_memory=pin)
     for i, b in enumerate(batch):
         s, t = b["input_tokens"].shape[0], b["target_audio_tokens"].shape[0]
         tok[i, :s] = b["input_tokens"]
         msk[i, :s] = b["input_masks"].bool()
         tgt[i, :t] = b["target_audio_tokens"]
-    return {"input_tokens": tok, "input_masks": msk, "target_audio_tokens": tgt}
+        lens[i] = t
+    return {"input_tokens": tok, "input_masks": msk, "target_audio_tokens": tgt, "target_lengths": lens}
 
 
 def length_bucketed_order(lengths: Sequence[int], batch_size: int, seed: int = 0, window: int = 50) -> List[List[int]]:

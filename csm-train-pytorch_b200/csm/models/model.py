@@ -248,31 +248,39 @@ class Model(nn.Module):
 
     @staticmethod
     def select_frames(tokens_mask: torch.Tensor, target_len: int, fraction: float = 1.0 / 16,
-                      generator: Optional[torch.Generator] = None) -> torch.Tensor:
-        """A8 (docs/reference/sesame_csm/training.md:58-62): per sample keep ceil(#audio/16) audio frames, uniformly
-        at random; returns int64 [N_sel, 2] of (b, p), p < min(S-1, T).  Runs on the host copy of the mask (the
-        data pipeline calls it before the H2D copy)."""
-        m = tokens_mask.detach().to("cpu")
-        B, S, W = m.shape
-        limit = min(S - 1, target_len)
+                      generator: Optional[torch.Generator] = None,
+                      target_lengths: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """A8 (docs/reference/sesame_csm/training.md:58-62): per sample keep ceil(T_b/16) of its TARGET frames,
+        uniformly at random; returns int64 [N_sel, 2] of (b, p).  Position p pairs the backbone state h[b,p] with the
+        target row targets[b,p,:] — the pairing the reference's semantic term fixes (utils.py:98-105) — so the valid
+        positions of sample b are p < min(S-1, T_b), T_b = that sample's true target length (``target_lengths``, carried
+        through collate; without it the padded length ``target_len``).  Frames in the zero-padded tail of the targets
+        are never selected.  Runs on the host (the data pipeline calls it before the H2D copy)."""
+        B, S = tokens_mask.shape[0], tokens_mask.shape[1]
+        lens = [int(target_len)] * B if target_lengths is None else [int(x) for x in target_lengths.tolist()]
         out = []
         for b in range(B):
-            cand = torch.nonzero(m[b, :limit, : W - 1].any(-1)).flatten()
-            if cand.numel() == 0:
+            limit = max(0, min(S - 1, int(target_len), lens[b]))
+            if limit == 0:
                 continue
-            keep = max(1, math.ceil(cand.numel() * fraction))
-            sel = cand[torch.randperm(cand.numel(), generator=generator)[:keep]].sort().values
+            keep = max(1, math.ceil(limit * fraction))
+            sel = torch.randperm(limit, generator=generator)[:keep].sort().values
             out.append(torch.stack([torch.full_like(sel, b), sel], dim=1))
         return torch.cat(out, 0) if out else torch.zeros(0, 2, dtype=torch.int64)
 
     def forward(self, tokens: torch.Tensor, tokens_mask: torch.Tensor,
                 target_audio_tokens: Optional[torch.Tensor] = None, *, frame_idx: Optional[torch.Tensor] = None,
                 decoder_frame_fraction: float = 1.0 / 16, semantic_weight: float = 100.0,
-                acoustic_weight: float = 1.0):
+                acoustic_weight: float = 1.0, target_lengths: Optional[torch.Tensor] = None,
+                mask_padded_targets: bool = False):
         """tokens int64 [B,S,33], tokens_mask bool [B,S,33], target_audio_tokens int64 [B,T,32].
 
         Returns (loss, {"semantic_loss", "acoustic_loss", "per_codebook_loss": fp32[32]}); with
         target_audio_tokens=None returns the backbone hidden state bf16 [B,S,D].
+
+        ``target_lengths`` int64 [B] (true target frames per sample before collate's zero padding): restricts the
+        decoder frame selection to real target frames, and with ``mask_padded_targets`` also drops the padded rows from
+        the semantic term (the reference averages over them, utils.py:101-105: the default keeps that).
         """
         if not tokens.is_cuda:
             raise RuntimeError("csm_b200: Model.forward needs CUDA tensors (no CPU fallback)")
@@ -290,11 +298,16 @@ class Model(nn.Module):
         # ---- semantic term (utils.py:98-107): position p predicts targets[b,p,0], p < S-1, mean over B*(S-1)
         tgt0 = torch.full((B, S), -1, dtype=torch.int64, device=tokens.device)
         tgt0[:, : S - 1] = target_audio_tokens[:, : S - 1, 0]
-        sem, _ = LinearCEFn.apply(hb.view(B * S, -1), self.codebook0_head.weight, tgt0.view(-1), B * (S - 1))
+        count = B * (S - 1)
+        if mask_padded_targets and target_lengths is not None:
+            tl = target_lengths.to(tokens.device).clamp(max=S - 1)
+            tgt0.masked_fill_(torch.arange(S, device=tokens.device)[None, :] >= tl[:, None], -1)
+            count = tl.sum().clamp(min=1).to(torch.float32)          # device scalar: graph-replayable
+        sem, _ = LinearCEFn.apply(hb.view(B * S, -1), self.codebook0_head.weight, tgt0.view(-1), count)
         per_cb = [sem.detach()]
         # ---- acoustic term (A7/A8)
         if frame_idx is None:
-            frame_idx = self.select_frames(tokens_mask, T, decoder_frame_fraction)
+            frame_idx = self.select_frames(tokens_mask, T, decoder_frame_fraction, target_lengths=target_lengths)
         frame_idx = frame_idx.to(tokens.device)
         if frame_idx.numel() > 0:
             Ns = frame_idx.shape[0]

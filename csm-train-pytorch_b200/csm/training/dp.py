@@ -55,6 +55,8 @@ class GradSynchronizer:
                 sparse_rows.is_cuda and os.environ.get("CSM_DP_DENSE_TEXT_GRAD", "0") != "1":
             self.sparse_param = sparse_rows
             self.params = [p for p in self.params if p is not sparse_rows]
+        self.text_capacity_seq = 2048        # frames per sample the text-row exchange is sized for (max_seq_len)
+        self.text_capacity_frames = None     # fixed by the first exchange
         self.accumulating = False            # True on all but the last micro-batch of an accumulation window
         self._hooks = []
         if not self.bucketed:
@@ -152,42 +154,51 @@ class GradSynchronizer:
     # ------------------------------------------------------------------ row-sparse text-embedding gradient
     def exchange_text_rows(self, tokens, mask, dh, table_shape) -> torch.Tensor:
         """Called by EmbedGatherSumFn.backward: returns the dense, rank-averaged text-embedding gradient.
-        Every rank contributes (tokens [B,S,C+1], mask [B,S,C+1], dh [B,S,D]); after the all-gathers each rank runs
-        the embedding scatter kernel over all ranks' frames (text column only).  Fixed shapes: graph-capturable."""
+        Every rank contributes its frames (tokens [B*S,C+1], mask [B*S,C+1], dh [B*S,D]) padded to a FIXED capacity
+        (``text_capacity_frames``); after the all-gathers each rank runs the embedding scatter kernel over all ranks'
+        frames (text column only).  The collective sequence and every message size are therefore the same on every rank
+        and in every step — whether a rank replays its CUDA graph or runs eagerly, and however ragged the batches are
+        (a data-dependent shape exchange in the eager path only would desynchronise NCCL)."""
         from .. import ops
         W = self.world
         dt = torch.zeros(table_shape, dtype=dh.dtype, device=dh.device)   # fresh: autograd may adopt it as .grad
         msk = mask.contiguous().view(torch.uint8) if mask.dtype == torch.bool else mask.to(torch.uint8).contiguous()
-        tokens, msk, dh = self.pad_to_common_frames(tokens, msk, dh)
+        tokens, msk, dh = self.pad_to_capacity(tokens, msk, dh)
         tok_all = torch.empty((W,) + tuple(tokens.shape), dtype=tokens.dtype, device=tokens.device)
         msk_all = torch.empty((W,) + tuple(msk.shape), dtype=torch.uint8, device=tokens.device)
         dh_all = torch.empty((W,) + tuple(dh.shape), dtype=dh.dtype, device=dh.device)
-        dist.all_gather_into_tensor(tok_all, tokens.contiguous(), group=self.group)
+        dist.all_gather_into_tensor(tok_all, tokens, group=self.group)
         dist.all_gather_into_tensor(msk_all, msk, group=self.group)
         dist.all_gather_into_tensor(dh_all, dh, group=self.group)
         dh_all.mul_(1.0 / W)                                     # mean over the ranks, like the bucket all-reduce(AVG)
-        B, S, Wc = tokens.shape
-        ops.embed_gather_sum_bwd(tok_all.view(W * B, S, Wc), msk_all.view(W * B, S, Wc), dh_all.view(W * B, S, -1),
+        F, Wc = tokens.shape
+        ops.embed_gather_sum_bwd(tok_all.view(W, F, Wc), msk_all.view(W, F, Wc), dh_all.view(W, F, -1),
                                  None, dt, 0, table_shape[0])
         return dt
 
-    def pad_to_common_frames(self, tokens, msk, dh):
-        """Ragged data: each rank pads its batch to its own longest sample, so [B, S] can differ between ranks while
-        the all-gathers need one shape.  Pads with masked-out frames (mask 0, dh 0: they scatter nothing) up to the
-        maximum over the ranks.  One tiny MAX all-reduce + host read per step; skipped while a CUDA graph is being
-        captured, where the shapes are static and equal by construction."""
-        if self.world == 1 or (tokens.is_cuda and torch.cuda.is_current_stream_capturing()):
-            return tokens, msk, dh
-        shape = torch.tensor([tokens.shape[0], tokens.shape[1]], dtype=torch.int64, device=tokens.device)
-        dist.all_reduce(shape, op=dist.ReduceOp.MAX, group=self.group)
-        Bm, Sm = (int(x) for x in shape.tolist())
+    def pad_to_capacity(self, tokens, msk, dh):
+        """[B,S,..] -> [capacity, ..] frame lists, padded with masked-out frames (mask 0, dh 0: they scatter nothing).
+        The capacity is fixed by the first exchange (frames of that batch rounded up to whole sequences of
+        ``text_capacity_seq`` frames, default 2048 = the model's max_seq_len), identically on every rank as long as
+        the ranks use the same batch size — no shape collective, no host read."""
         B, S = tokens.shape[0], tokens.shape[1]
-        if (Bm, Sm) == (B, S):
-            return tokens, msk, dh
+        frames = B * S
+        if self.text_capacity_frames is None:
+            seq = max(int(self.text_capacity_seq), 1)
+            self.text_capacity_frames = B * max(seq, -(-S // seq) * seq)
+        cap = self.text_capacity_frames
+        if frames > cap:
+            raise RuntimeError(
+                f"data-parallel text-embedding exchange: batch of {B} x {S} = {frames} frames exceeds the fixed capacity "
+                f"of {cap} frames set by the first step (every rank must use the same batch size; raise "
+                f"GradSynchronizer.text_capacity_seq for sequences longer than {self.text_capacity_seq})")
+        tokens, msk, dh = (t.reshape((frames,) + tuple(t.shape[2:])) for t in (tokens, msk, dh))
+        if frames == cap:
+            return tokens.contiguous(), msk.contiguous(), dh.contiguous()
 
         def grow(t):
-            out = t.new_zeros((Bm, Sm) + tuple(t.shape[2:]))
-            out[:B, :S] = t
+            out = t.new_zeros((cap,) + tuple(t.shape[1:]))
+            out[:frames] = t
             return out
         return grow(tokens), grow(msk), grow(dh)
 
@@ -197,26 +208,35 @@ class GradSynchronizer:
         if self.world == 1 and not self.bucketed:
             return
         if not self.bucketed:
-            grads = [p.grad for p in self.params if p.grad is not None]
-            if not grads:
+            # one flat fp32 buffer over ALL trainable parameters (fixed layout, kept across steps), filled and drained
+            # by multi-tensor copies.  A parameter without a gradient on this rank (e.g. the decoder adapters when the
+            # batch selected no decoder frame) contributes zeros: every rank issues the same all-reduce with the same
+            # count in every step.
+            if not self.params:
                 return
-            # one flat fp32 buffer (kept across steps), filled and drained by multi-tensor copies: a handful of
-            # launches instead of two per adapter tensor (~240 for r=8 q/v LoRA on CSM-1B)
-            n = sum(g.numel() for g in grads)
             flat = getattr(self, "_flat", None)
-            if flat is None or flat.numel() != n or flat.device != grads[0].device:
-                flat = self._flat = torch.empty(n, dtype=torch.float32, device=grads[0].device)
-            views, off = [], 0
-            for g in grads:
-                views.append(flat[off:off + g.numel()].view_as(g))
-                off += g.numel()
-            torch._foreach_copy_(views, grads)
+            if flat is None or flat.device != self.params[0].device:
+                n = sum(p.numel() for p in self.params)
+                flat = self._flat = torch.empty(n, dtype=torch.float32, device=self.params[0].device)
+                self._flat_views, off = [], 0
+                for p in self.params:
+                    self._flat_views.append(flat[off:off + p.numel()].view(p.shape))
+                    off += p.numel()
+            have = [(v, p.grad) for v, p in zip(self._flat_views, self.params) if p.grad is not None]
+            if len(have) != len(self.params):
+                flat.zero_()
+            if have:
+                torch._foreach_copy_([v for v, _ in have], [g for _, g in have])
             if dist.get_backend(self.group) == "nccl":
                 dist.all_reduce(flat, op=dist.ReduceOp.AVG, group=self.group)
             else:
                 dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group)
                 flat.mul_(1.0 / self.world)
-            torch._foreach_copy_(grads, views)
+            if have:
+                torch._foreach_copy_([g for _, g in have], [v for v, _ in have])
+            for v, p in zip(self._flat_views, self.params):
+                if p.grad is None:
+                    p.grad = v.to(p.dtype)
             return
         if self.accumulating:
             return

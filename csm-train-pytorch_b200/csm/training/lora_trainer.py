@@ -44,6 +44,9 @@ class CSMLoRATrainer:
         self.target_modules = target_modules or list(lora_mod.DEFAULT_TARGETS)
         self.target_layers, self.lora_use_bias = target_layers, lora_use_bias
         self.decoder_frame_fraction = 1.0 / 16
+        # batches from collate_pinned carry each sample's true target length: padded all-zero target frames are then
+        # left out of the semantic mean as well (the reference averages over them, utils.py:101-105; set False for that)
+        self.mask_padded_targets = True
         self.model = model
         self.optimizer = None
         self._sync = None
@@ -94,7 +97,8 @@ class CSMLoRATrainer:
         if "frame_idx" not in batch:
             batch = dict(batch)
             batch["frame_idx"] = Model.select_frames(batch["input_masks"], batch["target_audio_tokens"].shape[1],
-                                                     self.decoder_frame_fraction)
+                                                     self.decoder_frame_fraction,
+                                                     target_lengths=batch.get("target_lengths"))
         return {k: v.to(self.device, non_blocking=True) for k, v in batch.items()}
 
     def train_step(self, batch, max_grad_norm: float = 1.0) -> torch.Tensor:
@@ -105,7 +109,8 @@ class CSMLoRATrainer:
         if "frame_idx" not in batch:
             batch = dict(batch)
             batch["frame_idx"] = Model.select_frames(batch["input_masks"], batch["target_audio_tokens"].shape[1],
-                                                     self.decoder_frame_fraction)
+                                                     self.decoder_frame_fraction,
+                                                     target_lengths=batch.get("target_lengths"))
         self.global_step += 1
         if self._graphed is not None and max_grad_norm == self._graph_max_norm:
             return self._graphed(batch)
@@ -113,7 +118,9 @@ class CSMLoRATrainer:
 
     def _step_impl(self, b, max_grad_norm: float) -> torch.Tensor:
         loss, _ = compute_loss(self.model, b["input_tokens"], b["input_masks"], b["target_audio_tokens"],
-                               self.semantic_weight, self.acoustic_weight, frame_idx=b["frame_idx"])
+                               self.semantic_weight, self.acoustic_weight, frame_idx=b["frame_idx"],
+                                   target_lengths=b.get("target_lengths"),
+                                   mask_padded_targets=self.mask_padded_targets)
         loss.backward()
         self._sync.finish()
         clip_and_step(self.optimizer, list(self.get_lora_params().values()), max_grad_norm)
@@ -154,7 +161,9 @@ class CSMLoRATrainer:
             for batch in iterate_batches(val_dataset, batch_size, False):
                 b = self._to_device(batch)
                 loss, _ = compute_loss(self.model, b["input_tokens"], b["input_masks"], b["target_audio_tokens"],
-                                       self.semantic_weight, self.acoustic_weight, frame_idx=b["frame_idx"])
+                                       self.semantic_weight, self.acoustic_weight, frame_idx=b["frame_idx"],
+                                   target_lengths=b.get("target_lengths"),
+                                   mask_padded_targets=self.mask_padded_targets)
                 total += float(loss)
                 n += 1
         self.model.train()

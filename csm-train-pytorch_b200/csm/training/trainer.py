@@ -83,6 +83,9 @@ class CSMTrainer:
         self.acoustic_weight = acoustic_weight
         self.weight_decay = weight_decay
         self.decoder_frame_fraction = 1.0 / 16
+        # batches from collate_pinned carry each sample's true target length: padded all-zero target frames are then
+        # left out of the semantic mean as well (the reference averages over them, utils.py:101-105; set False for that)
+        self.mask_padded_targets = True
         self.model = None
         self.optimizer = None
         self._sync = None
@@ -131,6 +134,7 @@ class CSMTrainer:
         trainable = [p for p in self.model.parameters() if p.requires_grad]
         self._sync = dp.GradSynchronizer(trainable, bucket_bytes=64 << 20 if total > (32 << 20) else None,
                                          sparse_rows=self.model.text_embeddings.weight)
+        self._sync.text_capacity_seq = self.model.backbone.max_seq_len
         # text-embedding gradient: gathered rows instead of a dense 525 MB all-reduce (dp.exchange_text_rows)
         self.model._text_grad_exchange = self._sync.exchange_text_rows if self._sync.sparse_param is not None else None
         sink = self._sync if self._sync.bucketed else None
@@ -144,7 +148,9 @@ class CSMTrainer:
 
         def impl(b):
             loss, _ = compute_loss(self.model, b["input_tokens"], b["input_masks"], b["target_audio_tokens"],
-                                   self.semantic_weight, self.acoustic_weight, frame_idx=b["frame_idx"])
+                                   self.semantic_weight, self.acoustic_weight, frame_idx=b["frame_idx"],
+                                   target_lengths=b.get("target_lengths"),
+                                   mask_padded_targets=self.mask_padded_targets)
             loss.backward()
             self._sync.finish()
             clip_and_step(self.optimizer, [p for p in self.model.parameters() if p.requires_grad], max_grad_norm)
@@ -157,7 +163,8 @@ class CSMTrainer:
         if "frame_idx" not in batch:
             batch = dict(batch)
             batch["frame_idx"] = Model.select_frames(batch["input_masks"], batch["target_audio_tokens"].shape[1],
-                                                     self.decoder_frame_fraction)
+                                                     self.decoder_frame_fraction,
+                                                     target_lengths=batch.get("target_lengths"))
         if getattr(self, "_graphed", None) is not None:
             self.global_step += 1
             return self._graphed(batch)
@@ -169,7 +176,8 @@ class CSMTrainer:
         if "frame_idx" not in batch:                  # A8: chosen on the host copy, before the H2D copy
             batch = dict(batch)
             batch["frame_idx"] = Model.select_frames(batch["input_masks"], batch["target_audio_tokens"].shape[1],
-                                                     self.decoder_frame_fraction)
+                                                     self.decoder_frame_fraction,
+                                                     target_lengths=batch.get("target_lengths"))
         return {k: v.to(self.device, non_blocking=True) for k, v in batch.items()}
 
     def train_micro_batch(self, batch, accumulation_steps: int = 1, last: bool = True) -> torch.Tensor:
@@ -177,7 +185,9 @@ class CSMTrainer:
         self._sync.accumulating = not last
         b = self._to_device(batch)
         loss, _ = compute_loss(self.model, b["input_tokens"], b["input_masks"], b["target_audio_tokens"],
-                               self.semantic_weight, self.acoustic_weight, frame_idx=b["frame_idx"])
+                               self.semantic_weight, self.acoustic_weight, frame_idx=b["frame_idx"],
+                                   target_lengths=b.get("target_lengths"),
+                                   mask_padded_targets=self.mask_padded_targets)
         (loss / accumulation_steps).backward()
         return loss.detach()
 
@@ -237,7 +247,9 @@ class CSMTrainer:
             for batch in iterate_batches(val_dataset, batch_size, False):
                 b = self._to_device(batch)
                 loss, _ = compute_loss(self.model, b["input_tokens"], b["input_masks"], b["target_audio_tokens"],
-                                       self.semantic_weight, self.acoustic_weight, frame_idx=b["frame_idx"])
+                                       self.semantic_weight, self.acoustic_weight, frame_idx=b["frame_idx"],
+                                   target_lengths=b.get("target_lengths"),
+                                   mask_padded_targets=self.mask_padded_targets)
                 total += float(loss)
                 n += 1
         self.model.train()

@@ -112,6 +112,18 @@ int csm_adamw_clip_step(void* const* params, const void* const* grads, void* con
                         const int64_t* numel, const float* lr, const float* weight_decay, int32_t n_tensors, float beta1,
                         float beta2, float eps, float max_norm, float* step_dev, float* sq_norm_dev, csm_stream_t stream);
 
+/* Same step with the reference's precision (fp32 parameters + fp32 AdamW, trainer.py:107,166-173) and strided operands:
+ *   master      (nullable table) per-tensor fp32 master copy of the parameter: the update is applied to it and the bf16
+ *               parameter is re-derived by one rounding;  state_fp32 != 0: exp_avg / exp_avg_sq are fp32 (else bf16).
+ *   inner / p_stride / g_stride (nullable tables): tensor i is numel[i] / inner[i] runs of inner[i] contiguous elements,
+ *               p_stride[i] (parameter) resp. g_stride[i] (gradient) elements apart; inner[i] == numel[i] means dense.
+ *               master and the moments are always dense.  28 B/param in master + fp32-state mode. */
+int csm_adamw_clip_step_v2(void* const* params, const void* const* grads, void* const* exp_avg, void* const* exp_avg_sq,
+                           void* const* master, const int64_t* numel, const int64_t* inner, const int64_t* p_stride,
+                           const int64_t* g_stride, const float* lr, const float* weight_decay, int32_t n_tensors,
+                           float beta1, float beta2, float eps, float max_norm, int32_t state_fp32, float* step_dev,
+                           float* sq_norm_dev, csm_stream_t stream);
+
 /* ---- fused q|k|v projection + RoPE: C[M,N] = A[M,K] B[N,K]^T (+ A2 B2^T), then columns [0, rope_cols) — heads of
  * head_dim — are rotated by position (row % seq_len) exactly as csm_rope would (bf16 rounding of the projection first).
  * N must be a multiple of 32; returns CSM_ERR_SHAPE for shapes the tcgen05 GEMM does not take (then: csm_gemm_bf16 +

@@ -138,22 +138,39 @@ def _worker_ragged(rank, world, port, q):
     from csm.training.trainer import iterate_batches
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
-        # (1) ragged shapes: rank 0 holds [2, 5] frames, rank 1 [1, 7]; after padding both hold [2, 7] and the padding
-        #     is masked out with a zero upstream gradient, so the scatter kernel ignores it
+        # (1) ragged shapes: rank 0 holds [2, 5] frames, rank 1 [2, 7]; both pad their frame lists to the SAME fixed
+        #     capacity (batch x capacity sequence length) without talking to each other; the padding is masked out
+        #     with a zero upstream gradient, so the scatter kernel ignores it
         sync = dp.GradSynchronizer([torch.nn.Parameter(torch.zeros(3))], bucket_bytes=64)
-        B, S = (2, 5) if rank == 0 else (1, 7)
+        sync.text_capacity_seq = 8
+        B, S = (2, 5) if rank == 0 else (2, 7)
         tok = torch.arange(B * S * 3).view(B, S, 3) + 1
         msk = torch.ones(B, S, 3, dtype=torch.uint8)
         dh = torch.ones(B, S, 4)
-        t2, m2, d2 = sync.pad_to_common_frames(tok, msk, dh)
-        assert t2.shape == (2, 7, 3) and m2.shape == (2, 7, 3) and d2.shape == (2, 7, 4)
-        assert torch.equal(t2[:B, :S], tok) and torch.equal(m2[:B, :S], msk) and torch.equal(d2[:B, :S], dh)
+        t2, m2, d2 = sync.pad_to_capacity(tok, msk, dh)
+        assert t2.shape == (16, 3) and m2.shape == (16, 3) and d2.shape == (16, 4)
+        assert torch.equal(t2[:B * S], tok.view(-1, 3)) and torch.equal(m2[:B * S], msk.view(-1, 3))
         assert int(m2.sum()) == B * S * 3 and float(d2.sum()) == B * S * 4      # everything added is zero / masked
         gathered = torch.empty((world * t2.shape[0],) + tuple(t2.shape[1:]), dtype=t2.dtype)
-        dist.all_gather_into_tensor(gathered, t2)                                 # one shape on every rank now
-        # equal shapes: returned untouched
-        same = torch.zeros(2, 4, 3, dtype=torch.int64)
-        assert sync.pad_to_common_frames(same, same.to(torch.uint8), torch.zeros(2, 4, 4))[0] is same
+        dist.all_gather_into_tensor(gathered, t2)                                 # one shape on every rank
+        # a later, shorter batch (the ragged tail of an epoch) pads to the same capacity; a larger one is refused loudly
+        t3, _, _ = sync.pad_to_capacity(tok[:1, :3], msk[:1, :3], dh[:1, :3])
+        assert t3.shape == (16, 3)
+        try:
+            sync.pad_to_capacity(torch.zeros(3, 8, 3, dtype=torch.int64), torch.zeros(3, 8, 3, dtype=torch.uint8),
+                                 torch.zeros(3, 8, 4))
+            raise AssertionError("a batch above the fixed capacity must raise")
+        except RuntimeError:
+            pass
+        # (1b) LoRA flat exchange: rank 1 has no gradient for the second parameter (no decoder frame selected): both
+        #      ranks still issue one all-reduce of the same size, and the missing gradient counts as zero
+        pa, pb = torch.nn.Parameter(torch.zeros(4)), torch.nn.Parameter(torch.zeros(2, 3))
+        flat_sync = dp.GradSynchronizer([pa, pb])
+        pa.grad = torch.full((4,), float(rank + 1))
+        if rank == 0:
+            pb.grad = torch.full((2, 3), 4.0)
+        flat_sync.finish()
+        assert torch.allclose(pa.grad, torch.full((4,), 1.5)) and torch.allclose(pb.grad, torch.full((2, 3), 2.0))
         # (2) every rank sees the same number of batches even when the dataset does not divide evenly
         data = [{"input_tokens": torch.ones(3 + i, 33, dtype=torch.long),
                  "input_masks": torch.ones(3 + i, 33, dtype=torch.bool),

@@ -146,11 +146,18 @@ def test_synthetic_batch_contract_and_frame_selection():
     assert not msk[:, -4:].any() and (tok[:, -4:] == 0).all()                 # padding frames: zeros / False
     assert msk[:, :16, 32].all() and not msk[:, :16, :32].any()               # text frames
     assert fi.shape[1] == 2 and int(fi[:, 1].max()) < 63
+    # A8: ceil(T_b / 16) positions per sample out of the sample's REAL target frames, p < min(S-1, T_b) (ADVICE r1:
+    # never a frame from the zero-padded tail of the targets, whatever the input mask says)
     sel = Model.select_frames(msk, 64, 1 / 16, torch.Generator().manual_seed(0))
-    assert sel.shape == fi.shape
+    assert sel.shape == (2 * 4, 2) and int(sel[:, 1].max()) < 63              # ceil(63 / 16) = 4 per sample
+    lens = torch.tensor([20, 3])
+    sel = Model.select_frames(msk, 64, 1 / 16, torch.Generator().manual_seed(0), target_lengths=lens)
+    assert sel[:, 0].tolist() == [0, 0, 1]                                    # ceil(20/16) = 2, ceil(3/16) = 1
     for bb, p in sel.tolist():
-        assert msk[bb, p, :32].any() and p < 63                               # only audio frames, p < S-1
-    assert Model.select_frames(torch.zeros(1, 8, 33, dtype=torch.bool), 8).shape == (0, 2)
+        assert p < int(lens[bb])
+    sel = Model.select_frames(msk, 64, 1.0, target_lengths=torch.tensor([0, 100]))
+    assert sel[:, 0].tolist() == [1] * 63 and sel[:, 1].tolist() == list(range(63))   # no targets -> no frames; p < S-1
+    assert Model.select_frames(torch.zeros(1, 1, 33, dtype=torch.bool), 8).shape == (0, 2)
 
 
 def test_collate_pads_like_reference():
