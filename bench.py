@@ -145,6 +145,55 @@ def cpu_reference_step_rate(S, steps, warmup, lora_r=8, targets=None, mode="lora
             "ms_per_step": dt * 1e3}
 
 
+def gpu_stock_step_rate(device, mode, lora_r, targets, B, S, steps=5, warmup=2):
+    """SURVEY §8(d) / §0.1 "same box" comparator: the SAME step through stock PyTorch on the SAME GPU — the oracle model
+    (reference Model arithmetic + teacher-forced decoder term) in bf16 with cuBLAS GEMMs, SDPA attention,
+    F.cross_entropy and torch.optim.AdamW(fused) + clip_grad_norm_, same B / S / frame_idx, CUDA-event timed.  The
+    reference has no GPU kernels of its own; this is what its code does when moved to the device unchanged.  Runs
+    outside the repo's timed region; nothing of libcsm_b200 is on this path."""
+    from oracle import csm_oracle as O
+    cfg = O.cfg_csm_1b(max(2048, S))
+    with torch.device(device):
+        model = O.OracleModel(cfg)
+    g = torch.Generator(device=device).manual_seed(0)
+    with torch.no_grad():
+        for n, p in model.named_parameters():
+            if n.endswith(".scale"):
+                p.fill_(1.0)
+            else:
+                p.normal_(0.0, 0.02, generator=g)
+    model = model.to(torch.bfloat16)
+    if mode == "lora":
+        O.apply_lora(model, r=lora_r, alpha=16.0, target_modules=targets, seed=1)
+        model = model.to(device)
+    params = [p for p in model.parameters() if p.requires_grad]
+    opt = torch.optim.AdamW(params, lr=1e-4, weight_decay=0.01, fused=True)
+    batches = [{k: v.to(device) for k, v in O.synthetic_batch(cfg, B, S, seed=1234 + 97 * i).items()} for i in range(2)]
+
+    def one(i):
+        b = batches[i % 2]
+        loss, _ = O.oracle_forward(model, b["input_tokens"], b["input_masks"], b["target_audio_tokens"], b["frame_idx"])
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(params, 1.0)
+        opt.step()
+        opt.zero_grad(set_to_none=True)
+    for i in range(warmup):
+        one(i)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        one(i)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    del model, opt, params, batches
+    torch.cuda.empty_cache()
+    return {"value": B * S / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "steps": steps, "warmup": warmup,
+            "what": "stock PyTorch on the same GPU: oracle model in bf16 (cuBLAS + SDPA + F.cross_entropy + "
+                    "clip_grad_norm_ + torch.optim.AdamW(fused)), eager, same B / S / frame_idx"}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -200,6 +249,7 @@ def main():
     ap.add_argument("--seq", type=int, default=None)
     ap.add_argument("--cpu-seq", type=int, default=256, help="sequence length of the bounded CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-stock-baseline", action="store_true", help="skip the stock-PyTorch-on-GPU comparator")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="issue every kernel launch from Python (no CUDA graph)")
     args = ap.parse_args()
@@ -359,6 +409,16 @@ def main():
                 "step_model_tflops": step_flops / (ms_step * 1e-3) / 1e12,
                 "step_frac_of_peak": step_flops / (ms_step * 1e-3) / 1e12 / peak}
 
+    # ---- stock PyTorch on the same GPU (rank 0, N=1 only), outside every timed region of this repo's path
+    stock = None
+    if rank == 0 and world == 1 and not args.no_stock_baseline:
+        try:
+            stock = gpu_stock_step_rate(device, mode, r or 8, targets, B, S)
+            stock["speedup_of_this_repo"] = value / stock["value"]
+        except torch.OutOfMemoryError as e:      # the unfused path materialises [B,S,33,D] and full logits
+            stock = {"unavailable": f"out of memory: {str(e)[:120]}"}
+            torch.cuda.empty_cache()
+
     # ---- CPU baseline (rank 0, N=1 only): bounded sample of the same workload on the host cores
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -378,7 +438,7 @@ def main():
                            "l2": "per-step working set (3.1 GB weights + >4 GB activations) exceeds the 126 MB L2; "
                                  "4 distinct input batches cycled"},
                 "clocks": clk, "e2e": e2e, "gpu_launches": launches, "gpu_launches_per_step": launches / args.steps,
-                "roofline": roof, "cpu_baseline": cpu}
+                "roofline": roof, "cpu_baseline": cpu, "gpu_stock_baseline": stock}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

@@ -172,6 +172,33 @@ def test_compute_loss_contract(cuda):
     assert "acoustic_loss" in comp
 
 
+def test_reference_test_shape_b2_s5_matches_oracle(cuda):
+    """The reference's own fixture shape for this path (test_training.py:215-219: B=2, S=5, tokens < 100, all-ones
+    mask) — not just "a positive scalar": loss, semantic / acoustic terms, per-codebook losses and every gradient
+    against the oracle (whose semantic path is bit-equal to the reference's compute_loss, tests/golden/make_golden.py)."""
+    from csm.training.utils import compute_loss
+    from oracle import csm_oracle as O
+    orc, prod, cfg = _pair("tiny", cuda, lora=False)
+    B, S = 2, 5
+    g = torch.Generator().manual_seed(0)
+    tok = torch.randint(0, 100, (B, S, 33), generator=g)
+    msk = torch.ones(B, S, 33, dtype=torch.bool)
+    tgt = torch.randint(0, 100, (B, S, 32), generator=g)
+    fidx = torch.tensor([[0, 0], [0, 3], [1, 1], [1, 2], [1, 3]])              # p < S-1
+    ol, od = O.oracle_forward(orc, tok, msk, tgt, fidx)
+    ol.backward()
+    pl, pd = compute_loss(prod, tok.to(cuda), msk.to(cuda), tgt.to(cuda), frame_idx=fidx.to(cuda))
+    pl.backward()
+    torch.cuda.synchronize()
+    assert abs(float(pd["semantic_loss"]) - float(od["semantic_loss"])) <= LOSS_RTOL * float(od["semantic_loss"])
+    assert abs(float(pd["acoustic_loss"]) - float(od["acoustic_loss"])) <= LOSS_RTOL * float(od["acoustic_loss"])
+    _check(orc, prod, (ol.detach(), od), (pl.detach(), pd), min_cos=0.99)
+    # without an explicit frame_idx the model picks ceil(4/16) = 1 target frame per sample itself; the semantic term
+    # does not depend on that choice
+    pl2, pd2 = compute_loss(prod, tok.to(cuda), msk.to(cuda), tgt.to(cuda))
+    assert float(pd2["semantic_loss"]) == float(pd["semantic_loss"]) and float(pl2) > 0
+
+
 def test_no_cpu_fallback():
     from csm.models.model import Model, ModelArgs
     m = Model(ModelArgs("tiny-backbone", "tiny-decoder", 1000, 200, 32)).to(torch.bfloat16)

@@ -469,3 +469,35 @@ def test_linear_ce_grouped_heads(ops, cuda, backend, trans_w):
     assert cos(dy, y32.grad) > 0.999
     dwr = w32.grad if trans_w else w32.grad.transpose(1, 2)
     assert cos(dw, dwr) > 0.999
+
+
+@pytest.mark.parametrize("Ns", [64, 232, 1024])
+def test_linear_ce_grouped_heads_at_decoder_dimensions(ops, cuda, Ns):
+    """BASELINE config 5 shapes: 31 heads x [Dd = 1024 -> V = 2051] at N_sel in {64, 232, 1024} —
+    232 is the c2 / c3 decoder batch, 64 sits below one m-block, 1024 in the tensor-bound regime — through the tcgen05
+    fused-CE path, against F.cross_entropy on fp32 logits of the same bf16 operands: per-row loss, lse, dH and dW."""
+    g = torch.Generator().manual_seed(1000 + Ns)
+    C, Dd, V = 32, 1024, 2051
+    y = torch.randn(Ns, C, Dd, generator=g).to(BF).to(cuda)
+    head_t = (torch.randn(C - 1, V, Dd, generator=g) * 0.05).to(BF).to(cuda)      # the [31, V, Dd] TMA operand
+    codes = torch.randint(0, V, (Ns, C), generator=g).to(cuda)
+    codes[3, 5] = -1                                                              # an ignored (row, head)
+    hv = y[:, 1:]
+    loss, lse = ops.linear_ce_fwd(hv, head_t, codes[:, 1:], groups=C - 1, tgt_row_stride=C, tgt_group_stride=1,
+                                  backend=2)
+    y32, w32 = y.float().requires_grad_(True), head_t.float().requires_grad_(True)
+    logits = torch.einsum("ncd,cvd->ncv", y32[:, 1:], w32)
+    ref = F.cross_entropy(logits.reshape(-1, V), codes[:, 1:].reshape(-1), reduction="none",
+                          ignore_index=-1).view(Ns, C - 1)
+    assert torch.allclose(loss.t(), ref, atol=3e-3, rtol=3e-3), float((loss.t() - ref).abs().max())
+    assert torch.allclose(lse.t(), torch.logsumexp(logits, -1), atol=3e-3, rtol=1e-3)
+    assert float(loss[4, 3]) == 0.0
+    (ref.sum() / (Ns * (C - 1))).backward()
+    dy = torch.zeros_like(y)
+    dw = torch.zeros_like(head_t)
+    ops.linear_ce_bwd(hv, head_t, codes[:, 1:], lse, 1.0 / (Ns * (C - 1)), dh=dy[:, 1:], dw=dw, groups=C - 1,
+                      tgt_row_stride=C, tgt_group_stride=1, backend=2)
+    assert cos(dy, y32.grad) > 0.999 and rel_err(dy, y32.grad) < 2e-2
+    assert cos(dw, w32.grad) > 0.999 and rel_err(dw, w32.grad) < 2e-2
+    assert float(dy[3, 5].abs().max()) == 0.0                                      # the ignored (row, head) pair
+    assert float(dy[:, 0].abs().max()) == 0.0                                      # position 0 feeds no head
