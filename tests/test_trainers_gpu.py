@@ -267,8 +267,10 @@ def test_fused_adamw_row_strided_views_and_state_roundtrip(cuda):
         ov.step(max_grad_norm=1.0)
         od.step(max_grad_norm=1.0)
     for v, d in zip(views, dense):
-        assert torch.equal(v.detach().contiguous(), d.detach())
-        assert torch.equal(ov.state[v]["master"], od.state[d]["master"])
+        # same arithmetic up to fp32 contraction order (vector vs scalar loop) and the atomic order of the norm
+        assert torch.allclose(ov.state[v]["master"], od.state[d]["master"], rtol=2e-6, atol=1e-9)
+        assert torch.allclose(v.detach().float(), d.detach().float(), rtol=2.0 ** -7, atol=1e-9)
+        assert float((ov.state[v]["master"] - v.detach().float()).abs().max()) <= 2.0 ** -8 * float(v.abs().max())
     mask = torch.ones_like(big, dtype=torch.bool)
     for r, c in blocks:
         mask[r, c] = False
