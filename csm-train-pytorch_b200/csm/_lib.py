@@ -12,6 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("CSM_B200_LIB", os.path.join(os.path.dirname(_HERE), "libcsm_b200.so"))
 
 _lib = None
+ABI_VERSION = 2     # include/csm_b200.h CSM_ABI_VERSION
 
 _i32, _i64, _f32, _ptr, _sz = C.c_int32, C.c_int64, C.c_float, C.c_void_p, C.c_size_t
 
@@ -25,8 +26,8 @@ SIGNATURES = {
     "csm_embed_gather_sum_bwd": (_i32, [_ptr] * 5 + [_i64, _i32, _i64, _i64, _i32, _ptr]),
     "csm_decoder_input_fwd": (_i32, [_ptr] * 5 + [_i64, _i64, _i64, _i32, _i64, _i32, _ptr]),
     "csm_decoder_input_bwd": (_i32, [_ptr] * 5 + [_i64, _i64, _i64, _i32, _i64, _i32, _ptr]),
-    "csm_rmsnorm_fwd": (_i32, [_ptr] * 4 + [_i64, _i32, _f32, _ptr]),
-    "csm_rmsnorm_bwd": (_i32, [_ptr] * 7 + [_i64, _i32, _ptr]),
+    "csm_rmsnorm_fwd": (_i32, [_ptr] * 4 + [_i64, _i32, _f32, _i32, _ptr]),
+    "csm_rmsnorm_bwd": (_i32, [_ptr] * 7 + [_i64, _i32, _i32, _ptr]),
     "csm_rope": (_i32, [_ptr, _ptr, _i64, _i32, _i32, _i32, _i64, _i32, _ptr]),
     "csm_gemm_bf16": (_i32, [_ptr] * 4 + [_i64] * 7 + [_i32] * 4 + [_f32, _ptr, _ptr, _i64, _i64, _i64, _i32, _ptr]),
     "csm_gemm_bf16_rope": (_i32, [_ptr] * 3 + [_i64] * 6 + [_ptr, _ptr, _i64, _i64, _i64, _ptr, _i32, _i32, _i32, _ptr]),
@@ -72,8 +73,8 @@ def load():
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)          # AttributeError here == header/library mismatch: fail loudly
         fn.restype, fn.argtypes = res, args
-    if lib.csm_abi_version() != 1:
-        raise RuntimeError(f"libcsm_b200.so ABI version {lib.csm_abi_version()} != 1")
+    if lib.csm_abi_version() != ABI_VERSION:
+        raise RuntimeError(f"libcsm_b200.so ABI version {lib.csm_abi_version()} != {ABI_VERSION}: rebuild it")
     _lib = lib
     return lib
 

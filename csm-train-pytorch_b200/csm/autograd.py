@@ -19,6 +19,13 @@ BF16 = torch.bfloat16
 # 85 + 69 us for GEMM + swiglu_bwd at 4096 x 8192 x 2048; inside the step the unfused swiglu_bwd reads dact out of L2
 # and the whole step is 0.6 ms FASTER unfused (26.5 vs 27.1 ms), so the fused backward stays off (A/B switch, tested).
 FUSE_SWIGLU_BWD = False
+# The residual stream of both transformer stacks (x -> h = x + attn(..) -> out = h + mlp(..)) is kept in fp32 between
+# layers: the o-proj / down-proj GEMM epilogues add the fp32 residual and store fp32, RMSNorm reads fp32.  Measured
+# (tools/parity_probe*.py, profiles/r2_parity_*.txt): with a bf16 stream — what stock bf16 PyTorch does — the q/k
+# projection gradients of the late layers agree with the fp32 oracle only to cosine 0.9986-0.9989 (stock torch bf16:
+# 0.9986), because dS = P o (dP - delta) amplifies the rounding noise accumulated in the stream; with the fp32 stream
+# every trainable tensor clears the 0.999 gate.  Costs ~2 % of a step in extra bytes.  The gradient stream stays bf16.
+FP32_RESIDUAL = True
 
 
 # ----------------------------------------------------------------------------- A2: embedding gather-sum
@@ -106,11 +113,11 @@ class _Lin:
         self.iA = index_of[id(self.A)] if self.A is not None else -1
         self.iB = index_of[id(self.B)] if self.B is not None else -1
 
-    def fwd(self, x, residual=None):
+    def fwd(self, x, residual=None, out_dtype=BF16):
         if self.A is None:
-            return ops.gemm(x, self.w, residual=residual), None
+            return ops.gemm(x, self.w, residual=residual, out_dtype=out_dtype), None
         t = ops.gemm(x, self.A, alpha=self.s)                      # [N, r]
-        return ops.gemm(x, self.w, residual=residual, a2=t, b2=self.B), t
+        return ops.gemm(x, self.w, residual=residual, a2=t, b2=self.B, out_dtype=out_dtype), t
 
     def bwd(self, dy, x, t, grads, need, dx_out=None, accumulate=False, swiglu_gu=None):
         """Accumulates parameter grads into `grads` and returns dx (optionally accumulated into dx_out).
@@ -264,6 +271,7 @@ class StackFn(Function):
         index_of = {id(p): i for i, p in enumerate(params)}
         nq, nkv = H * hd, KV * hd
         cur = x.reshape(N, D).contiguous()
+        res_dtype = torch.float32 if FP32_RESIDUAL else BF16       # dtype of h / out (cur is bf16 for layer 0 only)
         saved = []
         for layer in stack.layers:
             a = layer.attn
@@ -275,14 +283,14 @@ class StackFn(Function):
             qkv, tqkv = gqkv.fwd(xn, rope=(cache, S, nq + nkv, hd))   # q and k heads rotated in the store epilogue
             q, k, v = qkv[:, :nq], qkv[:, nq:nq + nkv], qkv[:, nq + nkv:]
             o, lse = ops.attention_fwd(q, k, v, B, S, H, KV, hd)
-            h, to = lo.fwd(o, residual=cur)
+            h, to = lo.fwd(o, residual=cur, out_dtype=res_dtype)
             hn, rstd2 = ops.rmsnorm(h, layer.mlp_norm.scale, eps)
             if ops.swiglu_fusable(N, I, D):
                 gu, act, t13 = g13.fwd_swiglu(hn)
             else:
                 gu, t13 = g13.fwd(hn)
                 act = ops.swiglu(gu[:, :I], gu[:, I:])
-            out, t2 = l2.fwd(act, residual=h)
+            out, t2 = l2.fwd(act, residual=h, out_dtype=res_dtype)
             saved.append((cur, rstd1, xn, qkv, o, lse, h, rstd2, hn, gu, act, (tqkv, to, t13, t2),
                           (gqkv, lo, g13, l2), layer))
             cur = out

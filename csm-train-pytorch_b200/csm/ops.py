@@ -127,13 +127,15 @@ def decoder_input_bwd(dx, targets, frame_idx, dh, d_audio, codebooks: int, audio
 
 # ----------------------------------------------------------------------------- norm / rope / swiglu
 def rmsnorm(x, scale, eps: float) -> Tuple[torch.Tensor, torch.Tensor]:
+    """x bf16, or fp32 when it is the fp32 residual stream -> (y bf16, rstd fp32 [rows])."""
     _chk_cuda(x, scale)
     D = x.shape[-1]
     rows = x.numel() // D
-    y = torch.empty_like(x)
+    y = torch.empty(x.shape, dtype=BF16, device=x.device)
     rstd = torch.empty(rows, dtype=torch.float32, device=x.device)
     lib = _lib.load()
-    _lib.check(lib.csm_rmsnorm_fwd(_p(x), _p(scale), _p(y), _p(rstd), rows, D, eps, _st()), "rmsnorm_fwd")
+    _lib.check(lib.csm_rmsnorm_fwd(_p(x), _p(scale), _p(y), _p(rstd), rows, D, eps,
+                                   1 if x.dtype == torch.float32 else 0, _st()), "rmsnorm_fwd")
     return y, rstd
 
 
@@ -141,10 +143,10 @@ def rmsnorm_bwd(dy, x, scale, rstd, dres: Optional[torch.Tensor], dscale_f32: Op
     _chk_cuda(dy, x, scale, rstd, dres, dscale_f32)
     D = x.shape[-1]
     rows = x.numel() // D
-    dx = torch.empty_like(x)
+    dx = torch.empty(x.shape, dtype=BF16, device=x.device)
     lib = _lib.load()
     _lib.check(lib.csm_rmsnorm_bwd(_p(dy), _p(x), _p(scale), _p(rstd), _p(dres), _p(dx), _p(dscale_f32), rows, D,
-                                   _st()), "rmsnorm_bwd")
+                                   1 if x.dtype == torch.float32 else 0, _st()), "rmsnorm_bwd")
     return dx
 
 
@@ -296,9 +298,14 @@ def gemm(a, b, *, trans_a: bool = False, trans_b: bool = False, out: Optional[to
     if _gemm_prof is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
+    c_dtype = 1 if out.dtype == torch.float32 else 0
+    if residual is not None and residual.dtype == torch.float32:
+        if out.dtype != torch.float32:
+            raise RuntimeError("gemm: an fp32 residual needs an fp32 output (the fp32 residual stream)")
+        c_dtype |= 2                                   # CSM_DT_RES_F32
     _lib.check(lib.csm_gemm_bf16(_p(a), _p(b), _p(out), _p(residual), M, N, K, a.stride(0), b.stride(0),
                                  out.stride(0), residual.stride(0) if residual is not None else 0,
-                                 1 if trans_a else 0, 1 if trans_b else 0, 1 if out.dtype == torch.float32 else 0,
+                                 1 if trans_a else 0, 1 if trans_b else 0, c_dtype,
                                  1 if accumulate else 0, alpha, _p(a2), _p(b2), K2,
                                  a2.stride(0) if a2 is not None else 0, b2.stride(0) if b2 is not None else 0,
                                  be, _st()), "gemm_bf16")

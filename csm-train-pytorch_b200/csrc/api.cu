@@ -76,7 +76,9 @@ int gemm_dispatch(const void* A, const void* B, void* C, const void* R, int64_t 
                   int accumulate, float alpha, const void* A2, const void* B2, int64_t K2, int64_t lda2,
                   int64_t ldb2, int backend, cudaStream_t stream) {
   CSM_REQUIRE(M >= 0 && N >= 0 && K >= 0, CSM_ERR_SHAPE, "gemm: negative dimension");
-  CSM_REQUIRE(c_dtype == CSM_DT_BF16 || c_dtype == CSM_DT_F32, CSM_ERR_SHAPE, "gemm: bad c_dtype %d", c_dtype);
+  CSM_REQUIRE(c_dtype >= 0 && c_dtype <= (CSM_DT_F32 | CSM_DT_RES_F32), CSM_ERR_SHAPE, "gemm: bad c_dtype %d", c_dtype);
+  CSM_REQUIRE(!(c_dtype & CSM_DT_RES_F32) || (R && (c_dtype & CSM_DT_F32)), CSM_ERR_SHAPE,
+              "gemm: an fp32 residual needs R and an fp32 output");
   CSM_REQUIRE((A2 == nullptr) == (B2 == nullptr), CSM_ERR_SHAPE, "gemm: A2 and B2 must be given together");
   if (M == 0 || N == 0) return CSM_OK;
   const bool tc_ok = gemm_tc_supported(A, B, C, R, M, N, K, lda, ldb, ldc, ldr, transA, transB, c_dtype, A2, B2,

@@ -11,7 +11,7 @@ struct SimtGemmArgs {
   const bf16* A; const bf16* B; void* C; const bf16* R;
   int64_t M, N, K, sAm, sAk, sBn, sBk, ldc, ldr;
   const bf16* A2; const bf16* B2; int64_t K2, lda2, ldb2;
-  int c_f32, accumulate, transA, transB;
+  int c_f32, r_f32, accumulate, transA, transB;
   float alpha;
 };
 
@@ -78,7 +78,7 @@ __global__ void __launch_bounds__(SG_THREADS) gemm_simt_kernel(SimtGemmArgs a) {
       const int64_t n = n0 + tx * 4 + j;
       if (n >= a.N) continue;
       float v = a.alpha * acc[i][j];
-      if (a.R) v += __bfloat162float(a.R[m * a.ldr + n]);
+      if (a.R) v += a.r_f32 ? reinterpret_cast<const float*>(a.R)[m * a.ldr + n] : __bfloat162float(a.R[m * a.ldr + n]);
       if (a.c_f32) {
         float* c = reinterpret_cast<float*>(a.C) + m * a.ldc + n;
         *c = a.accumulate ? (*c + v) : v;
@@ -102,7 +102,7 @@ int gemm_simt_launch(const void* A, const void* B, void* C, const void* R, int64
   a.sBn = transB ? 1 : ldb; a.sBk = transB ? ldb : 1;
   a.ldc = ldc; a.ldr = ldr;
   a.A2 = (const bf16*)A2; a.B2 = (const bf16*)B2; a.K2 = (A2 && B2) ? K2 : 0; a.lda2 = lda2; a.ldb2 = ldb2;
-  a.c_f32 = (c_dtype == CSM_DT_F32); a.accumulate = accumulate; a.transA = transA; a.transB = transB;
+  a.c_f32 = (c_dtype & CSM_DT_F32) != 0; a.r_f32 = (c_dtype & CSM_DT_RES_F32) != 0; a.accumulate = accumulate; a.transA = transA; a.transB = transB;
   a.alpha = alpha;
   dim3 grid((unsigned)((N + SG_BN - 1) / SG_BN), (unsigned)((M + SG_BM - 1) / SG_BM));
   gemm_simt_kernel<<<grid, SG_THREADS, 0, stream>>>(a);

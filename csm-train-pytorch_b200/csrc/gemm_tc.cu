@@ -42,7 +42,7 @@ struct GemmTcParams {
   // EPI_STORE
   void* C; const bf16* R;
   int64_t ldc, ldr, c_group_stride, r_group_stride;
-  int c_f32, accumulate;
+  int c_f32, r_f32, accumulate;
   float alpha;
   // SwiGLU epilogues: C = gate|up buffer [M, 2*inter] (fwd: written, bwd: R = gate|up read, C = dgate|dup written),
   // C2 = act [M, inter] (fwd)
@@ -431,12 +431,50 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                              p.ldc, lane, w, wrows);
             continue;
           }
+          if (p.c_f32 && !p.accumulate && n + 32 <= p.N && (p.ldc & 3) == 0 &&
+              (!rrow || (p.ldr & (p.r_f32 ? 3 : 7)) == 0)) {
+            // warp-uniform fp32 output (the fp32 residual stream: o-proj / down-proj): alpha, residual (fp32 or bf16),
+            // then two 32 x 16 fp32 half tiles through the staging tile (64 B per row, like the bf16 32 x 32 tile)
+            float f[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]) * p.alpha;
+            if (rrow && row_ok) {
+              if (p.r_f32) {
+                const float* r32 = reinterpret_cast<const float*>(p.R) + (int64_t)g * p.r_group_stride + m * p.ldr + n;
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                  const float4 r4 = *reinterpret_cast<const float4*>(r32 + q * 4);
+                  f[q * 4 + 0] += r4.x; f[q * 4 + 1] += r4.y; f[q * 4 + 2] += r4.z; f[q * 4 + 3] += r4.w;
+                }
+              } else {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                  const uint4 r4 = *reinterpret_cast<const uint4*>(rrow + n + q * 8);
+                  f[q * 8 + 0] += bf16_lo(r4.x); f[q * 8 + 1] += bf16_hi(r4.x);
+                  f[q * 8 + 2] += bf16_lo(r4.y); f[q * 8 + 3] += bf16_hi(r4.y);
+                  f[q * 8 + 4] += bf16_lo(r4.z); f[q * 8 + 5] += bf16_hi(r4.z);
+                  f[q * 8 + 6] += bf16_lo(r4.w); f[q * 8 + 7] += bf16_hi(r4.w);
+                }
+              }
+            }
+            float* c32 = reinterpret_cast<float*>(p.C) + (int64_t)g * p.c_group_stride + wm0 * p.ldc + n;
+            store_tile_32x32(stage_s, reinterpret_cast<bf16*>(c32), 2 * p.ldc, lane,
+                             reinterpret_cast<const uint32_t*>(f), wrows);
+            store_tile_32x32(stage_s, reinterpret_cast<bf16*>(c32 + 16), 2 * p.ldc, lane,
+                             reinterpret_cast<const uint32_t*>(f) + 16, wrows);
+            continue;
+          }
           if (!row_ok) continue;
           float f[32];
 #pragma unroll
           for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]) * p.alpha;
           const bool full_vec = (n + 32 <= p.N);
-          if (rrow) {
+          if (rrow && p.r_f32) {
+            const float* r32 = reinterpret_cast<const float*>(p.R) + (int64_t)g * p.r_group_stride + m * p.ldr + n;
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (n + i < p.N) f[i] += r32[i];
+          } else if (rrow) {
             if (full_vec && (p.ldr % 8 == 0)) {
 #pragma unroll
               for (int q = 0; q < 4; ++q) {
@@ -922,7 +960,8 @@ int gemm_tc_launch_rope(const void* A, const void* B, void* C, const void* R, in
   GemmTcParams p{};
   p.M = M; p.N = N; p.K = K; p.groups = 1;
   p.C = C; p.R = (const bf16*)R; p.ldc = ldc; p.ldr = ldr;
-  p.c_f32 = (c_dtype == CSM_DT_F32); p.accumulate = accumulate; p.alpha = alpha;
+  p.c_f32 = (c_dtype & CSM_DT_F32) != 0; p.r_f32 = (c_dtype & CSM_DT_RES_F32) != 0;
+  p.accumulate = accumulate; p.alpha = alpha;
   p.rope_cache = rope_cache; p.rope_seq = rope_seq; p.rope_cols = rope_cols; p.rope_hd = rope_hd;
   return gemm_tc_run(o, p, EPI_STORE, stream);
 }

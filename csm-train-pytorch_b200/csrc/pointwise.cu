@@ -30,23 +30,35 @@ __device__ __forceinline__ uint4 pack8(const float* f) {
 }
 __device__ __forceinline__ float round_bf16(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
 
+// 8 consecutive elements of a row that is stored in bf16 or (the fp32 residual stream) in fp32
+template <bool XF32>
+__device__ __forceinline__ void load8x(const void* base, int64_t elem, float* f) {
+  if (XF32) {
+    const float* p = reinterpret_cast<const float*>(base) + elem;
+    const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+    f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+  } else {
+    unpack8(ld_nc16(reinterpret_cast<const bf16*>(base) + elem), f);
+  }
+}
+
+// XF32: x is the fp32 residual stream; the normalised value is then rounded ONCE, after the scale (torchtune's
+// `.type_as(x)` is a no-op for an fp32 x); for a bf16 x the reference's two roundings are kept.
+template <bool XF32>
 __global__ void __launch_bounds__(kNormThreads)
-rmsnorm_fwd_kernel(const bf16* __restrict__ x, const bf16* __restrict__ scale, bf16* __restrict__ y,
+rmsnorm_fwd_kernel(const void* __restrict__ x, const bf16* __restrict__ scale, bf16* __restrict__ y,
                    float* __restrict__ rstd, int64_t rows, int D, float eps) {
   __shared__ float red[32];
   for (int64_t r = blockIdx.x; r < rows; r += gridDim.x) {
-    const bf16* xr = x + r * D;
-    uint4 v[kNormMaxChunks];
+    float v[kNormMaxChunks][8];
     float ss = 0.f;
 #pragma unroll
     for (int c = 0; c < kNormMaxChunks; ++c) {
       const int d0 = (c * kNormThreads + threadIdx.x) * 8;
       if (d0 < D) {
-        v[c] = *reinterpret_cast<const uint4*>(xr + d0);
-        float f[8];
-        unpack8(v[c], f);
+        load8x<XF32>(x, r * D + d0, v[c]);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) ss += f[i] * f[i];
+        for (int i = 0; i < 8; ++i) ss += v[c][i] * v[c][i];
       }
     }
     ss = block_sum(ss, red);
@@ -57,18 +69,18 @@ rmsnorm_fwd_kernel(const bf16* __restrict__ x, const bf16* __restrict__ scale, b
       const int d0 = (c * kNormThreads + threadIdx.x) * 8;
       if (d0 < D) {
         float f[8], s[8];
-        unpack8(v[c], f);
         unpack8(*reinterpret_cast<const uint4*>(scale + d0), s);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) f[i] = round_bf16(f[i] * rs) * s[i];
+        for (int i = 0; i < 8; ++i) f[i] = XF32 ? v[c][i] * rs * s[i] : round_bf16(v[c][i] * rs) * s[i];
         *reinterpret_cast<uint4*>(y + r * D + d0) = pack8(f);
       }
     }
   }
 }
 
+template <bool XF32>
 __global__ void __launch_bounds__(kNormThreads)
-rmsnorm_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, const bf16* __restrict__ scale,
+rmsnorm_bwd_kernel(const bf16* __restrict__ dy, const void* __restrict__ x, const bf16* __restrict__ scale,
                    const float* __restrict__ rstd, const bf16* __restrict__ dres, bf16* __restrict__ dx,
                    float* __restrict__ dscale, int64_t rows, int D) {
   __shared__ float red[32];
@@ -86,7 +98,7 @@ rmsnorm_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, cons
       const int d0 = (c * kNormThreads + threadIdx.x) * 8;
       if (d0 < D) {
         float g[8], s[8];
-        unpack8(*reinterpret_cast<const uint4*>(x + r * D + d0), xh[c]);
+        load8x<XF32>(x, r * D + d0, xh[c]);
         unpack8(*reinterpret_cast<const uint4*>(dy + r * D + d0), g);
         unpack8(*reinterpret_cast<const uint4*>(scale + d0), s);
 #pragma unroll
@@ -130,44 +142,39 @@ rmsnorm_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, cons
 
 // ---- warp-per-row RMSNorm for D = 256 * VPL (CSM-1B: 2048 and 1024).  No block barriers, VPL independent 16-byte
 // loads per tensor in flight per lane (the CTA-per-row kernels above keep one and are latency-bound at ~2.5 TB/s).
-template <int VPL>
+template <int VPL, bool XF32>
 __global__ void __launch_bounds__(256)
-rmsnorm_fwd_warp_kernel(const bf16* __restrict__ x, const bf16* __restrict__ scale, bf16* __restrict__ y,
+rmsnorm_fwd_warp_kernel(const void* __restrict__ x, const bf16* __restrict__ scale, bf16* __restrict__ y,
                         float* __restrict__ rstd, int64_t rows, float eps) {
   constexpr int D = 256 * VPL;
   const int lane = threadIdx.x & 31;
   const int64_t nw = (int64_t)gridDim.x * (blockDim.x >> 5);
   for (int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); r < rows; r += nw) {
-    const bf16* xr = x + r * D;
-    uint4 v[VPL];
+    float v[VPL][8];
 #pragma unroll
-    for (int c = 0; c < VPL; ++c) v[c] = ld_nc16(xr + (c * 32 + lane) * 8);
+    for (int c = 0; c < VPL; ++c) load8x<XF32>(x, r * D + (c * 32 + lane) * 8, v[c]);
     float ss = 0.f;
 #pragma unroll
-    for (int c = 0; c < VPL; ++c) {
-      float f[8];
-      unpack8(v[c], f);
+    for (int c = 0; c < VPL; ++c)
 #pragma unroll
-      for (int i = 0; i < 8; ++i) ss += f[i] * f[i];
-    }
+      for (int i = 0; i < 8; ++i) ss += v[c][i] * v[c][i];
     ss = warp_sum(ss);
     const float rs = rsqrtf(ss / (float)D + eps);
     if (lane == 0 && rstd) rstd[r] = rs;
 #pragma unroll
     for (int c = 0; c < VPL; ++c) {
       float f[8], s[8];
-      unpack8(v[c], f);
       unpack8(*reinterpret_cast<const uint4*>(scale + (c * 32 + lane) * 8), s);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) f[i] = round_bf16(f[i] * rs) * s[i];
+      for (int i = 0; i < 8; ++i) f[i] = XF32 ? v[c][i] * rs * s[i] : round_bf16(v[c][i] * rs) * s[i];
       *reinterpret_cast<uint4*>(y + r * D + (c * 32 + lane) * 8) = pack8(f);
     }
   }
 }
 
-template <int VPL>
+template <int VPL, bool XF32>
 __global__ void __launch_bounds__(256)
-rmsnorm_bwd_warp_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, const bf16* __restrict__ scale,
+rmsnorm_bwd_warp_kernel(const bf16* __restrict__ dy, const void* __restrict__ x, const bf16* __restrict__ scale,
                         const float* __restrict__ rstd, const bf16* __restrict__ dres, bf16* __restrict__ dx,
                         float* __restrict__ dscale, int64_t rows) {
   constexpr int D = 256 * VPL;
@@ -184,10 +191,11 @@ rmsnorm_bwd_warp_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x,
     __syncthreads();
   }
   for (int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); r < rows; r += nw) {
-    uint4 vx[VPL], vg[VPL], ve[VPL];
+    float vx[VPL][8];
+    uint4 vg[VPL], ve[VPL];
 #pragma unroll
     for (int c = 0; c < VPL; ++c) {
-      vx[c] = ld_nc16(x + r * D + (c * 32 + lane) * 8);
+      load8x<XF32>(x, r * D + (c * 32 + lane) * 8, vx[c]);
       vg[c] = ld_nc16(dy + r * D + (c * 32 + lane) * 8);
       if (dres) ve[c] = ld_nc16(dres + r * D + (c * 32 + lane) * 8);
     }
@@ -196,7 +204,8 @@ rmsnorm_bwd_warp_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x,
 #pragma unroll
     for (int c = 0; c < VPL; ++c) {
       float xh[8], g[8], s[8];
-      unpack8(vx[c], xh);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) xh[i] = vx[c][i];
       unpack8(vg[c], g);
       unpack8(*reinterpret_cast<const uint4*>(scale + (c * 32 + lane) * 8), s);
 #pragma unroll
@@ -210,7 +219,8 @@ rmsnorm_bwd_warp_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x,
 #pragma unroll
     for (int c = 0; c < VPL; ++c) {
       float xh[8], g[8], s[8], o[8];
-      unpack8(vx[c], xh);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) xh[i] = vx[c][i];
       unpack8(vg[c], g);
       unpack8(*reinterpret_cast<const uint4*>(scale + (c * 32 + lane) * 8), s);
 #pragma unroll
@@ -341,55 +351,58 @@ static inline unsigned grid_for(int64_t work_items, int threads, int max_waves =
 using namespace csm;
 
 extern "C" int csm_rmsnorm_fwd(const void* x, const void* scale, void* y, float* rstd, int64_t rows,
-                               int32_t dim, float eps, csm_stream_t stream) {
+                               int32_t dim, float eps, int32_t x_dtype, csm_stream_t stream) {
   CSM_REQUIRE(rows >= 0 && dim > 0 && dim % 8 == 0 && dim <= kNormThreads * 8 * kNormMaxChunks, CSM_ERR_SHAPE,
               "rmsnorm_fwd: dim=%d must be a multiple of 8 and <= %d", dim, kNormThreads * 8 * kNormMaxChunks);
+  CSM_REQUIRE(x_dtype == CSM_DT_BF16 || x_dtype == CSM_DT_F32, CSM_ERR_SHAPE, "rmsnorm_fwd: bad x_dtype %d", x_dtype);
   CSM_REQUIRE(aligned16(x) && aligned16(y) && aligned16(scale), CSM_ERR_ALIGN, "rmsnorm_fwd: misaligned pointer");
   if (rows == 0) return CSM_OK;
+  const bool f32 = x_dtype == CSM_DT_F32;
+  cudaStream_t st = as_stream(stream);
   if ((dim == 2048 || dim == 1024) && rows >= 64) {
     const int64_t ctas = (rows + 7) / 8, cap = (int64_t)num_sms() * 8;
     const unsigned g = (unsigned)(ctas < cap ? ctas : cap);
-    if (dim == 2048)
-      rmsnorm_fwd_warp_kernel<8><<<g, 256, 0, as_stream(stream)>>>((const bf16*)x, (const bf16*)scale, (bf16*)y, rstd,
-                                                                   rows, eps);
-    else
-      rmsnorm_fwd_warp_kernel<4><<<g, 256, 0, as_stream(stream)>>>((const bf16*)x, (const bf16*)scale, (bf16*)y, rstd,
-                                                                   rows, eps);
+    const bf16* sc = (const bf16*)scale;
+    if (dim == 2048 && f32) rmsnorm_fwd_warp_kernel<8, true><<<g, 256, 0, st>>>(x, sc, (bf16*)y, rstd, rows, eps);
+    else if (dim == 2048) rmsnorm_fwd_warp_kernel<8, false><<<g, 256, 0, st>>>(x, sc, (bf16*)y, rstd, rows, eps);
+    else if (f32) rmsnorm_fwd_warp_kernel<4, true><<<g, 256, 0, st>>>(x, sc, (bf16*)y, rstd, rows, eps);
+    else rmsnorm_fwd_warp_kernel<4, false><<<g, 256, 0, st>>>(x, sc, (bf16*)y, rstd, rows, eps);
     CSM_CHECK_LAUNCH("rmsnorm_fwd");
     return CSM_OK;
   }
   unsigned grid = (unsigned)(rows < (int64_t)num_sms() * 8 ? rows : (int64_t)num_sms() * 8);
-  rmsnorm_fwd_kernel<<<grid, kNormThreads, 0, as_stream(stream)>>>((const bf16*)x, (const bf16*)scale, (bf16*)y,
-                                                                   rstd, rows, dim, eps);
+  if (f32) rmsnorm_fwd_kernel<true><<<grid, kNormThreads, 0, st>>>(x, (const bf16*)scale, (bf16*)y, rstd, rows, dim, eps);
+  else rmsnorm_fwd_kernel<false><<<grid, kNormThreads, 0, st>>>(x, (const bf16*)scale, (bf16*)y, rstd, rows, dim, eps);
   CSM_CHECK_LAUNCH("rmsnorm_fwd");
   return CSM_OK;
 }
 
 extern "C" int csm_rmsnorm_bwd(const void* dy, const void* x, const void* scale, const float* rstd,
                                const void* dres, void* dx, float* dscale_f32, int64_t rows, int32_t dim,
-                               csm_stream_t stream) {
+                               int32_t x_dtype, csm_stream_t stream) {
   CSM_REQUIRE(rows >= 0 && dim > 0 && dim % 8 == 0 && dim <= kNormThreads * 8 * kNormMaxChunks, CSM_ERR_SHAPE,
               "rmsnorm_bwd: bad dim=%d", dim);
+  CSM_REQUIRE(x_dtype == CSM_DT_BF16 || x_dtype == CSM_DT_F32, CSM_ERR_SHAPE, "rmsnorm_bwd: bad x_dtype %d", x_dtype);
   CSM_REQUIRE(aligned16(x) && aligned16(dy) && aligned16(dx) && aligned16(scale) && aligned16(dres),
               CSM_ERR_ALIGN, "rmsnorm_bwd: misaligned pointer");
   if (rows == 0) return CSM_OK;
+  const bool f32 = x_dtype == CSM_DT_F32;
+  cudaStream_t st = as_stream(stream);
+  const bf16 *gy = (const bf16*)dy, *sc = (const bf16*)scale, *dr = (const bf16*)dres;
   if ((dim == 2048 || dim == 1024) && rows >= 64) {
     // with dscale the grid stays small (one smem reduction + D global atomics per CTA), without it rows spread wide
     const int64_t ctas = (rows + 7) / 8, cap = (int64_t)num_sms() * (dscale_f32 ? 2 : 6);
     const unsigned g = (unsigned)(ctas < cap ? ctas : cap);
-    if (dim == 2048)
-      rmsnorm_bwd_warp_kernel<8><<<g, 256, 0, as_stream(stream)>>>((const bf16*)dy, (const bf16*)x, (const bf16*)scale,
-                                                                   rstd, (const bf16*)dres, (bf16*)dx, dscale_f32, rows);
-    else
-      rmsnorm_bwd_warp_kernel<4><<<g, 256, 0, as_stream(stream)>>>((const bf16*)dy, (const bf16*)x, (const bf16*)scale,
-                                                                   rstd, (const bf16*)dres, (bf16*)dx, dscale_f32, rows);
+    if (dim == 2048 && f32) rmsnorm_bwd_warp_kernel<8, true><<<g, 256, 0, st>>>(gy, x, sc, rstd, dr, (bf16*)dx, dscale_f32, rows);
+    else if (dim == 2048) rmsnorm_bwd_warp_kernel<8, false><<<g, 256, 0, st>>>(gy, x, sc, rstd, dr, (bf16*)dx, dscale_f32, rows);
+    else if (f32) rmsnorm_bwd_warp_kernel<4, true><<<g, 256, 0, st>>>(gy, x, sc, rstd, dr, (bf16*)dx, dscale_f32, rows);
+    else rmsnorm_bwd_warp_kernel<4, false><<<g, 256, 0, st>>>(gy, x, sc, rstd, dr, (bf16*)dx, dscale_f32, rows);
     CSM_CHECK_LAUNCH("rmsnorm_bwd");
     return CSM_OK;
   }
   unsigned grid = (unsigned)(rows < (int64_t)num_sms() * 2 ? rows : (int64_t)num_sms() * 2);
-  rmsnorm_bwd_kernel<<<grid, kNormThreads, 0, as_stream(stream)>>>((const bf16*)dy, (const bf16*)x,
-                                                                   (const bf16*)scale, rstd, (const bf16*)dres,
-                                                                   (bf16*)dx, dscale_f32, rows, dim);
+  if (f32) rmsnorm_bwd_kernel<true><<<grid, kNormThreads, 0, st>>>(gy, x, sc, rstd, dr, (bf16*)dx, dscale_f32, rows, dim);
+  else rmsnorm_bwd_kernel<false><<<grid, kNormThreads, 0, st>>>(gy, x, sc, rstd, dr, (bf16*)dx, dscale_f32, rows, dim);
   CSM_CHECK_LAUNCH("rmsnorm_bwd");
   return CSM_OK;
 }

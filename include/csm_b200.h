@@ -27,7 +27,7 @@ extern "C" {
 
 typedef void* csm_stream_t; /* cudaStream_t */
 
-#define CSM_ABI_VERSION 1
+#define CSM_ABI_VERSION 2
 
 #define CSM_OK 0
 #define CSM_ERR_SHAPE (-1)
@@ -37,6 +37,9 @@ typedef void* csm_stream_t; /* cudaStream_t */
 
 #define CSM_DT_BF16 0
 #define CSM_DT_F32 1
+/* OR'ed into csm_gemm_bf16's c_dtype next to CSM_DT_F32: the residual R is fp32 as well (the fp32 residual stream of
+ * the transformer stacks: h = x + attn(...), out = h + mlp(...) never round to bf16 between layers) */
+#define CSM_DT_RES_F32 2
 
 /* GEMM back-end selector (csm_gemm_bf16 `backend`): AUTO picks tcgen05 when the shape is tileable. */
 #define CSM_GEMM_AUTO 0
@@ -76,12 +79,14 @@ int csm_decoder_input_bwd(const void* dx, const int64_t* targets, const int64_t*
                           int64_t audio_vocab, int32_t dim, csm_stream_t stream);
 
 /* ---- torchtune RMSNorm (call sites model.py:13-25 norm_eps; restated in oracle/torchtune_shim.py)
- * y = bf16(x * rsqrt(mean(x^2)+eps)) * scale ; rstd[rows] fp32 is saved for backward. */
+ * y = bf16(x * rsqrt(mean(x^2)+eps)) * scale ; rstd[rows] fp32 is saved for backward.
+ * x_dtype: CSM_DT_BF16, or CSM_DT_F32 when x is the fp32 residual stream (then y = bf16(x * rstd * scale): torchtune's
+ * `.type_as(x)` does not round an fp32 x).  y, dy, dres and dx are bf16 in both cases. */
 int csm_rmsnorm_fwd(const void* x, const void* scale, void* y, float* rstd, int64_t rows, int32_t dim,
-                    float eps, csm_stream_t stream);
+                    float eps, int32_t x_dtype, csm_stream_t stream);
 /* dx = dres + d(rmsnorm)/dx (dres nullable); dscale_f32[dim] += sum_rows dy*xhat (nullable; fp32 atomics). */
 int csm_rmsnorm_bwd(const void* dy, const void* x, const void* scale, const float* rstd, const void* dres,
-                    void* dx, float* dscale_f32, int64_t rows, int32_t dim, csm_stream_t stream);
+                    void* dx, float* dscale_f32, int64_t rows, int32_t dim, int32_t x_dtype, csm_stream_t stream);
 
 /* ---- torchtune Llama3ScaledRoPE, interleaved pairs, fp32 math (restated in oracle/torchtune_shim.py)
  * in place on x[rows, heads, head_dim] with row stride ldx; position = row % seq_len;

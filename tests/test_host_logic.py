@@ -25,7 +25,7 @@ def test_library_exports_every_header_symbol():
     for s in syms:
         assert hasattr(lib, s), f"{s} declared in include/csm_b200.h but not exported"
     assert set(_lib.SIGNATURES) == set(syms), set(_lib.SIGNATURES) ^ set(syms)
-    assert lib.csm_abi_version() == 1
+    assert lib.csm_abi_version() == 2
     assert isinstance(lib.csm_last_error(), bytes)
     # sizing helpers are pure host functions
     assert lib.csm_attn_bwd_workspace_bytes(2, 64, 4, 1, 64) >= 2 * 4 * 64 * 4

@@ -30,7 +30,7 @@ def ops(cuda):
 def test_library_loads_and_device_supported(cuda):
     from csm import _lib
     lib = _lib.load()
-    assert lib.csm_abi_version() == 1
+    assert lib.csm_abi_version() == 2
     assert lib.csm_device_supported() == 1
 
 
@@ -501,3 +501,59 @@ def test_linear_ce_grouped_heads_at_decoder_dimensions(ops, cuda, Ns):
     assert cos(dw, w32.grad) > 0.999 and rel_err(dw, w32.grad) < 2e-2
     assert float(dy[3, 5].abs().max()) == 0.0                                      # the ignored (row, head) pair
     assert float(dy[:, 0].abs().max()) == 0.0                                      # position 0 feeds no head
+
+
+@pytest.mark.parametrize("rows,D", [(64, 32), (777, 2048), (300, 1024), (100, 256)])
+def test_rmsnorm_on_the_fp32_residual_stream(ops, cuda, rows, D):
+    """x fp32 (the residual stream between layers): y = bf16(x * rstd * scale), one rounding; backward reads the
+    fp32 x and keeps the bf16 gradient stream."""
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(rows, D, generator=g).to(cuda)
+    scale = (1 + 0.1 * torch.randn(D, generator=g)).to(BF).to(cuda)
+    dy = torch.randn(rows, D, generator=g).to(BF).to(cuda)
+    dres = torch.randn(rows, D, generator=g).to(BF).to(cuda)
+    y, rstd = ops.rmsnorm(x, scale, 1e-5)
+    assert y.dtype == BF
+    x32 = x.clone().requires_grad_(True)
+    s32 = scale.float().requires_grad_(True)
+    ref = x32 * torch.rsqrt(x32.pow(2).mean(-1, keepdim=True) + 1e-5) * s32
+    assert torch.equal(y, ref.to(BF)) or rel_err(y, ref) < 3e-3
+    assert torch.allclose(rstd, torch.rsqrt(x.pow(2).mean(-1) + 1e-5), rtol=1e-5)
+    ref.backward(dy.float())
+    ds = torch.zeros(D, dtype=torch.float32, device=cuda)
+    dx = ops.rmsnorm_bwd(dy, x, scale, rstd, dres, ds)
+    assert dx.dtype == BF
+    assert cos(dx, x32.grad + dres.float()) > 0.9999
+    assert cos(ds, s32.grad) > 0.9999
+
+
+@pytest.mark.parametrize("backend", [1, 2])
+@pytest.mark.parametrize("M,N,K", [(512, 384, 256), (300, 2048, 512), (4096, 2048, 2048)])
+def test_gemm_fp32_output_with_bf16_or_fp32_residual(ops, cuda, backend, M, N, K):
+    """The o-proj / down-proj form of the fp32 residual stream: out fp32 = x W^T (+ LoRA tail) + residual, with the
+    residual in bf16 (layer 0: the embedding sum) or fp32 (every later layer); single-CTA and CTA-pair tilings, ragged M."""
+    g = torch.Generator().manual_seed(M + N)
+    r = 16
+    x = (torch.randn(M, K, generator=g) * 0.5).to(BF).to(cuda)
+    w = (torch.randn(N, K, generator=g) * 0.05).to(BF).to(cuda)
+    t = (torch.randn(M, r, generator=g) * 0.5).to(BF).to(cuda)
+    lb = (torch.randn(N, r, generator=g) * 0.05).to(BF).to(cuda)
+    res32 = torch.randn(M, N, generator=g).to(cuda) * 3.0
+    base = x.float() @ w.float().t()
+    for res in (res32, res32.to(BF)):
+        out = ops.gemm(x, w, residual=res, out_dtype=torch.float32, backend=backend)
+        assert out.dtype == torch.float32
+        ref = base + res.float()
+        assert float((out - ref).abs().max()) <= 1e-3 * float(ref.abs().max())       # fp32: no bf16 rounding of the sum
+        out2 = ops.gemm(x, w, residual=res, a2=t, b2=lb, out_dtype=torch.float32, backend=backend)
+        ref2 = ref + t.float() @ lb.float().t()
+        assert float((out2 - ref2).abs().max()) <= 1e-3 * float(ref2.abs().max())
+    for mode in ((0, 1) if backend == 2 and M >= 256 else ()):
+        ops.set_gemm_cta_pair_mode(mode)
+        try:
+            out = ops.gemm(x, w, residual=res32, out_dtype=torch.float32, backend=backend)
+        finally:
+            ops.set_gemm_cta_pair_mode(-1)
+        assert float((out - (base + res32)).abs().max()) <= 1e-3 * float((base + res32).abs().max())
+    with pytest.raises(RuntimeError):
+        ops.gemm(x, w, residual=res32, backend=backend)                               # fp32 residual needs fp32 out
