@@ -57,6 +57,8 @@ class GradSynchronizer:
             self.params = [p for p in self.params if p is not sparse_rows]
         self.text_capacity_seq = 2048        # frames per sample the text-row exchange is sized for (max_seq_len)
         self.text_capacity_frames = None     # fixed by the first exchange
+        self.trace = None                    # a list while bench.py times the exchange: ("bucket", i, bytes, e0, e1) /
+        #                                      ("finish", e0, e1) CUDA-event records of one step
         self.accumulating = False            # True on all but the last micro-batch of an accumulation window
         self._hooks = []
         if not self.bucketed:
@@ -113,7 +115,16 @@ class GradSynchronizer:
         if self._stream is not None:
             self._stream.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(self._stream):
-                self._works.append(dist.all_reduce(buf, op=op, group=self.group, async_op=True))
+                if self.trace is not None:
+                    # timed form: the side stream itself waits for the collective, so two events on it bracket the
+                    # all-reduce (plus its queueing behind earlier buckets)
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record()
+                    dist.all_reduce(buf, op=op, group=self.group)
+                    e1.record()
+                    self.trace.append(("bucket", bi, buf.numel() * buf.element_size(), e0, e1))
+                else:
+                    self._works.append(dist.all_reduce(buf, op=op, group=self.group, async_op=True))
         else:
             self._works.append(dist.all_reduce(buf, op=op, group=self.group, async_op=True))
 
@@ -205,6 +216,20 @@ class GradSynchronizer:
     # ------------------------------------------------------------------ both modes
     def finish(self) -> None:
         """Call after backward, before clipping / optimizer.step()."""
+        if self.trace is not None and (self.world > 1 or self.bucketed):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            tr, self.trace = self.trace, None          # (the nested call below must not re-enter this branch)
+            try:
+                self._finish()
+            finally:
+                self.trace = tr
+            e1.record()
+            self.trace.append(("finish", e0, e1))
+            return
+        self._finish()
+
+    def _finish(self) -> None:
         if self.world == 1 and not self.bucketed:
             return
         if not self.bucketed:
