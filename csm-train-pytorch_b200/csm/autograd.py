@@ -102,13 +102,18 @@ class LinearFn(Function):
 class _Lin:
     """A (possibly LoRA-adapted) bias-free projection inside the stack: y = x W^T + t B^T, t = s * x A^T."""
 
-    __slots__ = ("w", "A", "B", "s", "iw", "iA", "iB")
+    __slots__ = ("w", "A", "B", "s", "iw", "iA", "iB", "rank", "K", "rows")
 
-    def __init__(self, mod, index_of):
+    def __init__(self, mod, index_of, adapter_rows=None):
         self.w = mod.weight
         self.A = getattr(mod, "lora_A", None)
         self.B = getattr(mod, "lora_B", None)
         self.s = float(getattr(mod, "lora_scaling", 1.0))
+        self.rank = int(getattr(mod, "lora_r", 0))
+        self.K = int(getattr(mod, "lora_adapters", 1))
+        self.rows = adapter_rows if self.K > 1 else None     # int32 [N]: adapter of every row (multi-adapter batching)
+        if self.A is not None and self.K > 1 and adapter_rows is None:
+            raise RuntimeError("this model holds several LoRA adapters per projection: pass speaker_ids")
         self.iw = index_of[id(self.w)]
         self.iA = index_of[id(self.A)] if self.A is not None else -1
         self.iB = index_of[id(self.B)] if self.B is not None else -1
@@ -116,7 +121,9 @@ class _Lin:
     def fwd(self, x, residual=None, out_dtype=BF16):
         if self.A is None:
             return ops.gemm(x, self.w, residual=residual, out_dtype=out_dtype), None
-        t = ops.gemm(x, self.A, alpha=self.s)                      # [N, r]
+        t = ops.gemm(x, self.A, alpha=self.s)                      # [N, K*r]
+        if self.rows is not None:
+            ops.lora_mask_rows_(t, self.rows, self.rank, self.K)
         return ops.gemm(x, self.w, residual=residual, a2=t, b2=self.B, out_dtype=out_dtype), t
 
     def bwd(self, dy, x, t, grads, need, dx_out=None, accumulate=False, swiglu_gu=None):
@@ -129,7 +136,9 @@ class _Lin:
             if swiglu_gu is not None:
                 return ops.gemm_swiglu_bwd(dy, self.w, swiglu_gu)
             return ops.gemm(dy, self.w, trans_b=True, out=dx_out, accumulate=accumulate)
-        dts = ops.gemm(dy, self.B, trans_b=True, alpha=self.s)     # s * dy B  [N, r]
+        dts = ops.gemm(dy, self.B, trans_b=True, alpha=self.s)     # s * dy B  [N, K*r]
+        if self.rows is not None:
+            ops.lora_mask_rows_(dts, self.rows, self.rank, self.K)
         if need[self.iB]:
             _acc(grads, self.iB, ops.gemm(dy, t, trans_a=True, trans_b=True))      # dy^T t   [out, r]
         if need[self.iA]:
@@ -176,8 +185,9 @@ class _Group:
     LoRA adapters on any member ride in the same GEMM through the extra K block: t = x [A_0; A_1; ..]^T and a
     block-diagonal [(s_0 B_0) 0; 0 (s_1 B_1)] tail operand."""
 
-    def __init__(self, mods, index_of, cache):
+    def __init__(self, mods, index_of, cache, adapter_rows=None):
         self.mods = mods
+        self.rows = None
         self.W = _packed_weight(mods, cache)
         self.iw = [index_of[id(m.weight)] for m in mods]
         self.offs, o = [], 0
@@ -189,8 +199,16 @@ class _Group:
         self.A_cat = self.B_bd = None
         if self.lora:
             R = sum(m.lora_A.shape[0] for _, m in self.lora)
-            if R > 64:
-                raise RuntimeError("fused LoRA group: total rank must be <= 64")
+            if R > 256:
+                raise RuntimeError("fused LoRA group: total rank (projections x adapters x r) must be <= 256")
+            Ks = {int(getattr(m, "lora_adapters", 1)) for _, m in self.lora}
+            rs = {int(m.lora_r) for _, m in self.lora}
+            if max(Ks) > 1:
+                if len(Ks) != 1 or len(rs) != 1:
+                    raise RuntimeError("multi-adapter LoRA: every projection of a fused group needs the same r and count")
+                if adapter_rows is None:
+                    raise RuntimeError("this model holds several LoRA adapters per projection: pass speaker_ids")
+                self.rows, self.rank, self.K = adapter_rows, rs.pop(), Ks.pop()
             # the common scaling alpha/r rides on the skinny GEMMs' alpha (t = s x A^T, dts = s dy B): the block-diagonal
             # tail operand then holds the raw B factors and no per-step scaling kernels are needed
             scal = {float(m.lora_scaling) for _, m in self.lora}
@@ -212,7 +230,10 @@ class _Group:
                 ro += r
 
     def _t(self, x):
-        return ops.gemm(x, self.A_cat, alpha=self.s if self.s is not None else 1.0)             # [N, R]
+        t = ops.gemm(x, self.A_cat, alpha=self.s if self.s is not None else 1.0)                # [N, R]
+        if self.rows is not None:
+            ops.lora_mask_rows_(t, self.rows, self.rank, self.K)
+        return t
 
     def fwd(self, x, rope=None):
         """rope = (cache, seq_len, rope_cols, head_dim): rotate the leading columns in the GEMM's store epilogue."""
@@ -243,6 +264,8 @@ class _Group:
         #   dB = dy^T t,   dts = s dy B,   dA = dts^T x,   dx = dy W + dts A
         s = self.s if self.s is not None else 1.0
         dts = ops.gemm(dy, self.B_bd, trans_b=True, alpha=s)           # [N, R]
+        if self.rows is not None:
+            ops.lora_mask_rows_(dts, self.rows, self.rank, self.K)
         if any(need[iB] for *_, iB in self.slots):
             dB = ops.gemm(dy, t, trans_a=True, trans_b=True)          # dy^T t       [n_out, R]
         if any(need[iA] for *_, iA, _ in self.slots):
@@ -270,14 +293,17 @@ class StackFn(Function):
         cache = stack.rope_cache(x.device)
         index_of = {id(p): i for i, p in enumerate(params)}
         nq, nkv = H * hd, KV * hd
+        rows = getattr(stack, "_adapter_rows", None)              # multi-adapter LoRA: int32 [N] adapter of each row
+        if rows is not None and rows.numel() != N:
+            raise RuntimeError(f"adapter row ids: expected {N} entries, got {rows.numel()}")
         cur = x.reshape(N, D).contiguous()
         res_dtype = torch.float32 if FP32_RESIDUAL else BF16       # dtype of h / out (cur is bf16 for layer 0 only)
         saved = []
         for layer in stack.layers:
             a = layer.attn
-            gqkv = _Group([a.q_proj, a.k_proj, a.v_proj], index_of, stack._packed)
-            g13 = _Group([layer.mlp.w1, layer.mlp.w3], index_of, stack._packed)
-            lo, l2 = _Lin(a.output_proj, index_of), _Lin(layer.mlp.w2, index_of)
+            gqkv = _Group([a.q_proj, a.k_proj, a.v_proj], index_of, stack._packed, rows)
+            g13 = _Group([layer.mlp.w1, layer.mlp.w3], index_of, stack._packed, rows)
+            lo, l2 = _Lin(a.output_proj, index_of, rows), _Lin(layer.mlp.w2, index_of, rows)
             I = layer.mlp.w1.weight.shape[0]
             xn, rstd1 = ops.rmsnorm(cur, layer.sa_norm.scale, eps)
             qkv, tqkv = gqkv.fwd(xn, rope=(cache, S, nq + nkv, hd))   # q and k heads rotated in the store epilogue

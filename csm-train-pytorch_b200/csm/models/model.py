@@ -102,13 +102,18 @@ class TransformerDecoder(nn.Module):
     def reset_caches(self):
         pass
 
-    def run(self, x: torch.Tensor) -> torch.Tensor:
-        """bf16 [B,S,D] -> bf16 [B,S,D] (layers + final norm) through the CUDA kernels."""
+    def run(self, x: torch.Tensor, adapter_rows: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """bf16 [B,S,D] -> bf16 [B,S,D] (layers + final norm) through the CUDA kernels.  ``adapter_rows`` int32 [B*S]:
+        which LoRA adapter each row uses (multi-adapter batching; csm/models/lora.py)."""
         if not x.is_cuda:
             raise RuntimeError("csm_b200: the transformer runs on CUDA only (no CPU fallback)")
         if x.dtype != BF16:
             raise RuntimeError(f"csm_b200: bf16 activations expected, got {x.dtype}; call model.to(torch.bfloat16)")
-        return StackFn.apply(x, self, *list(self.parameters()))
+        self._adapter_rows = adapter_rows
+        try:
+            return StackFn.apply(x, self, *list(self.parameters()))
+        finally:
+            self._adapter_rows = None
 
     def forward(self, h: torch.Tensor, *, input_pos: Optional[torch.Tensor] = None,
                 mask: Optional[torch.Tensor] = None) -> torch.Tensor:
@@ -272,7 +277,7 @@ class Model(nn.Module):
                 target_audio_tokens: Optional[torch.Tensor] = None, *, frame_idx: Optional[torch.Tensor] = None,
                 decoder_frame_fraction: float = 1.0 / 16, semantic_weight: float = 100.0,
                 acoustic_weight: float = 1.0, target_lengths: Optional[torch.Tensor] = None,
-                mask_padded_targets: bool = False):
+                mask_padded_targets: bool = False, speaker_ids: Optional[torch.Tensor] = None):
         """tokens int64 [B,S,33], tokens_mask bool [B,S,33], target_audio_tokens int64 [B,T,32].
 
         Returns (loss, {"semantic_loss", "acoustic_loss", "per_codebook_loss": fp32[32]}); with
@@ -281,6 +286,9 @@ class Model(nn.Module):
         ``target_lengths`` int64 [B] (true target frames per sample before collate's zero padding): restricts the
         decoder frame selection to real target frames, and with ``mask_padded_targets`` also drops the padded rows from
         the semantic term (the reference averages over them, utils.py:101-105: the default keeps that).
+        ``speaker_ids`` int [B] (multi-adapter LoRA models only): sample b runs through adapter speaker_ids[b] of every
+        adapted projection (index into the adapters, not the user's speaker number); a stack whose adapters are shared
+        (one adapter) ignores it.
         """
         if not tokens.is_cuda:
             raise RuntimeError("csm_b200: Model.forward needs CUDA tensors (no CPU fallback)")
@@ -289,7 +297,14 @@ class Model(nn.Module):
         B, S, W = tokens.shape
         C, V = self.args.audio_num_codebooks, self.args.audio_vocab_size
         h0 = self.embed(tokens, tokens_mask)
-        hb = self.backbone.run(h0)                               # [B,S,D] bf16 (final norm applied)
+        rows_b = rows_d = None
+        if speaker_ids is not None:
+            sid = speaker_ids.to(device=tokens.device, dtype=torch.int32)
+            if getattr(self.backbone, "lora_adapters", 1) > 1:
+                rows_b = sid.repeat_interleave(S).contiguous()
+        elif max(getattr(self.backbone, "lora_adapters", 1), getattr(self.decoder, "lora_adapters", 1)) > 1:
+            raise RuntimeError("this model holds several LoRA adapters per projection: pass speaker_ids [B]")
+        hb = self.backbone.run(h0, rows_b)                       # [B,S,D] bf16 (final norm applied)
         if target_audio_tokens is None:
             return hb
         T = target_audio_tokens.shape[1]
@@ -313,7 +328,9 @@ class Model(nn.Module):
             Ns = frame_idx.shape[0]
             x = DecoderInputFn.apply(hb, self.audio_embeddings.weight, target_audio_tokens, frame_idx, C, V)
             xp = LinearFn.apply(x.view(Ns * C, -1), self.projection.weight)
-            y = self.decoder.run(xp.view(Ns, C, -1))
+            if speaker_ids is not None and getattr(self.decoder, "lora_adapters", 1) > 1:
+                rows_d = sid[frame_idx[:, 0]].repeat_interleave(C).contiguous()
+            y = self.decoder.run(xp.view(Ns, C, -1), rows_d)
             codes = target_audio_tokens[frame_idx[:, 0], frame_idx[:, 1]].contiguous()      # [Ns, C] int64 gather
             ac, rows = GroupedLinearCEFn.apply(y, self.audio_head, self._audio_head_t(), codes)
             per_cb_ac = rows.mean(dim=1)

@@ -459,6 +459,17 @@ def linear_ce_bwd(h, w, targets, lse, grad_scale: float, *, dh: torch.Tensor, gr
     return dh, dw
 
 
+# ----------------------------------------------------------------------------- multi-adapter LoRA
+def lora_mask_rows_(t, adapter_ids, rank: int, adapters: int):
+    """In place: row i of t [rows, cols] keeps only the `rank`-column blocks of adapter adapter_ids[i] (int32)."""
+    _chk_cuda(t, adapter_ids)
+    assert t.dim() == 2 and t.stride(1) == 1 and adapter_ids.dtype == torch.int32 and adapter_ids.numel() == t.shape[0]
+    lib = _lib.load()
+    _lib.check(lib.csm_lora_mask_rows(_p(t), t.stride(0), t.shape[0], t.shape[1], _p(adapter_ids), rank, adapters,
+                                      _st()), "lora_mask_rows")
+    return t
+
+
 # ----------------------------------------------------------------------------- helpers
 def f32_to_bf16_(src_f32, dst_bf16, scale: float = 1.0, accumulate: bool = False):
     _chk_cuda(src_f32, dst_bf16)

@@ -210,7 +210,7 @@ static bool swiglu_args_ok(const void* a, const void* b, const void* c, const vo
                            int64_t ldb2) {
   if (!aligned16(a) || !aligned16(b) || !aligned16(c) || !aligned16(d)) return false;
   if ((l0 | l1 | l2 | l3) & 7) return false;
-  if (a2 && (!b2 || !aligned16(a2) || !aligned16(b2) || K2 < 1 || K2 > 64 || (lda2 & 7) || (ldb2 & 7))) return false;
+  if (a2 && (!b2 || !aligned16(a2) || !aligned16(b2) || K2 < 1 || K2 > 256 || (lda2 & 7) || (ldb2 & 7))) return false;
   return true;
 }
 

@@ -38,7 +38,7 @@ struct GemmTcParams {
   int groups;
   int num_m, num_n;         // tile grid per group
   int k_blocks;             // ceil(K / 64) main blocks
-  int has_tail;             // one extra k-block from (A2, B2)
+  int has_tail;             // extra k-blocks from (A2, B2): ceil(K2 / 64), K2 <= 256 (several LoRA adapters side by side)
   // EPI_STORE
   void* C; const bf16* R;
   int64_t ldc, ldr, c_group_stride, r_group_stride;
@@ -243,7 +243,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const bool tail = kb >= p.k_blocks;
           const CUtensorMap* ma = tail ? &tmA2 : &tmA;
           const CUtensorMap* mbp = tail ? &tmB2 : &tmB;
-          const int k0 = tail ? 0 : kb * BK;
+          const int k0 = tail ? (kb - p.k_blocks) * BK : kb * BK;
           if (!kCta2) {
             mbar_expect_tx(&full[stage], Cfg::kStageBytes);
             if (!kTransA) {
@@ -886,7 +886,7 @@ int gemm_tc_run(const GemmTcOperands& o, GemmTcParams p, int epi, cudaStream_t s
     const int cap = pair_capacity();
     const int P = cap < num_sms() / 2 ? cap : num_sms() / 2;
     const int64_t T = (int64_t)((p.num_m + 1) / 2) * ((p.N + 255) / 256);
-    const int64_t kb = (p.K + BK - 1) / BK + ((o.A2 && o.K2 > 0) ? 1 : 0);
+    const int64_t kb = (p.K + BK - 1) / BK + ((o.A2 && o.K2 > 0) ? (o.K2 + BK - 1) / BK : 0);
     const int64_t waves = (T + P - 1) / P;
     if (T > P && P <= kSkMaxPairs && kb >= 8 && (double)T / (double)(waves * P) < 0.93) {
       p.streamk = 1; p.sk_ws = g_sk_ws; p.sk_flags = g_sk_flags;
@@ -897,7 +897,7 @@ int gemm_tc_run(const GemmTcOperands& o, GemmTcParams p, int epi, cudaStream_t s
   p.num_n = epi == EPI_SWIGLU_FWD ? (int)((p.N + 127) / 128) : (int)((p.N + bn - 1) / bn);
   const uint64_t b_rows = epi == EPI_SWIGLU_FWD ? 2 * (uint64_t)p.N : (uint64_t)p.N;   // packed gate|up weight
   p.k_blocks = (int)((p.K + BK - 1) / BK);
-  p.has_tail = (o.A2 && o.K2 > 0) ? 1 : 0;
+  p.has_tail = (o.A2 && o.K2 > 0) ? (int)((o.K2 + BK - 1) / BK) : 0;
   CUtensorMap ta, tb, ta2, tb2;
   int rc;
   const uint64_t G = (uint64_t)p.groups;
@@ -946,7 +946,7 @@ bool gemm_tc_supported(const void* A, const void* B, const void* C, const void* 
   // (LoRA dA / dB: [r x in] = dt^T x over thousands of rows) still belongs on the tensor cores
   if (K < 64 || (double)M * (double)N * (double)K < (double)(1 << 21)) return false;
   if (!tma_ok(A, lda) || !tma_ok(B, ldb)) return false;
-  if (A2 && (!tma_ok(A2, lda2) || !tma_ok(B2, ldb2) || K2 < 1 || K2 > 64)) return false;
+  if (A2 && (!tma_ok(A2, lda2) || !tma_ok(B2, ldb2) || K2 < 1 || K2 > 256)) return false;
   if (M >= (1ll << 31) || N >= (1ll << 31) || K >= (1ll << 31)) return false;
   return true;
 }

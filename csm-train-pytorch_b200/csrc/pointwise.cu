@@ -350,6 +350,22 @@ static inline unsigned grid_for(int64_t work_items, int threads, int max_waves =
 
 using namespace csm;
 
+// Multi-adapter LoRA (several speakers' adapters side by side in one low-rank tail): t [rows, cols]
+// holds, per adapted projection, `adapters` blocks of `rank` columns; a row keeps only the block of ITS adapter
+// (ids[row]; a negative id keeps nothing: base model only).  Applied to t = s x A^T after the skinny GEMM and to
+// dts = s dy B before the dA / dx GEMMs, so one base GEMM serves every speaker in the batch.
+__global__ void __launch_bounds__(256)
+lora_mask_rows_kernel(bf16* __restrict__ t, int64_t ldt, int64_t rows, int cols, const int32_t* __restrict__ ids,
+                      int rank, int adapters) {
+  const int64_t total = rows * cols;
+  const int span = rank * adapters;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / cols;
+    const int c = (int)(i - r * cols);
+    if ((c % span) / rank != ids[r]) t[r * ldt + c] = __float2bfloat16_rn(0.f);
+  }
+}
+
 extern "C" int csm_rmsnorm_fwd(const void* x, const void* scale, void* y, float* rstd, int64_t rows,
                                int32_t dim, float eps, int32_t x_dtype, csm_stream_t stream) {
   CSM_REQUIRE(rows >= 0 && dim > 0 && dim % 8 == 0 && dim <= kNormThreads * 8 * kNormMaxChunks, CSM_ERR_SHAPE,
@@ -462,5 +478,20 @@ extern "C" int csm_add_bf16(const void* a, const void* b, void* out, int64_t n, 
   add_bf16_kernel<<<grid_for(n / 8 + 1, 256), 256, 0, as_stream(stream)>>>((const bf16*)a, (const bf16*)b,
                                                                            (bf16*)out, n);
   CSM_CHECK_LAUNCH("add_bf16");
+  return CSM_OK;
+}
+
+
+extern "C" int csm_lora_mask_rows(void* t, int64_t ldt, int64_t rows, int32_t cols, const int32_t* adapter_ids,
+                                  int32_t rank, int32_t adapters, csm_stream_t stream) {
+  CSM_REQUIRE(rows >= 0 && cols > 0 && rank > 0 && adapters > 0 && cols % (rank * adapters) == 0 && ldt >= cols,
+              CSM_ERR_SHAPE, "lora_mask_rows: cols=%d must be a whole number of %d x %d adapter blocks", cols, adapters,
+              rank);
+  CSM_REQUIRE(t && adapter_ids, CSM_ERR_SHAPE, "lora_mask_rows: null pointer");
+  if (rows == 0) return CSM_OK;
+  const int64_t total = rows * cols;
+  const unsigned grid = (unsigned)((total + 255) / 256 < (int64_t)num_sms() * 8 ? (total + 255) / 256 : (int64_t)num_sms() * 8);
+  lora_mask_rows_kernel<<<grid, 256, 0, as_stream(stream)>>>((bf16*)t, ldt, rows, cols, adapter_ids, rank, adapters);
+  CSM_CHECK_LAUNCH("lora_mask_rows");
   return CSM_OK;
 }

@@ -98,9 +98,9 @@ int csm_rope(void* x, const float* cache, int64_t rows, int32_t seq_len, int32_t
  * C[M,N] (=|+=) alpha * op(A)[M,K] * op(B)[K,N] (+ A2[M,K2] * B2[N,K2]^T) (+ R[M,N])
  *   transA == 0: A stored [M,K] row-major (lda);  transA != 0: stored [K,M] row-major.
  *   transB == 0: B stored [N,K] row-major (nn.Linear weight layout); transB != 0: stored [K,N] row-major.
- *   A2/B2 (nullable): LoRA low-rank tail (K2 <= 64), stored with the SAME orientation as A/B (A2 is [M,K2] or,
+ *   A2/B2 (nullable): LoRA low-rank tail (K2 <= 256: up to four extra K blocks), stored with the SAME orientation as A/B (A2 is [M,K2] or,
  *   when transA, [K2,M]; B2 is [N,K2] or, when transB, [K2,N]); fused into the main loop as one more K block
- *   (lora.py:82-105: y = x W0^T + (alpha/r)(x A^T) B^T).
+ *   (lora.py:82-105: y = x W0^T + (alpha/r)(x A^T) B^T; several adapters side by side: csm_lora_mask_rows).
  *   R (nullable, bf16, ldr): residual added in the epilogue.  c_dtype: CSM_DT_BF16 | CSM_DT_F32.
  *   accumulate != 0: C += result (read-modify-write in c_dtype). */
 int csm_gemm_bf16(const void* A, const void* B, void* C, const void* R, int64_t M, int64_t N, int64_t K,
@@ -235,6 +235,13 @@ int csm_linear_ce_bwd(const void* H, const void* W, const int64_t* targets, cons
                       int32_t transW, int64_t tgt_row_stride, int64_t tgt_group_stride, int64_t lddh,
                       int64_t dh_group_stride, void* workspace, size_t workspace_bytes, int32_t backend,
                       csm_stream_t stream);
+
+/* ---- multi-adapter LoRA batching (GPU-native form of MultiSpeakerLoRATrainer, multi_speaker_lora.py:276-300,378-438):
+ * the adapters of `adapters` speakers sit side by side in one low-rank tail (per adapted projection: `adapters` blocks of
+ * `rank` columns).  Zeroes, in place, every column block of row i of t[rows, cols] (bf16, row stride ldt) that does not
+ * belong to adapter_ids[i] (int32; negative: no adapter).  Applied to t = s x A^T and to dts = s dy B. */
+int csm_lora_mask_rows(void* t, int64_t ldt, int64_t rows, int32_t cols, const int32_t* adapter_ids, int32_t rank,
+                       int32_t adapters, csm_stream_t stream);
 
 /* ---- small helpers used by the training step */
 /* dst_bf16[i] (=|+=) src_f32[i] * scale */
