@@ -44,6 +44,11 @@ def set_gemm_cta_pair_mode(m: int) -> None:
     _lib.load().csm_set_gemm_cta_pair_mode(m)
 
 
+def set_gemm_dynamic_tiles(m: int) -> None:
+    """A/B hook: 1 (default) tiles drawn from a global counter, 0 static round-robin assignment."""
+    _lib.load().csm_set_gemm_dynamic_tiles(m)
+
+
 _attn_backend = 0
 
 

@@ -55,6 +55,13 @@ struct GemmTcParams {
   int streamk;
   // off by default (no gain measured): issue the MMAs of a ragged last column tile with N rounded up to 16 instead of BN
   int narrow_tail;
+  // dynamic tile scheduler (whole-tile schedules): tile_ctr[0] = next tile index (atomicAdd), tile_ctr[1] = CTAs that
+  // have finished; the last CTA re-zeroes both.  nullptr: static round-robin assignment (tile = unit + i * units).
+  // A persistent grid with a static assignment assumes every CTA is co-resident from the start; when another kernel
+  // holds SMs (NCCL's all-reduce CTAs overlapping the backward under data parallelism) the CTAs that start late still
+  // own a full share of tiles and the GEMM takes up to twice as long.  With the counter a late CTA simply finds less
+  // (or no) work left.
+  int* tile_ctr;
   float* sk_ws;             // [pairs][2 CTAs][BN cols][128 rows] fp32
   int* sk_flags;            // [pairs][2 CTAs][2]: partial-ready count, readers-done count (self-resetting)
   // CE epilogues
@@ -191,6 +198,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t* tfull = bars + 2 * kStages;
   uint64_t* tempty = bars + 2 * kStages + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+  uint64_t* tq_full = bars + 2 * kStages + 5;       // [4] tile-queue slot published (leader's producer -> everyone)
+  uint64_t* tq_empty = tq_full + 4;                 // [4] ... read by every consumer warp (of both CTAs of a pair)
+  volatile int* tq = reinterpret_cast<volatile int*>(tq_empty + 4);   // [4] tile index, -1 = no more work
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // CTA-pair mode: the scheduling unit is the pair; it walks (m-block pair, n-block) super-tiles in lockstep
@@ -201,6 +211,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int tile_step = kCta2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   const int kb_total = p.k_blocks + p.has_tail;
   const int sk = (kCta2 && kEpi == EPI_STORE) ? p.streamk : 0;
+  const bool dyn = p.tile_ctr != nullptr && !sk;
+  // consumers of a tile-queue slot: producer warp + epilogue warps of every CTA, MMA warp of the leader
+  constexpr uint32_t kTqConsumers = kCta2 ? 3 + 2 * epi_warps(kEpi) : 2 + epi_warps(kEpi);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -212,6 +225,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       mbar_init(&tfull[a], 1);
       mbar_init(&tempty[a], epi_warps(kEpi) * (kCta2 ? 2 : 1));
     }
+    for (int q = 0; q < 4; ++q) { mbar_init(&tq_full[q], 1); mbar_init(&tq_empty[q], kTqConsumers); }
     mbar_fence_init();
   }
   if (warp == 1) {
@@ -223,11 +237,47 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  // dynamic schedule: the it-th work item of this CTA (pair) is whatever tile index the leader's producer warp drew
+  // from the global counter and published in queue slot it % 4
+  auto take_tile = [&](int it, WorkItem& w) -> bool {
+    if (!dyn) return next_item(sk, first_tile, tile_step, num_tiles, kb_total, it, w);
+    const int slot = it & 3;
+    const uint32_t ph = (uint32_t)(it >> 2) & 1u;
+    if (kCta2 && rank != 0) mbar_wait_cluster(&tq_full[slot], ph); else mbar_wait(&tq_full[slot], ph);
+    const int t = tq[slot];
+    __syncwarp();
+    if (lane == 0) {
+      if (kCta2 && rank != 0) mbar_arrive_cluster(mapa(smem_u32(&tq_empty[slot]), 0)); else mbar_arrive(&tq_empty[slot]);
+    }
+    w.tile = t; w.kb0 = 0; w.kb1 = kb_total; w.kind = 0;
+    return t >= 0;
+  };
+
   if (warp == 0) {
     // ===================== TMA producer (warp-uniform control flow, one elected lane issues) =====================
     int stage = 0; uint32_t phase = 0;
     WorkItem w;
-    for (int it = 0; next_item(sk, first_tile, tile_step, num_tiles, kb_total, it, w); ++it) {
+    // leader only: draw the next tile index and publish it (to both CTAs of a pair); returns false after the -1
+    bool tq_open = dyn && rank == 0;
+    auto publish = [&](int it) {
+      const int slot = it & 3;
+      const uint32_t ph = (uint32_t)(it >> 2) & 1u;
+      mbar_wait(&tq_empty[slot], ph ^ 1);          // every consumer has read what the slot held four items ago
+      if (elect_one()) {
+        int t = atomicAdd(p.tile_ctr, 1);
+        if (t >= num_tiles) t = -1;
+        tq[slot] = t;
+        if (kCta2) st_shared_cluster_u32(mapa(smem_u32(const_cast<int*>(&tq[slot])), 1), (uint32_t)t);
+        mbar_arrive(&tq_full[slot]);
+        if (kCta2) mbar_arrive_cluster_release(mapa(smem_u32(&tq_full[slot]), 1));
+      }
+      __syncwarp();
+      if (tq[slot] < 0) tq_open = false;
+    };
+    if (tq_open) publish(0);
+    for (int it = 0;; ++it) {
+      if (tq_open) publish(it + 1);                // one item ahead: the atomic's latency hides behind this tile's loads
+      if (!take_tile(it, w)) break;
       int g, mb, nb;
       tile_coords(w.tile, tile_m, p.num_n, g, mb, nb);
       if (kCta2) mb = 2 * mb + (int)rank;
@@ -289,7 +339,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     int stage = 0; uint32_t phase = 0;
     int acc = 0; uint32_t acc_phase = 0;
     WorkItem w;
-    for (int it = 0; rank == 0 && next_item(sk, first_tile, tile_step, num_tiles, kb_total, it, w); ++it) {
+    for (int it = 0; rank == 0 && take_tile(it, w); ++it) {
       // (pair mode: the leader issues for both CTAs)
       mbar_wait(&tempty[acc], acc_phase ^ 1);
       tc_fence_after();
@@ -342,8 +392,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int c_lo = ehalf * kColsPerWarp, c_hi = c_lo + kColsPerWarp;
     int acc = 0; uint32_t acc_phase = 0;
     WorkItem w;
-    for (int it = 0; ehalf < epi_warps(kEpi) / 4 && next_item(sk, first_tile, tile_step, num_tiles, kb_total, it, w);
-         ++it) {
+    for (int it = 0; ehalf < epi_warps(kEpi) / 4 && take_tile(it, w); ++it) {
       int g, mb, nb;
       tile_coords(w.tile, tile_m, p.num_n, g, mb, nb);
       if (kCta2) mb = 2 * mb + (int)rank;
@@ -711,6 +760,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     tc_fence_after();
     if (kCta2) tmem_dealloc_2sm(tmem_base, Cfg::kTmemCols); else tmem_dealloc(tmem_base, Cfg::kTmemCols);
   }
+  if (dyn && threadIdx.x == 0) {
+    // the last CTA of the grid to get here re-arms the counters for the next launch on this slot
+    __threadfence();
+    if (atomicAdd(p.tile_ctr + 1, 1) == (int)gridDim.x - 1) {
+      p.tile_ctr[0] = 0;
+      p.tile_ctr[1] = 0;
+      __threadfence();
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------- host
@@ -766,6 +824,10 @@ static int* g_sk_flags = nullptr;
 // x16384: 176.9 vs 174.8; x3072: 60.4 vs 66.5.  The GPU is power-capped, so the pairs that sit out the last partial
 // wave are not lost throughput (the busy ones clock higher).  Correct and tested, therefore kept, but OFF by default.
 static std::atomic<int> g_sk_mode{0};    // 0 off (default), 1 cut tiles when the last wave is badly filled
+static std::atomic<int> g_dyn_mode{1};   // 1 (default) tiles are drawn from a global counter; 0 static round-robin
+constexpr int kTileCtrOffset = 512;      // ints into the flag area (the stream-K flags use the first 320)
+constexpr int kTileCtrSlots = 32;
+void gemm_tc_set_dynamic_tiles(int m) { g_dyn_mode.store(m); }
 constexpr size_t kSkFlagBytes = 4096;
 constexpr int kSkMaxPairs = 80;
 size_t gemm_tc_streamk_workspace_bytes() { return kSkFlagBytes + (size_t)kSkMaxPairs * 2 * 256 * BM * sizeof(float); }
@@ -893,6 +955,13 @@ int gemm_tc_run(const GemmTcOperands& o, GemmTcParams p, int epi, cudaStream_t s
     }
   }
   p.narrow_tail = (g_tail_mode.load() == 1 && !p.streamk) ? 1 : 0;
+  // dynamic tile scheduler: one of 32 self-resetting counter pairs in the registered scratch (launches on one stream are
+  // serialised, the rotation only separates launches that might overlap on different streams)
+  p.tile_ctr = nullptr;
+  if (g_sk_flags && !p.streamk && g_dyn_mode.load() != 0) {
+    static std::atomic<unsigned> seq{0};
+    p.tile_ctr = g_sk_flags + kTileCtrOffset + 2 * (int)(seq.fetch_add(1) % kTileCtrSlots);
+  }
   const uint32_t b_box = cta2 ? (uint32_t)bn / 2 : (uint32_t)bn;
   p.num_n = epi == EPI_SWIGLU_FWD ? (int)((p.N + 127) / 128) : (int)((p.N + bn - 1) / bn);
   const uint64_t b_rows = epi == EPI_SWIGLU_FWD ? 2 * (uint64_t)p.N : (uint64_t)p.N;   // packed gate|up weight

@@ -557,3 +557,49 @@ def test_gemm_fp32_output_with_bf16_or_fp32_residual(ops, cuda, backend, M, N, K
         assert float((out - (base + res32)).abs().max()) <= 1e-3 * float((base + res32).abs().max())
     with pytest.raises(RuntimeError):
         ops.gemm(x, w, residual=res32, backend=backend)                               # fp32 residual needs fp32 out
+
+
+@pytest.mark.timeout(300)
+def test_gemm_dynamic_tile_scheduler_is_bit_identical_to_static(ops, cuda):
+    """The persistent tcgen05 GEMM draws its tiles from a global counter by default (late CTAs find less work: data
+    parallel runs share the SMs with NCCL).  Every tile is computed the same way whoever takes it, so all outputs —
+    plain / LoRA-tail / residual / fp32 / transposed GEMMs in single-CTA and CTA-pair tilings, grouped split
+    reductions, the fused SwiGLU and fused-CE epilogues — must equal the static round-robin schedule bit for bit,
+    also over many back-to-back launches (the 32 self-resetting counter slots are reused)."""
+    g = torch.Generator().manual_seed(77)
+
+    def rnd(*shape, s=0.1):
+        return (torch.randn(*shape, generator=g) * s).to(BF).to(cuda)
+    cases = []
+    for (M, N, K, ta, tb) in [(4096, 2048, 2048, 0, 0), (4096, 2048, 1024, 0, 1), (2048, 1024, 4096, 1, 1),
+                              (300, 520, 256, 0, 0), (128, 64, 64, 0, 0), (7424, 1024, 2048, 0, 0), (16, 2048, 4096, 1, 1)]:
+        a = rnd(K, M) if ta else rnd(M, K)
+        b = rnd(K, N) if tb else rnd(N, K)
+        cases.append(lambda a=a, b=b, ta=ta, tb=tb: ops.gemm(a, b, trans_a=bool(ta), trans_b=bool(tb)))
+    x, w, t, lb = rnd(4096, 2048), rnd(2048, 2048), rnd(4096, 48), rnd(2048, 48)
+    res = torch.randn(4096, 2048, generator=g).to(cuda)
+    cases.append(lambda: ops.gemm(x, w, a2=t, b2=lb, residual=res, out_dtype=torch.float32))
+    w13 = rnd(2 * 1024, 2048)
+    cases.append(lambda: ops.gemm_swiglu_fwd(x, w13)[1])
+    y, head_t = rnd(232, 32, 1024, s=1.0), rnd(31, 2051, 1024, s=0.05)
+    codes = torch.randint(0, 2051, (232, 32), generator=g).to(cuda)
+    cases.append(lambda: ops.linear_ce_fwd(y[:, 1:], head_t, codes[:, 1:], groups=31, tgt_row_stride=32,
+                                           tgt_group_stride=1)[0])
+    outs = {}
+    try:
+        for mode in (0, 1):
+            ops.set_gemm_dynamic_tiles(mode)
+            outs[mode] = [[c().clone() for c in cases] for _ in range(3 if mode else 1)]
+        torch.cuda.synchronize()
+    finally:
+        ops.set_gemm_dynamic_tiles(1)
+    for rep in outs[1]:
+        for a, b in zip(outs[0][0], rep):
+            assert torch.equal(a, b)
+    # many launches in a row: every counter slot is used and re-armed several times
+    a, b = rnd(1024, 512), rnd(768, 512)
+    ref = ops.gemm(a, b).clone()
+    for _ in range(200):
+        out = ops.gemm(a, b)
+    torch.cuda.synchronize()
+    assert torch.equal(out, ref)
