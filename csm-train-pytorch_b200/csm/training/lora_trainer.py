@@ -27,7 +27,8 @@ class CSMLoRATrainer:
                  learning_rate: float = 1e-4, semantic_weight: float = 100.0, acoustic_weight: float = 1.0,
                  weight_decay: float = 0.01, lora_r: int = 8, lora_alpha: float = 16.0, lora_dropout: float = 0.0,
                  target_modules: Optional[List[str]] = None, target_layers: Optional[List[int]] = None,
-                 lora_use_bias: bool = False, *, model: Optional[Model] = None, device: str = "cuda"):
+                 lora_use_bias: bool = False, *, model: Optional[Model] = None, device: str = "cuda",
+                 num_adapters=1, target_decoder_layers: Optional[List[int]] = None):
         if lora_dropout != 0.0:
             raise NotImplementedError("lora_dropout > 0 is not implemented in the fused LoRA GEMM")
         if lora_use_bias:
@@ -43,6 +44,8 @@ class CSMLoRATrainer:
         self.lora_r, self.lora_alpha, self.lora_dropout = lora_r, lora_alpha, lora_dropout
         self.target_modules = target_modules or list(lora_mod.DEFAULT_TARGETS)
         self.target_layers, self.lora_use_bias = target_layers, lora_use_bias
+        # extensions used by MultiSpeakerLoRATrainer: several adapters per projection (one per speaker) in one model
+        self.num_adapters, self.target_decoder_layers = num_adapters, target_decoder_layers
         self.decoder_frame_fraction = 1.0 / 16
         # batches from collate_pinned carry each sample's true target length: padded all-zero target frames are then
         # left out of the semantic mean as well (the reference averages over them, utils.py:101-105; set False for that)
@@ -70,7 +73,8 @@ class CSMLoRATrainer:
             self.model.load_state_dict(state)
         self.model = self.model.to(torch.bfloat16).to(self.device)
         self.lora_names = lora_mod.apply_lora(self.model, self.lora_r, self.lora_alpha, self.target_modules,
-                                              self.target_layers)
+                                              self.target_layers, num_adapters=self.num_adapters,
+                                              target_decoder_layers=self.target_decoder_layers)
 
     def set_model(self, model: Model):
         self.model = model
@@ -120,7 +124,7 @@ class CSMLoRATrainer:
         loss, _ = compute_loss(self.model, b["input_tokens"], b["input_masks"], b["target_audio_tokens"],
                                self.semantic_weight, self.acoustic_weight, frame_idx=b["frame_idx"],
                                    target_lengths=b.get("target_lengths"),
-                                   mask_padded_targets=self.mask_padded_targets)
+                                   mask_padded_targets=self.mask_padded_targets, speaker_ids=b.get("speaker_ids"))
         loss.backward()
         self._sync.finish()
         clip_and_step(self.optimizer, list(self.get_lora_params().values()), max_grad_norm)
@@ -163,7 +167,7 @@ class CSMLoRATrainer:
                 loss, _ = compute_loss(self.model, b["input_tokens"], b["input_masks"], b["target_audio_tokens"],
                                        self.semantic_weight, self.acoustic_weight, frame_idx=b["frame_idx"],
                                    target_lengths=b.get("target_lengths"),
-                                   mask_padded_targets=self.mask_padded_targets)
+                                   mask_padded_targets=self.mask_padded_targets, speaker_ids=b.get("speaker_ids"))
                 total += float(loss)
                 n += 1
         self.model.train()
@@ -204,6 +208,15 @@ class CSMLoRATrainer:
                 merged[n] = t.cpu().contiguous()
             save_file(merged, full_path)
 
+    def _invalidate_optimizer_master(self):
+        """Parameters were overwritten outside the optimiser (a loaded adapter): drop the fp32 master copies so the
+        next step re-derives them from the new bf16 values."""
+        if self.optimizer is not None:
+            for st in self.optimizer.state.values():
+                st.pop("master", None)
+            if hasattr(self.optimizer, "_table_key"):
+                self.optimizer._table_key = None
+
     def load_lora_weights(self, lora_path: str):
         from safetensors.torch import load_file
         tensors = load_file(lora_path)
@@ -214,3 +227,4 @@ class CSMLoRATrainer:
         with torch.no_grad():
             for n, p in params.items():
                 p.copy_(tensors[n].to(p.dtype))
+        self._invalidate_optimizer_master()

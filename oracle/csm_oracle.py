@@ -199,6 +199,61 @@ def apply_lora(model: nn.Module, r: int = 8, alpha: float = 16.0,
     return names
 
 
+class MultiLoRALinear(nn.Module):
+    """K adapters side by side on one projection, each ROW of the input using its own (multi-speaker batching; the
+    reference trains one model copy per speaker instead, multi_speaker_lora.py:276-300,378-438 — same arithmetic per
+    sample):  y_n = x_n W0^T + (alpha/r) (x_n A_k^T) B_k^T  with k = adapter of row n.
+    Parameter layout == the product's: lora_A [K*r, in] (rows k*r..(k+1)*r = adapter k), lora_B [out, K*r]."""
+
+    def __init__(self, base: nn.Linear, r: int, alpha: float, K: int):
+        super().__init__()
+        self.weight = base.weight
+        self.weight.requires_grad_(False)
+        self.r, self.K, self.scaling = r, K, alpha / r
+        self.lora_A = nn.Parameter(torch.zeros(K * r, base.in_features, dtype=base.weight.dtype))
+        self.lora_B = nn.Parameter(torch.zeros(base.out_features, K * r, dtype=base.weight.dtype))
+        self.rows = None            # int tensor broadcastable to x.shape[:-1]: adapter index of every row
+
+    def forward(self, x):
+        t = F.linear(x, self.lora_A)
+        block = torch.arange(self.K * self.r, device=x.device) // self.r
+        keep = (block == self.rows.to(x.device).unsqueeze(-1)).to(t.dtype)
+        return F.linear(x, self.weight) + F.linear(t * keep, self.lora_B) * self.scaling
+
+
+def apply_multi_lora(model: nn.Module, r: int, alpha: float, num_adapters: Dict[str, int],
+                     target_modules: Optional[Sequence[str]] = None, seed: int = 1, b_std: float = 0.02) -> None:
+    """``num_adapters`` = {"backbone": Kb, "decoder": Kd}; a stack with K = 1 gets the plain LoRALinear."""
+    target_modules = list(target_modules or ["q_proj", "v_proj"])
+    for p in model.parameters():
+        p.requires_grad_(False)
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    for stack_name in ("backbone", "decoder"):
+        K = int(num_adapters.get(stack_name, 1))
+        for layer in getattr(model, stack_name).layers:
+            for t in target_modules:
+                parent_name, child = _TARGETS[t]
+                parent = getattr(layer, parent_name)
+                base = getattr(parent, child)
+                lin = MultiLoRALinear(base, r, alpha, K) if K > 1 else LoRALinear(base, r, alpha)
+                with torch.no_grad():
+                    lin.lora_A.copy_((torch.randn(lin.lora_A.shape, generator=g) /
+                                      math.sqrt(base.in_features)).to(lin.lora_A.dtype))
+                    lin.lora_B.copy_((torch.randn(lin.lora_B.shape, generator=g) * b_std).to(lin.lora_B.dtype))
+                setattr(parent, child, lin)
+
+
+def set_adapter_rows(model: nn.Module, speaker_ids: torch.Tensor, frame_idx: torch.Tensor, S: int, C: int) -> None:
+    """speaker_ids int [B] (adapter index per sample): backbone rows (b, s) and decoder rows (frame, position) get
+    the adapter of their sample."""
+    for stack_name in ("backbone", "decoder"):
+        rows = speaker_ids.view(-1, 1).expand(-1, S) if stack_name == "backbone" else \
+            speaker_ids[frame_idx[:, 0]].view(-1, 1).expand(-1, C)
+        for m in getattr(model, stack_name).modules():
+            if isinstance(m, MultiLoRALinear):
+                m.rows = rows
+
+
 # ----------------------------------------------------------------------------- inputs
 def synthetic_batch(cfg: OracleCfg, B: int, S: int, seed: int = 1234, fraction: float = 1 / 16,
                     s_text: Optional[int] = None) -> Dict[str, torch.Tensor]:

@@ -106,6 +106,37 @@ def test_api_signatures_match_reference():
     assert list(inspect.signature(load_checkpoint).parameters)[:3] == ["checkpoint_path", "model", "optimizer"]
 
 
+def test_multi_speaker_trainer_api_and_adapter_layout():
+    """MultiSpeakerLoRATrainer keeps the reference's constructor / method surface (multi_speaker_lora.py:36-60,
+    233-243, 326-437); apply_lora(num_adapters=...) lays K adapters side by side per projection."""
+    from csm.models import lora
+    from csm.models.model import Model, ModelArgs
+    from csm.training.multi_speaker_lora import MultiSpeakerLoRATrainer as T
+    p = list(inspect.signature(T.__init__).parameters)[1:19]
+    assert p == ["model_path", "output_dir", "speaker_ids", "log_file", "learning_rate", "semantic_weight",
+                 "acoustic_weight", "weight_decay", "lora_r", "lora_alpha", "lora_dropout", "share_backbone",
+                 "share_decoder", "target_modules", "target_backbone_layers", "target_decoder_layers",
+                 "lora_use_bias", "model"]
+    d = inspect.signature(T.__init__).parameters
+    assert (d["share_backbone"].default, d["share_decoder"].default, d["lora_r"].default) == (True, False, 8)
+    assert list(inspect.signature(T.train).parameters)[1:] == ["speaker_datasets", "batch_size", "epochs", "val_every",
+                                                               "save_every", "max_grad_norm", "resume_from"]
+    for name in ("initialize_trainers", "prepare_optimizers", "save_all_models", "load_speaker_model",
+                 "generate_sample", "merge_speaker_models"):
+        assert callable(getattr(T, name))
+    m = Model(ModelArgs("tiny-backbone", "tiny-decoder", 1000, 200, 32))
+    lora.apply_lora(m, r=4, num_adapters={"backbone": 1, "decoder": 3}, seed=0)
+    q = m.decoder.layers[0].attn.q_proj
+    assert q.lora_A.shape == (12, 16) and q.lora_B.shape == (16, 12) and q.lora_adapters == 3 and q.lora_r == 4
+    assert m.backbone.layers[0].attn.q_proj.lora_A.shape == (4, 32) and m.backbone.lora_adapters == 1
+    a1, b1 = lora.adapter_slices(q, 1)
+    assert a1.shape == (4, 16) and b1.shape == (16, 4) and a1.data_ptr() == q.lora_A[4:8].data_ptr()
+    with pytest.raises(RuntimeError):
+        lora.merge_lora(m)                                    # no single merged weight with several adapters
+    lora.apply_lora(m, r=4, target_layers=[0], target_decoder_layers=[])       # separate layer filters per stack
+    assert not any("decoder" in n for n, p in m.named_parameters() if p.requires_grad)
+
+
 def test_lora_names_counts_and_freezing():
     from csm.models import lora
     from csm.models.model import Model, ModelArgs

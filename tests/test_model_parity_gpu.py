@@ -199,6 +199,58 @@ def test_reference_test_shape_b2_s5_matches_oracle(cuda):
     assert float(pd2["semantic_loss"]) == float(pd["semantic_loss"]) and float(pl2) > 0
 
 
+@pytest.mark.parametrize("share_backbone", [True, False])
+def test_multi_adapter_batching_matches_per_row_adapter_oracle(cuda, share_backbone):
+    """three speakers' adapters side by side in every adapted projection, one mixed-speaker batch,
+    ONE base GEMM — against the plain-torch restatement that selects each row's adapter explicitly
+    (oracle.MultiLoRALinear): losses and every adapter gradient, including the zero gradient of a speaker that is
+    absent from the batch.  r=16 on all seven projections: the fused q|k|v tail is 3 x 3 x 16 = 144 columns wide."""
+    from csm.models import lora as plora
+    from oracle import csm_oracle as O
+    prod, cfg = _product_model("small")
+    orc = O.OracleModel(cfg)
+    O.init_weights(orc, 0)
+    orc, prod = orc.to(torch.bfloat16), prod.to(torch.bfloat16)
+    targets = ["q_proj", "k_proj", "v_proj", "o_proj", "gate_proj", "up_proj", "down_proj"]
+    adapters = {"backbone": 1 if share_backbone else 3, "decoder": 3}
+    O.apply_multi_lora(orc, 16, 16.0, adapters, target_modules=targets, seed=1)
+    plora.apply_lora(prod, r=16, alpha=16.0, target_modules=targets, seed=9, num_adapters=adapters)
+    prod.load_state_dict(orc.state_dict(), strict=True)
+    prod = prod.to(cuda)
+    B, S = 4, 128
+    batch = O.synthetic_batch(cfg, B, S, seed=31)
+    speakers = torch.tensor([2, 0, 2, 0])                                      # adapter 1 never appears
+    tok, msk, tgt, fidx = (batch[k] for k in ("input_tokens", "input_masks", "target_audio_tokens", "frame_idx"))
+    O.set_adapter_rows(orc, speakers, fidx, S, cfg.audio_num_codebooks)
+    ol, od = O.oracle_forward(orc, tok, msk, tgt, fidx)
+    ol.backward()
+    pl, pd = prod(tok.to(cuda), msk.to(cuda), tgt.to(cuda), frame_idx=fidx.to(cuda), speaker_ids=speakers.to(cuda))
+    pl.backward()
+    torch.cuda.synchronize()
+    assert abs(float(pl) - float(ol)) <= LOSS_RTOL * abs(float(ol))
+    rel = ((pd["per_codebook_loss"].cpu() - od["per_codebook_loss"]).abs() / od["per_codebook_loss"]).max().item()
+    assert rel <= LOSS_RTOL
+    named = dict(prod.named_parameters())
+    checked = 0
+    for n, q in orc.named_parameters():
+        if q.grad is None:
+            continue
+        a, b = q.grad.float(), named[n].grad.float().cpu()
+        K = adapters["backbone" if n.startswith("backbone") else "decoder"]
+        for k in range(K):
+            sa = a[k * 16:(k + 1) * 16] if n.endswith("lora_A") else a[:, k * 16:(k + 1) * 16]
+            sb = b[k * 16:(k + 1) * 16] if n.endswith("lora_A") else b[:, k * 16:(k + 1) * 16]
+            if K > 1 and k == 1:
+                assert float(sa.abs().max()) == 0.0 and float(sb.abs().max()) == 0.0, n     # absent speaker: no gradient
+                continue
+            c = float(F.cosine_similarity(sa.flatten(), sb.flatten(), dim=0))
+            assert c >= GRAD_COS, (n, k, c)
+            checked += 1
+    assert checked > 50
+    with pytest.raises(RuntimeError):
+        prod(tok.to(cuda), msk.to(cuda), tgt.to(cuda), frame_idx=fidx.to(cuda))     # several adapters: ids required
+
+
 def test_no_cpu_fallback():
     from csm.models.model import Model, ModelArgs
     m = Model(ModelArgs("tiny-backbone", "tiny-decoder", 1000, 200, 32)).to(torch.bfloat16)

@@ -603,3 +603,38 @@ def test_gemm_dynamic_tile_scheduler_is_bit_identical_to_static(ops, cuda):
         out = ops.gemm(a, b)
     torch.cuda.synchronize()
     assert torch.equal(out, ref)
+
+
+def test_lora_mask_rows_and_wide_multi_adapter_tail(ops, cuda):
+    """Multi-adapter batching: (1) csm_lora_mask_rows keeps, per row, only the rank-wide block of the row's adapter in
+    every projection's span; (2) the low-rank tail of the tcgen05 GEMM takes up to 256 columns (four extra K blocks),
+    plain and transposed, single-CTA and CTA-pair tilings."""
+    g = torch.Generator().manual_seed(21)
+    rows, r, K, proj = 300, 8, 3, 2
+    t = torch.randn(rows, proj * K * r, generator=g).to(BF).to(cuda)
+    ids = torch.randint(-1, K, (rows,), generator=g).to(torch.int32).to(cuda)
+    ref = t.clone().view(rows, proj, K, r)
+    keep = (torch.arange(K, device=cuda)[None, :] == ids[:, None]).view(rows, 1, K, 1)
+    ref = (ref * keep).view(rows, -1)
+    wide = torch.zeros(rows, proj * K * r + 16, dtype=BF, device=cuda)
+    view = wide[:, :proj * K * r]                                            # row stride > cols
+    view.copy_(t)
+    ops.lora_mask_rows_(view, ids, r, K)
+    assert torch.equal(view, ref) and float(wide[:, proj * K * r:].abs().max()) == 0.0
+    for K2 in (96, 192, 256):
+        for (M, N, Kd) in [(512, 384, 256), (4096, 2048, 1024)]:
+            x = (torch.randn(M, Kd, generator=g) * 0.5).to(BF).to(cuda)
+            w = (torch.randn(N, Kd, generator=g) * 0.1).to(BF).to(cuda)
+            t2 = (torch.randn(M, K2, generator=g) * 0.5).to(BF).to(cuda)
+            b2 = (torch.randn(N, K2, generator=g) * 0.1).to(BF).to(cuda)
+            ref = x.float() @ w.float().t() + t2.float() @ b2.float().t()
+            assert rel_err(ops.gemm(x, w, a2=t2, b2=b2, backend=2), ref) < 5e-3
+            assert rel_err(ops.gemm(x, w, a2=t2, b2=b2, backend=1), ref) < 5e-3
+            # dgrad form: dx = dy W + dts A with W [N(out), K(in)] read MN-major and A [K2, in]
+            dy = (torch.randn(M, N, generator=g) * 0.5).to(BF).to(cuda)
+            a_cat = (torch.randn(K2, Kd, generator=g) * 0.1).to(BF).to(cuda)
+            refd = dy.float() @ w.float() + t2.float() @ a_cat.float()
+            assert rel_err(ops.gemm(dy, w, trans_b=True, a2=t2, b2=a_cat, backend=2), refd) < 5e-3
+    with pytest.raises(RuntimeError):
+        ops.gemm(x, w, a2=torch.zeros(M, 264, dtype=BF, device=cuda), b2=torch.zeros(N, 264, dtype=BF, device=cuda),
+                 backend=2)                                                   # K2 > 256: not a tcgen05 shape

@@ -343,3 +343,57 @@ def test_train_loops_on_ragged_dataset(cuda, tmp_path):
     assert tl.global_step == 2
     assert os.path.exists(tmp_path / "lora" / "final_lora.safetensors") or \
         os.path.exists(tmp_path / "lora" / "final.safetensors")
+
+
+def test_multi_speaker_trainer_mixed_batches_and_per_speaker_files(cuda, tmp_path):
+    """MultiSpeakerLoRATrainer (multi_speaker_lora.py) as multi-adapter batching: shared backbone adapter, one decoder
+    adapter per speaker, mixed-speaker batches through CUDA-graph-replayed steps; a speaker without data keeps its
+    initial adapter; every per-speaker file loads into a plain single-adapter CSMLoRATrainer and reproduces that
+    speaker's loss."""
+    from safetensors.torch import load_file
+    from csm.training.lora_trainer import CSMLoRATrainer
+    from csm.training.multi_speaker_lora import MultiSpeakerLoRATrainer
+    from csm.training.utils import compute_loss
+    model, cfg = _small_model(cuda)
+    t = MultiSpeakerLoRATrainer("", str(tmp_path / "ms"), speaker_ids=[7, 11, 42], learning_rate=1e-3, lora_r=8,
+                                model=model, device=str(cuda))
+    assert set(t.trainers) == {7, 11, 42} and t.adapters == {"backbone": 1, "decoder": 3}
+    with torch.no_grad():                                     # B != 0 so that the speakers differ from the start
+        for n, p in t.engine.get_lora_params().items():
+            if n.endswith("lora_B"):
+                p.normal_(0.0, 0.02)
+    before = {sid: {n: v.clone() for n, v in t.speaker_state(sid).items()} for sid in t.speaker_ids}
+    data = {7: (_ragged_dataset(cfg, [128, 128, 128, 128]), _ragged_dataset(cfg, [128, 128])),
+            11: (_ragged_dataset(cfg, [128, 128, 128, 128]), _ragged_dataset(cfg, [128]))}      # 42: no data
+    t.engine.enable_cuda_graph(warmup=1)
+    best = t.train(data, batch_size=2, epochs=2, val_every=2, save_every=100)
+    assert set(best) == {7, 11} and t.global_step == 8 and t.engine._graphed.graph is not None
+    after = {sid: t.speaker_state(sid) for sid in t.speaker_ids}
+    dec = "decoder.layers.0.attn.q_proj.lora_B"
+    bb = "backbone.layers.0.attn.q_proj.lora_A"
+    assert not torch.equal(after[7][dec], before[7][dec]) and not torch.equal(after[11][dec], before[11][dec])
+    assert torch.equal(after[42][dec], before[42][dec])                      # never in a batch: untouched
+    assert not torch.equal(after[7][bb], before[7][bb]) and torch.equal(after[7][bb], after[42][bb])   # shared
+    for sid in (7, 11, 42):
+        assert os.path.exists(tmp_path / "ms" / f"speaker_{sid}" / f"speaker_{sid}_lora.safetensors")
+    shared = load_file(str(tmp_path / "ms" / "shared" / "shared_lora.safetensors"))
+    assert shared and all(k.startswith("backbone.") for k in shared)
+    merged = t.merge_speaker_models(shared_weight=0.5)
+    m7 = load_file(merged[7])
+    assert torch.allclose(m7["backbone.layers.0.attn.q_proj.lora_B"].to(cuda),
+                          0.5 * after[7]["backbone.layers.0.attn.q_proj.lora_B"].float(), atol=1e-3)
+    # a per-speaker file is a plain single-adapter LoRA file
+    single_model, _ = _small_model(cuda)
+    single = CSMLoRATrainer("", str(tmp_path / "single"), lora_r=8, model=single_model, device=str(cuda))
+    single.load_lora_weights(str(tmp_path / "ms" / "speaker_11" / "speaker_11_lora.safetensors"))
+    b = {k: v.to(cuda) for k, v in _batches(cfg, 1)[0].items()}
+    with torch.no_grad():
+        l_single, _ = compute_loss(single.model, b["input_tokens"], b["input_masks"], b["target_audio_tokens"],
+                                   frame_idx=b["frame_idx"])
+        l_multi, _ = compute_loss(t.engine.model, b["input_tokens"], b["input_masks"], b["target_audio_tokens"],
+                                  frame_idx=b["frame_idx"],
+                                  speaker_ids=torch.full((2,), t.index_of[11], device=cuda))
+    assert abs(float(l_single) - float(l_multi)) <= 2e-3 * abs(float(l_multi))
+    # and loads back into another speaker's slot
+    t.load_speaker_model(42, str(tmp_path / "ms" / "speaker_11" / "speaker_11_lora.safetensors"))
+    assert torch.equal(t.speaker_state(42)[dec], t.speaker_state(11)[dec])
