@@ -200,7 +200,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
   uint64_t* tq_full = bars + 2 * kStages + 5;       // [4] tile-queue slot published (leader's producer -> everyone)
   uint64_t* tq_empty = tq_full + 4;                 // [4] ... read by every consumer warp (of both CTAs of a pair)
-  volatile int* tq = reinterpret_cast<volatile int*>(tq_empty + 4);   // [4] tile index, -1 = no more work
+  volatile uint32_t* tq = reinterpret_cast<volatile uint32_t*>(tq_empty + 4);   // [4] (tag << 20) | (tile + 1)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // CTA-pair mode: the scheduling unit is the pair; it walks (m-block pair, n-block) super-tiles in lockstep
@@ -211,7 +211,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int tile_step = kCta2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   const int kb_total = p.k_blocks + p.has_tail;
   const int sk = (kCta2 && kEpi == EPI_STORE) ? p.streamk : 0;
-  const bool dyn = p.tile_ctr != nullptr && !sk;
+  const bool dyn = p.tile_ctr != nullptr && !sk && num_tiles < (1 << 20) - 1;
   // consumers of a tile-queue slot: producer warp + epilogue warps of every CTA, MMA warp of the leader
   constexpr uint32_t kTqConsumers = kCta2 ? 3 + 2 * epi_warps(kEpi) : 2 + epi_warps(kEpi);
 
@@ -225,7 +225,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       mbar_init(&tfull[a], 1);
       mbar_init(&tempty[a], epi_warps(kEpi) * (kCta2 ? 2 : 1));
     }
-    for (int q = 0; q < 4; ++q) { mbar_init(&tq_full[q], 1); mbar_init(&tq_empty[q], kTqConsumers); }
+    for (int q = 0; q < 4; ++q) { mbar_init(&tq_full[q], 1); mbar_init(&tq_empty[q], kTqConsumers); tq[q] = 0; }
     mbar_fence_init();
   }
   if (warp == 1) {
@@ -237,19 +237,25 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  // dynamic schedule: the it-th work item of this CTA (pair) is whatever tile index the leader's producer warp drew
-  // from the global counter and published in queue slot it % 4
+  // Dynamic schedule.  Item 0 of every CTA (pair) is its static tile (no start-up latency); item it >= 1 is the tile
+  // index the LEADER's producer warp drew from the global counter and wrote, tagged with `it`, into queue slot
+  // (it - 1) % 4 of its shared memory.  The word is self-validating ((tag << 20) | (tile + 1), tile + 1 == 0: no work
+  // left), so the peer CTA of a pair needs no release/acquire hand-off: its producer warp polls the leader's word through
+  // DSMEM and republishes it locally.  Consumers arrive on the LEADER's tq_empty (the peer's remotely, relaxed).
+  auto tq_tag = [](int it) -> uint32_t { return (uint32_t)((it & 0x7ff) + 1); };
   auto take_tile = [&](int it, WorkItem& w) -> bool {
     if (!dyn) return next_item(sk, first_tile, tile_step, num_tiles, kb_total, it, w);
-    const int slot = it & 3;
-    const uint32_t ph = (uint32_t)(it >> 2) & 1u;
-    if (kCta2 && rank != 0) mbar_wait_cluster(&tq_full[slot], ph); else mbar_wait(&tq_full[slot], ph);
-    const int t = tq[slot];
+    w.kb0 = 0; w.kb1 = kb_total; w.kind = 0;
+    if (it == 0) { w.tile = first_tile; return first_tile < num_tiles; }
+    const int slot = (it - 1) & 3;
+    const uint32_t ph = (uint32_t)((it - 1) >> 2) & 1u;
+    mbar_wait(&tq_full[slot], ph);
+    const int t = (int)(tq[slot] & 0xfffffu) - 1;
     __syncwarp();
     if (lane == 0) {
       if (kCta2 && rank != 0) mbar_arrive_cluster(mapa(smem_u32(&tq_empty[slot]), 0)); else mbar_arrive(&tq_empty[slot]);
     }
-    w.tile = t; w.kb0 = 0; w.kb1 = kb_total; w.kind = 0;
+    w.tile = t;
     return t >= 0;
   };
 
@@ -257,26 +263,35 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // ===================== TMA producer (warp-uniform control flow, one elected lane issues) =====================
     int stage = 0; uint32_t phase = 0;
     WorkItem w;
-    // leader only: draw the next tile index and publish it (to both CTAs of a pair); returns false after the -1
-    bool tq_open = dyn && rank == 0;
+    // publishes item `it` (>= 1) into this CTA's queue; returns through tq_open whether more work may follow.
+    // Leader: draws the tile from the counter.  Peer: relays the leader's word.
+    bool tq_open = dyn;
     auto publish = [&](int it) {
-      const int slot = it & 3;
-      const uint32_t ph = (uint32_t)(it >> 2) & 1u;
-      mbar_wait(&tq_empty[slot], ph ^ 1);          // every consumer has read what the slot held four items ago
-      if (elect_one()) {
-        int t = atomicAdd(p.tile_ctr, 1);
-        if (t >= num_tiles) t = -1;
-        tq[slot] = t;
-        if (kCta2) st_shared_cluster_u32(mapa(smem_u32(const_cast<int*>(&tq[slot])), 1), (uint32_t)t);
-        mbar_arrive(&tq_full[slot]);
-        if (kCta2) mbar_arrive_cluster_release(mapa(smem_u32(&tq_full[slot]), 1));
+      const int slot = (it - 1) & 3;
+      const uint32_t ph = (uint32_t)((it - 1) >> 2) & 1u;
+      uint32_t word = 0;
+      if (!kCta2 || rank == 0) {
+        mbar_wait(&tq_empty[slot], ph ^ 1);        // every consumer (of both CTAs) has read what the slot held before
+        if (elect_one()) {
+          const int t = tile_step + atomicAdd(p.tile_ctr, 1);
+          word = (tq_tag(it) << 20) | (uint32_t)(t < num_tiles ? t + 1 : 0);
+          tq[slot] = word;
+          mbar_arrive(&tq_full[slot]);
+        }
+      } else {
+        if (elect_one()) {
+          const uint32_t src = mapa(smem_u32(const_cast<uint32_t*>(&tq[slot])), 0);
+          do {
+            asm volatile("ld.volatile.shared::cluster.u32 %0, [%1];" : "=r"(word) : "r"(src) : "memory");
+          } while ((word >> 20) != tq_tag(it));
+          tq[slot] = word;
+          mbar_arrive(&tq_full[slot]);
+        }
       }
       __syncwarp();
-      if (tq[slot] < 0) tq_open = false;
+      if ((tq[slot] & 0xfffffu) == 0) tq_open = false;
     };
-    if (tq_open) publish(0);
     for (int it = 0;; ++it) {
-      if (tq_open) publish(it + 1);                // one item ahead: the atomic's latency hides behind this tile's loads
       if (!take_tile(it, w)) break;
       int g, mb, nb;
       tile_coords(w.tile, tile_m, p.num_n, g, mb, nb);
@@ -331,6 +346,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         __syncwarp();
         if (++stage == kStages) { stage = 0; phase ^= 1; }
+        // next item: drawn while this tile's first loads are in flight (the atomic's latency hides behind them)
+        if (kb == w.kb0 && tq_open) publish(it + 1);
       }
     }
   } else if (warp == 1) {

@@ -156,28 +156,6 @@ __device__ __forceinline__ uint32_t mapa(uint32_t local_smem_addr, uint32_t rank
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
-// Publishing a value into the peer CTA's shared memory: plain remote store, then a release.cluster arrive on the peer's
-// mbarrier; the peer waits with acquire.cluster.  (Used once per output tile by the dynamic tile scheduler; the issuing
-// lane has no global stores in flight, so the MEMBAR the release compiles to is cheap here.)
-__device__ __forceinline__ void st_shared_cluster_u32(uint32_t cluster_addr, uint32_t v) {
-  asm volatile("st.shared::cluster.u32 [%0], %1;" ::"r"(cluster_addr), "r"(v) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_cluster_release(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
-}
-__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "WAIT_LOOP_C:\n"
-      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n"
-      "@p bra DONE_C;\n"
-      "bra WAIT_LOOP_C;\n"
-      "DONE_C:\n"
-      "}\n" ::"r"(smem_u32(bar)),
-      "r"(parity)
-      : "memory");
-}
 // TMA load whose complete_tx lands on an mbarrier that may live in the peer CTA (shared::cluster address)
 __device__ __forceinline__ void tma_load_3d_2sm(void* smem_dst, const CUtensorMap* map, uint32_t bar_cluster_addr, int c0,
                                                 int c1, int c2) {
