@@ -56,6 +56,7 @@ SIGNATURES = {
                           [_i32] + [_i64] * 4 + [_ptr, _sz, _i32, _ptr]),
     "csm_adamw_clip_step": (_i32, [_ptr] * 7 + [_i32, _f32, _f32, _f32, _f32, _ptr, _ptr, _ptr]),
     "csm_adamw_clip_step_v2": (_i32, [_ptr] * 11 + [_i32, _f32, _f32, _f32, _f32, _i32, _ptr, _ptr, _ptr]),
+    "csm_attn_decode": (_i32, [_ptr] * 4 + [_i32] * 5 + [_i64] * 4 + [_f32, _ptr]),
     "csm_lora_mask_rows": (_i32, [_ptr, _i64, _i64, _i32, _ptr, _i32, _i32, _ptr]),
     "csm_f32_to_bf16": (_i32, [_ptr, _ptr, _i64, _f32, _i32, _ptr]),
     "csm_add_bf16": (_i32, [_ptr, _ptr, _ptr, _i64, _ptr]),

@@ -21,6 +21,7 @@ import torch
 import torch.nn as nn
 
 from .. import ops
+from .. import autograd as _ag
 from ..autograd import (DecoderInputFn, EmbedGatherSumFn, GroupedLinearCEFn, LinearCEFn, LinearFn, StackFn)
 from .rope import build_rope_cache
 
@@ -93,14 +94,77 @@ class TransformerDecoder(nn.Module):
         """Llama-3 scaling is position independent, so a longer context only extends the table."""
         self.max_seq_len = n
 
+    # ---- KV caches: inference only (generate_frame, model.py:140-195).  The training path (``run``) never touches
+    # them, so the reference trainer's habit of calling setup_caches before training (trainer.py:114,121) is harmless.
     def caches_are_enabled(self) -> bool:
-        return False
+        return getattr(self, "_kc", None) is not None
 
-    def setup_caches(self, *a, **k):
-        raise NotImplementedError("KV caches are an inference feature; the B200 path is the training step")
+    def setup_caches(self, max_batch_size: int, dtype=BF16, *, encoder_max_seq_len=None, decoder_max_seq_len=None):
+        """torchtune TransformerDecoder.setup_caches as model.py:134-135 calls it: per layer K / V caches
+        [max_batch, max_seq, KV*hd] (keys stored rotated; unlike torchtune 0.4.0 the KV heads are NOT expanded to the
+        query heads — the decode kernel shares them)."""
+        if dtype != BF16:
+            raise RuntimeError("csm_b200: KV caches are bf16")
+        n = decoder_max_seq_len if decoder_max_seq_len is not None else self.max_seq_len
+        dev = self.norm.scale.device
+        L, kvd = len(self.layers), self.num_kv_heads * self.head_dim
+        self._kc = torch.zeros(L, max_batch_size, n, kvd, dtype=BF16, device=dev)
+        self._vc = torch.zeros(L, max_batch_size, n, kvd, dtype=BF16, device=dev)
+        self._cache_len = 0
 
     def reset_caches(self):
-        pass
+        if self.caches_are_enabled():
+            self._cache_len = 0
+
+    @torch.no_grad()
+    def infer(self, x: torch.Tensor, pos0: int) -> torch.Tensor:
+        """Cached forward of S new positions pos0 .. pos0+S-1 (same for every sample): bf16 [B,S,D] -> bf16 [B,S,D].
+        Same kernels as training; K / V of the new positions are appended to the caches.  pos0 == 0 (prefill) runs the
+        causal attention kernels on the new block, S == 1 the decode kernel over the cache."""
+        if not self.caches_are_enabled():
+            raise RuntimeError("backbone caches are not enabled")          # model.py:164
+        B, S, D = x.shape
+        if pos0 != self._cache_len:
+            raise RuntimeError(f"KV cache holds {self._cache_len} positions, cannot continue at position {pos0}")
+        if B > self._kc.shape[1] or pos0 + S > self._kc.shape[2]:
+            raise RuntimeError(f"KV cache too small for batch {B}, positions up to {pos0 + S}")
+        if pos0 > 0 and S != 1:
+            raise NotImplementedError("cached forward: several new positions behind a non-empty cache (chunked "
+                                      "prefill) — generate_frame only prefills once and then steps by one")
+        H, KV, hd, eps = self.num_heads, self.num_kv_heads, self.head_dim, self.norm_eps
+        nq, nkv = H * hd, KV * hd
+        N = B * S
+        params = list(self.parameters())
+        index_of = {id(p): i for i, p in enumerate(params)}
+        rope = self.rope_cache(x.device)[pos0:]                              # row s of the block = position pos0 + s
+        res_dtype = torch.float32 if _ag.FP32_RESIDUAL else BF16
+        cur = x.reshape(N, D).contiguous()
+        for li, layer in enumerate(self.layers):
+            a = layer.attn
+            gqkv = _ag._Group([a.q_proj, a.k_proj, a.v_proj], index_of, self._packed)
+            g13 = _ag._Group([layer.mlp.w1, layer.mlp.w3], index_of, self._packed)
+            lo, l2 = _ag._Lin(a.output_proj, index_of), _ag._Lin(layer.mlp.w2, index_of)
+            I = layer.mlp.w1.weight.shape[0]
+            xn, _ = ops.rmsnorm(cur, layer.sa_norm.scale, eps)
+            qkv, _ = gqkv.fwd(xn, rope=(rope, S, nq + nkv, hd))
+            q, k, v = qkv[:, :nq], qkv[:, nq:nq + nkv], qkv[:, nq + nkv:]
+            self._kc[li, :B, pos0:pos0 + S].copy_(k.view(B, S, nkv))
+            self._vc[li, :B, pos0:pos0 + S].copy_(v.view(B, S, nkv))
+            if pos0 == 0:
+                o, _ = ops.attention_fwd(q, k, v, B, S, H, KV, hd)
+            else:
+                o = ops.attention_decode(q, self._kc[li], self._vc[li], B, H, KV, hd, pos0 + 1)
+            h, _ = lo.fwd(o, residual=cur, out_dtype=res_dtype)
+            hn, _ = ops.rmsnorm(h, layer.mlp_norm.scale, eps)
+            if ops.swiglu_fusable(N, I, D):
+                _, act, _ = g13.fwd_swiglu(hn)
+            else:
+                gu, _ = g13.fwd(hn)
+                act = ops.swiglu(gu[:, :I], gu[:, I:])
+            cur, _ = l2.fwd(act, residual=h, out_dtype=res_dtype)
+        y, _ = ops.rmsnorm(cur, self.norm.scale, eps)
+        self._cache_len = pos0 + S
+        return y.view(B, S, D)
 
     def run(self, x: torch.Tensor, adapter_rows: Optional[torch.Tensor] = None) -> torch.Tensor:
         """bf16 [B,S,D] -> bf16 [B,S,D] (layers + final norm) through the CUDA kernels.  ``adapter_rows`` int32 [B*S]:
@@ -175,6 +239,20 @@ def _index_causal_mask(mask: torch.Tensor, input_pos: torch.Tensor):  # model.py
     return mask[input_pos, :]
 
 
+def _multinomial_sample_one_no_sync(probs):                   # model.py:79-82
+    q = torch.empty_like(probs).exponential_(1)
+    return torch.argmax(probs / q, dim=-1, keepdim=True).to(dtype=torch.int)
+
+
+def sample_topk(logits: torch.Tensor, topk: int, temperature: float):   # model.py:85-96
+    """Top-k filter + softmax + exponential-race draw, on the device without a synchronisation (a few launches on a
+    [B, 2051] row: sampling policy, not arithmetic of the model)."""
+    logits = logits / temperature
+    indices_to_remove = logits < torch.topk(logits, topk)[0][..., -1, None]
+    scores = torch.nn.functional.log_softmax(logits.masked_fill(indices_to_remove, -float("inf")), dim=-1)
+    return _multinomial_sample_one_no_sync(torch.nn.functional.softmax(scores, dim=-1))
+
+
 @dataclass
 class ModelArgs:                                             # model.py:99-107
     backbone_flavor: str
@@ -200,16 +278,20 @@ class Model(nn.Module):
 
     # ---- reference helpers kept for API parity -------------------------------------------------
     def setup_caches(self, max_batch_size: int) -> None:
-        """model.py:128-138: the reference uses this to obtain the causal-mask buffers; KV caches themselves are
-        not part of the training path and are not allocated."""
+        """model.py:128-138: KV caches of both stacks (inference only; the training forward ignores them) and the
+        causal-mask buffers the reference's compute_loss indexes."""
         device = next(self.parameters()).device
+        if device.type == "cuda":
+            self.backbone.setup_caches(max_batch_size, BF16)
+            self.decoder.setup_caches(max_batch_size, BF16, decoder_max_seq_len=self.args.audio_num_codebooks)
         self.register_buffer("backbone_causal_mask", _create_causal_mask(self.backbone.max_seq_len, device),
                              persistent=False)
         self.register_buffer("decoder_causal_mask", _create_causal_mask(self.args.audio_num_codebooks, device),
                              persistent=False)
 
-    def reset_caches(self):
-        pass
+    def reset_caches(self):                                                          # model.py:197-200
+        self.backbone.reset_caches()
+        self.decoder.reset_caches()
 
     def _index_causal_mask(self, mask: torch.Tensor, input_pos: torch.Tensor) -> torch.Tensor:
         """Method form expected by compute_loss (utils.py:90) — a module-level function in the reference."""
@@ -227,8 +309,50 @@ class Model(nn.Module):
         audio = self.audio_embeddings(idx.view(-1)).reshape(tokens.size(0), tokens.size(1), C, -1)
         return torch.cat([audio, text], dim=-2)
 
-    def generate_frame(self, *a, **k):
-        raise NotImplementedError("inference (generate_frame, model.py:140-195) is outside the B200 training path")
+    @torch.no_grad()
+    def generate_frame(self, tokens: torch.Tensor, tokens_mask: torch.Tensor, input_pos: torch.Tensor,
+                       temperature: float, topk: int, *, return_logits: bool = False,
+                       forced_codes: Optional[torch.Tensor] = None):
+        """model.py:140-195 on the training kernels with KV caches: tokens [B,S,33], tokens_mask
+        [B,S,33], input_pos [B,S] (pos0 + arange(S), the same for every sample) -> sampled codes int32 [B,32].
+        Backbone: fused gather-sum, cached forward (prefill: causal attention kernels; later frames: the decode kernel),
+        codebook0 head GEMM; depth decoder: 31 cached steps (positions 0,1 together, then one by one) with a fresh cache
+        per frame.  Test aids: ``return_logits`` also returns the 32 logit rows, ``forced_codes`` int [B,32] replaces
+        the sampled codes that are fed back (teacher forcing), so two implementations can be compared step by step."""
+        if not tokens.is_cuda:
+            raise RuntimeError("csm_b200: generate_frame needs CUDA tensors (no CPU fallback)")
+        assert self.backbone.caches_are_enabled(), "backbone caches are not enabled"      # model.py:164
+        B, S, _ = tokens.shape
+        C, V = self.args.audio_num_codebooks, self.args.audio_vocab_size
+        pos0 = int(input_pos[0, 0])
+        if not torch.equal(input_pos, (pos0 + torch.arange(S, device=input_pos.device)).expand(B, S)):
+            raise NotImplementedError("generate_frame: input_pos must be pos0 + arange(S), identical for every sample")
+        h0 = ops.embed_gather_sum(tokens, tokens_mask, self.audio_embeddings.weight, self.text_embeddings.weight)
+        h = self.backbone.infer(h0, pos0)
+        last_h = h[:, -1, :].contiguous()
+        logits = [ops.gemm(last_h, self.codebook0_head.weight)]
+        sample = sample_topk(logits[0], topk, temperature)
+        if forced_codes is not None:
+            sample = forced_codes[:, 0:1].to(sample.dtype)
+        out = [sample]
+        emb = self._embed_audio(0, sample.long())                                     # [B,1,D]
+        x = torch.cat([last_h.unsqueeze(1), emb], dim=1)                             # positions 0, 1
+        self.decoder.reset_caches()                                                   # model.py:180-181
+        head_t = self._audio_head_t()
+        dpos = 0
+        for i in range(1, C):
+            n_new = x.shape[1]
+            xp = ops.gemm(x.reshape(B * n_new, -1).contiguous(), self.projection.weight)
+            y = self.decoder.infer(xp.view(B, n_new, -1), dpos)
+            dpos += n_new
+            logits.append(ops.gemm(y[:, -1, :].contiguous(), head_t[i - 1]))          # == mm(h, audio_head[i-1])
+            sample = sample_topk(logits[-1], topk, temperature)
+            if forced_codes is not None:
+                sample = forced_codes[:, i:i + 1].to(sample.dtype)
+            out.append(sample)
+            x = self._embed_audio(i, sample.long())
+        codes = torch.cat(out, dim=1)
+        return (codes, logits) if return_logits else codes
 
     # ---- B200 training forward ---------------------------------------------------------------
     def embed(self, tokens: torch.Tensor, tokens_mask: torch.Tensor) -> torch.Tensor:

@@ -413,6 +413,19 @@ def attention_bwd(q, k, v, o, lse, dout, batch, seq, heads, kv_heads, head_dim, 
     return dq, dk, dv
 
 
+def attention_decode(q, k_cache, v_cache, batch: int, heads: int, kv_heads: int, head_dim: int, kv_len: int):
+    """q [B, H*hd] (one new position per sample) vs caches [B_max, max_seq, KV*hd] (first kv_len positions of each of
+    the first B samples) -> o bf16 [B, H*hd]."""
+    _chk_cuda(q, k_cache, v_cache)
+    assert k_cache.dim() == 3 and k_cache.stride(2) == 1 and k_cache.stride() == v_cache.stride()
+    o = torch.empty(batch, heads * head_dim, dtype=BF16, device=q.device)
+    lib = _lib.load()
+    _lib.check(lib.csm_attn_decode(_p(q), _p(k_cache), _p(v_cache), _p(o), batch, heads, kv_heads, head_dim, kv_len,
+                                   q.stride(0), o.stride(0), k_cache.stride(0), k_cache.stride(1),
+                                   1.0 / math.sqrt(head_dim), _st()), "attn_decode")
+    return o
+
+
 # ----------------------------------------------------------------------------- fused linear + cross-entropy
 def _ce_geometry(h, w, trans_w: bool, groups: int):
     if groups == 1:

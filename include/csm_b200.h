@@ -241,6 +241,14 @@ int csm_linear_ce_bwd(const void* H, const void* W, const int64_t* targets, cons
                       int64_t dh_group_stride, void* workspace, size_t workspace_bytes, int32_t backend,
                       csm_stream_t stream);
 
+/* ---- KV-cache decode attention of Model.generate_frame (model.py:140-195; torchtune attention with kv_cache): one new
+ * query position per sample, q [batch, heads*head_dim] (row stride ldq), against the first kv_len cached positions of
+ * that sample: caches [batch, max_seq, kv_heads*head_dim] bf16 (cache_row_stride between positions, cache_batch_stride
+ * between samples; keys already rotated).  o [batch, heads*head_dim] bf16.  head_dim <= 128, heads/kv_heads <= 8. */
+int csm_attn_decode(const void* q, const void* k_cache, const void* v_cache, void* o, int32_t batch, int32_t heads,
+                    int32_t kv_heads, int32_t head_dim, int32_t kv_len, int64_t ldq, int64_t ldo,
+                    int64_t cache_batch_stride, int64_t cache_row_stride, float scale, csm_stream_t stream);
+
 /* ---- multi-adapter LoRA batching (GPU-native form of MultiSpeakerLoRATrainer, multi_speaker_lora.py:276-300,378-438):
  * the adapters of `adapters` speakers sit side by side in one low-rank tail (per adapted projection: `adapters` blocks of
  * `rank` columns).  Zeroes, in place, every column block of row i of t[rows, cols] (bf16, row stride ldt) that does not

@@ -124,6 +124,62 @@ class OracleModel(nn.Module):
         return torch.cat([audio, text], dim=-2)
 
 
+    # ---- inference (restates model.py:128-200; pinned against the reference's own generate_frame, run live through
+    # the shim, in tests/test_oracle.py::test_oracle_generate_frame_equals_reference_live)
+    def setup_caches(self, max_batch_size: int) -> None:                                  # model.py:128-138
+        dtype = next(self.parameters()).dtype
+        device = next(self.parameters()).device
+        self.backbone.setup_caches(max_batch_size, dtype)
+        self.decoder.setup_caches(max_batch_size, dtype, decoder_max_seq_len=self.cfg.audio_num_codebooks)
+        self.backbone_causal_mask = torch.tril(torch.ones(self.backbone.max_seq_len, self.backbone.max_seq_len,
+                                                          dtype=torch.bool, device=device))
+        self.decoder_causal_mask = torch.tril(torch.ones(self.cfg.audio_num_codebooks, self.cfg.audio_num_codebooks,
+                                                         dtype=torch.bool, device=device))
+
+    def reset_caches(self):                                                               # model.py:197-200
+        self.backbone.reset_caches()
+        self.decoder.reset_caches()
+
+    @torch.no_grad()
+    def generate_frame(self, tokens, tokens_mask, input_pos, temperature: float, topk: int, return_logits=False):
+        """model.py:140-195.  topk == 1 makes sample_topk the argmax (every other probability is exactly 0), which is
+        what the parity tests use.  ``return_logits``: also the 32 logit rows that were sampled from (test aid)."""
+        dtype = next(self.parameters()).dtype
+        assert self.backbone.caches_are_enabled(), "backbone caches are not enabled"
+        curr_backbone_mask = self.backbone_causal_mask[input_pos, :]
+        h = (self._embed_tokens(tokens) * tokens_mask.unsqueeze(-1)).sum(dim=2)
+        h = self.backbone(h, input_pos=input_pos, mask=curr_backbone_mask).to(dtype=dtype)
+        last_h = h[:, -1, :]
+        c0_logits = self.codebook0_head(last_h)
+        logits = [c0_logits]
+        c0_sample = sample_topk(c0_logits, topk, temperature)
+        c0_embed = self._embed_audio(0, c0_sample)
+        curr_h = torch.cat([last_h.unsqueeze(1), c0_embed], dim=1)
+        curr_sample = c0_sample.clone()
+        curr_pos = torch.arange(0, curr_h.size(1), device=curr_h.device).unsqueeze(0).repeat(curr_h.size(0), 1)
+        self.decoder.reset_caches()
+        for i in range(1, self.cfg.audio_num_codebooks):
+            curr_decoder_mask = self.decoder_causal_mask[curr_pos, :]
+            decoder_h = self.decoder(self.projection(curr_h), input_pos=curr_pos, mask=curr_decoder_mask).to(dtype=dtype)
+            ci_logits = torch.mm(decoder_h[:, -1, :], self.audio_head[i - 1])
+            logits.append(ci_logits)
+            ci_sample = sample_topk(ci_logits, topk, temperature)
+            curr_h = self._embed_audio(i, ci_sample)
+            curr_sample = torch.cat([curr_sample, ci_sample], dim=1)
+            curr_pos = curr_pos[:, -1:] + 1
+        return (curr_sample, logits) if return_logits else curr_sample
+
+
+def sample_topk(logits: torch.Tensor, topk: int, temperature: float) -> torch.Tensor:
+    """model.py:85-96 (+ _multinomial_sample_one_no_sync :79-82): top-k filter, softmax, Gumbel-style draw."""
+    logits = logits / temperature
+    indices_to_remove = logits < torch.topk(logits, topk)[0][..., -1, None]
+    scores = F.log_softmax(logits.masked_fill(indices_to_remove, -float("inf")), dim=-1)
+    probs = F.softmax(scores, dim=-1)
+    q = torch.empty_like(probs).exponential_(1)
+    return torch.argmax(probs / q, dim=-1, keepdim=True).to(dtype=torch.int)
+
+
 def gather_indices(tokens: torch.Tensor, audio_vocab: int, codebooks: int) -> torch.Tensor:
     """The integer half of A2 (SURVEY §8a): idx[b,s,c] = tokens[b,s,c] + c*V (int64), c<32;
     column 32 is the raw text token.  Bit-exact parity target for the gather kernel."""

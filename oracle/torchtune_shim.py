@@ -101,7 +101,7 @@ class MultiHeadAttention(nn.Module):
         self.v_proj = nn.Linear(embed_dim, num_kv_heads * head_dim, bias=False)
         self.output_proj = nn.Linear(embed_dim, embed_dim, bias=False)
         self.pos_embeddings = pos_embeddings
-        self.kv_cache = None
+        self.kv_cache = None        # inference only: (k [b, H, max_seq, hd], v, filled) — torchtune 0.4.0 KVCache
 
     def forward(self, x, y, *, mask=None, input_pos=None):
         b, s, _ = x.shape
@@ -115,6 +115,17 @@ class MultiHeadAttention(nn.Module):
         v = v.view(b, s, self.num_kv_heads, 1, self.head_dim).expand(b, s, self.num_kv_heads, rep, self.head_dim)
         k = k.reshape(b, s, -1, self.head_dim).transpose(1, 2)
         v = v.reshape(b, s, -1, self.head_dim).transpose(1, 2)
+        if self.kv_cache is not None:
+            # torchtune 0.4.0 KVCache.update: the (head-expanded, rotated) keys / values of this call are appended
+            # behind what the cache already holds; attention then runs over the WHOLE cache with the caller's
+            # [b, s, max_seq] mask (model.py:165,183: rows of the tril mask picked by input_pos)
+            kc, vc, filled = self.kv_cache
+            if filled + s > kc.shape[2]:
+                raise ValueError("kv cache overflow")
+            kc[:b, :, filled:filled + s] = k
+            vc[:b, :, filled:filled + s] = v
+            self.kv_cache = (kc, vc, filled + s)
+            k, v = kc[:b], vc[:b]
         if mask is not None:
             mask = mask[:, None, :, :]
         out = F.scaled_dot_product_attention(q, k, v, attn_mask=mask, dropout_p=0.0,
@@ -154,15 +165,25 @@ class TransformerDecoder(nn.Module):
         self.max_seq_len, self.num_heads, self.head_dim = max_seq_len, num_heads, head_dim
         self._caches = False
 
-    # KV caches are an inference feature; the training oracle never enables them.
+    # KV caches are an inference feature (generate_frame, model.py:140-195); the training oracle never enables them.
     def setup_caches(self, batch_size, dtype, *, encoder_max_seq_len=None, decoder_max_seq_len=None):
-        raise NotImplementedError("oracle shim: KV caches are not part of the training path")
+        n = decoder_max_seq_len if decoder_max_seq_len is not None else self.max_seq_len
+        for layer in self.layers:
+            a = layer.attn
+            dev = a.q_proj.weight.device
+            a.kv_cache = (torch.zeros(batch_size, a.num_heads, n, a.head_dim, dtype=dtype, device=dev),
+                          torch.zeros(batch_size, a.num_heads, n, a.head_dim, dtype=dtype, device=dev), 0)
+        self._caches = True
 
     def caches_are_enabled(self):
-        return False
+        return self._caches
 
     def reset_caches(self):
-        pass
+        if not self._caches:
+            raise RuntimeError("Key value caches are not setup. Call ``setup_caches()`` first.")
+        for layer in self.layers:
+            kc, vc, _ = layer.attn.kv_cache
+            layer.attn.kv_cache = (kc.zero_(), vc.zero_(), 0)
 
     def forward(self, tokens, *, mask=None, input_pos=None):
         seq_len = tokens.shape[1]

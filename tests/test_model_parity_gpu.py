@@ -251,6 +251,89 @@ def test_multi_adapter_batching_matches_per_row_adapter_oracle(cuda, share_backb
         prod(tok.to(cuda), msk.to(cuda), tgt.to(cuda), frame_idx=fidx.to(cuda))     # several adapters: ids required
 
 
+def _gen_prompt(cfg, B, S, seed):
+    g = torch.Generator().manual_seed(seed)
+    tok = torch.zeros(B, S, 33, dtype=torch.int64)
+    msk = torch.zeros(B, S, 33, dtype=torch.bool)
+    st = S // 2
+    tok[:, :st, 32] = torch.randint(0, cfg.text_vocab_size, (B, st), generator=g)
+    msk[:, :st, 32] = True
+    tok[:, st:, :32] = torch.randint(0, cfg.audio_vocab_size, (B, S - st, 32), generator=g)
+    msk[:, st:, :32] = True
+    return tok, msk
+
+
+def _frame_as_input(codes):
+    B = codes.shape[0]
+    t = torch.cat([codes.long(), torch.zeros(B, 1, dtype=torch.int64, device=codes.device)], dim=1).unsqueeze(1)
+    m = torch.cat([torch.ones(B, 32, dtype=torch.bool, device=codes.device),
+                   torch.zeros(B, 1, dtype=torch.bool, device=codes.device)], dim=1).unsqueeze(1)
+    return t, m
+
+
+@pytest.mark.parametrize("cfg_name,S,steps", [("tiny", 12, 4), ("small", 160, 3)])
+def test_generate_frame_with_kv_cache_matches_oracle(cuda, cfg_name, S, steps):
+    """Model.generate_frame (model.py:140-195) on the training kernels + KV caches — prompt
+    prefill, then single-frame steps through the decode-attention kernel, 31 cached depth-decoder steps per frame —
+    against the oracle's restatement, which equals the REFERENCE's own generate_frame code for code
+    (tests/golden/make_golden_generate.py, tests/test_oracle.py).  topk = 1: sample_topk is the argmax.  The oracle runs
+    in fp32 on the same bf16-representable weights; its codes are fed back on both sides (teacher forcing) so that every
+    one of the 32 logit rows of every frame is compared, and the kernels' own argmax must agree wherever the oracle's
+    top-2 margin is decisive.  The small config prefills 160 positions through the tcgen05 attention kernel."""
+    from oracle import csm_oracle as O
+    prod, cfg = _product_model(cfg_name)
+    orc = O.OracleModel(cfg)
+    O.init_weights(orc, 0, std=0.3 if cfg_name == "tiny" else 0.08)
+    with torch.no_grad():
+        for q in orc.parameters():
+            q.copy_(q.to(torch.bfloat16).float())
+    prod = prod.to(torch.bfloat16)
+    prod.load_state_dict(orc.state_dict())
+    prod = prod.to(cuda)
+    B = 2
+    tok, msk = _gen_prompt(cfg, B, S, 5)
+    orc.setup_caches(B)
+    prod.setup_caches(B)
+    assert prod.backbone.caches_are_enabled() and prod.decoder.caches_are_enabled()
+    agree = decisive = total = 0
+    t_o, m_o, pos = tok, msk, torch.arange(S).unsqueeze(0).repeat(B, 1)
+    for step in range(steps + 1):
+        o_codes, o_logits = orc.generate_frame(t_o, m_o, pos, 0.9, 1, return_logits=True)
+        p_codes, p_logits = prod.generate_frame(t_o.to(cuda), m_o.to(cuda), pos.to(cuda), 0.9, 1, return_logits=True,
+                                                forced_codes=o_codes.to(cuda))
+        assert p_codes.shape == (B, 32) and p_codes.dtype == torch.int32
+        assert torch.equal(p_codes.cpu(), o_codes)                       # forced: the fed-back codes are the oracle's
+        for i, (lo, lp) in enumerate(zip(o_logits, p_logits)):
+            lp = lp.float().cpu()
+            c = float(F.cosine_similarity(lo.flatten(), lp.flatten(), dim=0))
+            assert c >= 0.999, (step, i, c)
+            assert float((lo - lp).abs().max()) <= 0.1 * float(lo.std()) + 0.05, (step, i)
+            top2 = lo.topk(2, dim=-1).values
+            margin = top2[:, 0] - top2[:, 1]
+            mine = lp.argmax(-1)
+            for b in range(B):
+                total += 1
+                ok = int(mine[b]) == int(o_codes[b, i])
+                agree += ok
+                if float(margin[b]) > 0.25 * float(lo.std()):
+                    decisive += 1
+                    assert ok, (step, i, b, float(margin[b]))
+        t_o, m_o = _frame_as_input(o_codes)
+        pos = torch.full((B, 1), S + step)
+    assert decisive > total // 4 and agree >= 0.9 * total, (agree, decisive, total)
+    # free-running (no teacher forcing): the API call a user makes; same codes as the forced run on the first frame
+    prod.reset_caches()
+    free = prod.generate_frame(tok.to(cuda), msk.to(cuda), torch.arange(S, device=cuda).unsqueeze(0).repeat(B, 1), 0.9, 1)
+    assert free.shape == (B, 32)
+    if cfg_name == "tiny":
+        gold = torch.load(os.path.join(os.path.dirname(GOLD), "c1_tiny_generate.pt"))
+        assert torch.equal(gold["tokens"], tok) and torch.equal(gold["mask"], msk)
+        # the reference's own first frame (fp32 weights there, bf16-rounded here): nearly every code agrees
+        assert float((free.cpu().long() == gold["frames"][:, 0]).float().mean()) >= 0.8
+    with pytest.raises(RuntimeError):
+        prod.generate_frame(tok.to(cuda), msk.to(cuda), torch.arange(S, device=cuda).unsqueeze(0).repeat(B, 1), 0.9, 1)
+
+
 def test_no_cpu_fallback():
     from csm.models.model import Model, ModelArgs
     m = Model(ModelArgs("tiny-backbone", "tiny-decoder", 1000, 200, 32)).to(torch.bfloat16)

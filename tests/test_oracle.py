@@ -312,3 +312,47 @@ def test_decoder_alignment_position_i_predicts_code_i(tiny):
     pc0, pc1 = d0["per_codebook_loss"], d1["per_codebook_loss"]
     assert torch.allclose(pc0[1:j], pc1[1:j], atol=1e-6)            # earlier codebooks unaffected
     assert not torch.allclose(pc0[j:], pc1[j:], atol=1e-6)          # own target + later inputs change
+
+
+def _load_make_golden_generate():
+    import importlib.util
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "make_golden_generate.py")
+    spec = importlib.util.spec_from_file_location("_make_golden_generate", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def test_oracle_generate_frame_reproduces_reference_golden():
+    """tests/golden/c1_tiny_generate.pt holds codes produced by the REFERENCE's own Model.generate_frame (KV caches,
+    prompt + 4 single-frame steps, topk = 1); the oracle restatement (shim KV cache + OracleModel.generate_frame) must
+    reproduce them exactly — everywhere, also where /root/reference is absent."""
+    G = _load_make_golden_generate()
+    gold = torch.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "c1_tiny_generate.pt"))
+    torch.set_num_threads(1)
+    cfg = O.cfg_tiny()
+    om = O.OracleModel(cfg)
+    O.init_weights(om, gold["weight_seed"], std=gold["weight_std"])
+    tok, msk = G.prompt(cfg, gold["B"], gold["S"], gold["prompt_seed"])
+    assert torch.equal(tok, gold["tokens"]) and torch.equal(msk, gold["mask"])
+    got = G.run(om, tok, msk, gold["frames"].shape[1] - 1, gold["B"])
+    assert torch.equal(got.long(), gold["frames"])
+
+
+@pytest.mark.skipif(not R.available(), reason="/root/reference only exists in the build container")
+def test_oracle_generate_frame_equals_reference_live():
+    G = _load_make_golden_generate()
+    torch.set_num_threads(1)
+    rm, _ = R.load_reference()
+    cfg = O.cfg_tiny()
+    R.register_flavor(rm, "tiny-bb", cfg.backbone)
+    R.register_flavor(rm, "tiny-dec", cfg.decoder)
+    om = O.OracleModel(cfg)
+    O.init_weights(om, 11, std=0.3)
+    ref = rm.Model(rm.ModelArgs("tiny-bb", "tiny-dec", cfg.text_vocab_size, cfg.audio_vocab_size,
+                                cfg.audio_num_codebooks))
+    ref.load_state_dict(om.state_dict())
+    tok, msk = G.prompt(cfg, 3, 9, 2)
+    with torch.no_grad():
+        want = G.run(ref, tok, msk, 3, 3)
+    assert torch.equal(want.long(), G.run(om, tok, msk, 3, 3).long())
