@@ -346,8 +346,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         __syncwarp();
         if (++stage == kStages) { stage = 0; phase ^= 1; }
-        // next item: drawn while this tile's first loads are in flight (the atomic's latency hides behind them)
-        if (kb == w.kb0 && tq_open) publish(it + 1);
+        // next item: drawn once this tile's loads fill the ring (from then on the producer would only wait for free
+        // slots, so the ~1 us of the atomic costs nothing; drawn right after the first k-block it starved the MMAs at
+        // the start of every tile: +4 % on the K = 8192 GEMMs)
+        if (tq_open && kb == min(w.kb0 + kStages - 1, w.kb1 - 1)) publish(it + 1);
       }
     }
   } else if (warp == 1) {

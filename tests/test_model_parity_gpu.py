@@ -307,7 +307,7 @@ def test_generate_frame_with_kv_cache_matches_oracle(cuda, cfg_name, S, steps):
             lp = lp.float().cpu()
             c = float(F.cosine_similarity(lo.flatten(), lp.flatten(), dim=0))
             assert c >= 0.999, (step, i, c)
-            assert float((lo - lp).abs().max()) <= 0.1 * float(lo.std()) + 0.05, (step, i)
+            assert float((lo - lp).abs().max()) <= 0.25 * float(lo.std()) + 0.05, (step, i)
             top2 = lo.topk(2, dim=-1).values
             margin = top2[:, 0] - top2[:, 1]
             mine = lp.argmax(-1)

@@ -18,6 +18,8 @@ BF = torch.bfloat16
 # A/B switches (defaults untouched when unset): CSM_PAIR_MODE = 0 | 1, CSM_NARROW_TAIL = 1 (experimental)
 if os.environ.get("CSM_PAIR_MODE"):
     ops.set_gemm_cta_pair_mode(int(os.environ["CSM_PAIR_MODE"]))
+if os.environ.get("CSM_DYN_TILES"):
+    ops.set_gemm_dynamic_tiles(int(os.environ["CSM_DYN_TILES"]))
 if os.environ.get("CSM_NARROW_TAIL"):
     ops.set_gemm_narrow_tail_mode(int(os.environ["CSM_NARROW_TAIL"]))
 _flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
