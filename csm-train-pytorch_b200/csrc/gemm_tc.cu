@@ -352,6 +352,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (tq_open && kb == min(w.kb0 + kStages - 1, w.kb1 - 1)) publish(it + 1);
       }
     }
+    // This unit has made its last draw (the one that found no tile).  Once every drawing unit has, nobody touches the
+    // counter again in this launch: the last one re-arms it for the next launch on this slot — here, under the last
+    // tile's MMAs and epilogue, not at kernel exit (that cost ~2 us per launch).
+    if (dyn && rank == 0 && elect_one()) {
+      if (atomicAdd(p.tile_ctr + 1, 1) == tile_step - 1) {
+        p.tile_ctr[0] = 0;
+        p.tile_ctr[1] = 0;
+      }
+    }
+    __syncwarp();
   } else if (warp == 1) {
     // ===================== MMA issuer (warp-uniform control flow, one elected lane issues) =====================
     constexpr uint32_t idesc = make_idesc_bf16(kCta2 ? 2 * BM : BM, BN, kTransA ? 1 : 0, kTransB ? 1 : 0);
@@ -778,15 +788,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 1) {
     tc_fence_after();
     if (kCta2) tmem_dealloc_2sm(tmem_base, Cfg::kTmemCols); else tmem_dealloc(tmem_base, Cfg::kTmemCols);
-  }
-  if (dyn && threadIdx.x == 0) {
-    // the last CTA of the grid to get here re-arms the counters for the next launch on this slot
-    __threadfence();
-    if (atomicAdd(p.tile_ctr + 1, 1) == (int)gridDim.x - 1) {
-      p.tile_ctr[0] = 0;
-      p.tile_ctr[1] = 0;
-      __threadfence();
-    }
   }
 }
 
