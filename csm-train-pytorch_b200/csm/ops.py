@@ -45,7 +45,7 @@ def set_gemm_cta_pair_mode(m: int) -> None:
 
 
 def set_gemm_dynamic_tiles(m: int) -> None:
-    """A/B hook: 1 (default) tiles drawn from a global counter, 0 static round-robin assignment."""
+    """1: GEMM tiles drawn from a global counter (data-parallel runs: NCCL shares the SMs); 0 (default): static."""
     _lib.load().csm_set_gemm_dynamic_tiles(m)
 
 

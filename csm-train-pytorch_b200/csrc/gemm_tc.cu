@@ -844,7 +844,8 @@ static int* g_sk_flags = nullptr;
 // x16384: 176.9 vs 174.8; x3072: 60.4 vs 66.5.  The GPU is power-capped, so the pairs that sit out the last partial
 // wave are not lost throughput (the busy ones clock higher).  Correct and tested, therefore kept, but OFF by default.
 static std::atomic<int> g_sk_mode{0};    // 0 off (default), 1 cut tiles when the last wave is badly filled
-static std::atomic<int> g_dyn_mode{1};   // 1 (default) tiles are drawn from a global counter; 0 static round-robin
+static std::atomic<int> g_dyn_mode{0};   // 1: tiles after a CTA's first are drawn from a global counter; 0 (default): static
+                                         // round-robin (~1 us per launch cheaper when the GEMM has the GPU to itself)
 constexpr int kTileCtrOffset = 512;      // ints into the flag area (the stream-K flags use the first 320)
 constexpr int kTileCtrSlots = 32;
 void gemm_tc_set_dynamic_tiles(int m) { g_dyn_mode.store(m); }

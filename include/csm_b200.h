@@ -180,9 +180,10 @@ void csm_set_attn_backend(int32_t backend);
 /* test hook: CTA-pair (tcgen05 cta_group::2, 256-row tiles) mode of the tensor-core GEMM. -1 = automatic (large
  * plain GEMMs only), 0 = never, 1 = whenever the shape allows it. */
 void csm_set_gemm_cta_pair_mode(int32_t mode);
-/* A/B hook: 1 (default) the persistent GEMM draws its output tiles from a global counter (robust when another kernel —
- * NCCL's all-reduce under data parallelism — holds SMs: a CTA that starts late finds less work), 0 = static round-robin
- * assignment.  Needs the scratch registered with csm_gemm_set_streamk_workspace (the counters live in its flag area);
+/* 1: the persistent GEMM draws every tile after a CTA's first from a global counter — robust when another kernel
+ * (NCCL's all-reduce overlapping the backward under data parallelism) holds SMs: a CTA that starts late finds less
+ * work; the data-parallel full-fine-tune trainer turns it on.  0 (default) = static round-robin assignment, ~1 us per
+ * launch cheaper when the GEMM has the GPU to itself.  Needs the scratch registered with csm_gemm_set_streamk_workspace (the counters live in its flag area);
  * without it the static assignment is used. */
 void csm_set_gemm_dynamic_tiles(int32_t mode);
 /* Stream-K scratch of the CTA-pair GEMM (fp32 partial tiles + self-resetting flags).  The caller allocates

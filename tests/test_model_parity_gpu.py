@@ -326,10 +326,24 @@ def test_generate_frame_with_kv_cache_matches_oracle(cuda, cfg_name, S, steps):
     free = prod.generate_frame(tok.to(cuda), msk.to(cuda), torch.arange(S, device=cuda).unsqueeze(0).repeat(B, 1), 0.9, 1)
     assert free.shape == (B, 32)
     if cfg_name == "tiny":
+        # the committed golden: codes of the REFERENCE's own generate_frame (fp32 weights there, their bf16 rounding
+        # here).  Teacher-forced with the reference's codes (a flipped near-tie would otherwise cascade through the
+        # rest of the frame), the kernels' argmax reproduces nearly every one of the 2 x 5 x 32 draws.
         gold = torch.load(os.path.join(os.path.dirname(GOLD), "c1_tiny_generate.pt"))
         assert torch.equal(gold["tokens"], tok) and torch.equal(gold["mask"], msk)
-        # the reference's own first frame (fp32 weights there, bf16-rounded here): nearly every code agrees
-        assert float((free.cpu().long() == gold["frames"][:, 0]).float().mean()) >= 0.8
+        prod.reset_caches()
+        hits = n = 0
+        t_g, m_g, pos_g = tok, msk, torch.arange(S).unsqueeze(0).repeat(B, 1)
+        for f in range(gold["frames"].shape[1]):
+            want = gold["frames"][:, f]
+            _, lg = prod.generate_frame(t_g.to(cuda), m_g.to(cuda), pos_g.to(cuda), gold["temperature"], gold["topk"],
+                                        return_logits=True, forced_codes=want.to(cuda))
+            mine = torch.stack([x.float().argmax(-1) for x in lg], dim=1).cpu()
+            hits += int((mine == want).sum())
+            n += want.numel()
+            t_g, m_g = _frame_as_input(want)
+            pos_g = torch.full((B, 1), S + f)
+        assert hits >= 0.9 * n, (hits, n)
     with pytest.raises(RuntimeError):
         prod.generate_frame(tok.to(cuda), msk.to(cuda), torch.arange(S, device=cuda).unsqueeze(0).repeat(B, 1), 0.9, 1)
 

@@ -561,8 +561,8 @@ def test_gemm_fp32_output_with_bf16_or_fp32_residual(ops, cuda, backend, M, N, K
 
 @pytest.mark.timeout(300)
 def test_gemm_dynamic_tile_scheduler_is_bit_identical_to_static(ops, cuda):
-    """The persistent tcgen05 GEMM draws its tiles from a global counter by default (late CTAs find less work: data
-    parallel runs share the SMs with NCCL).  Every tile is computed the same way whoever takes it, so all outputs —
+    """The persistent tcgen05 GEMM can draw its tiles from a global counter (late CTAs find less work: data-parallel
+    full fine-tune shares the SMs with NCCL and turns it on).  Every tile is computed the same way whoever takes it, so all outputs —
     plain / LoRA-tail / residual / fp32 / transposed GEMMs in single-CTA and CTA-pair tilings, grouped split
     reductions, the fused SwiGLU and fused-CE epilogues — must equal the static round-robin schedule bit for bit,
     also over many back-to-back launches (the 32 self-resetting counter slots are reused)."""
@@ -592,16 +592,20 @@ def test_gemm_dynamic_tile_scheduler_is_bit_identical_to_static(ops, cuda):
             outs[mode] = [[c().clone() for c in cases] for _ in range(3 if mode else 1)]
         torch.cuda.synchronize()
     finally:
-        ops.set_gemm_dynamic_tiles(1)
+        ops.set_gemm_dynamic_tiles(0)
     for rep in outs[1]:
         for a, b in zip(outs[0][0], rep):
             assert torch.equal(a, b)
     # many launches in a row: every counter slot is used and re-armed several times
     a, b = rnd(1024, 512), rnd(768, 512)
     ref = ops.gemm(a, b).clone()
-    for _ in range(200):
-        out = ops.gemm(a, b)
-    torch.cuda.synchronize()
+    ops.set_gemm_dynamic_tiles(1)
+    try:
+        for _ in range(200):
+            out = ops.gemm(a, b)
+        torch.cuda.synchronize()
+    finally:
+        ops.set_gemm_dynamic_tiles(0)
     assert torch.equal(out, ref)
 
 
