@@ -126,12 +126,18 @@ class _Lin:
             ops.lora_mask_rows_(t, self.rows, self.rank, self.K)
         return ops.gemm(x, self.w, residual=residual, a2=t, b2=self.B, out_dtype=out_dtype), t
 
-    def bwd(self, dy, x, t, grads, need, dx_out=None, accumulate=False, swiglu_gu=None):
+    def bwd(self, dy, x, t, grads, need, dx_out=None, accumulate=False, swiglu_gu=None, sink=None, written=None):
         """Accumulates parameter grads into `grads` and returns dx (optionally accumulated into dx_out).
         With `swiglu_gu` (the saved gate|up buffer of a fused MLP) the dgrad GEMM's epilogue applies the SwiGLU
-        backward and the return value is dgate|dup instead of dx."""
+        backward and the return value is dgate|dup instead of dx.  With a data-parallel `sink` the wgrad GEMM writes
+        straight into the all-reduce bucket (index noted in `written`)."""
         if need[self.iw]:
-            _acc(grads, self.iw, ops.gemm(dy, x, trans_a=True, trans_b=True))
+            dst = sink.grad_view(self.w) if sink is not None else None
+            if dst is not None:
+                ops.gemm(dy, x, trans_a=True, trans_b=True, out=dst, accumulate=sink.has_grad(self.w))
+                written.add(self.iw)
+            else:
+                _acc(grads, self.iw, ops.gemm(dy, x, trans_a=True, trans_b=True))
         if self.A is None:
             if swiglu_gu is not None:
                 return ops.gemm_swiglu_bwd(dy, self.w, swiglu_gu)
@@ -252,12 +258,19 @@ class _Group:
         gu, act = ops.gemm_swiglu_fwd(x, self.W, a2=t, b2=self.B_bd)
         return gu, act, t
 
-    def bwd(self, dy, x, t, grads, need):
+    def bwd(self, dy, x, t, grads, need, sink=None, written=None):
         if any(need[i] for i in self.iw):
-            dW = ops.gemm(dy, x, trans_a=True, trans_b=True)          # [n_out, in] in one GEMM
-            for j, m in enumerate(self.mods):
-                if need[self.iw[j]]:
-                    _acc(grads, self.iw[j], dW[self.offs[j]:self.offs[j] + m.weight.shape[0]])
+            ws = [m.weight for m in self.mods]
+            dst = sink.packed_view(ws) if sink is not None and all(need[i] for i in self.iw) else None
+            if dst is not None:
+                # the whole [n_out, in] weight gradient of the group lands in the data-parallel bucket: no copy
+                ops.gemm(dy, x, trans_a=True, trans_b=True, out=dst, accumulate=sink.has_grad(ws[0]))
+                written.update(self.iw)
+            else:
+                dW = ops.gemm(dy, x, trans_a=True, trans_b=True)          # [n_out, in] in one GEMM
+                for j, m in enumerate(self.mods):
+                    if need[self.iw[j]]:
+                        _acc(grads, self.iw[j], dW[self.offs[j]:self.offs[j] + m.weight.shape[0]])
         if not self.lora:
             return ops.gemm(dy, self.W, trans_b=True)
         # with the common scaling s folded into t and dts:  y = x W^T + t B^T,  t = s x A^T
@@ -351,6 +364,7 @@ class StackFn(Function):
             return dx
 
         sink = getattr(stack, "_grad_sink", None)   # data-parallel bucket owner (csm/training/dp.py), optional
+        written = set()                             # parameter indices whose wgrad GEMM wrote straight into its bucket
 
         def hand_over(module):
             # gradients of `module` are final: give them to the DP synchroniser now so their all-reduce overlaps the
@@ -359,7 +373,9 @@ class StackFn(Function):
                 return
             for prm in module.parameters():
                 i = index_of[id(prm)]
-                if grads[i] is not None and sink.deliver(prm, grads[i]):
+                if i in written:
+                    sink.mark_written(prm)
+                elif grads[i] is not None and sink.deliver(prm, grads[i]):
                     grads[i] = None
 
         xf, rstd_f = ctx.final
@@ -371,21 +387,21 @@ class StackFn(Function):
             I = gu.shape[1] // 2
             # ---- MLP: out = h + w2(silu(w1 hn) * w3 hn)
             if FUSE_SWIGLU_BWD and ops.swiglu_fusable(N, I, D):
-                dgu = l2.bwd(dcur, act, t2, grads, need, swiglu_gu=gu)
+                dgu = l2.bwd(dcur, act, t2, grads, need, swiglu_gu=gu, sink=sink, written=written)
             else:
-                dact = l2.bwd(dcur, act, t2, grads, need)
+                dact = l2.bwd(dcur, act, t2, grads, need, sink=sink, written=written)
                 dgu = torch.empty_like(gu)
                 ops.swiglu_bwd(dact, gu[:, :I], gu[:, I:], dgate=dgu[:, :I], dup=dgu[:, I:])
-            dhn = g13.bwd(dgu, hn, t13, grads, need)
+            dhn = g13.bwd(dgu, hn, t13, grads, need, sink=sink, written=written)
             dh = norm_bwd(dhn, h, layer.mlp_norm, rstd2, dcur)
             # ---- attention: h = x + wo(attn(rope(wq xn), rope(wk xn), wv xn))
-            do = lo.bwd(dh, o, to, grads, need)
+            do = lo.bwd(dh, o, to, grads, need, sink=sink, written=written)
             q, k, v = qkv[:, :nq], qkv[:, nq:nq + nkv], qkv[:, nq + nkv:]
             dqkv = torch.empty_like(qkv)
             dq, dk, dv = dqkv[:, :nq], dqkv[:, nq:nq + nkv], dqkv[:, nq + nkv:]
             # (the inverse RoPE of dq / dk happens in the attention kernels' store epilogues when they can)
             ops.attention_bwd(q, k, v, o, lse, do, B, S, H, KV, hd, dq=dq, dk=dk, dv=dv, rope_cache=cache)
-            dxn = gqkv.bwd(dqkv, xn, tqkv, grads, need)
+            dxn = gqkv.bwd(dqkv, xn, tqkv, grads, need, sink=sink, written=written)
             dcur = norm_bwd(dxn, x, layer.sa_norm, rstd1, dh)
             hand_over(layer)
         ctx.saved = None

@@ -43,9 +43,13 @@ class GradSynchronizer:
     """
 
     def __init__(self, params: Iterable[torch.nn.Parameter], bucket_bytes: Optional[int] = None, group=None,
-                 force_buckets: bool = False, sparse_rows: Optional[torch.nn.Parameter] = None):
+                 force_buckets: bool = False, sparse_rows: Optional[torch.nn.Parameter] = None,
+                 bucket_order: Optional[List[torch.nn.Parameter]] = None):
         """`sparse_rows`: a parameter (the text-embedding table) whose gradient is exchanged as gathered rows by
-        ``exchange_text_rows`` from inside the embedding backward; it is kept out of the all-reduce buckets."""
+        ``exchange_text_rows`` from inside the embedding backward; it is kept out of the all-reduce buckets.
+        `bucket_order`: the parameters in the order the backward produces their gradients (bucket layout order);
+        default: reverse parameter order.  Projections that share a fused GEMM (q|k|v, gate|up) should be adjacent and
+        in GEMM order, so that one wgrad GEMM writes all of them straight into the bucket (``packed_view``)."""
         self.params: List[torch.nn.Parameter] = [p for p in params if p.requires_grad]
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.group = group
@@ -68,7 +72,14 @@ class GradSynchronizer:
         self._buckets: List[Dict] = []
         self._slot: Dict[int, tuple] = {}    # id(param) -> (bucket index, grad view)
         cur, size = [], 0
-        order = list(reversed(self.params))  # backward produces gradients roughly in reverse parameter order
+        if bucket_order is not None:
+            mine = {id(p) for p in self.params}
+            order = [p for p in bucket_order if id(p) in mine]
+            listed = {id(p) for p in order}
+            order += [p for p in reversed(self.params) if id(p) not in listed]
+        else:
+            order = list(reversed(self.params))  # backward produces gradients roughly in reverse parameter order
+        self._offset: Dict[int, tuple] = {}  # id(param) -> (bucket index, element offset)
 
         def close(ps):
             n = sum(p.numel() for p in ps)
@@ -76,6 +87,7 @@ class GradSynchronizer:
             bi, off = len(self._buckets), 0
             for p in ps:
                 self._slot[id(p)] = (bi, buf[off:off + p.numel()].view(p.shape))
+                self._offset[id(p)] = (bi, off)
                 off += p.numel()
             self._buckets.append({"buf": buf, "n": len(ps), "params": ps})
         for p in order:
@@ -150,6 +162,37 @@ class GradSynchronizer:
         self._pending[bi] -= 1
         if self._pending[bi] == 0:
             self._launch(bi)
+
+    # ---- gradients written straight into the bucket by the producing GEMM (no copy)
+    def grad_view(self, p: torch.nn.Parameter) -> Optional[torch.Tensor]:
+        """The bucket view that IS `p`'s gradient storage (None when `p` is not bucketed): a wgrad GEMM passes it as its
+        output (accumulate = ``has_grad(p)``) and then calls ``mark_written(p)``."""
+        if not self.bucketed or id(p) not in self._slot:
+            return None
+        return self._slot[id(p)][1]
+
+    def packed_view(self, ps: List[torch.nn.Parameter]) -> Optional[torch.Tensor]:
+        """One [sum(rows), cols] view over the adjacent bucket slots of several 2-D parameters with the same number of
+        columns (q|k|v, gate|up), or None if they are not adjacent in one bucket in this order."""
+        if not self.bucketed or any(id(p) not in self._offset for p in ps):
+            return None
+        bi, off0 = self._offset[id(ps[0])]
+        off, cols = off0, ps[0].shape[1]
+        for p in ps:
+            b, o = self._offset[id(p)]
+            if b != bi or o != off or p.dim() != 2 or p.shape[1] != cols:
+                return None
+            off += p.numel()
+        return self._buckets[bi]["buf"][off0:off].view(-1, cols)
+
+    def has_grad(self, p: torch.nn.Parameter) -> bool:
+        """True inside an accumulation window when an earlier micro-batch's gradient already sits in the view."""
+        return p.grad is not None and p.grad is self._slot[id(p)][1]
+
+    def mark_written(self, p: torch.nn.Parameter) -> None:
+        bi, view = self._slot[id(p)]
+        p.grad = view
+        self._mark(p, bi)
 
     def deliver(self, p: torch.nn.Parameter, g: torch.Tensor) -> bool:
         """Called by a hand-written backward with a FINAL gradient for `p`.  Returns True if the synchroniser took

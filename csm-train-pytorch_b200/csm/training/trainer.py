@@ -133,13 +133,31 @@ class CSMTrainer:
         self.optimizer = make_optimizer(param_groups, lr, self.weight_decay)
         trainable = [p for p in self.model.parameters() if p.requires_grad]
         self._sync = dp.GradSynchronizer(trainable, bucket_bytes=64 << 20 if total > (32 << 20) else None,
-                                         sparse_rows=self.model.text_embeddings.weight)
+                                         sparse_rows=self.model.text_embeddings.weight,
+                                         bucket_order=self._backward_order())
         self._sync.text_capacity_seq = self.model.backbone.max_seq_len
         # text-embedding gradient: gathered rows instead of a dense 525 MB all-reduce (dp.exchange_text_rows)
         self.model._text_grad_exchange = self._sync.exchange_text_rows if self._sync.sparse_param is not None else None
         sink = self._sync if self._sync.bucketed else None
         self.model.backbone._grad_sink = sink        # the stacks hand their layers' gradients over as they finish
         self.model.decoder._grad_sink = sink
+
+    def _backward_order(self):
+        """Parameters in the order the backward finishes their gradients: audio_head, decoder (final norm, layers
+        last to first), projection, codebook0_head, backbone, then the embedding tables (last: the scatter at the very
+        end of backward).  Inside a layer the projections of a fused GEMM are adjacent and in GEMM order (q|k|v,
+        gate|up) so that their wgrad GEMM writes straight into the bucket."""
+        m = self.model
+
+        def stack(st):
+            out = [st.norm.scale]
+            for layer in reversed(list(st.layers)):
+                a, f = layer.attn, layer.mlp
+                out += [a.q_proj.weight, a.k_proj.weight, a.v_proj.weight, a.output_proj.weight, f.w1.weight,
+                        f.w3.weight, f.w2.weight, layer.sa_norm.scale, layer.mlp_norm.scale]
+            return out
+        return [m.audio_head] + stack(m.decoder) + [m.projection.weight, m.codebook0_head.weight] + \
+            stack(m.backbone) + [m.audio_embeddings.weight, m.text_embeddings.weight]
 
     def enable_cuda_graph(self, warmup: int = 3, max_grad_norm: float = 1.0) -> None:
         """``train_step`` (one micro-batch + optimiser step) replayed as one CUDA graph (training/graph.py)."""
