@@ -28,9 +28,9 @@ SIGNATURES = {
     "csm_decoder_input_bwd": (_i32, [_ptr] * 5 + [_i64, _i64, _i64, _i32, _i64, _i32, _ptr]),
     "csm_rmsnorm_fwd": (_i32, [_ptr] * 4 + [_i64, _i32, _f32, _i32, _ptr]),
     "csm_rmsnorm_bwd": (_i32, [_ptr] * 7 + [_i64, _i32, _i32, _ptr]),
-    "csm_rope": (_i32, [_ptr, _ptr, _i64, _i32, _i32, _i32, _i64, _i32, _ptr]),
+    "csm_rope": (_i32, [_ptr, _ptr, _i64, _i32, _i32, _i32, _i64, _i32, _ptr, _ptr]),
     "csm_gemm_bf16": (_i32, [_ptr] * 4 + [_i64] * 7 + [_i32] * 4 + [_f32, _ptr, _ptr, _i64, _i64, _i64, _i32, _ptr]),
-    "csm_gemm_bf16_rope": (_i32, [_ptr] * 3 + [_i64] * 6 + [_ptr, _ptr, _i64, _i64, _i64, _ptr, _i32, _i32, _i32, _ptr]),
+    "csm_gemm_bf16_rope": (_i32, [_ptr] * 3 + [_i64] * 6 + [_ptr, _ptr, _i64, _i64, _i64, _ptr, _i32, _i32, _i32, _ptr, _ptr]),
     "csm_gemm_splitk_workspace_bytes": (_sz, [_i64, _i64, _i32]),
     "csm_gemm_bf16_splitk": (_i32, [_ptr] * 3 + [_i64] * 6 + [_i32, _i32, _f32, _i32, _ptr, _sz, _ptr]),
     "csm_gemm_swiglu_supported": (_i32, [_i64, _i64, _i64]),
@@ -56,6 +56,8 @@ SIGNATURES = {
                           [_i32] + [_i64] * 4 + [_ptr, _sz, _i32, _ptr]),
     "csm_adamw_clip_step": (_i32, [_ptr] * 7 + [_i32, _f32, _f32, _f32, _f32, _ptr, _ptr, _ptr]),
     "csm_adamw_clip_step_v2": (_i32, [_ptr] * 11 + [_i32, _f32, _f32, _f32, _f32, _i32, _ptr, _ptr, _ptr]),
+    "csm_attn_varlen_fwd": (_i32, [_ptr] * 5 + [_i32] * 5 + [_i64] * 4 + [_f32, _ptr, _ptr]),
+    "csm_attn_varlen_bwd": (_i32, [_ptr] * 9 + [_i32] * 5 + [_i64] * 7 + [_f32, _ptr, _ptr, _ptr, _ptr, _sz, _ptr]),
     "csm_attn_decode": (_i32, [_ptr] * 4 + [_i32] * 5 + [_i64] * 4 + [_f32, _ptr]),
     "csm_lora_mask_rows": (_i32, [_ptr, _i64, _i64, _i32, _ptr, _i32, _i32, _ptr]),
     "csm_f32_to_bf16": (_i32, [_ptr, _ptr, _i64, _f32, _i32, _ptr]),

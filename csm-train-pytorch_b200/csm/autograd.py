@@ -242,11 +242,12 @@ class _Group:
         return t
 
     def fwd(self, x, rope=None):
-        """rope = (cache, seq_len, rope_cols, head_dim): rotate the leading columns in the GEMM's store epilogue."""
+        """rope = (cache, seq_len, rope_cols, head_dim[, positions int32 [N]]): rotate the leading columns in the GEMM's
+        store epilogue (positions: sequence packing, they restart with every packed sample)."""
         t = self._t(x) if self.lora else None
         b2 = self.B_bd if self.lora else None
         if rope is not None:
-            return ops.gemm_rope(x, self.W, *rope, a2=t, b2=b2), t
+            return ops.gemm_rope(x, self.W, *rope[:4], a2=t, b2=b2, positions=rope[4] if len(rope) > 4 else None), t
         return ops.gemm(x, self.W, a2=t, b2=b2), t
 
     def fwd_swiglu(self, x):
@@ -309,6 +310,10 @@ class StackFn(Function):
         rows = getattr(stack, "_adapter_rows", None)              # multi-adapter LoRA: int32 [N] adapter of each row
         if rows is not None and rows.numel() != N:
             raise RuntimeError(f"adapter row ids: expected {N} entries, got {rows.numel()}")
+        # sequence packing: (seg_start int32 [B,S], seg_end int32 [B,S], positions int32 [B*S]) — block-diagonal causal
+        # attention and RoPE positions that restart with every packed sample
+        packing = getattr(stack, "_packing", None)
+        seg_start, seg_end, pos_rows = packing if packing is not None else (None, None, None)
         cur = x.reshape(N, D).contiguous()
         res_dtype = torch.float32 if FP32_RESIDUAL else BF16       # dtype of h / out (cur is bf16 for layer 0 only)
         saved = []
@@ -319,9 +324,9 @@ class StackFn(Function):
             lo, l2 = _Lin(a.output_proj, index_of, rows), _Lin(layer.mlp.w2, index_of, rows)
             I = layer.mlp.w1.weight.shape[0]
             xn, rstd1 = ops.rmsnorm(cur, layer.sa_norm.scale, eps)
-            qkv, tqkv = gqkv.fwd(xn, rope=(cache, S, nq + nkv, hd))   # q and k heads rotated in the store epilogue
+            qkv, tqkv = gqkv.fwd(xn, rope=(cache, S, nq + nkv, hd, pos_rows))   # q, k rotated in the store epilogue
             q, k, v = qkv[:, :nq], qkv[:, nq:nq + nkv], qkv[:, nq + nkv:]
-            o, lse = ops.attention_fwd(q, k, v, B, S, H, KV, hd)
+            o, lse = ops.attention_fwd(q, k, v, B, S, H, KV, hd, seg_start=seg_start)
             h, to = lo.fwd(o, residual=cur, out_dtype=res_dtype)
             hn, rstd2 = ops.rmsnorm(h, layer.mlp_norm.scale, eps)
             if ops.swiglu_fusable(N, I, D):
@@ -340,6 +345,7 @@ class StackFn(Function):
         ctx.index_of = index_of
         ctx.nparams = len(params)
         ctx.geom = (B, S, D)
+        ctx.packing = (seg_start, seg_end)
         return y.view(B, S, D)
 
     @staticmethod
@@ -400,7 +406,8 @@ class StackFn(Function):
             dqkv = torch.empty_like(qkv)
             dq, dk, dv = dqkv[:, :nq], dqkv[:, nq:nq + nkv], dqkv[:, nq + nkv:]
             # (the inverse RoPE of dq / dk happens in the attention kernels' store epilogues when they can)
-            ops.attention_bwd(q, k, v, o, lse, do, B, S, H, KV, hd, dq=dq, dk=dk, dv=dv, rope_cache=cache)
+            ops.attention_bwd(q, k, v, o, lse, do, B, S, H, KV, hd, dq=dq, dk=dk, dv=dv, rope_cache=cache,
+                              seg_start=ctx.packing[0], seg_end=ctx.packing[1])
             dxn = gqkv.bwd(dqkv, xn, tqkv, grads, need, sink=sink, written=written)
             dcur = norm_bwd(dxn, x, layer.sa_norm, rstd1, dh)
             hand_over(layer)

@@ -15,6 +15,7 @@ pinned host tensors, and a length-bucketed batch order that keeps padding (waste
 """
 from __future__ import annotations
 
+import math
 from typing import Dict, Iterable, List, Optional, Sequence, Tuple
 
 import torch
@@ -93,6 +94,81 @@ def collate_pinned(batch: List[Dict[str, torch.Tensor]], pin: bool = True,
         tgt[i, :t] = b["target_audio_tokens"]
         lens[i] = t
     return {"input_tokens": tok, "input_masks": msk, "target_audio_tokens": tgt, "target_lengths": lens}
+
+
+def pack_samples(samples: List[Dict[str, torch.Tensor]], max_len: int, pad_to_multiple: int = 128,
+                 fraction: float = 1.0 / 16, generator: Optional[torch.Generator] = None,
+                 pin: bool = True) -> Dict[str, torch.Tensor]:
+    """Sequence packing: variable-length samples laid back to back in rows of at most ``max_len``
+    frames instead of one zero-padded row per sample (the reference's collate pads every sample to the batch maximum,
+    training_data.py:379-408, and the padding frames cost full backbone FLOPs).  First-fit-decreasing bin packing; the
+    row length is the longest row rounded up to ``pad_to_multiple`` (whole attention tiles).
+
+    Returns the usual keys for R rows of S frames — ``input_tokens`` [R,S,C+1], ``input_masks`` [R,S,C+1],
+    ``target_audio_tokens`` [R,S,C] (each sample's target rows at its own positions: position p of a sample pairs with
+    its target row p, utils.py:101-104) — plus what the packed kernels need:
+      ``segment_starts`` / ``segment_ends`` int32 [R,S]   first / last+1 position of the sample position i belongs to
+                                                          (a padding frame is its own one-frame segment)
+      ``target_mask``  bool [R,S]    positions of the semantic term: p < min(len - 1, target rows) of each sample
+      ``frame_idx``    int64 [N,2]   decoder frames (row, position): ceil(n/16) of each sample's valid positions
+      ``sample_index`` int64 [R,S]   which input sample a position came from (-1: padding)"""
+    if not samples:
+        raise ValueError("pack_samples: no samples")
+    lens = [int(b["input_tokens"].shape[0]) for b in samples]
+    if max(lens) > max_len:
+        raise ValueError(f"pack_samples: a sample of {max(lens)} frames does not fit max_len={max_len}")
+    order = sorted(range(len(samples)), key=lambda j: -lens[j])
+    rows: List[List[int]] = []
+    used: List[int] = []
+    for j in order:
+        for r in range(len(rows)):
+            if used[r] + lens[j] <= max_len:
+                rows[r].append(j)
+                used[r] += lens[j]
+                break
+        else:
+            rows.append([j])
+            used.append(lens[j])
+    S = (max(used) + pad_to_multiple - 1) // pad_to_multiple * pad_to_multiple
+    R = len(rows)
+    W = samples[0]["input_tokens"].shape[1]
+    C = samples[0]["target_audio_tokens"].shape[1]
+    pin = pin and torch.cuda.is_available()
+    tok = torch.zeros(R, S, W, dtype=torch.int64, pin_memory=pin)
+    msk = torch.zeros(R, S, W, dtype=torch.bool, pin_memory=pin)
+    tgt = torch.zeros(R, S, C, dtype=torch.int64, pin_memory=pin)
+    idx = torch.arange(S, dtype=torch.int32)
+    ss = idx.repeat(R, 1).contiguous()
+    se = (idx + 1).repeat(R, 1).contiguous()
+    tmask = torch.zeros(R, S, dtype=torch.bool)
+    owner = torch.full((R, S), -1, dtype=torch.int64)
+    frames = []
+    for r, members in enumerate(rows):
+        off = 0
+        for j in members:
+            b, n = samples[j], lens[j]
+            t = min(int(b["target_audio_tokens"].shape[0]), n)
+            tok[r, off:off + n] = b["input_tokens"]
+            msk[r, off:off + n] = b["input_masks"].bool()
+            tgt[r, off:off + t] = b["target_audio_tokens"][:t]
+            ss[r, off:off + n] = off
+            se[r, off:off + n] = off + n
+            owner[r, off:off + n] = j
+            valid = max(0, min(n - 1, t))
+            tmask[r, off:off + valid] = True
+            if valid > 0:
+                keep = max(1, math.ceil(valid * fraction))
+                sel = torch.randperm(valid, generator=generator)[:keep].sort().values + off
+                frames.append(torch.stack([torch.full_like(sel, r), sel], dim=1))
+            off += n
+    fidx = torch.cat(frames, 0) if frames else torch.zeros(0, 2, dtype=torch.int64)
+    return {"input_tokens": tok, "input_masks": msk, "target_audio_tokens": tgt, "segment_starts": ss,
+            "segment_ends": se, "target_mask": tmask, "frame_idx": fidx, "sample_index": owner}
+
+
+def packing_efficiency(batch: Dict[str, torch.Tensor]) -> float:
+    """Fraction of the packed frames that are real (not padding)."""
+    return float((batch["sample_index"] >= 0).float().mean())
 
 
 def length_bucketed_order(lengths: Sequence[int], batch_size: int, seed: int = 0, window: int = 50) -> List[List[int]]:

@@ -166,18 +166,19 @@ class TransformerDecoder(nn.Module):
         self._cache_len = pos0 + S
         return y.view(B, S, D)
 
-    def run(self, x: torch.Tensor, adapter_rows: Optional[torch.Tensor] = None) -> torch.Tensor:
+    def run(self, x: torch.Tensor, adapter_rows: Optional[torch.Tensor] = None, packing=None) -> torch.Tensor:
         """bf16 [B,S,D] -> bf16 [B,S,D] (layers + final norm) through the CUDA kernels.  ``adapter_rows`` int32 [B*S]:
-        which LoRA adapter each row uses (multi-adapter batching; csm/models/lora.py)."""
+        which LoRA adapter each row uses (multi-adapter batching; csm/models/lora.py).  ``packing`` = (seg_start,
+        seg_end, positions): several samples per row (csm/data/frames.py::pack_samples)."""
         if not x.is_cuda:
             raise RuntimeError("csm_b200: the transformer runs on CUDA only (no CPU fallback)")
         if x.dtype != BF16:
             raise RuntimeError(f"csm_b200: bf16 activations expected, got {x.dtype}; call model.to(torch.bfloat16)")
-        self._adapter_rows = adapter_rows
+        self._adapter_rows, self._packing = adapter_rows, packing
         try:
             return StackFn.apply(x, self, *list(self.parameters()))
         finally:
-            self._adapter_rows = None
+            self._adapter_rows = self._packing = None
 
     def forward(self, h: torch.Tensor, *, input_pos: Optional[torch.Tensor] = None,
                 mask: Optional[torch.Tensor] = None) -> torch.Tensor:
@@ -401,7 +402,9 @@ class Model(nn.Module):
                 target_audio_tokens: Optional[torch.Tensor] = None, *, frame_idx: Optional[torch.Tensor] = None,
                 decoder_frame_fraction: float = 1.0 / 16, semantic_weight: float = 100.0,
                 acoustic_weight: float = 1.0, target_lengths: Optional[torch.Tensor] = None,
-                mask_padded_targets: bool = False, speaker_ids: Optional[torch.Tensor] = None):
+                mask_padded_targets: bool = False, speaker_ids: Optional[torch.Tensor] = None,
+                segment_starts: Optional[torch.Tensor] = None, segment_ends: Optional[torch.Tensor] = None,
+                target_mask: Optional[torch.Tensor] = None):
         """tokens int64 [B,S,33], tokens_mask bool [B,S,33], target_audio_tokens int64 [B,T,32].
 
         Returns (loss, {"semantic_loss", "acoustic_loss", "per_codebook_loss": fp32[32]}); with
@@ -413,6 +416,11 @@ class Model(nn.Module):
         ``speaker_ids`` int [B] (multi-adapter LoRA models only): sample b runs through adapter speaker_ids[b] of every
         adapted projection (index into the adapters, not the user's speaker number); a stack whose adapters are shared
         (one adapter) ignores it.
+        ``segment_starts`` / ``segment_ends`` int32 [B,S] (sequence packing, csm/data/frames.py::pack_samples): row b
+        holds several samples back to back; position i belongs to the sample spanning [start, end).  Attention is then
+        block-diagonal causal, RoPE positions restart per sample, and the semantic term covers ``target_mask`` [B,S]
+        (default: every position that is not the last of its sample) — i.e. exactly the positions the reference's
+        ``[:, :-1]`` rule (utils.py:98-104) keeps when each sample is run alone, without any padding frame.
         """
         if not tokens.is_cuda:
             raise RuntimeError("csm_b200: Model.forward needs CUDA tensors (no CPU fallback)")
@@ -428,17 +436,34 @@ class Model(nn.Module):
                 rows_b = sid.repeat_interleave(S).contiguous()
         elif max(getattr(self.backbone, "lora_adapters", 1), getattr(self.decoder, "lora_adapters", 1)) > 1:
             raise RuntimeError("this model holds several LoRA adapters per projection: pass speaker_ids [B]")
-        hb = self.backbone.run(h0, rows_b)                       # [B,S,D] bf16 (final norm applied)
+        packing = None
+        if segment_starts is not None:
+            if segment_ends is None:
+                raise RuntimeError("sequence packing needs segment_starts and segment_ends")
+            ss = segment_starts.to(device=tokens.device, dtype=torch.int32).contiguous()
+            se = segment_ends.to(device=tokens.device, dtype=torch.int32).contiguous()
+            pos = (torch.arange(S, device=tokens.device, dtype=torch.int32)[None, :] - ss).reshape(-1).contiguous()
+            packing = (ss, se, pos)
+        hb = self.backbone.run(h0, rows_b, packing)              # [B,S,D] bf16 (final norm applied)
         if target_audio_tokens is None:
             return hb
         T = target_audio_tokens.shape[1]
-        if T < S - 1:
+        if T < S - 1 and segment_starts is None:
             raise RuntimeError(f"target_audio_tokens has {T} frames, need at least seq_len-1 = {S - 1}")
         # ---- semantic term (utils.py:98-107): position p predicts targets[b,p,0], p < S-1, mean over B*(S-1)
         tgt0 = torch.full((B, S), -1, dtype=torch.int64, device=tokens.device)
         tgt0[:, : S - 1] = target_audio_tokens[:, : S - 1, 0]
         count = B * (S - 1)
-        if mask_padded_targets and target_lengths is not None:
+        if packing is not None:
+            idx = torch.arange(S, device=tokens.device)[None, :]
+            keep = (idx + 1 < packing[1]) if target_mask is None else target_mask.to(tokens.device).bool()
+            keep = keep & (idx < T)
+            tg = target_audio_tokens[:, :S, 0]
+            if T < S:
+                tg = torch.nn.functional.pad(tg, (0, S - T))
+            tgt0 = torch.where(keep, tg, torch.full_like(tg, -1))
+            count = keep.sum().clamp(min=1).to(torch.float32)
+        elif mask_padded_targets and target_lengths is not None:
             tl = target_lengths.to(tokens.device).clamp(max=S - 1)
             tgt0.masked_fill_(torch.arange(S, device=tokens.device)[None, :] >= tl[:, None], -1)
             count = tl.sum().clamp(min=1).to(torch.float32)          # device scalar: graph-replayable
@@ -446,6 +471,9 @@ class Model(nn.Module):
         per_cb = [sem.detach()]
         # ---- acoustic term (A7/A8)
         if frame_idx is None:
+            if packing is not None:
+                raise RuntimeError("a packed batch carries its own frame_idx (csm/data/frames.py::pack_samples picks the "
+                                   "decoder frames per sample)")
             frame_idx = self.select_frames(tokens_mask, T, decoder_frame_fraction, target_lengths=target_lengths)
         frame_idx = frame_idx.to(tokens.device)
         if frame_idx.numel() > 0:

@@ -155,14 +155,15 @@ def rmsnorm_bwd(dy, x, scale, rstd, dres: Optional[torch.Tensor], dscale_f32: Op
     return dx
 
 
-def rope_(x2d, cache, seq_len: int, heads: int, head_dim: int, inverse: bool = False, ld: Optional[int] = None):
-    """In place on x2d [rows, >= heads*head_dim] (row stride ld)."""
-    _chk_cuda(x2d, cache)
+def rope_(x2d, cache, seq_len: int, heads: int, head_dim: int, inverse: bool = False, ld: Optional[int] = None,
+          positions: Optional[torch.Tensor] = None):
+    """In place on x2d [rows, >= heads*head_dim] (row stride ld); `positions` int32 [rows] overrides row % seq_len."""
+    _chk_cuda(x2d, cache, positions)
     rows = x2d.shape[0]
     ld = x2d.stride(0) if ld is None else ld
     lib = _lib.load()
-    _lib.check(lib.csm_rope(_p(x2d), _p(cache), rows, seq_len, heads, head_dim, ld, 1 if inverse else 0, _st()),
-               "rope")
+    _lib.check(lib.csm_rope(_p(x2d), _p(cache), rows, seq_len, heads, head_dim, ld, 1 if inverse else 0,
+                            _p(positions), _st()), "rope")
     return x2d
 
 
@@ -230,7 +231,7 @@ def _splitk_choice(M: int, N: int, K: int) -> int:
 
 
 
-def gemm_rope(a, b, cache, seq_len: int, rope_cols: int, head_dim: int, *, a2=None, b2=None):
+def gemm_rope(a, b, cache, seq_len: int, rope_cols: int, head_dim: int, *, a2=None, b2=None, positions=None):
     """out = a @ b^T (+ a2 @ b2^T) with RoPE applied to columns [0, rope_cols) (heads of head_dim, position = row %
     seq_len): the fused q|k|v projection.  One launch when the tcgen05 GEMM takes the shape, else gemm + rope."""
     _chk_cuda(a, b, cache, a2, b2)
@@ -241,7 +242,7 @@ def gemm_rope(a, b, cache, seq_len: int, rope_cols: int, head_dim: int, *, a2=No
              and b.stride(1) == 1 and a.stride(0) % 8 == 0 and b.stride(0) % 8 == 0)
     if not fused:
         out = gemm(a, b, a2=a2, b2=b2)
-        rope_(out[:, :rope_cols], cache, seq_len, rope_cols // head_dim, head_dim)
+        rope_(out[:, :rope_cols], cache, seq_len, rope_cols // head_dim, head_dim, positions=positions)
         return out
     _ensure_streamk_workspace(a.device)
     out = torch.empty(M, N, dtype=BF16, device=a.device)
@@ -253,7 +254,7 @@ def gemm_rope(a, b, cache, seq_len: int, rope_cols: int, head_dim: int, *, a2=No
     _lib.check(lib.csm_gemm_bf16_rope(_p(a), _p(b), _p(out), M, N, K, a.stride(0), b.stride(0), out.stride(0), _p(a2),
                                       _p(b2), K2, a2.stride(0) if a2 is not None else 0,
                                       b2.stride(0) if b2 is not None else 0, _p(cache), seq_len, rope_cols, head_dim,
-                                      _st()), "gemm_bf16_rope")
+                                      _p(positions), _st()), "gemm_bf16_rope")
     if _gemm_prof is not None:
         e1.record()
         _gemm_prof.append((2.0 * M * N * (K + K2), e0, e1))
@@ -370,12 +371,19 @@ def gemm_swiglu_bwd(dy, w2, gu, *, a2=None, b2=None):
 
 
 # ----------------------------------------------------------------------------- attention
-def attention_fwd(q, k, v, batch: int, seq: int, heads: int, kv_heads: int, head_dim: int):
-    """q [B*S, H*hd], k/v [B*S, KV*hd] (row strides free) -> (o [B*S, H*hd], lse fp32 [B,H,S])."""
-    _chk_cuda(q, k, v)
+def attention_fwd(q, k, v, batch: int, seq: int, heads: int, kv_heads: int, head_dim: int, seg_start=None):
+    """q [B*S, H*hd], k/v [B*S, KV*hd] (row strides free) -> (o [B*S, H*hd], lse fp32 [B,H,S]).
+    `seg_start` int32 [B,S] (sequence packing): block-diagonal causal attention, see csm_attn_varlen_fwd."""
+    _chk_cuda(q, k, v, seg_start)
     o = torch.empty(batch * seq, heads * head_dim, dtype=BF16, device=q.device)
     lse = torch.empty(batch, heads, seq, dtype=torch.float32, device=q.device)
     lib = _lib.load()
+    if seg_start is not None:
+        assert seg_start.dtype == torch.int32 and seg_start.is_contiguous() and seg_start.numel() == batch * seq
+        _lib.check(lib.csm_attn_varlen_fwd(_p(q), _p(k), _p(v), _p(o), _p(lse), batch, seq, heads, kv_heads, head_dim,
+                                           q.stride(0), k.stride(0), v.stride(0), o.stride(0),
+                                           1.0 / math.sqrt(head_dim), _p(seg_start), _st()), "attn_varlen_fwd")
+        return o, lse
     _lib.check(lib.csm_attn_causal_gqa_fwd(_p(q), _p(k), _p(v), _p(o), _p(lse), batch, seq, heads, kv_heads,
                                            head_dim, q.stride(0), k.stride(0), v.stride(0), o.stride(0),
                                            1.0 / math.sqrt(head_dim), _st()), "attn_fwd")
@@ -383,7 +391,7 @@ def attention_fwd(q, k, v, batch: int, seq: int, heads: int, kv_heads: int, head
 
 
 def attention_bwd(q, k, v, o, lse, dout, batch, seq, heads, kv_heads, head_dim, dq=None, dk=None, dv=None,
-                  rope_cache=None):
+                  rope_cache=None, seg_start=None, seg_end=None):
     """With `rope_cache` the returned dq / dk are gradients w.r.t. the UN-rotated projections (inverse RoPE applied):
     inside the tcgen05 kernels' store epilogues when they take the shape, else by the rope kernel afterwards."""
     _chk_cuda(q, k, v, o, lse, dout, dq, dk, dv)
@@ -394,6 +402,14 @@ def attention_bwd(q, k, v, o, lse, dout, batch, seq, heads, kv_heads, head_dim, 
     lib = _lib.load()
     nbytes = lib.csm_attn_bwd_workspace_bytes(batch, seq, heads, kv_heads, head_dim)
     ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    if seg_start is not None:                          # sequence packing: tcgen05 kernels only (they raise otherwise)
+        _chk_cuda(seg_start, seg_end)
+        _lib.check(lib.csm_attn_varlen_bwd(_p(q), _p(k), _p(v), _p(o), _p(lse), _p(dout), _p(dq), _p(dk), _p(dv), batch,
+                                           seq, heads, kv_heads, head_dim, q.stride(0), k.stride(0), v.stride(0),
+                                           o.stride(0), dq.stride(0), dk.stride(0), dv.stride(0),
+                                           1.0 / math.sqrt(head_dim), _p(rope_cache), _p(seg_start), _p(seg_end),
+                                           _p(ws), nbytes, _st()), "attn_varlen_bwd")
+        return dq, dk, dv
     fuse = (rope_cache is not None and head_dim == 64 and seq >= 128 and _attn_backend in (0, 3)
             and all(t.stride(0) % 8 == 0 and t.data_ptr() % 16 == 0 for t in (q, k, v, o, dq, dk, dv, dout)))
     if fuse:

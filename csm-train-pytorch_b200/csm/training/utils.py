@@ -38,13 +38,16 @@ def compute_loss(model, input_tokens: torch.Tensor, input_masks: torch.Tensor, t
                  semantic_weight: float = 100.0, acoustic_weight: float = 1.0, *,
                  frame_idx: Optional[torch.Tensor] = None, decoder_frame_fraction: float = 1.0 / 16,
                  target_lengths: Optional[torch.Tensor] = None, mask_padded_targets: bool = False,
-                 speaker_ids: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, Dict[str, torch.Tensor]]:
+                 speaker_ids: Optional[torch.Tensor] = None, segment_starts: Optional[torch.Tensor] = None,
+                 segment_ends: Optional[torch.Tensor] = None,
+                 target_mask: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, Dict[str, torch.Tensor]]:
     """(total loss, {"semantic_loss", "acoustic_loss", "per_codebook_loss"}) — utils.py:56-119.  The keyword-only
     arguments are extensions (explicit decoder frames, true target lengths); without them the call is the reference's."""
     return model(input_tokens, input_masks, target_audio_tokens, frame_idx=frame_idx,
                  decoder_frame_fraction=decoder_frame_fraction, semantic_weight=semantic_weight,
                  acoustic_weight=acoustic_weight, target_lengths=target_lengths,
-                 mask_padded_targets=mask_padded_targets, speaker_ids=speaker_ids)
+                 mask_padded_targets=mask_padded_targets, speaker_ids=speaker_ids, segment_starts=segment_starts,
+                 segment_ends=segment_ends, target_mask=target_mask)
 
 
 def save_checkpoint(model, optimizer, epoch: int, global_step: int, loss: float, save_dir: str,

@@ -65,10 +65,10 @@ int attn_bwd_small_launch(const void*, const void*, const void*, const void*, co
 bool attn_tc_supported(int S, int hd, int64_t ldq, int64_t ldk, int64_t ldv, int64_t ldo, const void* q, const void* k,
                        const void* v, const void* o);
 int attn_fwd_tc_launch(const void*, const void*, const void*, void*, float*, int, int, int, int, int64_t, int64_t,
-                       int64_t, int64_t, float, cudaStream_t);
+                       int64_t, int64_t, float, const int32_t*, cudaStream_t);
 int attn_bwd_tc_launch(const void*, const void*, const void*, const void*, const float*, const void*, void*, void*,
                        void*, float*, int, int, int, int, int64_t, int64_t, int64_t, int64_t, int64_t, int64_t, int64_t,
-                       float, const float*, cudaStream_t);
+                       float, const float*, const int32_t*, const int32_t*, cudaStream_t);
 static std::atomic<int> g_attn_backend{0};  // 0 auto, 1 scalar, 2 mma.sync, 3 tcgen05, 4 short-sequence
 
 int gemm_dispatch(const void* A, const void* B, void* C, const void* R, int64_t M, int64_t N, int64_t K,
@@ -167,13 +167,13 @@ int gemm_tc_splitk(const void*, const void*, void*, int64_t, int64_t, int64_t, i
 namespace csm {
 int gemm_tc_launch_rope(const void*, const void*, void*, const void*, int64_t, int64_t, int64_t, int64_t, int64_t,
                         int64_t, int64_t, int, int, int, int, float, const void*, const void*, int64_t, int64_t, int64_t,
-                        const float*, int, int, int, cudaStream_t);
+                        const float*, int, int, int, const int32_t*, cudaStream_t);
 }  // namespace csm
 
 extern "C" int csm_gemm_bf16_rope(const void* A, const void* B, void* C, int64_t M, int64_t N, int64_t K, int64_t lda,
                                   int64_t ldb, int64_t ldc, const void* A2, const void* B2, int64_t K2, int64_t lda2,
                                   int64_t ldb2, const float* rope_cache, int32_t seq_len, int32_t rope_cols,
-                                  int32_t head_dim, csm_stream_t stream) {
+                                  int32_t head_dim, const int32_t* rope_pos, csm_stream_t stream) {
   CSM_REQUIRE(csm_device_supported() == 1, CSM_ERR_ARCH, "gemm_rope: needs an sm_100 device");
   CSM_REQUIRE(rope_cache && aligned16(rope_cache) && seq_len > 0 && head_dim >= 8 && head_dim % 8 == 0 &&
                   rope_cols >= 0 && rope_cols <= N && rope_cols % head_dim == 0,
@@ -184,7 +184,8 @@ extern "C" int csm_gemm_bf16_rope(const void* A, const void* B, void* C, int64_t
                                     lda2, ldb2),
               CSM_ERR_SHAPE, "gemm_rope: shape not supported by the tcgen05 GEMM (use csm_gemm_bf16 + csm_rope)");
   return gemm_tc_launch_rope(A, B, C, nullptr, M, N, K, lda, ldb, ldc, 0, 0, 0, CSM_DT_BF16, 0, 1.f, A2, A2 ? B2 : nullptr,
-                             A2 ? K2 : 0, lda2, ldb2, rope_cache, seq_len, rope_cols, head_dim, as_stream(stream));
+                             A2 ? K2 : 0, lda2, ldb2, rope_cache, seq_len, rope_cols, head_dim, rope_pos,
+                             as_stream(stream));
 }
 
 extern "C" size_t csm_gemm_splitk_workspace_bytes(int64_t M, int64_t N, int32_t splits) {
@@ -255,7 +256,7 @@ extern "C" int csm_attn_causal_gqa_fwd(const void* q, const void* k, const void*
   if (batch == 0) return CSM_OK;
   const int be = g_attn_backend.load();
   if ((be == 0 || be == 3) && attn_tc_supported(seq, head_dim, ldq, ldk, ldv, ldo, q, k, v, o))
-    return attn_fwd_tc_launch(q, k, v, o, lse, batch, seq, heads, kv_heads, ldq, ldk, ldv, ldo, scale,
+    return attn_fwd_tc_launch(q, k, v, o, lse, batch, seq, heads, kv_heads, ldq, ldk, ldv, ldo, scale, nullptr,
                               as_stream(stream));
   CSM_REQUIRE(be != 3, CSM_ERR_SHAPE, "attn_fwd: shape not supported by the tcgen05 kernel (hd=64, seq>=128)");
   if ((be == 0 || be == 4) && attn_small_supported(seq, heads, kv_heads, head_dim, ldq, ldk, ldv, ldo, q, k, v, o))
@@ -286,7 +287,40 @@ extern "C" int csm_attn_causal_gqa_bwd_rope(const void* q, const void* k, const 
   CSM_REQUIRE(workspace && workspace_bytes >= (size_t)batch * heads * seq * sizeof(float), CSM_ERR_SHAPE,
               "attn_bwd_rope: workspace too small");
   return attn_bwd_tc_launch(q, k, v, o, lse, dout, dq, dk, dv, reinterpret_cast<float*>(workspace), batch, seq, heads,
-                            kv_heads, ldq, ldk, ldv, ldo, lddq, lddk, lddv, scale, rope_cache, as_stream(stream));
+                            kv_heads, ldq, ldk, ldv, ldo, lddq, lddk, lddv, scale, rope_cache, nullptr, nullptr,
+                            as_stream(stream));
+}
+
+// ---- sequence packing: several samples per row, block-diagonal causal attention
+extern "C" int csm_attn_varlen_fwd(const void* q, const void* k, const void* v, void* o, float* lse, int32_t batch,
+                                   int32_t seq, int32_t heads, int32_t kv_heads, int32_t head_dim, int64_t ldq,
+                                   int64_t ldk, int64_t ldv, int64_t ldo, float scale, const int32_t* seg_start,
+                                   csm_stream_t stream) {
+  CSM_REQUIRE(batch > 0 && seq > 0 && heads > 0 && kv_heads > 0 && heads % kv_heads == 0 && seg_start, CSM_ERR_SHAPE,
+              "attn_varlen_fwd: bad arguments");
+  CSM_REQUIRE(attn_tc_supported(seq, head_dim, ldq, ldk, ldv, ldo, q, k, v, o), CSM_ERR_SHAPE,
+              "attn_varlen_fwd: packed attention runs on the tcgen05 kernels only (head_dim 64, rows of >= 128 frames, "
+              "16-byte aligned operands)");
+  return attn_fwd_tc_launch(q, k, v, o, lse, batch, seq, heads, kv_heads, ldq, ldk, ldv, ldo, scale, seg_start,
+                            as_stream(stream));
+}
+
+extern "C" int csm_attn_varlen_bwd(const void* q, const void* k, const void* v, const void* o, const float* lse,
+                                   const void* dout, void* dq, void* dk, void* dv, int32_t batch, int32_t seq,
+                                   int32_t heads, int32_t kv_heads, int32_t head_dim, int64_t ldq, int64_t ldk,
+                                   int64_t ldv, int64_t ldo, int64_t lddq, int64_t lddk, int64_t lddv, float scale,
+                                   const float* rope_cache, const int32_t* seg_start, const int32_t* seg_end,
+                                   void* workspace, size_t workspace_bytes, csm_stream_t stream) {
+  CSM_REQUIRE(batch > 0 && seq > 0 && heads > 0 && kv_heads > 0 && heads % kv_heads == 0 && seg_start && seg_end,
+              CSM_ERR_SHAPE, "attn_varlen_bwd: bad arguments");
+  CSM_REQUIRE(!rope_cache || aligned16(rope_cache), CSM_ERR_ALIGN, "attn_varlen_bwd: misaligned RoPE table");
+  CSM_REQUIRE(attn_tc_supported(seq, head_dim, ldq, ldk, ldv, ldo, q, k, v, o), CSM_ERR_SHAPE,
+              "attn_varlen_bwd: packed attention runs on the tcgen05 kernels only (head_dim 64, rows of >= 128 frames)");
+  CSM_REQUIRE(workspace && workspace_bytes >= (size_t)batch * heads * seq * sizeof(float), CSM_ERR_SHAPE,
+              "attn_varlen_bwd: workspace too small");
+  return attn_bwd_tc_launch(q, k, v, o, lse, dout, dq, dk, dv, reinterpret_cast<float*>(workspace), batch, seq, heads,
+                            kv_heads, ldq, ldk, ldv, ldo, lddq, lddk, lddv, scale, rope_cache, seg_start, seg_end,
+                            as_stream(stream));
 }
 
 extern "C" size_t csm_attn_bwd_workspace_bytes(int32_t batch, int32_t seq, int32_t heads, int32_t kv_heads,
@@ -311,7 +345,7 @@ extern "C" int csm_attn_causal_gqa_bwd(const void* q, const void* k, const void*
   const int be = g_attn_backend.load();
   if ((be == 0 || be == 3) && attn_tc_supported(seq, head_dim, ldq, ldk, ldv, ldo, q, k, v, o))
     return attn_bwd_tc_launch(q, k, v, o, lse, dout, dq, dk, dv, delta, batch, seq, heads, kv_heads, ldq, ldk, ldv, ldo,
-                              lddq, lddk, lddv, scale, nullptr, as_stream(stream));
+                              lddq, lddk, lddv, scale, nullptr, nullptr, nullptr, as_stream(stream));
   if ((be == 0 || be == 4) && attn_small_supported(seq, heads, kv_heads, head_dim, ldq, ldk, ldv, ldo, q, k, v, o))
     return attn_bwd_small_launch(q, k, v, o, lse, dout, dq, dk, dv, batch, seq, heads, kv_heads, head_dim, ldq, ldk,
                                  ldv, ldo, lddq, lddk, lddv, scale, as_stream(stream));

@@ -44,10 +44,16 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
+// kVarlen (sequence packing): several samples share one row of S frames; seg_start[b, i] is the
+// first position of the sample that position i belongs to (padding: i itself), so query i sees keys
+// seg_start[b, i] <= j <= i.  A query tile then starts at the key block that holds the first row's segment start
+// instead of block 0 — packed short samples cost what they would cost alone — and the blocks that straddle a
+// segment start are masked like the diagonal ones.
+template <bool kVarlen>
 __global__ void __launch_bounds__(kAttnThreads, 2)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                    const __grid_constant__ CUtensorMap tmV, bf16* __restrict__ o, float* __restrict__ lse, int S,
-                   int H, int KV, int64_t ldo, float scale_log2) {
+                   int H, int KV, int64_t ldo, float scale_log2, const int32_t* __restrict__ seg_start) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SM_BAR);
@@ -70,7 +76,9 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   const int h = hb % H, b = hb / H;
   const int kvh = h / (H / KV);
   const int q0 = qb * TQ;
-  const int nblk = min(2 * (qb + 1), (S + FK - 1) / FK);   // 64-key blocks up to the diagonal
+  const int blk_end = min(2 * (qb + 1), (S + FK - 1) / FK);   // 64-key blocks up to the diagonal
+  const int blk0 = kVarlen ? seg_start[(int64_t)b * S + q0] / FK : 0;   // first block any row of the tile can see
+  const int nblk = blk_end - blk0;                            // blocks are walked as jj = 0..nblk-1, key block blk0 + jj
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmQ);
@@ -107,8 +115,8 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       mbar_wait(&kv_empty[ks], ((j / FST) & 1) ^ 1);
       if (elect_one()) {
         mbar_expect_tx(&kv_full[ks], 2 * FK * THD * 2);
-        tma_load_3d(smem + SM_K + ks * (FK * THD * 2), &tmK, &kv_full[ks], kvh * THD, j * FK, b);
-        tma_load_3d(smem + SM_V + ks * (FK * THD * 2), &tmV, &kv_full[ks], kvh * THD, j * FK, b);
+        tma_load_3d(smem + SM_K + ks * (FK * THD * 2), &tmK, &kv_full[ks], kvh * THD, (blk0 + j) * FK, b);
+        tma_load_3d(smem + SM_V + ks * (FK * THD * 2), &tmV, &kv_full[ks], kvh * THD, (blk0 + j) * FK, b);
       }
       __syncwarp();
     }
@@ -164,6 +172,9 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     const int r = quad * 32 + lane;           // row inside the tile == TMEM lane
     const int qi = q0 + r;                    // query index inside the sequence
     const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16);
+    // packing: this row's first visible key and the latest segment start inside the tile (blocks below it need masks)
+    const int lo = kVarlen ? seg_start[(int64_t)b * S + min(qi, S - 1)] : 0;
+    const int lo_max = kVarlen ? seg_start[(int64_t)b * S + min(q0 + TQ - 1, S - 1)] : 0;
     float m = -INFINITY, l = 0.f, corr_prev = 1.f;
     float oacc[THD];
 #pragma unroll
@@ -186,7 +197,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     auto block = [&](int j, auto diag_tag) {
       constexpr bool DIAG = decltype(diag_tag)::value;
       const int st = j & 1;
-      const int kbase = j * FK;
+      const int kbase = (blk0 + j) * FK;
       mbar_wait(&s_full[st], (j >> 1) & 1);
       tc_fence_after();
       const uint32_t s_addr = lane_addr + COL_S + st * FK;
@@ -199,20 +210,24 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
       for (int i = 0; i < FK; ++i) {
-        if (DIAG && (kbase + i > qi)) v[i] = 0xff800000u;   // -inf
+        if (DIAG && ((kbase + i > qi) || (kVarlen && kbase + i < lo))) v[i] = 0xff800000u;   // -inf
         m4[i & 3] = fmaxf(m4[i & 3], __uint_as_float(v[i]));
       }
       const float mr = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));   // scale > 0: scaling commutes with max
-      const float mx = fmaxf(m, mr * scale_log2);
-      const float corr = ex2(m - mx);
+      float mx = fmaxf(m, mr * scale_log2);
+      // packing: a row whose segment starts later has seen no key yet (max still -inf): exponentials against 0 instead
+      // (exp2(-inf - 0) = 0 for the masked scores and for the correction of the still-empty accumulator)
+      const float mref = (kVarlen && DIAG && mx == -INFINITY) ? 0.f : mx;
+      const float corr = ex2(m - mref);
       m = mx;
+      mx = mref;
       float rs4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
       for (int c = 0; c < FK; c += 32) {
         float p[32];
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
-          p[i] = ex2(fmaf(__uint_as_float(v[c + i]), scale_log2, -m));   // exp2(-inf) = 0 for masked keys
+          p[i] = ex2(fmaf(__uint_as_float(v[c + i]), scale_log2, -mx));   // exp2(-inf) = 0 for masked keys
           rs4[i & 3] += p[i];
         }
         uint32_t pw[16];                      // bf16 pairs (key, key+1): the A operand of the PV MMA, kept in TMEM
@@ -228,10 +243,18 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       if (j > 0) fold(j - 1, corr_prev);
       corr_prev = corr;
     };
-    // blocks that reach past the first query row of the tile (kbase + 63 > q0) need the causal mask: the last two
-    const int nfull = min(nblk, q0 / FK);
-    for (int j = 0; j < nfull; ++j) block(j, std::false_type{});
-    for (int j = nfull; j < nblk; ++j) block(j, std::true_type{});
+    // blocks that reach past the first query row of the tile (kbase + 63 > q0) need the causal mask: the last two;
+    // packing: so do the blocks that start below the latest segment start of the tile
+    if (!kVarlen) {
+      const int nfull = min(nblk, q0 / FK);
+      for (int j = 0; j < nfull; ++j) block(j, std::false_type{});
+      for (int j = nfull; j < nblk; ++j) block(j, std::true_type{});
+    } else {
+      for (int j = 0; j < nblk; ++j) {
+        const int kb = (blk0 + j) * FK;
+        if (kb < lo_max || kb + FK - 1 > q0) block(j, std::true_type{}); else block(j, std::false_type{});
+      }
+    }
     fold(nblk - 1, corr_prev);
     if (qi < S) {
       const float inv = 1.f / l;
@@ -304,11 +327,13 @@ constexpr int DQ_V = DQ_K + KST * TK * THD * 2;      // KST x 16 KB
 constexpr int DQ_BAR = DQ_V + KST * TK * THD * 2;    // (dS goes back into TMEM, not through smem)
 constexpr int kDqSmem = DQ_BAR + 256 + 1024;
 
+template <bool kVarlen>
 __global__ void __launch_bounds__(kBwdThreads, 1)
 attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                       const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmDO,
                       const float* __restrict__ lse, const float* __restrict__ delta, bf16* __restrict__ dq, int S,
-                      int H, int KV, int64_t lddq, float scale, const float* __restrict__ rope_cache) {
+                      int H, int KV, int64_t lddq, float scale, const float* __restrict__ rope_cache,
+                      const int32_t* __restrict__ seg_start) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + DQ_BAR);
@@ -330,7 +355,9 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
   const int h = hb % H, b = hb / H;
   const int kvh = h / (H / KV);
   const int q0 = qb * TQ;
-  const int nblk = qb + 1;
+  // packing: the first 128-key tile any row of this query tile can see (see attn_fwd_tc_kernel)
+  const int jt0 = kVarlen ? seg_start[(int64_t)b * S + q0] / TK : 0;
+  const int nblk = qb + 1 - jt0;
   const int nsub = 2 * nblk;
 
   if (warp == 0 && lane == 0) {
@@ -363,8 +390,8 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       mbar_wait(&kv_empty[st], ((j / KST) & 1) ^ 1);
       if (elect_one()) {
         mbar_expect_tx(&kv_full[st], 2 * TK * THD * 2);
-        tma_load_3d(smem + DQ_K + st * (TK * THD * 2), &tmK, &kv_full[st], kvh * THD, j * TK, b);
-        tma_load_3d(smem + DQ_V + st * (TK * THD * 2), &tmV, &kv_full[st], kvh * THD, j * TK, b);
+        tma_load_3d(smem + DQ_K + st * (TK * THD * 2), &tmK, &kv_full[st], kvh * THD, (jt0 + j) * TK, b);
+        tma_load_3d(smem + DQ_V + st * (TK * THD * 2), &tmV, &kv_full[st], kvh * THD, (jt0 + j) * TK, b);
       }
       __syncwarp();
     }
@@ -411,10 +438,12 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     const int64_t li = ((int64_t)b * H + h) * S + qi;
     const float L2 = (qi < S) ? lse[li] * kLog2e : INFINITY;   // +inf => P = 0 for rows past the sequence end
     const float Dls = (qi < S) ? delta[li] * scale : 0.f;
+    const int lo = kVarlen ? seg_start[(int64_t)b * S + min(qi, S - 1)] : 0;
+    const int lo_max = kVarlen ? seg_start[(int64_t)b * S + min(q0 + TQ - 1, S - 1)] : 0;
     auto sub = [&](int u, auto diag_tag) {
       constexpr bool DIAG = decltype(diag_tag)::value;
       const int bb = u % NB;
-      const int kbase = (u >> 1) * TK + (u & 1) * SUB + half * 32;
+      const int kbase = (jt0 + (u >> 1)) * TK + (u & 1) * SUB + half * 32;
       mbar_wait(&sdp_full[bb], (u / NB) & 1);
       tc_fence_after();
       uint32_t sv_[32], dv_[32];
@@ -426,7 +455,7 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
 #pragma unroll
       for (int i = 0; i < 32; ++i) {
         float x = fmaf(__uint_as_float(sv_[i]), scale_log2, -L2);
-        if (DIAG && (kbase + i > qi)) x = -INFINITY;
+        if (DIAG && ((kbase + i > qi) || (kVarlen && kbase + i < lo))) x = -INFINITY;
         f[i] = ex2(x) * fmaf(__uint_as_float(dv_[i]), scale, -Dls);     // P * (dP - delta) * scale
       }
       // dS as bf16 pairs (key, key+1) over the first 16 of this warp's own 32 dP columns: the A operand of dQ += dS K
@@ -439,7 +468,10 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       __syncwarp();
       if (lane == 0) mbar_arrive(&ds_full[bb]);
     };
-    for (int u = 0; u < nsub - 2; ++u) sub(u, std::false_type{});
+    for (int u = 0; u < nsub - 2; ++u) {
+      if (kVarlen && (jt0 + (u >> 1)) * TK + (u & 1) * SUB < lo_max) sub(u, std::true_type{});
+      else sub(u, std::false_type{});
+    }
     sub(nsub - 2, std::true_type{});
     sub(nsub - 1, std::true_type{});
     mbar_wait(acc_full, 0);
@@ -459,7 +491,8 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
           w[2] = pack_bf16(__uint_as_float(v[c + 4]), __uint_as_float(v[c + 5]));
           w[3] = pack_bf16(__uint_as_float(v[c + 6]), __uint_as_float(v[c + 7]));
           // gradient w.r.t. the un-rotated q: the inverse rotation of the (bf16) gradient, as csm_rope(inverse) would do
-          if (rope_cache) rope_rotate8(w, rope_cache + (int64_t)qi * THD, (half * 32 + c) >> 1, -1.f);
+          // (packing: positions restart at every segment)
+          if (rope_cache) rope_rotate8(w, rope_cache + (int64_t)(qi - lo) * THD, (half * 32 + c) >> 1, -1.f);
           *reinterpret_cast<uint4*>(dp_ + c) = make_uint4(w[0], w[1], w[2], w[3]);
         }
       }
@@ -482,12 +515,16 @@ constexpr int DK_LD = DK_DO + KST * TQ * THD * 2;    // 2 x (128 lse*log2e + 128
 constexpr int DK_BAR = DK_LD + 2 * 256 * 4;
 constexpr int kDkSmem = DK_BAR + 256 + 1024;
 
+// kVarlen: key j is seen by queries j <= i < seg_end[b, j] (the end of j's sample), so a key tile walks the query tiles
+// only up to the end of its last key's segment and masks the sub-blocks that reach past its first key's segment end.
+template <bool kVarlen>
 __global__ void __launch_bounds__(kBwdThreads, 1)
 attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                         const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmDO,
                         const float* __restrict__ lse, const float* __restrict__ delta, bf16* __restrict__ dk,
                         bf16* __restrict__ dv, int S, int H, int KV, int64_t lddk, int64_t lddv, float scale,
-                        const float* __restrict__ rope_cache) {
+                        const float* __restrict__ rope_cache, const int32_t* __restrict__ seg_start,
+                        const int32_t* __restrict__ seg_end) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + DK_BAR);
@@ -508,7 +545,8 @@ attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
   const int kvh = ((int)blockIdx.x % per_k) % KV, b = ((int)blockIdx.x % per_k) / KV;
   const int rep = H / KV;
   const int k0 = kvb * TK;
-  const int nqb = (S + TQ - 1) / TQ;
+  // packing: query tiles end with the segment of the tile's last key
+  const int nqb = kVarlen ? (seg_end[(int64_t)b * S + min(k0 + TK - 1, S - 1)] + TQ - 1) / TQ : (S + TQ - 1) / TQ;
   const int nq_iter = nqb - kvb;
   const int total = rep * nq_iter;      // 128-query tiles
   const int nsub = 2 * total;
@@ -600,6 +638,8 @@ attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
     // per CTA; the global load for tile it+1 is issued one tile early so its latency hides behind tile it's math
     // (raw value only: scaling it here would make the thread wait for the load right away)
     const float ld_mul = ctid < 128 ? kLog2e : scale;
+    const int hi = kVarlen ? seg_end[(int64_t)b * S + min(kj, S - 1)] : S;              // this key's last query + 1
+    const int hi_min = kVarlen ? seg_end[(int64_t)b * S + min(k0, S - 1)] : S;          // earliest segment end of the tile
     auto load_ld = [&](int it) -> float {
       const int h = kvh * rep + it / nq_iter, qb = kvb + it % nq_iter;
       const int q = qb * TQ + (ctid & 127);
@@ -638,7 +678,7 @@ attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
         for (int t = 0; t < 4; ++t) {
           const int i = i4 * 4 + t;
           float x = fmaf(__uint_as_float(sv_[i]), scale_log2, -Ls[t]);
-          if (DIAG && (kj > qbase + i)) x = -INFINITY;
+          if (DIAG && ((kj > qbase + i) || (kVarlen && qbase + i >= hi))) x = -INFINITY;
           const float pv = ex2(x);
           pf[i] = pv;
           df[i] = pv * fmaf(__uint_as_float(dv_[i]), scale, -Ds[t]);
@@ -659,7 +699,9 @@ attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
       if (lane == 0) mbar_arrive(&pt_full[bb]);
     };
     for (int u = 0; u < nsub; ++u) {
-      if ((u >> 1) % nq_iter == 0) sub(u, std::true_type{}); else sub(u, std::false_type{});
+      const int qt = (u >> 1) % nq_iter;
+      if (qt == 0 || (kVarlen && (kvb + qt) * TQ + (u & 1) * SUB + SUB > hi_min)) sub(u, std::true_type{});
+      else sub(u, std::false_type{});
     }
     mbar_wait(acc_full, 0);
     tc_fence_after();
@@ -681,7 +723,9 @@ attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
           w[1] = pack_bf16(__uint_as_float(v[c8 + 2]), __uint_as_float(v[c8 + 3]));
           w[2] = pack_bf16(__uint_as_float(v[c8 + 4]), __uint_as_float(v[c8 + 5]));
           w[3] = pack_bf16(__uint_as_float(v[c8 + 6]), __uint_as_float(v[c8 + 7]));
-          if (rope_cache && half == 0) rope_rotate8(w, rope_cache + (int64_t)kj * THD, (c + c8) >> 1, -1.f);   // dK only
+          if (rope_cache && half == 0)                                                               // dK only
+            rope_rotate8(w, rope_cache + (int64_t)(kj - (kVarlen ? seg_start[(int64_t)b * S + kj] : 0)) * THD,
+                         (c + c8) >> 1, -1.f);
           *reinterpret_cast<uint4*>(outp + c + c8) = make_uint4(w[0], w[1], w[2], w[3]);
         }
       }
@@ -704,7 +748,8 @@ bool attn_tc_supported(int S, int hd, int64_t ldq, int64_t ldk, int64_t ldv, int
 }
 
 int attn_fwd_tc_launch(const void* q, const void* k, const void* v, void* o, float* lse, int B, int S, int H, int KV,
-                       int64_t ldq, int64_t ldk, int64_t ldv, int64_t ldo, float scale, cudaStream_t st) {
+                       int64_t ldq, int64_t ldk, int64_t ldv, int64_t ldo, float scale, const int32_t* seg_start,
+                       cudaStream_t st) {
   CUtensorMap tq, tk, tv;
   int rc;
   if ((rc = encode_tmap_bf16(&tq, q, (uint64_t)H * THD, S, B, ldq, (uint64_t)S * ldq, TQ))) return rc;
@@ -712,12 +757,19 @@ int attn_fwd_tc_launch(const void* q, const void* k, const void* v, void* o, flo
   if ((rc = encode_tmap_bf16(&tv, v, (uint64_t)KV * THD, S, B, ldv, (uint64_t)S * ldv, FK))) return rc;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(attn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem);
+    cudaError_t e = cudaFuncSetAttribute(attn_fwd_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(attn_fwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem);
     if (e != cudaSuccess) { set_error("attn_fwd_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return CSM_ERR_CUDA; }
     configured = true;
   }
   dim3 grid(((S + TQ - 1) / TQ) * H * B);
-  attn_fwd_tc_kernel<<<grid, kAttnThreads, kAttnSmem, st>>>(tq, tk, tv, (bf16*)o, lse, S, H, KV, ldo, scale * kLog2e);
+  if (seg_start)
+    attn_fwd_tc_kernel<true><<<grid, kAttnThreads, kAttnSmem, st>>>(tq, tk, tv, (bf16*)o, lse, S, H, KV, ldo,
+                                                                    scale * kLog2e, seg_start);
+  else
+    attn_fwd_tc_kernel<false><<<grid, kAttnThreads, kAttnSmem, st>>>(tq, tk, tv, (bf16*)o, lse, S, H, KV, ldo,
+                                                                     scale * kLog2e, nullptr);
   CSM_CHECK_LAUNCH("attn_fwd_tc");
   return CSM_OK;
 }
@@ -728,7 +780,7 @@ int attn_delta_launch(const void* o, const void* dout, float* delta, int B, int 
 int attn_bwd_tc_launch(const void* q, const void* k, const void* v, const void* o, const float* lse, const void* dout,
                        void* dq, void* dk, void* dv, float* delta, int B, int S, int H, int KV, int64_t ldq, int64_t ldk,
                        int64_t ldv, int64_t ldo, int64_t lddq, int64_t lddk, int64_t lddv, float scale,
-                       const float* rope_cache, cudaStream_t st) {
+                       const float* rope_cache, const int32_t* seg_start, const int32_t* seg_end, cudaStream_t st) {
   CSM_REQUIRE(aligned16(dout) && aligned16(dq) && aligned16(dk) && aligned16(dv) && lddq % 8 == 0 && lddk % 8 == 0 &&
                   lddv % 8 == 0,
               CSM_ERR_ALIGN, "attn_bwd_tc: misaligned gradient buffers");
@@ -741,19 +793,34 @@ int attn_bwd_tc_launch(const void* q, const void* k, const void* v, const void* 
   if ((rc = encode_tmap_bf16(&tdo, dout, (uint64_t)H * THD, S, B, ldo, (uint64_t)S * ldo, TQ))) return rc;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(attn_bwd_dq_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDqSmem);
+    cudaError_t e = cudaFuncSetAttribute(attn_bwd_dq_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDqSmem);
     if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(attn_bwd_dkdv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDkSmem);
+      e = cudaFuncSetAttribute(attn_bwd_dq_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDqSmem);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(attn_bwd_dkdv_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDkSmem);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(attn_bwd_dkdv_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDkSmem);
     if (e != cudaSuccess) { set_error("attn_bwd_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return CSM_ERR_CUDA; }
     configured = true;
   }
   dim3 gq(((S + TQ - 1) / TQ) * H * B);
-  attn_bwd_dq_tc_kernel<<<gq, kBwdThreads, kDqSmem, st>>>(tq, tk, tv, tdo, lse, delta, (bf16*)dq, S, H, KV, lddq, scale,
-                                                          rope_cache);
+  const bool varlen = seg_start != nullptr && seg_end != nullptr;
+  if (varlen)
+    attn_bwd_dq_tc_kernel<true><<<gq, kBwdThreads, kDqSmem, st>>>(tq, tk, tv, tdo, lse, delta, (bf16*)dq, S, H, KV, lddq,
+                                                                  scale, rope_cache, seg_start);
+  else
+    attn_bwd_dq_tc_kernel<false><<<gq, kBwdThreads, kDqSmem, st>>>(tq, tk, tv, tdo, lse, delta, (bf16*)dq, S, H, KV, lddq,
+                                                                   scale, rope_cache, nullptr);
   CSM_CHECK_LAUNCH("attn_bwd_dq_tc");
   dim3 gk(((S + TK - 1) / TK) * KV * B);
-  attn_bwd_dkdv_tc_kernel<<<gk, kBwdThreads, kDkSmem, st>>>(tq, tk, tv, tdo, lse, delta, (bf16*)dk, (bf16*)dv, S, H, KV,
-                                                            lddk, lddv, scale, rope_cache);
+  if (varlen)
+    attn_bwd_dkdv_tc_kernel<true><<<gk, kBwdThreads, kDkSmem, st>>>(tq, tk, tv, tdo, lse, delta, (bf16*)dk, (bf16*)dv, S,
+                                                                    H, KV, lddk, lddv, scale, rope_cache, seg_start,
+                                                                    seg_end);
+  else
+    attn_bwd_dkdv_tc_kernel<false><<<gk, kBwdThreads, kDkSmem, st>>>(tq, tk, tv, tdo, lse, delta, (bf16*)dk, (bf16*)dv, S,
+                                                                     H, KV, lddk, lddv, scale, rope_cache, nullptr,
+                                                                     nullptr);
   CSM_CHECK_LAUNCH("attn_bwd_dkdv_tc");
   return CSM_OK;
 }

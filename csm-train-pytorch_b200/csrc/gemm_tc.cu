@@ -52,6 +52,7 @@ struct GemmTcParams {
   // RoPE in the store epilogue (fused q|k|v projection): columns [0, rope_cols) are heads of rope_hd that get rotated
   // by the position row % rope_seq; the linear output is rounded to bf16 first, as the unfused rope kernel would read it
   const float* rope_cache; int rope_seq, rope_cols, rope_hd;
+  const int32_t* rope_pos;  // optional [M]: position of every row (sequence packing: positions restart per sample)
   int streamk;
   // off by default (no gain measured): issue the MMAs of a ragged last column tile with N rounded up to 16 instead of BN
   int narrow_tail;
@@ -502,7 +503,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               w[q * 4 + 0] = pack_bf16(f8[0], f8[1]); w[q * 4 + 1] = pack_bf16(f8[2], f8[3]);
               w[q * 4 + 2] = pack_bf16(f8[4], f8[5]); w[q * 4 + 3] = pack_bf16(f8[6], f8[7]);
               if (p.rope_cache && n + q * 8 < p.rope_cols && row_ok)
-                rope_rotate8(w + q * 4, p.rope_cache + (int64_t)(m % p.rope_seq) * p.rope_hd,
+                rope_rotate8(w + q * 4, p.rope_cache + (int64_t)(p.rope_pos ? p.rope_pos[m] : m % p.rope_seq) * p.rope_hd,
                              (int)((n + q * 8) % p.rope_hd) >> 1, 1.f);
             }
             store_tile_32x32(stage_s, reinterpret_cast<bf16*>(p.C) + (int64_t)g * p.c_group_stride + wm0 * p.ldc + n,
@@ -1045,7 +1046,7 @@ int gemm_tc_launch_rope(const void* A, const void* B, void* C, const void* R, in
                         int64_t lda, int64_t ldb, int64_t ldc, int64_t ldr, int transA, int transB, int c_dtype,
                         int accumulate, float alpha, const void* A2, const void* B2, int64_t K2, int64_t lda2,
                         int64_t ldb2, const float* rope_cache, int rope_seq, int rope_cols, int rope_hd,
-                        cudaStream_t stream) {
+                        const int32_t* rope_pos, cudaStream_t stream) {
   GemmTcOperands o{A, B, A2, B2, lda, ldb, lda2, ldb2, K2, 0, 0, transA, transB};
   GemmTcParams p{};
   p.M = M; p.N = N; p.K = K; p.groups = 1;
@@ -1053,6 +1054,7 @@ int gemm_tc_launch_rope(const void* A, const void* B, void* C, const void* R, in
   p.c_f32 = (c_dtype & CSM_DT_F32) != 0; p.r_f32 = (c_dtype & CSM_DT_RES_F32) != 0;
   p.accumulate = accumulate; p.alpha = alpha;
   p.rope_cache = rope_cache; p.rope_seq = rope_seq; p.rope_cols = rope_cols; p.rope_hd = rope_hd;
+  p.rope_pos = rope_pos;
   return gemm_tc_run(o, p, EPI_STORE, stream);
 }
 
@@ -1061,7 +1063,7 @@ int gemm_tc_launch(const void* A, const void* B, void* C, const void* R, int64_t
                    int accumulate, float alpha, const void* A2, const void* B2, int64_t K2, int64_t lda2,
                    int64_t ldb2, cudaStream_t stream) {
   return gemm_tc_launch_rope(A, B, C, R, M, N, K, lda, ldb, ldc, ldr, transA, transB, c_dtype, accumulate, alpha, A2, B2,
-                             K2, lda2, ldb2, nullptr, 0, 0, 0, stream);
+                             K2, lda2, ldb2, nullptr, 0, 0, 0, nullptr, stream);
 }
 
 // ------------------------------------------------------------------------------------------- fused SwiGLU MLP

@@ -247,7 +247,7 @@ rmsnorm_bwd_warp_kernel(const bf16* __restrict__ dy, const void* __restrict__ x,
 // one thread per 8 bf16 (= 4 rotation pairs)
 __global__ void __launch_bounds__(256)
 rope_kernel(bf16* __restrict__ x, const float* __restrict__ cache, int64_t rows, int seq_len, int heads,
-            int hd, int64_t ldx, float sgn) {
+            int hd, int64_t ldx, float sgn, const int32_t* __restrict__ pos_of_row) {
   const int vec_per_head = hd / 8;
   const int64_t total = rows * heads * vec_per_head;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
@@ -256,7 +256,7 @@ rope_kernel(bf16* __restrict__ x, const float* __restrict__ cache, int64_t rows,
     const int64_t t = i / vec_per_head;
     const int hh = (int)(t % heads);
     const int64_t r = t / heads;
-    const int pos = (int)(r % seq_len);
+    const int pos = pos_of_row ? pos_of_row[r] : (int)(r % seq_len);
     bf16* p = x + r * ldx + (int64_t)hh * hd + vv * 8;
     float f[8];
     unpack8(*reinterpret_cast<const uint4*>(p), f);
@@ -424,14 +424,14 @@ extern "C" int csm_rmsnorm_bwd(const void* dy, const void* x, const void* scale,
 }
 
 extern "C" int csm_rope(void* x, const float* cache, int64_t rows, int32_t seq_len, int32_t heads,
-                        int32_t head_dim, int64_t ldx, int32_t inverse, csm_stream_t stream) {
+                        int32_t head_dim, int64_t ldx, int32_t inverse, const int32_t* positions, csm_stream_t stream) {
   CSM_REQUIRE(rows >= 0 && seq_len > 0 && heads > 0 && head_dim > 0 && head_dim % 8 == 0 && ldx % 8 == 0,
               CSM_ERR_SHAPE, "rope: head_dim=%d and ldx=%lld must be multiples of 8", head_dim, (long long)ldx);
   CSM_REQUIRE(aligned16(x) && aligned16(cache), CSM_ERR_ALIGN, "rope: misaligned pointer");
   if (rows == 0) return CSM_OK;
   const int64_t total = rows * heads * (head_dim / 8);
   rope_kernel<<<grid_for(total, 256), 256, 0, as_stream(stream)>>>((bf16*)x, cache, rows, seq_len, heads,
-                                                                   head_dim, ldx, inverse ? -1.f : 1.f);
+                                                                   head_dim, ldx, inverse ? -1.f : 1.f, positions);
   CSM_CHECK_LAUNCH("rope");
   return CSM_OK;
 }

@@ -89,10 +89,11 @@ int csm_rmsnorm_bwd(const void* dy, const void* x, const void* scale, const floa
                     void* dx, float* dscale_f32, int64_t rows, int32_t dim, int32_t x_dtype, csm_stream_t stream);
 
 /* ---- torchtune Llama3ScaledRoPE, interleaved pairs, fp32 math (restated in oracle/torchtune_shim.py)
- * in place on x[rows, heads, head_dim] with row stride ldx; position = row % seq_len;
+ * in place on x[rows, heads, head_dim] with row stride ldx; position = positions[row] when `positions` (int32 [rows],
+ * nullable; sequence packing: positions restart with every packed sample) is given, else row % seq_len;
  * cache fp32 [max_seq, head_dim/2, 2] = (cos, sin). inverse != 0 applies the transpose rotation (backward). */
 int csm_rope(void* x, const float* cache, int64_t rows, int32_t seq_len, int32_t heads, int32_t head_dim,
-             int64_t ldx, int32_t inverse, csm_stream_t stream);
+             int64_t ldx, int32_t inverse, const int32_t* positions, csm_stream_t stream);
 
 /* ---- F.linear / torch.mm / their autograd (model.py:124-126,187; every torchtune projection)
  * C[M,N] (=|+=) alpha * op(A)[M,K] * op(B)[K,N] (+ A2[M,K2] * B2[N,K2]^T) (+ R[M,N])
@@ -136,7 +137,7 @@ int csm_adamw_clip_step_v2(void* const* params, const void* const* grads, void* 
 int csm_gemm_bf16_rope(const void* A, const void* B, void* C, int64_t M, int64_t N, int64_t K, int64_t lda, int64_t ldb,
                        int64_t ldc, const void* A2, const void* B2, int64_t K2, int64_t lda2, int64_t ldb2,
                        const float* rope_cache, int32_t seq_len, int32_t rope_cols, int32_t head_dim,
-                       csm_stream_t stream);
+                       const int32_t* positions /* nullable int32 [M]: see csm_rope */, csm_stream_t stream);
 
 /* ---- skinny GEMM with a long reduction (LoRA t = x A^T, dA = dt^T x, dB = dy^T t): same operand conventions as
  * csm_gemm_bf16 (no residual / tail / accumulate), C bf16 = alpha * op(A) op(B).  The reduction is split into `splits`
@@ -241,6 +242,22 @@ int csm_linear_ce_bwd(const void* H, const void* W, const int64_t* targets, cons
                       int32_t transW, int64_t tgt_row_stride, int64_t tgt_group_stride, int64_t lddh,
                       int64_t dh_group_stride, void* workspace, size_t workspace_bytes, int32_t backend,
                       csm_stream_t stream);
+
+/* ---- sequence packing (the reference pads every sample to the batch maximum,
+ * training_data.py:379-408): several samples share one row of `seq` frames and attention is block-diagonal causal.
+ * seg_start / seg_end: int32 [batch, seq], first position and last position + 1 of the sample that position i of row b
+ * belongs to (a padding frame: i and i + 1): query i sees keys seg_start[b,i] <= j <= i.  Same operand layout as
+ * csm_attn_causal_gqa_fwd / _bwd_rope; tcgen05 kernels only (head_dim 64, seq >= 128) — CSM_ERR_SHAPE otherwise.  A query
+ * tile starts at the key block of its first row's segment start, so packed short samples cost what they cost alone.
+ * With rope_cache (nullable) dq / dk come back un-rotated, positions counted from each sample's start. */
+int csm_attn_varlen_fwd(const void* q, const void* k, const void* v, void* o, float* lse, int32_t batch, int32_t seq,
+                        int32_t heads, int32_t kv_heads, int32_t head_dim, int64_t ldq, int64_t ldk, int64_t ldv,
+                        int64_t ldo, float scale, const int32_t* seg_start, csm_stream_t stream);
+int csm_attn_varlen_bwd(const void* q, const void* k, const void* v, const void* o, const float* lse, const void* dout,
+                        void* dq, void* dk, void* dv, int32_t batch, int32_t seq, int32_t heads, int32_t kv_heads,
+                        int32_t head_dim, int64_t ldq, int64_t ldk, int64_t ldv, int64_t ldo, int64_t lddq, int64_t lddk,
+                        int64_t lddv, float scale, const float* rope_cache, const int32_t* seg_start,
+                        const int32_t* seg_end, void* workspace, size_t workspace_bytes, csm_stream_t stream);
 
 /* ---- KV-cache decode attention of Model.generate_frame (model.py:140-195; torchtune attention with kv_cache): one new
  * query position per sample, q [batch, heads*head_dim] (row stride ldq), against the first kv_len cached positions of

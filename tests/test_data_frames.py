@@ -73,3 +73,38 @@ def test_length_bucketing_cuts_padding_and_covers_every_sample():
     assert all(1 <= len(b) <= 8 for b in bucketed)
     assert F.padding_fraction(lengths, bucketed) < 0.5 * F.padding_fraction(lengths, naive)
     assert bucketed != F.length_bucketed_order(lengths, 8, seed=2)                   # the epoch order stays random
+
+
+def test_pack_samples_layout_segments_targets_and_frames():
+    """Sequence packing host logic: first-fit-decreasing rows, per-position segment tables, targets aligned with their
+    sample's positions, the semantic mask (p < min(len - 1, target rows)), per-sample decoder frames."""
+    import math
+    import torch
+    from csm.data import frames as F
+    lens, tlens = [100, 156, 60, 250, 30], [100, 120, 60, 250, 10]
+    samples = [{"input_tokens": torch.full((n, 33), i + 1), "input_masks": torch.ones(n, 33, dtype=torch.bool),
+                "target_audio_tokens": torch.full((t, 32), 10 * (i + 1))} for i, (n, t) in enumerate(zip(lens, tlens))]
+    b = F.pack_samples(samples, 256, pad_to_multiple=128, generator=torch.Generator().manual_seed(0), pin=False)
+    R, S = b["input_tokens"].shape[:2]
+    assert S == 256 and R == 3 and b["segment_starts"].dtype == torch.int32
+    own, ss, se = b["sample_index"], b["segment_starts"], b["segment_ends"]
+    for j, (n, t) in enumerate(zip(lens, tlens)):
+        where = torch.nonzero(own == j)
+        assert where.shape[0] == n and len(set(where[:, 0].tolist())) == 1          # one contiguous run in one row
+        r, p0 = int(where[0, 0]), int(where[0, 1])
+        assert where[:, 1].tolist() == list(range(p0, p0 + n))
+        assert (ss[r, p0:p0 + n] == p0).all() and (se[r, p0:p0 + n] == p0 + n).all()
+        assert (b["input_tokens"][r, p0:p0 + n] == j + 1).all() and b["input_masks"][r, p0:p0 + n].all()
+        tt = min(n, t)
+        assert (b["target_audio_tokens"][r, p0:p0 + tt] == 10 * (j + 1)).all()
+        valid = min(n - 1, tt)
+        assert b["target_mask"][r, p0:p0 + valid].all() and not b["target_mask"][r, p0 + valid:p0 + n].any()
+        mine = b["frame_idx"][(own[b["frame_idx"][:, 0], b["frame_idx"][:, 1]] == j)]
+        assert mine.shape[0] == max(1, math.ceil(valid / 16)) and (mine[:, 1] < p0 + valid).all()
+    pad = own < 0
+    assert (ss[pad] == torch.arange(S).repeat(R, 1)[pad]).all() and (se[pad] == ss[pad] + 1).all()
+    assert not b["input_masks"][pad].any() and not b["target_mask"][pad].any()
+    assert abs(F.packing_efficiency(b) - sum(lens) / (R * S)) < 1e-6
+    import pytest
+    with pytest.raises(ValueError):
+        F.pack_samples(samples, 200, pin=False)

@@ -348,6 +348,69 @@ def test_generate_frame_with_kv_cache_matches_oracle(cuda, cfg_name, S, steps):
         prod.generate_frame(tok.to(cuda), msk.to(cuda), torch.arange(S, device=cuda).unsqueeze(0).repeat(B, 1), 0.9, 1)
 
 
+def test_sequence_packing_equals_running_every_sample_alone(cuda):
+    """SURVEY §8(f) row 2: five variable-length samples packed into rows of 384 frames (csm/data/frames.py::
+    pack_samples; block-diagonal causal attention, per-sample RoPE positions) give the loss and the gradients of the
+    same five samples run ONE BY ONE without any padding — the semantics of the reference's compute_loss on each
+    sample (position p predicts target row p, last position excluded), which its zero-padding collate only blurs."""
+    from csm.data.frames import pack_samples, packing_efficiency
+    from csm.data.synthetic import synthetic_batch
+    from oracle import csm_oracle as O
+    orc, prod, cfg = _pair("small", cuda, lora=False)
+    lens = [130, 200, 384, 150, 97]
+    samples = []
+    for i, n in enumerate(lens):
+        b = synthetic_batch(cfg.text_vocab_size, cfg.audio_vocab_size, cfg.audio_num_codebooks, 1, n, seed=70 + i)
+        samples.append({"input_tokens": b["input_tokens"][0], "input_masks": b["input_masks"][0],
+                        "target_audio_tokens": b["target_audio_tokens"][0]})
+    packed = pack_samples(samples, 384, pad_to_multiple=128, generator=torch.Generator().manual_seed(1), pin=False)
+    R, S = packed["input_tokens"].shape[:2]
+    assert (R, S) == (3, 384) and packing_efficiency(packed) > 0.8
+    dev = {k: v.to(cuda) for k, v in packed.items()}
+    loss, det = prod(dev["input_tokens"], dev["input_masks"], dev["target_audio_tokens"], frame_idx=dev["frame_idx"],
+                     segment_starts=dev["segment_starts"], segment_ends=dev["segment_ends"],
+                     target_mask=dev["target_mask"])
+    loss.backward()
+    torch.cuda.synchronize()
+    g_packed = {n: p.grad.detach().float().clone() for n, p in prod.named_parameters() if p.grad is not None}
+    for p in prod.parameters():
+        p.grad = None
+    # the same samples alone (B = 1, their own length, no padding), weighted as the packed means weight them
+    n_sem = sum(n - 1 for n in lens)
+    owner, fi = packed["sample_index"], packed["frame_idx"]
+    n_ac = fi.shape[0]
+    sem_sum = ac_sum = 0.0
+    o_sem = 0.0
+    for j, smp in enumerate(samples):
+        rows = (owner[fi[:, 0], fi[:, 1]] == j)
+        r = int(torch.nonzero((owner == j).any(1))[0])
+        off = int(packed["segment_starts"][r][owner[r] == j][0])
+        mine = fi[rows]
+        fj = torch.stack([torch.zeros_like(mine[:, 1]), mine[:, 1] - off], dim=1)
+        tok, msk, tgt = (smp[k].unsqueeze(0) for k in ("input_tokens", "input_masks", "target_audio_tokens"))
+        lj, dj = prod(tok.to(cuda), msk.to(cuda), tgt.to(cuda), frame_idx=fj.to(cuda),
+                      semantic_weight=100.0 * (lens[j] - 1) / n_sem, acoustic_weight=1.0 * fj.shape[0] / n_ac)
+        lj.backward()                                   # gradients accumulate over the samples
+        sem_sum += float(dj["semantic_loss"]) * (lens[j] - 1)
+        ac_sum += float(dj["acoustic_loss"]) * fj.shape[0]
+        ol, od = O.oracle_forward(orc, tok, msk, tgt, fj)
+        o_sem += float(od["semantic_loss"]) * (lens[j] - 1)
+    torch.cuda.synchronize()
+    assert abs(float(det["semantic_loss"]) - sem_sum / n_sem) <= 2e-3 * sem_sum / n_sem
+    assert abs(float(det["acoustic_loss"]) - ac_sum / n_ac) <= 2e-3 * ac_sum / n_ac
+    assert abs(float(det["semantic_loss"]) - o_sem / n_sem) <= LOSS_RTOL * o_sem / n_sem          # and the oracle's
+    for n, p in prod.named_parameters():
+        if p.grad is None:
+            continue
+        c = float(F.cosine_similarity(g_packed[n].flatten(), p.grad.float().flatten(), dim=0))
+        assert c >= 0.999, (n, c)
+        assert abs(float(g_packed[n].norm()) - float(p.grad.float().norm())) <= 3e-2 * float(p.grad.float().norm()), n
+    # packed rows need their segment tables and their own frame_idx
+    with pytest.raises(RuntimeError):
+        prod(dev["input_tokens"], dev["input_masks"], dev["target_audio_tokens"], segment_starts=dev["segment_starts"],
+             segment_ends=dev["segment_ends"])
+
+
 def test_no_cpu_fallback():
     from csm.models.model import Model, ModelArgs
     m = Model(ModelArgs("tiny-backbone", "tiny-decoder", 1000, 200, 32)).to(torch.bfloat16)

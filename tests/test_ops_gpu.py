@@ -642,3 +642,79 @@ def test_lora_mask_rows_and_wide_multi_adapter_tail(ops, cuda):
     with pytest.raises(RuntimeError):
         ops.gemm(x, w, a2=torch.zeros(M, 264, dtype=BF, device=cuda), b2=torch.zeros(N, 264, dtype=BF, device=cuda),
                  backend=2)                                                   # K2 > 256: not a tcgen05 shape
+
+
+def _segments(S, cuts, device):
+    """seg_start / seg_end int32 [S] for samples cut at `cuts` (last one may end before S: the tail is padding, every
+    padding frame its own one-frame segment)."""
+    ss = torch.arange(S, dtype=torch.int32)
+    se = ss + 1
+    a = 0
+    for b in cuts:
+        ss[a:b] = a
+        se[a:b] = b
+        a = b
+    return ss.to(device), se.to(device)
+
+
+@pytest.mark.parametrize("S,cuts", [(512, [(100, 256, 300, 470), (512,)]),
+                                    (256, [(1, 2, 130, 255), (64, 128, 192, 256)]),
+                                    (1024, [(700, 1000), (128, 129, 640, 1024)])])
+def test_packed_block_diagonal_attention_fwd_bwd(ops, cuda, S, cuts):
+    """Sequence packing: block-diagonal causal attention (several samples per row; boundaries anywhere — inside a
+    64-key block, one-frame samples, a padding tail) through the tcgen05 kernels, forward and both backward kernels,
+    against SDPA in fp32 with the explicit mask; with the inverse RoPE fused into the dq / dk stores, positions
+    restarting at every sample."""
+    B, H, KV, hd = len(cuts), 8, 2, 64
+    g = torch.Generator().manual_seed(S)
+    q, k, v, do = ((torch.randn(B * S, n * hd, generator=g) * 0.8).to(BF).to(cuda) for n in (H, KV, KV, H))
+    segs = [_segments(S, c, cuda) for c in cuts]
+    ss = torch.stack([a for a, _ in segs]).contiguous()
+    se = torch.stack([b for _, b in segs]).contiguous()
+    o, lse = ops.attention_fwd(q, k, v, B, S, H, KV, hd, seg_start=ss)
+    i = torch.arange(S, device=cuda)
+    mask = (i[None, None, :] <= i[None, :, None]) & (i[None, None, :] >= ss[:, :, None])          # [B, S(q), S(k)]
+    q4 = q.float().view(B, S, H, hd).transpose(1, 2).requires_grad_(True)
+    k3 = k.float().view(B, S, KV, hd).requires_grad_(True)
+    v3 = v.float().view(B, S, KV, hd).requires_grad_(True)
+    k4 = k3.repeat_interleave(H // KV, dim=2).transpose(1, 2)
+    v4 = v3.repeat_interleave(H // KV, dim=2).transpose(1, 2)
+    ref = F.scaled_dot_product_attention(q4, k4, v4, attn_mask=mask[:, None])
+    ref2 = ref.transpose(1, 2).reshape(B * S, H * hd)
+    assert rel_err(o, ref2) < 1e-2 and cos(o, ref2) > 0.9999
+    ref_lse = torch.logsumexp((q4 @ k4.transpose(-1, -2) / math.sqrt(hd)).masked_fill(~mask[:, None], -float("inf")), -1)
+    assert torch.allclose(lse, ref_lse, atol=2e-2, rtol=1e-3)
+    ref2.backward(do.float())
+    dq, dk, dv = ops.attention_bwd(q, k, v, o, lse, do, B, S, H, KV, hd, seg_start=ss, seg_end=se)
+    gq = q4.grad.transpose(1, 2).reshape(B * S, H * hd)
+    gk, gv = k3.grad.reshape(B * S, KV * hd), v3.grad.reshape(B * S, KV * hd)
+    assert cos(dq, gq) > 0.999 and cos(dk, gk) > 0.999 and cos(dv, gv) > 0.999
+    assert rel_err(dq, gq) < 3e-2 and rel_err(dk, gk) < 3e-2 and rel_err(dv, gv) < 3e-2
+    # fused inverse RoPE with per-sample positions == the rope kernel applied afterwards with the same positions
+    cache = _rope_cache(hd, 2048).to(cuda)
+    pos = (torch.arange(S, device=cuda, dtype=torch.int32)[None, :] - ss).reshape(-1).contiguous()
+    dq2, dk2, dv2 = ops.attention_bwd(q, k, v, o, lse, do, B, S, H, KV, hd, rope_cache=cache, seg_start=ss, seg_end=se)
+    ops.rope_(dq, cache, S, H, hd, inverse=True, positions=pos)
+    ops.rope_(dk, cache, S, KV, hd, inverse=True, positions=pos)
+    assert torch.equal(dq2, dq) and torch.equal(dk2, dk) and torch.equal(dv2, dv)
+
+
+def test_gemm_rope_epilogue_with_per_row_positions(ops, cuda):
+    """Packed rows: RoPE positions restart with every sample — the q|k|v GEMM's rotating store epilogue and the rope
+    kernel both take an int32 position per row; bit-identical to each other and equal to the interleaved-pair formula."""
+    g = torch.Generator().manual_seed(3)
+    M, N, K, hd, cols = 512, 384, 256, 64, 256
+    x = (torch.randn(M, K, generator=g) * 0.5).to(BF).to(cuda)
+    w = (torch.randn(N, K, generator=g) * 0.1).to(BF).to(cuda)
+    cache = _rope_cache(hd, 2048).to(cuda)
+    pos = torch.randint(0, 300, (M,), generator=g).to(torch.int32).to(cuda)
+    fused = ops.gemm_rope(x, w, cache, 128, cols, hd, positions=pos)
+    plain = ops.gemm(x, w, backend=2)
+    manual = plain.clone()
+    ops.rope_(manual[:, :cols], cache, 128, cols // hd, hd, positions=pos)
+    assert torch.equal(fused, manual)
+    xs = plain[:, :cols].float().view(M, cols // hd, hd // 2, 2)
+    cs = cache[pos.long()].view(M, 1, hd // 2, 2)
+    want = torch.stack([xs[..., 0] * cs[..., 0] - xs[..., 1] * cs[..., 1],
+                        xs[..., 1] * cs[..., 0] + xs[..., 0] * cs[..., 1]], -1).reshape(M, cols).to(BF)
+    assert torch.equal(fused[:, :cols], want) and torch.equal(fused[:, cols:], plain[:, cols:])
