@@ -19,7 +19,7 @@ from ..models.model import Model
 from . import dp
 from .graph import GraphedStep
 from .trainer import clip_and_step, csm_1b_args, iterate_batches, make_optimizer
-from .utils import compute_loss, setup_logger
+from .utils import batch_loss, compute_loss, setup_logger
 
 
 class CSMLoRATrainer:
@@ -50,6 +50,7 @@ class CSMLoRATrainer:
         # batches from collate_pinned carry each sample's true target length: padded all-zero target frames are then
         # left out of the semantic mean as well (the reference averages over them, utils.py:101-105; set False for that)
         self.mask_padded_targets = True
+        self.pack_sequences_to: Optional[int] = None       # sequence packing (see CSMTrainer)
         self.model = model
         self.optimizer = None
         self._sync = None
@@ -121,10 +122,7 @@ class CSMLoRATrainer:
         return self._step_impl({k: v.to(self.device, non_blocking=True) for k, v in batch.items()}, max_grad_norm)
 
     def _step_impl(self, b, max_grad_norm: float) -> torch.Tensor:
-        loss, _ = compute_loss(self.model, b["input_tokens"], b["input_masks"], b["target_audio_tokens"],
-                               self.semantic_weight, self.acoustic_weight, frame_idx=b["frame_idx"],
-                                   target_lengths=b.get("target_lengths"),
-                                   mask_padded_targets=self.mask_padded_targets, speaker_ids=b.get("speaker_ids"))
+        loss, _ = batch_loss(self.model, b, self.semantic_weight, self.acoustic_weight, self.mask_padded_targets)
         loss.backward()
         self._sync.finish()
         clip_and_step(self.optimizer, list(self.get_lora_params().values()), max_grad_norm)
@@ -140,7 +138,8 @@ class CSMLoRATrainer:
         self.model.train()
         for epoch in range(self.epoch, self.epoch + epochs):
             losses = []
-            for batch in iterate_batches(train_dataset, batch_size, True, self.rank, self.world, seed=epoch):
+            for batch in iterate_batches(train_dataset, batch_size, True, self.rank, self.world, seed=epoch,
+                                         pack_to=self.pack_sequences_to):
                 losses.append(self.train_step(batch, max_grad_norm))
                 if val_dataset is not None and self.global_step % val_every == 0:
                     val = self._validate(val_dataset, batch_size)
@@ -164,10 +163,7 @@ class CSMLoRATrainer:
         with torch.no_grad():
             for batch in iterate_batches(val_dataset, batch_size, False):
                 b = self._to_device(batch)
-                loss, _ = compute_loss(self.model, b["input_tokens"], b["input_masks"], b["target_audio_tokens"],
-                                       self.semantic_weight, self.acoustic_weight, frame_idx=b["frame_idx"],
-                                   target_lengths=b.get("target_lengths"),
-                                   mask_padded_targets=self.mask_padded_targets, speaker_ids=b.get("speaker_ids"))
+                loss, _ = batch_loss(self.model, b, self.semantic_weight, self.acoustic_weight, self.mask_padded_targets)
                 total += float(loss)
                 n += 1
         self.model.train()

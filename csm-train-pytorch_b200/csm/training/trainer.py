@@ -17,7 +17,7 @@ import torch
 from ..models.model import Model, ModelArgs
 from . import dp
 from .graph import GraphedStep
-from .utils import compute_loss, load_checkpoint, save_checkpoint, setup_logger
+from .utils import batch_loss, compute_loss, load_checkpoint, save_checkpoint, setup_logger
 
 
 def csm_1b_args() -> ModelArgs:                       # trainer.py:100-106
@@ -32,7 +32,10 @@ def collate_variable_length(batch):
     return collate_pinned(batch)
 
 
-def iterate_batches(dataset, batch_size: int, shuffle: bool, rank: int = 0, world: int = 1, seed: int = 0):
+def iterate_batches(dataset, batch_size: int, shuffle: bool, rank: int = 0, world: int = 1, seed: int = 0,
+                    pack_to: Optional[int] = None):
+    """`pack_to`: lay each batch's samples back to back in rows of at most that many frames (sequence packing,
+    csm/data/frames.py::pack_samples) instead of zero-padding every sample to the batch maximum."""
     n = len(dataset)
     order = torch.randperm(n, generator=torch.Generator().manual_seed(seed)).tolist() if shuffle else list(range(n))
     if world > 1:
@@ -40,7 +43,14 @@ def iterate_batches(dataset, batch_size: int, shuffle: bool, rank: int = 0, worl
         order = order[:(n // world) * world]
     order = order[rank::world]
     for i in range(0, len(order), batch_size):
-        yield collate_variable_length([dataset[j] for j in order[i:i + batch_size]])
+        samples = [dataset[j] for j in order[i:i + batch_size]]
+        if pack_to:
+            from ..data.frames import pack_samples
+            b = pack_samples(samples, pack_to, generator=torch.Generator().manual_seed(seed * 100003 + i))
+            b.pop("sample_index")
+            yield b
+        else:
+            yield collate_variable_length(samples)
 
 
 def make_optimizer(param_groups, lr: float, weight_decay: float):
@@ -86,6 +96,8 @@ class CSMTrainer:
         # batches from collate_pinned carry each sample's true target length: padded all-zero target frames are then
         # left out of the semantic mean as well (the reference averages over them, utils.py:101-105; set False for that)
         self.mask_padded_targets = True
+        # sequence packing: rows of at most this many frames holding several samples each (None: pad like the reference)
+        self.pack_sequences_to: Optional[int] = None
         self.model = None
         self.optimizer = None
         self._sync = None
@@ -165,10 +177,7 @@ class CSMTrainer:
             self.prepare_optimizer()
 
         def impl(b):
-            loss, _ = compute_loss(self.model, b["input_tokens"], b["input_masks"], b["target_audio_tokens"],
-                                   self.semantic_weight, self.acoustic_weight, frame_idx=b["frame_idx"],
-                                   target_lengths=b.get("target_lengths"),
-                                   mask_padded_targets=self.mask_padded_targets)
+            loss, _ = batch_loss(self.model, b, self.semantic_weight, self.acoustic_weight, self.mask_padded_targets)
             loss.backward()
             self._sync.finish()
             clip_and_step(self.optimizer, [p for p in self.model.parameters() if p.requires_grad], max_grad_norm)
@@ -202,10 +211,7 @@ class CSMTrainer:
         """`last` = this micro-batch closes the accumulation window (gradients are exchanged during its backward)."""
         self._sync.accumulating = not last
         b = self._to_device(batch)
-        loss, _ = compute_loss(self.model, b["input_tokens"], b["input_masks"], b["target_audio_tokens"],
-                               self.semantic_weight, self.acoustic_weight, frame_idx=b["frame_idx"],
-                                   target_lengths=b.get("target_lengths"),
-                                   mask_padded_targets=self.mask_padded_targets)
+        loss, _ = batch_loss(self.model, b, self.semantic_weight, self.acoustic_weight, self.mask_padded_targets)
         (loss / accumulation_steps).backward()
         return loss.detach()
 
@@ -229,7 +235,7 @@ class CSMTrainer:
             t0 = time.time()
             losses, window = [], []
             for bi, batch in enumerate(iterate_batches(train_dataset, batch_size, True, self.rank, self.world,
-                                                       seed=epoch)):
+                                                       seed=epoch, pack_to=self.pack_sequences_to)):
                 closes = (bi + 1) % accumulation_steps == 0
                 window.append(self.train_micro_batch(batch, accumulation_steps, last=closes))
                 if closes:
@@ -264,10 +270,7 @@ class CSMTrainer:
         with torch.no_grad():
             for batch in iterate_batches(val_dataset, batch_size, False):
                 b = self._to_device(batch)
-                loss, _ = compute_loss(self.model, b["input_tokens"], b["input_masks"], b["target_audio_tokens"],
-                                       self.semantic_weight, self.acoustic_weight, frame_idx=b["frame_idx"],
-                                   target_lengths=b.get("target_lengths"),
-                                   mask_padded_targets=self.mask_padded_targets)
+                loss, _ = batch_loss(self.model, b, self.semantic_weight, self.acoustic_weight, self.mask_padded_targets)
                 total += float(loss)
                 n += 1
         self.model.train()

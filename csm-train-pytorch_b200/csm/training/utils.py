@@ -50,6 +50,17 @@ def compute_loss(model, input_tokens: torch.Tensor, input_masks: torch.Tensor, t
                  segment_ends=segment_ends, target_mask=target_mask)
 
 
+def batch_loss(model, batch: Dict[str, torch.Tensor], semantic_weight: float = 100.0, acoustic_weight: float = 1.0,
+               mask_padded_targets: bool = False) -> Tuple[torch.Tensor, Dict[str, torch.Tensor]]:
+    """compute_loss on a batch dict as the trainers' collate / pack functions build it: the three reference keys plus
+    the optional extensions (frame_idx, target_lengths, speaker_ids, segment_starts / segment_ends / target_mask)."""
+    return compute_loss(model, batch["input_tokens"], batch["input_masks"], batch["target_audio_tokens"],
+                        semantic_weight, acoustic_weight, frame_idx=batch.get("frame_idx"),
+                        target_lengths=batch.get("target_lengths"), mask_padded_targets=mask_padded_targets,
+                        speaker_ids=batch.get("speaker_ids"), segment_starts=batch.get("segment_starts"),
+                        segment_ends=batch.get("segment_ends"), target_mask=batch.get("target_mask"))
+
+
 def save_checkpoint(model, optimizer, epoch: int, global_step: int, loss: float, save_dir: str,
                     name: str = "checkpoint") -> str:
     os.makedirs(save_dir, exist_ok=True)

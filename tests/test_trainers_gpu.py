@@ -397,3 +397,36 @@ def test_multi_speaker_trainer_mixed_batches_and_per_speaker_files(cuda, tmp_pat
     # and loads back into another speaker's slot
     t.load_speaker_model(42, str(tmp_path / "ms" / "speaker_11" / "speaker_11_lora.safetensors"))
     assert torch.equal(t.speaker_state(42)[dec], t.speaker_state(11)[dec])
+
+
+def test_trainers_with_sequence_packing(cuda, tmp_path):
+    """CSMTrainer.train / CSMLoRATrainer.train with ``pack_sequences_to``: every batch's ragged samples are packed into
+    rows (block-diagonal causal attention) instead of zero-padded; the loop runs, learns, and the packed first step's
+    loss equals the length-weighted loss of the same samples padded one per row (masking the padded targets)."""
+    from csm.data.frames import collate_pinned, pack_samples
+    from csm.training.trainer import CSMTrainer
+    from csm.training.utils import batch_loss
+    model, cfg = _small_model(cuda)
+    data = _ragged_dataset(cfg, [128, 200, 160, 140, 250, 130, 180, 150])
+    t = CSMTrainer("", str(tmp_path / "ft"), device=str(cuda), learning_rate=2e-4)
+    t.model = model
+    t.prepare_optimizer(freeze_embeddings=True)
+    packed = pack_samples(data[:4], 384, generator=torch.Generator().manual_seed(0))
+    padded = collate_pinned(data[:4])
+    with torch.no_grad():
+        bp = {k: v.to(cuda) for k, v in packed.items()}
+        lp, dp_ = batch_loss(model, bp, 100.0, 1.0)
+        bd = t._to_device(padded)
+        ld, dd = batch_loss(model, bd, 100.0, 1.0, mask_padded_targets=True)
+    # same samples, same semantic positions (p < len - 1 of every sample): the packed mean equals the padded-masked mean
+    assert abs(float(dp_["semantic_loss"]) - float(dd["semantic_loss"])) <= 3e-3 * float(dd["semantic_loss"])
+    assert packed["input_tokens"].shape[0] * packed["input_tokens"].shape[1] < \\
+        padded["input_tokens"].shape[0] * padded["input_tokens"].shape[1]               # fewer frames through the backbone
+    t.pack_sequences_to = 384
+    first = None
+    t.train(data, None, batch_size=4, accumulation_steps=1, epochs=3, val_every=100, save_every=100)
+    assert t.global_step == 6
+    tl, _ = _lora_trainer(tmp_path / "lora", cuda, graph=False)
+    tl.pack_sequences_to = 384
+    tl.train(data[:4], None, batch_size=4, epochs=2, val_every=100, save_every=100)
+    assert tl.global_step == 2
