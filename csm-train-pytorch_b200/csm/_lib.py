@@ -40,6 +40,7 @@ SIGNATURES = {
     "csm_swiglu_bwd": (_i32, [_ptr] * 5 + [_i64] * 7 + [_ptr]),
     "csm_attn_causal_gqa_fwd": (_i32, [_ptr] * 5 + [_i32] * 5 + [_i64] * 4 + [_f32, _ptr]),
     "csm_set_attn_backend": (None, [_i32]),
+    "csm_set_attn_fwd_variant": (None, [_i32]),
     "csm_set_gemm_cta_pair_mode": (None, [_i32]),
     "csm_set_gemm_dynamic_tiles": (None, [_i32]),
     "csm_set_reserved_sms": (None, [_i32]),

@@ -59,6 +59,11 @@ def set_attn_backend(b: int) -> None:
     _lib.load().csm_set_attn_backend(b)
 
 
+def set_attn_fwd_variant(v: int) -> None:
+    """A/B hook: tcgen05 attention forward with the output accumulated in TMEM (1, default) or in registers (0)."""
+    _lib.load().csm_set_attn_fwd_variant(v)
+
+
 def _p(t: Optional[torch.Tensor]):
     return None if t is None else t.data_ptr()
 

@@ -70,6 +70,7 @@ int attn_bwd_tc_launch(const void*, const void*, const void*, const void*, const
                        void*, float*, int, int, int, int, int64_t, int64_t, int64_t, int64_t, int64_t, int64_t, int64_t,
                        float, const float*, const int32_t*, const int32_t*, cudaStream_t);
 static std::atomic<int> g_attn_backend{0};  // 0 auto, 1 scalar, 2 mma.sync, 3 tcgen05, 4 short-sequence
+void attn_tc_set_fwd_variant(int v);
 
 int gemm_dispatch(const void* A, const void* B, void* C, const void* R, int64_t M, int64_t N, int64_t K,
                   int64_t lda, int64_t ldb, int64_t ldc, int64_t ldr, int transA, int transB, int c_dtype,
@@ -112,6 +113,7 @@ using namespace csm;
 
 extern "C" int csm_abi_version(void) { return CSM_ABI_VERSION; }
 extern "C" void csm_set_attn_backend(int32_t backend) { g_attn_backend.store(backend); }
+extern "C" void csm_set_attn_fwd_variant(int32_t v) { csm::attn_tc_set_fwd_variant(v); }
 extern "C" void csm_set_reserved_sms(int32_t n) { csm::g_reserved_sms.store(n < 0 ? 0 : n); }
 namespace csm {
 void gemm_tc_set_cta_pair_mode(int m);

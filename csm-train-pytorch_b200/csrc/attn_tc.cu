@@ -49,7 +49,12 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
 // seg_start[b, i] <= j <= i.  A query tile then starts at the key block that holds the first row's segment start
 // instead of block 0 — packed short samples cost what they would cost alone — and the blocks that straddle a
 // segment start are masked like the diagonal ones.
-template <bool kVarlen>
+// kTmemO: the output tile accumulates in TMEM across the key blocks (PV_j issued with accumulate) instead of being
+// folded into registers block by block.  The softmax threads then neither read PV_j back (64 tcgen05.ld columns + 64
+// FMAs per row and block) nor hold 64 accumulator registers; the running maximum is LAZY: a row keeps exponentiating
+// against its current reference until the block maximum exceeds it by more than 2^8, and only then is the TMEM
+// accumulator rescaled in place (rare after the first blocks; P stays <= 256, exact in bf16's exponent range).
+template <bool kVarlen, bool kTmemO>
 __global__ void __launch_bounds__(kAttnThreads, 2)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                    const __grid_constant__ CUtensorMap tmV, bf16* __restrict__ o, float* __restrict__ lse, int S,
@@ -159,8 +164,8 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           const uint64_t bd = make_smem_desc(sv, 64 * FK * 2, 1024);
 #pragma unroll
           for (int kk = 0; kk < FK / 16; ++kk)
-            umma_bf16_ts(tmem_base + COL_PV + st * THD, tmem_base + COL_S + st * FK + kk * 8,
-                         bd + (uint64_t)((kk * 16 * 128) >> 4), idesc_pv, kk ? 1u : 0u);
+            umma_bf16_ts(tmem_base + COL_PV + (kTmemO ? 0 : st * THD), tmem_base + COL_S + st * FK + kk * 8,
+                         bd + (uint64_t)((kk * 16 * 128) >> 4), idesc_pv, (kk || (kTmemO && j > 0)) ? 1u : 0u);
           umma_commit(&pv_full[st]);
           umma_commit(&kv_empty[j % FST]);
         }
@@ -193,8 +198,74 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       for (int i = 0; i < THD; ++i) oacc[i] = fmaf(oacc[i], corr, __uint_as_float(v[i]));
     };
 
+    // ---- kTmemO: lazy running maximum, accumulator rescaled in TMEM only when a row's reference moves
+    float m_used = -INFINITY;                  // the reference the row's exponentials are taken against (log2 domain)
+    auto block_tmem = [&](int j, auto diag_tag) {
+      constexpr bool DIAG = decltype(diag_tag)::value;
+      const int st = j & 1;
+      const int kbase = (blk0 + j) * FK;
+      mbar_wait(&s_full[st], (j >> 1) & 1);
+      tc_fence_after();
+      const uint32_t s_addr = lane_addr + COL_S + st * FK;
+      uint32_t v[FK];
+      __syncwarp();
+#pragma unroll
+      for (int c = 0; c < FK; c += 32) tmem_ld32(s_addr + c, v + c);
+      tmem_ld_wait();
+      float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+      for (int i = 0; i < FK; ++i) {
+        if (DIAG && ((kbase + i > qi) || (kVarlen && kbase + i < lo))) v[i] = 0xff800000u;   // -inf
+        m4[i & 3] = fmaxf(m4[i & 3], __uint_as_float(v[i]));
+      }
+      const float mrs = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])) * scale_log2;
+      // move the reference when the block maximum is more than 2^8 above it (or when the row had seen no key yet)
+      const bool move = mrs > m_used + 8.f;                       // (-inf + 8 = -inf: any finite maximum moves it)
+      const float m_new = move ? mrs : m_used;
+      const float corr = move ? ex2(m_used - m_new) : 1.f;        // exp2(-inf) = 0 on an accumulator that is still 0
+      if (j > 0 && __any_sync(0xffffffffu, move)) {
+        // PV(j-1) — the last MMA that wrote the accumulator — has completed; PV(j) cannot start before this warp
+        // arrives on p_full(j) below
+        mbar_wait(&pv_full[(j - 1) & 1], ((j - 1) >> 1) & 1);
+        tc_fence_after();
+        uint32_t ov[32];
+#pragma unroll
+        for (int c = 0; c < THD; c += 32) {
+          __syncwarp();
+          tmem_ld32(lane_addr + COL_PV + c, ov);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) ov[i] = __float_as_uint(__uint_as_float(ov[i]) * corr);
+          tmem_st16(lane_addr + COL_PV + c, ov);
+          tmem_st16(lane_addr + COL_PV + c + 16, ov + 16);
+        }
+      }
+      m_used = m_new;
+      const float mref = (m_new == -INFINITY) ? 0.f : m_new;      // packing: a row that still sees no key
+      float rs4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int c = 0; c < FK; c += 32) {
+        float p[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          p[i] = ex2(fmaf(__uint_as_float(v[c + i]), scale_log2, -mref));
+          rs4[i & 3] += p[i];
+        }
+        uint32_t pw[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) pw[i] = pack_bf16(p[2 * i], p[2 * i + 1]);
+        tmem_st16(s_addr + (c >> 1), pw);
+      }
+      l = l * corr + ((rs4[0] + rs4[1]) + (rs4[2] + rs4[3]));
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_full[st]);
+    };
+
     // one KV block of the online softmax; DIAG is the block on the causal diagonal (the only one that needs masks)
     auto block = [&](int j, auto diag_tag) {
+      if (kTmemO) { block_tmem(j, diag_tag); return; }
       constexpr bool DIAG = decltype(diag_tag)::value;
       const int st = j & 1;
       const int kbase = (blk0 + j) * FK;
@@ -255,7 +326,20 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         if (kb < lo_max || kb + FK - 1 > q0) block(j, std::true_type{}); else block(j, std::false_type{});
       }
     }
-    fold(nblk - 1, corr_prev);
+    if (kTmemO) {
+      mbar_wait(&pv_full[(nblk - 1) & 1], ((nblk - 1) >> 1) & 1);      // the last PV: the accumulator is complete
+      tc_fence_after();
+      uint32_t ov[THD];
+      __syncwarp();
+#pragma unroll
+      for (int c = 0; c < THD; c += 32) tmem_ld32(lane_addr + COL_PV + c, ov + c);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < THD; ++i) oacc[i] = __uint_as_float(ov[i]);
+      m = m_used;
+    } else {
+      fold(nblk - 1, corr_prev);
+    }
     if (qi < S) {
       const float inv = 1.f / l;
       bf16* op = o + ((int64_t)b * S + qi) * ldo + (int64_t)h * THD;
@@ -741,6 +825,10 @@ attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
 
 }  // namespace
 
+// forward variant: 0 = output folded into registers block by block, 1 = output accumulated in TMEM with a lazy maximum
+static std::atomic<int> g_attn_fwd_variant{1};
+void attn_tc_set_fwd_variant(int v) { g_attn_fwd_variant.store(v); }
+
 bool attn_tc_supported(int S, int hd, int64_t ldq, int64_t ldk, int64_t ldv, int64_t ldo, const void* q, const void* k,
                        const void* v, const void* o) {
   return hd == THD && S >= 128 && ldq % 8 == 0 && ldk % 8 == 0 && ldv % 8 == 0 && ldo % 8 == 0 && aligned16(q) &&
@@ -757,19 +845,23 @@ int attn_fwd_tc_launch(const void* q, const void* k, const void* v, void* o, flo
   if ((rc = encode_tmap_bf16(&tv, v, (uint64_t)KV * THD, S, B, ldv, (uint64_t)S * ldv, FK))) return rc;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(attn_fwd_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem);
+    cudaError_t e = cudaFuncSetAttribute(attn_fwd_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem);
     if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(attn_fwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem);
+      e = cudaFuncSetAttribute(attn_fwd_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(attn_fwd_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(attn_fwd_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem);
     if (e != cudaSuccess) { set_error("attn_fwd_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return CSM_ERR_CUDA; }
     configured = true;
   }
   dim3 grid(((S + TQ - 1) / TQ) * H * B);
-  if (seg_start)
-    attn_fwd_tc_kernel<true><<<grid, kAttnThreads, kAttnSmem, st>>>(tq, tk, tv, (bf16*)o, lse, S, H, KV, ldo,
-                                                                    scale * kLog2e, seg_start);
-  else
-    attn_fwd_tc_kernel<false><<<grid, kAttnThreads, kAttnSmem, st>>>(tq, tk, tv, (bf16*)o, lse, S, H, KV, ldo,
-                                                                     scale * kLog2e, nullptr);
+  const bool tmem_o = g_attn_fwd_variant.load() == 1;
+#define FWD(V, T) attn_fwd_tc_kernel<V, T><<<grid, kAttnThreads, kAttnSmem, st>>>(tq, tk, tv, (bf16*)o, lse, S, H, KV, ldo, \
+                                                                               scale * kLog2e, seg_start)
+  if (seg_start) { if (tmem_o) FWD(true, true); else FWD(true, false); }
+  else { if (tmem_o) FWD(false, true); else FWD(false, false); }
+#undef FWD
   CSM_CHECK_LAUNCH("attn_fwd_tc");
   return CSM_OK;
 }

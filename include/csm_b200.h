@@ -178,6 +178,9 @@ int csm_attn_causal_gqa_fwd(const void* q, const void* k, const void* v, void* o
  * short-sequence kernel for seq <= 32 and head_dim 64/128 (depth decoder), mma.sync for other head_dim 64 shapes,
  * scalar otherwise), 1 = scalar, 2 = mma.sync, 3 = tcgen05, 4 = short-sequence (3/4: error if unsupported). */
 void csm_set_attn_backend(int32_t backend);
+/* A/B hook for the tcgen05 attention forward: 1 (default) the output tile accumulates in TMEM across the key blocks
+ * with a lazily updated row maximum, 0 = folded into registers block by block (the round-1 kernel). */
+void csm_set_attn_fwd_variant(int32_t variant);
 /* test hook: CTA-pair (tcgen05 cta_group::2, 256-row tiles) mode of the tensor-core GEMM. -1 = automatic (large
  * plain GEMMs only), 0 = never, 1 = whenever the shape allows it. */
 void csm_set_gemm_cta_pair_mode(int32_t mode);

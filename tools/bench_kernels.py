@@ -18,6 +18,8 @@ BF = torch.bfloat16
 # A/B switches (defaults untouched when unset): CSM_PAIR_MODE = 0 | 1, CSM_NARROW_TAIL = 1 (experimental)
 if os.environ.get("CSM_PAIR_MODE"):
     ops.set_gemm_cta_pair_mode(int(os.environ["CSM_PAIR_MODE"]))
+if os.environ.get("CSM_ATTN_FWD_VARIANT"):
+    ops.set_attn_fwd_variant(int(os.environ["CSM_ATTN_FWD_VARIANT"]))
 if os.environ.get("CSM_DYN_TILES"):
     ops.set_gemm_dynamic_tiles(int(os.environ["CSM_DYN_TILES"]))
 if os.environ.get("CSM_NARROW_TAIL"):
@@ -110,10 +112,38 @@ def bench_attn():
         k4 = k.view(B, S, KV, hd).transpose(1, 2)
         v4 = v.view(B, S, KV, hd).transpose(1, 2)
         ref = timeit(lambda: F.scaled_dot_product_attention(q4, k4, v4, is_causal=True, enable_gqa=True))
+        # same-box comparators, forward AND backward (never on the product path): torch SDPA pinned to the cuDNN and to
+        # the flash back-end, and the flash-attn 2 package
+        comp = {}
+        from torch.nn.attention import SDPBackend, sdpa_kernel
+        do4 = do.view(B, S, H, hd).transpose(1, 2)
+        for name, be in (("cudnn", SDPBackend.CUDNN_ATTENTION), ("torch_flash", SDPBackend.FLASH_ATTENTION)):
+            try:
+                with sdpa_kernel(be):
+                    qg, kg, vg = (t.detach().requires_grad_(True) for t in (q4, k4, v4))
+                    tf = timeit(lambda: F.scaled_dot_product_attention(qg, kg, vg, is_causal=True, enable_gqa=True))
+                    out = F.scaled_dot_product_attention(qg, kg, vg, is_causal=True, enable_gqa=True)
+                    tb = timeit(lambda: torch.autograd.grad(out, (qg, kg, vg), do4, retain_graph=True))
+                comp[name] = {"fwd_ms": tf, "bwd_ms": tb}
+            except Exception as e:  # noqa: BLE001
+                comp[name] = {"error": str(e)[:100]}
+        try:
+            from flash_attn import flash_attn_func
+            qf, kf, vf = (t.view(B, S, n, hd).detach().requires_grad_(True) for t, n in ((q, H), (k, KV), (v, KV)))
+            tf = timeit(lambda: flash_attn_func(qf, kf, vf, causal=True))
+            out = flash_attn_func(qf, kf, vf, causal=True)
+            dof = do.view(B, S, H, hd)
+            tb = timeit(lambda: torch.autograd.grad(out, (qf, kf, vf), dof, retain_graph=True))
+            comp["flash_attn_2"] = {"fwd_ms": tf, "bwd_ms": tb}
+        except Exception as e:  # noqa: BLE001
+            comp["flash_attn_2"] = {"error": str(e)[:100]}
         rows.append({"B": B, "S": S, "H": H, "KV": KV, "hd": hd, "fwd_ms": f, "bwd_ms": bw,
-                     "fwd_tflops": fl / f / 1e9, "bwd_tflops": 2.5 * fl / bw / 1e9, "sdpa_fwd_ms": ref})
+                     "fwd_tflops": fl / f / 1e9, "bwd_tflops": 2.5 * fl / bw / 1e9, "sdpa_fwd_ms": ref,
+                     "comparators": comp})
+        cs = "  ".join(f"{n}: fwd {c['fwd_ms']*1e3:.0f} bwd {c['bwd_ms']*1e3:.0f} us" if "fwd_ms" in c else f"{n}: n/a"
+                       for n, c in comp.items())
         print(f"attn B={B} S={S} H={H} KV={KV} hd={hd}: fwd {f*1e3:.0f} us ({fl/f/1e9:.0f} TF/s causal-alg) "
-              f"bwd {bw*1e3:.0f} us ({2.5*fl/bw/1e9:.0f} TF/s)  [SDPA fwd {ref*1e3:.0f} us]", flush=True)
+              f"bwd {bw*1e3:.0f} us ({2.5*fl/bw/1e9:.0f} TF/s)  [SDPA fwd {ref*1e3:.0f} us]  [{cs}]", flush=True)
     return rows
 
 
