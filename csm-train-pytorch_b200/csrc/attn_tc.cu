@@ -40,6 +40,20 @@ __device__ __forceinline__ float ex2(float x) {   // one MUFU; -inf -> 0
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+// exp2 on the FMA pipe (Cody-Waite split + degree-3 polynomial, relative error ~1e-4 — far below the bf16 rounding P gets
+// next): floor(x) through the 1.5 * 2^23 magic add in round-down mode, 2^frac by Horner, the integer part added straight
+// into the exponent field.  The softmax is MUFU-bound (one ex2 per score, 4 lanes per clock per scheduler); evaluating a
+// share of the scores here runs both pipes side by side.  Inputs <= ~8 (lazy maximum); -inf (masked) -> 2^-127 ~ 0.
+__device__ __forceinline__ float ex2_fma(float x) {
+  x = fmaxf(x, -127.f);
+  float t;
+  asm("add.rm.f32 %0, %1, 0f4B400000;" : "=f"(t) : "f"(x));        // floor(x) + 12582912
+  const float xf = x - (t - 12582912.f);                              // in [0, 1)
+  float p = fmaf(0.077119089663028717f, xf, 0.227564394474029541f);
+  p = fmaf(p, xf, 0.695146143436431885f);
+  p = fmaf(p, xf, 1.0f);
+  return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
+}
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
@@ -54,7 +68,8 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
 // FMAs per row and block) nor hold 64 accumulator registers; the running maximum is LAZY: a row keeps exponentiating
 // against its current reference until the block maximum exceeds it by more than 2^8, and only then is the TMEM
 // accumulator rescaled in place (rare after the first blocks; P stays <= 256, exact in bf16's exponent range).
-template <bool kVarlen, bool kTmemO>
+// kPoly: every kPoly-th score of a row (0: none) takes ex2_fma instead of the MUFU.
+template <bool kVarlen, bool kTmemO, int kPoly = 0>
 __global__ void __launch_bounds__(kAttnThreads, 2)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                    const __grid_constant__ CUtensorMap tmV, bf16* __restrict__ o, float* __restrict__ lse, int S,
@@ -248,7 +263,8 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         float p[32];
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
-          p[i] = ex2(fmaf(__uint_as_float(v[c + i]), scale_log2, -mref));
+          const float x = fmaf(__uint_as_float(v[c + i]), scale_log2, -mref);
+          p[i] = (kPoly > 0 && (i % (kPoly > 0 ? kPoly : 1)) == (kPoly > 0 ? kPoly : 1) - 1) ? ex2_fma(x) : ex2(x);
           rs4[i & 3] += p[i];
         }
         uint32_t pw[16];
@@ -825,7 +841,8 @@ attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
 
 }  // namespace
 
-// forward variant: 0 = output folded into registers block by block, 1 = output accumulated in TMEM with a lazy maximum
+// forward variant: 0 = output folded into registers block by block, 1 = output accumulated in TMEM with a lazy maximum,
+// 2 / 3 / 4 = variant 1 with every 4th / 3rd / 2nd exponential on the FMA pipe (ex2_fma)
 static std::atomic<int> g_attn_fwd_variant{1};
 void attn_tc_set_fwd_variant(int v) { g_attn_fwd_variant.store(v); }
 
@@ -852,15 +869,27 @@ int attn_fwd_tc_launch(const void* q, const void* k, const void* v, void* o, flo
       e = cudaFuncSetAttribute(attn_fwd_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem);
     if (e == cudaSuccess)
       e = cudaFuncSetAttribute(attn_fwd_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(attn_fwd_tc_kernel<false, true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(attn_fwd_tc_kernel<true, true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(attn_fwd_tc_kernel<false, true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(attn_fwd_tc_kernel<false, true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem);
     if (e != cudaSuccess) { set_error("attn_fwd_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return CSM_ERR_CUDA; }
     configured = true;
   }
   dim3 grid(((S + TQ - 1) / TQ) * H * B);
-  const bool tmem_o = g_attn_fwd_variant.load() == 1;
-#define FWD(V, T) attn_fwd_tc_kernel<V, T><<<grid, kAttnThreads, kAttnSmem, st>>>(tq, tk, tv, (bf16*)o, lse, S, H, KV, ldo, \
-                                                                               scale * kLog2e, seg_start)
-  if (seg_start) { if (tmem_o) FWD(true, true); else FWD(true, false); }
-  else { if (tmem_o) FWD(false, true); else FWD(false, false); }
+  const int variant = g_attn_fwd_variant.load();
+#define FWD(V, T, P) attn_fwd_tc_kernel<V, T, P><<<grid, kAttnThreads, kAttnSmem, st>>>(tq, tk, tv, (bf16*)o, lse, S, H, KV, \
+                                                                                     ldo, scale * kLog2e, seg_start)
+  if (seg_start) { if (variant == 0) FWD(true, false, 0); else if (variant == 1) FWD(true, true, 0); else FWD(true, true, 4); }
+  else if (variant == 0) FWD(false, false, 0);
+  else if (variant == 1) FWD(false, true, 0);
+  else if (variant == 2) FWD(false, true, 4);
+  else if (variant == 3) FWD(false, true, 3);
+  else FWD(false, true, 2);
 #undef FWD
   CSM_CHECK_LAUNCH("attn_fwd_tc");
   return CSM_OK;

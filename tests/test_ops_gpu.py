@@ -718,3 +718,28 @@ def test_gemm_rope_epilogue_with_per_row_positions(ops, cuda):
     want = torch.stack([xs[..., 0] * cs[..., 0] - xs[..., 1] * cs[..., 1],
                         xs[..., 1] * cs[..., 0] + xs[..., 0] * cs[..., 1]], -1).reshape(M, cols).to(BF)
     assert torch.equal(fused[:, :cols], want) and torch.equal(fused[:, cols:], plain[:, cols:])
+
+
+@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4])
+def test_attention_forward_variants(ops, cuda, variant):
+    """tcgen05 attention forward: 0 = output folded into registers per block (round 1), 1 = output accumulated in TMEM
+    with a lazily updated row maximum, 2..4 = variant 1 with every 4th / 3rd / 2nd exponential evaluated on the FMA pipe
+    (Cody-Waite + cubic).  All against SDPA in fp32, with large score ranges so that the lazy maximum actually moves."""
+    B, S, H, KV, hd = 2, 640, 8, 2, 64
+    g = torch.Generator().manual_seed(5)
+    q = (torch.randn(B * S, H * hd, generator=g) * 2.0).to(BF).to(cuda)
+    k = (torch.randn(B * S, KV * hd, generator=g) * 2.0).to(BF).to(cuda)
+    k[S // 2:] *= 3.0                                   # later keys score higher: the reference maximum keeps moving
+    v = torch.randn(B * S, KV * hd, generator=g).to(BF).to(cuda)
+    ops.set_attn_fwd_variant(variant)
+    try:
+        o, lse = ops.attention_fwd(q, k, v, B, S, H, KV, hd)
+    finally:
+        ops.set_attn_fwd_variant(1)
+    ref = _sdpa_ref(q, k, v, B, S, H, KV, hd)
+    assert rel_err(o, ref) < 1.2e-2 and cos(o, ref) > 0.9999
+    q4 = q.float().view(B, S, H, hd).transpose(1, 2)
+    k4 = k.float().view(B, S, KV, hd).repeat_interleave(H // KV, dim=2).transpose(1, 2)
+    sc = (q4 @ k4.transpose(-1, -2) / math.sqrt(hd)).masked_fill(
+        ~torch.tril(torch.ones(S, S, dtype=torch.bool, device=cuda)), -float("inf"))
+    assert torch.allclose(lse, torch.logsumexp(sc, -1), atol=2e-2, rtol=2e-3)
