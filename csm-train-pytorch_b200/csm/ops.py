@@ -49,6 +49,11 @@ def set_gemm_dynamic_tiles(m: int) -> None:
     _lib.load().csm_set_gemm_dynamic_tiles(m)
 
 
+def set_ce_fused_combine(m: int) -> None:
+    """A/B hook: fused-CE forward combines its partials in the last tile's epilogue (1, default) or in a second kernel."""
+    _lib.load().csm_set_ce_fused_combine(m)
+
+
 _attn_backend = 0
 
 
