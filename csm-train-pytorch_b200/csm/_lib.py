@@ -62,6 +62,7 @@ SIGNATURES = {
     "csm_attn_varlen_bwd": (_i32, [_ptr] * 9 + [_i32] * 5 + [_i64] * 7 + [_f32, _ptr, _ptr, _ptr, _ptr, _sz, _ptr]),
     "csm_attn_decode": (_i32, [_ptr] * 4 + [_i32] * 5 + [_i64] * 4 + [_f32, _ptr]),
     "csm_lora_mask_rows": (_i32, [_ptr, _i64, _i64, _i32, _ptr, _i32, _i32, _ptr]),
+    "csm_lora_dropout": (_i32, [_ptr, _ptr, _i64, _i64, _i64, _i64, _f32, _ptr, _i64, _i32, _ptr]),
     "csm_f32_to_bf16": (_i32, [_ptr, _ptr, _i64, _f32, _i32, _ptr]),
     "csm_add_bf16": (_i32, [_ptr, _ptr, _ptr, _i64, _ptr]),
 }

@@ -231,9 +231,13 @@ class _Group:
     LoRA adapters on any member ride in the same GEMM through the extra K block: t = x [A_0; A_1; ..]^T and a
     block-diagonal [(s_0 B_0) 0; 0 (s_1 B_1)] tail operand."""
 
-    def __init__(self, mods, index_of, cache, adapter_rows=None):
+    def __init__(self, mods, index_of, cache, adapter_rows=None, drop=None):
+        """`drop` = (p, seed_dev int64 [1], salt): LoRA input dropout of this call (training only; lora.py:87-90)."""
         self.mods = mods
         self.rows = None
+        self.drop = drop if (drop is not None and drop[0] > 0.0) else None
+        self.bias = [(j, m) for j, m in enumerate(mods) if getattr(m, "lora_bias", None) is not None]
+        self.ib = {j: index_of[id(m.lora_bias)] for j, m in self.bias}
         self.W = _packed_weight(mods, cache)
         self.iw = [index_of[id(m.weight)] for m in mods]
         self.offs, o = [], 0
@@ -259,7 +263,9 @@ class _Group:
             # tail operand then holds the raw B factors and no per-step scaling kernels are needed
             scal = {float(m.lora_scaling) for _, m in self.lora}
             self.s = scal.pop() if len(scal) == 1 else None
-            self.views = self.s is not None and R % 8 == 0      # common scaling: the parameters can BE the operands
+            self.R = R
+            # common scaling: the parameters can BE the operands (not with the LoRA bias column, which is appended)
+            self.views = self.s is not None and R % 8 == 0 and not self.bias
             if self.views:
                 self.A_cat, self.B_bd = _packed_lora(self.lora, self.n_out, self.offs, self.W, cache,
                                                      ("lora",) + tuple(id(m) for m in mods))
@@ -281,20 +287,48 @@ class _Group:
                 self.slots.append((j, m, ro, r, index_of[id(m.lora_A)], index_of[id(m.lora_B)]))
                 ro += r
 
+    def _xd(self, x):
+        """The input of the low-rank path: x, or dropout(x) in training (mask re-derived from the seed in backward)."""
+        if self.drop is None:
+            return x
+        p, seed, salt = self.drop
+        return ops.lora_dropout(x, p, seed, salt)
+
     def _t(self, x):
-        t = ops.gemm(x, self.A_cat, alpha=self.s if self.s is not None else 1.0)                # [N, R]
+        s = self.s if self.s is not None else 1.0
+        if not self.bias:
+            t = ops.gemm(self._xd(x), self.A_cat, alpha=s)                                       # [N, R]
+            if self.rows is not None:
+                ops.lora_mask_rows_(t, self.rows, self.rank, self.K)
+            return t
+        # LoRA bias (lora.py:66,101-102: y += lora_bias, unscaled): one more tail column — t gets a column of ones and
+        # the tail operand the bias values, so the bias add rides in the same GEMM and its gradient (column sums of dy)
+        # falls out of the dB GEMM.  Eight columns are appended to keep the 16-byte row alignment.
         if self.rows is not None:
-            ops.lora_mask_rows_(t, self.rows, self.rank, self.K)
+            raise RuntimeError("lora_use_bias is not supported together with several adapters per projection")
+        R = self.R
+        t = torch.zeros(x.shape[0], R + 8, dtype=x.dtype, device=x.device)
+        ops.gemm(self._xd(x), self.A_cat, alpha=s, out=t[:, :R])
+        t[:, R].fill_(1.0)
+        Bx = torch.zeros(self.n_out, R + 8, dtype=x.dtype, device=x.device)
+        Bx[:, :R].copy_(self.B_bd)
+        for j, m in self.bias:
+            Bx[self.offs[j]:self.offs[j] + m.weight.shape[0], R].copy_(m.lora_bias.detach())
+        self.B_ext = Bx
         return t
 
-    def fwd(self, x, rope=None):
+    @property
+    def b2(self):
+        return self.B_ext if self.bias else self.B_bd
+
+    def fwd(self, x, rope=None, residual=None, out_dtype=BF16):
         """rope = (cache, seq_len, rope_cols, head_dim[, positions int32 [N]]): rotate the leading columns in the GEMM's
         store epilogue (positions: sequence packing, they restart with every packed sample)."""
         t = self._t(x) if self.lora else None
-        b2 = self.B_bd if self.lora else None
+        b2 = self.b2 if self.lora else None
         if rope is not None:
             return ops.gemm_rope(x, self.W, *rope[:4], a2=t, b2=b2, positions=rope[4] if len(rope) > 4 else None), t
-        return ops.gemm(x, self.W, a2=t, b2=b2), t
+        return ops.gemm(x, self.W, a2=t, b2=b2, residual=residual, out_dtype=out_dtype), t
 
     def fwd_swiglu(self, x):
         """gate/up group only: (gate|up, act = silu(gate) * up, t) with the SwiGLU in the GEMM epilogue."""
@@ -302,7 +336,7 @@ class _Group:
             gu, act = ops.gemm_swiglu_fwd(x, self.W)
             return gu, act, None
         t = self._t(x)
-        gu, act = ops.gemm_swiglu_fwd(x, self.W, a2=t, b2=self.B_bd)
+        gu, act = ops.gemm_swiglu_fwd(x, self.W, a2=t, b2=self.b2)
         return gu, act, t
 
     def bwd(self, dy, x, t, grads, need, sink=None, written=None):
@@ -323,18 +357,28 @@ class _Group:
         # with the common scaling s folded into t and dts:  y = x W^T + t B^T,  t = s x A^T
         #   dB = dy^T t,   dts = s dy B,   dA = dts^T x,   dx = dy W + dts A
         s = self.s if self.s is not None else 1.0
-        dts = ops.gemm(dy, self.B_bd, trans_b=True, alpha=s)           # [N, R]
+        dts = ops.gemm(dy, self.b2, trans_b=True, alpha=s)             # [N, R (+8 with the bias column)]
+        if self.bias:
+            dts = dts[:, :self.R]                                      # the ones column is not a function of x
         if self.rows is not None:
             ops.lora_mask_rows_(dts, self.rows, self.rank, self.K)
-        if any(need[iB] for *_, iB in self.slots):
-            dB = ops.gemm(dy, t, trans_a=True, trans_b=True)          # dy^T t       [n_out, R]
+        if any(need[iB] for *_, iB in self.slots) or self.bias:
+            dB = ops.gemm(dy, t, trans_a=True, trans_b=True)          # dy^T t       [n_out, R (+8)]
+            for j, m in self.bias:
+                if need[self.ib[j]]:
+                    _acc(grads, self.ib[j], dB[self.offs[j]:self.offs[j] + m.weight.shape[0], self.R].contiguous())
+        xd = self._xd(x)                                              # same seed -> same dropout mask as the forward
         if any(need[iA] for *_, iA, _ in self.slots):
-            dA = ops.gemm(dts, x, trans_a=True, trans_b=True)         # dts^T x      [R, in]
+            dA = ops.gemm(dts, xd, trans_a=True, trans_b=True)        # dts^T x      [R, in]
         for j, m, ro, r, iA, iB in self.slots:
             if need[iB]:
                 blk = dB[self.offs[j]:self.offs[j] + m.weight.shape[0], ro:ro + r]
-                if self.views:
-                    _acc(grads, iB, blk)          # row-strided like the parameter itself: no copy
+                if self.views and m.lora_B.grad is None and not torch.is_grad_enabled():
+                    # row-strided like the parameter itself.  Handed to the parameter directly: returned through
+                    # autograd, AccumulateGrad would clone it into a dense tensor (one copy kernel per adapter)
+                    m.lora_B.grad = blk
+                elif self.views:
+                    _acc(grads, iB, blk)
                 else:
                     _acc(grads, iB, blk.contiguous() if self.s is not None else
                          (blk * float(m.lora_scaling)).contiguous())
@@ -367,11 +411,24 @@ class StackFn(Function):
         cur = x.reshape(N, D).contiguous()
         res_dtype = torch.float32 if FP32_RESIDUAL else BF16       # dtype of h / out (cur is bf16 for layer 0 only)
         saved = []
-        for layer in stack.layers:
+        # LoRA options of the reference's LoRALinear (lora.py:87-90,101-102): input dropout (training only) and a bias
+        p_drop = float(getattr(stack, "lora_dropout", 0.0)) if stack.training else 0.0
+        seed = getattr(stack, "_lora_seed", None)
+        if p_drop > 0.0 and (seed is None or seed.device != x.device):
+            seed = stack._lora_seed = torch.zeros(1, dtype=torch.int64, device=x.device)
+        if p_drop > 0.0:
+            seed.add_(1)                                           # a fresh mask every step, also under graph replay
+
+        def lin(mod, salt):
+            if getattr(mod, "lora_A", None) is not None and (p_drop > 0.0 or getattr(mod, "lora_bias", None) is not None):
+                return _Group([mod], index_of, stack._packed, rows, (p_drop, seed, salt))
+            return _Lin(mod, index_of, rows)
+
+        for li, layer in enumerate(stack.layers):
             a = layer.attn
-            gqkv = _Group([a.q_proj, a.k_proj, a.v_proj], index_of, stack._packed, rows)
-            g13 = _Group([layer.mlp.w1, layer.mlp.w3], index_of, stack._packed, rows)
-            lo, l2 = _Lin(a.output_proj, index_of, rows), _Lin(layer.mlp.w2, index_of, rows)
+            gqkv = _Group([a.q_proj, a.k_proj, a.v_proj], index_of, stack._packed, rows, (p_drop, seed, 4 * li))
+            g13 = _Group([layer.mlp.w1, layer.mlp.w3], index_of, stack._packed, rows, (p_drop, seed, 4 * li + 1))
+            lo, l2 = lin(a.output_proj, 4 * li + 2), lin(layer.mlp.w2, 4 * li + 3)
             I = layer.mlp.w1.weight.shape[0]
             xn, rstd1 = ops.rmsnorm(cur, layer.sa_norm.scale, eps)
             qkv, tqkv = gqkv.fwd(xn, rope=(cache, S, nq + nkv, hd, pos_rows))   # q, k rotated in the store epilogue
@@ -442,7 +499,7 @@ class StackFn(Function):
             gqkv, lo, g13, l2 = lins
             I = gu.shape[1] // 2
             # ---- MLP: out = h + w2(silu(w1 hn) * w3 hn)
-            if FUSE_SWIGLU_BWD and ops.swiglu_fusable(N, I, D):
+            if FUSE_SWIGLU_BWD and isinstance(l2, _Lin) and ops.swiglu_fusable(N, I, D):
                 dgu = l2.bwd(dcur, act, t2, grads, need, swiglu_gu=gu, sink=sink, written=written)
             else:
                 dact = l2.bwd(dcur, act, t2, grads, need, sink=sink, written=written)

@@ -25,7 +25,8 @@ DEFAULT_TARGETS = ["q_proj", "v_proj"]          # lora.py:801-803
 
 def apply_lora(model: nn.Module, r: int = 8, alpha: float = 16.0, target_modules: Optional[Sequence[str]] = None,
                target_layers: Optional[Iterable[int]] = None, seed: Optional[int] = None,
-               b_std: float = 0.0, num_adapters=1, target_decoder_layers: Optional[Iterable[int]] = None) -> List[str]:
+               b_std: float = 0.0, num_adapters=1, target_decoder_layers: Optional[Iterable[int]] = None,
+               dropout: float = 0.0, use_bias: bool = False) -> List[str]:
     """Freezes every base parameter and adds adapters (A ~ N(0, 1/sqrt(in)), B = 0 as lora.py:62-66; ``b_std`` > 0
     draws B ~ N(0, b_std) for gradient-parity tests, since B = 0 makes dA identically 0).
 
@@ -34,7 +35,12 @@ def apply_lora(model: nn.Module, r: int = 8, alpha: float = 16.0, target_modules
     ``lora_A`` [K*r, in] (rows k*r..(k+1)*r = adapter k), ``lora_B`` [out, K*r] — and ride in ONE base GEMM; each row
     of the batch keeps only its own adapter's block of t = x A^T (csm_lora_mask_rows).  ``target_layers`` filters the
     backbone layers (and the decoder's too unless ``target_decoder_layers`` is given), like
-    target_backbone_layers / target_decoder_layers of the reference."""
+    target_backbone_layers / target_decoder_layers of the reference.
+    ``dropout`` (lora.py:87-90): the low-rank path sees dropout(x, p) in training mode — a stateless hashed mask
+    (csm_lora_dropout), re-derived in the backward.  ``use_bias`` (lora.py:66,101-102): a trainable ``lora_bias`` [out]
+    per adapted projection, added unscaled; it rides in the base GEMM as one more tail column."""
+    if not 0.0 <= dropout < 1.0:
+        raise ValueError("lora dropout must be in [0, 1)")
     if r < 1 or r > 64:
         raise ValueError("lora_r must be in [1, 64]")
     if isinstance(num_adapters, int):
@@ -59,6 +65,7 @@ def apply_lora(model: nn.Module, r: int = 8, alpha: float = 16.0, target_modules
         if K < 1:
             raise ValueError("num_adapters must be >= 1")
         stack.lora_adapters = K
+        stack.lora_dropout = float(dropout)
         for li, layer in enumerate(stack.layers):
             if layers_filter[stack_name] is not None and li not in layers_filter[stack_name]:
                 continue
@@ -73,12 +80,17 @@ def apply_lora(model: nn.Module, r: int = 8, alpha: float = 16.0, target_modules
                 lin.register_parameter("lora_B", nn.Parameter(B.to(device=w.device, dtype=w.dtype)))
                 lin.lora_scaling = alpha / r           # lora.py:52-53
                 lin.lora_r, lin.lora_alpha, lin.lora_adapters = r, alpha, K
+                if use_bias:
+                    if K > 1:
+                        raise ValueError("lora_use_bias is not supported with several adapters per projection")
+                    lin.register_parameter("lora_bias", nn.Parameter(torch.zeros(lin.out_features, device=w.device,
+                                                                                 dtype=w.dtype)))
                 names.append(f"{stack_name}.layers.{li}.{parent_name}.{child}")
     return names
 
 
 def lora_state_dict(model: nn.Module) -> Dict[str, torch.Tensor]:
-    return {n: p.detach() for n, p in model.named_parameters() if n.endswith(("lora_A", "lora_B"))}
+    return {n: p.detach() for n, p in model.named_parameters() if n.endswith(("lora_A", "lora_B", "lora_bias"))}
 
 
 def adapter_slices(mod: nn.Module, k: int):

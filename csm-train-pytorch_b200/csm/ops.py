@@ -340,6 +340,7 @@ def swiglu_fusable(M: int, inter: int, K: int) -> bool:
 def gemm_swiglu_fwd(x, w13, *, a2=None, b2=None):
     """x [M,K], w13 = [w1; w3] [2I,K] -> (gate_up bf16 [M,2I], act bf16 [M,I]) ; optional LoRA tail a2 [M,r], b2 [2I,r]."""
     _chk_cuda(x, w13, a2, b2)
+    _ensure_streamk_workspace(x.device)
     M, K = x.shape
     inter = w13.shape[0] // 2
     gu = torch.empty(M, 2 * inter, dtype=BF16, device=x.device)
@@ -470,6 +471,7 @@ def linear_ce_fwd(h, w, targets, *, trans_w: bool = False, groups: int = 1, tgt_
     """Returns (loss_rows fp32 [groups, M], lse fp32 [groups, M]).  `targets` is an int64 tensor whose element
     for (group g, row m) sits at offset m*tgt_row_stride + g*tgt_group_stride from its data pointer."""
     _chk_cuda(h, w, targets)
+    _ensure_streamk_workspace(h.device)       # (holds the arrival counters of the fused combine)
     M, V, K, ldh, hgs, ldw, wgs = _ce_geometry(h, w, trans_w, groups)
     lib = _lib.load()
     nbytes = lib.csm_linear_ce_workspace_bytes(M, V, K, groups)
@@ -487,6 +489,7 @@ def linear_ce_bwd(h, w, targets, lse, grad_scale: float, *, dh: torch.Tensor, gr
                   dw_accumulate: bool = False, trans_w: bool = False, groups: int = 1, tgt_row_stride: int = 1,
                   tgt_group_stride: int = 0, backend: Optional[int] = None):
     _chk_cuda(h, w, targets, lse, dh, dw, grad_scale_dev)
+    _ensure_streamk_workspace(h.device)
     M, V, K, ldh, hgs, ldw, wgs = _ce_geometry(h, w, trans_w, groups)
     lib = _lib.load()
     nbytes = lib.csm_linear_ce_workspace_bytes(M, V, K, groups)
@@ -512,6 +515,17 @@ def lora_mask_rows_(t, adapter_ids, rank: int, adapters: int):
     _lib.check(lib.csm_lora_mask_rows(_p(t), t.stride(0), t.shape[0], t.shape[1], _p(adapter_ids), rank, adapters,
                                       _st()), "lora_mask_rows")
     return t
+
+
+def lora_dropout(x, p: float, seed_dev, salt: int, out=None, accumulate: bool = False):
+    """out (=|+=) x o keep / (1 - p) with the stateless mask hash(seed_dev[0], salt, index) >= p (x, out: bf16 2-D)."""
+    _chk_cuda(x, seed_dev, out)
+    assert x.dim() == 2 and x.stride(1) == 1 and seed_dev.dtype == torch.int64
+    out = torch.empty(x.shape, dtype=BF16, device=x.device) if out is None else out
+    lib = _lib.load()
+    _lib.check(lib.csm_lora_dropout(_p(x), _p(out), x.shape[0], x.shape[1], x.stride(0), out.stride(0), float(p),
+                                    _p(seed_dev), int(salt), 1 if accumulate else 0, _st()), "lora_dropout")
+    return out
 
 
 # ----------------------------------------------------------------------------- helpers

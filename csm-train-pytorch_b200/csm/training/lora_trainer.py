@@ -29,10 +29,8 @@ class CSMLoRATrainer:
                  target_modules: Optional[List[str]] = None, target_layers: Optional[List[int]] = None,
                  lora_use_bias: bool = False, *, model: Optional[Model] = None, device: str = "cuda",
                  num_adapters=1, target_decoder_layers: Optional[List[int]] = None):
-        if lora_dropout != 0.0:
-            raise NotImplementedError("lora_dropout > 0 is not implemented in the fused LoRA GEMM")
-        if lora_use_bias:
-            raise NotImplementedError("lora_use_bias is not implemented (all CSM projections are bias-free)")
+        if not 0.0 <= lora_dropout < 1.0:
+            raise ValueError("lora_dropout must be in [0, 1)")
         self.model_path = model_path
         self.output_dir = Path(output_dir)
         self.output_dir.mkdir(parents=True, exist_ok=True)
@@ -75,14 +73,15 @@ class CSMLoRATrainer:
         self.model = self.model.to(torch.bfloat16).to(self.device)
         self.lora_names = lora_mod.apply_lora(self.model, self.lora_r, self.lora_alpha, self.target_modules,
                                               self.target_layers, num_adapters=self.num_adapters,
-                                              target_decoder_layers=self.target_decoder_layers)
+                                              target_decoder_layers=self.target_decoder_layers,
+                                              dropout=self.lora_dropout, use_bias=self.lora_use_bias)
 
     def set_model(self, model: Model):
         self.model = model
         self._load_model_with_lora()
 
     def get_lora_params(self) -> Dict[str, torch.nn.Parameter]:
-        return {n: p for n, p in self.model.named_parameters() if n.endswith(("lora_A", "lora_B"))}
+        return {n: p for n, p in self.model.named_parameters() if n.endswith(("lora_A", "lora_B", "lora_bias"))}
 
     def prepare_optimizer(self):
         params = list(self.get_lora_params().values())
@@ -191,7 +190,7 @@ class CSMLoRATrainer:
             merged = {}
             adapters = {n.rsplit(".", 1)[0] for n in self.get_lora_params()}
             for n, p in self.model.named_parameters():
-                if n.endswith(("lora_A", "lora_B")):
+                if n.endswith(("lora_A", "lora_B", "lora_bias")):
                     continue
                 t = p.detach()
                 mod_name = n.rsplit(".", 1)[0]

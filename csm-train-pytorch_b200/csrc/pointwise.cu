@@ -350,6 +350,38 @@ static inline unsigned grid_for(int64_t work_items, int threads, int max_waves =
 
 using namespace csm;
 
+// LoRA input dropout (reference lora.py:87-90: x_for_lora = dropout(x, p)): out = (accumulate ? out : 0) + x o keep / (1 - p).
+// The keep mask is a counter-based hash of (seed, salt, element index) — nothing is stored: the backward calls the same
+// kernel with the same seed to re-apply the mask (to x for dA, to dts A for dx).  The seed lives in DEVICE memory (the
+// trainer bumps it once per step), so a replayed CUDA graph draws a fresh mask every step.
+__device__ __forceinline__ uint32_t lora_hash(uint64_t key, uint64_t idx) {
+  uint64_t z = key + idx * 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return (uint32_t)((z ^ (z >> 31)) >> 32);
+}
+
+__global__ void __launch_bounds__(256)
+lora_dropout_kernel(const bf16* __restrict__ x, bf16* __restrict__ out, int64_t rows, int64_t cols, int64_t ldx,
+                    int64_t ldo, float p, const int64_t* __restrict__ seed, int64_t salt, int accumulate) {
+  const uint64_t key = ((uint64_t)(*seed) * 0xD1342543DE82EF95ull) ^ ((uint64_t)salt * 0xA0761D6478BD642Full);
+  const uint32_t thresh = (uint32_t)fminf(p * 4294967296.f, 4294967295.f);
+  const float inv = 1.f / (1.f - p);
+  const int64_t vc = cols / 8, total = rows * vc;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / vc, c = (i % vc) * 8;
+    float f[8], o[8];
+    unpack8(*reinterpret_cast<const uint4*>(x + r * ldx + c), f);
+    if (accumulate) unpack8(*reinterpret_cast<const uint4*>(out + r * ldo + c), o);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float v = lora_hash(key, (uint64_t)(r * cols + c + j)) >= thresh ? f[j] * inv : 0.f;
+      o[j] = accumulate ? o[j] + v : v;
+    }
+    *reinterpret_cast<uint4*>(out + r * ldo + c) = pack8(o);
+  }
+}
+
 // Multi-adapter LoRA (several speakers' adapters side by side in one low-rank tail): t [rows, cols]
 // holds, per adapted projection, `adapters` blocks of `rank` columns; a row keeps only the block of ITS adapter
 // (ids[row]; a negative id keeps nothing: base model only).  Applied to t = s x A^T after the skinny GEMM and to
@@ -493,5 +525,19 @@ extern "C" int csm_lora_mask_rows(void* t, int64_t ldt, int64_t rows, int32_t co
   const unsigned grid = (unsigned)((total + 255) / 256 < (int64_t)num_sms() * 8 ? (total + 255) / 256 : (int64_t)num_sms() * 8);
   lora_mask_rows_kernel<<<grid, 256, 0, as_stream(stream)>>>((bf16*)t, ldt, rows, cols, adapter_ids, rank, adapters);
   CSM_CHECK_LAUNCH("lora_mask_rows");
+  return CSM_OK;
+}
+
+
+extern "C" int csm_lora_dropout(const void* x, void* out, int64_t rows, int64_t cols, int64_t ldx, int64_t ldo, float p,
+                                const int64_t* seed_dev, int64_t salt, int32_t accumulate, csm_stream_t stream) {
+  CSM_REQUIRE(rows >= 0 && cols > 0 && cols % 8 == 0 && ldx % 8 == 0 && ldo % 8 == 0 && p >= 0.f && p < 1.f && seed_dev,
+              CSM_ERR_SHAPE, "lora_dropout: cols / strides must be multiples of 8 and 0 <= p < 1");
+  CSM_REQUIRE(aligned16(x) && aligned16(out), CSM_ERR_ALIGN, "lora_dropout: misaligned pointer");
+  if (rows == 0) return CSM_OK;
+  const int64_t total = rows * (cols / 8);
+  lora_dropout_kernel<<<grid_for(total, 256), 256, 0, as_stream(stream)>>>((const bf16*)x, (bf16*)out, rows, cols, ldx,
+                                                                          ldo, p, seed_dev, salt, accumulate);
+  CSM_CHECK_LAUNCH("lora_dropout");
   return CSM_OK;
 }

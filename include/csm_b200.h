@@ -280,6 +280,12 @@ int csm_attn_decode(const void* q, const void* k_cache, const void* v_cache, voi
 int csm_lora_mask_rows(void* t, int64_t ldt, int64_t rows, int32_t cols, const int32_t* adapter_ids, int32_t rank,
                        int32_t adapters, csm_stream_t stream);
 
+/* ---- LoRA input dropout (lora.py:87-90): out[rows, cols] (=|+=) x o keep / (1 - p), keep = hash(*seed_dev, salt, element
+ * index) >= p.  Stateless: the backward re-applies the same mask by calling again with the same seed and salt (to x for
+ * dA, to dts A — accumulated into dx — for the input gradient).  seed_dev: int64 in device memory (bumped per step). */
+int csm_lora_dropout(const void* x, void* out, int64_t rows, int64_t cols, int64_t ldx, int64_t ldo, float p,
+                     const int64_t* seed_dev, int64_t salt, int32_t accumulate, csm_stream_t stream);
+
 /* ---- small helpers used by the training step */
 /* dst_bf16[i] (=|+=) src_f32[i] * scale */
 int csm_f32_to_bf16(const float* src, void* dst, int64_t n, float scale, int32_t accumulate, csm_stream_t stream);

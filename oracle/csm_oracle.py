@@ -207,17 +207,23 @@ def init_weights(model: nn.Module, seed: int = 0, std: float = 0.02) -> None:
 class LoRALinear(nn.Module):
     """y = x W0^T + (alpha/r) (x A^T) B^T  — lora.py:82-105; A [r,in], B [out,r]."""
 
-    def __init__(self, base: nn.Linear, r: int, alpha: float):
+    def __init__(self, base: nn.Linear, r: int, alpha: float, use_bias: bool = False):
         super().__init__()
         self.weight = base.weight
         self.weight.requires_grad_(False)
         self.r, self.alpha, self.scaling = r, alpha, alpha / r
         self.lora_A = nn.Parameter(torch.zeros(r, base.in_features, dtype=base.weight.dtype))
         self.lora_B = nn.Parameter(torch.zeros(base.out_features, r, dtype=base.weight.dtype))
+        if use_bias:                                              # lora.py:66: optional LoRA bias, added unscaled (:101-102)
+            self.lora_bias = nn.Parameter(torch.zeros(base.out_features, dtype=base.weight.dtype))
+        self.keep = None          # test aid: a fixed dropout mask / (1 - p) for the low-rank path's input (lora.py:87-90)
 
     def forward(self, x):
         base = F.linear(x, self.weight)
-        lo = F.linear(F.linear(x, self.lora_A), self.lora_B) * self.scaling
+        xl = x if self.keep is None else x * self.keep.to(x.dtype).view(x.shape)
+        lo = F.linear(F.linear(xl, self.lora_A), self.lora_B) * self.scaling
+        if hasattr(self, "lora_bias"):
+            lo = lo + self.lora_bias
         return base + lo
 
 
@@ -228,7 +234,7 @@ _TARGETS = {"q_proj": ("attn", "q_proj"), "k_proj": ("attn", "k_proj"), "v_proj"
 
 def apply_lora(model: nn.Module, r: int = 8, alpha: float = 16.0,
                target_modules: Optional[Sequence[str]] = None, seed: int = 1,
-               b_std: float = 0.02) -> List[str]:
+               b_std: float = 0.02, use_bias: bool = False) -> List[str]:
     """lora.py:741-827 semantics: adapters on the chosen projections of backbone AND decoder;
     everything else frozen.  A ~ N(0, 1/sqrt(in)) (lora.py:62-65); B ~ N(0, b_std) — the reference
     initialises B=0 (lora.py:66), which makes every dA exactly 0, so parity runs use b_std>0
@@ -245,11 +251,13 @@ def apply_lora(model: nn.Module, r: int = 8, alpha: float = 16.0,
                 parent_name, child = _TARGETS[t]
                 parent = getattr(layer, parent_name)
                 base = getattr(parent, child)
-                lin = LoRALinear(base, r, alpha)
+                lin = LoRALinear(base, r, alpha, use_bias)
                 with torch.no_grad():
                     lin.lora_A.copy_((torch.randn(lin.lora_A.shape, generator=g) /
                                       math.sqrt(base.in_features)).to(lin.lora_A.dtype))
                     lin.lora_B.copy_((torch.randn(lin.lora_B.shape, generator=g) * b_std).to(lin.lora_B.dtype))
+                    if use_bias:                                  # non-zero so that the parity run exercises it
+                        lin.lora_bias.copy_((torch.randn(lin.lora_bias.shape, generator=g) * b_std).to(lin.lora_bias.dtype))
                 setattr(parent, child, lin)
                 names.append(f"{stack_name}.layers.{li}.{parent_name}.{child}")
     return names

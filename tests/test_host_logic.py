@@ -222,12 +222,23 @@ def test_checkpoint_roundtrip_format(tmp_path):
     assert torch.equal(m2.audio_head, m.audio_head)
 
 
-def test_lora_trainer_rejects_unimplemented_options(tmp_path):
+def test_lora_trainer_dropout_and_bias_options(tmp_path):
+    """lora_dropout / lora_use_bias (lora_trainer.py:42-47, lora.py:87-90,101-102) are constructor arguments of the API:
+    accepted, validated, and they shape the adapters (a ``lora_bias`` [out] per projection; the stack's dropout rate)."""
+    from csm.models import lora
+    from csm.models.model import Model, ModelArgs
     from csm.training.lora_trainer import CSMLoRATrainer
-    with pytest.raises(NotImplementedError):
-        CSMLoRATrainer("", str(tmp_path), lora_dropout=0.1)
-    with pytest.raises(NotImplementedError):
-        CSMLoRATrainer("", str(tmp_path), lora_use_bias=True)
+    with pytest.raises(ValueError):
+        CSMLoRATrainer("", str(tmp_path), lora_dropout=1.5)
+    m = Model(ModelArgs("tiny-backbone", "tiny-decoder", 1000, 200, 32))
+    t = CSMLoRATrainer("", str(tmp_path), lora_dropout=0.1, lora_use_bias=True, model=m, device="cpu")
+    names = set(t.get_lora_params())
+    assert "backbone.layers.0.attn.q_proj.lora_bias" in names and "decoder.layers.0.attn.v_proj.lora_bias" in names
+    assert m.backbone.layers[0].attn.q_proj.lora_bias.shape == (32,) and m.backbone.lora_dropout == 0.1
+    assert float(m.backbone.layers[0].attn.q_proj.lora_bias.abs().sum()) == 0.0          # zeros, lora.py:66
+    assert set(lora.lora_state_dict(m)) == names
+    with pytest.raises(ValueError):
+        lora.apply_lora(m, use_bias=True, num_adapters=2)
 
 
 def test_rope_table_matches_oracle():

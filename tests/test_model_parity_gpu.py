@@ -411,6 +411,61 @@ def test_sequence_packing_equals_running_every_sample_alone(cuda):
              segment_ends=dev["segment_ends"])
 
 
+@pytest.mark.parametrize("p_drop,use_bias", [(0.0, True), (0.25, False), (0.1, True)])
+def test_lora_dropout_and_bias_match_oracle(cuda, p_drop, use_bias):
+    """The two remaining options of the reference's LoRALinear (lora.py:87-90 dropout on the low-rank path's input,
+    :66,101-102 a LoRA bias), r=8 on all seven projections of the small model.  Dropout masks are stateless hashes:
+    the test regenerates the very masks the kernels will use (same seed / salt) and hands them to the oracle, so losses
+    and every gradient — lora_A, lora_B, lora_bias — are compared exactly like in the other parity tests; in eval mode
+    dropout is off."""
+    from csm import ops
+    from csm.models import lora as plora
+    from oracle import csm_oracle as O
+    prod, cfg = _product_model("small")
+    orc = O.OracleModel(cfg)
+    O.init_weights(orc, 0)
+    orc, prod = orc.to(torch.bfloat16), prod.to(torch.bfloat16)
+    targets = ["q_proj", "k_proj", "v_proj", "o_proj", "gate_proj", "up_proj", "down_proj"]
+    O.apply_lora(orc, r=8, alpha=16.0, target_modules=targets, seed=1, use_bias=use_bias)
+    plora.apply_lora(prod, r=8, alpha=16.0, target_modules=targets, seed=4, dropout=p_drop, use_bias=use_bias)
+    prod.load_state_dict(orc.state_dict(), strict=True)
+    prod = prod.to(cuda).train()
+    B, S = 2, 128
+    batch = O.synthetic_batch(cfg, B, S, seed=77)
+    tok, msk, tgt, fidx = (batch[k] for k in ("input_tokens", "input_masks", "target_audio_tokens", "frame_idx"))
+    if p_drop > 0:
+        seed = torch.ones(1, dtype=torch.int64, device=cuda)                  # the value of the first training forward
+        C = cfg.audio_num_codebooks
+        for stack, rows, shape3 in ((orc.backbone, B * S, (B, S)), (orc.decoder, fidx.shape[0] * C, (fidx.shape[0], C))):
+            for li, layer in enumerate(stack.layers):
+                a, f = layer.attn, layer.mlp
+                for salt, mods in ((4 * li, (a.q_proj, a.k_proj, a.v_proj)), (4 * li + 1, (f.w1, f.w3)),
+                                   (4 * li + 2, (a.output_proj,)), (4 * li + 3, (f.w2,))):
+                    ones = torch.ones(rows, mods[0].weight.shape[1], dtype=torch.bfloat16, device=cuda)
+                    keep = ops.lora_dropout(ones, p_drop, seed, salt).float().cpu()
+                    frac = float((keep > 0).float().mean())
+                    assert abs(frac - (1 - p_drop)) < 0.02 and abs(float(keep.max()) - 1 / (1 - p_drop)) < 1e-2
+                    for m in mods:
+                        m.keep = keep.view(*shape3, -1)
+    ol, od = O.oracle_forward(orc, tok, msk, tgt, fidx)
+    ol.backward()
+    pl, pd = prod(tok.to(cuda), msk.to(cuda), tgt.to(cuda), frame_idx=fidx.to(cuda))
+    pl.backward()
+    torch.cuda.synchronize()
+    _check(orc, prod, (ol.detach(), od), (pl.detach(), pd))
+    if use_bias:
+        assert prod.backbone.layers[0].attn.q_proj.lora_bias.grad is not None
+    if p_drop > 0:
+        prod.eval()
+        for m in orc.modules():
+            if isinstance(m, O.LoRALinear):
+                m.keep = None
+        with torch.no_grad():
+            pe, _ = prod(tok.to(cuda), msk.to(cuda), tgt.to(cuda), frame_idx=fidx.to(cuda))
+            oe, _ = O.oracle_forward(orc, tok, msk, tgt, fidx)
+        assert abs(float(pe) - float(oe)) <= LOSS_RTOL * abs(float(oe)) and float(pe) != float(pl)
+
+
 def test_no_cpu_fallback():
     from csm.models.model import Model, ModelArgs
     m = Model(ModelArgs("tiny-backbone", "tiny-decoder", 1000, 200, 32)).to(torch.bfloat16)

@@ -25,7 +25,7 @@ for r in rows:
     recs.append((d["Kernel Name"], d.get("Grid Size"), d.get("Block Size"), v_us))
 starts = [i for i, r in enumerate(recs) if "embed_gather_sum_fwd" in r[0]]
 if len(starts) >= 2:
-    recs = recs[starts[0]:starts[1]]
+    recs = recs[starts[-2]:starts[-1]]          # the last complete step (the first ones pack weights / create state)
 agg = collections.OrderedDict()
 for name, grid, block, us in recs:
     key = re.sub(r"\(.*", "", name)
