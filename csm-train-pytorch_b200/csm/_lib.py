@@ -43,7 +43,6 @@ SIGNATURES = {
     "csm_set_attn_fwd_variant": (None, [_i32]),
     "csm_set_gemm_cta_pair_mode": (None, [_i32]),
     "csm_set_gemm_dynamic_tiles": (None, [_i32]),
-    "csm_set_ce_fused_combine": (None, [_i32]),
     "csm_set_reserved_sms": (None, [_i32]),
     "csm_gemm_streamk_workspace_bytes": (_sz, []),
     "csm_gemm_set_streamk_workspace": (None, [_ptr, _sz]),

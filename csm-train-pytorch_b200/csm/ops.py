@@ -49,11 +49,6 @@ def set_gemm_dynamic_tiles(m: int) -> None:
     _lib.load().csm_set_gemm_dynamic_tiles(m)
 
 
-def set_ce_fused_combine(m: int) -> None:
-    """A/B hook: fused-CE forward combines its partials in the last tile's epilogue (1, default) or in a second kernel."""
-    _lib.load().csm_set_ce_fused_combine(m)
-
-
 _attn_backend = 0
 
 
@@ -471,7 +466,7 @@ def linear_ce_fwd(h, w, targets, *, trans_w: bool = False, groups: int = 1, tgt_
     """Returns (loss_rows fp32 [groups, M], lse fp32 [groups, M]).  `targets` is an int64 tensor whose element
     for (group g, row m) sits at offset m*tgt_row_stride + g*tgt_group_stride from its data pointer."""
     _chk_cuda(h, w, targets)
-    _ensure_streamk_workspace(h.device)       # (holds the arrival counters of the fused combine)
+    _ensure_streamk_workspace(h.device)
     M, V, K, ldh, hgs, ldw, wgs = _ce_geometry(h, w, trans_w, groups)
     lib = _lib.load()
     nbytes = lib.csm_linear_ce_workspace_bytes(M, V, K, groups)

@@ -122,7 +122,6 @@ void gemm_tc_set_streamk_workspace(void* ptr, size_t bytes);
 void gemm_tc_set_streamk_mode(int m);
 void gemm_tc_set_narrow_tail_mode(int m);
 void gemm_tc_set_dynamic_tiles(int m);
-void gemm_tc_set_ce_fused_combine(int m);
 }  // namespace csm
 extern "C" size_t csm_gemm_streamk_workspace_bytes(void) { return csm::gemm_tc_streamk_workspace_bytes(); }
 extern "C" void csm_gemm_set_streamk_workspace(void* workspace, size_t bytes) {
@@ -132,7 +131,6 @@ extern "C" void csm_set_gemm_streamk_mode(int32_t mode) { csm::gemm_tc_set_strea
 extern "C" void csm_set_gemm_narrow_tail_mode(int32_t mode) { csm::gemm_tc_set_narrow_tail_mode(mode); }
 extern "C" void csm_set_gemm_cta_pair_mode(int32_t mode) { csm::gemm_tc_set_cta_pair_mode(mode); }
 extern "C" void csm_set_gemm_dynamic_tiles(int32_t mode) { csm::gemm_tc_set_dynamic_tiles(mode); }
-extern "C" void csm_set_ce_fused_combine(int32_t mode) { csm::gemm_tc_set_ce_fused_combine(mode); }
 extern "C" const char* csm_last_error(void) { return g_err; }
 extern "C" int64_t csm_launch_count(void) { return g_launches.load(); }
 

@@ -69,10 +69,6 @@ struct GemmTcParams {
   const int64_t* targets; int64_t tgt_row_stride, tgt_group_stride;
   float4* ce_part;          // [groups*M, num_n]
   const float* lse; float gscale; const float* gscale_dev;
-  // EPI_CE_PARTIAL with the combine fused in: the epilogue warp that delivers the LAST column tile of its 32 rows
-  // (self-resetting arrival counter per (group, m-block, lane quadrant)) merges the num_n partials of those rows and
-  // writes loss / lse itself — no second kernel, no launch gap (12 of 50 us at decoder sizes).  nullptr: separate kernel.
-  int* ce_cnt; float* ce_loss; float* ce_lse;
 };
 
 // kCta2: CTA-pair mode (cluster of 2, tcgen05 cta_group::2).  The pair computes a 256 x BN tile: each CTA keeps its
@@ -736,32 +732,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           mx = nm;
         }
         if (row_ok) p.ce_part[((int64_t)g * p.M + m) * p.num_n + nb] = make_float4(mx, se, tl, 0.f);
-        if (p.ce_cnt) {
-          __threadfence();                                   // this warp's partials are visible before it is counted
-          __syncwarp();
-          int* cnt = p.ce_cnt + ((int64_t)g * p.num_m + mb) * 4 + quad;
-          int prev = 0;
-          if (lane == 0) prev = atomicAdd(cnt, 1);
-          prev = __shfl_sync(0xffffffffu, prev, 0);
-          if (prev == p.num_n - 1) {                         // every column tile of these 32 rows has been delivered
-            __threadfence();
-            if (row_ok) {
-              const float4* pr = p.ce_part + ((int64_t)g * p.M + m) * p.num_n;
-              float gm = -INFINITY;
-              for (int t = 0; t < p.num_n; ++t) gm = fmaxf(gm, __ldcg(&pr[t]).x);
-              float s = 0.f, tlg = -INFINITY;
-              for (int t = 0; t < p.num_n; ++t) {
-                const float4 q = __ldcg(&pr[t]);
-                s += q.y * __expf(q.x - gm);
-                tlg = fmaxf(tlg, q.z);
-              }
-              const float L = gm + logf(s);
-              p.ce_lse[(int64_t)g * p.M + m] = L;
-              p.ce_loss[(int64_t)g * p.M + m] = (tlg == -INFINITY) ? 0.f : L - tlg;   // no tile saw the target: ignored row
-            }
-            if (lane == 0) *cnt = 0;                         // re-armed for the next launch
-          }
-        }
       } else {  // EPI_CE_DLOGITS: bf16 gscale * (softmax - onehot), zero beyond N up to ldc
         int64_t tgt = -1;
         float L = 0.f;
@@ -880,11 +850,7 @@ static std::atomic<int> g_dyn_mode{0};   // 1: tiles after a CTA's first are dra
 constexpr int kTileCtrOffset = 512;      // ints into the flag area (the stream-K flags use the first 320)
 constexpr int kTileCtrSlots = 32;
 void gemm_tc_set_dynamic_tiles(int m) { g_dyn_mode.store(m); }
-static std::atomic<int> g_ce_fused{1};   // 1: the fused-CE forward combines its partials in the last tile's epilogue
-void gemm_tc_set_ce_fused_combine(int m) { g_ce_fused.store(m); }
-constexpr size_t kSkFlagBytes = 4096 + 65536;   // stream-K flags + tile counters (first 4 KB), fused-CE arrival counters
-constexpr int kCeCntOffset = 1024;              // ints
-constexpr int kCeCntCapacity = 16384;           // ints
+constexpr size_t kSkFlagBytes = 4096;           // stream-K flags + tile counters
 constexpr int kSkMaxPairs = 80;
 size_t gemm_tc_streamk_workspace_bytes() { return kSkFlagBytes + (size_t)kSkMaxPairs * 2 * 256 * BM * sizeof(float); }
 void gemm_tc_set_streamk_workspace(void* ptr, size_t bytes) {
@@ -1156,11 +1122,12 @@ int linear_ce_tc_fwd(const void* H, const void* W, const int64_t* targets, float
   p.alpha = 1.f;
   p.targets = targets; p.tgt_row_stride = trs; p.tgt_group_stride = tgs;
   p.ce_part = reinterpret_cast<float4*>(ws);
-  const int64_t counters = (int64_t)groups * ((M + BM - 1) / BM) * 4;
-  const bool fused = g_sk_flags && g_ce_fused.load() != 0 && counters <= kCeCntCapacity;
-  if (fused) { p.ce_cnt = g_sk_flags + kCeCntOffset; p.ce_loss = loss_rows; p.ce_lse = lse; }
+  // (Merging the partials in the epilogue of each row group's last column tile — arrival counters, no second launch —
+  // was built and measured in round 2: bit-identical, but SLOWER: 60.4 vs 50.2 us at N_sel = 232, 156.6 vs 107.5 us at
+  // 1024; the fence + atomic per tile and the serialised merge stall the epilogue warps that gate the next tile's
+  // MMAs.  The separate 5 us combine kernel stays.)
   int rc = gemm_tc_run(o, p, EPI_CE_PARTIAL, st);
-  if (rc || fused) return rc;
+  if (rc) return rc;
   const int bn = gemm_tc_tiling(EPI_CE_PARTIAL, groups, M, V, 0, 0, nullptr);  // the choice gemm_tc_run made
   const int nt = (int)((V + bn - 1) / bn);
   return ce_combine_launch(ws, nt, loss_rows, lse, (int64_t)groups * M, st);

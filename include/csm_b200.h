@@ -190,9 +190,6 @@ void csm_set_gemm_cta_pair_mode(int32_t mode);
  * launch cheaper when the GEMM has the GPU to itself.  Needs the scratch registered with csm_gemm_set_streamk_workspace (the counters live in its flag area);
  * without it the static assignment is used. */
 void csm_set_gemm_dynamic_tiles(int32_t mode);
-/* A/B hook: 1 (default) csm_linear_ce_fwd merges the per-tile online-softmax partials in the epilogue of the last
- * column tile of each 32-row group (arrival counters in the registered scratch); 0 = separate ce_combine kernel. */
-void csm_set_ce_fused_combine(int32_t mode);
 /* Stream-K scratch of the CTA-pair GEMM (fp32 partial tiles + self-resetting flags).  The caller allocates
  * csm_gemm_streamk_workspace_bytes() bytes of ZEROED device memory once per device and registers it; with no workspace
  * registered the GEMM never cuts tiles.  One buffer per device: GEMMs that may use it must be issued on one stream.

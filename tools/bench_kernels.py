@@ -20,8 +20,6 @@ if os.environ.get("CSM_PAIR_MODE"):
     ops.set_gemm_cta_pair_mode(int(os.environ["CSM_PAIR_MODE"]))
 if os.environ.get("CSM_ATTN_FWD_VARIANT"):
     ops.set_attn_fwd_variant(int(os.environ["CSM_ATTN_FWD_VARIANT"]))
-if os.environ.get("CSM_CE_FUSED"):
-    ops.set_ce_fused_combine(int(os.environ["CSM_CE_FUSED"]))
 if os.environ.get("CSM_DYN_TILES"):
     ops.set_gemm_dynamic_tiles(int(os.environ["CSM_DYN_TILES"]))
 if os.environ.get("CSM_NARROW_TAIL"):
