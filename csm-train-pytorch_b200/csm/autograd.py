@@ -384,6 +384,12 @@ class _Group:
                          (blk * float(m.lora_scaling)).contiguous())
             if need[iA]:
                 _acc(grads, iA, dA[ro:ro + r])
+        if self.drop is not None:
+            # dx = dy W + dropout_mask o (dts A) / (1 - p): the low-rank term passes back through the input mask
+            dx = ops.gemm(dy, self.W, trans_b=True)
+            tmp = ops.gemm(dts, self.A_cat, trans_b=True)
+            p_, seed, salt = self.drop
+            return ops.lora_dropout(tmp, p_, seed, salt, out=dx, accumulate=True)
         return ops.gemm(dy, self.W, trans_b=True, a2=dts, b2=self.A_cat)
 
 
