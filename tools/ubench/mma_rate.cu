@@ -1,5 +1,5 @@
 // Microbenchmark: issue rate of tcgen05.mma (cta_group::1, kind::f16) for the operand shapes the attention kernels use.
-//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -o mma_rate mma_rate.cu && ./mma_rate
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 --cudart=shared -o mma_rate mma_rate.cu && ./mma_rate
 // One CTA per SM; one thread issues `iters` groups of `per` MMAs followed by one tcgen05.commit and (optionally) waits
 // for that commit before the next group.  Reports cycles per MMA.
 #include <cstdio>
