@@ -51,8 +51,11 @@ WORKLOADS = {
     # name: (description, mode, lora_r, targets, default B, default S)
     "c2": ("CSM-1B LoRA r=8 q_proj/v_proj bf16, seq 2048 frames, decoder on 1/16 frames", "lora", 8, None, 2, 2048),
     "c3": ("CSM-1B full fine-tune bf16, decoder 1/16 frame amortisation, data-parallel", "full", 0, None, 2, 2048),
-    "c4": ("CSM-1B multi-speaker LoRA r=16 all attn+MLP projections, long-context 4096 frames", "lora", 16,
-           ["q_proj", "k_proj", "v_proj", "o_proj", "gate_proj", "up_proj", "down_proj"], 2, 4096),
+    # BASELINE configs[3]: 4 speakers in every batch — shared backbone adapter, one decoder adapter per speaker, all in
+    # one base GEMM per projection (multi-adapter batching, csm/training/multi_speaker_lora.py)
+    "c4": ("CSM-1B multi-speaker LoRA r=16 all attn+MLP projections (4 speakers per batch, shared backbone adapter, "
+           "per-speaker decoder adapters), long-context 4096 frames", "multi", 16,
+           ["q_proj", "k_proj", "v_proj", "o_proj", "gate_proj", "up_proj", "down_proj"], 16, 4096),
 }
 
 
@@ -121,7 +124,7 @@ def cpu_reference_step_rate(S, steps, warmup, lora_r=8, targets=None, mode="lora
                 p.fill_(1.0)
             else:
                 p.normal_(0.0, 0.02)
-    if mode == "lora":
+    if mode in ("lora", "multi"):
         O.apply_lora(model, r=lora_r, alpha=16.0, target_modules=targets, seed=1)
     params = [p for p in model.parameters() if p.requires_grad]
     opt = torch.optim.AdamW(params, lr=1e-4, weight_decay=0.01)
@@ -163,7 +166,7 @@ def gpu_stock_step_rate(device, mode, lora_r, targets, B, S, steps=5, warmup=2):
             else:
                 p.normal_(0.0, 0.02, generator=g)
     model = model.to(torch.bfloat16)
-    if mode == "lora":
+    if mode in ("lora", "multi"):                  # (stock torch has no multi-adapter batching: one adapter set)
         O.apply_lora(model, r=lora_r, alpha=16.0, target_modules=targets, seed=1)
         model = model.to(device)
     params = [p for p in model.parameters() if p.requires_grad]
@@ -235,7 +238,7 @@ def build_model(workload, device, max_seq):
         model.backbone.set_max_seq_len(max_seq)
     if mode == "lora":
         plora.apply_lora(model, r=r, alpha=16.0, target_modules=targets, seed=1)
-    return model
+    return model                                   # ("multi": the multi-speaker trainer adds its adapters itself)
 
 
 # ----------------------------------------------------------------------------- HBM-bound kernels beside the step
@@ -343,12 +346,26 @@ def run_workload(name, args, rank, world, local, device, headline):
     S = (args.seq if headline else None) or S0
     model = build_model(name, device, S)
     outdir = os.path.join("/tmp", f"csm_bench_{os.getpid()}_{name}")
+    n_speakers = 4
     if mode == "lora":
         trainer = CSMLoRATrainer("", outdir, lora_r=r, target_modules=targets, model=None, device=str(device))
         trainer.logger.setLevel(logging.ERROR)
         trainer.model = model                      # adapters were applied by build_model (seeded)
         trainer.prepare_optimizer()
         step = lambda batch: trainer.train_step(batch)                      # noqa: E731
+        eager_step = lambda batch: trainer._step_impl(batch, 1.0)           # noqa: E731
+    elif mode == "multi":
+        from csm.training.multi_speaker_lora import MultiSpeakerLoRATrainer
+        logging.getLogger("multi_speaker_lora_trainer").setLevel(logging.ERROR)
+        logging.getLogger("csm_lora_trainer").setLevel(logging.ERROR)
+        multi = MultiSpeakerLoRATrainer("", outdir, speaker_ids=list(range(n_speakers)), lora_r=r,
+                                        target_modules=targets, share_backbone=True, share_decoder=False, model=model,
+                                        device=str(device))
+        multi.logger.setLevel(logging.ERROR)
+        trainer = multi.engine
+        trainer.logger.setLevel(logging.ERROR)
+        multi.prepare_optimizers()
+        step = lambda batch: multi.train_step(batch)                        # noqa: E731
         eager_step = lambda batch: trainer._step_impl(batch, 1.0)           # noqa: E731
     else:
         trainer = CSMTrainer("", outdir, device=str(device))
@@ -366,6 +383,9 @@ def run_workload(name, args, rank, world, local, device, headline):
 
     n_batches = 4
     host = [synthetic_batch(128256, 2051, 32, B, S, seed=1234 + rank + 97 * i) for i in range(n_batches)]
+    if mode == "multi":
+        for i, b in enumerate(host):               # every batch mixes the speakers
+            b["speaker_ids"] = (torch.arange(B) + i) % n_speakers
     host = [{k: v.pin_memory() for k, v in b.items()} for b in host]
     resident = [{k: v.to(device) for k, v in b.items()} for b in host]
     n_sel = int(host[0]["frame_idx"].shape[0])
@@ -474,7 +494,7 @@ def run_workload(name, args, rank, world, local, device, headline):
             if peak is None:
                 peak, src = 1400.0, "fallback (B200_PROFILING.md sustained)"
             achieved = flops / (gms * 1e-3) / 1e12 if gms > 0 else 0.0
-            step_flops = fwd_flops_per_frame(S) * (2 if mode == "lora" else 3) * B * S
+            step_flops = fwd_flops_per_frame(S) * (3 if mode == "full" else 2) * B * S
             key = f"gemm_gateup_{B * S}x16384x2048"
             traffic, tsrc = measured_traffic(key)
             roof = {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05 cta_group::2 / TMEM / TMA bf16 GEMM)",
@@ -493,6 +513,7 @@ def run_workload(name, args, rank, world, local, device, headline):
                   "mean": sum(per_rank) / len(per_rank) / args.steps,
                   "per_rank": [t / args.steps for t in per_rank]}
         rec = {"value": value, "ms_per_step": ms_step, "name": name, "workload": desc, "mode": mode, "batch_per_gpu": B,
+               "max_memory_gb": torch.cuda.max_memory_allocated(device) / 1e9,
                "seq_len": S, "decoder_frames_per_gpu": n_sel, "e2e": e2e, "gpu_launches": launches, "clocks": clk,
                "rank_ms_per_step": spread, "exchange": exchange, "roofline": roof}
     # free everything this workload holds on the device before the next one is built
@@ -585,7 +606,8 @@ def main():
                                  "4 distinct input batches cycled"},
                 "clocks": m["clocks"], "e2e": m["e2e"], "gpu_launches": m["gpu_launches"],
                 "gpu_launches_per_step": m["gpu_launches"] / args.steps, "rank_ms_per_step": m["rank_ms_per_step"],
-                "exchange": m["exchange"], "roofline": m["roofline"], "cpu_baseline": cpu,
+                "exchange": m["exchange"], "max_memory_gb": m["max_memory_gb"], "roofline": m["roofline"],
+                "cpu_baseline": cpu,
                 "gpu_stock_baseline": stock, "fullft": fullft, "extra": extras}
         print(json.dumps(line), flush=True)
     if world > 1:
