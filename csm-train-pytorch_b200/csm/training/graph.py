@@ -36,6 +36,8 @@ class GraphedStep:
             for k, v in batch.items():
                 self.static[k].copy_(v, non_blocking=True)
             torch.cuda.synchronize(self.device)
+            torch.cuda.empty_cache()      # the capture allocates the step's activations again in the graph's private pool:
+            #                               hand the eager warm-up's cached blocks back first (long-context batches)
             from .. import _lib
             n0 = _lib.launch_count()
             self.graph = torch.cuda.CUDAGraph()
