@@ -378,7 +378,11 @@ def run_workload(name, args, rank, world, local, device, headline):
             loss = trainer.train_micro_batch(batch, 1)
             trainer.optimizer_step(1.0)
             return loss
-    if not args.no_graph:
+    # A captured step keeps its activations in the graph's private pool NEXT to the eager warm-up's: at c4's batch 16 x
+    # 4096 frames (138 GB of activations per step) that does not fit 180 GB, so that workload runs its launches eagerly
+    # (kernels of 65 536 rows: launch cost is invisible)
+    use_graph = not args.no_graph and B * S <= 32768
+    if use_graph:
         trainer.enable_cuda_graph(warmup=args.warmup)
 
     n_batches = 4
@@ -417,7 +421,7 @@ def run_workload(name, args, rank, world, local, device, headline):
         per_rank = [float(t.item()) for t in every]
         return max(per_rank), per_rank
 
-    n_warm = args.warmup + (2 if not args.no_graph else 0)       # graph mode: W eager steps, then capture + 1 replay
+    n_warm = args.warmup + (2 if use_graph else 0)               # graph mode: W eager steps, then capture + 1 replay
     for i in range(n_warm):
         phase(f"warm-up step {i}")
         step(resident[i % n_batches])
@@ -433,7 +437,7 @@ def run_workload(name, args, rank, world, local, device, headline):
     ms_total, per_rank = timed(lambda i: step(resident[i % n_batches]), args.steps)
     launches = _lib.launch_count() - l0
     graphed = getattr(trainer, "_graphed", None)
-    if not args.no_graph and graphed is not None and graphed.graph is not None:
+    if use_graph and graphed is not None and graphed.graph is not None:
         launches = graphed.kernels_per_replay * args.steps   # replayed graph nodes (counted at capture)
     ms_step = ms_total / args.steps
     frames_per_step = world * B * S
@@ -513,7 +517,7 @@ def run_workload(name, args, rank, world, local, device, headline):
                   "mean": sum(per_rank) / len(per_rank) / args.steps,
                   "per_rank": [t / args.steps for t in per_rank]}
         rec = {"value": value, "ms_per_step": ms_step, "name": name, "workload": desc, "mode": mode, "batch_per_gpu": B,
-               "max_memory_gb": torch.cuda.max_memory_allocated(device) / 1e9,
+               "max_memory_gb": torch.cuda.max_memory_allocated(device) / 1e9, "cuda_graph": use_graph,
                "seq_len": S, "decoder_frames_per_gpu": n_sel, "e2e": e2e, "gpu_launches": launches, "clocks": clk,
                "rank_ms_per_step": spread, "exchange": exchange, "roofline": roof}
     # free everything this workload holds on the device before the next one is built
@@ -599,7 +603,7 @@ def main():
                            "global_batch": m["batch_per_gpu"] * world, "seq_len": m["seq_len"],
                            "decoder_frames_per_gpu": m["decoder_frames_per_gpu"],
                            "parallelism": f"dp{world}" if world > 1 else "single",
-                           "cuda_graph": not args.no_graph,
+                           "cuda_graph": m["cuda_graph"],
                            "precision": "bf16 GEMM / attention operands, fp32 accumulation, fp32 residual stream, "
                                         "fp32 master weights + fp32 AdamW moments",
                            "l2": "per-step working set (3.1 GB weights + >4 GB activations) exceeds the 126 MB L2; "
