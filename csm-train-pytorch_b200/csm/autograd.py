@@ -18,7 +18,8 @@ BF16 = torch.bfloat16
 # segments and transposed to the row-per-lane TMEM layout through smem).  Cold-cache microbenchmark: 120 us against
 # 85 + 69 us for GEMM + swiglu_bwd at 4096 x 8192 x 2048; inside the step the unfused swiglu_bwd reads dact out of L2
 # and the whole step is 0.6 ms FASTER unfused (26.5 vs 27.1 ms), so the fused backward stays off (A/B switch, tested).
-FUSE_SWIGLU_BWD = False
+import os as _os
+FUSE_SWIGLU_BWD = _os.environ.get("CSM_FUSE_SWIGLU_BWD", "0") == "1"
 # The residual stream of both transformer stacks (x -> h = x + attn(..) -> out = h + mlp(..)) is kept in fp32 between
 # layers: the o-proj / down-proj GEMM epilogues add the fp32 residual and store fp32, RMSNorm reads fp32.  Measured
 # (tools/parity_probe*.py, profiles/r2_parity_*.txt): with a bf16 stream — what stock bf16 PyTorch does — the q/k
@@ -339,7 +340,7 @@ class _Group:
         gu, act = ops.gemm_swiglu_fwd(x, self.W, a2=t, b2=self.b2)
         return gu, act, t
 
-    def bwd(self, dy, x, t, grads, need, sink=None, written=None):
+    def bwd(self, dy, x, t, grads, need, sink=None, written=None, need_dx=True):
         if any(need[i] for i in self.iw):
             ws = [m.weight for m in self.mods]
             dst = sink.packed_view(ws) if sink is not None and all(need[i] for i in self.iw) else None
@@ -353,7 +354,7 @@ class _Group:
                     if need[self.iw[j]]:
                         _acc(grads, self.iw[j], dW[self.offs[j]:self.offs[j] + m.weight.shape[0]])
         if not self.lora:
-            return ops.gemm(dy, self.W, trans_b=True)
+            return ops.gemm(dy, self.W, trans_b=True) if need_dx else None
         # with the common scaling s folded into t and dts:  y = x W^T + t B^T,  t = s x A^T
         #   dB = dy^T t,   dts = s dy B,   dA = dts^T x,   dx = dy W + dts A
         s = self.s if self.s is not None else 1.0
@@ -384,6 +385,8 @@ class _Group:
                          (blk * float(m.lora_scaling)).contiguous())
             if need[iA]:
                 _acc(grads, iA, dA[ro:ro + r])
+        if not need_dx:
+            return None
         if self.drop is not None:
             # dx = dy W + dropout_mask o (dts A) / (1 - p): the low-rank term passes back through the input mask
             dx = ops.gemm(dy, self.W, trans_b=True)
@@ -521,11 +524,18 @@ class StackFn(Function):
             # (the inverse RoPE of dq / dk happens in the attention kernels' store epilogues when they can)
             ops.attention_bwd(q, k, v, o, lse, do, B, S, H, KV, hd, dq=dq, dk=dk, dv=dv, rope_cache=cache,
                               seg_start=ctx.packing[0], seg_end=ctx.packing[1])
-            dxn = gqkv.bwd(dqkv, xn, tqkv, grads, need, sink=sink, written=written)
-            dcur = norm_bwd(dxn, x, layer.sa_norm, rstd1, dh)
+            first = layer is stack.layers[0]
+            if first and not ctx.needs_input_grad[0] and not need[index_of[id(layer.sa_norm.scale)]]:
+                # LoRA on frozen embeddings: nobody consumes the gradient of the stack's input — the first layer's
+                # q|k|v dgrad GEMM and its RMSNorm backward are skipped (the adapters' own gradients are still taken)
+                gqkv.bwd(dqkv, xn, tqkv, grads, need, sink=sink, written=written, need_dx=False)
+                dcur = None
+            else:
+                dxn = gqkv.bwd(dqkv, xn, tqkv, grads, need, sink=sink, written=written)
+                dcur = norm_bwd(dxn, x, layer.sa_norm, rstd1, dh)
             hand_over(layer)
         ctx.saved = None
-        dx = dcur.view(B, S, D) if ctx.needs_input_grad[0] else None
+        dx = dcur.view(B, S, D) if (ctx.needs_input_grad[0] and dcur is not None) else None
         return (dx, None) + tuple(grads)
 
 
