@@ -14,12 +14,14 @@ from torch.autograd import Function
 from . import ops
 
 BF16 = torch.bfloat16
-# The w2-dgrad GEMM can apply the SwiGLU backward in its epilogue (gate/up fetched one chunk ahead as whole 64-byte row
-# segments and transposed to the row-per-lane TMEM layout through smem).  Cold-cache microbenchmark: 120 us against
-# 85 + 69 us for GEMM + swiglu_bwd at 4096 x 8192 x 2048; inside the step the unfused swiglu_bwd reads dact out of L2
-# and the whole step is 0.6 ms FASTER unfused (26.5 vs 27.1 ms), so the fused backward stays off (A/B switch, tested).
+# The w2-dgrad GEMM applies the SwiGLU backward in its epilogue (gate/up fetched one chunk ahead as whole 64-byte row
+# segments and transposed to the row-per-lane TMEM layout through smem): dact never exists and the separate swiglu_bwd
+# pass (1.3 ms per c2 step) disappears.  Cold-cache microbenchmark: 120 us against 87 + 67 us at 4096 x 8192 x 2048.
+# In-step A/B on B200 (round 2, same box, alternating runs): 24.33 / 24.37 ms fused vs 24.48 / 24.60 ms unfused — in
+# round 1 the unfused path had won by 0.6 ms because swiglu_bwd read dact out of L2; with the fp32 residual stream and
+# the other round-2 changes that no longer holds.  CSM_FUSE_SWIGLU_BWD=0 selects the unfused kernels.
 import os as _os
-FUSE_SWIGLU_BWD = _os.environ.get("CSM_FUSE_SWIGLU_BWD", "0") == "1"
+FUSE_SWIGLU_BWD = _os.environ.get("CSM_FUSE_SWIGLU_BWD", "1") == "1"
 # The residual stream of both transformer stacks (x -> h = x + attn(..) -> out = h + mlp(..)) is kept in fp32 between
 # layers: the o-proj / down-proj GEMM epilogues add the fp32 residual and store fp32, RMSNorm reads fp32.  Measured
 # (tools/parity_probe*.py, profiles/r2_parity_*.txt): with a bf16 stream — what stock bf16 PyTorch does — the q/k
