@@ -19,6 +19,17 @@ namespace csm {
 
 using namespace tc;
 
+// -DCSM_ATTN_PROF (tools/ubench/attn_prof.sh only; never in the product build): per-role cycle accounting of the backward
+// kernels — CTA 0's MMA warp and two compute warps add up the cycles they spend in each wait.
+#ifdef CSM_ATTN_PROF
+__device__ long long g_attn_prof[128];
+#define PROF_WAIT(acc, ...) { const long long _t = clock64(); __VA_ARGS__; acc += clock64() - _t; }
+#define PROF_ONLY(...) __VA_ARGS__
+#else
+#define PROF_WAIT(acc, ...) { __VA_ARGS__; }
+#define PROF_ONLY(...)
+#endif
+
 namespace {
 
 constexpr int TQ = 128, TK = 128, THD = 64;
@@ -145,34 +156,37 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       constexpr uint32_t idesc_s = make_idesc_bf16(TQ, FK, 0, 0);    // S = Q K^T : both K-major
       constexpr uint32_t idesc_pv = make_idesc_bf16(TQ, THD, 0, 1);  // PV = P V  : V is MN-major ([key][hd] rows)
       const uint32_t sq = smem_u32(smem + SM_Q);
-      auto issue_s = [&](int j) {
-        const int st = j & 1;
-        if (elect_one()) {
-          const uint32_t sk = smem_u32(smem + SM_K + (j % FST) * (FK * THD * 2));
+      // one elected thread runs the whole issue loop: warp-wide waits + elect + __syncwarp around every MMA block cost
+      // ~65 cycles each even when the barrier is open, and the tensor pipe's queue is too shallow to hide that behind
+      // 51-cycle N=64 MMAs (tools/ubench/mma_rate.cu k4)
+      if (elect_one()) {
+        int ks_s = 0, ks_v = 0;                    // K/V ring stage of the next S block resp. the next PV block
+        uint32_t ks_ph = 0;                        // parity of kv_full[ks_s]
+        auto issue_s = [&](int j) {
+          const int st = j & 1;
+          const uint32_t sk = smem_u32(smem + SM_K + ks_s * (FK * THD * 2));
           const uint64_t ad = make_smem_desc(sq, 16, 1024), bd = make_smem_desc(sk, 16, 1024);
 #pragma unroll
           for (int kk = 0; kk < THD / 16; ++kk)
             umma_bf16(tmem_base + COL_S + st * FK, ad + (uint64_t)((kk * 32) >> 4), bd + (uint64_t)((kk * 32) >> 4),
                       idesc_s, kk ? 1u : 0u);
           umma_commit(&s_full[st]);
-        }
-        __syncwarp();
-      };
-      mbar_wait(q_full, 0);
-      mbar_wait(&kv_full[0], 0);
-      tc_fence_after();
-      issue_s(0);
-      for (int j = 0; j < nblk; ++j) {
-        const int st = j & 1;
-        if (j + 1 < nblk) {
-          mbar_wait(&kv_full[(j + 1) % FST], ((j + 1) / FST) & 1);
-          tc_fence_after();
-          issue_s(j + 1);  // S buffer st^1 was drained before p_full(j-1) completed (waited last iteration)
-        }
-        mbar_wait(&p_full[st], (j >> 1) & 1);
+          if (++ks_s == FST) { ks_s = 0; ks_ph ^= 1; }
+        };
+        mbar_wait(q_full, 0);
+        mbar_wait(&kv_full[0], 0);
         tc_fence_after();
-        if (elect_one()) {
-          const uint32_t sv = smem_u32(smem + SM_V + (j % FST) * (FK * THD * 2));
+        issue_s(0);
+        for (int j = 0; j < nblk; ++j) {
+          const int st = j & 1;
+          if (j + 1 < nblk) {
+            mbar_wait(&kv_full[ks_s], ks_ph);
+            tc_fence_after();
+            issue_s(j + 1);  // S buffer st^1 was drained before p_full(j-1) completed (waited last iteration)
+          }
+          mbar_wait(&p_full[st], (j >> 1) & 1);
+          tc_fence_after();
+          const uint32_t sv = smem_u32(smem + SM_V + ks_v * (FK * THD * 2));
           // P: read straight from TMEM (bf16 pairs written back over the S columns, 8 cells per 16 keys) — no smem
           // round trip.  V: 16 key-rows x 128 B per K step.  The in-order tensor pipe runs PV(j) before S(j+2), which
           // overwrites the same columns.
@@ -182,10 +196,11 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
             umma_bf16_ts(tmem_base + COL_PV + (kTmemO ? 0 : st * THD), tmem_base + COL_S + st * FK + kk * 8,
                          bd + (uint64_t)((kk * 16 * 128) >> 4), idesc_pv, (kk || (kTmemO && j > 0)) ? 1u : 0u);
           umma_commit(&pv_full[st]);
-          umma_commit(&kv_empty[j % FST]);
+          umma_commit(&kv_empty[ks_v]);
+          if (++ks_v == FST) ks_v = 0;
         }
-        __syncwarp();
       }
+      __syncwarp();
     }
   } else {
     const int quad = warp & 3;
@@ -388,8 +403,9 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 // P / dS never go through shared memory: the 128 x 64 MMAs with both operands in smem were operand-feed-bound
 // (6 KB of smem per 32 math cycles) and the compute warps' tile stores competed for the same 128 B/clk
 // (ncu: pipe_tc 56 % busy for 25 % of math) — with A in TMEM the backward went from 286 to 239 us at B=2, S=2048.
-// The MMA warp runs two sub-blocks ahead of the 8 compute warps; a TMEM buffer is handed back by the commit of the
-// MMAs that consumed P / dS from it.
+// The MMA warp runs NB = 3 sub-blocks ahead of the 8 compute warps: S/dP(u + 3) is issued right behind the MMAs that
+// consume P / dS of sub-block u from the same TMEM buffer — tcgen05.mma instructions of one thread execute in issue order,
+// so no "buffer free" barrier (and no pipe drain per sub-block) is needed.
 // The Q / dO / K / V tiles are loaded once per use by TMA as [rows][64] 128B-swizzled tiles and serve BOTH as a
 // K-major operand (rows = M or N, hd = K) and as an MN-major B operand (hd = N, rows = K): same bytes, two descriptors.
 // Compute warps w and w+4 share a TMEM lane quadrant and split the 64 columns of a sub-block; no row reductions are
@@ -441,7 +457,6 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
   uint64_t* kv_full = bars + 1;       // [KST]
   uint64_t* kv_empty = bars + 4;      // [KST]
   uint64_t* sdp_full = bars + 7;      // [NB] S and dP sub-block ready in TMEM
-  uint64_t* sdp_empty = bars + 10;    // [NB] ... buffer free again (the dQ MMAs that read dS out of it have completed)
   uint64_t* ds_full = bars + 13;      // [NB] dS written back over the dP columns as bf16 pairs (8 warp arrivals)
   uint64_t* acc_full = bars + 17;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
@@ -465,7 +480,7 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     mbar_init(q_full, 1);
     for (int i = 0; i < 3; ++i) {
       mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1);
-      mbar_init(&sdp_full[i], 1); mbar_init(&sdp_empty[i], 1);
+      mbar_init(&sdp_full[i], 1);
       mbar_init(&ds_full[i], 8);
     }
     mbar_init(acc_full, 1);
@@ -497,40 +512,57 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     }
   } else if (warp == 1) {
     {
+      PROF_ONLY(long long pw0 = 0, pw1 = 0, pw2 = 0; const long long pt0 = clock64();)
       const uint32_t sq = smem_u32(smem + DQ_Q), sdo = smem_u32(smem + DQ_DO);
-      auto issue_sdp = [&](int u) {
-        const int jt = u >> 1, hk = u & 1, st = jt % KST, bb = u % NB;
-        if (hk == 0) mbar_wait(&kv_full[st], (jt / KST) & 1);
-        mbar_wait(&sdp_empty[bb], ((u / NB) & 1) ^ 1);
+      // S/dP(u + NB) overwrites the TMEM buffer of sub-block u.  No "buffer free" barrier is needed: it is issued after
+      // dQ(u) — the last reader of that buffer — and tcgen05.mma instructions of one thread execute in issue order (the
+      // forward kernel relies on the same property); the compute warps' loads of S/dP(u) completed before ds_full(u).
+      // The whole loop runs in ONE elected thread: a warp-wide mbarrier wait + elect + __syncwarp per MMA block costs
+      // ~65 cycles even when the barrier is already open (tools/ubench/mma_rate.cu k4: 668 vs 516 cycles per sub-block),
+      // and the tensor pipe's queue is too shallow to ride that out with 51-cycle N=64 MMAs.
+      if (elect_one()) {
+        // ring positions are carried incrementally (no divisions by KST / NB on the issue path): the producer side `p`
+        // walks S/dP(u + NB), the consumer side `c` walks dQ(u)
+        int p_st = 0, p_bb = 0, p_hk = 0;
+        uint32_t p_stph = 0;
+        auto issue_sdp = [&]() {
+          if (p_hk == 0) {
+            PROF_WAIT(pw0, mbar_wait(&kv_full[p_st], p_stph))
+            tc_fence_after();
+          }
+          const uint32_t sk = smem_u32(smem + DQ_K + p_st * (TK * THD * 2)) + p_hk * (SUB * 128);
+          const uint32_t sv = smem_u32(smem + DQ_V + p_st * (TK * THD * 2)) + p_hk * (SUB * 128);
+          issue_nt_64(tmem_base + COL_S + p_bb * SUB, sq, sk);     // S  = Q K_sub^T
+          issue_nt_64(tmem_base + COL_DP + p_bb * SUB, sdo, sv);   // dP = dO V_sub^T
+          umma_commit(&sdp_full[p_bb]);
+          if (++p_bb == NB) p_bb = 0;
+          if (p_hk) { if (++p_st == KST) { p_st = 0; p_stph ^= 1; } }
+          p_hk ^= 1;
+        };
+        mbar_wait(q_full, 0);
         tc_fence_after();
-        if (elect_one()) {
-          const uint32_t sk = smem_u32(smem + DQ_K + st * (TK * THD * 2)) + hk * (SUB * 128);
-          const uint32_t sv = smem_u32(smem + DQ_V + st * (TK * THD * 2)) + hk * (SUB * 128);
-          issue_nt_64(tmem_base + COL_S + bb * SUB, sq, sk);     // S  = Q K_sub^T
-          issue_nt_64(tmem_base + COL_DP + bb * SUB, sdo, sv);   // dP = dO V_sub^T
-          umma_commit(&sdp_full[bb]);
-        }
-        __syncwarp();
-      };
-      mbar_wait(q_full, 0);
-      issue_sdp(0);
-      issue_sdp(1);                    // nsub >= 2 always
-      for (int u = 0; u < nsub; ++u) {
-        if (u + 2 < nsub) issue_sdp(u + 2);
-        const int jt = u >> 1, hk = u & 1, st = jt % KST, bb = u % NB;
-        mbar_wait(&ds_full[bb], (u / NB) & 1);
-        tc_fence_after();
-        if (elect_one()) {
-          const uint32_t sk = smem_u32(smem + DQ_K + st * (TK * THD * 2)) + hk * (SUB * 128);
-          issue_atmem_bmn(tmem_base + COL_DQ, tmem_base + COL_DP + bb * SUB, sk, u > 0);   // dQ += dS K_sub (dS in TMEM)
-          umma_commit(&sdp_empty[bb]);
-          if (hk == 1) umma_commit(&kv_empty[st]);
+        for (int u = 0; u < NB && u < nsub; ++u) issue_sdp();
+        int c_st = 0, c_bb = 0, c_hk = 0;
+        uint32_t c_bbph = 0;
+        for (int u = 0; u < nsub; ++u) {
+          PROF_WAIT(pw2, mbar_wait(&ds_full[c_bb], c_bbph))
+          tc_fence_after();
+          const uint32_t sk = smem_u32(smem + DQ_K + c_st * (TK * THD * 2)) + c_hk * (SUB * 128);
+          issue_atmem_bmn(tmem_base + COL_DQ, tmem_base + COL_DP + c_bb * SUB, sk, u > 0);   // dQ += dS K_sub (dS in TMEM)
+          if (c_hk) { umma_commit(&kv_empty[c_st]); if (++c_st == KST) c_st = 0; }
           if (u == nsub - 1) umma_commit(acc_full);
+          if (u + NB < nsub) issue_sdp();
+          if (++c_bb == NB) { c_bb = 0; c_bbph ^= 1; }
+          c_hk ^= 1;
         }
-        __syncwarp();
       }
+      __syncwarp();
+      PROF_ONLY(if (blockIdx.x == 0 && lane == 0) {
+        g_attn_prof[0] = clock64() - pt0; g_attn_prof[1] = pw0; g_attn_prof[2] = pw1; g_attn_prof[3] = pw2; g_attn_prof[4] = nsub;
+      })
     }
   } else {
+    PROF_ONLY(long long pw0 = 0, pw1 = 0, pw2 = 0; const long long pt0 = clock64();)
     const int quad = warp & 3, half = (warp - 2) >> 2;
     const int r = quad * 32 + lane, qi = q0 + r;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16);
@@ -540,17 +572,18 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     const float Dls = (qi < S) ? delta[li] * scale : 0.f;
     const int lo = kVarlen ? seg_start[(int64_t)b * S + min(qi, S - 1)] : 0;
     const int lo_max = kVarlen ? seg_start[(int64_t)b * S + min(q0 + TQ - 1, S - 1)] : 0;
-    auto sub = [&](int u, auto diag_tag) {
+    int bb = 0, kbase = jt0 * TK + half * 32;      // TMEM buffer of the sub-block and this warp's first key in it
+    uint32_t bbph = 0;
+    auto sub = [&](auto diag_tag) {
       constexpr bool DIAG = decltype(diag_tag)::value;
-      const int bb = u % NB;
-      const int kbase = (jt0 + (u >> 1)) * TK + (u & 1) * SUB + half * 32;
-      mbar_wait(&sdp_full[bb], (u / NB) & 1);
+      PROF_WAIT(pw0, mbar_wait(&sdp_full[bb], bbph))
       tc_fence_after();
       uint32_t sv_[32], dv_[32];
       __syncwarp();
-      tmem_ld32(lane_addr + COL_S + bb * SUB + half * 32, sv_);
-      tmem_ld32(lane_addr + COL_DP + bb * SUB + half * 32, dv_);
-      tmem_ld_wait();
+      PROF_WAIT(pw1, tmem_ld32(lane_addr + COL_S + bb * SUB + half * 32, sv_);
+                tmem_ld32(lane_addr + COL_DP + bb * SUB + half * 32, dv_);
+                tmem_ld_wait())
+      PROF_ONLY(const long long pm0 = clock64();)
       float f[32];
 #pragma unroll
       for (int i = 0; i < 32; ++i) {
@@ -567,13 +600,20 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&ds_full[bb]);
+      PROF_ONLY(pw2 += clock64() - pm0;)
+      if (++bb == NB) { bb = 0; bbph ^= 1; }
+      kbase += SUB;
     };
     for (int u = 0; u < nsub - 2; ++u) {
-      if (kVarlen && (jt0 + (u >> 1)) * TK + (u & 1) * SUB < lo_max) sub(u, std::true_type{});
-      else sub(u, std::false_type{});
+      if (kVarlen && kbase - half * 32 < lo_max) sub(std::true_type{});
+      else sub(std::false_type{});
     }
-    sub(nsub - 2, std::true_type{});
-    sub(nsub - 1, std::true_type{});
+    sub(std::true_type{});
+    sub(std::true_type{});
+    PROF_ONLY(if (blockIdx.x == 0 && lane == 0 && (warp == 2 || warp == 7)) {
+      long long* o = g_attn_prof + (warp == 2 ? 8 : 16);
+      o[0] = clock64() - pt0; o[1] = pw0; o[2] = pw1; o[3] = pw2;
+    })
     mbar_wait(acc_full, 0);
     tc_fence_after();
     {
@@ -632,8 +672,6 @@ attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
   uint64_t* qd_full = bars + 1;       // [KST] Q_i + dO_i tiles landed
   uint64_t* qd_empty = bars + 4;      // [KST]
   uint64_t* sdp_full = bars + 7;      // [NB] S^T and dP^T sub-block ready
-  uint64_t* sdp_empty = bars + 10;    // [NB] ... its TMEM buffer is free again (the dV / dK MMAs that read P^T / dS^T
-                                      //      out of the same columns have completed)
   uint64_t* pt_full = bars + 13;      // [NB] P^T and dS^T written back into the buffer as bf16 (8 warp arrivals)
   uint64_t* acc_full = bars + 16;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
@@ -656,7 +694,7 @@ attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
     mbar_init(kv_full, 1);
     for (int i = 0; i < 3; ++i) {
       mbar_init(&qd_full[i], 1); mbar_init(&qd_empty[i], 1);
-      mbar_init(&sdp_full[i], 1); mbar_init(&sdp_empty[i], 1);
+      mbar_init(&sdp_full[i], 1);
       mbar_init(&pt_full[i], 8);
     }
     mbar_init(acc_full, 1);
@@ -691,44 +729,56 @@ attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
     }
   } else if (warp == 1) {
     {
+      PROF_ONLY(long long pw0 = 0, pw1 = 0, pw2 = 0; const long long pt0 = clock64();)
       const uint32_t sk = smem_u32(smem + DK_K), sv = smem_u32(smem + DK_V);
-      auto issue_sdp = [&](int u) {
-        const int it = u >> 1, hq = u & 1, st = it % KST, bb = u % NB;
-        if (hq == 0) mbar_wait(&qd_full[st], (it / KST) & 1);
-        mbar_wait(&sdp_empty[bb], ((u / NB) & 1) ^ 1);
+      // S^T/dP^T(u + NB) is issued right after dV/dK(u), the last readers of the buffer it overwrites: in-order execution
+      // of one thread's tcgen05.mma instructions replaces a "buffer free" barrier; one elected thread runs the whole
+      // loop (see the dQ kernel)
+      if (elect_one()) {
+        int p_st = 0, p_bb = 0, p_hq = 0;          // ring positions carried incrementally (see the dQ kernel)
+        uint32_t p_stph = 0;
+        auto issue_sdp = [&]() {
+          if (p_hq == 0) {
+            PROF_WAIT(pw0, mbar_wait(&qd_full[p_st], p_stph))
+            tc_fence_after();
+          }
+          const uint32_t sq = smem_u32(smem + DK_Q + p_st * (TQ * THD * 2)) + p_hq * (SUB * 128);
+          const uint32_t sdo = smem_u32(smem + DK_DO + p_st * (TQ * THD * 2)) + p_hq * (SUB * 128);
+          issue_nt_64(tmem_base + COL_ST + p_bb * SUB, sk, sq);      // S^T  = K Q_sub^T
+          issue_nt_64(tmem_base + COL_DPT + p_bb * SUB, sv, sdo);    // dP^T = V dO_sub^T
+          umma_commit(&sdp_full[p_bb]);
+          if (++p_bb == NB) p_bb = 0;
+          if (p_hq) { if (++p_st == KST) { p_st = 0; p_stph ^= 1; } }
+          p_hq ^= 1;
+        };
+        mbar_wait(kv_full, 0);
         tc_fence_after();
-        if (elect_one()) {
-          const uint32_t sq = smem_u32(smem + DK_Q + st * (TQ * THD * 2)) + hq * (SUB * 128);
-          const uint32_t sdo = smem_u32(smem + DK_DO + st * (TQ * THD * 2)) + hq * (SUB * 128);
-          issue_nt_64(tmem_base + COL_ST + bb * SUB, sk, sq);      // S^T  = K Q_sub^T
-          issue_nt_64(tmem_base + COL_DPT + bb * SUB, sv, sdo);    // dP^T = V dO_sub^T
-          umma_commit(&sdp_full[bb]);
-        }
-        __syncwarp();
-      };
-      mbar_wait(kv_full, 0);
-      issue_sdp(0);
-      issue_sdp(1);                    // nsub >= 2 always
-      for (int u = 0; u < nsub; ++u) {
-        if (u + 2 < nsub) issue_sdp(u + 2);
-        const int it = u >> 1, hq = u & 1, st = it % KST, bb = u % NB;
-        mbar_wait(&pt_full[bb], (u / NB) & 1);
-        tc_fence_after();
-        if (elect_one()) {
-          const uint32_t sq = smem_u32(smem + DK_Q + st * (TQ * THD * 2)) + hq * (SUB * 128);
-          const uint32_t sdo = smem_u32(smem + DK_DO + st * (TQ * THD * 2)) + hq * (SUB * 128);
+        for (int u = 0; u < NB && u < nsub; ++u) issue_sdp();
+        int c_st = 0, c_bb = 0, c_hq = 0;
+        uint32_t c_bbph = 0;
+        for (int u = 0; u < nsub; ++u) {
+          PROF_WAIT(pw2, mbar_wait(&pt_full[c_bb], c_bbph))
+          tc_fence_after();
+          const uint32_t sq = smem_u32(smem + DK_Q + c_st * (TQ * THD * 2)) + c_hq * (SUB * 128);
+          const uint32_t sdo = smem_u32(smem + DK_DO + c_st * (TQ * THD * 2)) + c_hq * (SUB * 128);
           // A operands straight from TMEM: P^T / dS^T were written back (bf16 pairs) over the S^T / dP^T columns they
           // came from — no shared-memory round trip for the 128 x 64 tiles, and the MMAs read only B from smem
-          issue_atmem_bmn(tmem_base + COL_DV, tmem_base + COL_ST + bb * SUB, sdo, u > 0);    // dV += P^T dO
-          issue_atmem_bmn(tmem_base + COL_DK, tmem_base + COL_DPT + bb * SUB, sq, u > 0);    // dK += dS^T Q
-          umma_commit(&sdp_empty[bb]);
-          if (hq == 1) umma_commit(&qd_empty[st]);
+          issue_atmem_bmn(tmem_base + COL_DV, tmem_base + COL_ST + c_bb * SUB, sdo, u > 0);    // dV += P^T dO
+          issue_atmem_bmn(tmem_base + COL_DK, tmem_base + COL_DPT + c_bb * SUB, sq, u > 0);    // dK += dS^T Q
+          if (c_hq) { umma_commit(&qd_empty[c_st]); if (++c_st == KST) c_st = 0; }
           if (u == nsub - 1) umma_commit(acc_full);
+          if (u + NB < nsub) issue_sdp();
+          if (++c_bb == NB) { c_bb = 0; c_bbph ^= 1; }
+          c_hq ^= 1;
         }
-        __syncwarp();
       }
+      __syncwarp();
+      PROF_ONLY(if (blockIdx.x == 0 && lane == 0) {
+        g_attn_prof[32] = clock64() - pt0; g_attn_prof[33] = pw0; g_attn_prof[34] = pw1; g_attn_prof[35] = pw2; g_attn_prof[36] = nsub;
+      })
     }
   } else {
+    PROF_ONLY(long long pw0 = 0, pw1 = 0, pw2 = 0, pw3 = 0; const long long pt0 = clock64();)
     const int quad = warp & 3, half = (warp - 2) >> 2;
     const int r = quad * 32 + lane, kj = k0 + r;               // this thread's key
     const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16);
@@ -740,33 +790,29 @@ attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
     const float ld_mul = ctid < 128 ? kLog2e : scale;
     const int hi = kVarlen ? seg_end[(int64_t)b * S + min(kj, S - 1)] : S;              // this key's last query + 1
     const int hi_min = kVarlen ? seg_end[(int64_t)b * S + min(k0, S - 1)] : S;          // earliest segment end of the tile
-    auto load_ld = [&](int it) -> float {
-      const int h = kvh * rep + it / nq_iter, qb = kvb + it % nq_iter;
-      const int q = qb * TQ + (ctid & 127);
-      const int64_t li = ((int64_t)b * H + h) * S + q;
+    // (head, query tile) of the 128-query tile whose lse / delta this thread fetches next: carried incrementally — the
+    // compute warps are a latency-bound serial chain, an integer division per sub-block shows up 1:1 in the kernel time
+    auto load_ld = [&](int hh, int qt) -> float {
+      const int q = (kvb + qt) * TQ + (ctid & 127);
+      const int64_t li = ((int64_t)b * H + (kvh * rep + hh)) * S + q;
       if (q >= S) return ctid < 128 ? INFINITY : 0.f;
       return __ldg((ctid < 128 ? lse : delta) + li);
     };
-    float ld_next = load_ld(0);
-    auto sub = [&](int u, auto diag_tag) {
+    float ld_next = load_ld(0, 0);
+    int bb = 0;
+    uint32_t bbph = 0;
+    auto sub = [&](int qb, int hq, const float* sLD, auto diag_tag) {
       constexpr bool DIAG = decltype(diag_tag)::value;
-      const int it = u >> 1, hq = u & 1, bb = u % NB;
-      const int qb = kvb + it % nq_iter;
-      float* sLD = reinterpret_cast<float*>(smem + DK_LD) + (it & 1) * 256;
-      if (hq == 0) {
-        sLD[ctid] = ld_next * ld_mul;
-        named_bar_sync(1, 256);
-        if (it + 1 < total) ld_next = load_ld(it + 1);
-      }
       const int col0 = hq * SUB + half * 32;                   // first query column (inside the 128-query tile)
       const int qbase = qb * TQ + col0;
-      mbar_wait(&sdp_full[bb], (u / NB) & 1);
+      PROF_WAIT(pw0, mbar_wait(&sdp_full[bb], bbph))
       tc_fence_after();
       uint32_t sv_[32], dv_[32];
       __syncwarp();
-      tmem_ld32(lane_addr + COL_ST + bb * SUB + half * 32, sv_);
-      tmem_ld32(lane_addr + COL_DPT + bb * SUB + half * 32, dv_);
-      tmem_ld_wait();
+      PROF_WAIT(pw1, tmem_ld32(lane_addr + COL_ST + bb * SUB + half * 32, sv_);
+                tmem_ld32(lane_addr + COL_DPT + bb * SUB + half * 32, dv_);
+                tmem_ld_wait())
+      PROF_ONLY(const long long pm0 = clock64();)
       float pf[32], df[32];
       const float4* L4 = reinterpret_cast<const float4*>(sLD + col0);
       const float4* D4 = reinterpret_cast<const float4*>(sLD + 128 + col0);
@@ -797,12 +843,32 @@ attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&pt_full[bb]);
+      PROF_ONLY(pw2 += clock64() - pm0;)
+      if (++bb == NB) { bb = 0; bbph ^= 1; }
     };
-    for (int u = 0; u < nsub; ++u) {
-      const int qt = (u >> 1) % nq_iter;
-      if (qt == 0 || (kVarlen && (kvb + qt) * TQ + (u & 1) * SUB + SUB > hi_min)) sub(u, std::true_type{});
-      else sub(u, std::false_type{});
+    int par = 0;                                  // which half of the lse/delta staging buffer this tile uses
+    for (int hh = 0; hh < rep; ++hh) {
+      for (int qt = 0; qt < nq_iter; ++qt) {
+        const int qb = kvb + qt;
+        float* sLD = reinterpret_cast<float*>(smem + DK_LD) + par * 256;
+        par ^= 1;
+        sLD[ctid] = ld_next * ld_mul;
+        PROF_WAIT(pw3, named_bar_sync(1, 256))
+        {
+          const bool wrap = qt + 1 == nq_iter;
+          if (!wrap || hh + 1 < rep) ld_next = load_ld(wrap ? hh + 1 : hh, wrap ? 0 : qt + 1);
+        }
+#pragma unroll
+        for (int hq = 0; hq < 2; ++hq) {
+          if (qt == 0 || (kVarlen && qb * TQ + hq * SUB + SUB > hi_min)) sub(qb, hq, sLD, std::true_type{});
+          else sub(qb, hq, sLD, std::false_type{});
+        }
+      }
     }
+    PROF_ONLY(if (blockIdx.x == 0 && lane == 0 && (warp == 2 || warp == 7)) {
+      long long* o = g_attn_prof + (warp == 2 ? 40 : 48);
+      o[0] = clock64() - pt0; o[1] = pw0; o[2] = pw1; o[3] = pw2; o[4] = pw3;
+    })
     mbar_wait(acc_full, 0);
     tc_fence_after();
     // warps 2..5 store dK rows, warps 6..9 store dV rows (64 columns each)
@@ -947,3 +1013,9 @@ int attn_bwd_tc_launch(const void* q, const void* k, const void* v, const void* 
 }
 
 }  // namespace csm
+
+#ifdef CSM_ATTN_PROF
+extern "C" int csm_debug_attn_prof(long long* host_out) {
+  return (int)cudaMemcpyFromSymbol(host_out, csm::g_attn_prof, sizeof(long long) * 128);
+}
+#endif
