@@ -408,20 +408,26 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 // so no "buffer free" barrier (and no pipe drain per sub-block) is needed.
 // The Q / dO / K / V tiles are loaded once per use by TMA as [rows][64] 128B-swizzled tiles and serve BOTH as a
 // K-major operand (rows = M or N, hd = K) and as an MN-major B operand (hd = N, rows = K): same bytes, two descriptors.
-// Compute warps w and w+4 share a TMEM lane quadrant and split the 64 columns of a sub-block; no row reductions are
-// needed (lse and delta come from the forward / the delta pre-pass).
-constexpr int kBwdThreads = 320;  // warp0 TMA, warp1 MMA, warps 2..9 compute
-constexpr int SUB = 64;           // columns (keys resp. queries) per pipelined sub-block
+// Sixteen compute warps: the four warps of a TMEM lane quadrant take 16 columns of a sub-block each, and every warp
+// issues the TMEM loads of sub-block u+1 before the math of sub-block u.  Measured (tools/ubench/tmem_rate.cu): one warp
+// reads TMEM at 16-19 B/clk, 8 warps in lock step at ~110 B/clk/SM (the loads of a 64 KB sub-block then take as long as its
+// 8192 exponentials on the MUFU, and the two phases did not overlap), 16 warps at 155-190 B/clk/SM.  No row reductions
+// are needed (lse and delta come from the forward / the delta pre-pass).
+constexpr int kBwdCW = 16;                      // compute warps: four per TMEM lane quadrant
+constexpr int kBwdThreads = 64 + kBwdCW * 32;   // warp0 TMA, warp1 MMA, warps 2..17 compute
+constexpr int SUB = 64;                         // columns (keys resp. queries) per pipelined sub-block
+constexpr int PC = SUB / (kBwdCW / 4);          // columns of a sub-block per compute warp (16)
+static_assert(PC == 16, "the compute warps use the x16 TMEM load / x8 store shapes");
 
 // D[128 x 64] (+)= A[TMEM, 128 lanes x 64 k as bf16 pairs] * B, B = [64 rows x 64] smem tile used MN-major.
-// The two compute warps of a lane quadrant each wrote 32 k (16 cells) at the start of their own 32-column half:
-// k-steps 0,1 live at columns 0 and 8, k-steps 2,3 at columns 32 and 40.
+// Each of the four compute warps of a lane quadrant wrote its 16 k (8 cells) at the start of its own 16-column quarter:
+// k-step kk lives at column 16 * kk.
 __device__ __forceinline__ void issue_atmem_bmn(uint32_t d_tmem, uint32_t a_tmem, uint32_t b_smem, bool accumulate_first) {
   constexpr uint32_t idesc = make_idesc_bf16(128, THD, 0, 1);
   const uint64_t bd = make_smem_desc(b_smem, 64 * 128 * 2, 1024);
 #pragma unroll
   for (int kk = 0; kk < SUB / 16; ++kk)
-    umma_bf16_ts(d_tmem, a_tmem + (uint32_t)((kk >> 1) * 32 + (kk & 1) * 8), bd + (uint64_t)((kk * 16 * 128) >> 4), idesc,
+    umma_bf16_ts(d_tmem, a_tmem + (uint32_t)(kk * PC), bd + (uint64_t)((kk * 16 * 128) >> 4), idesc,
                  (accumulate_first || kk) ? 1u : 0u);
 }
 
@@ -481,7 +487,7 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     for (int i = 0; i < 3; ++i) {
       mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1);
       mbar_init(&sdp_full[i], 1);
-      mbar_init(&ds_full[i], 8);
+      mbar_init(&ds_full[i], kBwdCW);
     }
     mbar_init(acc_full, 1);
     mbar_fence_init();
@@ -563,53 +569,66 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     }
   } else {
     PROF_ONLY(long long pw0 = 0, pw1 = 0, pw2 = 0; const long long pt0 = clock64();)
-    const int quad = warp & 3, half = (warp - 2) >> 2;
+    const int quad = warp & 3, part = (warp - 2) >> 2;          // TMEM lane quadrant, 16-column quarter of a sub-block
     const int r = quad * 32 + lane, qi = q0 + r;
-    const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16);
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(part * PC);
     const float scale_log2 = scale * kLog2e;
     const int64_t li = ((int64_t)b * H + h) * S + qi;
     const float L2 = (qi < S) ? lse[li] * kLog2e : INFINITY;   // +inf => P = 0 for rows past the sequence end
     const float Dls = (qi < S) ? delta[li] * scale : 0.f;
     const int lo = kVarlen ? seg_start[(int64_t)b * S + min(qi, S - 1)] : 0;
     const int lo_max = kVarlen ? seg_start[(int64_t)b * S + min(q0 + TQ - 1, S - 1)] : 0;
-    int bb = 0, kbase = jt0 * TK + half * 32;      // TMEM buffer of the sub-block and this warp's first key in it
-    uint32_t bbph = 0;
-    auto sub = [&](auto diag_tag) {
-      constexpr bool DIAG = decltype(diag_tag)::value;
-      PROF_WAIT(pw0, mbar_wait(&sdp_full[bb], bbph))
+    int fb = 0, bb = 0;                            // TMEM buffer of the sub-block being fetched / computed
+    uint32_t fph = 0;
+    int kbase = jt0 * TK + part * PC;              // this warp's first key of the sub-block being computed
+    // S / dP of the next sub-block into registers (asynchronous: the caller waits with tmem_ld_wait())
+    auto fetch = [&](uint32_t (&s_)[PC], uint32_t (&d_)[PC]) {
+      PROF_WAIT(pw0, mbar_wait(&sdp_full[fb], fph))
       tc_fence_after();
-      uint32_t sv_[32], dv_[32];
       __syncwarp();
-      PROF_WAIT(pw1, tmem_ld32(lane_addr + COL_S + bb * SUB + half * 32, sv_);
-                tmem_ld32(lane_addr + COL_DP + bb * SUB + half * 32, dv_);
-                tmem_ld_wait())
+      tmem_ld16(lane_addr + COL_S + fb * SUB, s_);
+      tmem_ld16(lane_addr + COL_DP + fb * SUB, d_);
+      if (++fb == NB) { fb = 0; fph ^= 1; }
+    };
+    auto compute = [&](const uint32_t (&s_)[PC], const uint32_t (&d_)[PC], auto diag_tag) {
+      constexpr bool DIAG = decltype(diag_tag)::value;
       PROF_ONLY(const long long pm0 = clock64();)
-      float f[32];
+      float f[PC];
 #pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        float x = fmaf(__uint_as_float(sv_[i]), scale_log2, -L2);
+      for (int i = 0; i < PC; ++i) {
+        float x = fmaf(__uint_as_float(s_[i]), scale_log2, -L2);
         if (DIAG && ((kbase + i > qi) || (kVarlen && kbase + i < lo))) x = -INFINITY;
-        f[i] = ex2(x) * fmaf(__uint_as_float(dv_[i]), scale, -Dls);     // P * (dP - delta) * scale
+        f[i] = ex2(x) * fmaf(__uint_as_float(d_[i]), scale, -Dls);     // P * (dP - delta) * scale
       }
-      // dS as bf16 pairs (key, key+1) over the first 16 of this warp's own 32 dP columns: the A operand of dQ += dS K
-      uint32_t dw[16];
+      // dS as bf16 pairs (key, key+1) over the first 8 of this warp's own 16 dP columns: the A operand of dQ += dS K
+      uint32_t dw[PC / 2];
 #pragma unroll
-      for (int j = 0; j < 16; ++j) dw[j] = pack_bf16(f[2 * j], f[2 * j + 1]);
-      tmem_st16(lane_addr + COL_DP + bb * SUB + half * 32, dw);
+      for (int j = 0; j < PC / 2; ++j) dw[j] = pack_bf16(f[2 * j], f[2 * j + 1]);
+      tmem_st8(lane_addr + COL_DP + bb * SUB, dw);
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&ds_full[bb]);
       PROF_ONLY(pw2 += clock64() - pm0;)
-      if (++bb == NB) { bb = 0; bbph ^= 1; }
+      if (++bb == NB) bb = 0;
       kbase += SUB;
     };
-    for (int u = 0; u < nsub - 2; ++u) {
-      if (kVarlen && kbase - half * 32 < lo_max) sub(std::true_type{});
-      else sub(std::false_type{});
+    auto step = [&](const uint32_t (&s_)[PC], const uint32_t (&d_)[PC], bool diag) {
+      if (diag) compute(s_, d_, std::true_type{});
+      else compute(s_, d_, std::false_type{});
+    };
+    uint32_t sa[PC], da[PC], sb[PC], db[PC];
+    fetch(sa, da);
+    tmem_ld_wait();
+    for (int t = 0; t < nblk; ++t) {               // two sub-blocks per 128-key tile; the last tile is the diagonal one
+      const bool last = t == nblk - 1;
+      fetch(sb, db);
+      step(sa, da, last || (kVarlen && kbase - part * PC < lo_max));
+      PROF_WAIT(pw1, tmem_ld_wait())
+      if (!last) fetch(sa, da);
+      step(sb, db, last || (kVarlen && kbase - part * PC < lo_max));
+      PROF_WAIT(pw1, tmem_ld_wait())
     }
-    sub(std::true_type{});
-    sub(std::true_type{});
     PROF_ONLY(if (blockIdx.x == 0 && lane == 0 && (warp == 2 || warp == 7)) {
       long long* o = g_attn_prof + (warp == 2 ? 8 : 16);
       o[0] = clock64() - pt0; o[1] = pw0; o[2] = pw1; o[3] = pw2;
@@ -617,14 +636,14 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     mbar_wait(acc_full, 0);
     tc_fence_after();
     {
-      uint32_t v[32];
+      uint32_t v[PC];
       __syncwarp();
-      tmem_ld32(lane_addr + COL_DQ + half * 32, v);
+      tmem_ld16(lane_addr + COL_DQ, v);
       tmem_ld_wait();
       if (qi < S) {
-        bf16* dp_ = dq + ((int64_t)b * S + qi) * lddq + (int64_t)h * THD + half * 32;
+        bf16* dp_ = dq + ((int64_t)b * S + qi) * lddq + (int64_t)h * THD + part * PC;
 #pragma unroll
-        for (int c = 0; c < 32; c += 8) {
+        for (int c = 0; c < PC; c += 8) {
           uint32_t w[4];
           w[0] = pack_bf16(__uint_as_float(v[c + 0]), __uint_as_float(v[c + 1]));
           w[1] = pack_bf16(__uint_as_float(v[c + 2]), __uint_as_float(v[c + 3]));
@@ -632,7 +651,7 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
           w[3] = pack_bf16(__uint_as_float(v[c + 6]), __uint_as_float(v[c + 7]));
           // gradient w.r.t. the un-rotated q: the inverse rotation of the (bf16) gradient, as csm_rope(inverse) would do
           // (packing: positions restart at every segment)
-          if (rope_cache) rope_rotate8(w, rope_cache + (int64_t)(qi - lo) * THD, (half * 32 + c) >> 1, -1.f);
+          if (rope_cache) rope_rotate8(w, rope_cache + (int64_t)(qi - lo) * THD, (part * PC + c) >> 1, -1.f);
           *reinterpret_cast<uint4*>(dp_ + c) = make_uint4(w[0], w[1], w[2], w[3]);
         }
       }
@@ -695,7 +714,7 @@ attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
     for (int i = 0; i < 3; ++i) {
       mbar_init(&qd_full[i], 1); mbar_init(&qd_empty[i], 1);
       mbar_init(&sdp_full[i], 1);
-      mbar_init(&pt_full[i], 8);
+      mbar_init(&pt_full[i], kBwdCW);
     }
     mbar_init(acc_full, 1);
     mbar_fence_init();
@@ -779,14 +798,16 @@ attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
     }
   } else {
     PROF_ONLY(long long pw0 = 0, pw1 = 0, pw2 = 0, pw3 = 0; const long long pt0 = clock64();)
-    const int quad = warp & 3, half = (warp - 2) >> 2;
+    const int quad = warp & 3, part = (warp - 2) >> 2;          // TMEM lane quadrant, 16-column quarter of a sub-block
     const int r = quad * 32 + lane, kj = k0 + r;               // this thread's key
-    const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16);
+    const uint32_t lane_base = tmem_base + ((uint32_t)(quad * 32) << 16);
+    const uint32_t lane_addr = lane_base + (uint32_t)(part * PC);
     const float scale_log2 = scale * kLog2e;
-    const int ctid = threadIdx.x - 64;                         // 0..255 among the compute warps
+    const int ctid = threadIdx.x - 64;                         // 0..511 among the compute warps
     // per 128-query tile: lse*log2e (+inf past the sequence end => P = 0) and delta*scale, staged through smem once
-    // per CTA; the global load for tile it+1 is issued one tile early so its latency hides behind tile it's math
-    // (raw value only: scaling it here would make the thread wait for the load right away)
+    // per CTA by the first 256 compute threads; the global load for tile it+1 is issued one tile early so its latency
+    // hides behind tile it's math (raw value only: scaling it here would make the thread wait for the load right away)
+    const bool stager = ctid < 256;
     const float ld_mul = ctid < 128 ? kLog2e : scale;
     const int hi = kVarlen ? seg_end[(int64_t)b * S + min(kj, S - 1)] : S;              // this key's last query + 1
     const int hi_min = kVarlen ? seg_end[(int64_t)b * S + min(k0, S - 1)] : S;          // earliest segment end of the tile
@@ -798,71 +819,80 @@ attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
       if (q >= S) return ctid < 128 ? INFINITY : 0.f;
       return __ldg((ctid < 128 ? lse : delta) + li);
     };
-    float ld_next = load_ld(0, 0);
-    int bb = 0;
-    uint32_t bbph = 0;
-    auto sub = [&](int qb, int hq, const float* sLD, auto diag_tag) {
-      constexpr bool DIAG = decltype(diag_tag)::value;
-      const int col0 = hq * SUB + half * 32;                   // first query column (inside the 128-query tile)
-      const int qbase = qb * TQ + col0;
-      PROF_WAIT(pw0, mbar_wait(&sdp_full[bb], bbph))
+    float ld_next = stager ? load_ld(0, 0) : 0.f;
+    int fb = 0, bb = 0;                            // TMEM buffer of the sub-block being fetched / computed
+    uint32_t fph = 0;
+    // S^T / dP^T of the next sub-block into registers (asynchronous: the caller waits with tmem_ld_wait())
+    auto fetch = [&](uint32_t (&s_)[PC], uint32_t (&d_)[PC]) {
+      PROF_WAIT(pw0, mbar_wait(&sdp_full[fb], fph))
       tc_fence_after();
-      uint32_t sv_[32], dv_[32];
       __syncwarp();
-      PROF_WAIT(pw1, tmem_ld32(lane_addr + COL_ST + bb * SUB + half * 32, sv_);
-                tmem_ld32(lane_addr + COL_DPT + bb * SUB + half * 32, dv_);
-                tmem_ld_wait())
+      tmem_ld16(lane_addr + COL_ST + fb * SUB, s_);
+      tmem_ld16(lane_addr + COL_DPT + fb * SUB, d_);
+      if (++fb == NB) { fb = 0; fph ^= 1; }
+    };
+    auto compute = [&](const uint32_t (&s_)[PC], const uint32_t (&d_)[PC], int qb, int hq, const float* sLD, auto diag_tag) {
+      constexpr bool DIAG = decltype(diag_tag)::value;
       PROF_ONLY(const long long pm0 = clock64();)
-      float pf[32], df[32];
+      const int col0 = hq * SUB + part * PC;                   // first query column (inside the 128-query tile)
+      const int qbase = qb * TQ + col0;
       const float4* L4 = reinterpret_cast<const float4*>(sLD + col0);
       const float4* D4 = reinterpret_cast<const float4*>(sLD + 128 + col0);
+      // bf16 pairs (q, q+1) back into the first 8 of this warp's own 16 columns of each buffer
+      uint32_t pw[PC / 2], dw[PC / 2];
 #pragma unroll
-      for (int i4 = 0; i4 < 8; ++i4) {
+      for (int i4 = 0; i4 < PC / 4; ++i4) {
         const float4 Lq = L4[i4], Dq = D4[i4];
         const float Ls[4] = {Lq.x, Lq.y, Lq.z, Lq.w}, Ds[4] = {Dq.x, Dq.y, Dq.z, Dq.w};
+        float pf[4], df[4];
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
           const int i = i4 * 4 + t;
-          float x = fmaf(__uint_as_float(sv_[i]), scale_log2, -Ls[t]);
+          float x = fmaf(__uint_as_float(s_[i]), scale_log2, -Ls[t]);
           if (DIAG && ((kj > qbase + i) || (kVarlen && qbase + i >= hi))) x = -INFINITY;
-          const float pv = ex2(x);
-          pf[i] = pv;
-          df[i] = pv * fmaf(__uint_as_float(dv_[i]), scale, -Ds[t]);
+          pf[t] = ex2(x);
+          df[t] = pf[t] * fmaf(__uint_as_float(d_[i]), scale, -Ds[t]);
         }
+        pw[2 * i4] = pack_bf16(pf[0], pf[1]);
+        pw[2 * i4 + 1] = pack_bf16(pf[2], pf[3]);
+        dw[2 * i4] = pack_bf16(df[0], df[1]);
+        dw[2 * i4 + 1] = pack_bf16(df[2], df[3]);
       }
-      // bf16 pairs (q, q+1) back into the first 16 of this warp's own 32 columns of each buffer
-      uint32_t pw[16], dw[16];
-#pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        pw[j] = pack_bf16(pf[2 * j], pf[2 * j + 1]);
-        dw[j] = pack_bf16(df[2 * j], df[2 * j + 1]);
-      }
-      tmem_st16(lane_addr + COL_ST + bb * SUB + half * 32, pw);
-      tmem_st16(lane_addr + COL_DPT + bb * SUB + half * 32, dw);
+      tmem_st8(lane_addr + COL_ST + bb * SUB, pw);
+      tmem_st8(lane_addr + COL_DPT + bb * SUB, dw);
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&pt_full[bb]);
       PROF_ONLY(pw2 += clock64() - pm0;)
-      if (++bb == NB) { bb = 0; bbph ^= 1; }
+      if (++bb == NB) bb = 0;
     };
+    auto step = [&](const uint32_t (&s_)[PC], const uint32_t (&d_)[PC], int qb, int hq, const float* sLD, bool diag) {
+      if (diag) compute(s_, d_, qb, hq, sLD, std::true_type{});
+      else compute(s_, d_, qb, hq, sLD, std::false_type{});
+    };
+    uint32_t sa[PC], da[PC], sb[PC], db[PC];
+    fetch(sa, da);
+    tmem_ld_wait();
     int par = 0;                                  // which half of the lse/delta staging buffer this tile uses
     for (int hh = 0; hh < rep; ++hh) {
       for (int qt = 0; qt < nq_iter; ++qt) {
         const int qb = kvb + qt;
+        const bool last = hh == rep - 1 && qt == nq_iter - 1;
         float* sLD = reinterpret_cast<float*>(smem + DK_LD) + par * 256;
         par ^= 1;
-        sLD[ctid] = ld_next * ld_mul;
-        PROF_WAIT(pw3, named_bar_sync(1, 256))
-        {
+        if (stager) sLD[ctid] = ld_next * ld_mul;
+        PROF_WAIT(pw3, named_bar_sync(1, kBwdCW * 32))
+        if (stager) {
           const bool wrap = qt + 1 == nq_iter;
-          if (!wrap || hh + 1 < rep) ld_next = load_ld(wrap ? hh + 1 : hh, wrap ? 0 : qt + 1);
+          if (!last) ld_next = load_ld(wrap ? hh + 1 : hh, wrap ? 0 : qt + 1);
         }
-#pragma unroll
-        for (int hq = 0; hq < 2; ++hq) {
-          if (qt == 0 || (kVarlen && qb * TQ + hq * SUB + SUB > hi_min)) sub(qb, hq, sLD, std::true_type{});
-          else sub(qb, hq, sLD, std::false_type{});
-        }
+        fetch(sb, db);
+        step(sa, da, qb, 0, sLD, qt == 0 || (kVarlen && qb * TQ + SUB > hi_min));
+        PROF_WAIT(pw1, tmem_ld_wait())
+        if (!last) fetch(sa, da);
+        step(sb, db, qb, 1, sLD, qt == 0 || (kVarlen && qb * TQ + 2 * SUB > hi_min));
+        PROF_WAIT(pw1, tmem_ld_wait())
       }
     }
     PROF_ONLY(if (blockIdx.x == 0 && lane == 0 && (warp == 2 || warp == 7)) {
@@ -871,15 +901,14 @@ attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
     })
     mbar_wait(acc_full, 0);
     tc_fence_after();
-    // warps 2..5 store dK rows, warps 6..9 store dV rows (64 columns each)
-    bf16* outp = half == 0 ? dk + ((int64_t)b * S + kj) * lddk + (int64_t)kvh * THD
-                           : dv + ((int64_t)b * S + kj) * lddv + (int64_t)kvh * THD;
-    const uint32_t col = half == 0 ? COL_DK : COL_DV;
-#pragma unroll
-    for (int c = 0; c < THD; c += 32) {
+    // quarters 0, 1 store the two 32-column halves of the dK rows, quarters 2, 3 those of the dV rows
+    {
+      const int c0 = (part & 1) * 32;
+      bf16* outp = part < 2 ? dk + ((int64_t)b * S + kj) * lddk + (int64_t)kvh * THD + c0
+                            : dv + ((int64_t)b * S + kj) * lddv + (int64_t)kvh * THD + c0;
       uint32_t v[32];
       __syncwarp();
-      tmem_ld32(lane_addr + col + c, v);
+      tmem_ld32(lane_base + (part < 2 ? COL_DK : COL_DV) + c0, v);
       tmem_ld_wait();
       if (kj < S) {
 #pragma unroll
@@ -889,10 +918,10 @@ attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
           w[1] = pack_bf16(__uint_as_float(v[c8 + 2]), __uint_as_float(v[c8 + 3]));
           w[2] = pack_bf16(__uint_as_float(v[c8 + 4]), __uint_as_float(v[c8 + 5]));
           w[3] = pack_bf16(__uint_as_float(v[c8 + 6]), __uint_as_float(v[c8 + 7]));
-          if (rope_cache && half == 0)                                                               // dK only
+          if (rope_cache && part < 2)                                                                // dK only
             rope_rotate8(w, rope_cache + (int64_t)(kj - (kVarlen ? seg_start[(int64_t)b * S + kj] : 0)) * THD,
-                         (c + c8) >> 1, -1.f);
-          *reinterpret_cast<uint4*>(outp + c + c8) = make_uint4(w[0], w[1], w[2], w[3]);
+                         (c0 + c8) >> 1, -1.f);
+          *reinterpret_cast<uint4*>(outp + c8) = make_uint4(w[0], w[1], w[2], w[3]);
         }
       }
     }
