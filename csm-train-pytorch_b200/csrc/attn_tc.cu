@@ -440,6 +440,25 @@ __device__ __forceinline__ void issue_nt_64(uint32_t d_tmem, uint32_t a_smem, ui
     umma_bf16(d_tmem, ad + (uint64_t)((kk * 32) >> 4), bd + (uint64_t)((kk * 32) >> 4), idesc, kk ? 1u : 0u);
 }
 
+// D[128 x 64] = A[TMEM: 128 lanes x 64 k as bf16 pairs in 32 consecutive columns] * B[64 x 64]^T (K-major smem tile)
+__device__ __forceinline__ void issue_ts_nt_64(uint32_t d_tmem, uint32_t a_tmem, uint32_t b_smem) {
+  constexpr uint32_t idesc = make_idesc_bf16(128, SUB, 0, 0);
+  const uint64_t bd = make_smem_desc(b_smem, 16, 1024);
+#pragma unroll
+  for (int kk = 0; kk < THD / 16; ++kk)
+    umma_bf16_ts(d_tmem, a_tmem + (uint32_t)(kk * 8), bd + (uint64_t)((kk * 32) >> 4), idesc, kk ? 1u : 0u);
+}
+
+// Copies this thread's 16-element slice of row `r` of a [128][64] bf16 tile (128B-swizzled, as TMA wrote it) into 8 TMEM
+// columns as (k, k+1) pairs: the A-operand layout of a K-major A in TMEM.  `part` selects elements 16*part .. 16*part+15.
+__device__ __forceinline__ void smem_row_to_tmem_a(const uint8_t* tile, int r, int part, uint32_t taddr) {
+  const uint8_t* row = tile + r * 128;
+  const uint4 c0 = *reinterpret_cast<const uint4*>(row + (((2 * part) ^ (r & 7)) << 4));
+  const uint4 c1 = *reinterpret_cast<const uint4*>(row + (((2 * part + 1) ^ (r & 7)) << 4));
+  const uint32_t w[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+  tmem_st8(taddr, w);
+}
+
 constexpr int DQ_Q = 0;                              // 16 KB  Q tile
 constexpr int DQ_DO = DQ_Q + TQ * THD * 2;           // 16 KB  dO tile
 constexpr int KST = 3;                               // K/V (resp. Q/dO) TMA ring depth of the backward kernels
@@ -464,6 +483,7 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
   uint64_t* kv_empty = bars + 4;      // [KST]
   uint64_t* sdp_full = bars + 7;      // [NB] S and dP sub-block ready in TMEM
   uint64_t* ds_full = bars + 13;      // [NB] dS written back over the dP columns as bf16 pairs (8 warp arrivals)
+  uint64_t* qa_full = bars + 16;      // Q and dO copied into TMEM as A operands (kBwdCW warp arrivals)
   uint64_t* acc_full = bars + 17;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
   static_assert(KST == 3 && NB == 3, "barrier slots");
@@ -489,6 +509,7 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       mbar_init(&sdp_full[i], 1);
       mbar_init(&ds_full[i], kBwdCW);
     }
+    mbar_init(qa_full, kBwdCW);
     mbar_init(acc_full, 1);
     mbar_fence_init();
   }
@@ -497,7 +518,8 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  constexpr uint32_t COL_S = 0, COL_DP = NB * SUB, COL_DQ = 2 * NB * SUB;   // 192 + 192 + 64 columns
+  // 192 (S) + 192 (dP) + 64 (dQ) + 32 (Q as A operand) + 32 (dO as A operand) = 512 columns
+  constexpr uint32_t COL_S = 0, COL_DP = NB * SUB, COL_DQ = 2 * NB * SUB, COL_QA = COL_DQ + THD, COL_DOA = COL_QA + THD / 2;
 
   if (warp == 0) {
     if (elect_one()) {
@@ -519,7 +541,6 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
   } else if (warp == 1) {
     {
       PROF_ONLY(long long pw0 = 0, pw1 = 0, pw2 = 0; const long long pt0 = clock64();)
-      const uint32_t sq = smem_u32(smem + DQ_Q), sdo = smem_u32(smem + DQ_DO);
       // S/dP(u + NB) overwrites the TMEM buffer of sub-block u.  No "buffer free" barrier is needed: it is issued after
       // dQ(u) — the last reader of that buffer — and tcgen05.mma instructions of one thread execute in issue order (the
       // forward kernel relies on the same property); the compute warps' loads of S/dP(u) completed before ds_full(u).
@@ -538,14 +559,17 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
           }
           const uint32_t sk = smem_u32(smem + DQ_K + p_st * (TK * THD * 2)) + p_hk * (SUB * 128);
           const uint32_t sv = smem_u32(smem + DQ_V + p_st * (TK * THD * 2)) + p_hk * (SUB * 128);
-          issue_nt_64(tmem_base + COL_S + p_bb * SUB, sq, sk);     // S  = Q K_sub^T
-          issue_nt_64(tmem_base + COL_DP + p_bb * SUB, sdo, sv);   // dP = dO V_sub^T
+          // Q and dO are read as A operands out of TMEM (copied there once per CTA): an N=64 MMA with both operands in
+          // smem is operand-fetch-bound (6 KB per 32 math cycles: 51 cycles measured, 41 with A in TMEM) and shares the
+          // 128 B/clk with the TMA writes of the K/V ring
+          issue_ts_nt_64(tmem_base + COL_S + p_bb * SUB, tmem_base + COL_QA, sk);     // S  = Q K_sub^T
+          issue_ts_nt_64(tmem_base + COL_DP + p_bb * SUB, tmem_base + COL_DOA, sv);   // dP = dO V_sub^T
           umma_commit(&sdp_full[p_bb]);
           if (++p_bb == NB) p_bb = 0;
           if (p_hk) { if (++p_st == KST) { p_st = 0; p_stph ^= 1; } }
           p_hk ^= 1;
         };
-        mbar_wait(q_full, 0);
+        mbar_wait(qa_full, 0);
         tc_fence_after();
         for (int u = 0; u < NB && u < nsub; ++u) issue_sdp();
         int c_st = 0, c_bb = 0, c_hk = 0;
@@ -617,6 +641,14 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       if (diag) compute(s_, d_, std::true_type{});
       else compute(s_, d_, std::false_type{});
     };
+    // Q and dO rows -> TMEM (A operands of S = Q K^T and dP = dO V^T), once per CTA
+    mbar_wait(q_full, 0);
+    smem_row_to_tmem_a(smem + DQ_Q, r, part, tmem_base + ((uint32_t)(quad * 32) << 16) + COL_QA + (uint32_t)(part * 8));
+    smem_row_to_tmem_a(smem + DQ_DO, r, part, tmem_base + ((uint32_t)(quad * 32) << 16) + COL_DOA + (uint32_t)(part * 8));
+    tmem_st_wait();
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(qa_full);
     uint32_t sa[PC], da[PC], sb[PC], db[PC];
     fetch(sa, da);
     tmem_ld_wait();
