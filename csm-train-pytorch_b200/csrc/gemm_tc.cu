@@ -259,6 +259,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     w.tile = t;
     return t >= 0;
   };
+  // the same for a caller that is ONE thread (the MMA issuer): no warp-level synchronisation around the arrive
+  auto take_tile_1t = [&](int it, WorkItem& w) -> bool {
+    if (!dyn) return next_item(sk, first_tile, tile_step, num_tiles, kb_total, it, w);
+    w.kb0 = 0; w.kb1 = kb_total; w.kind = 0;
+    if (it == 0) { w.tile = first_tile; return first_tile < num_tiles; }
+    const int slot = (it - 1) & 3;
+    mbar_wait(&tq_full[slot], (uint32_t)((it - 1) >> 2) & 1u);
+    const int t = (int)(tq[slot] & 0xfffffu) - 1;
+    mbar_arrive(&tq_empty[slot]);                 // (only the leader CTA's MMA warp runs)
+    w.tile = t;
+    return t >= 0;
+  };
 
   if (warp == 0) {
     // ===================== TMA producer (warp-uniform control flow, one elected lane issues) =====================
@@ -364,30 +376,31 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     __syncwarp();
   } else if (warp == 1) {
-    // ===================== MMA issuer (warp-uniform control flow, one elected lane issues) =====================
+    // ===================== MMA issuer: ONE elected thread runs the whole loop =====================
+    // (a warp-wide mbarrier wait + elect + __syncwarp around every k-block costs ~65 cycles even when the barrier is
+    // already open — tools/ubench/mma_rate.cu k4 — and delays the hand-over of finished accumulators and smem stages)
     constexpr uint32_t idesc = make_idesc_bf16(kCta2 ? 2 * BM : BM, BN, kTransA ? 1 : 0, kTransB ? 1 : 0);
-    int stage = 0; uint32_t phase = 0;
-    int acc = 0; uint32_t acc_phase = 0;
-    WorkItem w;
-    for (int it = 0; rank == 0 && take_tile(it, w); ++it) {
-      // (pair mode: the leader issues for both CTAs)
-      mbar_wait(&tempty[acc], acc_phase ^ 1);
-      tc_fence_after();
-      const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
-      uint32_t tile_idesc = idesc;
-      if (!kTransB && (kEpi == EPI_STORE || kEpi == EPI_CE_PARTIAL || kEpi == EPI_CE_DLOGITS) && p.narrow_tail) {
-        // K-major B: smem rows are output columns, rows past N are TMA zero fill.  A pair takes N/2 rows from each
-        // CTA (columns [0, N/2) from the leader's half), so the narrow form needs every valid column in the leader.
-        int g, mb, nb;
-        tile_coords(w.tile, tile_m, p.num_n, g, mb, nb);
-        const int valid = (int)min((int64_t)BN, p.N - (int64_t)nb * BN);
-        const int n_eff = kCta2 ? (valid > BN / 2 ? BN : ((2 * valid + 15) & ~15)) : ((valid + 15) & ~15);
-        tile_idesc = make_idesc_bf16(kCta2 ? 2 * BM : BM, n_eff, kTransA ? 1 : 0, 0);
-      }
-      for (int kb = w.kb0; kb < w.kb1; ++kb) {
-        mbar_wait(&full[stage], phase);
+    if (rank == 0 && elect_one()) {                  // (pair mode: the leader issues for both CTAs)
+      int stage = 0; uint32_t phase = 0;
+      int acc = 0; uint32_t acc_phase = 0;
+      WorkItem w;
+      for (int it = 0; take_tile_1t(it, w); ++it) {
+        mbar_wait(&tempty[acc], acc_phase ^ 1);
         tc_fence_after();
-        if (elect_one()) {
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+        uint32_t tile_idesc = idesc;
+        if (!kTransB && (kEpi == EPI_STORE || kEpi == EPI_CE_PARTIAL || kEpi == EPI_CE_DLOGITS) && p.narrow_tail) {
+          // K-major B: smem rows are output columns, rows past N are TMA zero fill.  A pair takes N/2 rows from each
+          // CTA (columns [0, N/2) from the leader's half), so the narrow form needs every valid column in the leader.
+          int g, mb, nb;
+          tile_coords(w.tile, tile_m, p.num_n, g, mb, nb);
+          const int valid = (int)min((int64_t)BN, p.N - (int64_t)nb * BN);
+          const int n_eff = kCta2 ? (valid > BN / 2 ? BN : ((2 * valid + 15) & ~15)) : ((valid + 15) & ~15);
+          tile_idesc = make_idesc_bf16(kCta2 ? 2 * BM : BM, n_eff, kTransA ? 1 : 0, 0);
+        }
+        for (int kb = w.kb0; kb < w.kb1; ++kb) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
           const uint32_t sb = sa + BM * BK * 2;
           // K-major: 8-row groups 1024 B apart, K advance = 32 B inside the swizzle atom.
@@ -404,16 +417,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
           // frees the smem slot (in both CTAs of a pair) once these MMAs have read it
           if (kCta2) umma_commit_2sm(&empty[stage], 3); else umma_commit(&empty[stage]);
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
-        __syncwarp();
-        if (++stage == kStages) { stage = 0; phase ^= 1; }
-      }
-      if (elect_one()) {                               // accumulator complete -> epilogue (of both CTAs)
+        // accumulator complete -> epilogue (of both CTAs)
         if (kCta2) umma_commit_2sm(&tfull[acc], 3); else umma_commit(&tfull[acc]);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
-      __syncwarp();
-      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
+    __syncwarp();
   } else {
     // ===================== epilogue (4 warps, TMEM lane quadrant = warp % 4) =====================
     const int quad = warp & 3;
