@@ -475,6 +475,7 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
                       const float* __restrict__ lse, const float* __restrict__ delta, bf16* __restrict__ dq, int S,
                       int H, int KV, int64_t lddq, float scale, const float* __restrict__ rope_cache,
                       const int32_t* __restrict__ seg_start) {
+  PROF_ONLY(const long long p_entry = clock64();)
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + DQ_BAR);
@@ -518,6 +519,7 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  PROF_ONLY(if (blockIdx.x == 0 && threadIdx.x == 64) g_attn_prof[64] = clock64() - p_entry;)   // setup done
   // 192 (S) + 192 (dP) + 64 (dQ) + 32 (Q as A operand) + 32 (dO as A operand) = 512 columns
   constexpr uint32_t COL_S = 0, COL_DP = NB * SUB, COL_DQ = 2 * NB * SUB, COL_QA = COL_DQ + THD, COL_DOA = COL_QA + THD / 2;
 
@@ -571,7 +573,9 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
         };
         mbar_wait(qa_full, 0);
         tc_fence_after();
+        PROF_ONLY(if (blockIdx.x == 0) g_attn_prof[65] = clock64() - p_entry;)   // Q/dO in TMEM
         for (int u = 0; u < NB && u < nsub; ++u) issue_sdp();
+        PROF_ONLY(if (blockIdx.x == 0) g_attn_prof[66] = clock64() - p_entry;)   // first S/dP issued
         int c_st = 0, c_bb = 0, c_hk = 0;
         uint32_t c_bbph = 0;
         for (int u = 0; u < nsub; ++u) {
@@ -652,6 +656,7 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     uint32_t sa[PC], da[PC], sb[PC], db[PC];
     fetch(sa, da);
     tmem_ld_wait();
+    PROF_ONLY(if (blockIdx.x == 0 && threadIdx.x == 64) g_attn_prof[67] = clock64() - p_entry;)   // first S/dP in registers
     for (int t = 0; t < nblk; ++t) {               // two sub-blocks per 128-key tile; the last tile is the diagonal one
       const bool last = t == nblk - 1;
       fetch(sb, db);
@@ -665,8 +670,10 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       long long* o = g_attn_prof + (warp == 2 ? 8 : 16);
       o[0] = clock64() - pt0; o[1] = pw0; o[2] = pw1; o[3] = pw2;
     })
+    PROF_ONLY(if (blockIdx.x == 0 && threadIdx.x == 64) g_attn_prof[68] = clock64() - p_entry;)   // last dS written
     mbar_wait(acc_full, 0);
     tc_fence_after();
+    PROF_ONLY(if (blockIdx.x == 0 && threadIdx.x == 64) g_attn_prof[69] = clock64() - p_entry;)   // dQ complete
     {
       uint32_t v[PC];
       __syncwarp();
@@ -695,6 +702,7 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
   }
+  PROF_ONLY(if (blockIdx.x == 0 && threadIdx.x == 64) g_attn_prof[70] = clock64() - p_entry;)   // exit
 }
 
 constexpr int DK_K = 0;                              // 16 KB  K tile

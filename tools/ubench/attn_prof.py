@@ -46,3 +46,6 @@ for w, base in (("2", 8), ("7", 16)):
 show("dkdv CTA 0  MMA warp", 32, ["wait Q/dO tile (TMA)", "wait S/dP buffer free (dV/dK MMA done)", "wait P/dS written (compute warps)"])
 for w, base in (("2", 40), ("7", 48)):
     show(f"dkdv CTA 0  compute warp {w}", base, ["wait S^T/dP^T ready (MMA)", "tcgen05.ld x2 + wait", "math + tcgen05.st x2 + wait + arrive", "lse/delta staging barrier"])
+
+print("dq CTA 0 timeline (cycles since kernel entry): setup done %d, Q/dO in TMEM %d, first S/dP issued %d, first S/dP in registers %d, "
+      "last dS written %d, dQ complete %d, exit %d" % tuple(p[64:71]))
