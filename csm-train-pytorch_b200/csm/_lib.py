@@ -62,6 +62,11 @@ SIGNATURES = {
     "csm_attn_decode": (_i32, [_ptr] * 4 + [_i32] * 5 + [_i64] * 4 + [_f32, _ptr]),
     "csm_lora_mask_rows": (_i32, [_ptr, _i64, _i64, _i32, _ptr, _i32, _i32, _ptr]),
     "csm_lora_dropout": (_i32, [_ptr, _ptr, _i64, _i64, _i64, _i64, _f32, _ptr, _i64, _i32, _ptr]),
+    "csm_set_pdl": (None, [_i32]),
+    "csm_set_skinny_mode": (None, [_i32]),
+    "csm_skinny_supported": (_i32, [_i32, _ptr, _ptr, _ptr] + [_i64] * 6 + [_i32]),
+    "csm_skinny_rowdot": (_i32, [_ptr] * 3 + [_i64] * 6 + [_i32, _f32, _ptr]),
+    "csm_skinny_coldot": (_i32, [_ptr] * 3 + [_i64] * 6 + [_i32, _f32, _ptr]),
     "csm_f32_to_bf16": (_i32, [_ptr, _ptr, _i64, _f32, _i32, _ptr]),
     "csm_add_bf16": (_i32, [_ptr, _ptr, _ptr, _i64, _ptr]),
 }

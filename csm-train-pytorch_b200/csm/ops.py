@@ -7,6 +7,7 @@ bf16 unless stated otherwise.
 from __future__ import annotations
 
 import math
+import os as _os
 from typing import Optional, Tuple
 
 import torch
@@ -57,6 +58,11 @@ def set_attn_backend(b: int) -> None:
     global _attn_backend
     _attn_backend = b
     _lib.load().csm_set_attn_backend(b)
+
+
+def set_pdl(on: int) -> None:
+    """Programmatic dependent launch between the step's kernels (csrc/common.cuh): 1 (default, or CSM_PDL) / 0."""
+    _lib.load().csm_set_pdl(int(on))
 
 
 def set_attn_fwd_variant(v: int) -> None:
@@ -236,6 +242,43 @@ def _splitk_choice(M: int, N: int, K: int) -> int:
 
 
 
+SKINNY_ENABLED = _os.environ.get("CSM_SKINNY", "1") != "0"
+
+
+def set_skinny_mode(m: int) -> None:
+    """A/B hook: 1 (default) tall-skinny LoRA products run on the streaming mma.sync kernels (csrc/skinny.cu), 0 = on
+    the tcgen05 GEMM with a split reduction."""
+    global SKINNY_ENABLED
+    SKINNY_ENABLED = bool(m)
+
+
+def _skinny(a, b, trans_a, trans_b, out, M, N, K, alpha) -> bool:
+    """Routes out[M,N] = alpha * op(a) op(b) to csrc/skinny.cu when one output dimension is <= 64 and the other operand
+    is a long stream: rowdot (t = x A^T, dts = dy B) or coldot (dB = dy^T t, dA = dts^T x).  False: not taken."""
+    lib = _lib.load()
+    if not trans_a:
+        if N > 64 or M < 256:
+            return False
+        lay = 1 if trans_b else 0
+        args = (_p(a), _p(b), _p(out), M, K, N, a.stride(0), b.stride(0), out.stride(0), lay)
+        if not lib.csm_skinny_supported(0, *args):
+            return False
+        _lib.check(lib.csm_skinny_rowdot(*args, alpha, _st()), "skinny_rowdot")
+        return True
+    if not trans_b or K < 256:
+        return False
+    if N <= 64 and M > N:            # out[C, R]: X = a [rows, C], T = b [rows, R]
+        args = (_p(a), _p(b), _p(out), K, M, N, a.stride(0), b.stride(0), out.stride(0), 0)
+    elif M <= 64:                    # out[R, C]: X = b [rows, C], T = a [rows, R]
+        args = (_p(b), _p(a), _p(out), K, N, M, b.stride(0), a.stride(0), out.stride(0), 1)
+    else:
+        return False
+    if not lib.csm_skinny_supported(1, *args):
+        return False
+    _lib.check(lib.csm_skinny_coldot(*args, alpha, _st()), "skinny_coldot")
+    return True
+
+
 def gemm_rope(a, b, cache, seq_len: int, rope_cols: int, head_dim: int, *, a2=None, b2=None, positions=None):
     """out = a @ b^T (+ a2 @ b2^T) with RoPE applied to columns [0, rope_cols) (heads of head_dim, position = row %
     seq_len): the fused q|k|v projection.  One launch when the tcgen05 GEMM takes the shape, else gemm + rope."""
@@ -285,8 +328,10 @@ def gemm(a, b, *, trans_a: bool = False, trans_b: bool = False, out: Optional[to
         out = torch.empty(M, N, dtype=out_dtype, device=a.device)
     assert out.shape == (M, N) and out.stride(1) == 1
     be = _backend_override if backend is None else backend
-    splits = _splitk_choice(M, N, K) if (be != GEMM_SIMT and a2 is None and residual is None and not accumulate
-                                         and out.dtype == BF16) else 0
+    plain = be != GEMM_SIMT and a2 is None and residual is None and not accumulate and out.dtype == BF16
+    if plain and SKINNY_ENABLED and _skinny(a, b, trans_a, trans_b, out, M, N, K, alpha):
+        return out
+    splits = _splitk_choice(M, N, K) if plain else 0
     if splits:
         lib = _lib.load()
         nbytes = lib.csm_gemm_splitk_workspace_bytes(M, N, splits)

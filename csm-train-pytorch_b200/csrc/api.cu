@@ -1,5 +1,6 @@
 // extern "C" surface that is not tied to one kernel file: error state, device probe, GEMM/attention dispatch.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -8,6 +9,12 @@ namespace csm {
 
 static thread_local char g_err[512] = "";
 std::atomic<int64_t> g_launches{0};
+// programmatic dependent launch between consecutive kernels of the step (common.cuh); CSM_PDL=0/1 sets the initial value
+static int pdl_env_default() {
+  const char* e = getenv("CSM_PDL");
+  return !e ? 1 : (e[0] == '0' ? 0 : (e[0] == '2' ? 2 : 1));
+}
+std::atomic<int> g_pdl{pdl_env_default()};
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -131,6 +138,7 @@ extern "C" void csm_set_gemm_streamk_mode(int32_t mode) { csm::gemm_tc_set_strea
 extern "C" void csm_set_gemm_narrow_tail_mode(int32_t mode) { csm::gemm_tc_set_narrow_tail_mode(mode); }
 extern "C" void csm_set_gemm_cta_pair_mode(int32_t mode) { csm::gemm_tc_set_cta_pair_mode(mode); }
 extern "C" void csm_set_gemm_dynamic_tiles(int32_t mode) { csm::gemm_tc_set_dynamic_tiles(mode); }
+extern "C" void csm_set_pdl(int32_t on) { csm::g_pdl.store(on < 0 ? 0 : (on > 2 ? 2 : on)); }
 extern "C" const char* csm_last_error(void) { return g_err; }
 extern "C" int64_t csm_launch_count(void) { return g_launches.load(); }
 

@@ -243,6 +243,8 @@ __global__ void __launch_bounds__(256)
 attn_delta_kernel(const bf16* __restrict__ o, const bf16* __restrict__ dout, float* __restrict__ delta, int B, int S,
                   int H, int64_t ldo, int64_t lddo) {
   static_assert(HD == 64, "8 lanes x 8 elements per head");
+  pdl_wait();
+  pdl_trigger();
   const int sub = threadIdx.x & 7;
   const int64_t total = (int64_t)B * S * H;                       // (row, head) pairs, head fastest
   const int64_t stride = (int64_t)gridDim.x * (blockDim.x >> 3);
@@ -476,7 +478,8 @@ static unsigned delta_grid(int64_t pairs) {
 int attn_delta_launch(const void* o, const void* dout, float* delta, int B, int S, int H, int64_t ldo,
                       cudaStream_t st) {
   const int64_t rows = (int64_t)B * H * S;
-  attn_delta_kernel<<<delta_grid(rows), 256, 0, st>>>((const bf16*)o, (const bf16*)dout, delta, B, S, H, ldo, ldo);
+  if (launch_k(attn_delta_kernel, dim3(delta_grid(rows)), dim3(256), 0, st, 1, (const bf16*)o, (const bf16*)dout, delta, B,
+               S, H, ldo, ldo) != cudaSuccess) { set_error("attn_delta: launch failed"); return CSM_ERR_CUDA; }
   CSM_CHECK_LAUNCH("attn_delta");
   return CSM_OK;
 }

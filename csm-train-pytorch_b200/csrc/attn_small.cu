@@ -177,6 +177,8 @@ attn_small_fwd_kernel(const bf16* __restrict__ q, const bf16* __restrict__ k, co
                       int64_t ldv, int64_t ldo, float scale) {
   constexpr int TB = kMaxS * HD * 2;               // bytes of one [32][HD] tile
   extern __shared__ __align__(128) uint8_t smem[];
+  pdl_wait();
+  pdl_trigger();
   const int b = blockIdx.x / KV, kvh = blockIdx.x % KV, rep = H / KV;
   const int tid = threadIdx.x, nthr = blockDim.x, warp = tid >> 5, lane = tid & 31;
   uint8_t* Ks = smem;
@@ -248,6 +250,8 @@ attn_small_bwd_kernel(const bf16* __restrict__ q, const bf16* __restrict__ k, co
   constexpr int TB = kMaxS * HD * 2;
   constexpr int PB = kMaxS * kMaxS * 2;            // bytes of one [32][32] bf16 tile
   extern __shared__ __align__(128) uint8_t smem[];
+  pdl_wait();
+  pdl_trigger();
   const int b = blockIdx.x / KV, kvh = blockIdx.x % KV, rep = H / KV;
   const int tid = threadIdx.x, nthr = blockDim.x, warp = tid >> 5, lane = tid & 31, nwarp = nthr >> 5;
   uint8_t* Ks = smem;
@@ -407,7 +411,7 @@ int attn_fwd_small_launch(const void* q, const void* k, const void* v, void* o, 
                          (int)fwd_smem_bytes(128, 4));
     attr_set = true;
   }
-#define LAUNCH(HD) attn_small_fwd_kernel<HD><<<grid, 128, smem, st>>>((const bf16*)q, (const bf16*)k, \
+#define LAUNCH(HD) launch_k(attn_small_fwd_kernel<HD>, dim3(grid), dim3(128), smem, st, 1, (const bf16*)q, (const bf16*)k, \
       (const bf16*)v, (bf16*)o, lse, S, H, KV, ldq, ldk, ldv, ldo, scale)
   if (hd == 64) LAUNCH(64); else LAUNCH(128);
 #undef LAUNCH
@@ -433,9 +437,9 @@ int attn_bwd_small_launch(const void* q, const void* k, const void* v, const voi
                          (int)bwd_smem_bytes(128, 4));
     attr_set = true;
   }
-#define LAUNCH(HD) attn_small_bwd_kernel<HD><<<grid, 128, smem, st>>>((const bf16*)q, (const bf16*)k, \
-      (const bf16*)v, lse, (const bf16*)dout, (bf16*)dq, (bf16*)dk, (bf16*)dv, S, H, KV, ldq, ldk, ldv, ldo, lddq, \
-      lddk, lddv, scale)
+#define LAUNCH(HD) launch_k(attn_small_bwd_kernel<HD>, dim3(grid), dim3(128), smem, st, 1, (const bf16*)q, (const bf16*)k, \
+      (const bf16*)v, (const float*)lse, (const bf16*)dout, (bf16*)dq, (bf16*)dk, (bf16*)dv, S, H, KV, ldq, ldk, ldv, ldo, \
+      lddq, lddk, lddv, scale)
   if (hd == 64) LAUNCH(64); else LAUNCH(128);
 #undef LAUNCH
   CSM_CHECK_LAUNCH("attn_small_bwd");

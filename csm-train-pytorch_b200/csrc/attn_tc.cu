@@ -97,6 +97,9 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
   static_assert(FST <= 4, "barrier slots");
 
+  // programmatic dependent launch (common.cuh): no global memory is touched before pdl_wait().  Packed rows read
+  // seg_start before the prologue, so they wait first; otherwise the prologue overlaps the previous kernel's tail.
+  if (kVarlen) pdl_wait();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // 1-D grid in longest-processing-time-first order: all (head, batch) CTAs of the last query tile (most key blocks)
   // are dispatched before any of the next-to-last one, ... — the causal triangle then packs to ~95 % of the SM-time
@@ -133,6 +136,8 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   constexpr uint32_t COL_S = 0, COL_PV = 128;
+  if (!kVarlen) pdl_wait();
+  pdl_trigger();
 
   // warps 0 and 1 keep warp-uniform control flow and elect one lane per TMA / tcgen05 issue (see tc::elect_one)
   if (warp == 0) {
@@ -476,6 +481,7 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
                       int H, int KV, int64_t lddq, float scale, const float* __restrict__ rope_cache,
                       const int32_t* __restrict__ seg_start) {
   PROF_ONLY(const long long p_entry = clock64();)
+  if (kVarlen) pdl_wait();            // (see attn_fwd_tc_kernel)
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + DQ_BAR);
@@ -519,6 +525,8 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (!kVarlen) pdl_wait();
+  pdl_trigger();
   PROF_ONLY(if (blockIdx.x == 0 && threadIdx.x == 64) g_attn_prof[64] = clock64() - p_entry;)   // setup done
   // 192 (S) + 192 (dP) + 64 (dQ) + 32 (Q as A operand) + 32 (dO as A operand) = 512 columns
   constexpr uint32_t COL_S = 0, COL_DP = NB * SUB, COL_DQ = 2 * NB * SUB, COL_QA = COL_DQ + THD, COL_DOA = COL_QA + THD / 2;
@@ -723,7 +731,13 @@ attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
                         const float* __restrict__ lse, const float* __restrict__ delta, bf16* __restrict__ dk,
                         bf16* __restrict__ dv, int S, int H, int KV, int64_t lddk, int64_t lddv, float scale,
                         const float* __restrict__ rope_cache, const int32_t* __restrict__ seg_start,
-                        const int32_t* __restrict__ seg_end) {
+                        const int32_t* __restrict__ seg_end, int late_wait) {
+  // late_wait (csm_set_pdl(2)): this kernel does not depend on the dQ kernel launched right before it — both read
+  // q, k, v, dO, lse, delta and write disjoint columns — so it does not wait for it: its CTAs fill the SMs the dQ
+  // kernel's tail leaves idle.  Every dQ CTA has passed its own wait before this grid can start, so everything older
+  // than the dQ kernel is complete; the wait moves to the END, which keeps "this kernel complete => all earlier
+  // kernels complete" for the successor.
+  if (kVarlen && !late_wait) pdl_wait();            // (see attn_fwd_tc_kernel)
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + DK_BAR);
@@ -764,6 +778,8 @@ attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (!kVarlen && !late_wait) pdl_wait();
+  pdl_trigger();
   constexpr uint32_t COL_ST = 0, COL_DPT = NB * SUB, COL_DK = 2 * NB * SUB, COL_DV = 2 * NB * SUB + THD;   // 512 columns
 
   if (warp == 0) {
@@ -972,6 +988,7 @@ attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
   }
+  if (late_wait) pdl_wait();
 }
 
 }  // namespace
@@ -1017,8 +1034,9 @@ int attn_fwd_tc_launch(const void* q, const void* k, const void* v, void* o, flo
   }
   dim3 grid(((S + TQ - 1) / TQ) * H * B);
   const int variant = g_attn_fwd_variant.load();
-#define FWD(V, T, P) attn_fwd_tc_kernel<V, T, P><<<grid, kAttnThreads, kAttnSmem, st>>>(tq, tk, tv, (bf16*)o, lse, S, H, KV, \
-                                                                                     ldo, scale * kLog2e, seg_start)
+  cudaError_t le = cudaSuccess;
+#define FWD(V, T, P) le = launch_k(attn_fwd_tc_kernel<V, T, P>, grid, dim3(kAttnThreads), kAttnSmem, st, 1, tq, tk, tv, (bf16*)o, \
+                              lse, S, H, KV, ldo, scale * kLog2e, seg_start)
   if (seg_start) { if (variant == 0) FWD(true, false, 0); else if (variant == 1) FWD(true, true, 0); else FWD(true, true, 4); }
   else if (variant == 0) FWD(false, false, 0);
   else if (variant == 1) FWD(false, true, 0);
@@ -1026,6 +1044,7 @@ int attn_fwd_tc_launch(const void* q, const void* k, const void* v, void* o, flo
   else if (variant == 3) FWD(false, true, 3);
   else FWD(false, true, 2);
 #undef FWD
+  if (le != cudaSuccess) { set_error("attn_fwd_tc: launch failed: %s", cudaGetErrorString(le)); return CSM_ERR_CUDA; }
   CSM_CHECK_LAUNCH("attn_fwd_tc");
   return CSM_OK;
 }
@@ -1061,22 +1080,27 @@ int attn_bwd_tc_launch(const void* q, const void* k, const void* v, const void* 
   }
   dim3 gq(((S + TQ - 1) / TQ) * H * B);
   const bool varlen = seg_start != nullptr && seg_end != nullptr;
+  const float* lse_c = lse;
+  const float* delta_c = delta;
+  const int32_t* no_seg = nullptr;
+  cudaError_t le;
   if (varlen)
-    attn_bwd_dq_tc_kernel<true><<<gq, kBwdThreads, kDqSmem, st>>>(tq, tk, tv, tdo, lse, delta, (bf16*)dq, S, H, KV, lddq,
-                                                                  scale, rope_cache, seg_start);
+    le = launch_k(attn_bwd_dq_tc_kernel<true>, gq, dim3(kBwdThreads), kDqSmem, st, 1, tq, tk, tv, tdo, lse_c, delta_c, (bf16*)dq,
+             S, H, KV, lddq, scale, rope_cache, seg_start);
   else
-    attn_bwd_dq_tc_kernel<false><<<gq, kBwdThreads, kDqSmem, st>>>(tq, tk, tv, tdo, lse, delta, (bf16*)dq, S, H, KV, lddq,
-                                                                   scale, rope_cache, nullptr);
+    le = launch_k(attn_bwd_dq_tc_kernel<false>, gq, dim3(kBwdThreads), kDqSmem, st, 1, tq, tk, tv, tdo, lse_c, delta_c,
+             (bf16*)dq, S, H, KV, lddq, scale, rope_cache, no_seg);
+  if (le != cudaSuccess) { set_error("attn_bwd_dq_tc: launch failed: %s", cudaGetErrorString(le)); return CSM_ERR_CUDA; }
   CSM_CHECK_LAUNCH("attn_bwd_dq_tc");
   dim3 gk(((S + TK - 1) / TK) * KV * B);
+  const int late = g_pdl.load(std::memory_order_relaxed) == 2 ? 1 : 0;   // dK/dV overlaps the dQ kernel's tail
   if (varlen)
-    attn_bwd_dkdv_tc_kernel<true><<<gk, kBwdThreads, kDkSmem, st>>>(tq, tk, tv, tdo, lse, delta, (bf16*)dk, (bf16*)dv, S,
-                                                                    H, KV, lddk, lddv, scale, rope_cache, seg_start,
-                                                                    seg_end);
+    le = launch_k(attn_bwd_dkdv_tc_kernel<true>, gk, dim3(kBwdThreads), kDkSmem, st, 1, tq, tk, tv, tdo, lse_c, delta_c,
+             (bf16*)dk, (bf16*)dv, S, H, KV, lddk, lddv, scale, rope_cache, seg_start, seg_end, late);
   else
-    attn_bwd_dkdv_tc_kernel<false><<<gk, kBwdThreads, kDkSmem, st>>>(tq, tk, tv, tdo, lse, delta, (bf16*)dk, (bf16*)dv, S,
-                                                                     H, KV, lddk, lddv, scale, rope_cache, nullptr,
-                                                                     nullptr);
+    le = launch_k(attn_bwd_dkdv_tc_kernel<false>, gk, dim3(kBwdThreads), kDkSmem, st, 1, tq, tk, tv, tdo, lse_c, delta_c,
+             (bf16*)dk, (bf16*)dv, S, H, KV, lddk, lddv, scale, rope_cache, no_seg, no_seg, late);
+  if (le != cudaSuccess) { set_error("attn_bwd_dkdv_tc: launch failed: %s", cudaGetErrorString(le)); return CSM_ERR_CUDA; }
   CSM_CHECK_LAUNCH("attn_bwd_dkdv_tc");
   return CSM_OK;
 }

@@ -76,6 +76,8 @@ ce_rows_bwd_kernel(const float* __restrict__ logits, int64_t ldl, const int64_t*
 __global__ void __launch_bounds__(256)
 ce_combine_kernel(const float4* __restrict__ part, int nt, float* __restrict__ loss, float* __restrict__ lse,
                   int64_t rows) {
+  pdl_wait();
+  pdl_trigger();
   const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (r >= rows) return;
   float mx = -INFINITY;
@@ -92,7 +94,8 @@ ce_combine_kernel(const float4* __restrict__ part, int nt, float* __restrict__ l
 }
 
 int ce_combine_launch(const void* part, int nt, float* loss, float* lse, int64_t rows, cudaStream_t st) {
-  ce_combine_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, st>>>((const float4*)part, nt, loss, lse, rows);
+  if (launch_k(ce_combine_kernel, dim3((unsigned)((rows + 255) / 256)), dim3(256), 0, st, 1, (const float4*)part, nt, loss,
+               lse, rows) != cudaSuccess) { set_error("ce_combine: launch failed"); return CSM_ERR_CUDA; }
   CSM_CHECK_LAUNCH("ce_combine");
   return CSM_OK;
 }

@@ -6,6 +6,7 @@
 #include <stdio.h>
 
 #include <atomic>
+#include <utility>
 
 #include "../../include/csm_b200.h"
 
@@ -35,6 +36,37 @@ inline cudaStream_t as_stream(csm_stream_t s) { return reinterpret_cast<cudaStre
       return CSM_ERR_CUDA;                                                       \
     }                                                                            \
   } while (0)
+
+// Programmatic dependent launch (csm_set_pdl / CSM_PDL): a kernel launched through launch_k() may be scheduled while the
+// previous kernel of the stream is still draining; every such kernel calls pdl_wait() before its first global-memory
+// access (reads AND writes: the caching allocator reuses buffers in stream order) and pdl_trigger() right after, so at
+// most one successor is parked behind a running kernel.  Its launch latency and prologue (barrier init, TMEM
+// allocation, tensor-map prefetch) then overlap the predecessor's tail instead of following its completion.
+extern std::atomic<int> g_pdl;
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+// <<<grid, block, smem, st>>> with optional cluster width and the PDL attribute.  Only for kernels that call pdl_wait().
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, int cluster_x,
+                            Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[2];
+  unsigned n = 0;
+  if (cluster_x > 1) {
+    at[n].id = cudaLaunchAttributeClusterDimension;
+    at[n].val.clusterDim.x = (unsigned)cluster_x; at[n].val.clusterDim.y = 1; at[n].val.clusterDim.z = 1;
+    ++n;
+  }
+  if (g_pdl.load(std::memory_order_relaxed)) {
+    at[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[n].val.programmaticStreamSerializationAllowed = 1;
+    ++n;
+  }
+  cfg.attrs = at; cfg.numAttrs = n;
+  return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
+}
 
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 

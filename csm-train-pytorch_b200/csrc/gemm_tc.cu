@@ -237,6 +237,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (kCta2) cluster_sync();      // the peer's barriers are initialised before any remote arrive / complete_tx
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // everything above (barrier init, TMEM allocation, tensor-map prefetch) touched no global memory and may have run
+  // while the previous kernel of the stream was still draining (programmatic dependent launch, common.cuh)
+  pdl_wait();
+  pdl_trigger();
 
   // Dynamic schedule.  Item 0 of every CTA (pair) is its static tile (no start-up latency); item it >= 1 is the tile
   // index the LEADER's producer warp drew from the global counter and wrote, tagged with `it`, into queue slot
@@ -895,19 +899,13 @@ static int launch_inst(const CUtensorMap& a, const CUtensorMap& b, const CUtenso
   if (!CTA2) {
     const int tiles = p.groups * p.num_m * p.num_n;
     const int grid = tiles < num_sms() ? tiles : num_sms();
-    kern<<<grid, kGemmThreads, Cfg::kSmemBytes, st>>>(a, b, a2, b2, p);
+    cudaError_t e = launch_k(kern, dim3(grid), dim3(kGemmThreads), Cfg::kSmemBytes, st, 1, a, b, a2, b2, p);
+    if (e != cudaSuccess) { set_error("gemm_tc: launch failed: %s", cudaGetErrorString(e)); return CSM_ERR_CUDA; }
   } else {
     const int tiles = p.groups * ((p.num_m + 1) / 2) * p.num_n;
     const int avail = max_pairs < num_sms() / 2 ? max_pairs : num_sms() / 2;   // num_sms() honours reserved SMs
     const int pairs = tiles < avail ? tiles : avail;
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(2 * pairs); cfg.blockDim = dim3(kGemmThreads); cfg.dynamicSmemBytes = Cfg::kSmemBytes;
-    cfg.stream = st;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeClusterDimension;
-    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-    cfg.attrs = at; cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, a, b, a2, b2, p);
+    cudaError_t e = launch_k(kern, dim3(2 * pairs), dim3(kGemmThreads), Cfg::kSmemBytes, st, 2, a, b, a2, b2, p);
     if (e != cudaSuccess) { set_error("gemm_tc (CTA pair): launch failed: %s", cudaGetErrorString(e)); return CSM_ERR_CUDA; }
   }
   CSM_CHECK_LAUNCH("gemm_tc");
@@ -1166,6 +1164,8 @@ int linear_ce_tc_bwd_dlogits(const void* H, const void* W, const int64_t* target
 __global__ void __launch_bounds__(256)
 splitk_reduce_kernel(const float* __restrict__ part, bf16* __restrict__ out, int64_t M, int64_t N, int64_t ldc,
                      int splits, float alpha) {
+  pdl_wait();
+  pdl_trigger();
   const int64_t total = M * N;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     float acc = 0.f;
@@ -1192,7 +1192,8 @@ int gemm_tc_splitk(const void* A, const void* B, void* C, int64_t M, int64_t N, 
   if (rc) return rc;
   const int64_t total = M * N;
   const unsigned grid = (unsigned)((total + 255) / 256 < 1184 ? (total + 255) / 256 : 1184);
-  splitk_reduce_kernel<<<grid, 256, 0, st>>>(ws, (bf16*)C, M, N, ldc, splits, alpha);
+  if (launch_k(splitk_reduce_kernel, dim3(grid), dim3(256), 0, st, 1, (const float*)ws, (bf16*)C, M, N, ldc, splits,
+               alpha) != cudaSuccess) { set_error("splitk_reduce: launch failed"); return CSM_ERR_CUDA; }
   CSM_CHECK_LAUNCH("splitk_reduce");
   return CSM_OK;
 }

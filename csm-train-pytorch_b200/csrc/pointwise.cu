@@ -147,6 +147,8 @@ __global__ void __launch_bounds__(256)
 rmsnorm_fwd_warp_kernel(const void* __restrict__ x, const bf16* __restrict__ scale, bf16* __restrict__ y,
                         float* __restrict__ rstd, int64_t rows, float eps) {
   constexpr int D = 256 * VPL;
+  pdl_wait();
+  pdl_trigger();
   const int lane = threadIdx.x & 31;
   const int64_t nw = (int64_t)gridDim.x * (blockDim.x >> 5);
   for (int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); r < rows; r += nw) {
@@ -172,19 +174,25 @@ rmsnorm_fwd_warp_kernel(const void* __restrict__ x, const bf16* __restrict__ sca
   }
 }
 
-template <int VPL, bool XF32>
-__global__ void __launch_bounds__(256)
+// DS: the scale gradient is wanted (full fine-tune).  Without it (LoRA: frozen norms) the 8 * VPL partial-sum registers
+// and the smem reduction disappear — the DS kernel sits at 255 registers (one 8-warp CTA per SM, 24 us per 4096 x 2048
+// call = half the HBM rate) — and the CTAs shrink to 4 warps, three of them per SM.
+template <int VPL, bool XF32, bool DS>
+__global__ void __launch_bounds__(DS ? 256 : 128, DS ? 1 : 3)
 rmsnorm_bwd_warp_kernel(const bf16* __restrict__ dy, const void* __restrict__ x, const bf16* __restrict__ scale,
                         const float* __restrict__ rstd, const bf16* __restrict__ dres, bf16* __restrict__ dx,
-                        float* __restrict__ dscale, int64_t rows) {
+                        float* __restrict__ dscale_arg, int64_t rows) {
   constexpr int D = 256 * VPL;
-  __shared__ float sds[256 * VPL];          // dscale partials of the CTA's 8 warps (only touched when dscale != null)
+  __shared__ float sds[DS ? 256 * VPL : 1]; // dscale partials of the CTA's 8 warps
+  float* const dscale = DS ? dscale_arg : nullptr;
+  pdl_wait();
+  pdl_trigger();
   const int lane = threadIdx.x & 31;
   const int64_t nw = (int64_t)gridDim.x * (blockDim.x >> 5);
-  float ds[VPL][8];
-  if (dscale) {
+  float ds[DS ? VPL : 1][8];
+  if (DS && dscale) {
 #pragma unroll
-    for (int c = 0; c < VPL; ++c)
+    for (int c = 0; c < (DS ? VPL : 1); ++c)
 #pragma unroll
       for (int i = 0; i < 8; ++i) ds[c][i] = 0.f;
     for (int i = threadIdx.x; i < D; i += blockDim.x) sds[i] = 0.f;
@@ -211,7 +219,7 @@ rmsnorm_bwd_warp_kernel(const bf16* __restrict__ dy, const void* __restrict__ x,
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         xh[i] *= rs;
-        if (dscale) ds[c][i] += g[i] * xh[i];
+        if (DS) ds[DS ? c : 0][i] += g[i] * xh[i];
         dot += g[i] * s[i] * xh[i];
       }
     }
@@ -234,9 +242,9 @@ rmsnorm_bwd_warp_kernel(const bf16* __restrict__ dy, const void* __restrict__ x,
       *reinterpret_cast<uint4*>(dx + r * D + (c * 32 + lane) * 8) = pack8(o);
     }
   }
-  if (dscale) {
+  if (DS && dscale) {
 #pragma unroll
-    for (int c = 0; c < VPL; ++c)
+    for (int c = 0; c < (DS ? VPL : 1); ++c)
 #pragma unroll
       for (int i = 0; i < 8; ++i) atomicAdd(&sds[(c * 32 + lane) * 8 + i], ds[c][i]);
     __syncthreads();
@@ -411,10 +419,14 @@ extern "C" int csm_rmsnorm_fwd(const void* x, const void* scale, void* y, float*
     const int64_t ctas = (rows + 7) / 8, cap = (int64_t)num_sms() * 8;
     const unsigned g = (unsigned)(ctas < cap ? ctas : cap);
     const bf16* sc = (const bf16*)scale;
-    if (dim == 2048 && f32) rmsnorm_fwd_warp_kernel<8, true><<<g, 256, 0, st>>>(x, sc, (bf16*)y, rstd, rows, eps);
-    else if (dim == 2048) rmsnorm_fwd_warp_kernel<8, false><<<g, 256, 0, st>>>(x, sc, (bf16*)y, rstd, rows, eps);
-    else if (f32) rmsnorm_fwd_warp_kernel<4, true><<<g, 256, 0, st>>>(x, sc, (bf16*)y, rstd, rows, eps);
-    else rmsnorm_fwd_warp_kernel<4, false><<<g, 256, 0, st>>>(x, sc, (bf16*)y, rstd, rows, eps);
+    cudaError_t e;
+#define NF(V, F) e = launch_k(rmsnorm_fwd_warp_kernel<V, F>, dim3(g), dim3(256), 0, st, 1, x, sc, (bf16*)y, rstd, rows, eps)
+    if (dim == 2048 && f32) NF(8, true);
+    else if (dim == 2048) NF(8, false);
+    else if (f32) NF(4, true);
+    else NF(4, false);
+#undef NF
+    if (e != cudaSuccess) { set_error("rmsnorm_fwd: launch failed: %s", cudaGetErrorString(e)); return CSM_ERR_CUDA; }
     CSM_CHECK_LAUNCH("rmsnorm_fwd");
     return CSM_OK;
   }
@@ -441,10 +453,23 @@ extern "C" int csm_rmsnorm_bwd(const void* dy, const void* x, const void* scale,
     // with dscale the grid stays small (one smem reduction + D global atomics per CTA), without it rows spread wide
     const int64_t ctas = (rows + 7) / 8, cap = (int64_t)num_sms() * (dscale_f32 ? 2 : 6);
     const unsigned g = (unsigned)(ctas < cap ? ctas : cap);
-    if (dim == 2048 && f32) rmsnorm_bwd_warp_kernel<8, true><<<g, 256, 0, st>>>(gy, x, sc, rstd, dr, (bf16*)dx, dscale_f32, rows);
-    else if (dim == 2048) rmsnorm_bwd_warp_kernel<8, false><<<g, 256, 0, st>>>(gy, x, sc, rstd, dr, (bf16*)dx, dscale_f32, rows);
-    else if (f32) rmsnorm_bwd_warp_kernel<4, true><<<g, 256, 0, st>>>(gy, x, sc, rstd, dr, (bf16*)dx, dscale_f32, rows);
-    else rmsnorm_bwd_warp_kernel<4, false><<<g, 256, 0, st>>>(gy, x, sc, rstd, dr, (bf16*)dx, dscale_f32, rows);
+    cudaError_t e;
+#define NB(V, F, D_, G, T) e = launch_k(rmsnorm_bwd_warp_kernel<V, F, D_>, dim3(G), dim3(T), 0, st, 1, gy, x, sc, rstd, dr, \
+                                     (bf16*)dx, dscale_f32, rows)
+    if (dscale_f32) {
+      if (dim == 2048 && f32) NB(8, true, true, g, 256);
+      else if (dim == 2048) NB(8, false, true, g, 256);
+      else if (f32) NB(4, true, true, g, 256);
+      else NB(4, false, true, g, 256);
+    } else {
+      const unsigned g4 = (unsigned)((rows + 3) / 4);      // one row per warp, 4-warp CTAs
+      if (dim == 2048 && f32) NB(8, true, false, g4, 128);
+      else if (dim == 2048) NB(8, false, false, g4, 128);
+      else if (f32) NB(4, true, false, g4, 128);
+      else NB(4, false, false, g4, 128);
+    }
+#undef NB
+    if (e != cudaSuccess) { set_error("rmsnorm_bwd: launch failed: %s", cudaGetErrorString(e)); return CSM_ERR_CUDA; }
     CSM_CHECK_LAUNCH("rmsnorm_bwd");
     return CSM_OK;
   }

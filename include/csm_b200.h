@@ -283,6 +283,26 @@ int csm_lora_mask_rows(void* t, int64_t ldt, int64_t rows, int32_t cols, const i
 int csm_lora_dropout(const void* x, void* out, int64_t rows, int64_t cols, int64_t ldx, int64_t ldo, float p,
                      const int64_t* seed_dev, int64_t salt, int32_t accumulate, csm_stream_t stream);
 
+/* ---- tall-skinny products of the LoRA path (lora.py:87-105 and its autograd; trainer call sites
+ * lora_trainer.py:150-178): one dimension R <= 64 (even), the other operand a long stream read once.
+ *   rowdot: T[M, R] (bf16, ldt) = alpha * X[M, K] . W, W stored [R, K] (w_is_kr == 0: t = s x A^T) or [K, R]
+ *           (w_is_kr != 0: dts = s dy B).  K a multiple of 32, X rows 16-byte aligned.
+ *   coldot: G = alpha * X[N, C]^T Tm[N, R], stored [C, R] (out_is_rk == 0: dB = dy^T t) or [R, C] (out_is_rk != 0:
+ *           dA = dts^T x).  C a multiple of 8, X rows 16-byte aligned.
+ * fp32 accumulation, fixed summation order (bit-reproducible), no workspace.  csm_skinny_supported(kind 0 = rowdot /
+ * 1 = coldot, same operands) == 0: use csm_gemm_bf16 / csm_gemm_bf16_splitk.  csm_set_skinny_mode(0) disables (A/B). */
+int csm_skinny_supported(int32_t kind, const void* X, const void* W, const void* out, int64_t rows, int64_t cols,
+                         int64_t R, int64_t ldx, int64_t ldw, int64_t ldo, int32_t layout);
+int csm_skinny_rowdot(const void* X, const void* W, void* T, int64_t M, int64_t K, int64_t R, int64_t ldx, int64_t ldw,
+                      int64_t ldt, int32_t w_is_kr, float alpha, csm_stream_t stream);
+int csm_skinny_coldot(const void* X, const void* Tm, void* G, int64_t N, int64_t C, int64_t R, int64_t ldx, int64_t ldt,
+                      int64_t ldg, int32_t out_is_rk, float alpha, csm_stream_t stream);
+void csm_set_skinny_mode(int32_t mode);
+/* Programmatic dependent launch between consecutive kernels of the step (default 1, or the CSM_PDL environment
+ * variable): each kernel's launch latency and prologue overlap the tail of its predecessor; every kernel waits
+ * (griddepcontrol.wait) before its first global-memory access, so results are unchanged. */
+void csm_set_pdl(int32_t on);
+
 /* ---- small helpers used by the training step */
 /* dst_bf16[i] (=|+=) src_f32[i] * scale */
 int csm_f32_to_bf16(const float* src, void* dst, int64_t n, float scale, int32_t accumulate, csm_stream_t stream);

@@ -291,14 +291,86 @@ def test_gemm_split_reduction_skinny(ops, cuda, M, N, K, ta, tb):
     a = mk(K, M) if ta else mk(M, K)
     b = mk(K, N) if tb else mk(N, K)
     ref = (a.float().t() if ta else a.float()) @ (b.float() if tb else b.float().t())
-    out = ops.gemm(a, b, trans_a=ta, trans_b=tb, alpha=0.25)
-    assert rel_err(out, 0.25 * ref) < 5e-3, rel_err(out, 0.25 * ref)
-    O.SPLITK_ENABLED = False
+    O.SKINNY_ENABLED = False                # (the streaming kernels of csrc/skinny.cu would take these shapes first)
     try:
-        one = ops.gemm(a, b, trans_a=ta, trans_b=tb, alpha=0.25)
+        out = ops.gemm(a, b, trans_a=ta, trans_b=tb, alpha=0.25)
+        assert rel_err(out, 0.25 * ref) < 5e-3, rel_err(out, 0.25 * ref)
+        O.SPLITK_ENABLED = False
+        try:
+            one = ops.gemm(a, b, trans_a=ta, trans_b=tb, alpha=0.25)
+        finally:
+            O.SPLITK_ENABLED = True
     finally:
-        O.SPLITK_ENABLED = True
+        O.SKINNY_ENABLED = True
     assert rel_err(out, one.float()) < 5e-3
+
+
+# (rows of the long operand, its columns, skinny dimension R)
+SKINNY_SHAPES = [(4096, 2048, 16), (4096, 3072, 16), (4096, 8192, 16), (4136, 1024, 8), (1000, 2048, 48),
+                 (300, 256, 24), (7424, 1024, 64), (4096, 3072, 10), (257, 64, 2)]
+
+
+@pytest.mark.parametrize("pdl", [1, 0])
+@pytest.mark.parametrize("rows,cols,R", SKINNY_SHAPES)
+def test_skinny_lora_products(ops, cuda, rows, cols, R, pdl):
+    """The four tall-skinny products of a LoRA projection (t = x A^T, dts = dy B, dB = dy^T t, dA = dts^T x) on the
+    streaming mma.sync kernels, against fp32 torch on the same bf16 inputs; strided operands and outputs; bit-reproducible."""
+    from csm import _lib
+    lib = _lib.load()
+    ops.set_pdl(pdl)
+    try:
+        g = torch.Generator().manual_seed(rows + cols + R)
+        def mk(r, c, pad=0):
+            ld = (c + 7) // 8 * 8 + pad
+            return (torch.randn(r, ld, generator=g) * 0.5).to(BF).to(cuda)[:, :c]
+        x = mk(rows, cols, pad=8)                       # the long operand, row stride != cols
+        A = mk(R, cols)                                 # [R, K]
+        Bm = (torch.randn(cols, R + 2, generator=g) * 0.5).to(BF).to(cuda)[:, :R]     # [K, R], row stride R + 2
+        tm = (torch.randn(rows, R + 6, generator=g) * 0.5).to(BF).to(cuda)[:, :R]     # [rows, R], row stride R + 6
+        n0 = _lib.launch_count()
+        # rowdot, W = [R, K]
+        t = ops.gemm(x, A, alpha=0.5)
+        if cols % 32 == 0:
+            assert lib.csm_skinny_supported(0, x.data_ptr(), A.data_ptr(), t.data_ptr(), rows, cols, R, x.stride(0),
+                                            A.stride(0), t.stride(0), 0) == 1
+        assert rel_err(t, 0.5 * (x.float() @ A.float().t())) < 4e-3
+        # rowdot, W = [K, R], into a strided output view
+        buf = torch.full((rows, R + 8), 7.0, dtype=BF, device=cuda)
+        ops.gemm(x, Bm, trans_b=True, alpha=2.0, out=buf[:, :R])
+        assert rel_err(buf[:, :R], 2.0 * (x.float() @ Bm.float())) < 4e-3
+        assert bool((buf[:, R:] == 7.0).all())          # nothing written past R
+        # coldot, out [C, R] and [R, C]
+        dB = ops.gemm(x, tm, trans_a=True, trans_b=True)
+        assert dB.shape == (cols, R)
+        assert rel_err(dB, x.float().t() @ tm.float()) < 4e-3
+        dA = ops.gemm(tm, x, trans_a=True, trans_b=True, alpha=0.125)
+        assert dA.shape == (R, cols)
+        assert rel_err(dA, 0.125 * (tm.float().t() @ x.float())) < 4e-3
+        assert _lib.launch_count() - n0 == 4            # one launch each: no reduction kernel, no workspace
+        # fixed summation order: a second run is bit-identical
+        assert torch.equal(dA, ops.gemm(tm, x, trans_a=True, trans_b=True, alpha=0.125))
+        assert torch.equal(t, ops.gemm(x, A, alpha=0.5))
+    finally:
+        ops.set_pdl(1)
+
+
+def test_rmsnorm_bwd_without_scale_gradient(ops, cuda):
+    """LoRA (frozen norms): the dscale-free instantiation (4-warp CTAs) gives the same dx as the one that also
+    accumulates the scale gradient."""
+    g = torch.Generator().manual_seed(5)
+    for rows, D, f32 in ((4099, 2048, True), (777, 2048, False), (300, 1024, True), (64, 1024, False)):
+        x = torch.randn(rows, D, generator=g).to(cuda)
+        x = x if f32 else x.to(BF)
+        scale = (1 + 0.1 * torch.randn(D, generator=g)).to(BF).to(cuda)
+        dy = torch.randn(rows, D, generator=g).to(BF).to(cuda)
+        dres = torch.randn(rows, D, generator=g).to(BF).to(cuda)
+        _, rstd = ops.rmsnorm(x, scale, 1e-5)
+        ds = torch.zeros(D, dtype=torch.float32, device=cuda)
+        a = ops.rmsnorm_bwd(dy, x, scale, rstd, dres, ds)
+        b = ops.rmsnorm_bwd(dy, x, scale, rstd, dres, None)
+        assert torch.equal(a, b)
+        c = ops.rmsnorm_bwd(dy, x, scale, rstd, None, None)
+        assert rel_err(c.float() + dres.float(), a) < 4e-3
 
 
 @pytest.mark.parametrize("backend", [1, 2])
@@ -743,3 +815,47 @@ def test_attention_forward_variants(ops, cuda, variant):
     sc = (q4 @ k4.transpose(-1, -2) / math.sqrt(hd)).masked_fill(
         ~torch.tril(torch.ones(S, S, dtype=torch.bool, device=cuda)), -float("inf"))
     assert torch.allclose(lse, torch.logsumexp(sc, -1), atol=2e-2, rtol=2e-3)
+
+
+def test_programmatic_dependent_launch_modes_are_bit_identical(ops, cuda):
+    """csm_set_pdl 0 / 1 / 2: a chain of dependent kernels (norm -> GEMM -> attention forward -> backward, the dK/dV
+    kernel overlapping the dQ kernel's tail in mode 2 -> skinny products) gives bit-identical results; buffers are
+    freed and re-allocated between the launches, as in the training step."""
+    B, S, H, KV, hd = 2, 2048, 32, 8, 64
+    g = torch.Generator().manual_seed(11)
+    D = H * hd
+    x = torch.randn(B * S, D, generator=g).to(cuda)
+    scale = (1 + 0.1 * torch.randn(D, generator=g)).to(BF).to(cuda)
+    wqkv = (torch.randn((H + 2 * KV) * hd, D, generator=g) * 0.02).to(BF).to(cuda)
+    do = (torch.randn(B * S, D, generator=g) * 0.1).to(BF).to(cuda)
+    Bm = (torch.randn((H + 2 * KV) * hd, 16, generator=g) * 0.1).to(BF).to(cuda)
+    cache = _rope_cache(hd, S).to(cuda)
+
+    def chain():
+        outs = []
+        for _ in range(3):                                    # back to back, allocator re-using the freed buffers
+            xn, _ = ops.rmsnorm(x, scale, 1e-5)
+            qkv = ops.gemm_rope(xn, wqkv, cache, S, (H + KV) * hd, hd)
+            q, k, v = qkv[:, :H * hd], qkv[:, H * hd:(H + KV) * hd], qkv[:, (H + KV) * hd:]
+            o, lse = ops.attention_fwd(q, k, v, B, S, H, KV, hd)
+            dqkv = torch.empty_like(qkv)
+            ops.attention_bwd(q, k, v, o, lse, do, B, S, H, KV, hd, dq=dqkv[:, :H * hd],
+                              dk=dqkv[:, H * hd:(H + KV) * hd], dv=dqkv[:, (H + KV) * hd:], rope_cache=cache)
+            dts = ops.gemm(dqkv, Bm, trans_b=True, alpha=2.0)
+            dA = ops.gemm(dts, xn, trans_a=True, trans_b=True)
+            dxn = ops.gemm(dqkv, wqkv, trans_b=True)
+            outs = [o, dqkv, dts, dA, dxn]
+            del xn, qkv, q, k, v, lse
+        torch.cuda.synchronize()
+        return outs
+
+    try:
+        ops.set_pdl(0)
+        ref = chain()
+        for mode in (1, 2):
+            ops.set_pdl(mode)
+            got = chain()
+            for a, b in zip(ref, got):
+                assert torch.equal(a, b), mode
+    finally:
+        ops.set_pdl(1)
