@@ -44,7 +44,11 @@ inline cudaStream_t as_stream(csm_stream_t s) { return reinterpret_cast<cudaStre
 // allocation, tensor-map prefetch) then overlap the predecessor's tail instead of following its completion.
 extern std::atomic<int> g_pdl;
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+#ifdef CSM_PDL_NO_TRIGGER   // A/B build: the dependent grid launches only when every CTA of this one has exited
+__device__ __forceinline__ void pdl_trigger() {}
+#else
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+#endif
 
 // <<<grid, block, smem, st>>> with optional cluster width and the PDL attribute.  Only for kernels that call pdl_wait().
 template <typename... KArgs, typename... Args>

@@ -29,7 +29,19 @@ __device__ __forceinline__ void mma16816(float* c, uint32_t a0, uint32_t a1, uin
 __device__ __forceinline__ uint32_t lo_pair(uint32_t a, uint32_t b) { return __byte_perm(a, b, 0x5410); }  // (a.lo, b.lo)
 __device__ __forceinline__ uint32_t hi_pair(uint32_t a, uint32_t b) { return __byte_perm(a, b, 0x7632); }  // (a.hi, b.hi)
 __device__ __forceinline__ uint32_t word_of(const uint4& v, int i) { return i == 0 ? v.x : i == 1 ? v.y : i == 2 ? v.z : v.w; }
-__device__ __forceinline__ uint32_t ld_u32(const bf16* p) { return *reinterpret_cast<const uint32_t*>(p); }
+// Loads and MMAs are all `asm volatile`: volatile asms keep their program order, so the loads of a whole round (U chunks)
+// are issued back to back before the first MMA that consumes them — one memory round trip per round.  (Left to the
+// scheduler, ptxas sinks every load next to its MMA to save registers: one round trip per chunk, 2-3x slower.)
+__device__ __forceinline__ uint32_t ld_u32(const bf16* p) {
+  uint32_t r;
+  asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(r) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ uint4 ld16(const bf16* p) {          // small re-used operand: may stay in L1
+  uint4 r;
+  asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+  return r;
+}
 
 __device__ __forceinline__ uint32_t cluster_rank() {
   uint32_t r;
@@ -54,7 +66,7 @@ constexpr int kSkThreads = kSkWarps * 32;
 // One CTA = 16 rows of X; its 8 warps take the 32-element chunks of K round-robin (so the CTA walks 512 contiguous
 // bytes of every row per round).  NT = ceil(R / 8) column tiles.  WKR: W is [K, R] (R contiguous).
 template <int NT, bool WKR>
-__global__ void __launch_bounds__(kSkThreads)
+__global__ void __launch_bounds__(kSkThreads, 2)
 skinny_rowdot_kernel(const bf16* __restrict__ X, const bf16* __restrict__ W, bf16* __restrict__ T, int64_t M, int K,
                      int R, int64_t ldx, int64_t ldw, int64_t ldt, float alpha) {
   __shared__ float red[kSkWarps][16][NT * 8 + 1];
@@ -69,35 +81,59 @@ skinny_rowdot_kernel(const bf16* __restrict__ X, const bf16* __restrict__ W, bf1
 #pragma unroll
   for (int j = 0; j < NT; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
   const int chunks = K >> 5;
-#pragma unroll 2
-  for (int c = warp; c < chunks; c += kSkWarps) {
-    const int k0 = c << 5;
-    const uint4 xa = ld_nc16(xa_p + k0), xb = ld_nc16(xb_p + k0);
-    if (!WKR) {
-      // column tile j = rows 8j .. 8j+7 of W; lane (g, t) takes W[8j + g][k0 + 8t .. + 7]
+  // U chunks per round: all their loads are issued before the first MMA (one memory round trip per U chunks)
+  constexpr int U = NT <= 2 ? 4 : (NT <= 4 ? 2 : 1);
+  constexpr int NQ = (NT + 1) / 2;
+  for (int c0 = warp; c0 < chunks; c0 += kSkWarps * U) {
+    uint4 xa[U], xb[U];
+    uint4 wv[WKR ? 1 : U][WKR ? 1 : NT];          // [R, K] operand: 8 consecutive k of row 8j + g
+    uint32_t wk[WKR ? U : 1][WKR ? NQ : 1][8];    // [K, R] operand: rows k0 + 8t + i at the column pair (16q + 2g, +1)
 #pragma unroll
-      for (int j = 0; j < NT; ++j) {
-        const int n = 8 * j + g;
-        uint4 w = make_uint4(0, 0, 0, 0);
-        if (n < R) w = *reinterpret_cast<const uint4*>(W + (int64_t)n * ldw + k0 + 8 * t);
-        mma16816(acc[j], xa.x, xb.x, xa.y, xb.y, w.x, w.y);
-        mma16816(acc[j], xa.z, xb.z, xa.w, xb.w, w.z, w.w);
+    for (int u = 0; u < U; ++u) {
+      const int c = c0 + u * kSkWarps;
+      const bool ok = c < chunks;
+      const int k0 = (ok ? c : warp) << 5;        // (clamped: a chunk past the end contributes zeros)
+      xa[u] = ld_nc16(xa_p + k0);
+      xb[u] = ld_nc16(xb_p + k0);
+      if (!ok) xa[u] = xb[u] = make_uint4(0, 0, 0, 0);
+      if (!WKR) {
+#pragma unroll
+        for (int j = 0; j < NT; ++j) {
+          const int n = 8 * j + g;
+          wv[WKR ? 0 : u][WKR ? 0 : j] = n < R ? ld16(W + (int64_t)n * ldw + k0 + 8 * t) : make_uint4(0, 0, 0, 0);
+        }
+      } else {
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) {
+          const int col = 16 * q + 2 * g;
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            wk[WKR ? u : 0][WKR ? q : 0][i] = col < R ? ld_u32(W + (int64_t)(k0 + 8 * t + i) * ldw + col) : 0u;
+        }
       }
-    } else {
-      // W rows are reduction indices: the 8 rows k0 + 8t + i of W at the column pair (16q + 2g, +1) give the fragments
-      // of the two column tiles 2q (even physical columns) and 2q + 1 (odd ones)
+    }
 #pragma unroll
-      for (int q = 0; q < (NT + 1) / 2; ++q) {
-        const int col = 16 * q + 2 * g;
-        uint32_t w[8];
+    for (int u = 0; u < U; ++u) {
+      if (!WKR) {
+        // column tile j = rows 8j .. 8j+7 of W; lane (g, t) holds W[8j + g][k0 + 8t .. + 7]
 #pragma unroll
-        for (int i = 0; i < 8; ++i)
-          w[i] = col < R ? ld_u32(W + (int64_t)(k0 + 8 * t + i) * ldw + col) : 0u;
-        mma16816(acc[2 * q], xa.x, xb.x, xa.y, xb.y, lo_pair(w[0], w[1]), lo_pair(w[2], w[3]));
-        mma16816(acc[2 * q], xa.z, xb.z, xa.w, xb.w, lo_pair(w[4], w[5]), lo_pair(w[6], w[7]));
-        if (2 * q + 1 < NT) {
-          mma16816(acc[2 * q + 1], xa.x, xb.x, xa.y, xb.y, hi_pair(w[0], w[1]), hi_pair(w[2], w[3]));
-          mma16816(acc[2 * q + 1], xa.z, xb.z, xa.w, xb.w, hi_pair(w[4], w[5]), hi_pair(w[6], w[7]));
+        for (int j = 0; j < NT; ++j) {
+          const uint4 w = wv[WKR ? 0 : u][WKR ? 0 : j];
+          mma16816(acc[j], xa[u].x, xb[u].x, xa[u].y, xb[u].y, w.x, w.y);
+          mma16816(acc[j], xa[u].z, xb[u].z, xa[u].w, xb[u].w, w.z, w.w);
+        }
+      } else {
+        // W rows are reduction indices: the column pair (16q + 2g, +1) gives the fragments of the two column tiles 2q
+        // (even physical columns) and 2q + 1 (odd ones)
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) {
+          const uint32_t* w = wk[WKR ? u : 0][WKR ? q : 0];
+          mma16816(acc[2 * q], xa[u].x, xb[u].x, xa[u].y, xb[u].y, lo_pair(w[0], w[1]), lo_pair(w[2], w[3]));
+          mma16816(acc[2 * q], xa[u].z, xb[u].z, xa[u].w, xb[u].w, lo_pair(w[4], w[5]), lo_pair(w[6], w[7]));
+          if (2 * q + 1 < NT) {
+            mma16816(acc[2 * q + 1], xa[u].x, xb[u].x, xa[u].y, xb[u].y, hi_pair(w[0], w[1]), hi_pair(w[2], w[3]));
+            mma16816(acc[2 * q + 1], xa[u].z, xb[u].z, xa[u].w, xb[u].w, hi_pair(w[4], w[5]), hi_pair(w[6], w[7]));
+          }
         }
       }
     }
@@ -129,7 +165,7 @@ skinny_rowdot_kernel(const bf16* __restrict__ X, const bf16* __restrict__ W, bf1
 // MT = ceil(R / 16) row tiles of the output (the MMA's M dimension is R, its N dimension the columns of X).
 // ORK: output stored [R, C] (else [C, R]).
 template <int MT, bool ORK>
-__global__ void __launch_bounds__(kSkThreads)
+__global__ void __launch_bounds__(kSkThreads, MT == 1 ? 2 : 1)      // R <= 16: two CTAs per SM, the whole grid in one wave
 skinny_coldot_kernel(const bf16* __restrict__ X, const bf16* __restrict__ Tm, bf16* __restrict__ G, int64_t N, int C,
                      int R, int64_t ldx, int64_t ldt, int64_t ldg, int splits, float alpha) {
   __shared__ float part[64][MT * 16 + 1];
@@ -149,36 +185,43 @@ skinny_coldot_kernel(const bf16* __restrict__ X, const bf16* __restrict__ Tm, bf
     for (int j = 0; j < 8; ++j) acc[m][j][0] = acc[m][j][1] = acc[m][j][2] = acc[m][j][3] = 0.f;
 
   const int64_t steps = (n_end > n_begin) ? (n_end - n_begin + 15) / 16 : 0;
-#pragma unroll 2
-  for (int64_t s = warp; s < steps; s += kSkWarps) {
-    const int64_t n0 = n_begin + s * 16 + 2 * t;     // this lane's rows: n0, n0 + 1, n0 + 8, n0 + 9
-    uint4 x0 = make_uint4(0, 0, 0, 0), x1 = x0, x8 = x0, x9 = x0;
-    if (col_ok) {
-      if (n0 < n_end) x0 = ld_nc16(X + n0 * ldx + xcol);
-      if (n0 + 1 < n_end) x1 = ld_nc16(X + (n0 + 1) * ldx + xcol);
-      if (n0 + 8 < n_end) x8 = ld_nc16(X + (n0 + 8) * ldx + xcol);
-      if (n0 + 9 < n_end) x9 = ld_nc16(X + (n0 + 9) * ldx + xcol);
-    }
-    uint32_t a[MT][4];
+  // U 16-row steps per round: all their loads are issued before the first MMA
+  constexpr int U = 2;
+  for (int64_t s0 = warp; s0 < steps; s0 += kSkWarps * U) {
+    uint4 xr[U][4];
+    uint32_t tr[U][MT][4];
 #pragma unroll
-    for (int m = 0; m < MT; ++m) {
-      const int r = 16 * m + 2 * g;                  // physical rows r (logical row g) and r + 1 (logical row g + 8)
-      uint32_t t0 = 0, t1 = 0, t8 = 0, t9 = 0;
-      if (r < R) {
-        if (n0 < n_end) t0 = ld_u32(Tm + n0 * ldt + r);
-        if (n0 + 1 < n_end) t1 = ld_u32(Tm + (n0 + 1) * ldt + r);
-        if (n0 + 8 < n_end) t8 = ld_u32(Tm + (n0 + 8) * ldt + r);
-        if (n0 + 9 < n_end) t9 = ld_u32(Tm + (n0 + 9) * ldt + r);
+    for (int u = 0; u < U; ++u) {
+      // this lane's rows: n0, n0 + 1, n0 + 8, n0 + 9 (a step past the end has n0 >= n_end: all zeros)
+      const int64_t n0 = n_begin + (s0 + (int64_t)u * kSkWarps) * 16 + 2 * t;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int64_t n = n0 + (i & 1) + (i >> 1) * 8;
+        xr[u][i] = (col_ok && n < n_end) ? ld_nc16(X + n * ldx + xcol) : make_uint4(0, 0, 0, 0);
+#pragma unroll
+        for (int m = 0; m < MT; ++m) {
+          const int r = 16 * m + 2 * g;              // physical rows r (logical row g) and r + 1 (logical row g + 8)
+          tr[u][m][i] = (r < R && n < n_end) ? ld_u32(Tm + n * ldt + r) : 0u;
+        }
       }
-      a[m][0] = lo_pair(t0, t1); a[m][1] = hi_pair(t0, t1); a[m][2] = lo_pair(t8, t9); a[m][3] = hi_pair(t8, t9);
     }
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {                    // column tile j = physical column 8g' + j of lane group g'
-      const uint32_t w0 = word_of(x0, j >> 1), w1 = word_of(x1, j >> 1), w8 = word_of(x8, j >> 1), w9 = word_of(x9, j >> 1);
-      const uint32_t b0 = (j & 1) ? hi_pair(w0, w1) : lo_pair(w0, w1);
-      const uint32_t b1 = (j & 1) ? hi_pair(w8, w9) : lo_pair(w8, w9);
+    for (int u = 0; u < U; ++u) {
+      uint32_t a[MT][4];
 #pragma unroll
-      for (int m = 0; m < MT; ++m) mma16816(acc[m][j], a[m][0], a[m][1], a[m][2], a[m][3], b0, b1);
+      for (int m = 0; m < MT; ++m) {
+        a[m][0] = lo_pair(tr[u][m][0], tr[u][m][1]); a[m][1] = hi_pair(tr[u][m][0], tr[u][m][1]);
+        a[m][2] = lo_pair(tr[u][m][2], tr[u][m][3]); a[m][3] = hi_pair(tr[u][m][2], tr[u][m][3]);
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {                  // column tile j = physical column 8g' + j of lane group g'
+        const uint32_t w0 = word_of(xr[u][0], j >> 1), w1 = word_of(xr[u][1], j >> 1);
+        const uint32_t w8 = word_of(xr[u][2], j >> 1), w9 = word_of(xr[u][3], j >> 1);
+        const uint32_t b0 = (j & 1) ? hi_pair(w0, w1) : lo_pair(w0, w1);
+        const uint32_t b1 = (j & 1) ? hi_pair(w8, w9) : lo_pair(w8, w9);
+#pragma unroll
+        for (int m = 0; m < MT; ++m) mma16816(acc[m][j], a[m][0], a[m][1], a[m][2], a[m][3], b0, b1);
+      }
     }
   }
   // CTA partial: the warps add their accumulators in warp order (fixed summation order)

@@ -17,36 +17,62 @@ BF = torch.bfloat16
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
 
-def timed(fn, cold, iters=20, warm=3):
-    for _ in range(warm):
-        fn()
-    ts = []
-    for _ in range(iters):
-        if cold:
-            flush.zero_()
-        else:
-            fn()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        fn()
-        e1.record()
-        torch.cuda.synchronize()
-        ts.append(e0.elapsed_time(e1) * 1e3)
-    ts.sort()
-    return round(ts[len(ts) // 2], 2)
+REPS = 10
 
 
-def graphed(fn):
+def _capture(body):
     s = torch.cuda.Stream()
     s.wait_stream(torch.cuda.current_stream())
     with torch.cuda.stream(s):
-        for _ in range(3):
-            fn()
+        body()
     torch.cuda.current_stream().wait_stream(s)
+    torch.cuda.synchronize()
     g = torch.cuda.CUDAGraph()
     with torch.cuda.graph(g):
-        fn()
-    return g.replay
+        body()
+    return g
+
+
+def _graph_ms(g, iters=7):
+    g.replay()
+    ts = []
+    for _ in range(iters):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        g.replay()
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    ts.sort()
+    return ts[len(ts) // 2]
+
+
+def _flush_only():
+    for _ in range(REPS):
+        flush.zero_()
+
+
+_flush_ms = None
+
+
+def per_op_us(fn):
+    """(cold, warm) microseconds per call: a graph of REPS x [256 MB flush, op] minus a graph of REPS x [flush]; and a
+    graph of REPS x [op] back to back (operands L2-resident).  Graph replays take the host launch path out of the number."""
+    global _flush_ms
+    if _flush_ms is None:
+        _flush_ms = _graph_ms(_capture(_flush_only))
+
+    def cold():
+        for _ in range(REPS):
+            flush.zero_()
+            fn()
+
+    def warm():
+        for _ in range(REPS):
+            fn()
+    c = (_graph_ms(_capture(cold)) - _flush_ms) / REPS * 1e3
+    w = _graph_ms(_capture(warm)) / REPS * 1e3
+    return round(c, 2), round(w, 2)
 
 
 g = torch.Generator(device=dev).manual_seed(0)
@@ -67,9 +93,7 @@ for name, fn in cases.items():
     row = {}
     for label, on in (("skinny", True), ("tcgen05_splitk", False)):
         ops.SKINNY_ENABLED = on
-        rep = graphed(fn)
-        row[label + "_cold_us"] = timed(rep, True)
-        row[label + "_l2_us"] = timed(rep, False)
+        row[label + "_cold_us"], row[label + "_l2_us"] = per_op_us(fn)
     ops.SKINNY_ENABLED = True
     out["skinny"][name] = row
 
@@ -80,9 +104,9 @@ dres = torch.randn(N, D, device=dev, generator=g).to(BF)
 _, rstd = ops.rmsnorm(xf, scale, 1e-5)
 ds = torch.zeros(D, device=dev)
 for label, dsarg in (("no_dscale", None), ("with_dscale", ds)):
-    rep = graphed(lambda: ops.rmsnorm_bwd(dyn, xf, scale, rstd, dres, dsarg))
-    out["rmsnorm_bwd"][label] = {"cold_us": timed(rep, True), "l2_us": timed(rep, False),
-                                 "bytes": N * D * (4 + 2 + 2 + 2)}
-rep = graphed(lambda: ops.rmsnorm(xf, scale, 1e-5))
-out["rmsnorm_fwd"] = {"cold_us": timed(rep, True), "l2_us": timed(rep, False), "bytes": N * D * (4 + 2)}
+    c, w = per_op_us(lambda: ops.rmsnorm_bwd(dyn, xf, scale, rstd, dres, dsarg))
+    out["rmsnorm_bwd"][label] = {"cold_us": c, "l2_us": w, "bytes": N * D * (4 + 2 + 2 + 2)}
+c, w = per_op_us(lambda: ops.rmsnorm(xf, scale, 1e-5))
+out["rmsnorm_fwd"] = {"cold_us": c, "l2_us": w, "bytes": N * D * (4 + 2)}
+out["timing"] = "graph of 10 x [256 MB L2 flush, op] minus graph of 10 x [flush] (cold) / graph of 10 x [op] (operands in L2)"
 print(json.dumps(out, indent=1))

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Tiny launch targets for `ncu --set full` (one kernel family per invocation, a handful of launches).
-   python tools/ncu_target.py gemm|ce|embed|attn"""
+   python tools/ncu_target.py gemm|ce|embed|attn|swiglu|skinny|rmsnorm"""
 import os
 import sys
 
@@ -60,5 +60,28 @@ elif what == "attn":
     for _ in range(2):
         o, lse = ops.attention_fwd(q, k, v, B, S, H, KV, hd)
         ops.attention_bwd(q, k, v, o, lse, do, B, S, H, KV, hd)
+elif what == "skinny":      # the four tall-skinny LoRA products of one backbone layer (q/v adapters, r = 8 each)
+    N, D, R = 4096, 2048, 16
+    x = torch.randn(N, D, device=dev).to(BF)
+    dy = torch.randn(N, 3072, device=dev).to(BF)
+    A = torch.randn(R, D, device=dev).to(BF)
+    Bm = torch.randn(3072, R, device=dev).to(BF)
+    t = torch.randn(N, R, device=dev).to(BF)
+    for _ in range(2):
+        ops.gemm(x, A, alpha=2.0)
+        ops.gemm(dy, Bm, trans_b=True, alpha=2.0)
+        ops.gemm(dy, t, trans_a=True, trans_b=True)
+        ops.gemm(t, x, trans_a=True, trans_b=True)
+elif what == "rmsnorm":     # RMSNorm forward / backward on the fp32 residual stream, without and with the scale gradient
+    N, D = 4096, 2048
+    xf = torch.randn(N, D, device=dev)
+    scale = torch.ones(D, device=dev, dtype=BF)
+    dyn = torch.randn(N, D, device=dev).to(BF)
+    dres = torch.randn(N, D, device=dev).to(BF)
+    ds = torch.zeros(D, device=dev)
+    for _ in range(2):
+        _, rstd = ops.rmsnorm(xf, scale, 1e-5)
+        ops.rmsnorm_bwd(dyn, xf, scale, rstd, dres, None)
+        ops.rmsnorm_bwd(dyn, xf, scale, rstd, dres, ds)
 torch.cuda.synchronize()
 print("done", what)
