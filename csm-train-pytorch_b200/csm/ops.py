@@ -61,7 +61,7 @@ def set_attn_backend(b: int) -> None:
 
 
 def set_pdl(on: int) -> None:
-    """Programmatic dependent launch between the step's kernels (csrc/common.cuh): 1 (default, or CSM_PDL) / 0."""
+    """Programmatic dependent launch between the step's kernels (csrc/common.cuh): 0 (default) / 1 (or CSM_PDL=1)."""
     _lib.load().csm_set_pdl(int(on))
 
 

@@ -9,10 +9,14 @@ namespace csm {
 
 static thread_local char g_err[512] = "";
 std::atomic<int64_t> g_launches{0};
-// programmatic dependent launch between consecutive kernels of the step (common.cuh); CSM_PDL=0/1 sets the initial value
+// Programmatic dependent launch between consecutive kernels of the step (common.cuh); CSM_PDL=1 turns it on.
+// OFF by default — measured on B200 (round 2, profiles/r2b_summary.md): the CSM-1B LoRA step replayed as a CUDA graph
+// takes 24.2 ms with it (dependents triggered right after each kernel's wait), 23.8-24.0 ms with the implicit trigger
+// at kernel exit, 23.7-24.1 ms without: inside a graph the launch gaps it hides are already small, and the GPU is
+// power-capped, so idle gaps are not lost throughput.
 static int pdl_env_default() {
   const char* e = getenv("CSM_PDL");
-  return !e ? 1 : (e[0] == '0' ? 0 : (e[0] == '2' ? 2 : 1));
+  return (e && e[0] == '1') ? 1 : 0;
 }
 std::atomic<int> g_pdl{pdl_env_default()};
 
@@ -138,7 +142,7 @@ extern "C" void csm_set_gemm_streamk_mode(int32_t mode) { csm::gemm_tc_set_strea
 extern "C" void csm_set_gemm_narrow_tail_mode(int32_t mode) { csm::gemm_tc_set_narrow_tail_mode(mode); }
 extern "C" void csm_set_gemm_cta_pair_mode(int32_t mode) { csm::gemm_tc_set_cta_pair_mode(mode); }
 extern "C" void csm_set_gemm_dynamic_tiles(int32_t mode) { csm::gemm_tc_set_dynamic_tiles(mode); }
-extern "C" void csm_set_pdl(int32_t on) { csm::g_pdl.store(on < 0 ? 0 : (on > 2 ? 2 : on)); }
+extern "C" void csm_set_pdl(int32_t on) { csm::g_pdl.store(on ? 1 : 0); }
 extern "C" const char* csm_last_error(void) { return g_err; }
 extern "C" int64_t csm_launch_count(void) { return g_launches.load(); }
 

@@ -731,13 +731,8 @@ attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
                         const float* __restrict__ lse, const float* __restrict__ delta, bf16* __restrict__ dk,
                         bf16* __restrict__ dv, int S, int H, int KV, int64_t lddk, int64_t lddv, float scale,
                         const float* __restrict__ rope_cache, const int32_t* __restrict__ seg_start,
-                        const int32_t* __restrict__ seg_end, int late_wait) {
-  // late_wait (csm_set_pdl(2)): this kernel does not depend on the dQ kernel launched right before it — both read
-  // q, k, v, dO, lse, delta and write disjoint columns — so it does not wait for it: its CTAs fill the SMs the dQ
-  // kernel's tail leaves idle.  Every dQ CTA has passed its own wait before this grid can start, so everything older
-  // than the dQ kernel is complete; the wait moves to the END, which keeps "this kernel complete => all earlier
-  // kernels complete" for the successor.
-  if (kVarlen && !late_wait) pdl_wait();            // (see attn_fwd_tc_kernel)
+                        const int32_t* __restrict__ seg_end) {
+  if (kVarlen) pdl_wait();            // (see attn_fwd_tc_kernel)
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + DK_BAR);
@@ -778,7 +773,7 @@ attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  if (!kVarlen && !late_wait) pdl_wait();
+  if (!kVarlen) pdl_wait();
   pdl_trigger();
   constexpr uint32_t COL_ST = 0, COL_DPT = NB * SUB, COL_DK = 2 * NB * SUB, COL_DV = 2 * NB * SUB + THD;   // 512 columns
 
@@ -988,7 +983,6 @@ attn_bwd_dkdv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
   }
-  if (late_wait) pdl_wait();
 }
 
 }  // namespace
@@ -1093,13 +1087,12 @@ int attn_bwd_tc_launch(const void* q, const void* k, const void* v, const void* 
   if (le != cudaSuccess) { set_error("attn_bwd_dq_tc: launch failed: %s", cudaGetErrorString(le)); return CSM_ERR_CUDA; }
   CSM_CHECK_LAUNCH("attn_bwd_dq_tc");
   dim3 gk(((S + TK - 1) / TK) * KV * B);
-  const int late = g_pdl.load(std::memory_order_relaxed) == 2 ? 1 : 0;   // dK/dV overlaps the dQ kernel's tail
   if (varlen)
     le = launch_k(attn_bwd_dkdv_tc_kernel<true>, gk, dim3(kBwdThreads), kDkSmem, st, 1, tq, tk, tv, tdo, lse_c, delta_c,
-             (bf16*)dk, (bf16*)dv, S, H, KV, lddk, lddv, scale, rope_cache, seg_start, seg_end, late);
+             (bf16*)dk, (bf16*)dv, S, H, KV, lddk, lddv, scale, rope_cache, seg_start, seg_end);
   else
     le = launch_k(attn_bwd_dkdv_tc_kernel<false>, gk, dim3(kBwdThreads), kDkSmem, st, 1, tq, tk, tv, tdo, lse_c, delta_c,
-             (bf16*)dk, (bf16*)dv, S, H, KV, lddk, lddv, scale, rope_cache, no_seg, no_seg, late);
+             (bf16*)dk, (bf16*)dv, S, H, KV, lddk, lddv, scale, rope_cache, no_seg, no_seg);
   if (le != cudaSuccess) { set_error("attn_bwd_dkdv_tc: launch failed: %s", cudaGetErrorString(le)); return CSM_ERR_CUDA; }
   CSM_CHECK_LAUNCH("attn_bwd_dkdv_tc");
   return CSM_OK;

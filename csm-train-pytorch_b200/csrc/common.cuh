@@ -37,18 +37,14 @@ inline cudaStream_t as_stream(csm_stream_t s) { return reinterpret_cast<cudaStre
     }                                                                            \
   } while (0)
 
-// Programmatic dependent launch (csm_set_pdl / CSM_PDL): a kernel launched through launch_k() may be scheduled while the
+// Programmatic dependent launch (csm_set_pdl / CSM_PDL, off by default — see api.cu for the measurement): a kernel launched through launch_k() may be scheduled while the
 // previous kernel of the stream is still draining; every such kernel calls pdl_wait() before its first global-memory
 // access (reads AND writes: the caching allocator reuses buffers in stream order) and pdl_trigger() right after, so at
 // most one successor is parked behind a running kernel.  Its launch latency and prologue (barrier init, TMEM
 // allocation, tensor-map prefetch) then overlap the predecessor's tail instead of following its completion.
 extern std::atomic<int> g_pdl;
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
-#ifdef CSM_PDL_NO_TRIGGER   // A/B build: the dependent grid launches only when every CTA of this one has exited
-__device__ __forceinline__ void pdl_trigger() {}
-#else
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
-#endif
 
 // <<<grid, block, smem, st>>> with optional cluster width and the PDL attribute.  Only for kernels that call pdl_wait().
 template <typename... KArgs, typename... Args>

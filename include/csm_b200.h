@@ -298,9 +298,10 @@ int csm_skinny_rowdot(const void* X, const void* W, void* T, int64_t M, int64_t 
 int csm_skinny_coldot(const void* X, const void* Tm, void* G, int64_t N, int64_t C, int64_t R, int64_t ldx, int64_t ldt,
                       int64_t ldg, int32_t out_is_rk, float alpha, csm_stream_t stream);
 void csm_set_skinny_mode(int32_t mode);
-/* Programmatic dependent launch between consecutive kernels of the step (default 1, or the CSM_PDL environment
- * variable): each kernel's launch latency and prologue overlap the tail of its predecessor; every kernel waits
- * (griddepcontrol.wait) before its first global-memory access, so results are unchanged. */
+/* Programmatic dependent launch between consecutive kernels of the step (default 0; 1, or CSM_PDL=1 in the environment,
+ * turns it on): each kernel's launch latency and prologue overlap the tail of its predecessor; every kernel waits
+ * (griddepcontrol.wait) before its first global-memory access, so results are unchanged.  Measured neutral to slightly
+ * negative on the CUDA-graph-replayed step of a power-capped B200, hence off. */
 void csm_set_pdl(int32_t on);
 
 /* ---- small helpers used by the training step */
