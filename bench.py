@@ -242,47 +242,27 @@ def build_model(workload, device, max_seq):
 
 
 # ----------------------------------------------------------------------------- HBM-bound kernels beside the step
-_FLUSH_MS = {}
-
-
-def _graph_ms(body, iters):
-    """Median CUDA-event time (ms) of replaying a CUDA graph of body()."""
-    torch.cuda.synchronize()
-    g = torch.cuda.CUDAGraph()
-    with torch.cuda.graph(g):
-        body()
-    g.replay()
-    ts = []
-    for _ in range(iters):
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        g.replay()
-        e1.record()
-        torch.cuda.synchronize()
-        ts.append(e0.elapsed_time(e1))
-    ts.sort()
-    return ts[len(ts) // 2]
-
-
-def _timed_us(fn, flush, iters=10, warm=3, reps=8):
-    """Device time of one fn() with a cold L2: a CUDA graph of reps x [256 MB flush write, fn()] minus a graph of
-    reps x [flush], per repetition (median of `iters` replays each).  The op runs as it does inside the graph-replayed
-    training step; issued eagerly from Python, a 2-launch op that takes ~40 us on the device is timed with ~10 us of
-    host launch latency between its kernels, and a single replay still carries ~7 us of graph-launch latency."""
+def _timed_us(fn, flush, iters=10, warm=3):
+    """Median CUDA-event time of fn() with a cold L2.  Before every timed call two READ passes over a 512 MB buffer run
+    on the stream: they evict L2 with clean lines (a flush by writing leaves 126 MB of dirty lines whose write-back then
+    competes with the timed op's reads) and keep the GPU busy for ~200 us, so the host has enqueued every kernel of the
+    op before the first one starts — the op's kernels then run back to back as they do in the graph-replayed step
+    (issued against an idle GPU, a 2-launch op of ~40 us is timed with ~10 us of host launch latency inside it)."""
     for _ in range(warm):
         fn()
-    key = (flush.data_ptr(), reps)
-    if key not in _FLUSH_MS:
-        def only_flush():
-            for _ in range(reps):
-                flush.zero_()
-        _FLUSH_MS[key] = _graph_ms(only_flush, iters)
-
-    def body():
-        for _ in range(reps):
-            flush.zero_()
-            fn()
-    return (_graph_ms(body, iters) - _FLUSH_MS[key]) / reps * 1e3
+    words = flush.view(torch.int32)
+    ts = []
+    for _ in range(iters):
+        words.max()
+        words.max()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1) * 1e3)
+    ts.sort()
+    return ts[len(ts) // 2]
 
 
 def hbm_kernel_extras(device, peaks):
@@ -292,7 +272,7 @@ def hbm_kernel_extras(device, peaks):
     from csm import ops
     hbm = peaks.get("hbm_gbs") or 6500.0
     tf = peaks.get("bf16_tflops_sustained") or 1400.0
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)
+    flush = torch.zeros(512 << 20, dtype=torch.uint8, device=device)
     g = torch.Generator(device=device).manual_seed(5)
     C, Dd, V, D = 32, 1024, 2051, 2048
     head_t = (torch.randn(C - 1, V, Dd, device=device, generator=g) * 0.02).to(torch.bfloat16)
@@ -333,8 +313,8 @@ def hbm_kernel_extras(device, peaks):
         nbytes = frames * (32 * D * 2 + D * 2 + 33 * 8 + 33)                 # 135 465 B / audio frame
         k1.append({"audio_frames": frames, "us": us, "gbs": nbytes / us * 1e-3, "frac_hbm": nbytes / us * 1e-3 / hbm})
     return {"c5_fused_audio_head_ce": c5, "k1_embed_gather_sum": k1, "hbm_peak_gbs": hbm, "tensor_peak_tflops": tf,
-            "timing": "CUDA events around replays of a graph of 8 x [256 MB L2 flush, op] minus a graph of 8 x [flush], "
-                      "per op; median of 10 replays (6 for backward)"}
+            "timing": "CUDA events around the op, median of 10 (6 for backward); before every timed call two read passes "
+                      "over a 512 MB buffer evict L2 (clean lines) and let the host enqueue the op's kernels ahead"}
 
 
 def load_peaks():
