@@ -94,7 +94,8 @@ ce_combine_kernel(const float4* __restrict__ part, int nt, float* __restrict__ l
 }
 
 int ce_combine_launch(const void* part, int nt, float* loss, float* lse, int64_t rows, cudaStream_t st) {
-  if (launch_k(ce_combine_kernel, dim3((unsigned)((rows + 255) / 256)), dim3(256), 0, st, 1, (const float4*)part, nt, loss,
+  // always with the PDL attribute: the combine is scheduled while the CE GEMM drains and starts the moment it completes
+  if (launch_k(ce_combine_kernel, dim3((unsigned)((rows + 255) / 256)), dim3(256), 0, st, -1, (const float4*)part, nt, loss,
                lse, rows) != cudaSuccess) { set_error("ce_combine: launch failed"); return CSM_ERR_CUDA; }
   CSM_CHECK_LAUNCH("ce_combine");
   return CSM_OK;

@@ -47,9 +47,13 @@ __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;"
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 // <<<grid, block, smem, st>>> with optional cluster width and the PDL attribute.  Only for kernels that call pdl_wait().
+// cluster_x < 0: |cluster_x| is the cluster width and the PDL attribute is set regardless of the global switch (a small
+// kernel that directly follows its producer, e.g. the CE combine behind the CE GEMM: its launch overlaps the GEMM's tail).
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, int cluster_x,
                             Args&&... args) {
+  const bool force_pdl = cluster_x < 0;
+  if (force_pdl) cluster_x = -cluster_x;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
   cudaLaunchAttribute at[2];
@@ -59,7 +63,7 @@ inline cudaError_t launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_
     at[n].val.clusterDim.x = (unsigned)cluster_x; at[n].val.clusterDim.y = 1; at[n].val.clusterDim.z = 1;
     ++n;
   }
-  if (g_pdl.load(std::memory_order_relaxed)) {
+  if (force_pdl || g_pdl.load(std::memory_order_relaxed)) {
     at[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[n].val.programmaticStreamSerializationAllowed = 1;
     ++n;

@@ -174,31 +174,30 @@ rmsnorm_fwd_warp_kernel(const void* __restrict__ x, const bf16* __restrict__ sca
   }
 }
 
-// DS: the scale gradient is wanted (full fine-tune).  Without it (LoRA: frozen norms) the 8 * VPL partial-sum registers
-// and the smem reduction disappear — the DS kernel sits at 255 registers (one 8-warp CTA per SM, 24 us per 4096 x 2048
-// call = half the HBM rate) — and the CTAs shrink to 4 warps, three of them per SM.
+// DS: the scale gradient is wanted (full fine-tune).  Its partial sums (8 * VPL per lane) live in WARP-PRIVATE shared
+// memory (conflict-free float4 planes), not in registers: with them in registers the kernel sat at 255 registers — one
+// 8-warp CTA per SM, 24-29 us per 4096 x 2048 call, half the HBM rate; now both variants run 4-warp CTAs, three per SM
+// (15 us without DS).  The CTA folds its four copies at the end: D global fp32 atomics per CTA.
 template <int VPL, bool XF32, bool DS>
-__global__ void __launch_bounds__(DS ? 256 : 128, DS ? 1 : 3)
+__global__ void __launch_bounds__(128, 3)
 rmsnorm_bwd_warp_kernel(const bf16* __restrict__ dy, const void* __restrict__ x, const bf16* __restrict__ scale,
                         const float* __restrict__ rstd, const bf16* __restrict__ dres, bf16* __restrict__ dx,
-                        float* __restrict__ dscale_arg, int64_t rows) {
+                        float* __restrict__ dscale, int64_t rows) {
   constexpr int D = 256 * VPL;
-  __shared__ float sds[DS ? 256 * VPL : 1]; // dscale partials of the CTA's 8 warps
-  float* const dscale = DS ? dscale_arg : nullptr;
+  // element (c, lane, i) of a warp's copy sits in float4 slot (2c + i/4) * 32 + lane: a quarter-warp's float4 accesses
+  // cover 128 contiguous bytes
+  __shared__ float4 sds[DS ? 4 * (D / 4) : 1];
   pdl_wait();
   pdl_trigger();
-  const int lane = threadIdx.x & 31;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t nw = (int64_t)gridDim.x * (blockDim.x >> 5);
-  float ds[DS ? VPL : 1][8];
-  if (DS && dscale) {
+  float4* const my = sds + (DS ? warp * (D / 4) : 0);
+  if (DS) {
 #pragma unroll
-    for (int c = 0; c < (DS ? VPL : 1); ++c)
-#pragma unroll
-      for (int i = 0; i < 8; ++i) ds[c][i] = 0.f;
-    for (int i = threadIdx.x; i < D; i += blockDim.x) sds[i] = 0.f;
-    __syncthreads();
+    for (int q = 0; q < 2 * VPL; ++q) my[q * 32 + lane] = make_float4(0.f, 0.f, 0.f, 0.f);
+    __syncwarp();
   }
-  for (int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); r < rows; r += nw) {
+  for (int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp; r < rows; r += nw) {
     float vx[VPL][8];
     uint4 vg[VPL], ve[VPL];
 #pragma unroll
@@ -219,8 +218,14 @@ rmsnorm_bwd_warp_kernel(const bf16* __restrict__ dy, const void* __restrict__ x,
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         xh[i] *= rs;
-        if (DS) ds[DS ? c : 0][i] += g[i] * xh[i];
         dot += g[i] * s[i] * xh[i];
+      }
+      if (DS) {
+        float4 a = my[(2 * c) * 32 + lane], b = my[(2 * c + 1) * 32 + lane];
+        a.x += g[0] * xh[0]; a.y += g[1] * xh[1]; a.z += g[2] * xh[2]; a.w += g[3] * xh[3];
+        b.x += g[4] * xh[4]; b.y += g[5] * xh[5]; b.z += g[6] * xh[6]; b.w += g[7] * xh[7];
+        my[(2 * c) * 32 + lane] = a;
+        my[(2 * c + 1) * 32 + lane] = b;
       }
     }
     dot = warp_sum(dot) / (float)D;
@@ -242,13 +247,14 @@ rmsnorm_bwd_warp_kernel(const bf16* __restrict__ dy, const void* __restrict__ x,
       *reinterpret_cast<uint4*>(dx + r * D + (c * 32 + lane) * 8) = pack8(o);
     }
   }
-  if (DS && dscale) {
-#pragma unroll
-    for (int c = 0; c < (DS ? VPL : 1); ++c)
-#pragma unroll
-      for (int i = 0; i < 8; ++i) atomicAdd(&sds[(c * 32 + lane) * 8 + i], ds[c][i]);
+  if (DS) {
     __syncthreads();
-    for (int i = threadIdx.x; i < D; i += blockDim.x) atomicAdd(dscale + i, sds[i]);
+    const float* flat = reinterpret_cast<const float*>(sds);
+    for (int j = threadIdx.x; j < D; j += blockDim.x) {
+      const int q = j >> 2, e = j & 3, ln = q & 31, ch = q >> 5;            // float4 slot -> (c, lane, i)
+      const int col = ((ch >> 1) * 32 + ln) * 8 + (ch & 1) * 4 + e;
+      atomicAdd(dscale + col, flat[j] + flat[D + j] + flat[2 * D + j] + flat[3 * D + j]);
+    }
   }
 }
 
@@ -450,23 +456,25 @@ extern "C" int csm_rmsnorm_bwd(const void* dy, const void* x, const void* scale,
   cudaStream_t st = as_stream(stream);
   const bf16 *gy = (const bf16*)dy, *sc = (const bf16*)scale, *dr = (const bf16*)dres;
   if ((dim == 2048 || dim == 1024) && rows >= 64) {
-    // with dscale the grid stays small (one smem reduction + D global atomics per CTA), without it rows spread wide
-    const int64_t ctas = (rows + 7) / 8, cap = (int64_t)num_sms() * (dscale_f32 ? 2 : 6);
-    const unsigned g = (unsigned)(ctas < cap ? ctas : cap);
+    // one row per warp, 4-warp CTAs; with dscale the grid is capped at three CTAs per SM (D global atomics per CTA)
+    // (whole rows per warp, the same number for every warp: e.g. 4096 rows -> 342 CTAs x 4 warps x 3 rows)
+    const unsigned g4 = (unsigned)((rows + 3) / 4);
+    const int64_t cap_warps = 4ll * 3 * num_sms();
+    const int64_t rows_per_warp = (rows + cap_warps - 1) / cap_warps;
+    const unsigned gds = (unsigned)((rows + 4 * rows_per_warp - 1) / (4 * rows_per_warp));
     cudaError_t e;
-#define NB(V, F, D_, G, T) e = launch_k(rmsnorm_bwd_warp_kernel<V, F, D_>, dim3(G), dim3(T), 0, st, 1, gy, x, sc, rstd, dr, \
-                                     (bf16*)dx, dscale_f32, rows)
+#define NB(V, F, D_, G) e = launch_k(rmsnorm_bwd_warp_kernel<V, F, D_>, dim3(G), dim3(128), 0, st, 1, gy, x, sc, rstd, dr, \
+                                  (bf16*)dx, dscale_f32, rows)
     if (dscale_f32) {
-      if (dim == 2048 && f32) NB(8, true, true, g, 256);
-      else if (dim == 2048) NB(8, false, true, g, 256);
-      else if (f32) NB(4, true, true, g, 256);
-      else NB(4, false, true, g, 256);
+      if (dim == 2048 && f32) NB(8, true, true, gds);
+      else if (dim == 2048) NB(8, false, true, gds);
+      else if (f32) NB(4, true, true, gds);
+      else NB(4, false, true, gds);
     } else {
-      const unsigned g4 = (unsigned)((rows + 3) / 4);      // one row per warp, 4-warp CTAs
-      if (dim == 2048 && f32) NB(8, true, false, g4, 128);
-      else if (dim == 2048) NB(8, false, false, g4, 128);
-      else if (f32) NB(4, true, false, g4, 128);
-      else NB(4, false, false, g4, 128);
+      if (dim == 2048 && f32) NB(8, true, false, g4);
+      else if (dim == 2048) NB(8, false, false, g4);
+      else if (f32) NB(4, true, false, g4);
+      else NB(4, false, false, g4);
     }
 #undef NB
     if (e != cudaSuccess) { set_error("rmsnorm_bwd: launch failed: %s", cudaGetErrorString(e)); return CSM_ERR_CUDA; }
