@@ -24,6 +24,8 @@ SIGNATURES = {
     "csm_launch_count": (_i64, []),
     "csm_embed_gather_sum_fwd": (_i32, [_ptr] * 8 + [_i64, _i32, _i64, _i64, _i32, _ptr]),
     "csm_embed_gather_sum_bwd": (_i32, [_ptr] * 5 + [_i64, _i32, _i64, _i64, _i32, _ptr]),
+    "csm_embed_gather_sum_packed_fwd": (_i32, [_ptr] * 6 + [_i64, _i32, _i64, _i64, _i32, _ptr]),
+    "csm_embed_gather_sum_packed_bwd": (_i32, [_ptr] * 5 + [_i64, _i32, _i64, _i64, _i32, _ptr]),
     "csm_decoder_input_fwd": (_i32, [_ptr] * 5 + [_i64, _i64, _i64, _i32, _i64, _i32, _ptr]),
     "csm_decoder_input_bwd": (_i32, [_ptr] * 5 + [_i64, _i64, _i64, _i32, _i64, _i32, _ptr]),
     "csm_rmsnorm_fwd": (_i32, [_ptr] * 4 + [_i64, _i32, _f32, _i32, _ptr]),

@@ -45,6 +45,9 @@ class EmbedGatherSumFn(Function):
         ctx.save_for_backward(tokens, mask)
         ctx.shapes = (audio_w.shape, text_w.shape, tokens.shape[-1] - 1)
         ctx.text_exchange = text_exchange
+        ctx.packed = ops.is_packed_tokens(tokens, mask)     # compact device format (csm/data/frames.py::pack_tokens)
+        if ctx.packed:
+            return ops.embed_gather_sum_packed(tokens, mask, audio_w, text_w)
         return ops.embed_gather_sum(tokens, mask, audio_w, text_w)
 
     @staticmethod
@@ -52,6 +55,21 @@ class EmbedGatherSumFn(Function):
         tokens, mask = ctx.saved_tensors
         ashape, tshape, C = ctx.shapes
         dh = dh.contiguous()
+        if ctx.packed:
+            da = torch.zeros(ashape, dtype=BF16, device=dh.device) if ctx.needs_input_grad[2] else None
+            dt = None
+            if ctx.needs_input_grad[3]:
+                if ctx.text_exchange is not None:
+                    # the rank exchange works on the unpacked layout; only the text column matters to it
+                    W = tokens.shape[-1]
+                    bits = (mask.unsqueeze(-1) >> torch.arange(W, device=mask.device)) & 1
+                    dt = ctx.text_exchange(tokens.to(torch.int64), bits.to(torch.uint8), dh, tshape)
+                else:
+                    dt = torch.zeros(tshape, dtype=BF16, device=dh.device)
+            local_dt = dt if ctx.text_exchange is None else None
+            if da is not None or local_dt is not None:
+                ops.embed_gather_sum_packed_bwd(tokens, mask, dh, da, local_dt, ashape[0] // C, tshape[0])
+            return None, None, da, dt, None
         da = torch.zeros(ashape, dtype=BF16, device=dh.device) if ctx.needs_input_grad[2] else None
         dt = None
         if ctx.needs_input_grad[3]:

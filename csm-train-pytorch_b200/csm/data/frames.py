@@ -70,6 +70,49 @@ def build_sample(context: Iterable[Tuple[Sequence[int], torch.Tensor]], target_t
     return {"input_tokens": tokens, "input_masks": masks, "target_audio_tokens": target_codes.t().contiguous().long()}
 
 
+def pack_tokens(tokens: torch.Tensor, masks: torch.Tensor, audio_vocab: int,
+                pin: bool = False) -> Tuple[torch.Tensor, torch.Tensor]:
+    """The compact device format: tokens int64 [..., C+1] + bool mask [..., C+1]  ->
+    rows int32 [..., C+1] of PRE-OFFSET embedding-table rows (audio column c: id + c * audio_vocab — the index
+    ``Model._embed_tokens`` computes, model.py:209-212 — text column: the id) and one int64 word per frame whose bit c is
+    the mask of column c.  140 instead of 297 bytes per frame; ``Model.forward`` takes the pair in place of
+    (tokens, tokens_mask) and produces bit-identical results (csm_embed_gather_sum_packed_fwd / _bwd)."""
+    W = tokens.shape[-1]
+    C = W - 1
+    if W > 63:
+        raise ValueError("pack_tokens: at most 63 columns fit the mask word")
+    off = torch.arange(W, dtype=torch.int64) * int(audio_vocab)
+    off[C] = 0
+    rows64 = tokens.to(torch.int64) + off
+    if int(rows64.max()) >= 2 ** 31 or int(rows64.min()) < -(2 ** 31):
+        raise ValueError("pack_tokens: table rows do not fit int32")
+    bits64 = (masks.to(torch.int64) << torch.arange(W, dtype=torch.int64)).sum(dim=-1)
+    pin = pin and torch.cuda.is_available()
+    rows = torch.empty(rows64.shape, dtype=torch.int32, pin_memory=pin)
+    bits = torch.empty(bits64.shape, dtype=torch.int64, pin_memory=pin)
+    rows.copy_(rows64)
+    bits.copy_(bits64)
+    return rows, bits
+
+
+def unpack_tokens(rows: torch.Tensor, mask_bits: torch.Tensor, audio_vocab: int) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Inverse of pack_tokens: (tokens int64 [..., C+1], masks bool [..., C+1])."""
+    W = rows.shape[-1]
+    off = torch.arange(W, dtype=torch.int64, device=rows.device) * int(audio_vocab)
+    off[W - 1] = 0
+    tokens = rows.to(torch.int64) - off
+    masks = ((mask_bits.unsqueeze(-1) >> torch.arange(W, dtype=torch.int64, device=rows.device)) & 1).bool()
+    return tokens, masks
+
+
+def compact_batch(batch: Dict[str, torch.Tensor], audio_vocab: int, pin: bool = True) -> Dict[str, torch.Tensor]:
+    """A copy of a collated (or packed) host batch whose ``input_tokens`` / ``input_masks`` are in the compact device
+    format (pack_tokens); every other key is passed through.  The trainers and ``Model.forward`` take it as is."""
+    out = dict(batch)
+    out["input_tokens"], out["input_masks"] = pack_tokens(batch["input_tokens"], batch["input_masks"], audio_vocab, pin)
+    return out
+
+
 def collate_pinned(batch: List[Dict[str, torch.Tensor]], pin: bool = True,
                    pad_to_multiple: int = 1) -> Dict[str, torch.Tensor]:
     """Zero / False padding to the batch maximum (training_data.py:379-408) straight into pinned host tensors, so the

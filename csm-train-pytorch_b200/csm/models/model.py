@@ -406,6 +406,8 @@ class Model(nn.Module):
                 segment_starts: Optional[torch.Tensor] = None, segment_ends: Optional[torch.Tensor] = None,
                 target_mask: Optional[torch.Tensor] = None):
         """tokens int64 [B,S,33], tokens_mask bool [B,S,33], target_audio_tokens int64 [B,T,32].
+        (Or the compact device format of csm/data/frames.py::pack_tokens in their place: tokens int32 [B,S,33] of
+        pre-offset table rows and tokens_mask int64 [B,S], one mask word per frame — bit-identical results.)
 
         Returns (loss, {"semantic_loss", "acoustic_loss", "per_codebook_loss": fp32[32]}); with
         target_audio_tokens=None returns the backbone hidden state bf16 [B,S,D].

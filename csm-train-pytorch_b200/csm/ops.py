@@ -118,6 +118,37 @@ def embed_gather_sum_bwd(tokens, mask, dh, d_audio: Optional[torch.Tensor], d_te
                "embed_gather_sum_bwd")
 
 
+def is_packed_tokens(tokens, mask) -> bool:
+    """True for the compact device format of csm/data/frames.py::pack_tokens: int32 pre-offset rows [B,S,C+1] and one
+    int64 mask word per frame [B,S]."""
+    return tokens.dtype == torch.int32 and mask.dtype == torch.int64 and mask.dim() == tokens.dim() - 1
+
+
+def embed_gather_sum_packed(rows, mask_bits, audio_emb, text_emb, *, status=None):
+    """rows int32 [B,S,C+1] (pre-offset table rows), mask_bits int64 [B,S] (bit c = mask of column c) -> h bf16 [B,S,D];
+    bit-identical to embed_gather_sum on the unpacked batch."""
+    _chk_cuda(rows, mask_bits, audio_emb, text_emb, status)
+    assert rows.dtype == torch.int32 and mask_bits.dtype == torch.int64
+    B, S, W = rows.shape
+    C = W - 1
+    D = audio_emb.shape[1]
+    h = torch.empty(B, S, D, dtype=BF16, device=rows.device)
+    lib = _lib.load()
+    _lib.check(lib.csm_embed_gather_sum_packed_fwd(_p(rows.contiguous()), _p(mask_bits.contiguous()), _p(audio_emb),
+                                                   _p(text_emb), _p(h), _p(status), B * S, C, audio_emb.shape[0] // C,
+                                                   text_emb.shape[0], D, _st()), "embed_gather_sum_packed_fwd")
+    return h
+
+
+def embed_gather_sum_packed_bwd(rows, mask_bits, dh, d_audio, d_text, audio_vocab: int, text_vocab: int) -> None:
+    _chk_cuda(rows, mask_bits, dh, d_audio, d_text)
+    B, S, W = rows.shape
+    lib = _lib.load()
+    _lib.check(lib.csm_embed_gather_sum_packed_bwd(_p(rows.contiguous()), _p(mask_bits.contiguous()), _p(dh.contiguous()),
+                                                   _p(d_audio), _p(d_text), B * S, W - 1, audio_vocab, text_vocab,
+                                                   dh.shape[-1], _st()), "embed_gather_sum_packed_bwd")
+
+
 def decoder_input(h, audio_emb, targets, frame_idx, codebooks: int, audio_vocab: int):
     """h bf16 [B,S,D], targets int64 [B,T,C], frame_idx int64 [Ns,2] -> x bf16 [Ns, C, D]."""
     _chk_cuda(h, audio_emb, targets, frame_idx)

@@ -49,6 +49,7 @@ class CSMLoRATrainer:
         # left out of the semantic mean as well (the reference averages over them, utils.py:101-105; set False for that)
         self.mask_padded_targets = True
         self.pack_sequences_to: Optional[int] = None       # sequence packing (see CSMTrainer)
+        self.compact_tokens: bool = False                  # batches as int32 rows + mask words (see CSMTrainer)
         self.model = model
         self.optimizer = None
         self._sync = None
@@ -138,7 +139,9 @@ class CSMLoRATrainer:
         for epoch in range(self.epoch, self.epoch + epochs):
             losses = []
             for batch in iterate_batches(train_dataset, batch_size, True, self.rank, self.world, seed=epoch,
-                                         pack_to=self.pack_sequences_to):
+                                         pack_to=self.pack_sequences_to,
+                                         compact_vocab=(int(self.model.args.audio_vocab_size)
+                                                        if self.compact_tokens else None)):
                 losses.append(self.train_step(batch, max_grad_norm))
                 if val_dataset is not None and self.global_step % val_every == 0:
                     val = self._validate(val_dataset, batch_size)

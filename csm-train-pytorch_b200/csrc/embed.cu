@@ -8,8 +8,12 @@ namespace csm {
 
 constexpr int kEmbThreads = 256;
 
+// kPacked: the compact device format of the data pipeline (csm/data/frames.py::pack_tokens) —
+// `tokens` is int32 [n, C+1] of PRE-OFFSET table rows (audio column c: id + c * V, text column: id) and `mask` one
+// uint64 per frame whose bit c is the mask of column c: 140 instead of 297 bytes per frame over PCIe and from HBM.
+template <bool kPacked>
 __global__ void __launch_bounds__(kEmbThreads)
-embed_gather_sum_fwd_kernel(const int64_t* __restrict__ tokens, const uint8_t* __restrict__ mask,
+embed_gather_sum_fwd_kernel(const void* __restrict__ tokens_v, const void* __restrict__ mask_v,
                             const bf16* __restrict__ audio_emb, const bf16* __restrict__ text_emb,
                             bf16* __restrict__ h, int64_t* __restrict__ idx_out,
                             uint8_t* __restrict__ mask_out, int32_t* __restrict__ status, int C, int64_t V,
@@ -18,10 +22,19 @@ embed_gather_sum_fwd_kernel(const int64_t* __restrict__ tokens, const uint8_t* _
   const int64_t n = blockIdx.x;
   const int W = C + 1;
   for (int c = threadIdx.x; c < W; c += blockDim.x) {
-    const int64_t t = tokens[n * W + c];
-    const uint8_t m = mask[n * W + c];
-    const int64_t idx = (c < C) ? t + (int64_t)c * V : t;  // integer half of the op: bit-exact
-    const bool ok = (t >= 0) && (t < ((c < C) ? V : Vt));
+    int64_t idx;
+    bool m, ok;
+    if (kPacked) {
+      idx = reinterpret_cast<const int32_t*>(tokens_v)[n * W + c];
+      m = (reinterpret_cast<const uint64_t*>(mask_v)[n] >> c) & 1ull;
+      const int64_t t = (c < C) ? idx - (int64_t)c * V : idx;
+      ok = (t >= 0) && (t < ((c < C) ? V : Vt));
+    } else {
+      const int64_t t = reinterpret_cast<const int64_t*>(tokens_v)[n * W + c];
+      m = reinterpret_cast<const uint8_t*>(mask_v)[n * W + c] != 0;
+      idx = (c < C) ? t + (int64_t)c * V : t;  // integer half of the op: bit-exact
+      ok = (t >= 0) && (t < ((c < C) ? V : Vt));
+    }
     if (idx_out) idx_out[n * W + c] = idx;
     if (mask_out) mask_out[n * W + c] = m ? 1 : 0;
     if (!ok && status) *status = 1;
@@ -71,17 +84,25 @@ __device__ __forceinline__ void red_add_bf16x8(bf16* dst, uint4 v) {
   atomicAdd(p + 3, *reinterpret_cast<bf162*>(&v.w));
 }
 
+template <bool kPacked>
 __global__ void __launch_bounds__(kEmbThreads)
-embed_gather_sum_bwd_kernel(const int64_t* __restrict__ tokens, const uint8_t* __restrict__ mask,
+embed_gather_sum_bwd_kernel(const void* __restrict__ tokens_v, const void* __restrict__ mask_v,
                             const bf16* __restrict__ dh, bf16* __restrict__ d_audio, bf16* __restrict__ d_text,
                             int C, int64_t V, int64_t Vt, int D) {
   extern __shared__ int64_t s_idx[];
   const int64_t n = blockIdx.x;
   const int W = C + 1;
   for (int c = threadIdx.x; c < W; c += blockDim.x) {
-    const int64_t t = tokens[n * W + c];
-    const bool ok = mask[n * W + c] && (t >= 0) && (t < ((c < C) ? V : Vt));
-    s_idx[c] = ok ? ((c < C) ? t + (int64_t)c * V : t) : -1;
+    if (kPacked) {
+      const int64_t idx = reinterpret_cast<const int32_t*>(tokens_v)[n * W + c];
+      const int64_t t = (c < C) ? idx - (int64_t)c * V : idx;
+      const bool ok = ((reinterpret_cast<const uint64_t*>(mask_v)[n] >> c) & 1ull) && (t >= 0) && (t < ((c < C) ? V : Vt));
+      s_idx[c] = ok ? idx : -1;
+    } else {
+      const int64_t t = reinterpret_cast<const int64_t*>(tokens_v)[n * W + c];
+      const bool ok = reinterpret_cast<const uint8_t*>(mask_v)[n * W + c] && (t >= 0) && (t < ((c < C) ? V : Vt));
+      s_idx[c] = ok ? ((c < C) ? t + (int64_t)c * V : t) : -1;
+    }
   }
   __syncthreads();
   for (int d0 = threadIdx.x * 8; d0 < D; d0 += blockDim.x * 8) {
@@ -153,11 +174,31 @@ extern "C" int csm_embed_gather_sum_fwd(const int64_t* tokens, const uint8_t* ma
   CSM_REQUIRE(aligned16(audio_emb) && aligned16(text_emb) && aligned16(h), CSM_ERR_ALIGN,
               "embed_gather_sum_fwd: tables and output must be 16-byte aligned");
   if (n_frames == 0) return CSM_OK;
-  embed_gather_sum_fwd_kernel<<<(unsigned)n_frames, kEmbThreads, (codebooks + 1) * sizeof(int64_t),
-                                as_stream(stream)>>>(tokens, mask, (const bf16*)audio_emb, (const bf16*)text_emb,
-                                                     (bf16*)h, idx_out, mask_out, status, codebooks,
-                                                     audio_vocab, text_vocab, dim);
+  embed_gather_sum_fwd_kernel<false><<<(unsigned)n_frames, kEmbThreads, (codebooks + 1) * sizeof(int64_t),
+                                       as_stream(stream)>>>(tokens, mask, (const bf16*)audio_emb, (const bf16*)text_emb,
+                                                            (bf16*)h, idx_out, mask_out, status, codebooks,
+                                                            audio_vocab, text_vocab, dim);
   CSM_CHECK_LAUNCH("embed_gather_sum_fwd");
+  return CSM_OK;
+}
+
+extern "C" int csm_embed_gather_sum_packed_fwd(const int32_t* rows, const uint64_t* mask_bits, const void* audio_emb,
+                                               const void* text_emb, void* h, int32_t* status, int64_t n_frames,
+                                               int32_t codebooks, int64_t audio_vocab, int64_t text_vocab, int32_t dim,
+                                               csm_stream_t stream) {
+  CSM_REQUIRE(n_frames >= 0 && codebooks > 0 && codebooks < 64 && dim > 0 && dim % 8 == 0, CSM_ERR_SHAPE,
+              "embed_gather_sum_packed_fwd: bad shape n=%lld C=%d D=%d (C + 1 mask bits must fit 64, D % 8 == 0)",
+              (long long)n_frames, codebooks, dim);
+  CSM_REQUIRE((int64_t)codebooks * audio_vocab < (1ll << 31) && text_vocab < (1ll << 31), CSM_ERR_SHAPE,
+              "embed_gather_sum_packed_fwd: table rows do not fit int32");
+  CSM_REQUIRE(aligned16(audio_emb) && aligned16(text_emb) && aligned16(h), CSM_ERR_ALIGN,
+              "embed_gather_sum_packed_fwd: tables and output must be 16-byte aligned");
+  if (n_frames == 0) return CSM_OK;
+  embed_gather_sum_fwd_kernel<true><<<(unsigned)n_frames, kEmbThreads, (codebooks + 1) * sizeof(int64_t),
+                                      as_stream(stream)>>>(rows, mask_bits, (const bf16*)audio_emb, (const bf16*)text_emb,
+                                                           (bf16*)h, nullptr, nullptr, status, codebooks, audio_vocab,
+                                                           text_vocab, dim);
+  CSM_CHECK_LAUNCH("embed_gather_sum_packed_fwd");
   return CSM_OK;
 }
 
@@ -169,10 +210,25 @@ extern "C" int csm_embed_gather_sum_bwd(const int64_t* tokens, const uint8_t* ma
               "embed_gather_sum_bwd: bad shape");
   CSM_REQUIRE(aligned16(dh), CSM_ERR_ALIGN, "embed_gather_sum_bwd: dh must be 16-byte aligned");
   if (n_frames == 0 || (!d_audio_emb && !d_text_emb)) return CSM_OK;
-  embed_gather_sum_bwd_kernel<<<(unsigned)n_frames, kEmbThreads, (codebooks + 1) * sizeof(int64_t),
-                                as_stream(stream)>>>(tokens, mask, (const bf16*)dh, (bf16*)d_audio_emb,
-                                                     (bf16*)d_text_emb, codebooks, audio_vocab, text_vocab, dim);
+  embed_gather_sum_bwd_kernel<false><<<(unsigned)n_frames, kEmbThreads, (codebooks + 1) * sizeof(int64_t),
+                                       as_stream(stream)>>>(tokens, mask, (const bf16*)dh, (bf16*)d_audio_emb,
+                                                            (bf16*)d_text_emb, codebooks, audio_vocab, text_vocab, dim);
   CSM_CHECK_LAUNCH("embed_gather_sum_bwd");
+  return CSM_OK;
+}
+
+extern "C" int csm_embed_gather_sum_packed_bwd(const int32_t* rows, const uint64_t* mask_bits, const void* dh,
+                                               void* d_audio_emb, void* d_text_emb, int64_t n_frames, int32_t codebooks,
+                                               int64_t audio_vocab, int64_t text_vocab, int32_t dim,
+                                               csm_stream_t stream) {
+  CSM_REQUIRE(n_frames >= 0 && codebooks > 0 && codebooks < 64 && dim > 0 && dim % 8 == 0, CSM_ERR_SHAPE,
+              "embed_gather_sum_packed_bwd: bad shape");
+  CSM_REQUIRE(aligned16(dh), CSM_ERR_ALIGN, "embed_gather_sum_packed_bwd: dh must be 16-byte aligned");
+  if (n_frames == 0 || (!d_audio_emb && !d_text_emb)) return CSM_OK;
+  embed_gather_sum_bwd_kernel<true><<<(unsigned)n_frames, kEmbThreads, (codebooks + 1) * sizeof(int64_t),
+                                      as_stream(stream)>>>(rows, mask_bits, (const bf16*)dh, (bf16*)d_audio_emb,
+                                                           (bf16*)d_text_emb, codebooks, audio_vocab, text_vocab, dim);
+  CSM_CHECK_LAUNCH("embed_gather_sum_packed_bwd");
   return CSM_OK;
 }
 

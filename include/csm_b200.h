@@ -67,6 +67,18 @@ int csm_embed_gather_sum_bwd(const int64_t* tokens, const uint8_t* mask, const v
                              void* d_text_emb, int64_t n_frames, int32_t codebooks, int64_t audio_vocab,
                              int64_t text_vocab, int32_t dim, csm_stream_t stream);
 
+/* The same two ops on the COMPACT device format of the data pipeline (the reference's collate,
+ * training_data.py:379-408, feeds int64 tokens and a bool mask: 297 bytes per frame): rows int32 [n_frames, C+1] holds
+ * PRE-OFFSET table rows (audio column c: id + c*audio_vocab, text column: id), mask_bits one uint64 per frame whose bit
+ * c is the mask of column c — 140 bytes per frame over PCIe and out of HBM.  Same summation order: h is bit-identical
+ * to csm_embed_gather_sum_fwd on the unpacked batch.  Needs C < 64 and table rows that fit int32. */
+int csm_embed_gather_sum_packed_fwd(const int32_t* rows, const uint64_t* mask_bits, const void* audio_emb,
+                                    const void* text_emb, void* h, int32_t* status, int64_t n_frames, int32_t codebooks,
+                                    int64_t audio_vocab, int64_t text_vocab, int32_t dim, csm_stream_t stream);
+int csm_embed_gather_sum_packed_bwd(const int32_t* rows, const uint64_t* mask_bits, const void* dh, void* d_audio_emb,
+                                    void* d_text_emb, int64_t n_frames, int32_t codebooks, int64_t audio_vocab,
+                                    int64_t text_vocab, int32_t dim, csm_stream_t stream);
+
 /* ---- A7 decoder input assembly (model.py:176,189-191 teacher-forced; _embed_audio model.py:202-204)
  * x[f,0,:] = h[b_f*seq + p_f,:]; x[f,1+i,:] = audio_emb[targets[b_f,p_f,i] + i*audio_vocab,:], i < C-1.
  * frame_idx int64 [n_sel,2] = (b,p); targets int64 [batch, tgt_len, C]. */

@@ -108,3 +108,32 @@ def test_pack_samples_layout_segments_targets_and_frames():
     import pytest
     with pytest.raises(ValueError):
         F.pack_samples(samples, 200, pin=False)
+
+
+def test_pack_tokens_compact_device_format_round_trip():
+    """int32 pre-offset table rows + one 33-bit mask word per frame; the offsets are the ones
+    Model._embed_tokens adds (model.py:209-212)."""
+    g = torch.Generator().manual_seed(3)
+    C, V, Vt = 32, 2051, 128256
+    tok = torch.zeros(2, 7, C + 1, dtype=torch.int64)
+    tok[..., :C] = torch.randint(0, V, (2, 7, C), generator=g)
+    tok[..., C] = torch.randint(0, Vt, (2, 7), generator=g)
+    msk = torch.rand(2, 7, C + 1, generator=g) < 0.5
+    rows, bits = F.pack_tokens(tok, msk, V, pin=False)
+    assert rows.dtype == torch.int32 and rows.shape == tok.shape
+    assert bits.dtype == torch.int64 and bits.shape == (2, 7)
+    assert torch.equal(rows[..., :C].long(), tok[..., :C] + V * torch.arange(C))
+    assert torch.equal(rows[..., C].long(), tok[..., C])
+    for c in (0, 5, 31, 32):
+        assert torch.equal(((bits >> c) & 1).bool(), msk[..., c])
+    assert int(bits.max()) < 2 ** 33
+    t2, m2 = F.unpack_tokens(rows, bits, V)
+    assert torch.equal(t2, tok) and torch.equal(m2, msk)
+    # bytes per frame: 33 * 4 + 8 against 33 * 8 + 33
+    assert rows[0, 0].numel() * 4 + 8 == 140
+    b = {"input_tokens": tok, "input_masks": msk, "target_audio_tokens": torch.zeros(2, 7, C, dtype=torch.int64)}
+    cb = F.compact_batch(b, V, pin=False)
+    assert cb["input_tokens"].dtype == torch.int32 and cb["input_masks"].dtype == torch.int64
+    assert cb["target_audio_tokens"] is b["target_audio_tokens"]
+    with pytest.raises(ValueError):
+        F.pack_tokens(torch.full((1, 1, 33), 2 ** 31, dtype=torch.int64), torch.ones(1, 1, 33, dtype=torch.bool), V)

@@ -466,6 +466,35 @@ def test_lora_dropout_and_bias_match_oracle(cuda, p_drop, use_bias):
         assert abs(float(pe) - float(oe)) <= LOSS_RTOL * abs(float(oe)) and float(pe) != float(pl)
 
 
+@pytest.mark.parametrize("lora", [True, False])
+def test_compact_token_format_is_bit_identical(cuda, lora):
+    """the int32-rows + mask-word batch gives the same loss and gradients as the reference's int64 /
+    bool batch (same kernels downstream; the embedding tables' scatter-add uses bf16 atomics and the norm scales' gradient
+    fp32 atomics, so those are compared with a tolerance)."""
+    from csm.data.frames import compact_batch
+    from oracle import csm_oracle as O
+    _, prod, cfg = _pair("small", cuda, lora=lora)
+    batch = O.synthetic_batch(cfg, 2, 128, seed=99)
+    cb = compact_batch(batch, cfg.audio_vocab_size, pin=False)
+    outs = []
+    for b in (batch, cb):
+        prod.zero_grad(set_to_none=True)
+        loss, d = prod(b["input_tokens"].to(cuda), b["input_masks"].to(cuda), b["target_audio_tokens"].to(cuda),
+                       frame_idx=b["frame_idx"].to(cuda))
+        loss.backward()
+        torch.cuda.synchronize()
+        outs.append((loss.detach().clone(), d["per_codebook_loss"].clone(),
+                     {n: p.grad.clone() for n, p in prod.named_parameters() if p.grad is not None}))
+    (l0, c0, g0), (l1, c1, g1) = outs
+    assert torch.equal(l0, l1) and torch.equal(c0, c1)
+    assert set(g0) == set(g1)
+    for n in g0:
+        if "embeddings" in n or n.endswith(".scale"):
+            assert float(F.cosine_similarity(g0[n].float().flatten(), g1[n].float().flatten(), dim=0)) > 0.9999, n
+        else:
+            assert torch.equal(g0[n], g1[n]), n
+
+
 def test_no_cpu_fallback():
     from csm.models.model import Model, ModelArgs
     m = Model(ModelArgs("tiny-backbone", "tiny-decoder", 1000, 200, 32)).to(torch.bfloat16)

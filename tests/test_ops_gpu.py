@@ -71,6 +71,24 @@ def test_embed_gather_sum_bit_exact(ops, cuda, D, C, V, Vt, B, S):
     ra.index_add_(0, ref_idx[..., :C].reshape(-1), contrib[:, :, :C].reshape(-1, D))
     rt.index_add_(0, tokens[..., C].reshape(-1), contrib[:, :, C].reshape(-1, D))
     assert cos(da, ra) > 0.9999 and cos(dt, rt) > 0.9999
+    # compact device format (int32 pre-offset rows + one mask word per frame): bit-identical forward, same scatter
+    from csm.data.frames import pack_tokens
+    rows, bits = pack_tokens(tokens.cpu(), mask.cpu(), V)
+    rows, bits = rows.to(cuda), bits.to(cuda)
+    assert ops.is_packed_tokens(rows, bits) and not ops.is_packed_tokens(tokens, mask)
+    st = torch.zeros(1, dtype=torch.int32, device=cuda)
+    hp = ops.embed_gather_sum_packed(rows, bits, audio, text, status=st)
+    assert torch.equal(hp, h) and int(st.item()) == 0
+    da2, dt2 = torch.zeros_like(audio), torch.zeros_like(text)
+    ops.embed_gather_sum_packed_bwd(rows, bits, dh, da2, dt2, V, Vt)
+    assert cos(da2, ra) > 0.9999 and cos(dt2, rt) > 0.9999
+    assert rel_err(da2, da) < 2e-2 and rel_err(dt2, dt) < 2e-2        # (bf16 atomics: order differs run to run)
+    bad = rows.clone()
+    bad[0, 0, 3] = 5 * V + 7                                          # a row of another codebook's range
+    bits2 = bits.clone()
+    bits2[0, 0] |= 1 << 3
+    ops.embed_gather_sum_packed(bad, bits2, audio, text, status=st)
+    assert int(st.item()) == 1
 
 
 def test_embed_out_of_range_sets_status(ops, cuda):

@@ -57,6 +57,24 @@ def test_lora_train_step_graph_equals_eager(cuda, tmp_path):
         assert torch.allclose(pe[n].float(), pg[n].float(), atol=2e-3, rtol=2e-2), n
 
 
+def test_lora_trainer_takes_compact_batches_eager_and_graph(cuda, tmp_path):
+    """host batches in the compact device format (int32 pre-offset rows + one mask word per frame)
+    go through train_step — eager and captured / replayed — and train to the same losses as the int64 / bool batches."""
+    from csm.data.frames import compact_batch
+    te, cfg = _lora_trainer(tmp_path / "e", cuda, graph=False)
+    tg, _ = _lora_trainer(tmp_path / "g", cuda, graph=True)
+    batches = _batches(cfg, 6)
+    compact = [compact_batch(b, cfg.audio_vocab_size, pin=True) for b in batches]
+    assert compact[0]["input_tokens"].dtype == torch.int32 and compact[0]["input_masks"].dim() == 2
+    le = [float(te.train_step(b)) for b in batches]
+    lg = [float(x) for x in [tg.train_step(b) for b in compact]]
+    assert tg._graphed.graph is not None
+    for a, b in zip(le, lg):
+        assert abs(a - b) <= 2e-3 * abs(a), (le, lg)
+    h2d = lambda b: sum(v.numel() * v.element_size() for k, v in b.items() if k.startswith("input_"))  # noqa: E731
+    assert h2d(compact[0]) * 2 < h2d(batches[0])
+
+
 def test_full_finetune_trainer_steps_and_graph(cuda, tmp_path):
     from csm.training.trainer import CSMTrainer
     losses = {}
