@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Per-kernel microbenchmarks on one B200 (CUDA events, L2 flushed between iterations, >=3 warm-ups).
+"""Per-kernel microbenchmarks on one B200 (CUDA events, L2 evicted by reads between iterations, >=3 warm-ups).
    python tools/bench_kernels.py gemm|attn|embed|ce|all
 cuBLAS / SDPA numbers are printed beside ours as same-box comparators only (never on the product path)."""
 import json
@@ -24,15 +24,19 @@ if os.environ.get("CSM_DYN_TILES"):
     ops.set_gemm_dynamic_tiles(int(os.environ["CSM_DYN_TILES"]))
 if os.environ.get("CSM_NARROW_TAIL"):
     ops.set_gemm_narrow_tail_mode(int(os.environ["CSM_NARROW_TAIL"]))
-_flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+_flush = torch.zeros(512 << 20, dtype=torch.uint8, device=dev).view(torch.int32)
 
 
 def timeit(fn, iters=10, warm=3):
+    """Median CUDA-event time (ms) with a cold L2.  Two READ passes over 512 MB before every timed call: clean eviction
+    (a flush by writing leaves dirty lines whose write-back competes with an HBM-bound kernel) and ~200 us during which
+    the host enqueues every kernel of the op, so multi-launch ops are not timed with host launch latency inside."""
     for _ in range(warm):
         fn()
     ts = []
     for _ in range(iters):
-        _flush.zero_()
+        _flush.max()
+        _flush.max()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         fn()
