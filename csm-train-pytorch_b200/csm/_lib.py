@@ -46,6 +46,7 @@ SIGNATURES = {
     "csm_set_gemm_cta_pair_mode": (None, [_i32]),
     "csm_set_gemm_dynamic_tiles": (None, [_i32]),
     "csm_set_reserved_sms": (None, [_i32]),
+    "csm_gemm_experiments_compiled": (_i32, []),
     "csm_gemm_streamk_workspace_bytes": (_sz, []),
     "csm_gemm_set_streamk_workspace": (None, [_ptr, _sz]),
     "csm_set_gemm_streamk_mode": (None, [_i32]),

@@ -133,7 +133,9 @@ void gemm_tc_set_streamk_workspace(void* ptr, size_t bytes);
 void gemm_tc_set_streamk_mode(int m);
 void gemm_tc_set_narrow_tail_mode(int m);
 void gemm_tc_set_dynamic_tiles(int m);
+int gemm_tc_experiments_compiled();
 }  // namespace csm
+extern "C" int csm_gemm_experiments_compiled(void) { return csm::gemm_tc_experiments_compiled(); }
 extern "C" size_t csm_gemm_streamk_workspace_bytes(void) { return csm::gemm_tc_streamk_workspace_bytes(); }
 extern "C" void csm_gemm_set_streamk_workspace(void* workspace, size_t bytes) {
   csm::gemm_tc_set_streamk_workspace(workspace, bytes);

@@ -21,6 +21,15 @@ namespace csm {
 using namespace tc;
 
 constexpr int BM = 128, BK = 64;
+// Two measured-and-rejected experiments (stream-K tile cutting, narrow MMAs on ragged last column tiles: both correct,
+// neither faster on a power-capped B200 — profiles/r1_summary.md, r2_summary.md) are compiled OUT of the kernels unless
+// the library is built with -DCSM_GEMM_EXPERIMENTS (CSM_EXTRA_NVCC_FLAGS of build.sh); csm_gemm_experiments_compiled()
+// reports it, and their mode setters are then no-ops.
+#ifdef CSM_GEMM_EXPERIMENTS
+constexpr bool kExperiments = true;
+#else
+constexpr bool kExperiments = false;
+#endif
 constexpr int kGemmThreads = 320;   // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
 // Two epilogue warps per TMEM lane quadrant split the tile's columns (the fused SwiGLU epilogues must finish inside
 // one main loop, ~9 us at K = 2048); the CE epilogues keep whole rows thread-local, so only warps 2..5 work there.
@@ -211,7 +220,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int first_tile = kCta2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
   const int tile_step = kCta2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   const int kb_total = p.k_blocks + p.has_tail;
-  const int sk = (kCta2 && kEpi == EPI_STORE) ? p.streamk : 0;
+  const int sk = (kExperiments && kCta2 && kEpi == EPI_STORE) ? p.streamk : 0;
   const bool dyn = p.tile_ctr != nullptr && !sk && num_tiles < (1 << 20) - 1;
   // consumers of a tile-queue slot: producer warp + epilogue warps of every CTA, MMA warp of the leader
   constexpr uint32_t kTqConsumers = kCta2 ? 3 + 2 * epi_warps(kEpi) : 2 + epi_warps(kEpi);
@@ -393,7 +402,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
         uint32_t tile_idesc = idesc;
-        if (!kTransB && (kEpi == EPI_STORE || kEpi == EPI_CE_PARTIAL || kEpi == EPI_CE_DLOGITS) && p.narrow_tail) {
+        if (kExperiments && !kTransB && (kEpi == EPI_STORE || kEpi == EPI_CE_PARTIAL || kEpi == EPI_CE_DLOGITS) &&
+            p.narrow_tail) {
           // K-major B: smem rows are output columns, rows past N are TMA zero fill.  A pair takes N/2 rows from each
           // CTA (columns [0, N/2) from the leader's half), so the narrow form needs every valid column in the leader.
           int g, mb, nb;
@@ -460,9 +470,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         float* sk_out = nullptr;
         const float* sk_in = nullptr;
         // (layout [BN / 4][128 rows][4 cols]: one float4 per lane, 512 contiguous bytes per warp access)
-        if (kCta2 && w.kind == 1)
+        if (kExperiments && kCta2 && w.kind == 1)
           sk_out = p.sk_ws + ((size_t)(my_pair * 2 + (int)rank) * BN) * BM + (quad * 32 + lane) * 4;
-        if (kCta2 && w.kind == 2) {
+        if (kExperiments && kCta2 && w.kind == 2) {
           sk_in = p.sk_ws + ((size_t)((my_pair - 1) * 2 + (int)rank) * BN) * BM + (quad * 32 + lane) * 4;
           const int* ready = p.sk_flags + ((my_pair - 1) * 2 + (int)rank) * 2;
           int seen;
@@ -877,6 +887,7 @@ void gemm_tc_set_streamk_workspace(void* ptr, size_t bytes) {
   }
 }
 void gemm_tc_set_streamk_mode(int m) { g_sk_mode.store(m); }
+int gemm_tc_experiments_compiled() { return kExperiments ? 1 : 0; }
 static std::atomic<int> g_tail_mode{0};  // 0 off (default), 1 narrow MMAs on ragged last column tiles (bit-identical, no gain measured)
 void gemm_tc_set_narrow_tail_mode(int m) { g_tail_mode.store(m); }
 
@@ -974,7 +985,7 @@ int gemm_tc_run(const GemmTcOperands& o, GemmTcParams p, int epi, cudaStream_t s
   p.num_m = (int)((p.M + BM - 1) / BM);
   bool cta2 = false;
   const int bn = gemm_tc_tiling(epi, p.groups, p.M, p.N, o.transA, o.transB, &cta2);
-  if (cta2 && epi == EPI_STORE && p.groups == 1 && g_sk_ws && g_sk_mode.load() == 1) {
+  if (kExperiments && cta2 && epi == EPI_STORE && p.groups == 1 && g_sk_ws && g_sk_mode.load() == 1) {
     // stream-K when the tile count leaves the last wave badly filled (e.g. 128 super-tiles on 74 pairs = 1.73 waves)
     const int cap = pair_capacity();
     const int P = cap < num_sms() / 2 ? cap : num_sms() / 2;
@@ -985,7 +996,7 @@ int gemm_tc_run(const GemmTcOperands& o, GemmTcParams p, int epi, cudaStream_t s
       p.streamk = 1; p.sk_ws = g_sk_ws; p.sk_flags = g_sk_flags;
     }
   }
-  p.narrow_tail = (g_tail_mode.load() == 1 && !p.streamk) ? 1 : 0;
+  p.narrow_tail = (kExperiments && g_tail_mode.load() == 1 && !p.streamk) ? 1 : 0;
   // dynamic tile scheduler: one of 32 self-resetting counter pairs in the registered scratch (launches on one stream are
   // serialised, the rotation only separates launches that might overlap on different streams)
   p.tile_ctr = nullptr;

@@ -206,11 +206,16 @@ void csm_set_gemm_dynamic_tiles(int32_t mode);
  * csm_gemm_streamk_workspace_bytes() bytes of ZEROED device memory once per device and registers it; with no workspace
  * registered the GEMM never cuts tiles.  One buffer per device: GEMMs that may use it must be issued on one stream.
  * csm_set_gemm_streamk_mode: 0 never cut tiles (default: no gain measured on a power-capped B200), 1 cut tiles when
- * the last wave of whole tiles would be badly filled. */
+ * the last wave of whole tiles would be badly filled (only in a -DCSM_GEMM_EXPERIMENTS build; a no-op otherwise).  The
+ * default build uses the scratch for the dynamic tile scheduler's counters only. */
+/* 1 when the library was built with -DCSM_GEMM_EXPERIMENTS: stream-K and the narrow-tail MMAs are compiled into the GEMM
+ * kernels and the two mode setters below act; 0 (the default build): both are compiled out and the setters are no-ops. */
+int csm_gemm_experiments_compiled(void);
 size_t csm_gemm_streamk_workspace_bytes(void);
 void csm_gemm_set_streamk_workspace(void* workspace, size_t bytes);
 void csm_set_gemm_streamk_mode(int32_t mode);
-/* Experimental, default 0 (measured: bit-identical, no gain — profiles/r1_ctest_narrow_tail.txt): 1 issues the MMAs of a ragged last column tile (K-major B
+/* Experimental (-DCSM_GEMM_EXPERIMENTS builds only; a no-op otherwise), default 0 (measured: bit-identical, no gain —
+ * profiles/r1_ctest_narrow_tail.txt): 1 issues the MMAs of a ragged last column tile (K-major B
  * operand; e.g. the 3 leftover columns of the 2051-wide audio heads) with N rounded up to 16 instead of the full tile
  * width.  Results are identical; only tensor-pipe time changes. */
 void csm_set_gemm_narrow_tail_mode(int32_t mode);

@@ -245,6 +245,10 @@ def test_gemm_stream_k_matches_whole_tiles(ops, cuda, ta, tb, M, N, K):
     """Tile counts that fill the last wave badly are dealt out by k-blocks (stream-K): a tile cut between two CTA pairs
     is finished by one of them from the other's fp32 partial.  Same result as the whole-tile schedule, with residual,
     alpha, accumulate and the LoRA extra K block; repeated launches re-arm the flags."""
+    from csm import _lib
+    if not _lib.load().csm_gemm_experiments_compiled():
+        pytest.skip("stream-K is compiled out of the default build (no gain measured); build with "
+                    "CSM_EXTRA_NVCC_FLAGS=-DCSM_GEMM_EXPERIMENTS to test it")
     g = torch.Generator().manual_seed(M + N + K)
     def mk(r, c):
         ld = (c + 7) // 8 * 8
@@ -515,6 +519,9 @@ def test_linear_ce_single_head(ops, cuda, backend, M, V, K):
 def test_narrow_tail_mode_is_bit_identical(ops, cuda, pair, M, V, K):
     """Ragged last column tile issued with N rounded up to 16 (pair: every valid column in the leader's half): the
     plain GEMM, the fused-CE partials and dlogits must not change by a bit."""
+    from csm import _lib
+    if not _lib.load().csm_gemm_experiments_compiled():
+        pytest.skip("the narrow-tail MMAs are compiled out of the default build (-DCSM_GEMM_EXPERIMENTS enables them)")
     g = torch.Generator().manual_seed(M + V + K)
     h = torch.randn(M, K, generator=g).to(BF).to(cuda)
     w = (torch.randn(V, K, generator=g) * (2.0 / math.sqrt(K))).to(BF).to(cuda)
